@@ -1,0 +1,267 @@
+#!/usr/bin/env python
+"""bench.py — the hot path's headline metric on B200.
+
+Workload (BASELINE.json configs[1]): DC operating point of a Mos1 differential-pair amplifier
+(N = 9 unknowns, 8 devices), 8192 Monte-Carlo instances per GPU (vt0/kp per transistor, g per load resistor). One
+"step" = one batched dcop of all instances from a cold start (x = 0, fresh device state).
+
+Metric: batched Newton iterations / second = sum over instances of the iterations that reached the linear solve,
+divided by device time (CUDA events on the launch stream, max over ranks). Multi-GPU: the batch shards by instance
+(weak scaling: 8192 instances per rank, no data-path collective; NCCL only gathers iteration counts and status flags).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+`--impl reference` times the reference algorithm's CPU restatement (oracle/, C++; the Rust original cannot be built in
+this image) on the host cores for the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+B_PER_GPU = 8192
+METRIC = "batched_newton_iters_per_sec"
+UNIT = "newton_iters/s"
+WORKLOAD = "C2: Mos1 diff-pair dcop x 8192 Monte-Carlo instances per GPU (N=9, 8 devices)"
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def algorithmic_bytes_per_iteration(n, nnz_a, nnz_lu, per_inst_cols):
+    """SURVEY.md §8(d) B_iter for this circuit, real arithmetic (w = 8): 2 Mos1 + 2 R + 1 I + 3 V.
+    B_eval counts terminals gathered, per-instance parameter columns and Mos1 state (9 read + 9 written)."""
+    w = 8
+    b_eval = 2 * (48 + 8 * (9 + 9)) + 2 * 16 + 8 * per_inst_cols
+    b_asm = w * (nnz_a + n)
+    b_res = w * (nnz_a + 3 * n)
+    b_lu = 2 * w * nnz_lu
+    b_solve = w * (nnz_lu + 3 * n)
+    b_conv = w * (2 * n + 2 * n)
+    return {"eval": b_eval, "asm": b_asm, "res": b_res, "lu": b_lu, "solve": b_solve, "conv": b_conv,
+            "total": b_eval + b_asm + b_res + b_lu + b_solve + b_conv}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+def run_reference(args):
+    """The reference arm: the CPU restatement of the reference algorithm on all host cores, same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import circuits as cc
+    from oracle import pyoracle as po
+    po.build()
+    B = B_PER_GPU
+    cores = host_cores()
+    ck, ovr = cc.diffpair(), cc.diffpair_mc(B)
+    oc = po.Circuit(ck.to_text())
+    secs, iters = [], 0
+    for k in range(args.warmup + args.steps):
+        r = oc.batch(0, B, overrides=ovr, nthreads=cores, want_x=False)
+        if k >= args.warmup:
+            secs.append(r["seconds"])
+            iters = int(r["iters"].sum())
+    total = float(np.sum(secs))
+    value = iters * args.steps / total
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": WORKLOAD, "instances": B, "newton_iters_per_step": iters, "timed": "Solver::solve only (solvers pre-built)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"all {B} instances per step, {args.steps} steps; C++ restatement of the Rust reference (oracle/)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import circuits as cc
+    import spice21_b200 as s21
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if s21.cuda_device_count() < 1 or not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B = B_PER_GPU
+    ck = cc.diffpair()
+    ovr = cc.diffpair_mc(B, first_instance=rank * B)  # each rank owns its own Monte-Carlo samples
+    c = ck.to_s21().elaborate()
+    batch = s21.Batch(c, B, device=local)
+    stream = torch.cuda.current_stream()
+    batch.set_stream(stream.cuda_stream)
+    for k, v in ovr.items():
+        batch.override(k, v)
+    h2d = batch.sync_params(force_upload=True)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # > 126 MB L2
+
+    def step_device():
+        batch.reset()
+        batch.dcop_device()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    torch.cuda.synchronize()
+    x, status, iters = batch.read()
+    assert np.all(status == 0), "non-converged instances in the benchmark batch"
+    iters_per_step = int(iters.sum())
+    st = batch.stats()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.zero_()  # evict the batch from L2 between timed steps (not timed)
+        ev[k][0].record(stream)
+        batch.reset()
+        kev[k][0].record(stream)
+        batch.dcop_device()
+        kev[k][1].record(stream)
+        ev[k][1].record(stream)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    step_ms = sum(a.elapsed_time(b) for a, b in ev)
+    kern_ms = sum(a.elapsed_time(b) for a, b in kev)
+
+    # end to end through the public API with host buffers: H2D of the per-instance parameter pool from pinned memory,
+    # reset, solve, D2H of x / status / iteration counts — every step.
+    e2e_steps = max(args.steps, 5)
+    for _ in range(2):
+        batch.sync_params(force_upload=True); batch.reset(); batch.dcop()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        batch.sync_params(force_upload=True)
+        batch.reset()
+        x, status, iters = batch.dcop()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    d2h = B * c.n_vars * 8 + 3 * B * 4
+
+    tot_ms, tot_kern_ms, tot_iters, tot_e2e = step_ms, kern_ms, iters_per_step, e2e_s
+    if dist:
+        t = torch.tensor([step_ms, kern_ms, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tot_ms, tot_kern_ms, tot_e2e = t.tolist()
+        # the only collective of the path: gather per-instance iteration counts / status flags to every rank
+        it_all = [torch.empty(B, dtype=torch.int32, device="cuda") for _ in range(world)]
+        dist.all_gather(it_all, torch.from_numpy(iters).to("cuda"))
+        tot_iters = int(sum(int(v.sum().item()) for v in it_all))
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        per_inst_cols = (h2d // 8 - 0) // ((B + 31) // 32 * 32) if h2d else 0
+        bi = algorithmic_bytes_per_iteration(st["n"], st["nnz_a"], st["nnz_lu"], per_inst_cols)
+        kernel_ms_avg = tot_kern_ms / args.steps
+        achieved = bi["total"] * iters_per_step / (kernel_ms_avg * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": tot_iters * args.steps / (tot_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "instances_per_gpu": B, "newton_iters_per_step_per_gpu": iters_per_step,
+                       "n": st["n"], "nnz_a": st["nnz_a"], "nnz_lu": st["nnz_lu"], "stamp_slots": st["stamps"],
+                       "l2": "256 MiB flush write between timed steps (untimed)", "step": "reset (cold start) + batched dcop kernel"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "kernel": "s21::k_dcop", "kernel_ms": kernel_ms_avg,
+                         "algorithmic_bytes_per_iteration": bi},
+            "e2e": {"value": tot_iters * e2e_steps / tot_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * tot_e2e / e2e_steps, "steps": e2e_steps,
+                    "path": "s21_batch_sync_params(force) + s21_batch_reset + s21_batch_dcop (host buffers)"},
+            "gpu_launches": args.steps * st["launches"],
+            "clocks": sampler.summary(),
+        }
+        if world == 1:
+            line["cpu_baseline"] = cpu_baseline(ck, ovr, B)
+        print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(ck, ovr, B):
+    from oracle import pyoracle as po
+    po.build()
+    cores = host_cores()
+    oc = po.Circuit(ck.to_text())
+    oc.batch(0, B, overrides=ovr, nthreads=cores, want_x=False)  # warm-up
+    r = oc.batch(0, B, overrides=ovr, nthreads=cores, want_x=False)
+    r1 = oc.batch(0, min(B, 2048), overrides={k: v[:2048] for k, v in ovr.items()}, nthreads=1, want_x=False)
+    return {"value": float(r["iters"].sum() / r["seconds"]), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"all {B} instances, one pass, {cores} threads; Solver::solve only",
+            "single_core_value": float(r1["iters"].sum() / r1["seconds"])}
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -236,6 +236,7 @@ struct Structure {
   // after the first factorisation (first Newton iteration from x = 0):
   std::vector<int> row_i2e, col_i2e;          // pivot order
   std::vector<int> lu_row, lu_col, lu_fill;   // every element incl. fill-ins, internal coords + fill flag, creation order
+  std::vector<double> a0;                     // assembled values of the first load sweep, by element id
 };
 
 int fail(int code, const std::exception& e, char* err, int errlen) {
@@ -248,6 +249,7 @@ int classify(const std::exception& e) {
   std::string w = e.what();
   if (w == "Convergence Failed") return ST_CONV;
   if (w == "Singular Matrix") return ST_SINGULAR;
+  if (w.rfind("Assert Neq Failed", 0) == 0) return ST_SINGULAR;  // zero pivot, reported through the assert helper (mod.rs:872)
   if (w == "Pivot Search Fail") return ST_PIVOT;
   if (w.find("AC Not Implemented") != std::string::npos) return ST_UNSUPPORTED;
   if (dynamic_cast<const Panic*>(&e)) return ST_INVALID;
@@ -366,6 +368,7 @@ int orc_structure(void* ckt, const double* opts5, int n_ic, const char** ic_node
     s.rhs.assign(s.vars.len(), 0.0);
     update(s, an);
     std::vector<double> res = s.mat.res(s.vars.values, s.rhs);
+    for (auto& e : s.mat.elements) st->a0.push_back(e.val);
     try {
       s.mat.solve(res);
       for (size_t k = 0; k < s.mat.axes[ROWS].mapping.i2e.size(); k++) st->row_i2e.push_back((int)s.mat.axes[ROWS].mapping.i2e[k]);
@@ -400,7 +403,46 @@ int orc_st_vec(void* s, int which, int* out, int cap) {
   }
   return -1;
 }
+int orc_st_a0(void* s, double* out, int cap) {
+  auto* st = (Structure*)s;
+  if (out) for (size_t k = 0; k < st->a0.size() && (int)k < cap; k++) out[k] = st->a0[k];
+  return (int)st->a0.size();
+}
 void orc_st_free(void* s) { delete (Structure*)s; }
+
+// Factorise an arbitrary matrix with the restated sparse21 and report the pivot order and the L+U pattern
+// (internal coordinates, creation order). width 1 = real vals[nnz], 2 = complex vals[nnz][2].
+// Returns the status of lu_factorize (0 OK / 2 singular / 3 pivot fail); outputs sized by the caller:
+// row_i2e[n], col_i2e[n], lu_row/lu_col/lu_fill[cap]; *nnz_lu receives the element count incl. fill-ins.
+}  // extern "C"
+template <class T>
+static int lu_order_impl(int n, int nnz, const int* rows, const int* cols, const T* vals, int* row_i2e, int* col_i2e, int* lu_row,
+                         int* lu_col, int* lu_fill, int cap, int* nnz_lu) {
+  Matrix<T> m;
+  for (int k = 0; k < nnz; k++) m.add_element((size_t)rows[k], (size_t)cols[k], vals[k]);
+  int st = ST_OK;
+  try {
+    m.lu_factorize();
+  } catch (const std::exception& e) { st = classify(e); }
+  if (m.axes[ROWS].has_mapping)
+    for (int k = 0; k < n && k < (int)m.axes[ROWS].mapping.i2e.size(); k++) row_i2e[k] = (int)m.axes[ROWS].mapping.i2e[(size_t)k];
+  if (m.axes[COLS].has_mapping)
+    for (int k = 0; k < n && k < (int)m.axes[COLS].mapping.i2e.size(); k++) col_i2e[k] = (int)m.axes[COLS].mapping.i2e[(size_t)k];
+  *nnz_lu = (int)m.elements.size();
+  for (int k = 0; k < (int)m.elements.size() && k < cap; k++) {
+    lu_row[k] = (int)m.elements[(size_t)k].row; lu_col[k] = (int)m.elements[(size_t)k].col; lu_fill[k] = m.elements[(size_t)k].fillin ? 1 : 0;
+  }
+  if (st == ST_OK && (int)m.diag.size() == n && n > 0 && m.diag[(size_t)n - 1] < 0) st = ST_SINGULAR;  // surfaces in solve() (mod.rs:969-972)
+  return st;
+}
+extern "C" {
+int orc_lu_order(int n, int nnz, const int* rows, const int* cols, const double* vals, int width, int* row_i2e, int* col_i2e, int* lu_row,
+                 int* lu_col, int* lu_fill, int cap, int* nnz_lu) {
+  if (width == 1) return lu_order_impl<double>(n, nnz, rows, cols, vals, row_i2e, col_i2e, lu_row, lu_col, lu_fill, cap, nnz_lu);
+  std::vector<Cplx> z((size_t)nnz);
+  for (int k = 0; k < nnz; k++) z[(size_t)k] = Cplx(vals[2 * k], vals[2 * k + 1]);
+  return lu_order_impl<Cplx>(n, nnz, rows, cols, z.data(), row_i2e, col_i2e, lu_row, lu_col, lu_fill, cap, nnz_lu);
+}
 
 // Batched runs for the CPU baseline: B independent instances of one circuit with per-instance overrides.
 // kind 0 = dcop, 1 = tran. Solvers are built first (untimed); then `nthreads` std::threads pull instances off an

@@ -162,6 +162,12 @@ class Circuit:
             v = np.zeros(max(n, 1), dtype=np.int32)
             L.orc_st_vec(out, which, v.ctypes.data_as(C.c_void_p), n)
             st[key] = v[:n]
+        L.orc_st_a0.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_st_a0.restype = C.c_int
+        n = L.orc_st_a0(out, None, 0)
+        a0 = np.zeros(max(n, 1))
+        L.orc_st_a0(out, a0.ctypes.data_as(C.c_void_p), n)
+        st["a0"] = a0[:n]
         L.orc_st_free(out)
         return st
 
@@ -206,6 +212,25 @@ class Circuit:
         self._check(stt, err)
         return {"x": x[:, 0, :] if (want_x and kind == 0) else x, "iters": iters, "status": status, "seconds": secs.value,
                 "n_vars": nv.value, "n_pts": npt.value, "names": st["names"]}
+
+
+def lu_order(n, rows, cols, vals):
+    """Pivot order + L+U pattern the restated sparse21 produces for an arbitrary matrix (real or complex vals)."""
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    cols = np.ascontiguousarray(cols, dtype=np.int32)
+    vals = np.asarray(vals)
+    width = 2 if np.iscomplexobj(vals) else 1
+    v = np.ascontiguousarray(vals, dtype=np.complex128 if width == 2 else np.float64)
+    cap = n * n + len(rows) + 8
+    row_i2e, col_i2e = np.arange(n, dtype=np.int32), np.arange(n, dtype=np.int32)
+    lr, lc, lf = (np.zeros(cap, dtype=np.int32) for _ in range(3))
+    nnz = C.c_int()
+    f = lib().orc_lu_order
+    f.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.POINTER(C.c_int)]
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    st = f(n, len(rows), p(rows), p(cols), p(v), width, p(row_i2e), p(col_i2e), p(lr), p(lc), p(lf), cap, C.byref(nnz))
+    k = nnz.value
+    return {"status": st, "row_i2e": row_i2e, "col_i2e": col_i2e, "lu_row": lr[:k], "lu_col": lc[:k], "lu_fill": lf[:k]}
 
 
 def sparse21_selftest():

@@ -487,7 +487,7 @@ struct Matrix {  // mod.rs:220-228
     if (de < 0) throw SpError("Singular Matrix");
     if (de != pivot) throw SpError("Assertion Failed");
     T pivot_val = el(pivot).val;
-    if (pivot_val == zero<T>()) throw SpError("Assertion Failed");
+    if (pivot_val == zero<T>()) throw SpError("Assert Neq Failed: zero pivot");  // assert(pivot_val).ne(T::zero())? (assert.rs:38-44)
     int plower = el(pivot).next_in_col;
     while (plower >= 0) {
       el(plower).val = el(plower).val / pivot_val;

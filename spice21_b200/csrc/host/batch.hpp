@@ -1,0 +1,533 @@
+// Batch runtime: owns the device tables, the per-instance workspace in HBM, the LU plans and the CUDA stream of one
+// batch of circuit instances, and drives the kernels of kernels/newton.cu. Host work here is setup only (tables,
+// the once-per-mode symbolic phase, per-instance parameter derivation); the Newton loop itself never returns to the
+// host. There is no CPU path: every solve needs a CUDA device.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <thread>
+
+#include "../kernels/engine.hpp"
+#include "flatten.hpp"
+#include "symbolic.hpp"
+
+namespace s21 {
+
+inline void cuda_check(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) throw S21Error(ST_CUDA, std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e));
+}
+#define S21_CUDA(x) ::s21::cuda_check((x), #x)
+
+template <class T>
+struct DBuf {  // device buffer
+  T* p = nullptr;
+  size_t n = 0;
+  DBuf() {}
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  ~DBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void alloc(size_t count) {
+    if (count <= n && p) return;
+    release();
+    S21_CUDA(cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T)));
+    n = count;
+  }
+  void upload(const std::vector<T>& h, cudaStream_t s) {
+    alloc(h.size());
+    if (!h.empty()) S21_CUDA(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+};
+template <class T>
+struct PinnedBuf {  // page-locked host buffer
+  T* p = nullptr;
+  size_t n = 0;
+  PinnedBuf() {}
+  PinnedBuf(const PinnedBuf&) = delete;
+  PinnedBuf& operator=(const PinnedBuf&) = delete;
+  ~PinnedBuf() { if (p) cudaFreeHost(p); }
+  void alloc(size_t count) {
+    if (count <= n && p) return;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    S21_CUDA(cudaMallocHost((void**)&p, std::max<size_t>(count, 1) * sizeof(T)));
+    n = count;
+  }
+};
+
+struct PlanDevice {
+  Plan host;
+  bool valid = false;
+  DBuf<int> row_i2e, col_i2e, col_e2i, rowptr, colidx, diag_slot, l_off, l_slot, l_row, upd_off, upd_t, upd_u, upd_l, itab;
+  PlanTables tables() const {
+    PlanTables t;
+    t.N = host.N; t.nnz = host.nnzLU;
+    t.row_i2e = row_i2e.p; t.col_i2e = col_i2e.p; t.col_e2i = col_e2i.p;
+    t.rowptr = rowptr.p; t.colidx = colidx.p; t.diag_slot = diag_slot.p;
+    t.l_off = l_off.p; t.l_slot = l_slot.p; t.l_row = l_row.p;
+    t.upd_off = upd_off.p; t.upd_t = upd_t.p; t.upd_u = upd_u.p; t.upd_l = upd_l.p;
+    return t;
+  }
+};
+
+struct Override {
+  std::string kind, name, param;
+  std::vector<double> values;  // [B]
+};
+
+class Batch {
+ public:
+  Batch(const CktSpec& spec, const FlatCkt& flat, int device, size_t B) : spec_(spec), flat_(flat), device_(device), B_(B) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+      throw S21Error(ST_CUDA, "no CUDA device available: libspice21cu has no CPU fallback (" + std::string(cudaGetErrorString(e)) + ")");
+    if (device < 0 || device >= count) throw S21Error(ST_CUDA, "invalid CUDA device index");
+    if (B == 0) throw S21Error(ST_OTHER, "batch size must be positive");
+    S21_CUDA(cudaSetDevice(device_));
+    S21_CUDA(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
+    stream_ = own_stream_;
+    S21_CUDA(cudaEventCreate(&ev0_));
+    S21_CUDA(cudaEventCreate(&ev1_));
+    Bs_ = (B_ + 31) / 32 * 32;
+    const int N = flat_.n_vars();
+    // shared device tables
+    std::vector<int> type, ioff, poff, soff;
+    for (const FlatDev& d : flat_.devs) { type.push_back(d.type); ioff.push_back(d.itab_off); poff.push_back(d.par_off); soff.push_back(d.state_off); }
+    d_type_.upload(type, stream_); d_ioff_.upload(ioff, stream_); d_poff_.upload(poff, stream_); d_soff_.upload(soff, stream_);
+    d_itab_raw_.upload(flat_.itab, stream_);
+    // workspace
+    x_.alloc((size_t)N * Bs_); rhs_.alloc((size_t)N * Bs_); c_.alloc((size_t)N * Bs_);
+    st_op_.alloc((size_t)std::max(flat_.n_state, 1) * Bs_); st_guess_.alloc((size_t)std::max(flat_.n_state, 1) * Bs_);
+    status_.alloc(Bs_); iters_.alloc(Bs_); loads_.alloc(Bs_);
+    ensure_lu_rows((size_t)flat_.n_elems());
+    params_dirty_ = true;
+    reset();
+  }
+  ~Batch() {
+    cudaSetDevice(device_);
+    cudaStreamSynchronize(stream_);
+    if (ev0_) cudaEventDestroy(ev0_);
+    if (ev1_) cudaEventDestroy(ev1_);
+    if (own_stream_) cudaStreamDestroy(own_stream_);
+  }
+  size_t B() const { return B_; }
+  int N() const { return flat_.n_vars(); }
+  void set_stream(void* s) { stream_ = s ? (cudaStream_t)s : own_stream_; }
+
+  void add_override(const std::string& spec, const double* values) {
+    Override o;
+    size_t a = spec.find(':'), b = a == std::string::npos ? a : spec.find(':', a + 1);
+    if (a == std::string::npos || b == std::string::npos) throw S21Error(ST_OTHER, "bad override spec: " + spec);
+    o.kind = spec.substr(0, a); o.name = spec.substr(a + 1, b - a - 1); o.param = spec.substr(b + 1);
+    o.values.assign(values, values + B_);
+    for (Override& x : overrides_)
+      if (x.kind == o.kind && x.name == o.name && x.param == o.param) { x.values = o.values; params_dirty_ = true; rebuild_ = true; return; }
+    overrides_.push_back(o);
+    params_dirty_ = true;
+    rebuild_ = true;
+  }
+
+  void reset() {  // a fresh Solver: x = 0, op = guess = Default (all zeros)
+    S21_CUDA(cudaSetDevice(device_));
+    S21_CUDA(cudaMemsetAsync(x_.p, 0, x_.n * sizeof(double), stream_));
+    S21_CUDA(cudaMemsetAsync(st_op_.p, 0, st_op_.n * sizeof(double), stream_));
+    S21_CUDA(cudaMemsetAsync(st_guess_.p, 0, st_guess_.n * sizeof(double), stream_));
+    S21_CUDA(cudaMemsetAsync(status_.p, 0, status_.n * sizeof(int32_t), stream_));
+    S21_CUDA(cudaMemsetAsync(iters_.p, 0, iters_.n * sizeof(int32_t), stream_));
+    S21_CUDA(cudaMemsetAsync(loads_.p, 0, loads_.n * sizeof(int32_t), stream_));
+  }
+
+  // (Re)build the parameter pool on the host (derivations per instance where overridden) and upload it.
+  void sync_params(bool force_upload) {
+    S21_CUDA(cudaSetDevice(device_));
+    if (rebuild_ || pcode_h_.empty()) { rebuild_param_pool(); rebuild_ = false; params_dirty_ = true; }
+    if (params_dirty_ || force_upload) {
+      d_pcode_.upload(pcode_h_, stream_);
+      d_pval_.alloc(pval_n_);
+      S21_CUDA(cudaMemcpyAsync(d_pval_.p, pval_h_.p, pval_n_ * sizeof(double), cudaMemcpyHostToDevice, stream_));
+      params_dirty_ = false;
+      h2d_bytes_ = pval_n_ * sizeof(double) + pcode_h_.size() * sizeof(int);
+    }
+  }
+  size_t last_h2d_bytes() const { return h2d_bytes_; }
+
+  // ---- dcop -----------------------------------------------------------------------------------------------
+  void dcop_device() {
+    S21_CUDA(cudaSetDevice(device_));
+    sync_params(false);
+    launches_ = 0;
+    ensure_plan(op_plan_, AN_OP, 0.0);
+    S21_CUDA(cudaEventRecord(ev0_, stream_));
+    run_op();
+    S21_CUDA(cudaEventRecord(ev1_, stream_));
+    last_plan_ = &op_plan_;
+  }
+  void read(double* x, int32_t* status, int32_t* iters) {
+    S21_CUDA(cudaSetDevice(device_));
+    const int N = flat_.n_vars();
+    if (x) {
+      hx_.alloc((size_t)N * Bs_);
+      S21_CUDA(cudaMemcpyAsync(hx_.p, x_.p, (size_t)N * Bs_ * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    }
+    hstatus_.alloc(Bs_); hiters_.alloc(Bs_); hloads_.alloc(Bs_);
+    S21_CUDA(cudaMemcpyAsync(hstatus_.p, status_.p, Bs_ * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+    S21_CUDA(cudaMemcpyAsync(hiters_.p, iters_.p, Bs_ * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+    S21_CUDA(cudaMemcpyAsync(hloads_.p, loads_.p, Bs_ * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+    S21_CUDA(cudaStreamSynchronize(stream_));
+    if (x)
+      for (size_t i = 0; i < B_; i++)
+        for (int k = 0; k < N; k++) x[i * (size_t)N + (size_t)k] = hx_.p[(size_t)k * Bs_ + i];
+    sum_iters_ = 0; sum_loads_ = 0;
+    for (size_t i = 0; i < B_; i++) {
+      if (status) status[i] = hstatus_.p[i];
+      if (iters) iters[i] = hiters_.p[i];
+      sum_iters_ += hiters_.p[i];
+      sum_loads_ += hloads_.p[i];
+    }
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev0_, ev1_) == cudaSuccess) last_ms_ = ms;
+  }
+
+  // ---- tran -----------------------------------------------------------------------------------------------
+  void tran(double tstep, int T, const int32_t* save_vars, size_t n_save, double* wave, int32_t* status, int64_t* iters) {
+    S21_CUDA(cudaSetDevice(device_));
+    sync_params(false);
+    launches_ = 0;
+    ensure_plan(op_plan_, AN_OP, 0.0);
+    S21_CUDA(cudaEventRecord(ev0_, stream_));
+    run_op();
+    // The matrix changes character after the OP (capacitor companions appear, IC resistors are released):
+    // take the pivot order again from the first transient iteration.
+    tran_plan_.valid = false;
+    ensure_plan(tran_plan_, AN_TRAN, tstep);
+    std::vector<int> sv(save_vars, save_vars + n_save);
+    d_save_.upload(sv, stream_);
+    d_wave_.alloc((size_t)T * n_save * Bs_);
+    DevTables dt = dev_tables(tran_plan_.itab.p);
+    SolveCtl ctl = make_ctl(AN_TRAN, tstep);
+    int rc = launch_tran(dt, tran_plan_.tables(), work(), out(), ctl, T, d_save_.p, (int)n_save, d_wave_.p, stream_);
+    launches_++;
+    if (rc) throw S21Error(ST_CUDA, std::string("k_tran launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+    S21_CUDA(cudaEventRecord(ev1_, stream_));
+    last_plan_ = &tran_plan_;
+    if (wave) {
+      hwave_.alloc((size_t)T * n_save * Bs_);
+      S21_CUDA(cudaMemcpyAsync(hwave_.p, d_wave_.p, (size_t)T * n_save * Bs_ * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    }
+    std::vector<int32_t> it32(B_);
+    read(nullptr, status, it32.data());
+    if (iters) for (size_t i = 0; i < B_; i++) iters[i] = it32[i];
+    if (wave)
+      for (size_t i = 0; i < B_; i++)
+        for (int t = 0; t < T; t++)
+          for (size_t s = 0; s < n_save; s++) wave[(i * (size_t)T + (size_t)t) * n_save + s] = hwave_.p[((size_t)t * n_save + s) * Bs_ + i];
+  }
+
+  // ---- ac: frequency points are the batch axis of circuit instance 0 ------------------------------------------
+  void ac(const double* freqs, size_t F, double* x_out, int32_t* status, int32_t* iters) {
+    S21_CUDA(cudaSetDevice(device_));
+    for (const FlatDev& d : flat_.devs)
+      if (d.type != DT_R && d.type != DT_C && d.type != DT_V && d.type != DT_MOS1)
+        throw S21Error(ST_UNSUPPORTED, "AC Not Implemented For This Component!");  // comps/mod.rs:86-88
+    sync_params(false);
+    launches_ = 0;
+    ensure_plan(op_plan_, AN_OP, 0.0);
+    S21_CUDA(cudaEventRecord(ev0_, stream_));
+    run_op();
+    {  // the reference stops at the OP error (analysis.rs:775)
+      int32_t st0 = 0;
+      S21_CUDA(cudaMemcpyAsync(&st0, status_.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+      S21_CUDA(cudaStreamSynchronize(stream_));
+      if (st0 != ST_OK) throw S21Error(st0, status_text(st0));
+    }
+    const size_t Fs = (F + 31) / 32 * 32;
+    const int N = flat_.n_vars();
+    const double PI = 3.14159265358979323846264338327950288;
+    std::vector<double> om(Fs, 0.0);
+    for (size_t k = 0; k < F; k++) om[k] = 2.0 * PI * freqs[k];  // analysis.rs:799
+    d_omega_.upload(om, stream_);
+    ac_status_.alloc(Fs); ac_iters_.alloc(Fs); ac_loads_.alloc(Fs);
+    S21_CUDA(cudaMemsetAsync(ac_status_.p, 0, Fs * sizeof(int32_t), stream_));
+    S21_CUDA(cudaMemsetAsync(ac_iters_.p, 0, Fs * sizeof(int32_t), stream_));
+    S21_CUDA(cudaMemsetAsync(ac_loads_.p, 0, Fs * sizeof(int32_t), stream_));
+    zx_.alloc((size_t)N * Fs); zrhs_.alloc((size_t)N * Fs); zc_.alloc((size_t)N * Fs);
+    S21_CUDA(cudaMemsetAsync(zx_.p, 0, zx_.n * sizeof(cplx), stream_));  // Variables::from zeroes the values (analysis.rs:59-65)
+    zlu_.alloc((size_t)flat_.n_elems() * Fs);
+    WorkTables<cplx> w;
+    w.x = zx_.p; w.rhs = zrhs_.p; w.c = zc_.p; w.lu = zlu_.p; w.stride = Fs;
+    w.st_op = st_op_.p; w.st_guess = st_guess_.p; w.st_stride = Bs_;
+    SolveCtl ctl = make_ctl(AN_AC, 0.0);
+    ctl.B = (int)F; ctl.omega = d_omega_.p; ctl.par_inst_stride = 0;
+    // symbolic phase on the first frequency point
+    {
+      DevTables dt = dev_tables(d_itab_raw_.p);
+      DBuf<cplx> probe;
+      probe.alloc((size_t)flat_.n_elems());
+      int rc = launch_probe_cplx(dt, w, ctl, flat_.n_elems(), N, 0, probe.p, stream_);
+      launches_++;
+      if (rc) throw S21Error(ST_CUDA, "k_probe launch failed");
+      std::vector<cplx> vals((size_t)flat_.n_elems());
+      S21_CUDA(cudaMemcpyAsync(vals.data(), probe.p, vals.size() * sizeof(cplx), cudaMemcpyDeviceToHost, stream_));
+      S21_CUDA(cudaStreamSynchronize(stream_));
+      ac_plan_.host = build_plan<cplx>(N, flat_.elem_row, flat_.elem_col, vals.data());
+      upload_plan(ac_plan_);
+    }
+    if (ac_plan_.host.status != ST_OK) throw S21Error(ac_plan_.host.status, status_text(ac_plan_.host.status));
+    if ((size_t)ac_plan_.host.nnzLU > (size_t)flat_.n_elems()) { zlu_.alloc((size_t)ac_plan_.host.nnzLU * Fs); w.lu = zlu_.p; }
+    NewtonOut o;
+    o.status = ac_status_.p; o.iters = ac_iters_.p; o.loads = ac_loads_.p;
+    DevTables dt = dev_tables(ac_plan_.itab.p);
+    int rc = launch_ac(dt, ac_plan_.tables(), w, o, ctl, stream_);
+    launches_++;
+    if (rc) throw S21Error(ST_CUDA, "k_ac launch failed");
+    S21_CUDA(cudaEventRecord(ev1_, stream_));
+    last_plan_ = &ac_plan_;
+    std::vector<cplx> hx((size_t)N * Fs);
+    std::vector<int32_t> hs(Fs), hi(Fs), hl(Fs);
+    S21_CUDA(cudaMemcpyAsync(hx.data(), zx_.p, hx.size() * sizeof(cplx), cudaMemcpyDeviceToHost, stream_));
+    S21_CUDA(cudaMemcpyAsync(hs.data(), ac_status_.p, Fs * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+    S21_CUDA(cudaMemcpyAsync(hi.data(), ac_iters_.p, Fs * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+    S21_CUDA(cudaMemcpyAsync(hl.data(), ac_loads_.p, Fs * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+    S21_CUDA(cudaStreamSynchronize(stream_));
+    sum_iters_ = 0; sum_loads_ = 0;
+    for (size_t f = 0; f < F; f++) {
+      if (status) status[f] = hs[f];
+      if (iters) iters[f] = hi[f];
+      sum_iters_ += hi[f]; sum_loads_ += hl[f];
+      if (x_out)
+        for (int k = 0; k < N; k++) {
+          x_out[(f * (size_t)N + (size_t)k) * 2 + 0] = hx[(size_t)k * Fs + f].re;
+          x_out[(f * (size_t)N + (size_t)k) * 2 + 1] = hx[(size_t)k * Fs + f].im;
+        }
+    }
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev0_, ev1_) == cudaSuccess) last_ms_ = ms;
+  }
+
+  const Plan* last_plan() const { return last_plan_ ? &last_plan_->host : nullptr; }
+  void stats(double* out8) const {
+    out8[0] = launches_; out8[1] = last_ms_; out8[2] = (double)sum_iters_; out8[3] = (double)sum_loads_;
+    out8[4] = flat_.n_elems(); out8[5] = last_plan_ ? last_plan_->host.nnzLU : 0; out8[6] = flat_.n_vars(); out8[7] = flat_.n_stamps;
+  }
+  static const char* status_text(int st) {
+    switch (st) {
+      case ST_CONV: return "Convergence Failed";
+      case ST_SINGULAR: return "Singular Matrix";
+      case ST_PIVOT: return "Pivot Search Fail";
+      case ST_UNSUPPORTED: return "AC Not Implemented For This Component!";
+      default: return "Error";
+    }
+  }
+
+ private:
+  CktSpec spec_;
+  FlatCkt flat_;
+  int device_;
+  size_t B_, Bs_ = 0;
+  cudaStream_t own_stream_ = nullptr, stream_ = nullptr;
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+  DBuf<int> d_type_, d_ioff_, d_poff_, d_soff_, d_itab_raw_, d_pcode_, d_save_;
+  DBuf<double> d_pval_, x_, rhs_, c_, lu_, st_op_, st_guess_, d_wave_, d_omega_;
+  DBuf<cplx> zx_, zrhs_, zc_, zlu_;
+  DBuf<int32_t> status_, iters_, loads_, ac_status_, ac_iters_, ac_loads_;
+  PinnedBuf<double> pval_h_, hx_, hwave_;
+  PinnedBuf<int32_t> hstatus_, hiters_, hloads_;
+  std::vector<int> pcode_h_;
+  size_t pval_n_ = 0, h2d_bytes_ = 0;
+  std::vector<Override> overrides_;
+  bool params_dirty_ = true, rebuild_ = true;
+  PlanDevice op_plan_, tran_plan_, ac_plan_;
+  const PlanDevice* last_plan_ = nullptr;
+  size_t lu_rows_ = 0;
+  int launches_ = 0;
+  float last_ms_ = 0.f;
+  long long sum_iters_ = 0, sum_loads_ = 0;
+
+  void ensure_lu_rows(size_t rows) {
+    if (rows <= lu_rows_) return;
+    lu_.alloc(rows * Bs_);
+    lu_rows_ = rows;
+  }
+  DevTables dev_tables(const int* itab) const {
+    DevTables d;
+    d.n_dev = (int)flat_.devs.size();
+    d.type = d_type_.p; d.itab_off = d_ioff_.p; d.par_off = d_poff_.p; d.state_off = d_soff_.p;
+    d.itab = itab; d.pcode = d_pcode_.p; d.pval = d_pval_.p; d.n_state = flat_.n_state;
+    return d;
+  }
+  WorkTables<double> work() const {
+    WorkTables<double> w;
+    w.x = x_.p; w.rhs = rhs_.p; w.c = c_.p; w.lu = lu_.p; w.stride = Bs_;
+    w.st_op = st_op_.p; w.st_guess = st_guess_.p; w.st_stride = Bs_;
+    return w;
+  }
+  NewtonOut out() const {
+    NewtonOut o;
+    o.status = status_.p; o.iters = iters_.p; o.loads = loads_.p;
+    return o;
+  }
+  SolveCtl make_ctl(int mode, double dt) const {
+    SolveCtl c;
+    c.B = (int)B_; c.mode = mode; c.gmin = flat_.opts.gmin; c.dt = dt;
+    c.reltol = flat_.opts.reltol; c.iabstol = flat_.opts.iabstol; c.omega = nullptr; c.par_inst_stride = 1;
+    return c;
+  }
+  void run_op() {
+    if (op_plan_.host.status != ST_OK) {  // the reference fails in its first factorisation: every instance reports it
+      std::vector<int32_t> st(Bs_, op_plan_.host.status);
+      S21_CUDA(cudaMemcpyAsync(status_.p, st.data(), Bs_ * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
+      S21_CUDA(cudaStreamSynchronize(stream_));
+      return;
+    }
+    DevTables dt = dev_tables(op_plan_.itab.p);
+    int rc = launch_dcop(dt, op_plan_.tables(), work(), out(), make_ctl(AN_OP, 0.0), stream_);
+    launches_++;
+    if (rc) throw S21Error(ST_CUDA, std::string("k_dcop launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+  }
+  // Symbolic phase for one analysis mode: probe instance 0's first load sweep on the GPU, pivot on the host.
+  void ensure_plan(PlanDevice& pd, int mode, double dt) {
+    if (pd.valid) return;
+    const int N = flat_.n_vars();
+    DevTables dtab = dev_tables(d_itab_raw_.p);
+    DBuf<double> probe;
+    probe.alloc((size_t)flat_.n_elems());
+    int rc = launch_probe_real(dtab, work(), make_ctl(mode, dt), flat_.n_elems(), N, 0, probe.p, stream_);
+    launches_++;
+    if (rc) throw S21Error(ST_CUDA, std::string("k_probe launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+    std::vector<double> vals((size_t)flat_.n_elems());
+    S21_CUDA(cudaMemcpyAsync(vals.data(), probe.p, vals.size() * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    S21_CUDA(cudaStreamSynchronize(stream_));
+    pd.host = build_plan<double>(N, flat_.elem_row, flat_.elem_col, vals.data());
+    upload_plan(pd);
+    ensure_lu_rows((size_t)pd.host.nnzLU);
+  }
+  void upload_plan(PlanDevice& pd) {
+    const Plan& P = pd.host;
+    pd.row_i2e.upload(P.row_i2e, stream_); pd.col_i2e.upload(P.col_i2e, stream_); pd.col_e2i.upload(P.col_e2i, stream_);
+    pd.rowptr.upload(P.rowptr, stream_); pd.colidx.upload(P.colidx, stream_); pd.diag_slot.upload(P.diag_slot, stream_);
+    pd.l_off.upload(P.l_off, stream_); pd.l_slot.upload(P.l_slot, stream_); pd.l_row.upload(P.l_row, stream_);
+    pd.upd_off.upload(P.upd_off, stream_); pd.upd_t.upload(P.upd_t, stream_); pd.upd_u.upload(P.upd_u, stream_); pd.upd_l.upload(P.upd_l, stream_);
+    // element handles -> L+U slots
+    std::vector<int> itab = flat_.itab;
+    for (const FlatDev& d : flat_.devs) {
+      int first_elem = 0;
+      switch (d.type) {
+        case DT_R: case DT_C: first_elem = R_EPP; break;
+        case DT_I: first_elem = I_NI; break;
+        case DT_V: first_elem = V_EPI; break;
+        case DT_DIODE: first_elem = D_EPP; break;
+        case DT_MOS0: first_elem = M0_EDD; break;
+        case DT_MOS1: first_elem = M1_E0; break;
+        default: first_elem = d.n_itab;
+      }
+      for (int k = first_elem; k < d.n_itab; k++) {
+        int& h = itab[(size_t)d.itab_off + (size_t)k];
+        if (h >= 0) h = P.elem_slot[(size_t)h];
+      }
+    }
+    pd.itab.upload(itab, stream_);
+    S21_CUDA(cudaStreamSynchronize(stream_));  // host vectors above are temporaries
+    pd.valid = true;
+  }
+
+  // Parameter pool: shared values first (one per (device, param)), then one B-column per parameter that varies.
+  void rebuild_param_pool() {
+    const size_t n_shared = flat_.par.size();
+    std::vector<double> shared = flat_.par;
+    pcode_h_.assign(n_shared, 0);
+    for (size_t j = 0; j < n_shared; j++) pcode_h_[j] = (int)(j << 1);
+    std::vector<std::vector<double>> columns;  // each [B]
+    std::vector<size_t> column_target;         // index into the shared table
+    auto set_column = [&](size_t j, const std::vector<double>& col) {
+      bool same = true;
+      for (size_t i = 1; i < B_ && same; i++) same = col[i] == col[0];
+      if (same) { shared[j] = col[0]; return; }
+      columns.push_back(col);
+      column_target.push_back(j);
+    };
+    if (!overrides_.empty()) {
+      for (const FlatDev& d : flat_.devs) {
+        if (d.is_ic) continue;
+        std::vector<const Override*> mine;
+        for (const Override& o : overrides_) {
+          bool hit = false;
+          if (o.kind == "opt") hit = (d.type == DT_MOS1 || d.type == DT_DIODE) && o.param == "temp";
+          else if (o.kind == "mos1model") hit = d.type == DT_MOS1 && d.model == o.name;
+          else if (o.kind == "mos1inst") hit = d.type == DT_MOS1 && d.params == o.name;
+          else if (o.kind == "diodemodel") hit = d.type == DT_DIODE && d.model == o.name;
+          else if (o.kind == "diodeinst") hit = d.type == DT_DIODE && d.params == o.name;
+          else if (o.kind == "R") hit = d.type == DT_R && d.path == o.name;
+          else if (o.kind == "C") hit = d.type == DT_C && d.path == o.name;
+          else if (o.kind == "I") hit = d.type == DT_I && d.path == o.name;
+          else if (o.kind == "V") hit = d.type == DT_V && d.path == o.name;
+          else throw S21Error(ST_OTHER, "unknown override kind: " + o.kind);
+          if (hit) mine.push_back(&o);
+        }
+        if (mine.empty()) continue;
+        const size_t base = (size_t)d.par_off;
+        if (d.type == DT_R || d.type == DT_C || d.type == DT_I || d.type == DT_V) {
+          for (const Override* o : mine) {
+            if (d.type == DT_R) { set_column(base + RP_G_OP, o->values); set_column(base + RP_G_TRAN, o->values); }
+            else if (d.type == DT_C) set_column(base + CP_C, o->values);
+            else if (d.type == DT_I) set_column(base + IP_I, o->values);
+            else if (o->param == "acm") set_column(base + VP_ACM, o->values);
+            else { set_column(base + VP_V_OP, o->values); set_column(base + VP_V_TRAN, o->values); }
+          }
+          continue;
+        }
+        // Mos1 / Diode: re-run the reference derivation per instance
+        const int np = d.n_par;
+        std::vector<std::vector<double>> cols((size_t)np, std::vector<double>(B_));
+        unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        size_t nt = std::min<size_t>(hw, std::max<size_t>(1, B_ / 256));
+        std::vector<std::thread> th;
+        std::vector<std::string> errs(nt);
+        for (size_t t = 0; t < nt; t++)
+          th.emplace_back([&, t]() {
+            try {
+              MosModelSpec mm;
+              ParamBag mbag, ibag;
+              if (d.type == DT_MOS1) { mm = spec_.mos1_models.at(d.model); ibag = spec_.mos1_insts.at(d.params); }
+              else { mbag = spec_.diode_models.at(d.model); ibag = spec_.diode_insts.at(d.params); }
+              for (size_t i = t; i < B_; i += nt) {
+                SimOptions o = flat_.opts;
+                for (const Override* ov : mine) {
+                  const double v = ov->values[i];
+                  if (ov->kind == "opt") o.temp = v;
+                  else if (ov->kind == "mos1model") mm.p.kv[ov->param] = v;
+                  else if (ov->kind == "diodemodel") mbag.kv[ov->param] = v;
+                  else ibag.kv[ov->param] = v;
+                }
+                if (d.type == DT_MOS1) {
+                  Mos1Derived r = mos1_derive(mm, ibag, o);
+                  for (int k = 0; k < np; k++) cols[(size_t)k][i] = r.par[k];
+                } else {
+                  DiodeDerived r = diode_derive(mbag, ibag, o);
+                  for (int k = 0; k < np; k++) cols[(size_t)k][i] = r.par[k];
+                }
+              }
+            } catch (const std::exception& e) { errs[t] = e.what(); }
+          });
+        for (auto& x : th) x.join();
+        for (auto& e : errs) if (!e.empty()) throw S21Error(ST_INVALID, e);
+        for (int k = 0; k < np; k++) set_column(base + (size_t)k, cols[(size_t)k]);
+      }
+    }
+    pval_n_ = n_shared + columns.size() * Bs_;
+    pval_h_.alloc(pval_n_);
+    std::memcpy(pval_h_.p, shared.data(), n_shared * sizeof(double));
+    for (size_t c = 0; c < columns.size(); c++) {
+      double* dst = pval_h_.p + n_shared + c * Bs_;
+      std::memcpy(dst, columns[c].data(), B_ * sizeof(double));
+      for (size_t i = B_; i < Bs_; i++) dst[i] = columns[c][0];
+      pcode_h_[column_target[c]] = (int)(((n_shared + c * Bs_) << 1) | 1);
+    }
+    // a parameter change invalidates the frozen pivot orders
+    op_plan_.valid = false; tran_plan_.valid = false;
+  }
+};
+
+}  // namespace s21

@@ -1,0 +1,261 @@
+// Symbolic phase of the sparse LU, run ONCE per analysis mode on the host with the values of the first Newton
+// iteration. It reproduces the reference solver's decisions exactly —
+//   spice21/src/sparse21/mod.rs:647-674  lu_factorize (N-1 pivot steps; singular checks)
+//   spice21/src/sparse21/mod.rs:735-783  markowitz_search_diagonal (rel. threshold 1e-3, ties_mult 5, early exit)
+//   spice21/src/sparse21/mod.rs:785-834  markowitz_search_submatrix (as written: only column n is examined)
+//   spice21/src/sparse21/mod.rs:837-863  find_max
+//   spice21/src/sparse21/mod.rs:865-919  row_col_elim (fill-in creation, Markowitz count maintenance)
+// — but works on permutation vectors over externally-indexed rows/columns instead of physically swapping
+// orthogonal linked lists. "First in list order" tie-breaks of the reference become "smallest current internal
+// index". The product is a static plan: pivot order, L+U pattern with fill, and flat op lists for the numeric
+// kernels (refactorisation, forward/back substitution, residual SpMV), all in final internal coordinates.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <unordered_map>
+#include <vector>
+
+#include "../scalar.h"
+#include "circuit.hpp"
+
+namespace s21 {
+
+struct Plan {
+  int status = ST_OK;  // ST_SINGULAR / ST_PIVOT when the reference would have returned that SpError on this matrix
+  int N = 0, nnzA = 0, nnzLU = 0;
+  std::vector<int> row_i2e, row_e2i, col_i2e, col_e2i;
+  // L+U pattern: CSR over internal rows, ascending internal column. Slot = position in this order.
+  std::vector<int> rowptr, colidx, diag_slot;
+  std::vector<int> lu_row, lu_col, lu_fill;  // per slot (export / tests)
+  std::vector<int> elem_slot;                // original element id -> slot
+  // Numeric refactorisation, pivot k = 0..N-2: L_k = slots below the diagonal in column k (with their rows),
+  // and one (target, u, l) triple per Schur update. Offsets have N entries + 1.
+  std::vector<int> l_off, l_slot, l_row;
+  std::vector<int> upd_off, upd_t, upd_u, upd_l;
+};
+
+namespace detail {
+template <class T>
+struct SymEntry {
+  int r, c;  // external coordinates
+  T val;
+  bool fill;
+};
+inline uint64_t rc_key(int r, int c) { return ((uint64_t)(uint32_t)r << 32) | (uint32_t)c; }
+}  // namespace detail
+
+// vals[e] = assembled value of element e after the first device-load sweep.
+template <class T>
+Plan build_plan(int N, const std::vector<int>& elem_row, const std::vector<int>& elem_col, const T* vals) {
+  using detail::SymEntry;
+  using detail::rc_key;
+  Plan P;
+  P.N = N;
+  P.nnzA = (int)elem_row.size();
+  std::vector<SymEntry<T>> E;
+  E.reserve(elem_row.size() * 2);
+  std::vector<std::vector<int>> in_row((size_t)N), in_col((size_t)N);
+  std::unordered_map<uint64_t, int> at;
+  at.reserve(elem_row.size() * 2);
+  for (size_t e = 0; e < elem_row.size(); e++) {
+    E.push_back({elem_row[e], elem_col[e], vals[e], false});
+    in_row[(size_t)elem_row[e]].push_back((int)e);
+    in_col[(size_t)elem_col[e]].push_back((int)e);
+    at.emplace(rc_key(elem_row[e], elem_col[e]), (int)e);
+  }
+  P.row_i2e.resize((size_t)N); P.row_e2i.resize((size_t)N); P.col_i2e.resize((size_t)N); P.col_e2i.resize((size_t)N);
+  for (int k = 0; k < N; k++) P.row_i2e[(size_t)k] = P.row_e2i[(size_t)k] = P.col_i2e[(size_t)k] = P.col_e2i[(size_t)k] = k;
+  auto lookup = [&](int r, int c) { auto it = at.find(rc_key(r, c)); return it == at.end() ? -1 : it->second; };
+
+  // mod.rs:649-658 — an empty row or column is "Singular Matrix"
+  for (int k = 0; k < N; k++)
+    if (in_row[(size_t)k].empty() || in_col[(size_t)k].empty()) { P.status = ST_SINGULAR; }
+  std::vector<long> mrow((size_t)N), mcol((size_t)N);  // Markowitz counts, keyed by external row / column
+  for (int k = 0; k < N; k++) { mrow[(size_t)k] = (long)in_row[(size_t)k].size(); mcol[(size_t)k] = (long)in_col[(size_t)k].size(); }
+
+  struct Step { std::vector<int> L, U; };  // entry ids, in the order the reference walks them
+  std::vector<Step> steps((size_t)std::max(N - 1, 0));
+
+  auto swap_int = [](std::vector<int>& i2e, std::vector<int>& e2i, int x, int y) {
+    std::swap(i2e[(size_t)x], i2e[(size_t)y]);
+    e2i[(size_t)i2e[(size_t)x]] = x;
+    e2i[(size_t)i2e[(size_t)y]] = y;
+  };
+  // max |val| among the entries of external column c whose current internal row is >= n; ties -> smallest internal row
+  auto col_max_from = [&](int c, int n) {
+    int best = -1, best_ir = 0;
+    double best_val = 0.0;
+    for (int id : in_col[(size_t)c]) {
+      int ir = P.row_e2i[(size_t)E[(size_t)id].r];
+      if (ir < n) continue;
+      double a = s_abs(E[(size_t)id].val);
+      // max_after_loc walks the column in ascending internal row and replaces `best` only on a strictly larger
+      // value: the winner is the largest |val|, ties going to the smallest internal row (finite values).
+      if (best < 0 || a > best_val || (a == best_val && ir < best_ir)) { best = id; best_val = a; best_ir = ir; }
+    }
+    return best;
+  };
+
+  for (int n = 0; n + 1 < N && P.status == ST_OK; n++) {
+    int pivot = -1;
+    {  // ---- markowitz_search_diagonal
+      long best_mark = -1;  // -1 stands for usize::MAX
+      double best_ratio = 0.0;
+      long num_ties = 0;
+      bool done = false;
+      for (int k = n; k < N && !done; k++) {
+        int d = lookup(P.row_i2e[(size_t)k], P.col_i2e[(size_t)k]);
+        if (d < 0) continue;
+        int mx = col_max_from(E[(size_t)d].c, n);
+        if (mx < 0) continue;
+        double threshold = 1e-3 * s_abs(E[(size_t)mx].val) + 0.0;
+        if (s_abs(E[(size_t)d].val) < threshold) continue;
+        long mr = mrow[(size_t)E[(size_t)d].r], mc = mcol[(size_t)E[(size_t)d].c];
+        if (!(mr > 0 && mc > 0)) throw S21Error(ST_OTHER, "markowitz count underflow");
+        long mark = (mr - 1) * (mc - 1);
+        if (best_mark < 0 || mark < best_mark) {
+          num_ties = 0;
+          pivot = d;
+          best_mark = mark;
+          best_ratio = s_abs(s_div(E[(size_t)d].val, E[(size_t)mx].val));
+        } else if (mark == best_mark) {
+          num_ties += 1;
+          double ratio = s_abs(s_div(E[(size_t)d].val, E[(size_t)mx].val));
+          if (ratio > best_ratio) { pivot = d; best_ratio = ratio; }
+          if (num_ties >= best_mark * 5) done = true;
+        }
+      }
+    }
+    if (pivot < 0) {  // ---- markowitz_search_submatrix: column n only
+      std::vector<std::pair<int, int>> cand;  // (internal row, id)
+      for (int id : in_col[(size_t)P.col_i2e[(size_t)n]]) {
+        int ir = P.row_e2i[(size_t)E[(size_t)id].r];
+        if (ir >= n) cand.push_back({ir, id});
+      }
+      std::sort(cand.begin(), cand.end());
+      if (!cand.empty()) {
+        int mx = cand[0].second;
+        double mxv = s_abs(E[(size_t)mx].val);
+        for (auto& c : cand) { double a = s_abs(E[(size_t)c.second].val); if (a > mxv) { mx = c.second; mxv = a; } }
+        long best_mark = -1;
+        double best_ratio = 0.0;
+        for (auto& c : cand) {
+          int id = c.second;
+          long mr = mrow[(size_t)E[(size_t)id].r], mc = mcol[(size_t)E[(size_t)id].c];
+          if (!(mr > 0 && mc > 0)) throw S21Error(ST_OTHER, "markowitz count underflow");
+          long mark = (mr - 1) * (mc - 1);
+          double ratio = s_abs(s_div(E[(size_t)id].val, E[(size_t)mx].val));
+          if (best_mark < 0 || mark < best_mark) { pivot = id; best_mark = mark; best_ratio = ratio; }
+          else if (mark == best_mark && ratio > best_ratio) { pivot = id; best_ratio = ratio; }
+        }
+      }
+    }
+    if (pivot < 0) {  // ---- find_max over the active submatrix, column-major in internal order
+      double max_val = 0.0;
+      for (int k = n; k < N; k++) {
+        std::vector<std::pair<int, int>> cand;
+        for (int id : in_col[(size_t)P.col_i2e[(size_t)k]]) {
+          int ir = P.row_e2i[(size_t)E[(size_t)id].r];
+          if (ir >= n) cand.push_back({ir, id});
+        }
+        std::sort(cand.begin(), cand.end());
+        for (auto& c : cand) { double a = s_abs(E[(size_t)c.second].val); if (a > max_val) { pivot = c.second; max_val = a; } }
+      }
+    }
+    if (pivot < 0) { P.status = ST_PIVOT; break; }
+
+    // ---- swap the pivot to (n, n)
+    swap_int(P.row_i2e, P.row_e2i, P.row_e2i[(size_t)E[(size_t)pivot].r], n);
+    swap_int(P.col_i2e, P.col_e2i, P.col_e2i[(size_t)E[(size_t)pivot].c], n);
+
+    // ---- row_col_elim
+    const int pr = E[(size_t)pivot].r, pc = E[(size_t)pivot].c;
+    T pivot_val = E[(size_t)pivot].val;
+    if (s_is_zero(pivot_val)) { P.status = ST_SINGULAR; break; }
+    Step& st = steps[(size_t)n];
+    {
+      std::vector<std::pair<int, int>> ls, us;
+      for (int id : in_col[(size_t)pc]) { int ir = P.row_e2i[(size_t)E[(size_t)id].r]; if (ir > n) ls.push_back({ir, id}); }
+      for (int id : in_row[(size_t)pr]) { int ic = P.col_e2i[(size_t)E[(size_t)id].c]; if (ic > n) us.push_back({ic, id}); }
+      std::sort(ls.begin(), ls.end());
+      std::sort(us.begin(), us.end());
+      for (auto& x : ls) st.L.push_back(x.second);
+      for (auto& x : us) st.U.push_back(x.second);
+    }
+    for (int l : st.L) E[(size_t)l].val = s_div(E[(size_t)l].val, pivot_val);
+    for (int u : st.U) {
+      const int uc = E[(size_t)u].c;
+      for (int l : st.L) {
+        const int lr = E[(size_t)l].r;
+        int t = lookup(lr, uc);
+        if (t < 0) {  // fill-in
+          t = (int)E.size();
+          E.push_back({lr, uc, Scalar<T>::zero(), true});
+          in_row[(size_t)lr].push_back(t);
+          in_col[(size_t)uc].push_back(t);
+          at.emplace(rc_key(lr, uc), t);
+          mrow[(size_t)lr] += 1;
+          mcol[(size_t)uc] += 1;
+        }
+        E[(size_t)t].val = s_sub(E[(size_t)t].val, s_mul(E[(size_t)u].val, E[(size_t)l].val));
+      }
+      mcol[(size_t)uc] -= 1;
+    }
+    mrow[(size_t)pr] -= 1;
+    mcol[(size_t)pc] -= 1;
+    for (int l : st.L) mrow[(size_t)E[(size_t)l].r] -= 1;
+  }
+
+  // ---- freeze: slots in final internal coordinates
+  P.nnzLU = (int)E.size();
+  std::vector<int> order((size_t)P.nnzLU);
+  for (int k = 0; k < P.nnzLU; k++) order[(size_t)k] = k;
+  auto irow = [&](int id) { return P.row_e2i[(size_t)E[(size_t)id].r]; };
+  auto icol = [&](int id) { return P.col_e2i[(size_t)E[(size_t)id].c]; };
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return irow(a) != irow(b) ? irow(a) < irow(b) : icol(a) < icol(b); });
+  std::vector<int> slot_of((size_t)P.nnzLU);
+  P.rowptr.assign((size_t)N + 1, 0);
+  P.colidx.resize((size_t)P.nnzLU);
+  P.lu_row.resize((size_t)P.nnzLU); P.lu_col.resize((size_t)P.nnzLU); P.lu_fill.resize((size_t)P.nnzLU);
+  P.diag_slot.assign((size_t)N, -1);
+  for (int s = 0; s < P.nnzLU; s++) {
+    int id = order[(size_t)s];
+    slot_of[(size_t)id] = s;
+    int r = irow(id), c = icol(id);
+    P.rowptr[(size_t)r + 1] += 1;
+    P.colidx[(size_t)s] = c;
+    P.lu_row[(size_t)s] = r; P.lu_col[(size_t)s] = c; P.lu_fill[(size_t)s] = E[(size_t)id].fill ? 1 : 0;
+    if (r == c) P.diag_slot[(size_t)r] = s;
+  }
+  for (int r = 0; r < N; r++) P.rowptr[(size_t)r + 1] += P.rowptr[(size_t)r];
+  P.elem_slot.resize(elem_row.size());
+  for (size_t e = 0; e < elem_row.size(); e++) P.elem_slot[e] = slot_of[e];
+  if (P.status == ST_OK)
+    for (int k = 0; k < N; k++)
+      if (P.diag_slot[(size_t)k] < 0) P.status = ST_SINGULAR;  // mod.rs:955-958, 969-972
+
+  P.l_off.assign((size_t)N + 1, 0);
+  P.upd_off.assign((size_t)N + 1, 0);
+  for (int n = 0; n < N; n++) {
+    if (n + 1 < N && P.status == ST_OK) {
+      const Step& st = steps[(size_t)n];
+      // L in ascending FINAL internal row (the order forward substitution and the kernels walk)
+      std::vector<std::pair<int, int>> ls;
+      for (int l : st.L) ls.push_back({irow(l), slot_of[(size_t)l]});
+      std::sort(ls.begin(), ls.end());
+      for (auto& x : ls) { P.l_row.push_back(x.first); P.l_slot.push_back(x.second); }
+      for (int u : st.U)
+        for (int l : st.L) {
+          int t = lookup(E[(size_t)l].r, E[(size_t)u].c);
+          P.upd_t.push_back(slot_of[(size_t)t]);
+          P.upd_u.push_back(slot_of[(size_t)u]);
+          P.upd_l.push_back(slot_of[(size_t)l]);
+        }
+    }
+    P.l_off[(size_t)n + 1] = (int)P.l_slot.size();
+    P.upd_off[(size_t)n + 1] = (int)P.upd_t.size();
+  }
+  return P;
+}
+
+}  // namespace s21

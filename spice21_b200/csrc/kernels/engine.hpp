@@ -1,0 +1,72 @@
+// Host-visible interface of the CUDA engine (kernels/newton.cu). Plain structs of device pointers; no CUDA headers
+// needed by the includer.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+#include "../scalar.h"
+
+namespace s21 {
+
+// Device tables shared by every instance of a batch (device_layout.h). `itab` holds element handles that index the
+// value array the kernel assembles into: raw element ids for a probe, L+U slots for a planned solve.
+struct DevTables {
+  int n_dev;
+  const int* type;
+  const int* itab_off;
+  const int* par_off;
+  const int* state_off;
+  const int* itab;
+  const int* pcode;     // (offset << 1) | per_instance
+  const double* pval;   // parameter value pool
+  int n_state;
+};
+
+// Static plan of the sparse LU (host/symbolic.hpp), in internal (pivoted) coordinates.
+struct PlanTables {
+  int N, nnz;
+  const int *row_i2e, *col_i2e, *col_e2i;
+  const int *rowptr, *colidx, *diag_slot;
+  const int *l_off, *l_slot, *l_row;
+  const int *upd_off, *upd_t, *upd_u, *upd_l;
+};
+
+// Per-instance workspace, structure-of-arrays with the instance index fastest: entry k of instance i is a[k*stride+i].
+template <class T>
+struct WorkTables {
+  T* x;     // [N]   solution / Newton guess (persists across solves: warm start, analysis.rs:139-147)
+  T* rhs;   // [N]
+  T* c;     // [N]   residual -> forward/back substitution -> dx, internal order
+  T* lu;    // [nnz] assembled matrix, factorised in place
+  size_t stride;
+  double* st_op;     // [n_state] committed device state (Component::commit, comps/mod.rs:77)
+  double* st_guess;  // [n_state] in-flight device state
+  size_t st_stride;
+};
+
+struct NewtonOut {
+  int32_t* status;    // [B] S21_* code
+  int32_t* iters;     // [B] iterations that reached the linear solve (accumulated)
+  int32_t* loads;     // [B] device-load sweeps (accumulated)
+};
+
+struct SolveCtl {
+  int B;             // instances (threads)
+  int mode;          // AnMode
+  double gmin, dt;
+  double reltol, iabstol;  // real solve: |dx| <= reltol (absolute!) and |res| <= iabstol (analysis.rs:331-345)
+  const double* omega;     // [B] AC only
+  size_t par_inst_stride;  // 1: parameter/state instance == workspace instance; 0: all columns use instance 0 (AC sweep)
+};
+
+// All launchers enqueue on `stream` (a cudaStream_t) and return a cudaError_t as int.
+int launch_dcop(const DevTables& d, const PlanTables& p, const WorkTables<double>& w, const NewtonOut& o, const SolveCtl& c, void* stream);
+// OP must already be solved and committed; runs points 1..T-1 of Tran::solve. wave: [T][n_save][B] device (point 0 written too).
+int launch_tran(const DevTables& d, const PlanTables& p, const WorkTables<double>& w, const NewtonOut& o, const SolveCtl& c, int T,
+                const int* save_vars, int n_save, double* wave, void* stream);
+int launch_ac(const DevTables& d, const PlanTables& p, const WorkTables<cplx>& w, const NewtonOut& o, const SolveCtl& c, void* stream);
+// First load sweep of instance `inst` in `mode`, assembled by raw element id into out[n_elems] (device memory).
+int launch_probe_real(const DevTables& d, const WorkTables<double>& w, const SolveCtl& c, int n_elems, int N, int inst, double* out, void* stream);
+int launch_probe_cplx(const DevTables& d, const WorkTables<cplx>& w, const SolveCtl& c, int n_elems, int N, int inst, cplx* out, void* stream);
+
+}  // namespace s21

@@ -1,0 +1,303 @@
+// The batched Newton loop on the GPU: one thread per circuit instance, the whole loop (and for transient the whole
+// time loop) inside ONE kernel launch — device evaluation, MNA assembly, residual, convergence test, sparse LU
+// refactorisation, forward/back substitution, step limiting and the solution update never leave the device.
+//
+// Replaces, per instance:  Solver::<f64>::solve      spice21/src/analysis.rs:169-210
+//                          Solver::<Complex>::solve  spice21/src/analysis.rs:253-303
+//                          Solver::converged         spice21/src/analysis.rs:331-345
+//                          Matrix::{reset,update,res,lu_factorize(numeric part),solve}  spice21/src/sparse21/mod.rs:272-327, 865-991
+//                          Tran::solve time loop     spice21/src/analysis.rs:553-570
+//
+// Data layout: every per-instance quantity is a column of a structure-of-arrays table, a[k*stride + instance], so a
+// warp (32 consecutive instances) touches 256 contiguous bytes per access; all index tables (device tables, stamp
+// handles, the LU plan) are shared by the batch and are read with warp-uniform addresses (one L1/L2 sector per warp).
+// Within an instance every floating-point operation happens in the reference's order (assembly in component/push
+// order, Schur updates in ascending pivot order, substitution sums in list order) and the file is compiled with
+// -fmad=false, so results differ from the CPU restatement only through libm's exp/log.
+#include <cuda_runtime.h>
+
+#include "devices.cuh"
+#include "engine.hpp"
+
+namespace s21 {
+
+enum { ST_OK_ = 0, ST_CONV_ = 1, ST_SINGULAR_ = 2 };
+
+// ------------------------------------------------------------------------------------------------ per-thread Env
+template <class T>
+struct Env {
+  // program (warp-uniform)
+  const int* it;
+  const int* pc;
+  const double* pval;
+  // state columns of this device
+  double* sop;
+  double* sguess;
+  size_t sstride, sinst, pinst;
+  // workspace columns of this instance
+  const T* x;
+  T* lu;
+  T* rhs;
+  size_t stride, w;
+  int mode;
+  double dt, gmin, omega;
+
+  __device__ __forceinline__ int node(int k) const { return __ldg(it + k); }
+  __device__ __forceinline__ double par(int k) const {
+    const int c = __ldg(pc + k);
+    return pval[(size_t)(c >> 1) + (size_t)(c & 1) * pinst];
+  }
+  __device__ __forceinline__ double volt(int var) const;
+  __device__ __forceinline__ double op(int k) const { return sop[(size_t)k * sstride + sinst]; }
+  __device__ __forceinline__ double guess(int k) const { return sguess[(size_t)k * sstride + sinst]; }
+  __device__ __forceinline__ void set_guess(int k, double v) { sguess[(size_t)k * sstride + sinst] = v; }
+  __device__ __forceinline__ void add_g(int h, T v) {
+    if (h >= 0) { T* a = lu + (size_t)h * stride + w; *a = s_add(*a, v); }
+  }
+  __device__ __forceinline__ void add_b(int var, T v) {
+    if (var >= 0) { T* a = rhs + (size_t)var * stride + w; *a = s_add(*a, v); }
+  }
+};
+template <> __device__ __forceinline__ double Env<double>::volt(int var) const { return var < 0 ? 0.0 : x[(size_t)var * stride + w]; }
+template <> __device__ __forceinline__ double Env<cplx>::volt(int) const { return 0.0; }  // load_ac never reads the guess
+
+// One pass of Solver::update (analysis.rs:153-168 / 237-252): every device, in component order.
+// Returns false when a device has no load function for this analysis (the reference panics: comps/mod.rs:86-88).
+template <class T>
+__device__ __forceinline__ bool load_sweep(const DevTables& d, Env<T>& e, double* st_op, double* st_guess);
+
+template <>
+__device__ __forceinline__ bool load_sweep<double>(const DevTables& d, Env<double>& e, double* st_op, double* st_guess) {
+  for (int k = 0; k < d.n_dev; k++) {
+    e.it = d.itab + __ldg(d.itab_off + k);
+    e.pc = d.pcode + __ldg(d.par_off + k);
+    const size_t so = (size_t)__ldg(d.state_off + k) * e.sstride;
+    e.sop = st_op + so;
+    e.sguess = st_guess + so;
+    switch (__ldg(d.type + k)) {
+      case DT_R: load_resistor(e); break;
+      case DT_C: load_capacitor(e); break;
+      case DT_I: load_isrc(e); break;
+      case DT_V: load_vsrc(e); break;
+      case DT_DIODE: load_diode(e); break;
+      case DT_MOS0: load_mos0(e); break;
+      case DT_MOS1: load_mos1(e); break;
+      default: return false;
+    }
+  }
+  return true;
+}
+template <>
+__device__ __forceinline__ bool load_sweep<cplx>(const DevTables& d, Env<cplx>& e, double* st_op, double* st_guess) {
+  for (int k = 0; k < d.n_dev; k++) {
+    e.it = d.itab + __ldg(d.itab_off + k);
+    e.pc = d.pcode + __ldg(d.par_off + k);
+    const size_t so = (size_t)__ldg(d.state_off + k) * e.sstride;
+    e.sop = st_op + so;
+    e.sguess = st_guess + so;
+    switch (__ldg(d.type + k)) {
+      case DT_R: load_ac_resistor(e); break;
+      case DT_C: load_ac_capacitor(e); break;
+      case DT_V: load_ac_vsrc(e); break;
+      case DT_MOS1: load_ac_mos1(e); break;
+      default: return false;  // Isrc, Diode, Mos0, Bsim4 have no load_ac in the reference
+    }
+  }
+  return true;
+}
+
+template <class T> struct Tol;
+template <> struct Tol<double> {  // analysis.rs:331-345: fail on  > tol
+  static __device__ __forceinline__ bool ok(double a, double tol) { return !(a > tol); }
+  static const int max_iter = 100;  // analysis.rs:173
+};
+template <> struct Tol<cplx> {  // analysis.rs:271-272: pass on  < tol
+  static __device__ __forceinline__ bool ok(double a, double tol) { return a < tol; }
+  static const int max_iter = 20;  // analysis.rs:258
+};
+
+// Commit every device: op <- guess (analysis.rs:190-192; Capacitor/Diode/Mos1::commit)
+__device__ __forceinline__ void commit_state(const DevTables& d, double* st_op, const double* st_guess, size_t sstride, size_t sinst) {
+  for (int k = 0; k < d.n_state; k++) st_op[(size_t)k * sstride + sinst] = st_guess[(size_t)k * sstride + sinst];
+}
+
+// The Newton shell for one instance. Returns an S21 status; *n_solves / *n_loads are incremented.
+template <class T>
+__device__ int newton_solve(const DevTables& d, const PlanTables& p, const WorkTables<T>& wk, const SolveCtl& ctl, size_t inst,
+                            double omega, double vtol, double itol, bool do_commit, int* n_solves, int* n_loads) {
+  const size_t S = wk.stride;
+  T* x = wk.x + inst;
+  T* rhs = wk.rhs + inst;
+  T* c = wk.c + inst;
+  T* lu = wk.lu + inst;
+  const size_t pinst = inst * ctl.par_inst_stride;
+  Env<T> e;
+  e.pval = d.pval;
+  e.sstride = wk.st_stride; e.sinst = pinst; e.pinst = pinst;
+  e.x = wk.x; e.lu = wk.lu; e.rhs = wk.rhs; e.stride = S; e.w = inst;
+  e.mode = ctl.mode; e.dt = ctl.dt; e.gmin = ctl.gmin; e.omega = omega;
+  const int N = p.N;
+  bool dx_ok = true;  // dx = 0 before the first iteration
+  for (int iter = 0; iter < Tol<T>::max_iter; iter++) {
+    // Matrix::reset + fresh rhs (analysis.rs:178-179)
+    for (int k = 0; k < p.nnz; k++) lu[(size_t)k * S] = Scalar<T>::zero();
+    for (int k = 0; k < N; k++) rhs[(size_t)k * S] = Scalar<T>::zero();
+    if (!load_sweep<T>(d, e, wk.st_op, wk.st_guess)) return 6;  // S21_UNSUPPORTED
+    *n_loads += 1;
+    // Matrix::res (sparse21/mod.rs:298-327), produced directly in internal row order: c[k] = res[row_i2e[k]]
+    bool res_ok = true;
+    for (int r = 0; r < N; r++) {
+      T acc = Scalar<T>::zero();
+      const int b = __ldg(p.rowptr + r), en = __ldg(p.rowptr + r + 1);
+      for (int s = b; s < en; s++) {
+        const int col = __ldg(p.colidx + s);
+        acc = s_add(acc, s_mul(lu[(size_t)s * S], x[(size_t)__ldg(p.col_i2e + col) * S]));
+      }
+      const T rv = s_sub(rhs[(size_t)__ldg(p.row_i2e + r) * S], acc);
+      c[(size_t)r * S] = rv;
+      res_ok = res_ok && Tol<T>::ok(s_abs(rv), itol);
+    }
+    if (dx_ok && res_ok) {
+      if (do_commit) commit_state(d, wk.st_op, wk.st_guess, wk.st_stride, pinst);
+      return ST_OK_;
+    }
+    // ---- numeric LU on the frozen pattern (row_col_elim, sparse21/mod.rs:865-919), ascending pivot index
+    for (int k = 0; k + 1 < N; k++) {
+      const T piv = lu[(size_t)__ldg(p.diag_slot + k) * S];
+      if (s_is_zero(piv)) return ST_SINGULAR_;
+      const int lb = __ldg(p.l_off + k), le = __ldg(p.l_off + k + 1);
+      for (int j = lb; j < le; j++) {
+        T* a = lu + (size_t)__ldg(p.l_slot + j) * S;
+        *a = s_div(*a, piv);
+      }
+      const int ub = __ldg(p.upd_off + k), ue = __ldg(p.upd_off + k + 1);
+      for (int j = ub; j < ue; j++) {
+        T* t = lu + (size_t)__ldg(p.upd_t + j) * S;
+        const T v = s_mul(lu[(size_t)__ldg(p.upd_u + j) * S], lu[(size_t)__ldg(p.upd_l + j) * S]);
+        *t = s_sub(*t, v);
+      }
+    }
+    // ---- forward substitution (sparse21/mod.rs:947-964)
+    for (int k = 0; k < N; k++) {
+      const T ck = c[(size_t)k * S];
+      if (s_is_zero(ck)) continue;
+      const int lb = __ldg(p.l_off + k), le = __ldg(p.l_off + k + 1);
+      for (int j = lb; j < le; j++) {
+        T* t = c + (size_t)__ldg(p.l_row + j) * S;
+        *t = s_sub(*t, s_mul(ck, lu[(size_t)__ldg(p.l_slot + j) * S]));
+      }
+    }
+    // ---- backward substitution (sparse21/mod.rs:967-979)
+    for (int k = N - 1; k >= 0; k--) {
+      const int ds = __ldg(p.diag_slot + k);
+      const int en = __ldg(p.rowptr + k + 1);
+      T ck = c[(size_t)k * S];
+      for (int s = ds + 1; s < en; s++) ck = s_sub(ck, s_mul(c[(size_t)__ldg(p.colidx + s) * S], lu[(size_t)s * S]));
+      const T dv = lu[(size_t)ds * S];
+      if (s_is_zero(dv)) return ST_SINGULAR_;
+      c[(size_t)k * S] = s_div(ck, dv);
+    }
+    *n_solves += 1;
+    // ---- global step limit + update (analysis.rs:197-207 / 283-293); dx[e] = c[col_e2i[e]]
+    double max_abs = 0.0;
+    for (int k = 0; k < N; k++) {
+      const double a = s_abs(c[(size_t)__ldg(p.col_e2i + k) * S]);
+      if (a > max_abs) max_abs = a;
+    }
+    const bool limit = max_abs > 1.0;
+    dx_ok = true;
+    for (int k = 0; k < N; k++) {
+      T dxk = c[(size_t)__ldg(p.col_e2i + k) * S];
+      if (limit) dxk = s_scale(dxk, 1.0, max_abs);
+      x[(size_t)k * S] = s_add(x[(size_t)k * S], dxk);
+      dx_ok = dx_ok && Tol<T>::ok(s_abs(dxk), vtol);
+    }
+  }
+  return ST_CONV_;
+}
+
+// ------------------------------------------------------------------------------------------------ kernels
+__global__ void __launch_bounds__(128) k_dcop(DevTables d, PlanTables p, WorkTables<double> w, NewtonOut o, SolveCtl ctl) {
+  const size_t inst = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= (size_t)ctl.B) return;
+  int ns = 0, nl = 0;
+  const int st = newton_solve<double>(d, p, w, ctl, inst, 0.0, ctl.reltol, ctl.iabstol, true, &ns, &nl);
+  o.status[inst] = st;
+  o.iters[inst] += ns;
+  o.loads[inst] += nl;
+}
+
+__global__ void __launch_bounds__(128) k_tran(DevTables d, PlanTables p, WorkTables<double> w, NewtonOut o, SolveCtl ctl, int T,
+                                             const int* save_vars, int n_save, double* wave) {
+  const size_t inst = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= (size_t)ctl.B) return;
+  const size_t B = (size_t)ctl.B;
+  int st = o.status[inst];  // status of the OP solve
+  for (int s = 0; s < n_save; s++) wave[(size_t)s * B + inst] = w.x[(size_t)__ldg(save_vars + s) * w.stride + inst];
+  int ns = 0, nl = 0;
+  for (int tp = 1; tp < T; tp++) {
+    if (st == ST_OK_) st = newton_solve<double>(d, p, w, ctl, inst, 0.0, ctl.reltol, ctl.iabstol, true, &ns, &nl);
+    for (int s = 0; s < n_save; s++) {
+      const double v = st == ST_OK_ ? w.x[(size_t)__ldg(save_vars + s) * w.stride + inst] : __longlong_as_double(0x7ff8000000000000LL);
+      wave[((size_t)tp * n_save + s) * B + inst] = v;
+    }
+  }
+  o.status[inst] = st;
+  o.iters[inst] += ns;
+  o.loads[inst] += nl;
+}
+
+__global__ void __launch_bounds__(128) k_ac(DevTables d, PlanTables p, WorkTables<cplx> w, NewtonOut o, SolveCtl ctl) {
+  const size_t inst = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= (size_t)ctl.B) return;
+  int ns = 0, nl = 0;
+  // hard-coded complex tolerances (analysis.rs:271-272); no commit is observable in AC (load_ac reads only `op`)
+  const int st = newton_solve<cplx>(d, p, w, ctl, inst, ctl.omega[inst], 1e-3, 1e-9, false, &ns, &nl);
+  o.status[inst] = st;
+  o.iters[inst] += ns;
+  o.loads[inst] += nl;
+}
+
+// Probe: the first load sweep of one instance with RAW element ids as handles, assembled into that instance's own
+// `lu` column (the caller sizes it for max(n_elems, nnz)) and copied out densely. Feeds the host symbolic phase.
+template <class T>
+__global__ void k_probe(DevTables d, WorkTables<T> w, SolveCtl ctl, int n_elems, int N, int inst_, T* out) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const size_t inst = (size_t)inst_;
+  const size_t pinst = inst * ctl.par_inst_stride;
+  Env<T> e;
+  e.pval = d.pval;
+  e.sstride = w.st_stride; e.sinst = pinst; e.pinst = pinst;
+  e.x = w.x; e.lu = w.lu; e.rhs = w.rhs; e.stride = w.stride; e.w = inst;
+  e.mode = ctl.mode; e.dt = ctl.dt; e.gmin = ctl.gmin; e.omega = ctl.omega ? ctl.omega[inst] : 0.0;
+  for (int k = 0; k < n_elems; k++) w.lu[(size_t)k * w.stride + inst] = Scalar<T>::zero();
+  for (int k = 0; k < N; k++) w.rhs[(size_t)k * w.stride + inst] = Scalar<T>::zero();
+  load_sweep<T>(d, e, w.st_op, w.st_guess);
+  for (int k = 0; k < n_elems; k++) out[k] = w.lu[(size_t)k * w.stride + inst];
+}
+
+static inline int grid_for(int B, int block) { return (B + block - 1) / block; }
+
+int launch_dcop(const DevTables& d, const PlanTables& p, const WorkTables<double>& w, const NewtonOut& o, const SolveCtl& c, void* stream) {
+  k_dcop<<<grid_for(c.B, 128), 128, 0, (cudaStream_t)stream>>>(d, p, w, o, c);
+  return (int)cudaGetLastError();
+}
+int launch_tran(const DevTables& d, const PlanTables& p, const WorkTables<double>& w, const NewtonOut& o, const SolveCtl& c, int T,
+                const int* save_vars, int n_save, double* wave, void* stream) {
+  k_tran<<<grid_for(c.B, 128), 128, 0, (cudaStream_t)stream>>>(d, p, w, o, c, T, save_vars, n_save, wave);
+  return (int)cudaGetLastError();
+}
+int launch_ac(const DevTables& d, const PlanTables& p, const WorkTables<cplx>& w, const NewtonOut& o, const SolveCtl& c, void* stream) {
+  k_ac<<<grid_for(c.B, 128), 128, 0, (cudaStream_t)stream>>>(d, p, w, o, c);
+  return (int)cudaGetLastError();
+}
+int launch_probe_real(const DevTables& d, const WorkTables<double>& w, const SolveCtl& c, int n_elems, int N, int inst, double* out, void* stream) {
+  k_probe<double><<<1, 32, 0, (cudaStream_t)stream>>>(d, w, c, n_elems, N, inst, out);
+  return (int)cudaGetLastError();
+}
+int launch_probe_cplx(const DevTables& d, const WorkTables<cplx>& w, const SolveCtl& c, int n_elems, int N, int inst, cplx* out, void* stream) {
+  k_probe<cplx><<<1, 32, 0, (cudaStream_t)stream>>>(d, w, c, n_elems, N, inst, out);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace s21

@@ -1,0 +1,319 @@
+"""Test circuits, described once and rendered three ways:
+
+* ``to_text()``   — the oracle's line netlist (oracle/oracle_capi.cpp),
+* ``to_proto()``  — a ``spice21.Circuit`` protobuf message (what the reference's bindings send),
+* ``to_s21()``    — builder calls on the C ABI (``spice21_b200.Circuit``).
+
+The circuit bodies restate the reference's own test circuits (spice21/src/tests.rs, file:line cited per function) and
+the synthetic benchmark configurations of SURVEY.md §8(d).
+"""
+import numpy as np
+
+GND = ""
+
+
+def _n(x):
+    return "~" if x == "" else str(x)
+
+
+def _fmt(v):
+    return repr(float(v))
+
+
+class _Scope:
+    def __init__(self):
+        self.comps = []
+
+    def R(self, name, p, n, g):
+        self.comps.append(("R", name, str(p), str(n), float(g)))
+        return self
+
+    def C(self, name, p, n, c):
+        self.comps.append(("C", name, str(p), str(n), float(c)))
+        return self
+
+    def I(self, name, p, n, dc):  # noqa: E743
+        self.comps.append(("I", name, str(p), str(n), float(dc)))
+        return self
+
+    def V(self, name, p, n, dc, acm=0.0):
+        self.comps.append(("V", name, str(p), str(n), float(dc), float(acm)))
+        return self
+
+    def D(self, name, p, n, model, params):
+        self.comps.append(("D", name, str(p), str(n), model, params))
+        return self
+
+    def M(self, name, model, params, d, g, s, b):
+        self.comps.append(("M", name, model, params, str(d), str(g), str(s), str(b)))
+        return self
+
+    def X(self, name, module, **ports):
+        self.comps.append(("X", name, module, {k: str(v) for k, v in ports.items()}))
+        return self
+
+
+class Module(_Scope):
+    def __init__(self, name, ports, signals=()):
+        super().__init__()
+        self.name, self.ports, self.signals = name, list(ports), list(signals)
+
+
+class Ckt(_Scope):
+    def __init__(self, signals=(), name=""):
+        super().__init__()
+        self.name = name
+        self.signals = [str(s) for s in signals]
+        self.modules = []
+        self.defs = []  # (kind, name, mos_type, params dict)
+
+    def module(self, name, ports, signals=()):
+        m = Module(name, ports, signals)
+        self.modules.append(m)
+        return m
+
+    def define(self, kind, name, mos_type=0, **params):
+        self.defs.append((kind, name, int(mos_type), params))
+        return self
+
+    # ------------------------------------------------------------------ oracle text
+    @staticmethod
+    def _comp_text(c):
+        k = c[0]
+        if k in "RCI":
+            return f"{k} {c[1]} {_n(c[2])} {_n(c[3])} {_fmt(c[4])}"
+        if k == "V":
+            return f"V {c[1]} {_n(c[2])} {_n(c[3])} {_fmt(c[4])} {_fmt(c[5])}"
+        if k == "D":
+            return f"D {c[1]} {_n(c[2])} {_n(c[3])} {_n(c[4])} {_n(c[5])}"
+        if k == "M":
+            return f"M {c[1]} {_n(c[2])} {_n(c[3])} {_n(c[4])} {_n(c[5])} {_n(c[6])} {_n(c[7])}"
+        if k == "X":
+            return f"X {c[1]} {c[2]} " + " ".join(f"{p}={_n(v)}" for p, v in c[3].items())
+        raise ValueError(k)
+
+    def to_text(self):
+        out = [f"signal {s}" for s in self.signals]
+        for kind, name, t, p in self.defs:
+            kv = " ".join(f"{k}={_fmt(v) if k != 'tpg' else int(v)}" for k, v in p.items())
+            if kind == "mos0":
+                out.append(f"mos0 {name} {t}")
+            elif kind in ("mos1model", "bsim4model"):
+                out.append(f"{kind} {name} {t} {kv}")
+            else:
+                out.append(f"{kind} {_n(name)} {kv}")
+        for m in self.modules:
+            out.append(f"module {m.name} " + " ".join(m.ports))
+            out += [f"msignal {s}" for s in m.signals]
+            out += [self._comp_text(c) for c in m.comps]
+            out.append("endmodule")
+        out += [self._comp_text(c) for c in self.comps]
+        return "\n".join(out) + "\n"
+
+    # ------------------------------------------------------------------ protobuf
+    @staticmethod
+    def _comp_proto(c):
+        from spice21_b200 import protos as P
+        k = c[0]
+        if k == "R":
+            return P.Instance(r=P.Resistor(name=c[1], p=c[2], n=c[3], g=c[4]))
+        if k == "C":
+            return P.Instance(c=P.Capacitor(name=c[1], p=c[2], n=c[3], c=c[4]))
+        if k == "I":
+            return P.Instance(i=P.Isrc(name=c[1], p=c[2], n=c[3], dc=c[4]))
+        if k == "V":
+            return P.Instance(v=P.Vsrc(name=c[1], p=c[2], n=c[3], dc=c[4], acm=c[5]))
+        if k == "D":
+            return P.Instance(d=P.Diode(name=c[1], p=c[2], n=c[3], model=c[4], params=c[5]))
+        if k == "M":
+            return P.Instance(m=P.Mos(name=c[1], model=c[2], params=c[3], ports=P.MosPorts(d=c[4], g=c[5], s=c[6], b=c[7])))
+        if k == "X":
+            return P.Instance(x=P.ModuleInstance(name=c[1], module=c[2], ports=c[3]))
+        raise ValueError(k)
+
+    def to_proto(self):
+        from google.protobuf import wrappers_pb2 as W
+        from spice21_b200 import protos as P
+        ck = P.Circuit(name=self.name, signals=self.signals)
+        for kind, name, t, p in self.defs:
+            if kind == "mos0":
+                raise ValueError("Mos0 models cannot be expressed on the reference's wire format (tests.rs:1443-1447)")
+            cls = {"mos1model": P.Mos1Model, "mos1inst": P.Mos1InstParams, "diodemodel": P.DiodeModel, "diodeinst": P.DiodeInstParams,
+                   "bsim4model": P.Bsim4Model, "bsim4inst": P.Bsim4InstParams}[kind]
+            msg = cls(name=name)
+            if kind in ("mos1model", "bsim4model"):
+                msg.mos_type = t
+            if kind == "bsim4model" and p:
+                raise ValueError("Bsim4Model carries only mos_type on the wire (bsim4.proto:45-50)")
+            for k, v in p.items():
+                fld = msg.DESCRIPTOR.fields_by_name[k]
+                sub = getattr(msg, k)
+                if fld.message_type.name == "DoubleValue":
+                    sub.CopyFrom(W.DoubleValue(value=float(v)))
+                elif fld.message_type.name == "Int64Value":
+                    sub.CopyFrom(W.Int64Value(value=int(v)))
+                else:
+                    sub.CopyFrom(W.UInt64Value(value=int(v)))
+            ck.defs.append(P.Def(**{kind: msg}))
+        for m in self.modules:
+            ck.defs.append(P.Def(module=P.Module(name=m.name, ports=m.ports, signals=m.signals, comps=[self._comp_proto(c) for c in m.comps])))
+        for c in self.comps:
+            ck.comps.append(self._comp_proto(c))
+        return ck
+
+    # ------------------------------------------------------------------ C-ABI builder
+    @staticmethod
+    def _comp_s21(ck, c, module=None):
+        k = c[0]
+        if k == "R":
+            ck.r(c[1], c[2], c[3], c[4], module=module)
+        elif k == "C":
+            ck.c(c[1], c[2], c[3], c[4], module=module)
+        elif k == "I":
+            ck.i(c[1], c[2], c[3], c[4], module=module)
+        elif k == "V":
+            ck.v(c[1], c[2], c[3], c[4], c[5], module=module)
+        elif k == "D":
+            ck.d(c[1], c[2], c[3], c[4], c[5], module=module)
+        elif k == "M":
+            ck.mos(c[1], c[2], c[3], c[4], c[5], c[6], c[7], module=module)
+        elif k == "X":
+            ck.x(c[1], c[2], c[3], module=module)
+
+    def to_s21(self, via_proto=False):
+        import spice21_b200 as s21
+        if via_proto:
+            return s21.Circuit(self.to_proto())
+        ck = s21.Circuit()
+        for s in self.signals:
+            ck.signal(s)
+        for kind, name, t, p in self.defs:
+            ck.define(kind, name, t, **p)
+        for m in self.modules:
+            ck.def_module(m.name, m.ports)
+            for s in m.signals:
+                ck.signal(s, module=m.name)
+            for c in m.comps:
+                self._comp_s21(ck, c, module=m.name)
+        for c in self.comps:
+            self._comp_s21(ck, c)
+        return ck
+
+
+# ======================================================================================== reference test circuits
+def add_mos0_defaults(c):  # tests.rs:1443-1447
+    return c.define("mos0", "default", 0).define("mos0", "nmos", 0).define("mos0", "pmos", 1)
+
+
+def add_mos1_defaults(c):  # tests.rs:1449-1461
+    return c.define("mos1model", "default", 0).define("mos1model", "nmos", 0).define("mos1model", "pmos", 1).define("mos1inst", "default")
+
+
+def add_diode_defaults(c):  # tests.rs:1475-1485
+    return c.define("diodemodel", "default").define("diodeinst", "default")
+
+
+def cmos_ro3(defaults):  # tests.rs:889-912
+    c = Ckt(signals=["1", "2", "3", "vdd"], name="ro")
+    defaults(c)
+    inv = c.module("inv", ["inp", "out", "vdd", "vss"])
+    inv.M("p", "pmos", "default", d="out", g="inp", s="vdd", b="vdd")
+    inv.M("n", "nmos", "default", d="out", g="inp", s="vss", b="vss")
+    inv.C("c", "out", "vss", 1e-15)
+    c.V("v1", "vdd", GND, 1.0)
+    c.X("x1", "inv", inp="1", out="2", vdd="vdd", vss=GND)
+    c.X("x2", "inv", inp="2", out="3", vdd="vdd", vss=GND)
+    c.X("x3", "inv", inp="3", out="1", vdd="vdd", vss=GND)
+    return c
+
+
+def nmos_ro3(defaults):  # tests.rs:966-990
+    c = Ckt(signals=["1", "2", "3", "vdd"], name="nmos_ro3")
+    defaults(c)
+    st = c.module("stg", ["inp", "out", "vdd", "vss"])
+    st.M("m", "nmos", "default", d="out", g="inp", s="vss", b="vss")
+    st.R("r", "out", "vdd", 1e-6)
+    st.C("c", "out", "vdd", 0.5e-15)
+    c.V("v1", "vdd", GND, 1.0)
+    for k, (a, b) in enumerate((("1", "2"), ("2", "3"), ("3", "1"))):
+        c.X(f"x{k + 1}", "stg", inp=a, out=b, vdd="vdd", vss=GND)
+    return c
+
+
+def pmos_ro3(defaults):  # tests.rs:1009-1033
+    c = Ckt(signals=["1", "2", "3", "vdd"], name="pmos_ro")
+    defaults(c)
+    st = c.module("stg", ["inp", "out", "vdd", "vss"])
+    st.C("c", "out", "vss", 1e-16)
+    st.R("r", "out", "vss", 1e-6)
+    st.M("m", "pmos", "default", d="out", g="inp", s="vdd", b="vdd")
+    c.V("v1", "vdd", GND, 1.0)
+    for k, (a, b) in enumerate((("1", "2"), ("2", "3"), ("3", "1"))):
+        c.X(f"x{k + 1}", "stg", inp=a, out=b, vdd="vdd", vss=GND)
+    return c
+
+
+def cmos_inv(defaults):  # tests.rs:870-885
+    c = Ckt(signals=["inp", "out", "vdd", "vss"], name="cmos_inv")
+    defaults(c)
+    c.M("p", "pmos", "default", d="out", g="inp", s="vdd", b="vdd")
+    c.M("n", "nmos", "default", d="out", g="inp", s="vss", b="vss")
+    c.V("v1", "vdd", "vss", 1.0)
+    c.V("v2", "vss", GND, 0.0)
+    c.V("v3", "inp", "vss", 0.0)
+    return c
+
+
+# ======================================================================================== benchmark configurations
+C2_MODEL = dict(vt0=0.5, kp=1.2e-4, gamma=0.45, phi=0.7, **{"lambda": 0.04}, tox=9e-9, cgso=3e-10, cgdo=3e-10, cj=1e-3, cjsw=2e-10)
+C2_INST = dict(w=10e-6, l=1e-6, a_d=1e-11, a_s=1e-11, pd=2.2e-5, ps=2.2e-5)
+
+
+def diffpair():
+    """Mos1 differential pair, N = 9, D = 8. Each transistor has its own model so that
+    Monte-Carlo can vary vt0/kp per device."""
+    c = Ckt(name="diffpair")
+    c.define("mos1model", "nch1", 0, **C2_MODEL).define("mos1model", "nch2", 0, **C2_MODEL).define("mos1inst", "wl", **C2_INST)
+    c.V("vsup", "vdd", GND, 1.8)
+    c.V("vinp", "inp", GND, 0.9)
+    c.V("vinn", "inn", GND, 0.9)
+    c.M("m1", "nch1", "wl", d="on", g="inp", s="tail", b=GND)
+    c.M("m2", "nch2", "wl", d="op", g="inn", s="tail", b=GND)
+    c.R("r1", "on", "vdd", 5e-5)
+    c.R("r2", "op", "vdd", 5e-5)
+    c.I("itail", GND, "tail", 20e-6)
+    return c
+
+
+def _normals(B, n, first_instance=0):
+    """[B, n] standard normals: one SplitMix64 stream per instance seeded 0x5EED0021 + instance_id, Box–Muller pairs
+    (the PRNG of all synthetic sampling). Vectorised over instances."""
+    x = np.uint64(0x5EED0021) + np.arange(first_instance, first_instance + B, dtype=np.uint64)
+    out = np.zeros((B, n + (n & 1)))
+    with np.errstate(over="ignore"):
+        def draw():
+            nonlocal x
+            x = x + np.uint64(0x9E3779B97F4A7C15)
+            z = x
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            z = z ^ (z >> np.uint64(31))
+            return (z >> np.uint64(11)).astype(np.float64) * (1.0 / (1 << 53))
+        for k in range(0, n, 2):
+            u1, u2 = np.maximum(draw(), 1e-300), draw()
+            r = np.sqrt(-2.0 * np.log(u1))
+            out[:, k], out[:, k + 1] = r * np.cos(2 * np.pi * u2), r * np.sin(2 * np.pi * u2)
+    return out[:, :n]
+
+
+def diffpair_mc(B, first_instance=0):
+    """Per-instance overrides of config C2: vt0 ~ N(0.5, 5 mV), kp ~ N(1.2e-4, 2 %) per transistor, g ~ N(5e-5, 1 %) per load."""
+    z = _normals(B, 6, first_instance)
+    return {
+        "mos1model:nch1:vt0": 0.5 + 5e-3 * z[:, 0],
+        "mos1model:nch1:kp": 1.2e-4 * (1 + 0.02 * z[:, 1]),
+        "mos1model:nch2:vt0": 0.5 + 5e-3 * z[:, 2],
+        "mos1model:nch2:kp": 1.2e-4 * (1 + 0.02 * z[:, 3]),
+        "R:r1:g": 5e-5 * (1 + 0.01 * z[:, 4]),
+        "R:r2:g": 5e-5 * (1 + 0.01 * z[:, 5]),
+    }

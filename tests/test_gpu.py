@@ -1,0 +1,255 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the oracle on the same inputs, against the
+reference's golden waveforms, and — at BASELINE.json's full batch size — through size-independent properties.
+
+Tolerances (BASELINE.json north_star): dcop node voltages / branch currents within 1e-9 relative; tran and ac within
+SPICE reltol = 1e-3 / vntol = 1e-6 — in practice both agree to ~1e-12, and the tests assert the tighter figure so a
+regression in operation order is caught. Integer structures (stamp map, pivot order, fill) are exact.
+"""
+import numpy as np
+import pytest
+
+import circuits as cc
+from circuits import GND, Ckt
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b, floor=1e-6):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))
+
+
+# ------------------------------------------------------------------------------------------------ transient
+RO = [
+    (cc.cmos_ro3, cc.add_mos1_defaults, "test_mos1_cmos_ro_tran", 1e-11, 1e-8, True),
+    (cc.cmos_ro3, cc.add_mos0_defaults, "test_mos0_cmos_ro_tran", 1e-15, 1e-12, False),
+    (cc.nmos_ro3, cc.add_mos1_defaults, "test_mos1_nmos_ro_tran", 1e-11, 1e-8, True),
+    (cc.pmos_ro3, cc.add_mos1_defaults, "test_mos1_pmos_ro_tran", 1e-11, 1e-8, True),
+]
+
+
+@pytest.mark.parametrize("builder,defaults,fixture,tstep,tstop,protoable", RO, ids=[r[2] for r in RO])
+def test_golden_waveforms(s21, oracle, builder, defaults, fixture, tstep, tstop, protoable):
+    """BASELINE config 1 and its siblings: the reference's golden transients (abs tol 1e-6, tests.rs:788)."""
+    g = golden(fixture)
+    ck = builder(defaults)
+    c = ck.to_s21(via_proto=protoable).elaborate(ic={"1": 0.0})
+    t, wave, status, iters = s21.Batch(c, 1).tran(tstep, tstop)
+    assert status[0] == 0
+    assert np.array_equal(t, g["time"])
+    for k, name in enumerate(c.names):
+        assert np.max(np.abs(wave[0, :, k] - g[name])) <= 1e-6, name
+    o = oracle.Circuit(ck.to_text()).tran(tstep, tstop, ic={"1": 0.0})
+    assert np.max(np.abs(wave[0] - o.data)) <= 1e-9
+    # iteration-count parity with the reference algorithm (hard thresholds; allow a handful of flips)
+    assert abs(int(iters[0]) - o.solves) <= max(3, o.solves // 500), (int(iters[0]), o.solves)
+
+
+def test_tran_bytes_api_matches_golden(s21):
+    """Tran::call_bytes drop-in (proto.rs:79-97): protobuf in, protobuf out, incl. the "time" key."""
+    from spice21_b200 import protos as P
+    g = golden("test_mos1_cmos_ro_tran")
+    res = s21.tran(cc.cmos_ro3(cc.add_mos1_defaults).to_proto(), args=P.TranOptions(tstep=1e-11, tstop=1e-8, ic={"1": 0.0}))
+    assert set(res.keys()) == set(g.keys())
+    for k in g:
+        assert np.max(np.abs(np.array(res[k]) - g[k])) <= 1e-6, k
+
+
+def test_tran_rc_step(s21, oracle):  # tests.rs:695-717
+    ck = Ckt().V("v1", "inp", GND, 1.0).R("r1", "inp", "out", 1e-3).C("c1", "out", GND, 1e-9)
+    c = ck.to_s21().elaborate(ic={"out": 0.0})
+    t, w, st, _ = s21.Batch(c, 1).tran(10e-9, 10e-6)
+    inp, out = w[0, :, c.names.index("inp")], w[0, :, c.names.index("out")]
+    assert st[0] == 0 and np.all(inp == 1.0)
+    assert abs(out[0]) < 1e-3 and abs(out[-1] - 1.0) < 1e-3 and np.all(np.diff(out) > 0)
+    o = oracle.Circuit(ck.to_text()).tran(10e-9, 10e-6, ic={"out": 0.0})
+    assert np.max(np.abs(w[0] - o.data)) <= 1e-12
+
+
+def test_tran_batched_sweep(s21, oracle):
+    """A VDD sweep of the ring oscillator: every instance must match its own oracle run."""
+    B = 8
+    ck = cc.cmos_ro3(cc.add_mos1_defaults)
+    vdd = np.linspace(0.8, 1.2, B)
+    b = s21.Batch(ck.to_s21().elaborate(ic={"1": 0.0}), B)
+    b.override("V:v1:dc", vdd)
+    t, w, st, it = b.tran(1e-11, 2e-9)
+    o = oracle.Circuit(ck.to_text()).batch(1, B, overrides={"V:v1:dc": vdd}, tstep=1e-11, tstop=2e-9, ic={"1": 0.0})
+    assert np.all(st == 0) and np.all(o["status"] == 0)
+    assert np.max(np.abs(w - o["x"])) <= 1e-9
+
+
+# ------------------------------------------------------------------------------------------------ dcop
+def _both_dcop(s21, oracle, ck, via_proto=False, **kw):
+    c = ck.to_s21(via_proto=via_proto).elaborate(**kw)
+    x, st, it = s21.Batch(c, 1).dcop()
+    o = oracle.Circuit(ck.to_text()).dcop(**{k: v for k, v in kw.items() if k == "opts"})
+    assert c.names == o.names
+    return dict(zip(c.names, x[0])), x[0], st[0], int(it[0]), o
+
+
+def test_dcop_known_answers(s21, oracle):
+    # tests.rs:30-44 (exact), 66-83 (exact), 670-692 (exact vectors)
+    v, x, st, it, o = _both_dcop(s21, oracle, Ckt(signals=["vdd"]).I("i1", "vdd", GND, 1e-3).R("r1", "vdd", GND, 1e-3), via_proto=True)
+    assert st == 0 and v["vdd"] == 1.0
+    ck = Ckt(signals=["vdd", "div"]).V("v1", "vdd", GND, 1.0).R("r1", "vdd", "div", 2e-3).R("r2", GND, "div", 2e-3)
+    v, x, st, it, o = _both_dcop(s21, oracle, ck, via_proto=True)
+    assert v["vdd"] == 1.0 and v["div"] == 0.5 and v["v1"] == -1e-3
+    v, x, st, it, o = _both_dcop(s21, oracle, Ckt().R("r1", "1", "0", 1e-3).C("c1", "1", GND, 1e-9).V("v1", "0", GND, 1.0))
+    assert x.tolist() == [1.0, 1.0, 0.0]
+    v, x, st, it, o = _both_dcop(s21, oracle, Ckt().C("c1", "i", "o", 1e-9).R("r1", "o", GND, 1e-3).V("v1", "i", GND, 1.0))
+    assert x.tolist() == [1.0, 0.0, 0.0]
+    v, x, st, it, o = _both_dcop(s21, oracle, Ckt().R("r1", "a", GND, 1e-3))
+    assert x.tolist() == [0.0] and it == 0
+
+
+DCOP = [
+    ("mos0_nchar", lambda: cc.add_mos0_defaults(Ckt(signals=["g", "d"])).M("m", "nmos", "default", d="d", g="g", s=GND, b=GND)
+        .V("v1", "g", GND, 1.0).V("v2", "d", GND, 1.0)),
+    ("mos0_diode_swapped", lambda: cc.add_mos0_defaults(Ckt()).I("i1", "0", GND, -5e-3).M("m", "pmos", "", d=GND, g="0", s="0", b=GND)),
+    ("mos1_op", lambda: cc.add_mos1_defaults(Ckt()).M("m", "default", "default", d="0", g="0", s=GND, b=GND).V("v1", "0", GND, 1.0)),
+    ("mos1_inv", lambda: cc.cmos_inv(cc.add_mos1_defaults)),
+    ("mos1_ro3", lambda: cc.cmos_ro3(cc.add_mos1_defaults)),
+    ("diffpair", cc.diffpair),
+    ("diode_v", lambda: cc.add_diode_defaults(Ckt(signals=["p"])).D("dd", "p", GND, "default", "default").V("vin", "p", GND, 0.7)),
+    ("diode_i", lambda: cc.add_diode_defaults(Ckt(signals=["p"])).D("dd", "p", GND, "default", "default").I("i1", "p", GND, 5.7e-3)),
+    ("diode_rs_bv", lambda: Ckt(signals=["p"]).define("diodemodel", "default", rs=10.0, bv=5.0, cj0=1e-12).define("diodeinst", "default", area=2.0)
+        .D("dd", "p", GND, "default", "default").V("vin", "p", GND, -6.0)),
+    ("mos1_rd_rs", lambda: Ckt().define("mos1model", "n", 0, rd=10.0, rs=5.0, vt0=0.4, kp=1e-4).define("mos1inst", "i")
+        .M("m", "n", "i", d="d", g="g", s=GND, b=GND).V("vg", "g", GND, 1.0).V("vd", "d", GND, 1.0)),
+]
+
+
+@pytest.mark.parametrize("name,build", DCOP, ids=[d[0] for d in DCOP])
+def test_dcop_matches_oracle(s21, oracle, name, build):
+    v, x, st, it, o = _both_dcop(s21, oracle, build())
+    assert st == 0
+    assert rel_err(x, o.data[0], floor=1e-9) <= 1e-9
+    assert it == o.solves
+
+
+def test_dcop_bytes_api(s21):
+    """Op::call_bytes drop-in: the reference's Python-binding test (spice21py/tests/test_spice21.py:21-29)."""
+    c = s21.circuit([s21.Resistor(p="1", g=1e-3), s21.Capacitor(p="1"), s21.Isrc(p="1", dc=1e-3)])
+    res = s21.dcop(s21.protos.Op(ckt=c))
+    assert isinstance(res, dict) and res["1"] == 1.0
+    res = s21.tran(c)  # test_spice21.py:42-50: default TranOptions -> the t=0 point only
+    assert res["1"] == [1.0]
+
+
+def test_dcop_options(s21, oracle):
+    ck = cc.add_diode_defaults(Ckt(signals=["p"])).D("dd", "p", GND, "default", "default").V("vin", "p", GND, 0.65)
+    opts = {"temp": 350.0, "gmin": 1e-10}
+    v, x, st, it, o = _both_dcop(s21, oracle, ck, opts=opts)
+    assert st == 0 and rel_err(x, o.data[0], floor=1e-9) <= 1e-9
+
+
+def test_pivot_order_from_device_values(s21, oracle):
+    """The symbolic phase runs on values probed on the GPU: the resulting order/fill equals the reference's."""
+    for ck, ic in ((cc.cmos_ro3(cc.add_mos1_defaults), {"1": 0.0}), (cc.diffpair(), None)):
+        o = oracle.Circuit(ck.to_text()).structure(ic=ic)
+        b = s21.Batch(ck.to_s21().elaborate(ic=ic), 1)
+        b.dcop()
+        p = b.pivot_order()
+        assert np.array_equal(p["row_i2e"], o["row_i2e"]) and np.array_equal(p["col_i2e"], o["col_i2e"])
+        assert set(zip(p["lu_row"].tolist(), p["lu_col"].tolist(), p["lu_fill"].tolist())) == \
+            set(zip(o["lu_row"].tolist(), o["lu_col"].tolist(), o["lu_fill"].tolist()))
+
+
+def test_monte_carlo_dcop_matches_oracle(s21, oracle):
+    """BASELINE config 2 at a size the oracle finishes in well under a second."""
+    B = 512
+    ck, ovr = cc.diffpair(), cc.diffpair_mc(512)
+    o = oracle.Circuit(ck.to_text()).batch(0, B, overrides=ovr, nthreads=4)
+    b = s21.Batch(ck.to_s21().elaborate(), B)
+    for k, v in ovr.items():
+        b.override(k, v)
+    x, st, it = b.dcop()
+    assert np.all(st == 0) and np.all(o["status"] == 0)
+    assert rel_err(x, o["x"], floor=1e-9) <= 1e-9
+    assert np.mean(it == o["iters"]) >= 0.99
+    # warm restart: a second dcop from the converged point needs no linear solve (analysis.rs:188-194)
+    x2, st2, it2 = b.dcop()
+    assert np.all(st2 == 0) and np.array_equal(it2, it) and np.array_equal(x2, x)
+    b.reset()
+    x3, st3, it3 = b.dcop()
+    assert np.array_equal(x3, x) and np.array_equal(it3, it)  # deterministic
+
+
+def test_monte_carlo_dcop_full_size_properties(s21):
+    """BASELINE config 2 at full size (8192 instances): size-independent properties of the solution."""
+    B = 8192
+    ck, ovr = cc.diffpair(), cc.diffpair_mc(8192)
+    c = ck.to_s21().elaborate()
+    b = s21.Batch(c, B)
+    for k, v in ovr.items():
+        b.override(k, v)
+    x, st, it = b.dcop()
+    assert np.all(st == 0)
+    n = {name: k for k, name in enumerate(c.names)}
+    # forced nodes are exact; KCL at the supply: i(vdd) = -(g1 (vdd - on) + g2 (vdd - op)); tail current splits
+    assert np.all(x[:, n["vdd"]] == 1.8) and np.all(x[:, n["inp"]] == 0.9)
+    i_sup = ovr["R:r1:g"] * (1.8 - x[:, n["on"]]) + ovr["R:r2:g"] * (1.8 - x[:, n["op"]])
+    assert np.max(np.abs(i_sup + x[:, n["vsup"]])) < 1e-11  # branch current of the supply source
+    assert np.max(np.abs(i_sup - 20e-6)) < 1e-9  # all of the tail current comes from the supply
+    assert np.all(it >= 2) and np.all(it <= 100)
+    # permutation equivariance: solving a shuffled batch gives the shuffled solution, bit for bit
+    perm = np.random.default_rng(0).permutation(B)
+    b2 = s21.Batch(c, B)
+    for k, v in ovr.items():
+        b2.override(k, v[perm])
+    x2, st2, it2 = b2.dcop()
+    assert np.array_equal(x2, x[perm]) and np.array_equal(it2, it[perm])
+
+
+def test_per_instance_failure_is_contained(s21):
+    """One non-converging Monte-Carlo sample must not take the batch down (per-instance status vector)."""
+    B = 64
+    ck = cc.diffpair()
+    b = s21.Batch(ck.to_s21().elaborate(), B)
+    g = np.full(B, 5e-5)
+    g[7] = np.nan
+    b.override("R:r1:g", g)
+    x, st, it = b.dcop()
+    assert st[7] != 0 and np.all(np.delete(st, 7) == 0)
+
+
+def test_singular_matrix_status(s21, oracle):
+    ck = Ckt().R("r1", "a", "b", 1e-3).C("c1", "b", GND, 1e-9)  # no DC path anywhere: A is singular
+    with pytest.raises(oracle.OracleError) as e:
+        oracle.Circuit(ck.to_text()).dcop()
+    x, st, it = s21.Batch(ck.to_s21().elaborate(), 1).dcop()
+    assert st[0] == e.value.status == s21.S21_SINGULAR_MATRIX
+
+
+# ------------------------------------------------------------------------------------------------ ac
+def test_ac_rc_lowpass(s21, oracle):  # spice21py/tests/test_spice21.py:53-70
+    ck = Ckt().R("r1", "inp", "out", 1e-3).C("c1", "out", GND, 1e-9).V("vi", "inp", GND, 1e-3, acm=1.0)
+    res = s21.ac(ck.to_proto(), args=s21.protos.AcOptions(fstart=1, fstop=10**9, npts=90))
+    f = s21.ac_freqs(1, 10**9, 90)
+    assert len(res["inp"]) == 91 and all(v == complex(1.0, 0.0) for v in res["inp"])
+    out = np.array(res["out"])
+    assert np.all(np.diff(np.abs(out)) <= 0)
+    assert np.max(np.abs(out - 1.0 / (1.0 + 2j * np.pi * f * 1e-9 / 1e-3))) < 1e-9
+    o = oracle.Circuit(ck.to_text()).ac(fstart=1, fstop=10**9, npts=90)
+    assert np.max(np.abs(out - o.get("out"))) < 1e-12
+
+
+def test_ac_mos1_common_source(s21, oracle):  # tests.rs:1296-1325 (the reference asserts only "does not error")
+    ck = cc.add_mos1_defaults(Ckt()).C("c1", "d", GND, 1e-9).M("m", "default", "default", d="d", g="g", s=GND, b=GND)
+    ck.V("v1", "vdd", GND, 1.0).V("vg", "g", GND, 0.7, acm=1.0)
+    c = ck.to_s21().elaborate()
+    f = s21.ac_freqs(1, 10**6, 30)
+    x, st, it = s21.Batch(c, 1).ac(f)
+    o = oracle.Circuit(ck.to_text()).ac(fstart=1, fstop=10**6, npts=30)
+    assert np.all(st == 0) and np.array_equal(f, o.axis)
+    assert np.max(np.abs(x - o.data)) <= 1e-9 * max(1.0, np.max(np.abs(o.data)))
+    x0, _, _ = s21.Batch(c, 1).ac(np.array([0.0]))  # AcOptions::default -> a single point at f = 0 (tests.rs:1246)
+    assert x0.shape == (1, c.n_vars)
+
+
+def test_ac_unsupported(s21):
+    c = Ckt().R("r1", "a", GND, 1e-3).I("i1", "a", GND, 1e-3).to_s21().elaborate()
+    with pytest.raises(s21.Spice21Error) as e:
+        s21.Batch(c, 1).ac(np.array([1.0, 10.0]))
+    assert e.value.status == s21.S21_UNSUPPORTED

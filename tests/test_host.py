@@ -1,0 +1,153 @@
+"""Host logic of the product, no GPU needed: the C-ABI library loads and exports every declared symbol, the protobuf
+decoder and the builder produce the reference's variable numbering and stamp map, and the symbolic phase picks the
+reference's pivot order and fill pattern integer for integer (checked against the oracle)."""
+import re
+
+import numpy as np
+import pytest
+
+import circuits as cc
+from circuits import GND, Ckt
+
+
+def test_abi_symbols_match_header(s21):
+    import os
+    hdr = open(os.path.join(os.path.dirname(s21.__file__), "..", "include", "spice21cu.h")).read()
+    declared = sorted(set(re.findall(r"\b(s21_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared == sorted(s21.ABI_SYMBOLS)
+    for sym in declared:
+        assert hasattr(s21.lib(), sym), sym
+
+
+def test_no_cpu_fallback(s21):
+    """Without a CUDA device the compute entry points must fail loudly (never fall back to a CPU path)."""
+    if s21.cuda_device_count() > 0:
+        pytest.skip("a GPU is present")
+    c = Ckt(signals=["vdd"]).I("i1", "vdd", GND, 1e-3).R("r1", "vdd", GND, 1e-3).to_s21().elaborate()
+    with pytest.raises(s21.Spice21Error) as e:
+        s21.Batch(c, 4)
+    assert e.value.status == s21.S21_CUDA_ERROR
+    with pytest.raises(s21.Spice21Error) as e:
+        s21.dcop(Ckt(signals=["vdd"]).I("i1", "vdd", GND, 1e-3).R("r1", "vdd", GND, 1e-3).to_proto())
+    assert e.value.status == s21.S21_CUDA_ERROR
+
+
+def test_product_does_not_touch_oracle():
+    import os
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "spice21_b200")
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".hpp", ".h", ".cu", ".cuh", "Makefile")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle/" not in txt and "pyoracle" not in txt and "liboracle" not in txt, os.path.join(dirpath, f)
+
+
+CASES = [
+    ("cmos_ro3_mos1", lambda: cc.cmos_ro3(cc.add_mos1_defaults), {"1": 0.0}, True),
+    ("cmos_ro3_mos0", lambda: cc.cmos_ro3(cc.add_mos0_defaults), {"1": 0.0}, False),
+    ("nmos_ro3", lambda: cc.nmos_ro3(cc.add_mos1_defaults), {"1": 0.0}, True),
+    ("pmos_ro3", lambda: cc.pmos_ro3(cc.add_mos1_defaults), {"1": 0.0}, True),
+    ("cmos_inv", lambda: cc.cmos_inv(cc.add_mos1_defaults), None, True),
+    ("diffpair", cc.diffpair, None, True),
+    ("diode", lambda: cc.add_diode_defaults(Ckt(signals=["p"])).D("dd", "p", GND, "default", "default").V("vin", "p", GND, 0.7), None, True),
+    ("diode_rs", lambda: Ckt(signals=["p"]).define("diodemodel", "default", rs=10.0, bv=5.0, cj0=1e-12).define("diodeinst", "default", area=2.0)
+        .D("dd", "p", GND, "default", "default").V("vin", "p", GND, 0.7), None, True),
+    ("mos1_rd_rs", lambda: Ckt().define("mos1model", "n", 0, rd=10.0, rs=5.0, vt0=0.4).define("mos1inst", "i")
+        .M("m", "n", "i", d="d", g="g", s=GND, b=GND).V("vg", "g", GND, 1.0).V("vd", "d", GND, 1.0), None, True),
+]
+
+
+@pytest.mark.parametrize("name,build,ic,protoable", CASES, ids=[c[0] for c in CASES])
+def test_numbering_and_stamp_map(s21, oracle, name, build, ic, protoable):
+    """Variable order (elab.rs:244-265) and element ids (Matrix::make in component order) are bit-exact."""
+    ck = build()
+    o = oracle.Circuit(ck.to_text()).structure(ic=ic)
+    for via in ([False, True] if protoable else [False]):
+        c = ck.to_s21(via_proto=via).elaborate(ic=ic)
+        sm = c.stamp_map()
+        assert c.names == o["names"]
+        assert np.array_equal(sm["elem_row"], o["elem_row"]) and np.array_equal(sm["elem_col"], o["elem_col"])
+        assert np.array_equal(sm["dev_off"], o["comp_off"]) and np.array_equal(sm["dev_elems"], o["comp_matps"])
+
+
+def _same_plan(a, b):
+    if a["status"] != b["status"]:
+        return False
+    if a["status"] != 0:
+        return True
+    return (np.array_equal(a["row_i2e"], b["row_i2e"]) and np.array_equal(a["col_i2e"], b["col_i2e"]) and
+            set(zip(a["lu_row"].tolist(), a["lu_col"].tolist(), a["lu_fill"].tolist())) ==
+            set(zip(b["lu_row"].tolist(), b["lu_col"].tolist(), b["lu_fill"].tolist())))
+
+
+@pytest.mark.parametrize("name,build,ic,protoable", CASES, ids=[c[0] for c in CASES])
+def test_pivot_order_on_circuit_matrices(s21, oracle, name, build, ic, protoable):
+    """Symbolic phase == the reference's first factorisation (Markowitz order + fill), on the first-iteration matrix."""
+    o = oracle.Circuit(build().to_text()).structure(ic=ic)
+    sy = s21.symbolic(o["n_vars"], o["elem_row"], o["elem_col"], o["a0"])
+    if len(o["row_i2e"]) == 0:
+        assert sy["status"] != 0
+        return
+    assert sy["status"] == 0
+    assert np.array_equal(sy["row_i2e"], o["row_i2e"]) and np.array_equal(sy["col_i2e"], o["col_i2e"])
+    assert set(zip(sy["lu_row"].tolist(), sy["lu_col"].tolist(), sy["lu_fill"].tolist())) == \
+        set(zip(o["lu_row"].tolist(), o["lu_col"].tolist(), o["lu_fill"].tolist()))
+
+
+def test_pivot_order_random_matrices(s21, oracle):
+    """Random sparse matrices incl. missing diagonals, structural zeros, ties and complex values."""
+    rng = np.random.default_rng(21)
+    for trial in range(400):
+        n = int(rng.integers(2, 40))
+        mask = rng.random((n, n)) < rng.uniform(0.05, 0.5)
+        if rng.random() < 0.7:
+            mask |= np.eye(n, dtype=bool)
+        if rng.random() < 0.3:
+            mask[int(rng.integers(0, n)), int(rng.integers(0, n))] = False
+        mask[n - 1, int(rng.integers(0, n))] = True  # the reference sizes the matrix by its elements
+        mask[int(rng.integers(0, n)), n - 1] = True
+        r, c = np.nonzero(mask)
+        perm = rng.permutation(len(r))
+        r, c = r[perm], c[perm]
+        cplx = rng.random() < 0.3
+        v = rng.standard_normal(len(r)) * 10.0 ** rng.integers(-6, 3, len(r))
+        if cplx:
+            v = v + 1j * rng.standard_normal(len(r))
+        if rng.random() < 0.3:
+            v = np.round(v.real) + (1j * np.round(v.imag) if cplx else 0)
+        assert _same_plan(oracle.lu_order(n, r, c, v), s21.symbolic(n, r, c, v)), trial
+
+
+def test_proto_decode_errors(s21):
+    with pytest.raises(s21.Spice21Error) as e:
+        s21.Circuit(b"\x0a\xff\xff\xff\xff\x0f")  # truncated length-delimited field
+    assert e.value.status == s21.S21_DECODE_ERROR
+    with pytest.raises(s21.Spice21Error) as e:  # "No Circuit Provided" (proto.rs:62)
+        s21._dcop(b"")
+    assert "No Circuit Provided" in e.value.desc
+
+
+def test_invalid_circuits(s21):
+    c = cc.add_mos1_defaults(Ckt()).M("m", "nosuchmodel", "default", d="d", g="g", s=GND, b=GND).to_s21()
+    with pytest.raises(s21.Spice21Error) as e:  # elab.rs:167 panics "Model not defined"
+        c.elaborate()
+    assert e.value.status == s21.S21_INVALID_CIRCUIT and "Model not defined" in e.value.desc
+    c = Ckt()
+    c.module("m", ["a"]).R("r", "a", "undeclared", 1.0)
+    c.R("r0", "x", GND, 1.0).X("x1", "m", a="x")
+    with pytest.raises(s21.Spice21Error) as e:  # elab.rs:49: nodes inside modules must pre-exist
+        c.to_s21().elaborate()
+    assert e.value.status == s21.S21_INVALID_CIRCUIT
+
+
+def test_time_and_frequency_axes(s21, oracle):
+    """Point counts are decided by the reference's floating-point accumulation (analysis.rs:553-570, 791-819)."""
+    assert s21.lib().s21_tran_num_points(1e-11, 1e-8) == 1001
+    assert s21.lib().s21_tran_num_points(1e-15, 1e-12) == 1000
+    assert s21.lib().s21_tran_num_points(1e-10, 3e-7) == 3000
+    assert s21.lib().s21_tran_num_points(0.0, 0.0) == 1
+    f = s21.ac_freqs(1, 10**9, 90)
+    c = Ckt().R("r1", "inp", "out", 1e-3).C("c1", "out", GND, 1e-9).V("vi", "inp", GND, 1e-3, acm=1.0)
+    assert np.array_equal(f, oracle.Circuit(c.to_text()).ac(fstart=1, fstop=10**9, npts=90).axis)
+    assert len(s21.ac_freqs(1, 10**10, 99999)) == 100000
+    assert len(s21.ac_freqs(0, 0, 0)) == 1

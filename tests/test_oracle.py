@@ -1,0 +1,148 @@
+"""The oracle (oracle/, CPU restatement of the reference) against everything the reference's own tests pin for the
+hot path: sparse21 unit vectors, dcop known answers, and the golden transient waveforms."""
+import numpy as np
+import pytest
+
+import circuits as cc
+from circuits import GND, Ckt
+from conftest import golden
+
+
+def test_sparse21_unit_vectors(oracle):
+    # spice21/src/sparse21/mod.rs:1165-1526 restated in oracle_capi.cpp::orc_sparse21_selftest
+    rc, msg = oracle.sparse21_selftest()
+    assert rc == 0, msg
+
+
+@pytest.mark.parametrize("builder,defaults,fixture,tstep,tstop", [
+    (cc.cmos_ro3, cc.add_mos1_defaults, "test_mos1_cmos_ro_tran", 1e-11, 1e-8),   # tests.rs:932-947  (BASELINE config 1)
+    (cc.cmos_ro3, cc.add_mos0_defaults, "test_mos0_cmos_ro_tran", 1e-15, 1e-12),  # tests.rs:773-790
+    (cc.nmos_ro3, cc.add_mos1_defaults, "test_mos1_nmos_ro_tran", 1e-11, 1e-8),   # tests.rs:993-1008
+    (cc.pmos_ro3, cc.add_mos1_defaults, "test_mos1_pmos_ro_tran", 1e-11, 1e-8),   # tests.rs:1036-1051
+])
+def test_golden_waveforms(oracle, builder, defaults, fixture, tstep, tstop):
+    g = golden(fixture)
+    r = oracle.Circuit(builder(defaults).to_text()).tran(tstep, tstop, ic={"1": 0.0})
+    assert r.data.shape[0] == len(g["time"])  # the float-accumulated time loop decides the point count
+    assert np.array_equal(r.axis, g["time"])
+    assert set(r.names) | {"time"} == set(g.keys())
+    for k, name in enumerate(r.names):
+        # reference tolerance is 1e-6 abs (tests.rs:788); the restatement is in fact bit-identical on glibc
+        assert np.max(np.abs(r.data[:, k] - g[name])) <= 1e-6, name
+
+
+def _dcop(oracle, ckt, **kw):
+    r = oracle.Circuit(ckt.to_text()).dcop(**kw)
+    return dict(zip(r.names, r.data[0])), r
+
+
+def test_dcop_r_only(oracle):  # tests.rs:22-27
+    v, _ = _dcop(oracle, Ckt().R("r1", "a", GND, 1e-3))
+    assert v == {"a": 0.0}
+
+
+def test_dcop_i_r(oracle):  # tests.rs:30-44
+    v, _ = _dcop(oracle, Ckt(signals=["vdd"]).I("i1", "vdd", GND, 1e-3).R("r1", "vdd", GND, 1e-3))
+    assert v["vdd"] == 1.0
+
+
+def test_dcop_v_r_r_exact(oracle):  # tests.rs:66-83 — exact equality in the reference
+    c = Ckt(signals=["vdd", "div"]).V("v1", "vdd", GND, 1.0).R("r1", "vdd", "div", 2e-3).R("r2", GND, "div", 2e-3)
+    v, _ = _dcop(oracle, c)
+    assert v["vdd"] == 1.0 and v["div"] == 0.5 and v["v1"] == -1e-3
+
+
+def test_dcop_diode_bias_consistency(oracle):  # tests.rs:87-133
+    c = cc.add_diode_defaults(Ckt(signals=["p"])).D("dd", "p", GND, "default", "default").V("vin", "p", GND, 0.70)
+    v, _ = _dcop(oracle, c)
+    i = abs(v["vin"])
+    assert 1e-3 < i < 100e-3
+    c2 = cc.add_diode_defaults(Ckt(signals=["p"])).D("dd", "p", GND, "default", "default").I("i1", "p", GND, i)
+    v2, _ = _dcop(oracle, c2)
+    assert abs(v2["p"] - 0.70) < 1e-3
+
+
+@pytest.mark.parametrize("model,vdc,isign", [("nmos", 1.0, -1), ("pmos", -1.0, +1)])
+def test_dcop_mos0_char(oracle, model, vdc, isign):  # tests.rs:137-180
+    c = cc.add_mos0_defaults(Ckt(signals=["g", "d"])).M("m", model, "default", d="d", g="g", s=GND, b=GND)
+    c.V("v1", "g", GND, vdc).V("v2", "d", GND, vdc)
+    v, _ = _dcop(oracle, c)
+    assert v["g"] == vdc and v["d"] == vdc and v["v1"] == 0.0
+    assert abs(v["v2"] - isign * 14.1e-3) < 1e-4
+
+
+@pytest.mark.parametrize("model,idc,d,s,expect", [
+    ("nmos", 5e-3, "0", GND, 0.697), ("nmos", 5e-3, GND, "0", 0.697),      # tests.rs:183-204, 237-258
+    ("pmos", -5e-3, "0", GND, -0.697), ("pmos", -5e-3, GND, "0", -0.697),  # tests.rs:261-281, 315-335
+])
+def test_dcop_mos0_diode_connected(oracle, model, idc, d, s, expect):
+    c = cc.add_mos0_defaults(Ckt()).I("i1", "0", GND, idc).M("m", model, "", d=d, g="0", s=s, b=GND)
+    v, _ = _dcop(oracle, c)
+    assert abs(v["0"] - expect) < 1e-3
+
+
+def test_dcop_mos0_series_inverters(oracle):  # tests.rs:558-666
+    c = cc.add_mos0_defaults(Ckt())
+    for k in range(5):
+        c.R("r1", str(k), GND, 1e-9)
+    for k in range(4):
+        c.M(f"p{k + 1}", "pmos", "", d=str(k + 1), g=str(k), s="0", b="0")
+        c.M(f"n{k + 1}", "nmos", "", d=str(k + 1), g=str(k), s=GND, b=GND)
+    c.V("v1", "0", GND, 1.0)
+    _, r = _dcop(oracle, c)
+    x = r.data[0]
+    assert x[0] == 1.0 and abs(x[1]) < 1e-3 and abs(x[2] - 1.0) < 1e-3 and abs(x[3]) < 1e-3 and abs(x[4] - 1.0) < 1e-3 and abs(x[5]) < 1e-6
+
+
+def test_dcop_rc_exact(oracle):  # tests.rs:670-692
+    _, r = _dcop(oracle, Ckt().R("r1", "1", "0", 1e-3).C("c1", "1", GND, 1e-9).V("v1", "0", GND, 1.0))
+    assert r.data[0].tolist() == [1.0, 1.0, 0.0]
+    _, r = _dcop(oracle, Ckt().C("c1", "i", "o", 1e-9).R("r1", "o", GND, 1e-3).V("v1", "i", GND, 1.0))
+    assert r.data[0].tolist() == [1.0, 0.0, 0.0]
+
+
+def test_tran_rc_step(oracle):  # tests.rs:695-717
+    c = Ckt().V("v1", "inp", GND, 1.0).R("r1", "inp", "out", 1e-3).C("c1", "out", GND, 1e-9)
+    r = oracle.Circuit(c.to_text()).tran(10e-9, 10e-6, ic={"out": 0.0})
+    inp, out = r.get("inp"), r.get("out")
+    assert np.all(inp == 1.0)
+    assert abs(out[0]) < 1e-3 and abs(out[-1] - 1.0) < 1e-3 and np.all(np.diff(out) > 0)
+
+
+def test_mos1_op_and_inverter(oracle):  # tests.rs:792-815, 851-866, 915-929
+    c = cc.add_mos1_defaults(Ckt()).M("m", "default", "default", d="0", g="0", s=GND, b=GND).V("v1", "0", GND, 1.0)
+    _, r = _dcop(oracle, c)
+    assert r.data[0][0] == 1.0 and -1e-3 < r.data[0][1] < 0.0
+    v, _ = _dcop(oracle, cc.cmos_inv(cc.add_mos1_defaults))
+    assert v["vdd"] == 1.0 and v["vss"] == 0.0 and v["inp"] == 0.0 and abs(v["out"] - 1.0) < 1e-3
+    assert all(abs(v[k]) < 1e-6 for k in ("v1", "v2", "v3"))
+    v, _ = _dcop(oracle, cc.cmos_ro3(cc.add_mos1_defaults))
+    assert v["vdd"] == 1.0 and all(0.45 < v[k] < 0.55 for k in "123")
+
+
+def test_hier_elaboration_counts(oracle):  # tests.rs:1380-1409: 11 comps / 5 vars after flattening
+    c = Ckt()
+    m = c.module("good_luck", ["inp", "out", "vss"])
+    m.R("r1", "inp", "out", 0.001).C("r2", "out", "vss", 0.001)
+    c.R("r0", "inp", GND, 0.001).R("rt", "out", "out2", 0.001).C("ct", "out2", GND, 0.001).C("ct", "out3", GND, 0.001).C("ct", "out4", GND, 0.001)
+    c.X("x1", "good_luck", inp="inp", out="out", vss=GND).X("x2", "good_luck", inp="out2", out="out3", vss=GND)
+    c.X("x3", "good_luck", inp="out3", out="out4", vss=GND)
+    st = oracle.Circuit(c.to_text()).structure()
+    assert st["n_vars"] == 5 and len(st["comp_kinds"]) == 11
+
+
+def test_ac_rc_lowpass(oracle):  # spice21py/tests/test_spice21.py:53-70 + analytic check (AC values are unpinned by the reference)
+    c = Ckt().R("r1", "inp", "out", 1e-3).C("c1", "out", GND, 1e-9).V("vi", "inp", GND, 1e-3, acm=1.0)
+    r = oracle.Circuit(c.to_text()).ac(fstart=1, fstop=10**9, npts=90)
+    assert r.data.shape[0] == 91  # end-inclusive sweep: npts + 1 points (analysis.rs:797-819)
+    assert np.all(r.get("inp") == 1.0 + 0j)
+    h = 1.0 / (1.0 + 2j * np.pi * r.axis * 1e-9 / 1e-3)
+    assert np.max(np.abs(r.get("out") - h)) < 1e-9
+    assert np.all(np.diff(np.abs(r.get("out"))) <= 0)
+
+
+def test_ac_unsupported_device(oracle):  # comps/mod.rs:86-88: Isrc has no load_ac
+    c = Ckt().R("r1", "a", GND, 1e-3).I("i1", "a", GND, 1e-3)
+    with pytest.raises(oracle.OracleError) as e:
+        oracle.Circuit(c.to_text()).ac(fstart=1, fstop=10, npts=2)
+    assert e.value.status == 6
