@@ -146,7 +146,8 @@ def run_ours(args):
     ovr = cc.diffpair_mc(B, first_instance=rank * B)  # each rank owns its own Monte-Carlo samples
     c = ck.to_s21().elaborate()
     batch = s21.Batch(c, B, device=local)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # a real (non-legacy) stream: the library launches on it, the events below time it
+    torch.cuda.set_stream(stream)
     batch.set_stream(stream.cuda_stream)
     for k, v in ovr.items():
         batch.override(k, v)

@@ -61,7 +61,7 @@ struct SolveCtl {
 
 // All launchers enqueue on `stream` (a cudaStream_t) and return a cudaError_t as int.
 int launch_dcop(const DevTables& d, const PlanTables& p, const WorkTables<double>& w, const NewtonOut& o, const SolveCtl& c, void* stream);
-// OP must already be solved and committed; runs points 1..T-1 of Tran::solve. wave: [T][n_save][B] device (point 0 written too).
+// OP must already be solved and committed; runs points 1..T-1 of Tran::solve. wave: [T][n_save][w.stride] device (point 0 written too).
 int launch_tran(const DevTables& d, const PlanTables& p, const WorkTables<double>& w, const NewtonOut& o, const SolveCtl& c, int T,
                 const int* save_vars, int n_save, double* wave, void* stream);
 int launch_ac(const DevTables& d, const PlanTables& p, const WorkTables<cplx>& w, const NewtonOut& o, const SolveCtl& c, void* stream);

@@ -193,9 +193,7 @@ __device__ int newton_solve(const DevTables& d, const PlanTables& p, const WorkT
       const int en = __ldg(p.rowptr + k + 1);
       T ck = c[(size_t)k * S];
       for (int s = ds + 1; s < en; s++) ck = s_sub(ck, s_mul(c[(size_t)__ldg(p.colidx + s) * S], lu[(size_t)s * S]));
-      const T dv = lu[(size_t)ds * S];
-      if (s_is_zero(dv)) return ST_SINGULAR_;
-      c[(size_t)k * S] = s_div(ck, dv);
+      c[(size_t)k * S] = s_div(ck, lu[(size_t)ds * S]);  // no zero check here in the reference either (mod.rs:978)
     }
     *n_solves += 1;
     // ---- global step limit + update (analysis.rs:197-207 / 283-293); dx[e] = c[col_e2i[e]]
@@ -231,7 +229,7 @@ __global__ void __launch_bounds__(128) k_tran(DevTables d, PlanTables p, WorkTab
                                              const int* save_vars, int n_save, double* wave) {
   const size_t inst = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (inst >= (size_t)ctl.B) return;
-  const size_t B = (size_t)ctl.B;
+  const size_t B = w.stride;  // wave is [T][n_save][stride], instance fastest, like every other per-instance table
   int st = o.status[inst];  // status of the OP solve
   for (int s = 0; s < n_save; s++) wave[(size_t)s * B + inst] = w.x[(size_t)__ldg(save_vars + s) * w.stride + inst];
   int ns = 0, nl = 0;

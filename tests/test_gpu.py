@@ -202,24 +202,35 @@ def test_monte_carlo_dcop_full_size_properties(s21):
     assert np.array_equal(x2, x[perm]) and np.array_equal(it2, it[perm])
 
 
-def test_per_instance_failure_is_contained(s21):
+def test_per_instance_failure_is_contained(s21, oracle):
     """One non-converging Monte-Carlo sample must not take the batch down (per-instance status vector)."""
     B = 64
     ck = cc.diffpair()
     b = s21.Batch(ck.to_s21().elaborate(), B)
-    g = np.full(B, 5e-5)
-    g[7] = np.nan
-    b.override("R:r1:g", g)
+    v = np.full(B, 0.9)
+    v[7] = 500.0  # 1 V per iteration step limit (analysis.rs:197-203): 100 iterations cannot reach 500 V
+    b.override("V:vinp:dc", v)
     x, st, it = b.dcop()
-    assert st[7] != 0 and np.all(np.delete(st, 7) == 0)
+    assert st[7] == s21.S21_CONVERGENCE_FAILED and it[7] == 100 and np.all(np.delete(st, 7) == 0)
+    o = oracle.Circuit(ck.to_text()).batch(0, B, overrides={"V:vinp:dc": v})
+    assert np.array_equal(o["status"], st) and np.array_equal(o["iters"], it)
 
 
 def test_singular_matrix_status(s21, oracle):
-    ck = Ckt().R("r1", "a", "b", 1e-3).C("c1", "b", GND, 1e-9)  # no DC path anywhere: A is singular
+    # two voltage sources in parallel: the last pivot position has no element -> "Singular Matrix" (mod.rs:969-972)
+    ck = Ckt().V("v1", "a", GND, 1.0).V("v2", "a", GND, 1.0)
     with pytest.raises(oracle.OracleError) as e:
         oracle.Circuit(ck.to_text()).dcop()
     x, st, it = s21.Batch(ck.to_s21().elaborate(), 1).dcop()
     assert st[0] == e.value.status == s21.S21_SINGULAR_MATRIX
+    with pytest.raises(s21.Spice21Error) as e2:  # and through the bytes API it is the reference's error string
+        s21.dcop(ck.to_proto())
+    assert e2.value.desc == "Singular Matrix"
+    # a numerically singular matrix is NOT an error in the reference (0/0 in back-substitution): NaNs, status OK
+    ck = Ckt().R("r1", "a", "b", 1e-3).C("c1", "b", GND, 1e-9)
+    o = oracle.Circuit(ck.to_text()).dcop()
+    x, st, it = s21.Batch(ck.to_s21().elaborate(), 1).dcop()
+    assert st[0] == 0 and np.array_equal(np.isnan(x[0]), np.isnan(o.data[0]))
 
 
 # ------------------------------------------------------------------------------------------------ ac
