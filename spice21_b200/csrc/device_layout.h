@@ -35,7 +35,9 @@ enum { DS_VD = 0, DS_CHARGE, DS_N };
 enum { M0_D = 0, M0_G, M0_S, M0_EDD, M0_ESS, M0_EDS, M0_ESD, M0_EDG, M0_ESG, M0_NI };
 enum { M0P_P = 0, M0P_N };
 // ---- Mos1 (comps/mos.rs:625-969): itab [D,G,S,B,DP,SP, e[6][6]] with e indexed by the reference's Mos1Var values.
-enum { M1_D = 0, M1_G = 1, M1_S = 2, M1_B = 3, M1_DP = 4, M1_SP = 5, M1_E0 = 6, M1_NI = 6 + 36 };
+enum { M1_D = 0, M1_G = 1, M1_S = 2, M1_B = 3, M1_DP = 4, M1_SP = 5, M1_E0 = 6, M1_NI = 6 + 36,
+       M1_DUP_GDR = M1_NI,  // staging slot of load_ac's second (G,dr) push (mos.rs:954)
+       M1_NSTAGE = M1_NI + 1 };
 enum {
   M1P_P = 0, M1P_VT0T, M1P_PHIT, M1P_GAMMA, M1P_BETA, M1P_LAMBDA, M1P_VTHERM, M1P_COX, M1P_CGSOV, M1P_CGDOV, M1P_CGBOV, M1P_GRD,
   M1P_GRS, M1P_MJ, M1P_MJSW,

@@ -11,6 +11,7 @@
 
 #include "../kernels/engine.hpp"
 #include "flatten.hpp"
+#include "staging.hpp"
 #include "symbolic.hpp"
 
 namespace s21 {
@@ -61,6 +62,39 @@ struct PlanDevice {
   Plan host;
   bool valid = false;
   DBuf<int> row_i2e, col_i2e, col_e2i, rowptr, colidx, diag_slot, l_off, l_slot, l_row, upd_off, upd_t, upd_u, upd_l, itab;
+  // cooperative kernel: every shared index table packed into one allocation ("arena") so that a CTA can bring all of
+  // them into shared memory with a single TMA bulk copy. Offsets are in ints, each table 16-byte aligned.
+  DBuf<int> arena;
+  size_t arena_bytes = 0;
+  struct ArenaOffsets {
+    size_t type, itab_off, par_off, state_off, itab, pcode, row_i2e, col_i2e, col_e2i, rowptr, colidx, diag_slot, stage_off, eval_order,
+        asm_off, asm_src, lu_lvl_off, lu_t, lu_u, lu_l, fw_lvl_off, fw_k, fw_row, fw_slot, bw_lvl_off, bw_row;
+  } ao;
+  DevTables coop_dev(int n_dev, const double* pval, int n_state) const {
+    DevTables d;
+    d.n_dev = n_dev; d.n_state = n_state; d.pval = pval;
+    d.type = arena.p + ao.type; d.itab_off = arena.p + ao.itab_off; d.par_off = arena.p + ao.par_off; d.state_off = arena.p + ao.state_off;
+    d.itab = arena.p + ao.itab; d.pcode = arena.p + ao.pcode;
+    return d;
+  }
+  PlanTables coop_plan() const {
+    PlanTables t;
+    t.N = host.N; t.nnz = host.nnzLU;
+    t.row_i2e = arena.p + ao.row_i2e; t.col_i2e = arena.p + ao.col_i2e; t.col_e2i = arena.p + ao.col_e2i;
+    t.rowptr = arena.p + ao.rowptr; t.colidx = arena.p + ao.colidx; t.diag_slot = arena.p + ao.diag_slot;
+    t.l_off = t.l_slot = t.l_row = t.upd_off = t.upd_t = t.upd_u = t.upd_l = nullptr;
+    return t;
+  }
+  CoopTables coop() const {
+    CoopTables c;
+    c.n_stage = host.n_stage; c.stage_off = arena.p + ao.stage_off; c.eval_order = arena.p + ao.eval_order;
+    c.asm_off = arena.p + ao.asm_off; c.asm_src = arena.p + ao.asm_src;
+    c.n_lu_lvl = (int)host.lu_lvl_off.size() - 1; c.n_fw_lvl = (int)host.fw_lvl_off.size() - 1; c.n_bw_lvl = (int)host.bw_lvl_off.size() - 1;
+    c.lu_lvl_off = arena.p + ao.lu_lvl_off; c.lu_t = arena.p + ao.lu_t; c.lu_u = arena.p + ao.lu_u; c.lu_l = arena.p + ao.lu_l;
+    c.fw_lvl_off = arena.p + ao.fw_lvl_off; c.fw_k = arena.p + ao.fw_k; c.fw_row = arena.p + ao.fw_row; c.fw_slot = arena.p + ao.fw_slot;
+    c.bw_lvl_off = arena.p + ao.bw_lvl_off; c.bw_row = arena.p + ao.bw_row;
+    return c;
+  }
   PlanTables tables() const {
     PlanTables t;
     t.N = host.N; t.nnz = host.nnzLU;
@@ -98,6 +132,11 @@ class Batch {
     for (const FlatDev& d : flat_.devs) { type.push_back(d.type); ioff.push_back(d.itab_off); poff.push_back(d.par_off); soff.push_back(d.state_off); }
     d_type_.upload(type, stream_); d_ioff_.upload(ioff, stream_); d_poff_.upload(poff, stream_); d_soff_.upload(soff, stream_);
     d_itab_raw_.upload(flat_.itab, stream_);
+    si_ = make_stage_info(flat_);
+    d_stage_off_.upload(si_.stage_off, stream_);
+    d_eval_order_.upload(si_.eval_order, stream_);
+    if (const char* k = std::getenv("S21_KERNEL")) use_coop_ = std::string(k) != "direct";
+    max_smem_ = (size_t)coop_max_smem_optin(device_);
     // workspace
     x_.alloc((size_t)N * Bs_); rhs_.alloc((size_t)N * Bs_); c_.alloc((size_t)N * Bs_);
     st_op_.alloc((size_t)std::max(flat_.n_state, 1) * Bs_); st_guess_.alloc((size_t)std::max(flat_.n_state, 1) * Bs_);
@@ -208,9 +247,18 @@ class Batch {
     d_wave_.alloc((size_t)T * n_save * Bs_);
     DevTables dt = dev_tables(tran_plan_.itab.p);
     SolveCtl ctl = make_ctl(AN_TRAN, tstep);
-    int rc = launch_tran(dt, tran_plan_.tables(), work(), out(), ctl, T, d_save_.p, (int)n_save, d_wave_.p, stream_);
+    int rc = 0;
+    if (tran_plan_.host.status != ST_OK) {
+      throw S21Error(tran_plan_.host.status, status_text(tran_plan_.host.status));
+    } else if (use_coop_) {
+      CoopCfg cfg = coop_cfg(tran_plan_, B_, 1);
+      rc = launch_coop_tran(coop_dev(tran_plan_), tran_plan_.coop_plan(), tran_plan_.coop(), work(), stage_for(cfg, tran_plan_.host),
+                            out(), ctl, cfg, T, d_save_.p, (int)n_save, d_wave_.p, stream_);
+    } else {
+      rc = launch_tran(dt, tran_plan_.tables(), work(), out(), ctl, T, d_save_.p, (int)n_save, d_wave_.p, stream_);
+    }
     launches_++;
-    if (rc) throw S21Error(ST_CUDA, std::string("k_tran launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+    if (rc) throw S21Error(ST_CUDA, std::string("tran kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
     S21_CUDA(cudaEventRecord(ev1_, stream_));
     last_plan_ = &tran_plan_;
     if (wave) {
@@ -273,16 +321,24 @@ class Batch {
       S21_CUDA(cudaMemcpyAsync(vals.data(), probe.p, vals.size() * sizeof(cplx), cudaMemcpyDeviceToHost, stream_));
       S21_CUDA(cudaStreamSynchronize(stream_));
       ac_plan_.host = build_plan<cplx>(N, flat_.elem_row, flat_.elem_col, vals.data());
-      upload_plan(ac_plan_);
+      upload_plan(ac_plan_, AN_AC);
     }
     if (ac_plan_.host.status != ST_OK) throw S21Error(ac_plan_.host.status, status_text(ac_plan_.host.status));
     if ((size_t)ac_plan_.host.nnzLU > (size_t)flat_.n_elems()) { zlu_.alloc((size_t)ac_plan_.host.nnzLU * Fs); w.lu = zlu_.p; }
     NewtonOut o;
     o.status = ac_status_.p; o.iters = ac_iters_.p; o.loads = ac_loads_.p;
     DevTables dt = dev_tables(ac_plan_.itab.p);
-    int rc = launch_ac(dt, ac_plan_.tables(), w, o, ctl, stream_);
+    int rc;
+    if (use_coop_) {
+      CoopCfg cfg = coop_cfg(ac_plan_, F, 2);
+      cplx* stage = nullptr;
+      if (cfg.smem_bytes == 0) { zstage_.alloc((size_t)ac_plan_.host.n_stage * Fs); stage = zstage_.p; }
+      rc = launch_coop_ac(coop_dev(ac_plan_), ac_plan_.coop_plan(), ac_plan_.coop(), w, stage, o, ctl, cfg, stream_);
+    } else {
+      rc = launch_ac(dt, ac_plan_.tables(), w, o, ctl, stream_);
+    }
     launches_++;
-    if (rc) throw S21Error(ST_CUDA, "k_ac launch failed");
+    if (rc) throw S21Error(ST_CUDA, std::string("ac kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
     S21_CUDA(cudaEventRecord(ev1_, stream_));
     last_plan_ = &ac_plan_;
     std::vector<cplx> hx((size_t)N * Fs);
@@ -346,6 +402,49 @@ class Batch {
   float last_ms_ = 0.f;
   long long sum_iters_ = 0, sum_loads_ = 0;
 
+  StageInfo si_;
+  DBuf<int> d_stage_off_, d_eval_order_;
+  DBuf<double> d_stage_;
+  DBuf<cplx> zstage_;
+  bool use_coop_ = true;
+  size_t max_smem_ = 0;
+
+  // Launch geometry of the cooperative kernel: the largest instance group per CTA that still leaves >= 2 CTAs per SM
+  // (148 SMs) and whose workspace fits in shared memory; HBM-resident workspace when even one instance does not fit.
+  DevTables coop_dev(const PlanDevice& pd) const { return pd.coop_dev((int)flat_.devs.size(), d_pval_.p, flat_.n_state); }
+  CoopCfg coop_cfg(const PlanDevice& pd, size_t n_inst, int width) const {
+    const Plan& P = pd.host;
+    CoopCfg cfg;
+    cfg.arena = pd.arena.p;
+    cfg.arena_bytes = pd.arena_bytes;
+    auto total = [&](int gi, bool with_arena) {
+      return coop_ctrl_bytes(gi) + (with_arena ? pd.arena_bytes : 0) + coop_work_bytes(P.N, P.nnzLU, P.n_stage, flat_.n_state, gi, width);
+    };
+    int gi = 32;
+    if (const char* e = std::getenv("S21_COOP_GI")) gi = std::max(1, std::min(32, std::atoi(e)));
+    else while (gi > 1 && (n_inst + (size_t)gi - 1) / (size_t)gi < 2 * 148) gi >>= 1;
+    int lg = 0;
+    while ((1 << lg) < gi) lg++;
+    gi = 1 << lg;
+    while (gi > 1 && total(gi, false) > max_smem_) gi >>= 1;
+    cfg.gi = gi;
+    const bool work_fits = total(gi, false) <= max_smem_;
+    cfg.smem_bytes = work_fits ? coop_work_bytes(P.N, P.nnzLU, P.n_stage, flat_.n_state, gi, width) : 0;
+    // the arena rides along in shared memory when it is small next to what the CTA already uses (occupancy first)
+    cfg.arena_in_smem = pd.arena_bytes <= 48 * 1024 && (work_fits ? total(gi, true) : coop_ctrl_bytes(gi) + pd.arena_bytes) <= max_smem_;
+    if (const char* e = std::getenv("S21_COOP_ARENA")) cfg.arena_in_smem = cfg.arena_in_smem && std::atoi(e) != 0;
+    const size_t widest = (size_t)std::max(P.nnzLU + P.N, (int)flat_.devs.size()) * (size_t)gi;
+    cfg.threads = widest <= 64 ? 64 : widest <= 1024 ? 128 : 256;
+    if (const char* e = std::getenv("S21_COOP_THREADS")) cfg.threads = std::max(32, std::min(256, std::atoi(e) / 32 * 32));
+    cfg.threads = std::max(cfg.threads, gi);
+    return cfg;
+  }
+  double* stage_for(const CoopCfg& cfg, const Plan& P) {
+    if (cfg.smem_bytes) return nullptr;
+    d_stage_.alloc((size_t)P.n_stage * Bs_);
+    return d_stage_.p;
+  }
+
   void ensure_lu_rows(size_t rows) {
     if (rows <= lu_rows_) return;
     lu_.alloc(rows * Bs_);
@@ -383,9 +482,16 @@ class Batch {
       return;
     }
     DevTables dt = dev_tables(op_plan_.itab.p);
-    int rc = launch_dcop(dt, op_plan_.tables(), work(), out(), make_ctl(AN_OP, 0.0), stream_);
+    int rc;
+    if (use_coop_) {
+      CoopCfg cfg = coop_cfg(op_plan_, B_, 1);
+      rc = launch_coop_dcop(coop_dev(op_plan_), op_plan_.coop_plan(), op_plan_.coop(), work(), stage_for(cfg, op_plan_.host), out(),
+                            make_ctl(AN_OP, 0.0), cfg, stream_);
+    } else {
+      rc = launch_dcop(dt, op_plan_.tables(), work(), out(), make_ctl(AN_OP, 0.0), stream_);
+    }
     launches_++;
-    if (rc) throw S21Error(ST_CUDA, std::string("k_dcop launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+    if (rc) throw S21Error(ST_CUDA, std::string("dcop kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
   }
   // Symbolic phase for one analysis mode: probe instance 0's first load sweep on the GPU, pivot on the host.
   void ensure_plan(PlanDevice& pd, int mode, double dt) {
@@ -401,11 +507,11 @@ class Batch {
     S21_CUDA(cudaMemcpyAsync(vals.data(), probe.p, vals.size() * sizeof(double), cudaMemcpyDeviceToHost, stream_));
     S21_CUDA(cudaStreamSynchronize(stream_));
     pd.host = build_plan<double>(N, flat_.elem_row, flat_.elem_col, vals.data());
-    upload_plan(pd);
+    upload_plan(pd, mode);
     ensure_lu_rows((size_t)pd.host.nnzLU);
   }
-  void upload_plan(PlanDevice& pd) {
-    const Plan& P = pd.host;
+  void upload_plan(PlanDevice& pd, int mode) {
+    Plan& P = pd.host;
     pd.row_i2e.upload(P.row_i2e, stream_); pd.col_i2e.upload(P.col_i2e, stream_); pd.col_e2i.upload(P.col_e2i, stream_);
     pd.rowptr.upload(P.rowptr, stream_); pd.colidx.upload(P.colidx, stream_); pd.diag_slot.upload(P.diag_slot, stream_);
     pd.l_off.upload(P.l_off, stream_); pd.l_slot.upload(P.l_slot, stream_); pd.l_row.upload(P.l_row, stream_);
@@ -429,6 +535,28 @@ class Batch {
       }
     }
     pd.itab.upload(itab, stream_);
+    if (P.status == ST_OK) {
+      build_gather(flat_, si_, mode, itab, P);
+      std::vector<int> A;
+      auto put = [&](const std::vector<int>& v) {
+        const size_t at = A.size();
+        A.insert(A.end(), v.begin(), v.end());
+        while (A.size() % 4) A.push_back(0);
+        return at;
+      };
+      std::vector<int> type, ioff, poff, soff;
+      for (const FlatDev& d : flat_.devs) { type.push_back(d.type); ioff.push_back(d.itab_off); poff.push_back(d.par_off); soff.push_back(d.state_off); }
+      auto& o = pd.ao;
+      o.type = put(type); o.itab_off = put(ioff); o.par_off = put(poff); o.state_off = put(soff); o.itab = put(itab); o.pcode = put(pcode_h_);
+      o.row_i2e = put(P.row_i2e); o.col_i2e = put(P.col_i2e); o.col_e2i = put(P.col_e2i); o.rowptr = put(P.rowptr); o.colidx = put(P.colidx);
+      o.diag_slot = put(P.diag_slot); o.stage_off = put(si_.stage_off); o.eval_order = put(si_.eval_order);
+      o.asm_off = put(P.asm_off); o.asm_src = put(P.asm_src);
+      o.lu_lvl_off = put(P.lu_lvl_off); o.lu_t = put(P.lu_t); o.lu_u = put(P.lu_u); o.lu_l = put(P.lu_l);
+      o.fw_lvl_off = put(P.fw_lvl_off); o.fw_k = put(P.fw_k); o.fw_row = put(P.fw_row); o.fw_slot = put(P.fw_slot);
+      o.bw_lvl_off = put(P.bw_lvl_off); o.bw_row = put(P.bw_row);
+      pd.arena_bytes = A.size() * sizeof(int);
+      pd.arena.upload(A, stream_);
+    }
     S21_CUDA(cudaStreamSynchronize(stream_));  // host vectors above are temporaries
     pd.valid = true;
   }

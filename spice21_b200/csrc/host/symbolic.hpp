@@ -32,7 +32,91 @@ struct Plan {
   // and one (target, u, l) triple per Schur update. Offsets have N entries + 1.
   std::vector<int> l_off, l_slot, l_row;
   std::vector<int> upd_off, upd_t, upd_u, upd_l;
+  // Level schedule for the cooperative kernel: the same operations, grouped so that every operation of a level is
+  // independent of the others in it (one barrier per level). Within any single value the operations keep the
+  // reference's order (ascending pivot index), so the arithmetic is unchanged.
+  //   LU op j: l < 0 ? lu[t] /= lu[u] : lu[t] -= lu[u] * lu[l]
+  std::vector<int> lu_lvl_off, lu_t, lu_u, lu_l;
+  //   forward op j: c[row] -= c[k] * lu[slot]   (skipped when c[k] == 0, sparse21/mod.rs:949-951)
+  std::vector<int> fw_lvl_off, fw_k, fw_row, fw_slot;
+  //   backward level: rows whose c[k] = (c[k] - sum_j U[k,j] c[j]) / U[k,k] can be formed together
+  std::vector<int> bw_lvl_off, bw_row;
+  // Staged assembly (filled per analysis mode by the batch runtime): target t in [0, nnzLU) is an L+U slot, target
+  // nnzLU + v is rhs[v]; asm_src lists the staging slots to sum, in the reference's accumulation order.
+  std::vector<int> asm_off, asm_src;
+  int n_stage = 0;
 };
+
+// Group operations by dependency level. `lev[j]` >= 1 for every op; returns offsets of the stable level sort.
+inline std::vector<int> level_sort(const std::vector<int>& lev, std::vector<int>* order) {
+  int nl = 0;
+  for (int l : lev) nl = std::max(nl, l);
+  std::vector<int> cnt((size_t)nl + 2, 0);  // after the prefix sum: cnt[l] = number of ops with level < l
+  for (int l : lev) cnt[(size_t)l + 1] += 1;
+  for (int l = 1; l <= nl + 1; l++) cnt[(size_t)l] += cnt[(size_t)l - 1];
+  order->assign(lev.size(), 0);
+  std::vector<int> pos(cnt.begin(), cnt.end());
+  for (size_t j = 0; j < lev.size(); j++) (*order)[(size_t)pos[(size_t)lev[j]]++] = (int)j;
+  std::vector<int> offs;
+  for (int l = 1; l <= nl + 1; l++) offs.push_back(cnt[(size_t)l]);
+  return offs;  // offs[q] = first op of the q-th level (q = 0 .. nl), offs[nl] = total
+}
+
+inline void build_levels(Plan& P) {
+  const int N = P.N;
+  // ---- LU
+  {
+    std::vector<int> ready((size_t)P.nnzLU, 0), t, u, l, lev;
+    for (int k = 0; k + 1 < N; k++) {
+      const int piv = P.diag_slot[(size_t)k];
+      if (piv < 0) continue;
+      for (int j = P.l_off[(size_t)k]; j < P.l_off[(size_t)k + 1]; j++) {
+        const int ls = P.l_slot[(size_t)j];
+        const int lv = std::max(ready[(size_t)ls], ready[(size_t)piv]) + 1;
+        t.push_back(ls); u.push_back(piv); l.push_back(-1); lev.push_back(lv);
+        ready[(size_t)ls] = lv;
+      }
+      for (int j = P.upd_off[(size_t)k]; j < P.upd_off[(size_t)k + 1]; j++) {
+        const int tt = P.upd_t[(size_t)j], uu = P.upd_u[(size_t)j], ll = P.upd_l[(size_t)j];
+        const int lv = std::max(ready[(size_t)tt], std::max(ready[(size_t)uu], ready[(size_t)ll])) + 1;
+        t.push_back(tt); u.push_back(uu); l.push_back(ll); lev.push_back(lv);
+        ready[(size_t)tt] = lv;
+      }
+    }
+    std::vector<int> order;
+    P.lu_lvl_off = level_sort(lev, &order);
+    for (int j : order) { P.lu_t.push_back(t[(size_t)j]); P.lu_u.push_back(u[(size_t)j]); P.lu_l.push_back(l[(size_t)j]); }
+  }
+  // ---- forward substitution
+  {
+    std::vector<int> ready((size_t)N, 0), kk, rr, ss, lev;
+    for (int k = 0; k < N; k++)
+      for (int j = P.l_off[(size_t)k]; j < P.l_off[(size_t)k + 1]; j++) {
+        const int row = P.l_row[(size_t)j];
+        const int lv = std::max(ready[(size_t)k], ready[(size_t)row]) + 1;
+        kk.push_back(k); rr.push_back(row); ss.push_back(P.l_slot[(size_t)j]); lev.push_back(lv);
+        ready[(size_t)row] = lv;
+      }
+    std::vector<int> order;
+    P.fw_lvl_off = level_sort(lev, &order);
+    for (int j : order) { P.fw_k.push_back(kk[(size_t)j]); P.fw_row.push_back(rr[(size_t)j]); P.fw_slot.push_back(ss[(size_t)j]); }
+  }
+  // ---- backward substitution
+  {
+    std::vector<int> lvl((size_t)N, 1), rows, lev;
+    for (int k = N - 1; k >= 0; k--) {
+      const int ds = P.diag_slot[(size_t)k];
+      if (ds < 0) continue;
+      int lv = 1;
+      for (int s = ds + 1; s < P.rowptr[(size_t)k + 1]; s++) lv = std::max(lv, lvl[(size_t)P.colidx[(size_t)s]] + 1);
+      lvl[(size_t)k] = lv;
+      rows.push_back(k); lev.push_back(lv);
+    }
+    std::vector<int> order;
+    P.bw_lvl_off = level_sort(lev, &order);
+    for (int j : order) P.bw_row.push_back(rows[(size_t)j]);
+  }
+}
 
 namespace detail {
 template <class T>
@@ -255,6 +339,7 @@ Plan build_plan(int N, const std::vector<int>& elem_row, const std::vector<int>&
     P.l_off[(size_t)n + 1] = (int)P.l_slot.size();
     P.upd_off[(size_t)n + 1] = (int)P.upd_t.size();
   }
+  if (P.status == ST_OK) build_levels(P);
   return P;
 }
 

@@ -1,0 +1,441 @@
+// Cooperative Newton kernel: a CTA owns `gi` consecutive circuit instances and ALL of its threads work on them, one
+// phase at a time, with the instances' whole workspace (x, rhs, residual, L+U values, stamp staging, device state)
+// resident in shared memory for the entire Newton loop — and, for transient, for the entire time loop. The shared
+// index tables of the circuit (device tables, stamp handles, gather lists, LU plan and level schedules — one packed
+// "arena") are brought into shared memory once per CTA with a TMA bulk copy (cp.async.bulk + mbarrier).
+//
+// Why: with one thread per instance (newton.cu) the 8192-instance benchmark batch is only 256 warps on 148 SMs and
+// every warp walks ~9 k dependent instructions per iteration, 45 % of them 64-bit address arithmetic
+// (profiles/r01a_*: 6 % warps active, 0.03 % DRAM). Here the work of an iteration is spread over (item, instance) pairs,
+// instance fastest, every thread keeping one fixed instance column:
+//     eval      item = device            (devices evaluated in parallel into private staging slots)
+//     assemble  item = L+U slot | rhs row (gather of staging slots in the reference's accumulation order)
+//     residual  item = row
+//     LU        item = operation of the current dependency level (host/symbolic.hpp build_levels)
+//     forward / backward substitution: item = operation / row of the current level
+//     update    item = variable
+// With gi = 32 a warp is one item x 32 instances (convergent, conflict-free smem columns); with smaller gi a warp spans
+// several items, which buys more CTAs when the batch is small. Every floating-point operation on any single value
+// happens in the same order as in newton.cu (and hence as in the reference): results are bit-identical.
+//
+// Replaces the same reference functions as newton.cu (analysis.rs:153-210, 253-303, 331-345, 553-570;
+// sparse21/mod.rs:272-327, 865-991).
+#include <cuda_runtime.h>
+
+#include <type_traits>
+
+#include "devices.cuh"
+#include "engine.hpp"
+
+namespace s21 {
+
+namespace {
+
+enum { K_DCOP = 0, K_TRAN = 1, K_AC = 2 };
+enum { CST_OK = 0, CST_CONV = 1, CST_SINGULAR = 2 };
+
+// ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier (sm_90+; SASS: UBLKCP + SYNCS)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  }
+}
+
+template <class T, class I>
+struct EnvS {  // staged Env (see devices.cuh): stamps go to this device's private staging slots
+  const int* it;
+  const int* pc;
+  const double* pval;
+  size_t pinst;
+  double* sop;      // already offset to (state_off, instance); element k at sop[k * sstride]
+  double* sguess;
+  I sstride;
+  const T* x;       // already offset to the instance column; variable v at x[v * xstride]
+  T* S;             // already offset to (stage_off, instance); position p at S[p * xstride]
+  I xstride;
+  int mode;
+  double dt, gmin, omega;
+  __device__ __forceinline__ int node(int k) const { return it[k]; }
+  __device__ __forceinline__ double par(int k) const {
+    const int c = pc[k];
+    return __ldg(pval + (size_t)(c >> 1) + (size_t)(c & 1) * pinst);
+  }
+  __device__ __forceinline__ double volt(int var) const {
+    if constexpr (std::is_same<T, double>::value) return var < 0 ? 0.0 : x[(I)var * xstride];
+    else return 0.0;  // load_ac never reads the guess
+  }
+  __device__ __forceinline__ double op(int k) const { return sop[(I)k * sstride]; }
+  __device__ __forceinline__ double guess(int k) const { return sguess[(I)k * sstride]; }
+  __device__ __forceinline__ void set_guess(int k, double v) { sguess[(I)k * sstride] = v; }
+  __device__ __forceinline__ void add_g_at(int pos, T v) { S[(I)pos * xstride] = v; }
+  __device__ __forceinline__ void add_b_at(int pos, T v) { S[(I)pos * xstride] = v; }
+  __device__ __forceinline__ void add_g_dup(int, int dup, T v) { S[(I)dup * xstride] = v; }
+};
+
+template <class T, class E> __device__ __forceinline__ void load_one(int type, E& e) {
+  if constexpr (std::is_same<T, double>::value) {
+    switch (type) {
+      case DT_R: load_resistor(e); break;
+      case DT_C: load_capacitor(e); break;
+      case DT_I: load_isrc(e); break;
+      case DT_V: load_vsrc(e); break;
+      case DT_DIODE: load_diode(e); break;
+      case DT_MOS0: load_mos0(e); break;
+      case DT_MOS1: load_mos1(e); break;
+      default: break;
+    }
+  } else {
+    switch (type) {
+      case DT_R: load_ac_resistor(e); break;
+      case DT_C: load_ac_capacitor(e); break;
+      case DT_V: load_ac_vsrc(e); break;
+      case DT_MOS1: load_ac_mos1(e); break;
+      default: break;  // the host refuses AC for devices without load_ac before launching
+    }
+  }
+}
+
+template <class T> struct TolC;
+template <> struct TolC<double> {
+  static __device__ __forceinline__ bool ok(double a, double tol) { return !(a > tol); }
+  static const int max_iter = 100;
+};
+template <> struct TolC<cplx> {
+  static __device__ __forceinline__ bool ok(double a, double tol) { return a < tol; }
+  static const int max_iter = 20;
+};
+
+struct CoopArgs {
+  int lg_gi;
+  int T_points, n_save;
+  const int* save_vars;
+  double* wave;
+  const int* arena;      // packed index tables in HBM (all table pointers point into it)
+  int arena_bytes;       // > 0: copy the arena into shared memory with TMA and rebase the pointers
+};
+
+template <class T, int KIND, bool SMEM>
+__global__ void __launch_bounds__(256, 2) k_coop(DevTables d, PlanTables p, CoopTables ct, WorkTables<T> g, T* gstage, NewtonOut o,
+                                                SolveCtl ctl, CoopArgs a) {
+  typedef typename std::conditional<SMEM, unsigned, size_t>::type I;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int lg_gi = a.lg_gi, gi = 1 << lg_gi;
+  const int li = tid & (gi - 1);        // this thread's instance column, fixed for the whole kernel (nt % gi == 0)
+  const int item0 = tid >> lg_gi;       // first item of this thread in every phase
+  const int istep = nt >> lg_gi;        // items handled per sweep of the CTA
+  const int i0 = blockIdx.x * gi;
+  const int ni = min(gi, ctl.B - i0);
+  const int N = p.N, nnz = p.nnz;
+  constexpr bool real_kind = KIND != K_AC;
+
+  // ---- carve shared memory: [control words][arena copy][workspace]
+  double* maxabs = (double*)smem_raw;
+  int* act = (int*)(maxabs + gi);
+  int* resok = act + gi;
+  int* dxok = resok + gi;
+  int* sing = dxok + gi;
+  int* stat = sing + gi;
+  int* nsol = stat + gi;
+  int* nld = nsol + gi;
+  int* convnow = nld + gi;
+  uint64_t* mbar = (uint64_t*)(convnow + gi);
+  size_t off = ((size_t)((unsigned char*)(mbar + 1) - smem_raw) + 15) / 16 * 16;
+  if (a.arena_bytes > 0) {
+    int* sa = (int*)(smem_raw + off);
+    if (tid == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(mbar, (uint32_t)a.arena_bytes);
+      tma_load_1d(sa, a.arena, (uint32_t)a.arena_bytes, mbar);
+    }
+    off += (size_t)a.arena_bytes;
+    // Rebase every table pointer onto the shared-memory copy. The new pointer must be DERIVED FROM `sa`: nvcc assumes
+    // pointers that come from kernel arguments address global memory and would emit ld.global for them.
+#define RB(ptr) ptr = sa + ((ptr) - a.arena)
+    RB(d.type); RB(d.itab_off); RB(d.par_off); RB(d.state_off); RB(d.itab); RB(d.pcode);
+    RB(p.row_i2e); RB(p.col_i2e); RB(p.col_e2i); RB(p.rowptr); RB(p.colidx); RB(p.diag_slot);
+    RB(ct.stage_off); RB(ct.eval_order); RB(ct.asm_off); RB(ct.asm_src);
+    RB(ct.lu_lvl_off); RB(ct.lu_t); RB(ct.lu_u); RB(ct.lu_l);
+    RB(ct.fw_lvl_off); RB(ct.fw_k); RB(ct.fw_row); RB(ct.fw_slot); RB(ct.bw_lvl_off); RB(ct.bw_row);
+#undef RB
+  }
+  // ---- workspace views: entry k of this thread's instance is a[k * ws + col]
+  T *x, *rhs, *c, *lu, *S;
+  double *sop, *sguess;
+  I ws, col, ss, scol;
+  if constexpr (SMEM) {
+    x = (T*)(smem_raw + off); off += sizeof(T) * (size_t)N * gi;
+    rhs = (T*)(smem_raw + off); off += sizeof(T) * (size_t)N * gi;
+    c = (T*)(smem_raw + off); off += sizeof(T) * (size_t)N * gi;
+    lu = (T*)(smem_raw + off); off += sizeof(T) * (size_t)nnz * gi;
+    S = (T*)(smem_raw + off); off += sizeof(T) * (size_t)ct.n_stage * gi;
+    sop = (double*)(smem_raw + off); off += sizeof(double) * (size_t)d.n_state * gi;
+    sguess = (double*)(smem_raw + off);
+    ws = (I)gi; col = (I)li; ss = (I)gi; scol = (I)li;
+  } else {
+    x = g.x; rhs = g.rhs; c = g.c; lu = g.lu; S = gstage;
+    sop = g.st_op; sguess = g.st_guess;
+    ws = (I)g.stride; col = (I)i0 + (I)li; ss = (I)g.st_stride; scol = ((I)i0 + (I)li) * (I)ctl.par_inst_stride;
+  }
+  const bool valid = li < ni;
+
+  // ---- prologue
+  if (tid < gi) {
+    stat[tid] = (tid < ni && KIND == K_TRAN) ? o.status[i0 + tid] : 0;
+    nsol[tid] = 0; nld[tid] = 0; convnow[tid] = 0; dxok[tid] = 1; act[tid] = 0;
+  }
+  if constexpr (SMEM) {
+    for (int k = item0; k < N; k += istep) x[(I)k * ws + col] = valid ? g.x[(size_t)k * g.stride + i0 + li] : Scalar<T>::zero();
+    for (int k = item0; k < d.n_state; k += istep) {
+      const size_t src = (size_t)k * g.st_stride + ((size_t)i0 + (size_t)(valid ? li : 0)) * ctl.par_inst_stride;
+      sop[(I)k * ss + scol] = g.st_op[src];
+      sguess[(I)k * ss + scol] = g.st_guess[src];
+    }
+  }
+  if (a.arena_bytes > 0) mbar_wait(mbar, 0);
+  __syncthreads();
+  if constexpr (KIND == K_TRAN) {
+    for (int s = item0; s < a.n_save; s += istep)
+      if (valid) a.wave[(size_t)s * g.stride + i0 + li] = x[(I)a.save_vars[s] * ws + col];
+  }
+  const double vtol = real_kind ? ctl.reltol : 1e-3, itol = real_kind ? ctl.iabstol : 1e-9;  // analysis.rs:271-272, 331-345
+  const int n_points = KIND == K_TRAN ? a.T_points : 2;
+  const size_t pinst = ((size_t)i0 + (size_t)li) * ctl.par_inst_stride;
+  double omega = 0.0;
+  if constexpr (KIND == K_AC) omega = valid ? ctl.omega[i0 + li] : 0.0;
+
+  for (int tp = 1; tp < n_points; tp++) {
+    if (tid < gi) { act[tid] = (tid < ni && stat[tid] == CST_OK) ? 1 : 0; dxok[tid] = 1; }
+    __syncthreads();
+    for (int iter = 0; iter < TolC<T>::max_iter; iter++) {
+      const bool on = act[li] != 0;  // stable until the decision phase (which is fenced by barriers on both sides)
+      // ---- P1: device evaluation (Solver::update, analysis.rs:153-168), devices in parallel
+      if (on) {
+        for (int item = item0; item < d.n_dev; item += istep) {
+          const int dev = ct.eval_order[item];
+          EnvS<T, I> e;
+          e.it = d.itab + d.itab_off[dev];
+          e.pc = d.pcode + d.par_off[dev];
+          e.pval = d.pval;
+          e.pinst = pinst;
+          const I so = (I)d.state_off[dev] * ss + scol;
+          e.sop = sop + so; e.sguess = sguess + so; e.sstride = ss;
+          e.x = x + col; e.xstride = ws;
+          e.S = S + (I)ct.stage_off[dev] * ws + col;
+          e.mode = ctl.mode; e.dt = ctl.dt; e.gmin = ctl.gmin; e.omega = omega;
+          load_one<T>(d.type[dev], e);
+        }
+      }
+      if (tid < gi) { resok[tid] = 1; sing[tid] = 0; maxabs[tid] = 0.0; }
+      __syncthreads();
+      // ---- P2: assembly — gather staging slots per L+U slot / rhs row in the reference's accumulation order
+      if (on) {
+        for (int t = item0; t < nnz + N; t += istep) {
+          T acc = Scalar<T>::zero();
+          for (int q = ct.asm_off[t]; q < ct.asm_off[t + 1]; q++) acc = s_add(acc, S[(I)ct.asm_src[q] * ws + col]);
+          if (t < nnz) lu[(I)t * ws + col] = acc;
+          else rhs[(I)(t - nnz) * ws + col] = acc;
+        }
+      }
+      __syncthreads();
+      // ---- P3: residual in pivoted row order (Matrix::res, sparse21/mod.rs:298-327)
+      if (on) {
+        for (int r = item0; r < N; r += istep) {
+          T acc = Scalar<T>::zero();
+          for (int s = p.rowptr[r]; s < p.rowptr[r + 1]; s++)
+            acc = s_add(acc, s_mul(lu[(I)s * ws + col], x[(I)p.col_i2e[p.colidx[s]] * ws + col]));
+          const T rv = s_sub(rhs[(I)p.row_i2e[r] * ws + col], acc);
+          c[(I)r * ws + col] = rv;
+          if (!TolC<T>::ok(s_abs(rv), itol)) resok[li] = 0;
+        }
+      }
+      __syncthreads();
+      // ---- convergence decision (Solver::converged, analysis.rs:331-345)
+      if (tid < gi) {
+        int cn = 0;
+        if (act[tid]) {
+          nld[tid] += 1;
+          if (dxok[tid] && resok[tid]) { act[tid] = 0; cn = 1; }
+        }
+        convnow[tid] = cn;
+        dxok[tid] = 1;
+      }
+      __syncthreads();
+      if (real_kind && convnow[li]) {  // Component::commit on convergence: op <- guess
+        for (int k = item0; k < d.n_state; k += istep) sop[(I)k * ss + scol] = sguess[(I)k * ss + scol];
+      }
+      if (!__syncthreads_or(tid < gi && act[tid])) break;
+      const bool go = act[li] != 0;
+      // ---- numeric LU on the frozen pattern, one barrier per dependency level (row_col_elim, mod.rs:865-919)
+      for (int q = 0; q < ct.n_lu_lvl; q++) {
+        if (go) {
+          const int b = ct.lu_lvl_off[q], e_ = ct.lu_lvl_off[q + 1];
+          for (int op = b + item0; op < e_; op += istep) {
+            const int l = ct.lu_l[op];
+            T* t = lu + (I)ct.lu_t[op] * ws + col;
+            const T u = lu[(I)ct.lu_u[op] * ws + col];
+            if (l < 0) *t = s_div(*t, u);
+            else *t = s_sub(*t, s_mul(u, lu[(I)l * ws + col]));
+          }
+        }
+        __syncthreads();
+      }
+      // ---- forward substitution (mod.rs:947-964); c is already in pivoted row order
+      for (int q = 0; q < ct.n_fw_lvl; q++) {
+        if (go) {
+          const int b = ct.fw_lvl_off[q], e_ = ct.fw_lvl_off[q + 1];
+          for (int op = b + item0; op < e_; op += istep) {
+            const T ck = c[(I)ct.fw_k[op] * ws + col];
+            if (s_is_zero(ck)) continue;
+            T* t = c + (I)ct.fw_row[op] * ws + col;
+            *t = s_sub(*t, s_mul(ck, lu[(I)ct.fw_slot[op] * ws + col]));
+          }
+        }
+        __syncthreads();
+      }
+      // ---- backward substitution (mod.rs:967-979): each row's sum runs in list order inside one thread
+      for (int q = 0; q < ct.n_bw_lvl; q++) {
+        if (go) {
+          const int b = ct.bw_lvl_off[q], e_ = ct.bw_lvl_off[q + 1];
+          for (int r = b + item0; r < e_; r += istep) {
+            const int k = ct.bw_row[r];
+            const int ds = p.diag_slot[k];
+            T ck = c[(I)k * ws + col];
+            for (int s = ds + 1; s < p.rowptr[k + 1]; s++) ck = s_sub(ck, s_mul(c[(I)p.colidx[s] * ws + col], lu[(I)s * ws + col]));
+            c[(I)k * ws + col] = s_div(ck, lu[(I)ds * ws + col]);
+          }
+        }
+        __syncthreads();
+      }
+      // ---- zero-pivot check (assert(pivot_val).ne(0), mod.rs:871-872) and max |dx| (analysis.rs:198)
+      if (go) {
+        double m = 0.0;
+        for (int k = item0; k < N; k += istep) {
+          if (k + 1 < N && s_is_zero(lu[(I)p.diag_slot[k] * ws + col])) sing[li] = 1;
+          const double v = s_abs(c[(I)p.col_e2i[k] * ws + col]);
+          if (v > m) m = v;
+        }
+        if (m > 0.0) atomicMax((unsigned long long*)&maxabs[li], (unsigned long long)__double_as_longlong(m));
+      }
+      __syncthreads();
+      // ---- global step limit and update (analysis.rs:197-207 / 283-293)
+      if (go && !sing[li]) {
+        const double m = maxabs[li];
+        for (int k = item0; k < N; k += istep) {
+          T dxk = c[(I)p.col_e2i[k] * ws + col];
+          if (m > 1.0) dxk = s_scale(dxk, 1.0, m);
+          T* xv = x + (I)k * ws + col;
+          *xv = s_add(*xv, dxk);
+          if (!TolC<T>::ok(s_abs(dxk), vtol)) dxok[li] = 0;
+        }
+      }
+      __syncthreads();
+      if (tid < gi && act[tid]) {
+        if (sing[tid]) { act[tid] = 0; stat[tid] = CST_SINGULAR; }
+        else nsol[tid] += 1;
+      }
+      __syncthreads();
+    }
+    if (tid < gi && act[tid]) { stat[tid] = CST_CONV; act[tid] = 0; }  // "Convergence Failed" (analysis.rs:209, 302)
+    __syncthreads();
+    if constexpr (KIND == K_TRAN) {
+      if (valid) {
+        const bool good = stat[li] == CST_OK;
+        for (int s = item0; s < a.n_save; s += istep)
+          a.wave[((size_t)tp * a.n_save + s) * g.stride + i0 + li] =
+              good ? x[(I)a.save_vars[s] * ws + col] : __longlong_as_double(0x7ff8000000000000LL);
+      }
+    }
+  }
+
+  // ---- epilogue: results back to HBM
+  if constexpr (SMEM) {
+    if (valid) {
+      for (int k = item0; k < N; k += istep) g.x[(size_t)k * g.stride + i0 + li] = x[(I)k * ws + col];
+      if (real_kind)
+        for (int k = item0; k < d.n_state; k += istep) {
+          const size_t dst = (size_t)k * g.st_stride + i0 + li;
+          g.st_op[dst] = sop[(I)k * ss + scol];
+          g.st_guess[dst] = sguess[(I)k * ss + scol];
+        }
+    }
+  }
+  if (tid < ni) {
+    o.status[i0 + tid] = stat[tid];
+    o.iters[i0 + tid] += nsol[tid];
+    o.loads[i0 + tid] += nld[tid];
+  }
+}
+
+int lg2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
+size_t ctrl_bytes(int gi) { return ((8 + 8 * 4) * (size_t)gi + 8 + 15) / 16 * 16; }
+
+template <class T, int KIND>
+int launch(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<T>& w, T* stage, const NewtonOut& o,
+           const SolveCtl& c, const CoopCfg& cfg, int T_points, const int* save_vars, int n_save, double* wave, void* stream) {
+  CoopArgs a;
+  a.lg_gi = lg2(cfg.gi); a.T_points = T_points; a.n_save = n_save; a.save_vars = save_vars; a.wave = wave;
+  a.arena = cfg.arena; a.arena_bytes = cfg.arena_in_smem ? (int)cfg.arena_bytes : 0;
+  const size_t smem = ctrl_bytes(cfg.gi) + (size_t)a.arena_bytes + cfg.smem_bytes;
+  const int grid = (c.B + cfg.gi - 1) / cfg.gi;
+  cudaError_t e;
+  if (cfg.smem_bytes > 0) {
+    auto kern = k_coop<T, KIND, true>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<grid, cfg.threads, smem, (cudaStream_t)stream>>>(d, p, ct, w, stage, o, c, a);
+  } else {
+    auto kern = k_coop<T, KIND, false>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<grid, cfg.threads, smem, (cudaStream_t)stream>>>(d, p, ct, w, stage, o, c, a);
+  }
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+size_t coop_ctrl_bytes(int gi) { return ctrl_bytes(gi); }
+size_t coop_work_bytes(int N, int nnz, int n_stage, int n_state, int gi, int scalar_width) {
+  const size_t ts = 8 * (size_t)scalar_width;
+  return ts * (size_t)gi * (3 * (size_t)N + (size_t)nnz + (size_t)n_stage) + 8 * (size_t)gi * 2 * (size_t)n_state;
+}
+int coop_max_smem_optin(int device) {
+  int v = 0;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess) return 0;
+  return v;
+}
+
+int launch_coop_dcop(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<double>& w, double* stage,
+                     const NewtonOut& o, const SolveCtl& c, const CoopCfg& cfg, void* stream) {
+  return launch<double, K_DCOP>(d, p, ct, w, stage, o, c, cfg, 2, nullptr, 0, nullptr, stream);
+}
+int launch_coop_tran(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<double>& w, double* stage,
+                     const NewtonOut& o, const SolveCtl& c, const CoopCfg& cfg, int T, const int* save_vars, int n_save, double* wave,
+                     void* stream) {
+  return launch<double, K_TRAN>(d, p, ct, w, stage, o, c, cfg, T, save_vars, n_save, wave, stream);
+}
+int launch_coop_ac(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<cplx>& w, cplx* stage,
+                   const NewtonOut& o, const SolveCtl& c, const CoopCfg& cfg, void* stream) {
+  return launch<cplx, K_AC>(d, p, ct, w, stage, o, c, cfg, 2, nullptr, 0, nullptr, stream);
+}
+
+}  // namespace s21

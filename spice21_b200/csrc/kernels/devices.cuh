@@ -10,7 +10,11 @@
 //   double par(k)             k-th parameter (shared or per-instance column)
 //   double volt(var)          real solution entry, 0 for ground (-1)
 //   double op(k), guess(k)    committed / in-flight state slot k of this device;  set_guess(k, v)
-//   void   add_g(handle, v)   A[handle] += v  (dropped when handle < 0);   add_b(var, v)  rhs[var] += v
+//   void   add_g_at(pos, v)   push a matrix stamp for the element handle stored at itab position `pos`
+//   void   add_b_at(pos, v)   push an RHS stamp for the variable stored at itab position `pos`
+//   void   add_g_dup(pos, dup, v)  second push to the same element within one load (own staging slot `dup`)
+// A direct Env adds straight into A / rhs (one thread owns the instance); a staged Env writes private per-device
+// staging slots that a later gather phase sums in the reference's order (devices evaluated in parallel).
 //   int mode; double dt, gmin, omega
 #pragma once
 #include "../device_layout.h"
@@ -31,10 +35,10 @@ __device__ __forceinline__ Integ integrate_be(double dt, double dq, double dq_dv
 // ---------------------------------------------------------------- Resistor (comps/mod.rs:299-310)
 template <class Env> __device__ __forceinline__ void load_resistor(Env& e) {
   const double g = e.par(e.mode == AN_OP ? RP_G_OP : RP_G_TRAN);
-  e.add_g(e.node(R_EPP), g);
-  e.add_g(e.node(R_ENN), g);
-  e.add_g(e.node(R_EPN), -g);
-  e.add_g(e.node(R_ENP), -g);
+  e.add_g_at(R_EPP, g);
+  e.add_g_at(R_ENN, g);
+  e.add_g_at(R_EPN, -g);
+  e.add_g_at(R_ENP, -g);
 }
 // ---------------------------------------------------------------- Capacitor (comps/mod.rs:200-222)
 template <class Env> __device__ __forceinline__ void load_capacitor(Env& e) {
@@ -44,26 +48,26 @@ template <class Env> __device__ __forceinline__ void load_capacitor(Env& e) {
   e.set_guess(CS_Q, q);
   if (e.mode == AN_OP) return;  // no stamps in OP; only records guess{v, q}
   const Integ k = integrate_be(e.dt, q - e.op(CS_Q), c, vd);
-  e.add_g(e.node(R_EPP), k.g);
-  e.add_g(e.node(R_ENN), k.g);
-  e.add_g(e.node(R_EPN), -k.g);
-  e.add_g(e.node(R_ENP), -k.g);
-  e.add_b(e.node(R_P), -k.rhs);
-  e.add_b(e.node(R_N), k.rhs);
+  e.add_g_at(R_EPP, k.g);
+  e.add_g_at(R_ENN, k.g);
+  e.add_g_at(R_EPN, -k.g);
+  e.add_g_at(R_ENP, -k.g);
+  e.add_b_at(R_P, -k.rhs);
+  e.add_b_at(R_N, k.rhs);
 }
 // ---------------------------------------------------------------- Isrc (comps/mod.rs:340-345)
 template <class Env> __device__ __forceinline__ void load_isrc(Env& e) {
   const double i = e.par(IP_I);
-  e.add_b(e.node(I_P), i);
-  e.add_b(e.node(I_N), -i);
+  e.add_b_at(I_P, i);
+  e.add_b_at(I_N, -i);
 }
 // ---------------------------------------------------------------- Vsrc (comps/mod.rs:133-138)
 template <class Env> __device__ __forceinline__ void load_vsrc(Env& e) {
-  e.add_g(e.node(V_EPI), 1.0);
-  e.add_g(e.node(V_EIP), 1.0);
-  e.add_g(e.node(V_ENI), -1.0);
-  e.add_g(e.node(V_EIN), -1.0);
-  e.add_b(e.node(V_I), e.par(e.mode == AN_OP ? VP_V_OP : VP_V_TRAN));
+  e.add_g_at(V_EPI, 1.0);
+  e.add_g_at(V_EIP, 1.0);
+  e.add_g_at(V_ENI, -1.0);
+  e.add_g_at(V_EIN, -1.0);
+  e.add_b_at(V_I, e.par(e.mode == AN_OP ? VP_V_OP : VP_V_TRAN));
 }
 // ---------------------------------------------------------------- Diode (comps/diode.rs:228-245, 279-355)
 template <class Env> __device__ __forceinline__ double diode_limit(Env& e, double vd, double vold) {
@@ -124,15 +128,15 @@ template <class Env> __device__ __forceinline__ void load_diode(Env& e) {
   e.set_guess(DS_VD, vd);
   e.set_guess(DS_CHARGE, qd);
   const double irhs = id - vd * gd;
-  e.add_g(e.node(D_ENN), gd);
-  e.add_g(e.node(D_ERN), -gd);
-  e.add_g(e.node(D_ENR), -gd);
-  e.add_g(e.node(D_ERR), gd + gspr);
-  e.add_g(e.node(D_EPP), gspr);
-  e.add_g(e.node(D_EPR), -gspr);
-  e.add_g(e.node(D_ERP), -gspr);
-  e.add_b(r, -irhs);
-  e.add_b(n, irhs);
+  e.add_g_at(D_ENN, gd);
+  e.add_g_at(D_ERN, -gd);
+  e.add_g_at(D_ENR, -gd);
+  e.add_g_at(D_ERR, gd + gspr);
+  e.add_g_at(D_EPP, gspr);
+  e.add_g_at(D_EPR, -gspr);
+  e.add_g_at(D_ERP, -gspr);
+  e.add_b_at(D_R, -irhs);
+  e.add_b_at(D_N, irhs);
 }
 // ---------------------------------------------------------------- Mos0 (comps/mos.rs:1051-1099)
 template <class Env> __device__ __forceinline__ void load_mos0(Env& e) {
@@ -159,17 +163,17 @@ template <class Env> __device__ __forceinline__ void load_mos0(Env& e) {
   }
   const double irhs = ids - gm * vgs - gds * vds;
   // (sr, dr) = (S, D) or swapped
-  const int e_drdr = e.node(reversed ? M0_ESS : M0_EDD), e_srsr = e.node(reversed ? M0_EDD : M0_ESS);
-  const int e_drsr = e.node(reversed ? M0_ESD : M0_EDS), e_srdr = e.node(reversed ? M0_EDS : M0_ESD);
-  const int e_drg = e.node(reversed ? M0_ESG : M0_EDG), e_srg = e.node(reversed ? M0_EDG : M0_ESG);
-  e.add_g(e_drdr, gds + gmin);
-  e.add_g(e_srsr, (gm + gds + gmin));
-  e.add_g(e_drsr, -(gm + gds + gmin));
-  e.add_g(e_srdr, -gds - gmin);
-  e.add_g(e_drg, gm);
-  e.add_g(e_srg, -gm);
-  e.add_b(e.node(reversed ? M0_S : M0_D), -p * irhs);
-  e.add_b(e.node(reversed ? M0_D : M0_S), p * irhs);
+  const int e_drdr = reversed ? M0_ESS : M0_EDD, e_srsr = reversed ? M0_EDD : M0_ESS;
+  const int e_drsr = reversed ? M0_ESD : M0_EDS, e_srdr = reversed ? M0_EDS : M0_ESD;
+  const int e_drg = reversed ? M0_ESG : M0_EDG, e_srg = reversed ? M0_EDG : M0_ESG;
+  e.add_g_at(e_drdr, gds + gmin);
+  e.add_g_at(e_srsr, (gm + gds + gmin));
+  e.add_g_at(e_drsr, -(gm + gds + gmin));
+  e.add_g_at(e_srdr, -gds - gmin);
+  e.add_g_at(e_drg, gm);
+  e.add_g_at(e_srg, -gm);
+  e.add_b_at(reversed ? M0_S : M0_D, -p * irhs);
+  e.add_b_at(reversed ? M0_D : M0_S, p * irhs);
 }
 // ---------------------------------------------------------------- Mos1 (comps/mos.rs:504-521, 649-893)
 // MosJunction::qc (mos.rs:504-521) feeds only tr.bs/tr.bd and op.cbs/op.cbd, none of which is ever stamped or read back
@@ -258,33 +262,33 @@ template <class Env> __device__ __forceinline__ void load_mos1(Env& e) {
   const double irhs = ids - gm * vgs - gds * vds;
   const int sr = reversed ? M1_DP : M1_SP, sx = reversed ? M1_D : M1_S, dr = reversed ? M1_SP : M1_DP, dx = reversed ? M1_S : M1_D;
   const double grd = e.par(M1P_GRD), grs = e.par(M1P_GRS);
-#define M1E(a, b) e.node(M1_E0 + (a) * 6 + (b))
-  e.add_g(M1E(dr, dr), gds + grd + gbd + tr_gd.g);
-  e.add_g(M1E(sr, sr), gm + gds + grs + gbs + gmbs + tr_gs.g);
-  e.add_g(M1E(dr, sr), -gm - gds - gmbs);
-  e.add_g(M1E(sr, dr), -gds);
-  e.add_g(M1E(dr, M1_G), gm - tr_gd.g);
-  e.add_g(M1E(sr, M1_G), -gm - tr_gs.g);
-  e.add_g(M1E(M1_G, M1_G), (tr_gd.g + tr_gs.g + tr_gb.g));
-  e.add_g(M1E(M1_B, M1_B), (gbd + gbs + tr_gb.g));
-  e.add_g(M1E(M1_G, M1_B), -tr_gb.g);
-  e.add_g(M1E(M1_G, dr), -tr_gd.g);
-  e.add_g(M1E(M1_G, sr), -tr_gs.g);
-  e.add_g(M1E(M1_B, M1_G), -tr_gb.g);
-  e.add_g(M1E(M1_B, dr), -gbd);
-  e.add_g(M1E(M1_B, sr), -gbs);
-  e.add_g(M1E(dr, M1_B), -gbd + gmbs);
-  e.add_g(M1E(sr, M1_B), -gbs - gmbs);
-  e.add_g(M1E(dx, dr), -grd);
-  e.add_g(M1E(dr, dx), -grd);
-  e.add_g(M1E(dx, dx), grd);
-  e.add_g(M1E(sx, sr), -grs);
-  e.add_g(M1E(sr, sx), -grs);
-  e.add_g(M1E(sx, sx), grs);
-  e.add_b(e.node(dr), p * (-irhs + ibd_rhs + tr_gd.rhs));
-  e.add_b(e.node(sr), p * (irhs + ibs_rhs + tr_gs.rhs));
-  e.add_b(e.node(M1_G), -p * (tr_gs.rhs + tr_gb.rhs + tr_gd.rhs));
-  e.add_b(e.node(M1_B), -p * (ibd_rhs + ibs_rhs - tr_gb.rhs));
+#define M1E(a, b) (M1_E0 + (a) * 6 + (b))
+  e.add_g_at(M1E(dr, dr), gds + grd + gbd + tr_gd.g);
+  e.add_g_at(M1E(sr, sr), gm + gds + grs + gbs + gmbs + tr_gs.g);
+  e.add_g_at(M1E(dr, sr), -gm - gds - gmbs);
+  e.add_g_at(M1E(sr, dr), -gds);
+  e.add_g_at(M1E(dr, M1_G), gm - tr_gd.g);
+  e.add_g_at(M1E(sr, M1_G), -gm - tr_gs.g);
+  e.add_g_at(M1E(M1_G, M1_G), (tr_gd.g + tr_gs.g + tr_gb.g));
+  e.add_g_at(M1E(M1_B, M1_B), (gbd + gbs + tr_gb.g));
+  e.add_g_at(M1E(M1_G, M1_B), -tr_gb.g);
+  e.add_g_at(M1E(M1_G, dr), -tr_gd.g);
+  e.add_g_at(M1E(M1_G, sr), -tr_gs.g);
+  e.add_g_at(M1E(M1_B, M1_G), -tr_gb.g);
+  e.add_g_at(M1E(M1_B, dr), -gbd);
+  e.add_g_at(M1E(M1_B, sr), -gbs);
+  e.add_g_at(M1E(dr, M1_B), -gbd + gmbs);
+  e.add_g_at(M1E(sr, M1_B), -gbs - gmbs);
+  e.add_g_at(M1E(dx, dr), -grd);
+  e.add_g_at(M1E(dr, dx), -grd);
+  e.add_g_at(M1E(dx, dx), grd);
+  e.add_g_at(M1E(sx, sr), -grs);
+  e.add_g_at(M1E(sr, sx), -grs);
+  e.add_g_at(M1E(sx, sx), grs);
+  e.add_b_at(dr, p * (-irhs + ibd_rhs + tr_gd.rhs));
+  e.add_b_at(sr, p * (irhs + ibs_rhs + tr_gs.rhs));
+  e.add_b_at(M1_G, -p * (tr_gs.rhs + tr_gb.rhs + tr_gd.rhs));
+  e.add_b_at(M1_B, -p * (ibd_rhs + ibs_rhs - tr_gb.rhs));
   e.set_guess(M1S_VGS, vgs); e.set_guess(M1S_VGD, vgd); e.set_guess(M1S_VGB, vgb); e.set_guess(M1S_VSB, vsb);
   e.set_guess(M1S_VDB, vdb); e.set_guess(M1S_CGS, cgs1); e.set_guess(M1S_CGD, cgd1); e.set_guess(M1S_CGB, cgb1);
   e.set_guess(M1S_REV, reversed ? 1.0 : 0.0);
@@ -295,25 +299,25 @@ template <class Env> __device__ __forceinline__ void load_mos1(Env& e) {
 // Resistor / Capacitor / Vsrc load_ac (comps/mod.rs:139-149, 223-238, 311-322); Mos1::load_ac (mos.rs:914-968).
 template <class Env> __device__ __forceinline__ void load_ac_resistor(Env& e) {
   const double g = e.par(RP_G_TRAN);
-  e.add_g(e.node(R_EPP), mk(g, 0.0));
-  e.add_g(e.node(R_ENN), mk(g, 0.0));
-  e.add_g(e.node(R_EPN), mk(-g, 0.0));
-  e.add_g(e.node(R_ENP), mk(-g, 0.0));
+  e.add_g_at(R_EPP, mk(g, 0.0));
+  e.add_g_at(R_ENN, mk(g, 0.0));
+  e.add_g_at(R_EPN, mk(-g, 0.0));
+  e.add_g_at(R_ENP, mk(-g, 0.0));
 }
 template <class Env> __device__ __forceinline__ void load_ac_capacitor(Env& e) {
   const double c = e.par(CP_C);
   const double w = e.omega;
-  e.add_g(e.node(R_EPP), mk(0.0, w * c));
-  e.add_g(e.node(R_ENN), mk(0.0, w * c));
-  e.add_g(e.node(R_EPN), mk(0.0, -w * c));
-  e.add_g(e.node(R_ENP), mk(0.0, -w * c));
+  e.add_g_at(R_EPP, mk(0.0, w * c));
+  e.add_g_at(R_ENN, mk(0.0, w * c));
+  e.add_g_at(R_EPN, mk(0.0, -w * c));
+  e.add_g_at(R_ENP, mk(0.0, -w * c));
 }
 template <class Env> __device__ __forceinline__ void load_ac_vsrc(Env& e) {
-  e.add_g(e.node(V_EPI), mk(1.0, 0.0));
-  e.add_g(e.node(V_EIP), mk(1.0, 0.0));
-  e.add_g(e.node(V_ENI), mk(-1.0, 0.0));
-  e.add_g(e.node(V_EIN), mk(-1.0, 0.0));
-  e.add_b(e.node(V_I), mk(e.par(VP_ACM), 0.0));
+  e.add_g_at(V_EPI, mk(1.0, 0.0));
+  e.add_g_at(V_EIP, mk(1.0, 0.0));
+  e.add_g_at(V_ENI, mk(-1.0, 0.0));
+  e.add_g_at(V_EIN, mk(-1.0, 0.0));
+  e.add_b_at(V_I, mk(e.par(VP_ACM), 0.0));
 }
 template <class Env> __device__ __forceinline__ void load_ac_mos1(Env& e) {
   const double omega = e.omega;
@@ -324,29 +328,29 @@ template <class Env> __device__ __forceinline__ void load_ac_mos1(Env& e) {
   const bool reversed = e.op(M1S_REV) != 0.0;
   const int sr = reversed ? M1_DP : M1_SP, sx = reversed ? M1_D : M1_S, dr = reversed ? M1_SP : M1_DP, dx = reversed ? M1_S : M1_D;
   const double grd = e.par(M1P_GRD), grs = e.par(M1P_GRS);
-  e.add_g(M1E(dr, dr), mk(gds + grd + gbd, gcgd));
-  e.add_g(M1E(sr, sr), mk(gm + gds + grs + gbs + gmbs, gcgs));
-  e.add_g(M1E(dr, sr), mk(-gm - gds - gmbs, 0.0));
-  e.add_g(M1E(sr, dr), mk(-gds, 0.0));
-  e.add_g(M1E(dr, M1_G), mk(gm, -gcgd));
-  e.add_g(M1E(sr, M1_G), mk(-gm, -gcgs));
-  e.add_g(M1E(M1_G, M1_G), mk(0.0, gcgd + gcgs + gcgb));
-  e.add_g(M1E(M1_B, M1_B), mk(gbd + gbs, gcgb));
-  e.add_g(M1E(M1_G, M1_B), mk(0.0, -gcgb));
-  e.add_g(M1E(M1_G, dr), mk(0.0, -gcgd));
-  e.add_g(M1E(M1_G, sr), mk(0.0, -gcgs));
-  e.add_g(M1E(M1_B, M1_G), mk(0.0, -gcgb));
-  e.add_g(M1E(M1_G, dr), mk(0.0, -gcgd));  // pushed twice by the reference (mos.rs:951 and :954)
-  e.add_g(M1E(M1_B, dr), mk(-gbd, 0.0));
-  e.add_g(M1E(M1_B, sr), mk(-gbs, 0.0));
-  e.add_g(M1E(dr, M1_B), mk(-gbd + gmbs, 0.0));
-  e.add_g(M1E(sr, M1_B), mk(-gbs - gmbs, 0.0));
-  e.add_g(M1E(dx, dr), mk(-grd, 0.0));
-  e.add_g(M1E(dr, dx), mk(-grd, 0.0));
-  e.add_g(M1E(dx, dx), mk(grd, 0.0));
-  e.add_g(M1E(sx, sr), mk(-grs, 0.0));
-  e.add_g(M1E(sr, sx), mk(-grs, 0.0));
-  e.add_g(M1E(sx, sx), mk(grs, 0.0));
+  e.add_g_at(M1E(dr, dr), mk(gds + grd + gbd, gcgd));
+  e.add_g_at(M1E(sr, sr), mk(gm + gds + grs + gbs + gmbs, gcgs));
+  e.add_g_at(M1E(dr, sr), mk(-gm - gds - gmbs, 0.0));
+  e.add_g_at(M1E(sr, dr), mk(-gds, 0.0));
+  e.add_g_at(M1E(dr, M1_G), mk(gm, -gcgd));
+  e.add_g_at(M1E(sr, M1_G), mk(-gm, -gcgs));
+  e.add_g_at(M1E(M1_G, M1_G), mk(0.0, gcgd + gcgs + gcgb));
+  e.add_g_at(M1E(M1_B, M1_B), mk(gbd + gbs, gcgb));
+  e.add_g_at(M1E(M1_G, M1_B), mk(0.0, -gcgb));
+  e.add_g_at(M1E(M1_G, dr), mk(0.0, -gcgd));
+  e.add_g_at(M1E(M1_G, sr), mk(0.0, -gcgs));
+  e.add_g_at(M1E(M1_B, M1_G), mk(0.0, -gcgb));
+  e.add_g_dup(M1E(M1_G, dr), M1_DUP_GDR, mk(0.0, -gcgd));  // pushed twice by the reference (mos.rs:951 and :954)
+  e.add_g_at(M1E(M1_B, dr), mk(-gbd, 0.0));
+  e.add_g_at(M1E(M1_B, sr), mk(-gbs, 0.0));
+  e.add_g_at(M1E(dr, M1_B), mk(-gbd + gmbs, 0.0));
+  e.add_g_at(M1E(sr, M1_B), mk(-gbs - gmbs, 0.0));
+  e.add_g_at(M1E(dx, dr), mk(-grd, 0.0));
+  e.add_g_at(M1E(dr, dx), mk(-grd, 0.0));
+  e.add_g_at(M1E(dx, dx), mk(grd, 0.0));
+  e.add_g_at(M1E(sx, sr), mk(-grs, 0.0));
+  e.add_g_at(M1E(sr, sx), mk(-grs, 0.0));
+  e.add_g_at(M1E(sx, sx), mk(grs, 0.0));
 }
 #undef M1E
 

@@ -59,7 +59,43 @@ struct SolveCtl {
   size_t par_inst_stride;  // 1: parameter/state instance == workspace instance; 0: all columns use instance 0 (AC sweep)
 };
 
+// Extra shared tables of the cooperative kernel (kernels/coop.cu): staged assembly + level schedules (host/symbolic.hpp).
+struct CoopTables {
+  int n_stage;               // staging slots (sum over devices of their itab length, +1 per Mos1)
+  const int* stage_off;      // [n_dev] first staging slot of each device
+  const int* eval_order;     // [n_dev] device ids sorted by type (keeps warps convergent when a warp spans devices)
+  const int *asm_off, *asm_src;  // [nnz + N + 1], gather lists
+  int n_lu_lvl, n_fw_lvl, n_bw_lvl;
+  const int *lu_lvl_off, *lu_t, *lu_u, *lu_l;
+  const int *fw_lvl_off, *fw_k, *fw_row, *fw_slot;
+  const int *bw_lvl_off, *bw_row;
+};
+
+// Launch geometry of the cooperative kernel: a CTA of `threads` threads (a multiple of `gi`) owns `gi` consecutive
+// instances and keeps their whole workspace in `smem_bytes` of shared memory (0 = workspace stays in HBM, read through
+// L1). All shared index tables (DevTables ints, PlanTables, CoopTables) must live in ONE device allocation, the arena;
+// with arena_in_smem the kernel TMA-copies it into shared memory and rebases the table pointers.
+struct CoopCfg {
+  int gi, threads;
+  size_t smem_bytes;
+  const int* arena;
+  size_t arena_bytes;  // multiple of 16
+  bool arena_in_smem;
+};
+// Shared-memory budget of one CTA: control words + (optional) arena copy + workspace.
+size_t coop_ctrl_bytes(int gi);
+size_t coop_work_bytes(int N, int nnz, int n_stage, int n_state, int gi, int scalar_width);
+int coop_max_smem_optin(int device);
+
 // All launchers enqueue on `stream` (a cudaStream_t) and return a cudaError_t as int.
+// Cooperative variants: same contracts as launch_dcop / launch_tran / launch_ac, bit-identical results.
+int launch_coop_dcop(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<double>& w, double* stage,
+                     const NewtonOut& o, const SolveCtl& c, const CoopCfg& cfg, void* stream);
+int launch_coop_tran(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<double>& w, double* stage,
+                     const NewtonOut& o, const SolveCtl& c, const CoopCfg& cfg, int T, const int* save_vars, int n_save, double* wave,
+                     void* stream);
+int launch_coop_ac(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<cplx>& w, cplx* stage,
+                   const NewtonOut& o, const SolveCtl& c, const CoopCfg& cfg, void* stream);
 int launch_dcop(const DevTables& d, const PlanTables& p, const WorkTables<double>& w, const NewtonOut& o, const SolveCtl& c, void* stream);
 // OP must already be solved and committed; runs points 1..T-1 of Tran::solve. wave: [T][n_save][w.stride] device (point 0 written too).
 int launch_tran(const DevTables& d, const PlanTables& p, const WorkTables<double>& w, const NewtonOut& o, const SolveCtl& c, int T,

@@ -57,6 +57,10 @@ struct Env {
   __device__ __forceinline__ void add_b(int var, T v) {
     if (var >= 0) { T* a = rhs + (size_t)var * stride + w; *a = s_add(*a, v); }
   }
+  // direct sinks: one thread owns the instance, so stamps go straight into A / rhs in push order
+  __device__ __forceinline__ void add_g_at(int pos, T v) { add_g(node(pos), v); }
+  __device__ __forceinline__ void add_b_at(int pos, T v) { add_b(node(pos), v); }
+  __device__ __forceinline__ void add_g_dup(int pos, int, T v) { add_g(node(pos), v); }
 };
 template <> __device__ __forceinline__ double Env<double>::volt(int var) const { return var < 0 ? 0.0 : x[(size_t)var * stride + w]; }
 template <> __device__ __forceinline__ double Env<cplx>::volt(int) const { return 0.0; }  // load_ac never reads the guess
