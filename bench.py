@@ -227,7 +227,7 @@ def run_ours(args):
                        "n": st["n"], "nnz_a": st["nnz_a"], "nnz_lu": st["nnz_lu"], "stamp_slots": st["stamps"],
                        "l2": "256 MiB flush write between timed steps (untimed)", "step": "reset (cold start) + batched dcop kernel"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "peak_source": peak_src, "kernel": "s21::k_dcop", "kernel_ms": kernel_ms_avg,
+                         "peak_source": peak_src, "kernel": "s21::k_hyb<double, dcop> (hybrid cooperative Newton kernel)", "kernel_ms": kernel_ms_avg,
                          "algorithmic_bytes_per_iteration": bi},
             "e2e": {"value": tot_iters * e2e_steps / tot_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * tot_e2e / e2e_steps, "steps": e2e_steps,

@@ -18,7 +18,7 @@ flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
 stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
 ref = None
-for kernel, gi, th in [("direct", 0, 0)] + [("coop", g, t) for g in (32, 16, 8, 4) for t in (32, 64, 128, 256) if t >= g]:
+for kernel, gi, th in [("direct", 0, 0), ("hybrid", 0, 0)] + [("coop", g, t) for g in (32, 16) for t in (128, 256)]:
     os.environ["S21_KERNEL"] = kernel
     if gi:
         os.environ["S21_COOP_GI"], os.environ["S21_COOP_THREADS"] = str(gi), str(th)

@@ -135,7 +135,11 @@ class Batch {
     si_ = make_stage_info(flat_);
     d_stage_off_.upload(si_.stage_off, stream_);
     d_eval_order_.upload(si_.eval_order, stream_);
-    if (const char* k = std::getenv("S21_KERNEL")) use_coop_ = std::string(k) != "direct";
+    if (const char* k = std::getenv("S21_KERNEL")) {
+      const std::string v(k);
+      use_coop_ = v != "direct";
+      allow_hybrid_ = v != "coop" && v != "direct";
+    }
     max_smem_ = (size_t)coop_max_smem_optin(device_);
     // workspace
     x_.alloc((size_t)N * Bs_); rhs_.alloc((size_t)N * Bs_); c_.alloc((size_t)N * Bs_);
@@ -144,6 +148,7 @@ class Batch {
     ensure_lu_rows((size_t)flat_.n_elems());
     params_dirty_ = true;
     reset();
+    materialize_reset();
   }
   ~Batch() {
     cudaSetDevice(device_);
@@ -169,7 +174,12 @@ class Batch {
     rebuild_ = true;
   }
 
-  void reset() {  // a fresh Solver: x = 0, op = guess = Default (all zeros)
+  // A fresh Solver: x = 0, op = guess = Default (all zeros), counters cleared. Lazy: the hybrid dcop kernel folds the
+  // reset into its prologue (it then never reads the old x / state from HBM); every other consumer materialises it.
+  void reset() { reset_pending_ = true; }
+  void materialize_reset() {
+    if (!reset_pending_) return;
+    reset_pending_ = false;
     S21_CUDA(cudaSetDevice(device_));
     S21_CUDA(cudaMemsetAsync(x_.p, 0, x_.n * sizeof(double), stream_));
     S21_CUDA(cudaMemsetAsync(st_op_.p, 0, st_op_.n * sizeof(double), stream_));
@@ -206,6 +216,7 @@ class Batch {
   }
   void read(double* x, int32_t* status, int32_t* iters) {
     S21_CUDA(cudaSetDevice(device_));
+    materialize_reset();
     const int N = flat_.n_vars();
     if (x) {
       hx_.alloc((size_t)N * Bs_);
@@ -233,6 +244,7 @@ class Batch {
   // ---- tran -----------------------------------------------------------------------------------------------
   void tran(double tstep, int T, const int32_t* save_vars, size_t n_save, double* wave, int32_t* status, int64_t* iters) {
     S21_CUDA(cudaSetDevice(device_));
+    materialize_reset();
     sync_params(false);
     launches_ = 0;
     ensure_plan(op_plan_, AN_OP, 0.0);
@@ -250,6 +262,9 @@ class Batch {
     int rc = 0;
     if (tran_plan_.host.status != ST_OK) {
       throw S21Error(tran_plan_.host.status, status_text(tran_plan_.host.status));
+    } else if (CoopCfg hcfg; use_coop_ && use_hybrid(tran_plan_, 1, &hcfg)) {
+      rc = launch_hybrid_tran(coop_dev(tran_plan_), tran_plan_.coop_plan(), tran_plan_.coop(), work(), out(), ctl, hcfg, T, d_save_.p,
+                              (int)n_save, d_wave_.p, stream_);
     } else if (use_coop_) {
       CoopCfg cfg = coop_cfg(tran_plan_, B_, 1);
       rc = launch_coop_tran(coop_dev(tran_plan_), tran_plan_.coop_plan(), tran_plan_.coop(), work(), stage_for(cfg, tran_plan_.host),
@@ -277,6 +292,7 @@ class Batch {
   // ---- ac: frequency points are the batch axis of circuit instance 0 ------------------------------------------
   void ac(const double* freqs, size_t F, double* x_out, int32_t* status, int32_t* iters) {
     S21_CUDA(cudaSetDevice(device_));
+    materialize_reset();
     for (const FlatDev& d : flat_.devs)
       if (d.type != DT_R && d.type != DT_C && d.type != DT_V && d.type != DT_MOS1)
         throw S21Error(ST_UNSUPPORTED, "AC Not Implemented For This Component!");  // comps/mod.rs:86-88
@@ -329,7 +345,10 @@ class Batch {
     o.status = ac_status_.p; o.iters = ac_iters_.p; o.loads = ac_loads_.p;
     DevTables dt = dev_tables(ac_plan_.itab.p);
     int rc;
-    if (use_coop_) {
+    CoopCfg hcfg;
+    if (use_coop_ && use_hybrid(ac_plan_, 2, &hcfg)) {
+      rc = launch_hybrid_ac(coop_dev(ac_plan_), ac_plan_.coop_plan(), ac_plan_.coop(), w, o, ctl, hcfg, stream_);
+    } else if (use_coop_) {
       CoopCfg cfg = coop_cfg(ac_plan_, F, 2);
       cplx* stage = nullptr;
       if (cfg.smem_bytes == 0) { zstage_.alloc((size_t)ac_plan_.host.n_stage * Fs); stage = zstage_.p; }
@@ -406,7 +425,8 @@ class Batch {
   DBuf<int> d_stage_off_, d_eval_order_;
   DBuf<double> d_stage_;
   DBuf<cplx> zstage_;
-  bool use_coop_ = true;
+  bool use_coop_ = true, allow_hybrid_ = true;
+  bool reset_pending_ = false;
   size_t max_smem_ = 0;
 
   // Launch geometry of the cooperative kernel: the largest instance group per CTA that still leaves >= 2 CTAs per SM
@@ -438,6 +458,17 @@ class Batch {
     if (const char* e = std::getenv("S21_COOP_THREADS")) cfg.threads = std::max(32, std::min(256, std::atoi(e) / 32 * 32));
     cfg.threads = std::max(cfg.threads, gi);
     return cfg;
+  }
+  // Small circuits take the hybrid kernel: its whole footprint must leave room for >= 2 CTAs per SM.
+  bool use_hybrid(const PlanDevice& pd, int width, CoopCfg* cfg) const {
+    if (!allow_hybrid_) return false;
+    const Plan& P = pd.host;
+    const size_t need = hybrid_smem_bytes(P.N, P.nnzLU, P.n_stage, flat_.n_state, pd.arena_bytes, width);
+    if (need > max_smem_ / 2 || P.N > 96) return false;
+    cfg->gi = 32; cfg->threads = 256;
+    cfg->arena = pd.arena.p; cfg->arena_bytes = pd.arena_bytes; cfg->arena_in_smem = true;
+    cfg->smem_bytes = hybrid_work_bytes(P.N, P.nnzLU, P.n_stage, flat_.n_state, width);
+    return true;
   }
   double* stage_for(const CoopCfg& cfg, const Plan& P) {
     if (cfg.smem_bytes) return nullptr;
@@ -476,6 +507,7 @@ class Batch {
   }
   void run_op() {
     if (op_plan_.host.status != ST_OK) {  // the reference fails in its first factorisation: every instance reports it
+      materialize_reset();
       std::vector<int32_t> st(Bs_, op_plan_.host.status);
       S21_CUDA(cudaMemcpyAsync(status_.p, st.data(), Bs_ * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
       S21_CUDA(cudaStreamSynchronize(stream_));
@@ -483,11 +515,18 @@ class Batch {
     }
     DevTables dt = dev_tables(op_plan_.itab.p);
     int rc;
-    if (use_coop_) {
+    CoopCfg hcfg;
+    if (use_coop_ && use_hybrid(op_plan_, 1, &hcfg)) {
+      hcfg.cold = reset_pending_;
+      reset_pending_ = false;
+      rc = launch_hybrid_dcop(coop_dev(op_plan_), op_plan_.coop_plan(), op_plan_.coop(), work(), out(), make_ctl(AN_OP, 0.0), hcfg, stream_);
+    } else if (use_coop_) {
+      materialize_reset();
       CoopCfg cfg = coop_cfg(op_plan_, B_, 1);
       rc = launch_coop_dcop(coop_dev(op_plan_), op_plan_.coop_plan(), op_plan_.coop(), work(), stage_for(cfg, op_plan_.host), out(),
                             make_ctl(AN_OP, 0.0), cfg, stream_);
     } else {
+      materialize_reset();
       rc = launch_dcop(dt, op_plan_.tables(), work(), out(), make_ctl(AN_OP, 0.0), stream_);
     }
     launches_++;
@@ -496,6 +535,7 @@ class Batch {
   // Symbolic phase for one analysis mode: probe instance 0's first load sweep on the GPU, pivot on the host.
   void ensure_plan(PlanDevice& pd, int mode, double dt) {
     if (pd.valid) return;
+    materialize_reset();
     const int N = flat_.n_vars();
     DevTables dtab = dev_tables(d_itab_raw_.p);
     DBuf<double> probe;

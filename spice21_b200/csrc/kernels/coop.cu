@@ -20,116 +20,13 @@
 //
 // Replaces the same reference functions as newton.cu (analysis.rs:153-210, 253-303, 331-345, 553-570;
 // sparse21/mod.rs:272-327, 865-991).
-#include <cuda_runtime.h>
-
-#include <type_traits>
-
-#include "devices.cuh"
-#include "engine.hpp"
+#include "coop_common.cuh"
 
 namespace s21 {
 
+using namespace coopk;
+
 namespace {
-
-enum { K_DCOP = 0, K_TRAN = 1, K_AC = 2 };
-enum { CST_OK = 0, CST_CONV = 1, CST_SINGULAR = 2 };
-
-// ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier (sm_90+; SASS: UBLKCP + SYNCS)
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
-               "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done = 0;
-  while (!done) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done)
-                 : "r"(smem_u32(bar)), "r"(parity)
-                 : "memory");
-  }
-}
-
-template <class T, class I>
-struct EnvS {  // staged Env (see devices.cuh): stamps go to this device's private staging slots
-  const int* it;
-  const int* pc;
-  const double* pval;
-  size_t pinst;
-  double* sop;      // already offset to (state_off, instance); element k at sop[k * sstride]
-  double* sguess;
-  I sstride;
-  const T* x;       // already offset to the instance column; variable v at x[v * xstride]
-  T* S;             // already offset to (stage_off, instance); position p at S[p * xstride]
-  I xstride;
-  int mode;
-  double dt, gmin, omega;
-  __device__ __forceinline__ int node(int k) const { return it[k]; }
-  __device__ __forceinline__ double par(int k) const {
-    const int c = pc[k];
-    return __ldg(pval + (size_t)(c >> 1) + (size_t)(c & 1) * pinst);
-  }
-  __device__ __forceinline__ double volt(int var) const {
-    if constexpr (std::is_same<T, double>::value) return var < 0 ? 0.0 : x[(I)var * xstride];
-    else return 0.0;  // load_ac never reads the guess
-  }
-  __device__ __forceinline__ double op(int k) const { return sop[(I)k * sstride]; }
-  __device__ __forceinline__ double guess(int k) const { return sguess[(I)k * sstride]; }
-  __device__ __forceinline__ void set_guess(int k, double v) { sguess[(I)k * sstride] = v; }
-  __device__ __forceinline__ void add_g_at(int pos, T v) { S[(I)pos * xstride] = v; }
-  __device__ __forceinline__ void add_b_at(int pos, T v) { S[(I)pos * xstride] = v; }
-  __device__ __forceinline__ void add_g_dup(int, int dup, T v) { S[(I)dup * xstride] = v; }
-};
-
-template <class T, class E> __device__ __forceinline__ void load_one(int type, E& e) {
-  if constexpr (std::is_same<T, double>::value) {
-    switch (type) {
-      case DT_R: load_resistor(e); break;
-      case DT_C: load_capacitor(e); break;
-      case DT_I: load_isrc(e); break;
-      case DT_V: load_vsrc(e); break;
-      case DT_DIODE: load_diode(e); break;
-      case DT_MOS0: load_mos0(e); break;
-      case DT_MOS1: load_mos1(e); break;
-      default: break;
-    }
-  } else {
-    switch (type) {
-      case DT_R: load_ac_resistor(e); break;
-      case DT_C: load_ac_capacitor(e); break;
-      case DT_V: load_ac_vsrc(e); break;
-      case DT_MOS1: load_ac_mos1(e); break;
-      default: break;  // the host refuses AC for devices without load_ac before launching
-    }
-  }
-}
-
-template <class T> struct TolC;
-template <> struct TolC<double> {
-  static __device__ __forceinline__ bool ok(double a, double tol) { return !(a > tol); }
-  static const int max_iter = 100;
-};
-template <> struct TolC<cplx> {
-  static __device__ __forceinline__ bool ok(double a, double tol) { return a < tol; }
-  static const int max_iter = 20;
-};
-
-struct CoopArgs {
-  int lg_gi;
-  int T_points, n_save;
-  const int* save_vars;
-  double* wave;
-  const int* arena;      // packed index tables in HBM (all table pointers point into it)
-  int arena_bytes;       // > 0: copy the arena into shared memory with TMA and rebase the pointers
-};
 
 template <class T, int KIND, bool SMEM>
 __global__ void __launch_bounds__(256, 2) k_coop(DevTables d, PlanTables p, CoopTables ct, WorkTables<T> g, T* gstage, NewtonOut o,
@@ -392,7 +289,7 @@ template <class T, int KIND>
 int launch(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<T>& w, T* stage, const NewtonOut& o,
            const SolveCtl& c, const CoopCfg& cfg, int T_points, const int* save_vars, int n_save, double* wave, void* stream) {
   CoopArgs a;
-  a.lg_gi = lg2(cfg.gi); a.T_points = T_points; a.n_save = n_save; a.save_vars = save_vars; a.wave = wave;
+  a.lg_gi = lg2(cfg.gi); a.cold = 0; a.T_points = T_points; a.n_save = n_save; a.save_vars = save_vars; a.wave = wave;
   a.arena = cfg.arena; a.arena_bytes = cfg.arena_in_smem ? (int)cfg.arena_bytes : 0;
   const size_t smem = ctrl_bytes(cfg.gi) + (size_t)a.arena_bytes + cfg.smem_bytes;
   const int grid = (c.B + cfg.gi - 1) / cfg.gi;

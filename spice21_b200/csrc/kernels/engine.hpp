@@ -81,6 +81,7 @@ struct CoopCfg {
   const int* arena;
   size_t arena_bytes;  // multiple of 16
   bool arena_in_smem;
+  bool cold = false;   // hybrid kernel only: start from x = 0 / zero device state instead of loading them (a folded reset)
 };
 // Shared-memory budget of one CTA: control words + (optional) arena copy + workspace.
 size_t coop_ctrl_bytes(int gi);
@@ -96,6 +97,16 @@ int launch_coop_tran(const DevTables& d, const PlanTables& p, const CoopTables& 
                      void* stream);
 int launch_coop_ac(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<cplx>& w, cplx* stage,
                    const NewtonOut& o, const SolveCtl& c, const CoopCfg& cfg, void* stream);
+// Hybrid variants (kernels/hybrid.cu) for small circuits: 32 instances per 256-thread CTA, workspace + arena always in
+// shared memory (cfg.gi / cfg.threads are ignored; cfg.smem_bytes = hybrid_work_bytes(...)). Bit-identical results.
+size_t hybrid_smem_bytes(int N, int nnz, int n_stage, int n_state, size_t arena_bytes, int scalar_width);
+size_t hybrid_work_bytes(int N, int nnz, int n_stage, int n_state, int scalar_width);
+int launch_hybrid_dcop(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<double>& w, const NewtonOut& o,
+                       const SolveCtl& c, const CoopCfg& cfg, void* stream);
+int launch_hybrid_tran(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<double>& w, const NewtonOut& o,
+                       const SolveCtl& c, const CoopCfg& cfg, int T, const int* save_vars, int n_save, double* wave, void* stream);
+int launch_hybrid_ac(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<cplx>& w, const NewtonOut& o,
+                     const SolveCtl& c, const CoopCfg& cfg, void* stream);
 int launch_dcop(const DevTables& d, const PlanTables& p, const WorkTables<double>& w, const NewtonOut& o, const SolveCtl& c, void* stream);
 // OP must already be solved and committed; runs points 1..T-1 of Tran::solve. wave: [T][n_save][w.stride] device (point 0 written too).
 int launch_tran(const DevTables& d, const PlanTables& p, const WorkTables<double>& w, const NewtonOut& o, const SolveCtl& c, int T,
