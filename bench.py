@@ -210,9 +210,11 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         tot_ms, tot_kern_ms, tot_e2e = t.tolist()
         # the only collective of the path: gather per-instance iteration counts / status flags to every rank
-        it_all = [torch.empty(B, dtype=torch.int32, device="cuda") for _ in range(world)]
-        dist.all_gather(it_all, torch.from_numpy(iters).to("cuda"))
-        tot_iters = int(sum(int(v.sum().item()) for v in it_all))
+        from spice21_b200.shard import gather_instances
+        it_all = gather_instances(iters, B * world, device="cuda")
+        st_all = gather_instances(status, B * world, device="cuda")
+        assert np.all(st_all == 0)
+        tot_iters = int(it_all.sum())
     if rank == 0:
         peak, peak_src = measured_peak()
         per_inst_cols = (h2d // 8 - 0) // ((B + 31) // 32 * 32) if h2d else 0

@@ -305,15 +305,15 @@ int orc_run_tran(void* ckt, const double* opts5, double tstep, double tstop, int
   } catch (const std::exception& e) { return fail(classify(e), e, err, errlen); }
 }
 
-int orc_run_ac(void* ckt, const double* opts5, unsigned long long fstart, unsigned long long fstop, unsigned long long npts, void** out,
-               char* err, int errlen) {
+int orc_run_ac(void* ckt, const double* opts5, unsigned long long fstart, unsigned long long fstop, unsigned long long npts, long max_points,
+               void** out, char* err, int errlen) {
   try {
     Options o = make_opts(opts5);
     Ckt c = build_ckt(*(CktSpec*)ckt, {}, nullptr, &o);
     AcOptions a;
     a.fstart = fstart; a.fstop = fstop; a.npts = npts;
     SolveStats st_op, st_ac;
-    AcResult r = ac(c, o, a, &st_op, &st_ac);
+    AcResult r = ac(c, o, a, &st_op, &st_ac, (size_t)max_points);
     auto* res = new Result();
     set_names(res, r.signals);
     res->npts = (int)r.freq.size();

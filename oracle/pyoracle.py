@@ -136,12 +136,12 @@ class Circuit:
                       max_points, C.byref(out), err, 512), err)
         return Result(out)
 
-    def ac(self, fstart=0, fstop=0, npts=0, opts=None):
+    def ac(self, fstart=0, fstop=0, npts=0, opts=None, max_points=0):
         out, err = C.c_void_p(), C.create_string_buffer(512)
         o = _opts5(opts)
         f = lib().orc_run_ac
-        f.argtypes = [C.c_void_p, C.c_void_p, C.c_ulonglong, C.c_ulonglong, C.c_ulonglong, C.POINTER(C.c_void_p), C.c_char_p, C.c_int]
-        self._check(f(self.h, o.ctypes.data_as(C.c_void_p), int(fstart), int(fstop), int(npts), C.byref(out), err, 512), err)
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_ulonglong, C.c_ulonglong, C.c_ulonglong, C.c_long, C.POINTER(C.c_void_p), C.c_char_p, C.c_int]
+        self._check(f(self.h, o.ctypes.data_as(C.c_void_p), int(fstart), int(fstop), int(npts), int(max_points), C.byref(out), err, 512), err)
         return Result(out)
 
     def structure(self, ic=None, opts=None):

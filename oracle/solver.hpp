@@ -216,8 +216,9 @@ struct Tran {  // analysis.rs:489-574
 struct AcOptions { uint64_t fstart = 0, fstop = 0, npts = 0; };  // analysis.rs:701-713
 
 // analysis.rs:761-832 (stream.ac.json / ac.json side effects omitted)
+// max_points: oracle-only bound so tests can check a prefix of a long sweep (0 = unbounded)
 inline AcResult ac(const Ckt& ckt, const Options& opts, const AcOptions& args, SolveStats* op_stats = nullptr,
-                   SolveStats* ac_stats = nullptr) {
+                   SolveStats* ac_stats = nullptr, size_t max_points = 0) {
   Solver<double> re = Solver<double>::make(ckt, opts);
   AnalysisInfo op;
   op.kind = AnalysisInfo::OP;
@@ -239,6 +240,7 @@ inline AcResult ac(const Ckt& ckt, const Options& opts, const AcOptions& args, S
     results.freq.push_back(f);
     results.data.push_back(fsoln);
     if (f == fstop) break;
+    if (max_points && results.freq.size() >= max_points) break;
     f = std::fmin(f * fstep, fstop);
   }
   if (ac_stats) *ac_stats = solver.stats;

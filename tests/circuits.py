@@ -317,3 +317,35 @@ def diffpair_mc(B, first_instance=0):
         "R:r1:g": 5e-5 * (1 + 0.01 * z[:, 4]),
         "R:r2:g": 5e-5 * (1 + 0.01 * z[:, 5]),
     }
+
+
+def rc_opamp(n_sections=64):
+    """an RC ladder (g = 1e-3 S, 1 pF per section) driving a two-stage Mos1 op-amp in unity-gain
+    feedback (diff pair + PMOS mirror, PMOS common-source second stage, 2 pF Miller capacitor). Biasing uses resistors and
+    diode-connected devices only — Isrc and Diode have no load_ac in the reference (comps/mod.rs:86-88). The feedback keeps
+    every small-signal node voltage of order 1, which the reference's AC Newton shell needs (1.0 step cap, 20 iterations,
+    analysis.rs:258-293). PMOS uses a positive vt0: the reference does not multiply vt0 by the polarity (mos.rs:670-676)."""
+    c = Ckt(name="rc_opamp")
+    c.define("mos1model", "nch", 0, **C2_MODEL).define("mos1model", "pch", 1, **C2_MODEL)
+    c.define("mos1inst", "n10", **C2_INST).define("mos1inst", "p20", **dict(C2_INST, w=20e-6))
+    c.V("vsup", "vdd", GND, 1.8)
+    c.V("vin", "l0", GND, 0.9, acm=1.0)
+    for k in range(n_sections):
+        c.R(f"rl{k}", f"l{k}", f"l{k + 1}", 1e-3)
+        c.C(f"cl{k}", f"l{k + 1}", GND, 1e-12)
+    inp = f"l{n_sections}"
+    # bias: resistor into a diode-connected NMOS sets the mirror gate
+    c.R("rbias", "vdd", "nb", 2e-5)
+    c.M("m6", "nch", "n10", d="nb", g="nb", s=GND, b=GND)
+    # first stage
+    c.M("m5", "nch", "n10", d="tail", g="nb", s=GND, b=GND)
+    c.M("m1", "nch", "n10", d="x1", g="out", s="tail", b=GND)   # inverting input (two inversions to `out`): feedback
+    c.M("m2", "nch", "n10", d="o1", g=inp, s="tail", b=GND)     # non-inverting input: the ladder output
+    c.M("m3", "pch", "p20", d="x1", g="x1", s="vdd", b="vdd")
+    c.M("m4", "pch", "p20", d="o1", g="x1", s="vdd", b="vdd")
+    # second stage + Miller compensation
+    c.M("m7", "pch", "p20", d="out", g="o1", s="vdd", b="vdd")
+    c.M("m8", "nch", "n10", d="out", g="nb", s=GND, b=GND)
+    c.C("cc", "o1", "out", 2e-12)
+    c.C("cload", "out", GND, 1e-12)
+    return c

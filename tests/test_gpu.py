@@ -264,3 +264,82 @@ def test_ac_unsupported(s21):
     with pytest.raises(s21.Spice21Error) as e:
         s21.Batch(c, 1).ac(np.array([1.0, 10.0]))
     assert e.value.status == s21.S21_UNSUPPORTED
+
+
+# ------------------------------------------------------------------------------------------------ config C5 / ragged batches
+def test_ac_rc_opamp_matches_oracle(s21, oracle):
+    """BASELINE config 5 (RC ladder + Mos1 op-amp) at a size the oracle finishes in a fraction of a second."""
+    ck = cc.rc_opamp(64)
+    c = ck.to_s21().elaborate()
+    f = s21.ac_freqs(1, 10**10, 999)
+    x, st, it = s21.Batch(c, 1).ac(f)
+    o = oracle.Circuit(ck.to_text()).ac(fstart=1, fstop=10**10, npts=999)
+    assert np.all(st == 0) and np.array_equal(f, o.axis) and c.names == o.names
+    # SPICE reltol / vntol (north_star tolerance for ac): |dx| <= 1e-3 |x| + 1e-6. The reference warm-starts every point
+    # from the previous frequency and accepts it untouched while |res| < 1e-9 A (analysis.rs:271-279), so on high-impedance
+    # nodes its own answer lags by up to ~1e-3 V; the batched solve starts every point cold and is exact.
+    assert np.all(np.abs(x - o.data) <= 1e-3 * np.abs(o.data) + 1e-6)
+    # exactness: single-point sweeps make the reference start cold too -> agreement to round-off
+    for fq in (1, 10, 1000, 10**5, 10**7, 10**9):
+        o1 = oracle.Circuit(ck.to_text()).ac(fstart=fq, fstop=fq, npts=1)
+        x1, st1, _ = s21.Batch(c, 1).ac(np.array([float(fq)]))
+        assert st1[0] == 0 and o1.data.shape[0] == 1
+        assert np.max(np.abs(x1[0] - o1.data[0])) <= 1e-12 * max(1.0, np.max(np.abs(o1.data[0])))
+
+
+def test_ac_rc_opamp_full_sweep_properties(s21, oracle):
+    """BASELINE config 5 at full size: 100 000 frequency points (end-inclusive sweep, analysis.rs:791-819)."""
+    ck = cc.rc_opamp(64)
+    c = ck.to_s21().elaborate()
+    f = s21.ac_freqs(1, 10**10, 99999)
+    assert len(f) == 100000
+    b = s21.Batch(c, 1)
+    x, st, it = b.ac(f)
+    n = {name: k for k, name in enumerate(c.names)}
+    assert np.all(st == 0) and np.all(it >= 1) and np.all(it <= 3)  # linear problem: 1-2 solves per point
+    assert np.all(x[:, n["l0"]] == 1.0 + 0j)                          # the driven node is exact
+    out = np.abs(x[:, n["out"]])
+    assert abs(out[0] - 1.0) < 1e-3 and np.max(out) < 1.2 and out[-1] < 1e-12  # unity-gain buffer behind a low-pass ladder
+    lad = np.abs(x[:, [n[f"l{k}"] for k in range(65)]])
+    assert np.all(np.diff(lad, axis=1) <= 1e-12)                     # magnitude decays monotonically along the ladder
+    # the first points of the long sweep are the same frequencies the reference would visit: compare with the oracle
+    o = oracle.Circuit(ck.to_text()).ac(fstart=1, fstop=10**10, npts=99999, max_points=1500)
+    assert np.array_equal(o.axis, f[:1500]) and np.all(np.abs(x[:1500] - o.data) <= 1e-3 * np.abs(o.data) + 1e-6)
+    # frequency points are independent: a shuffled batch gives the shuffled answer bit for bit
+    perm = np.random.default_rng(5).permutation(4096)
+    x2, st2, _ = b.ac(f[:4096][perm])
+    assert np.array_equal(x2, x[:4096][perm])
+
+
+@pytest.mark.parametrize("B", [1, 31, 33, 257])
+def test_ragged_batch_sizes(s21, oracle, B):
+    """Batch sizes that do not fill a warp / a CTA."""
+    ck, ovr = cc.diffpair(), cc.diffpair_mc(B)
+    o = oracle.Circuit(ck.to_text()).batch(0, B, overrides=ovr)
+    b = s21.Batch(ck.to_s21().elaborate(), B)
+    for k, v in ovr.items():
+        b.override(k, v)
+    x, st, it = b.dcop()
+    assert np.all(st == 0) and rel_err(x, o["x"], floor=1e-9) <= 1e-9 and np.array_equal(it, o["iters"])
+
+
+@pytest.mark.parametrize("kernel", ["direct", "coop", "hybrid"])
+def test_kernel_variants_bit_identical(s21, kernel, monkeypatch):
+    """The three Newton kernels (one thread per instance, CTA-cooperative, hybrid) perform the same operations in the
+    same order per value: identical bits, identical iteration counts — dcop and transient."""
+    B = 96
+    ck, ovr = cc.diffpair(), cc.diffpair_mc(B)
+
+    def run(k):
+        monkeypatch.setenv("S21_KERNEL", k)
+        b = s21.Batch(ck.to_s21().elaborate(), B)
+        for key, v in ovr.items():
+            b.override(key, v)
+        x, st, it = b.dcop()
+        ro = cc.cmos_ro3(cc.add_mos1_defaults)
+        t, w, st2, it2 = s21.Batch(ro.to_s21().elaborate(ic={"1": 0.0}), 3).tran(1e-11, 5e-10)
+        return x, st, it, w, it2
+
+    ref, got = run("direct"), run(kernel)
+    for a, b_ in zip(ref, got):
+        assert np.array_equal(a, b_)

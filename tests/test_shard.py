@@ -1,0 +1,69 @@
+"""The N>1 path on CPU: instance sharding + the final gather over torch.distributed with the gloo backend, world_size 2
+(and 3, to cover a short last block). The data path itself has no collective."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, n, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from spice21_b200.shard import gather_instances, shard_bounds
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard_bounds(n, rank, world)
+    ids = np.arange(lo, hi)
+    x = np.stack([ids * 1.5, -ids.astype(np.float64)], axis=1)          # stand-in for per-instance solutions
+    iters = (ids % 7).astype(np.int32)                                   # and iteration counts
+    fx, fi = gather_instances(x, n), gather_instances(iters, n)
+    ok = np.array_equal(fx[:, 0], np.arange(n) * 1.5) and np.array_equal(fi, (np.arange(n) % 7).astype(np.int32))
+    q.put((rank, bool(ok), int(fi.sum())))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 8192), (2, 101), (3, 100)])
+def test_shard_and_gather_gloo(world, n):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + world * 7 + n) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res)
+    assert len({s for _, _, s in res}) == 1  # every rank sees the same gathered totals
+
+
+def test_shard_bounds_cover_everything():
+    sys.path.insert(0, ROOT)
+    from spice21_b200.shard import shard_bounds
+    for n in (1, 7, 8192, 100000):
+        for world in (1, 2, 3, 4, 8):
+            b = [shard_bounds(n, r, world) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == n and all(b[k][1] == b[k + 1][0] for k in range(world - 1))
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference`: one JSON line on rank 0 with the contract keys; other ranks print nothing."""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data",
+                "config", "impl", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    env["RANK"] = "1"
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip() == ""
