@@ -349,3 +349,23 @@ def rc_opamp(n_sections=64):
     c.C("cc", "o1", "out", 2e-12)
     c.C("cload", "out", GND, 1e-12)
     return c
+
+
+def inverter_array(n_rings=400, n_stages=25, vdd=1.0):
+    """`n_rings` independent `n_stages`-stage CMOS ring oscillators, 1 fF per stage, all fed from one
+    internal supply node `vddi` that hangs off V(vdd) through a 10 S resistor; every ring gets an initial condition on its
+    first stage. Defaults give 20 000 Mos1 transistors, N = 10 803. Device models are the reference's default Mos1
+    NMOS/PMOS at VDD = 1 V (as in its own ring-oscillator tests, tests.rs:889-947): with the C2 model card at 1.8 V the
+    reference's un-damped Newton loop does not converge on a ring (checked with the oracle), so that variant is not used."""
+    c = Ckt(name="inverter_array")
+    add_mos1_defaults(c)
+    c.V("vsup", "vdd", GND, vdd)
+    c.R("rsup", "vdd", "vddi", 10.0)
+    for r in range(n_rings):
+        for s in range(n_stages):
+            a, b = f"r{r}s{s}", f"r{r}s{(s + 1) % n_stages}"
+            c.M(f"mp{r}_{s}", "pmos", "default", d=b, g=a, s="vddi", b="vddi")
+            c.M(f"mn{r}_{s}", "nmos", "default", d=b, g=a, s=GND, b=GND)
+            c.C(f"c{r}_{s}", b, GND, 1e-15)
+    ic = {f"r{r}s0": 0.0 for r in range(n_rings)}
+    return c, ic
