@@ -56,3 +56,20 @@ with open(OUT2, "w") as f:
     for r in rows:
         f.write("B4BIN(%s, %s, %s, %s, %s)\n" % r)
 print(len(rows), "binned parameters ->", OUT2)
+
+# ---- third table: field inventories of the per-size and per-instance precomputed blocks (bsim4/mod.rs:69-164, 441-676),
+# so the flat device parameter block (bsim4_params.hpp) can be laid out without typing ~350 names.
+SRC3 = "/root/reference/spice21/src/comps/bsim4/mod.rs"
+OUT3 = "spice21_b200/csrc/bsim4/bsim4_fields.inc"
+mod = open(SRC3).read()
+def fields(struct):
+    body = mod[mod.index("struct " + struct):]
+    body = body[:body.index("\n}")]
+    return re.findall(r"pub\(crate\) (?:r#)?(\w+): (\w+)", body)
+with open(OUT3, "w") as f:
+    f.write("// Field inventories: B4S(name) size-dependent block, B4I(name) per-instance block (all stored as double).\n")
+    for n, _ in fields("Bsim4SizeDepParams"):
+        f.write("B4S(%s)\n" % n)
+    for n, _ in fields("Bsim4InternalParams"):
+        f.write("B4I(%s)\n" % n)
+print("field inventories ->", OUT3)
