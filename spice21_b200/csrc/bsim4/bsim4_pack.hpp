@@ -27,6 +27,26 @@ inline void pack_params(const Model& m, const ModelDerived& d, const SizeDep& s,
 #undef B4I
 }
 
+// Instance card from a name -> value bag (bsim4.proto:6-43 field names; unknown keys are an error).
+inline InstSpec inst_from_map(const std::map<std::string, double>& kv) {
+  InstSpec in;
+  for (auto& e : kv) {
+    const std::string& k = e.first;
+    const double x = e.second;
+    if (k == "l") in.l = x; else if (k == "w") in.w = x; else if (k == "nf") in.nf = x; else if (k == "sa") in.sa = x;
+    else if (k == "sb") in.sb = x; else if (k == "sd") in.sd = x; else if (k == "sca") in.sca = x; else if (k == "scb") in.scb = x;
+    else if (k == "scc") in.scc = x; else if (k == "sc") in.sc = x; else if (k == "ad") in.ad = x; else if (k == "as") in.as = x;
+    else if (k == "pd") in.pd = x; else if (k == "ps") in.ps = x; else if (k == "nrd") in.nrd = x; else if (k == "nrs") in.nrs = x;
+    else if (k == "delvto") in.delvto = x; else if (k == "min") in.min = x; else if (k == "rgeomod") in.rgeomod = x;
+    else if (k == "rbdb") in.rbdb = x; else if (k == "rbsb") in.rbsb = x; else if (k == "rbpb") in.rbpb = x; else if (k == "rbps") in.rbps = x;
+    else if (k == "rbpd") in.rbpd = x; else if (k == "xgw") in.xgw = x; else if (k == "ngcon") in.ngcon = x;
+    else if (k == "trnqsmod" || k == "acnqsmod" || k == "rbodymod" || k == "rgatemod" || k == "geomod") {
+      // accepted on the wire, ignored by the reference: the model card's selectors win (bsim4inst.rs:134-146)
+    } else throw ModelError("unknown Bsim4 instance parameter: " + k);
+  }
+  return in;
+}
+
 // Which optional parts of the device exist.
 struct Flavor {
   int rgatemod = 0, rdsmod = 0, rbodymod = 0, trnqsmod = 0;
@@ -37,6 +57,19 @@ inline Flavor flavor_of(const Model& m, const Internal& i) {
   f.rgatemod = (int)i.rgatemod; f.rdsmod = (int)m.rdsmod; f.rbodymod = (int)i.rbodymod; f.trnqsmod = (int)i.trnqsmod;
   f.drain_source_prime = m.rdsmod != 0 || m.tnoimod == 1;
   return f;
+}
+
+// One (model card, instance card) pair reduced to what a device needs: the parameter block and the flavour.
+struct Derived { std::vector<double> par; Flavor flavor; };
+inline Derived derive_device(int mos_type, const std::map<std::string, double>& model_kv, const std::map<std::string, double>& inst_kv) {
+  const Model m = resolve_model(mos_type, model_kv);
+  const ModelDerived d = derive_model(m);
+  const SizeAndInstance si = size_and_instance(m, d, inst_from_map(inst_kv));
+  Derived r;
+  r.par.assign(B4F_COUNT, 0.0);
+  pack_params(m, d, si.s, si.i, r.par.data());
+  r.flavor = flavor_of(m, si.i);
+  return r;
 }
 
 // Matrix elements in the reference's creation order (bsim4solver.rs:28-115): (row node, col node) as B4Node positions.

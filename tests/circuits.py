@@ -209,6 +209,10 @@ def add_mos1_defaults(c):  # tests.rs:1449-1461
     return c.define("mos1model", "default", 0).define("mos1model", "nmos", 0).define("mos1model", "pmos", 1).define("mos1inst", "default")
 
 
+def add_bsim4_defaults(c):  # tests.rs:1462-1473
+    return c.define("bsim4model", "default", 0).define("bsim4model", "nmos", 0).define("bsim4model", "pmos", 1).define("bsim4inst", "default")
+
+
 def add_diode_defaults(c):  # tests.rs:1475-1485
     return c.define("diodemodel", "default").define("diodeinst", "default")
 

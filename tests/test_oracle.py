@@ -19,6 +19,9 @@ def test_sparse21_unit_vectors(oracle):
     (cc.cmos_ro3, cc.add_mos0_defaults, "test_mos0_cmos_ro_tran", 1e-15, 1e-12),  # tests.rs:773-790
     (cc.nmos_ro3, cc.add_mos1_defaults, "test_mos1_nmos_ro_tran", 1e-11, 1e-8),   # tests.rs:993-1008
     (cc.pmos_ro3, cc.add_mos1_defaults, "test_mos1_pmos_ro_tran", 1e-11, 1e-8),   # tests.rs:1036-1051
+    (cc.cmos_ro3, cc.add_bsim4_defaults, "test_bsim4_cmos_ro_tran", 1e-10, 3e-7),  # tests.rs:948-964
+    (cc.nmos_ro3, cc.add_bsim4_defaults, "test_bsim4_nmos_ro_tran", 1e-9, 1e-6),   # tests.rs:1360-1376
+    (cc.pmos_ro3, cc.add_bsim4_defaults, "test_bsim4_pmos_ro_tran", 1e-11, 1e-8),  # tests.rs:1053-1069
 ])
 def test_golden_waveforms(oracle, builder, defaults, fixture, tstep, tstop):
     g = golden(fixture)
@@ -34,6 +37,31 @@ def test_golden_waveforms(oracle, builder, defaults, fixture, tstep, tstop):
 def _dcop(oracle, ckt, **kw):
     r = oracle.Circuit(ckt.to_text()).dcop(**kw)
     return dict(zip(r.names, r.data[0])), r
+
+
+def test_bsim4_nmos_dcop1(oracle):  # bsim4/tests.rs:57-87
+    c = cc.add_bsim4_defaults(Ckt()).M("bsim4", "default", "default", d="gd", g="gd", s=GND, b=GND)
+    c.V("v1", "gd", GND, 1.0).R("r1", "gd", GND, 1e-10)
+    v, _ = _dcop(oracle, c)
+    assert v["gd"] == 1.0
+    assert abs(abs(v["v1"]) - 150e-6) < 1e-6
+
+
+def test_bsim4_pmos_dcop1(oracle):  # bsim4/tests.rs:88-117
+    c = cc.add_bsim4_defaults(Ckt()).M("bsim4", "pmos", "default", d="gd", g="gd", s=GND, b=GND)
+    c.V("v1", "gd", GND, -1.0).R("r1", "gd", GND, 1e-10)
+    v, _ = _dcop(oracle, c)
+    assert v["gd"] == -1.0
+    assert abs(abs(v["v1"]) - 57e-6) < 1e-6
+
+
+def test_bsim4_inv_dcop(oracle):  # bsim4/tests.rs:118-160
+    c = cc.add_bsim4_defaults(Ckt())
+    c.M("p", "pmos", "default", d="d", g="inp", s="vdd", b="vdd").M("n", "nmos", "default", d="d", g="inp", s=GND, b=GND)
+    c.V("vinp", "inp", GND, 0.0).V("vvdd", "vdd", GND, 1.0)
+    v, _ = _dcop(oracle, c)
+    assert v["vdd"] == 1.0 and v["inp"] == 0.0 and v["d"] > 0.95
+    assert abs(v["vinp"]) < 1e-6 and abs(v["vvdd"]) < 1e-6
 
 
 def test_dcop_r_only(oracle):  # tests.rs:22-27
