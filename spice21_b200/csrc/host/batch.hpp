@@ -573,6 +573,10 @@ class Batch {
         int& h = itab[(size_t)d.itab_off + (size_t)k];
         if (h >= 0) h = P.elem_slot[(size_t)h];
       }
+      for (int k : d.push_g) {  // Bsim4: element handles are interleaved with variable slots
+        int& h = itab[(size_t)d.itab_off + (size_t)k];
+        if (h >= 0) h = P.elem_slot[(size_t)h];
+      }
     }
     pd.itab.upload(itab, stream_);
     if (P.status == ST_OK) {
@@ -627,6 +631,8 @@ class Batch {
           else if (o.kind == "mos1inst") hit = d.type == DT_MOS1 && d.params == o.name;
           else if (o.kind == "diodemodel") hit = d.type == DT_DIODE && d.model == o.name;
           else if (o.kind == "diodeinst") hit = d.type == DT_DIODE && d.params == o.name;
+          else if (o.kind == "bsim4model") hit = d.type == DT_BSIM4 && d.model == o.name;
+          else if (o.kind == "bsim4inst") hit = d.type == DT_BSIM4 && d.params == o.name;
           else if (o.kind == "R") hit = d.type == DT_R && d.path == o.name;
           else if (o.kind == "C") hit = d.type == DT_C && d.path == o.name;
           else if (o.kind == "I") hit = d.type == DT_I && d.path == o.name;
@@ -646,7 +652,7 @@ class Batch {
           }
           continue;
         }
-        // Mos1 / Diode: re-run the reference derivation per instance
+        // Mos1 / Diode / Bsim4: re-run the reference derivation per instance
         const int np = d.n_par;
         std::vector<std::vector<double>> cols((size_t)np, std::vector<double>(B_));
         unsigned hw = std::max(1u, std::thread::hardware_concurrency());
@@ -659,19 +665,25 @@ class Batch {
               MosModelSpec mm;
               ParamBag mbag, ibag;
               if (d.type == DT_MOS1) { mm = spec_.mos1_models.at(d.model); ibag = spec_.mos1_insts.at(d.params); }
+              else if (d.type == DT_BSIM4) { mm = spec_.bsim4_models.at(d.model); ibag = spec_.bsim4_insts.at(d.params); }
               else { mbag = spec_.diode_models.at(d.model); ibag = spec_.diode_insts.at(d.params); }
               for (size_t i = t; i < B_; i += nt) {
                 SimOptions o = flat_.opts;
                 for (const Override* ov : mine) {
                   const double v = ov->values[i];
                   if (ov->kind == "opt") o.temp = v;
-                  else if (ov->kind == "mos1model") mm.p.kv[ov->param] = v;
+                  else if (ov->kind == "mos1model" || ov->kind == "bsim4model") mm.p.kv[ov->param] = v;
                   else if (ov->kind == "diodemodel") mbag.kv[ov->param] = v;
                   else ibag.kv[ov->param] = v;
                 }
                 if (d.type == DT_MOS1) {
                   Mos1Derived r = mos1_derive(mm, ibag, o);
                   for (int k = 0; k < np; k++) cols[(size_t)k][i] = r.par[k];
+                } else if (d.type == DT_BSIM4) {
+                  b4::Derived r = b4::derive_device(mm.mos_type, mm.p.kv, ibag.kv);
+                  if (b4::g_push_sequence(r.flavor).size() != d.push_g.size() || b4::b_push_sequence(r.flavor).size() != d.push_b.size())
+                    throw std::runtime_error("a Bsim4 override may not change the device topology (rgatemod/rdsmod/rbodymod/trnqsmod)");
+                  for (int k = 0; k < np; k++) cols[(size_t)k][i] = r.par[(size_t)k];
                 } else {
                   DiodeDerived r = diode_derive(mbag, ibag, o);
                   for (int k = 0; k < np; k++) cols[(size_t)k][i] = r.par[k];

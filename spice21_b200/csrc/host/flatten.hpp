@@ -8,6 +8,7 @@
 #pragma once
 #include <unordered_map>
 
+#include "../bsim4/bsim4_pack.hpp"
 #include "params.hpp"
 
 namespace s21 {
@@ -20,6 +21,7 @@ struct FlatDev {
   std::vector<int> created;      // element handles in create_matrix_elems order (-1 = ground): stamp-map export
   std::string model, params;     // definition names (Mos1 / Diode / Bsim4), for re-derivation under overrides
   bool is_ic = false;
+  std::vector<int> push_g, push_b;  // Bsim4 only: itab slots of this flavour's G / RHS pushes, in push order (bsim4_pack.hpp)
 };
 
 struct FlatCkt {
@@ -203,7 +205,7 @@ class Flattener {
     int d_ = node(c.d, top, ns), g_ = node(c.g, top, ns), s_ = node(c.s, top, ns), b_ = node(c.b, top, ns);
     std::string path = joined(c.name);
     if (spec_.bsim4_models.count(c.model)) {
-      throw S21Error(ST_UNSUPPORTED, "Bsim4 device evaluation is not part of this build yet: " + c.model);
+      bsim4(c, path, d_, g_, s_, b_);
     } else if (spec_.mos1_models.count(c.model)) {
       auto ii = spec_.mos1_insts.find(c.params);
       if (ii == spec_.mos1_insts.end()) throw S21Error(ST_INVALID, "Parameters not defined: " + c.params);
@@ -233,6 +235,50 @@ class Flattener {
     } else {
       throw S21Error(ST_INVALID, "Model not defined: " + c.model);
     }
+  }
+  // Bsim4 (elab.rs:143-146): internal variables per bsim4ports.rs:24-112, elements in the order of bsim4solver.rs:28-115
+  void bsim4(const CompSpec& c, const std::string& path, int d_, int g_, int s_, int b_) {
+    auto ii = spec_.bsim4_insts.find(c.params);
+    if (ii == spec_.bsim4_insts.end()) throw S21Error(ST_INVALID, "Parameters not defined: " + c.params);
+    const MosModelSpec& mm = spec_.bsim4_models.at(c.model);
+    b4::Derived bd;
+    try {
+      bd = b4::derive_device(mm.mos_type, mm.p.kv, ii->second.kv);
+    } catch (const b4::ModelError& e) {
+      throw S21Error(ST_INVALID, e.what());
+    }
+    const b4::Flavor& f = bd.flavor;
+    int nodev[B4N_COUNT];
+    nodev[B4N_D] = d_; nodev[B4N_S] = s_; nodev[B4N_GE] = g_; nodev[B4N_B] = b_;
+    nodev[B4N_DP] = f.drain_source_prime ? new_var(path + ".drain", 0) : d_;
+    nodev[B4N_SP] = f.drain_source_prime ? new_var(path + ".source", 0) : s_;
+    nodev[B4N_GP] = f.rgatemod > 0 ? new_var(path + ".gate", 0) : g_;
+    nodev[B4N_GM] = f.rgatemod == 3 ? new_var(path + ".midgate", 0) : g_;
+    if (f.rbodymod == 1 || f.rbodymod == 2) {
+      nodev[B4N_DB] = new_var(path + ".dbody", 0);
+      nodev[B4N_BP] = new_var(path + ".body", 0);
+      nodev[B4N_SB] = new_var(path + ".sbody", 0);
+    } else {
+      nodev[B4N_DB] = b_; nodev[B4N_BP] = b_; nodev[B4N_SB] = b_;
+    }
+    nodev[B4N_Q] = f.trnqsmod != 0 ? new_var(path + ".charge", 2) : -1;
+    const std::vector<b4::PushSpec> pg = b4::g_push_sequence(f), pb = b4::b_push_sequence(f);
+    int n_itab = B4N_COUNT;
+    for (auto& p : pg) n_itab = std::max(n_itab, p.slot + 1);
+    for (auto& p : pb) n_itab = std::max(n_itab, p.slot + 1);
+    FlatDev& d = begin_dev(DT_BSIM4, path, n_itab, B4F_COUNT, B4S_COUNT, (int)(pg.size() + pb.size()));
+    int* t = it(d);
+    for (int k = 0; k < B4N_COUNT; k++) t[k] = nodev[k];
+    int mp_elem[b4::MP_COUNT];
+    for (int& e : mp_elem) e = -1;
+    for (const b4::ElemSpec& e : b4::matrix_pointers(f)) {
+      mp_elem[e.slot_key] = element(nodev[e.row], nodev[e.col]);
+      d.created.push_back(mp_elem[e.slot_key]);
+    }
+    for (auto& p : pg) { t[p.slot] = mp_elem[p.matp]; d.push_g.push_back(p.slot); }
+    for (auto& p : pb) { t[p.slot] = nodev[p.matp]; d.push_b.push_back(p.slot); }
+    for (int k = 0; k < B4F_COUNT; k++) pp(d)[k] = bd.par[(size_t)k];
+    d.model = c.model; d.params = c.params;
   }
   void module_instance(const CompSpec& c, Namespace& ns) {  // elab.rs:182-239
     auto mi = spec_.modules.find(c.module);

@@ -40,8 +40,9 @@ struct PushLists {
   std::vector<std::pair<int, int>> g;
   std::vector<int> b;
 };
-inline PushLists push_lists(int type, int mode) {
+inline PushLists push_lists(const FlatDev& dev, int mode) {
   PushLists L;
+  const int type = dev.type;
   auto G = [&](int pos) { L.g.push_back({pos, pos}); };
   auto m1 = [](int a, int b) { return M1_E0 + a * 6 + b; };
   switch (type) {
@@ -84,6 +85,10 @@ inline PushLists push_lists(int type, int mode) {
       }
       break;
     }
+    case DT_BSIM4:  // stamp.rs:338-567: same pushes in OP and TRAN; each has its own slot (bsim4_layout.h)
+      for (int slot : dev.push_g) G(slot);
+      L.b = dev.push_b;
+      break;
     default: break;
   }
   return L;
@@ -95,7 +100,7 @@ inline void build_gather(const FlatCkt& flat, const StageInfo& si, int mode, con
   std::vector<std::vector<int>> src((size_t)nt);
   for (size_t k = 0; k < flat.devs.size(); k++) {
     const FlatDev& d = flat.devs[k];
-    const PushLists L = push_lists(d.type, mode);
+    const PushLists L = push_lists(d, mode);
     const int* t = itab.data() + d.itab_off;
     for (auto& ge : L.g) {
       const int h = t[ge.first];

@@ -79,6 +79,7 @@ template <class T, class E> __device__ __forceinline__ void load_one(int type, E
       case DT_DIODE: load_diode(e); break;
       case DT_MOS0: load_mos0(e); break;
       case DT_MOS1: load_mos1(e); break;
+      case DT_BSIM4: load_bsim4(e); break;
       default: break;
     }
   } else {

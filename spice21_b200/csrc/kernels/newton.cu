@@ -86,6 +86,7 @@ __device__ __forceinline__ bool load_sweep<double>(const DevTables& d, Env<doubl
       case DT_DIODE: load_diode(e); break;
       case DT_MOS0: load_mos0(e); break;
       case DT_MOS1: load_mos1(e); break;
+      case DT_BSIM4: load_bsim4(e); break;
       default: return false;
     }
   }

@@ -25,6 +25,9 @@ RO = [
     (cc.cmos_ro3, cc.add_mos0_defaults, "test_mos0_cmos_ro_tran", 1e-15, 1e-12, False),
     (cc.nmos_ro3, cc.add_mos1_defaults, "test_mos1_nmos_ro_tran", 1e-11, 1e-8, True),
     (cc.pmos_ro3, cc.add_mos1_defaults, "test_mos1_pmos_ro_tran", 1e-11, 1e-8, True),
+    (cc.cmos_ro3, cc.add_bsim4_defaults, "test_bsim4_cmos_ro_tran", 1e-10, 3e-7, True),   # tests.rs:948-964
+    (cc.nmos_ro3, cc.add_bsim4_defaults, "test_bsim4_nmos_ro_tran", 1e-9, 1e-6, True),    # tests.rs:1360-1376
+    (cc.pmos_ro3, cc.add_bsim4_defaults, "test_bsim4_pmos_ro_tran", 1e-11, 1e-8, True),   # tests.rs:1053-1069
 ]
 
 
@@ -343,3 +346,89 @@ def test_kernel_variants_bit_identical(s21, kernel, monkeypatch):
     ref, got = run("direct"), run(kernel)
     for a, b_ in zip(ref, got):
         assert np.array_equal(a, b_)
+
+
+# ------------------------------------------------------------------------------------------------ Bsim4
+def _bsim4_amp(nsel=None, psel=None, inst=None):
+    """A CMOS stage with a resistive load and caps, Bsim4 cards given through the C ABI (the wire format carries none)."""
+    c = Ckt().define("bsim4model", "n", 0, **(nsel or {})).define("bsim4model", "p", 1, **(psel or nsel or {}))
+    c.define("bsim4inst", "i", **(inst or {"l": 1e-6, "w": 4e-6}))
+    c.M("mp", "p", "i", d="out", g="inp", s="vdd", b="vdd").M("mn", "n", "i", d="out", g="inp", s=GND, b=GND)
+    c.V("vi", "src", GND, 0.45).R("rg", "src", "inp", 1e-4).V("vd", "vdd", GND, 1.0).R("rl", "out", GND, 1e-6).C("cl", "out", GND, 1e-14)
+    return c
+
+
+BSIM4_IC = {"inp": 0.9, "out": 0.6}  # released at t = 0: gate and drain both move, so every charge term is exercised
+
+
+def test_bsim4_known_answers(s21):  # bsim4/tests.rs:57-160
+    c = cc.add_bsim4_defaults(Ckt()).M("bsim4", "default", "default", d="gd", g="gd", s=GND, b=GND)
+    c.V("v1", "gd", GND, 1.0).R("r1", "gd", GND, 1e-10)
+    v = s21.dcop(c.to_proto())
+    assert v["gd"] == 1.0 and abs(abs(v["v1"]) - 150e-6) < 1e-6
+    c = cc.add_bsim4_defaults(Ckt()).M("bsim4", "pmos", "default", d="gd", g="gd", s=GND, b=GND)
+    c.V("v1", "gd", GND, -1.0).R("r1", "gd", GND, 1e-10)
+    v = s21.dcop(c.to_proto())
+    assert v["gd"] == -1.0 and abs(abs(v["v1"]) - 57e-6) < 1e-6
+    c = cc.add_bsim4_defaults(Ckt())
+    c.M("p", "pmos", "default", d="d", g="inp", s="vdd", b="vdd").M("n", "nmos", "default", d="d", g="inp", s=GND, b=GND)
+    c.V("vinp", "inp", GND, 0.0).V("vvdd", "vdd", GND, 1.0)
+    v = s21.dcop(c.to_proto())
+    assert v["vdd"] == 1.0 and v["inp"] == 0.0 and v["d"] > 0.95 and abs(v["vinp"]) < 1e-6 and abs(v["vvdd"]) < 1e-6
+
+
+BSIM4_VARIANTS = [
+    {}, {"rgatemod": 1}, {"rgatemod": 2}, {"rgatemod": 3}, {"rbodymod": 1}, {"rdsmod": 1}, {"trnqsmod": 1},
+    {"rgatemod": 3, "rbodymod": 1, "rdsmod": 1, "trnqsmod": 1},
+    {"capmod": 0}, {"capmod": 1}, {"capmod": 0, "xpart": 1.0}, {"capmod": 1, "xpart": 0.5}, {"xpart": 1.0}, {"cvchargemod": 1},
+    {"mobmod": 1}, {"mobmod": 2}, {"mobmod": 3}, {"mobmod": 4}, {"mobmod": 5}, {"mobmod": 6},
+    {"igcmod": 1, "igbmod": 1}, {"igcmod": 2, "igbmod": 1, "pigcd": 1.0}, {"gidlmod": 1}, {"diomod": 0}, {"diomod": 2},
+    {"tempmod": 2, "tnom": 40.0}, {"mtrlmod": 1}, {"vtl": 2.0e5}, {"lambda": 2.0e-5}, {"dvtp0": 1e-8, "dvtp4": 0.5, "dvtp2": 0.1},
+    {"jss": 1e-4, "jsd": 1e-4, "cjs": 5e-4, "cjd": 5e-4, "cjsws": 5e-10, "cjswd": 5e-10, "jtss": 1e-4, "jtsd": 1e-4},
+]
+
+
+@pytest.mark.parametrize("sel", BSIM4_VARIANTS, ids=["_".join(f"{k}{v}" for k, v in s_.items()) or "default" for s_ in BSIM4_VARIANTS])
+def test_bsim4_variants_match_oracle(s21, oracle, sel):
+    """Every selector branch of the model: dcop and a short transient on the GPU against the oracle."""
+    ck = _bsim4_amp(sel)
+    o = oracle.Circuit(ck.to_text())
+    c = ck.to_s21().elaborate()
+    b = s21.Batch(c, 1)
+    x, status, iters = b.dcop()
+    od = o.dcop()
+    assert status[0] == 0
+    assert rel_err(x[0], od.data[0], 1e-9) <= 1e-9
+    ot = oracle.Circuit(ck.to_text()).tran(2e-11, 2e-9, ic=BSIM4_IC)
+    t, wave, status, _ = s21.Batch(ck.to_s21().elaborate(ic=BSIM4_IC), 1).tran(2e-11, 2e-9)
+    assert status[0] == 0 and wave.shape[1] == ot.data.shape[0]
+    assert np.max(np.abs(wave[0] - ot.data)) <= 1e-9
+
+
+def test_bsim4_instance_sweep_matches_oracle(s21, oracle):
+    """Per-instance Bsim4 cards (config C4's sweep axis): width / length / threshold shift differ per instance."""
+    B = 96
+    rng = np.random.default_rng(4)
+    ck = _bsim4_amp()
+    w = 4e-6 * (1.0 + 0.2 * rng.standard_normal(B).clip(-2, 2))
+    l = 1e-6 * (1.0 + 0.1 * rng.standard_normal(B).clip(-2, 2))
+    dv = 0.03 * rng.standard_normal(B)
+    ovr = {"bsim4inst:i:w": w, "bsim4inst:i:l": l, "bsim4inst:i:delvto": dv}
+    b = s21.Batch(ck.to_s21().elaborate(), B)
+    for k, v in ovr.items():
+        b.override(k, v)
+    x, status, iters = b.dcop()
+    o = oracle.Circuit(ck.to_text()).batch(0, B, overrides=ovr, nthreads=4)
+    assert np.all(status == 0) and np.all(o["status"] == 0)
+    assert rel_err(x, o["x"].reshape(x.shape), 1e-9) <= 1e-9
+    out = b.ckt.names.index("out")
+    assert len(np.unique(np.round(x[:, out], 9))) > B // 2  # the sweep really differs per instance
+
+
+@pytest.mark.parametrize("kernel", ["direct", "coop", "hybrid"])
+def test_bsim4_kernel_variants_bit_identical(s21, kernel, monkeypatch):
+    ck = cc.cmos_ro3(cc.add_bsim4_defaults)
+    ref = s21.Batch(ck.to_s21().elaborate(ic={"1": 0.0}), 3).tran(1e-10, 2e-8)
+    monkeypatch.setenv("S21_KERNEL", kernel)
+    got = s21.Batch(ck.to_s21().elaborate(ic={"1": 0.0}), 3).tran(1e-10, 2e-8)
+    assert np.array_equal(ref[1], got[1]) and np.array_equal(ref[3], got[3])

@@ -54,6 +54,16 @@ CASES = [
         .D("dd", "p", GND, "default", "default").V("vin", "p", GND, 0.7), None, True),
     ("mos1_rd_rs", lambda: Ckt().define("mos1model", "n", 0, rd=10.0, rs=5.0, vt0=0.4).define("mos1inst", "i")
         .M("m", "n", "i", d="d", g="g", s=GND, b=GND).V("vg", "g", GND, 1.0).V("vd", "d", GND, 1.0), None, True),
+    ("cmos_ro3_bsim4", lambda: cc.cmos_ro3(cc.add_bsim4_defaults), {"1": 0.0}, True),
+    ("nmos_ro3_bsim4", lambda: cc.nmos_ro3(cc.add_bsim4_defaults), {"1": 0.0}, True),
+] + [
+    # every optional Bsim4 sub-network: internal nodes (bsim4ports.rs:24-112) and matrix pointers (bsim4solver.rs:28-115)
+    ("bsim4_" + "_".join(f"{k}{v}" for k, v in sel.items()),
+     (lambda sel=sel: Ckt().define("bsim4model", "n", 0, **sel).define("bsim4model", "p", 1, **sel).define("bsim4inst", "i", l=1e-6, w=2e-6)
+      .M("mp", "p", "i", d="out", g="inp", s="vdd", b="vdd").M("mn", "n", "i", d="out", g="inp", s=GND, b=GND)
+      .V("vi", "inp", GND, 0.4).V("vd", "vdd", GND, 1.0).R("rl", "out", GND, 1e-6)), None, False)
+    for sel in ({"rgatemod": 1}, {"rgatemod": 2}, {"rgatemod": 3}, {"rbodymod": 1}, {"rdsmod": 1}, {"trnqsmod": 1},
+                {"rgatemod": 3, "rbodymod": 1, "rdsmod": 1, "trnqsmod": 1})
 ]
 
 
