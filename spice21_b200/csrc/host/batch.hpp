@@ -503,6 +503,8 @@ class Batch {
     SolveCtl c;
     c.B = (int)B_; c.mode = mode; c.gmin = flat_.opts.gmin; c.dt = dt;
     c.reltol = flat_.opts.reltol; c.iabstol = flat_.opts.iabstol; c.omega = nullptr; c.par_inst_stride = 1;
+    c.has_bsim4 = 0;
+    for (const FlatDev& d : flat_.devs) if (d.type == DT_BSIM4) { c.has_bsim4 = 1; break; }
     return c;
   }
   void run_op() {

@@ -28,7 +28,7 @@ using namespace coopk;
 
 namespace {
 
-template <class T, int KIND, bool SMEM>
+template <class T, int KIND, bool SMEM, bool B4>
 __global__ void __launch_bounds__(256, 2) k_coop(DevTables d, PlanTables p, CoopTables ct, WorkTables<T> g, T* gstage, NewtonOut o,
                                                 SolveCtl ctl, CoopArgs a) {
   typedef typename std::conditional<SMEM, unsigned, size_t>::type I;
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256, 2) k_coop(DevTables d, PlanTables p, Coop
           e.x = x + col; e.xstride = ws;
           e.S = S + (I)ct.stage_off[dev] * ws + col;
           e.mode = ctl.mode; e.dt = ctl.dt; e.gmin = ctl.gmin; e.omega = omega;
-          load_one<T>(d.type[dev], e);
+          load_one<T, B4>(d.type[dev], e);
         }
       }
       if (tid < gi) { resok[tid] = 1; sing[tid] = 0; maxabs[tid] = 0.0; }
@@ -285,8 +285,8 @@ __global__ void __launch_bounds__(256, 2) k_coop(DevTables d, PlanTables p, Coop
 int lg2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
 size_t ctrl_bytes(int gi) { return ((8 + 8 * 4) * (size_t)gi + 8 + 15) / 16 * 16; }
 
-template <class T, int KIND>
-int launch(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<T>& w, T* stage, const NewtonOut& o,
+template <class T, int KIND, bool B4>
+int launch_b4(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<T>& w, T* stage, const NewtonOut& o,
            const SolveCtl& c, const CoopCfg& cfg, int T_points, const int* save_vars, int n_save, double* wave, void* stream) {
   CoopArgs a;
   a.lg_gi = lg2(cfg.gi); a.cold = 0; a.T_points = T_points; a.n_save = n_save; a.save_vars = save_vars; a.wave = wave;
@@ -295,17 +295,26 @@ int launch(const DevTables& d, const PlanTables& p, const CoopTables& ct, const 
   const int grid = (c.B + cfg.gi - 1) / cfg.gi;
   cudaError_t e;
   if (cfg.smem_bytes > 0) {
-    auto kern = k_coop<T, KIND, true>;
+    auto kern = k_coop<T, KIND, true, B4>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<grid, cfg.threads, smem, (cudaStream_t)stream>>>(d, p, ct, w, stage, o, c, a);
   } else {
-    auto kern = k_coop<T, KIND, false>;
+    auto kern = k_coop<T, KIND, false, B4>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<grid, cfg.threads, smem, (cudaStream_t)stream>>>(d, p, ct, w, stage, o, c, a);
   }
   return (int)cudaGetLastError();
+}
+
+template <class T, int KIND>
+int launch(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<T>& w, T* stage, const NewtonOut& o,
+           const SolveCtl& c, const CoopCfg& cfg, int T_points, const int* save_vars, int n_save, double* wave, void* stream) {
+  if constexpr (KIND != K_AC) {
+    if (c.has_bsim4) return launch_b4<T, KIND, true>(d, p, ct, w, stage, o, c, cfg, T_points, save_vars, n_save, wave, stream);
+  }
+  return launch_b4<T, KIND, false>(d, p, ct, w, stage, o, c, cfg, T_points, save_vars, n_save, wave, stream);
 }
 
 }  // namespace

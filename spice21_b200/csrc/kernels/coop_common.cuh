@@ -69,7 +69,7 @@ struct EnvS {  // staged Env (see devices.cuh): stamps go to this device's priva
   __device__ __forceinline__ void add_g_dup(int, int dup, T v) { S[(I)dup * xstride] = v; }
 };
 
-template <class T, class E> __device__ __forceinline__ void load_one(int type, E& e) {
+template <class T, bool B4, class E> __device__ __forceinline__ void load_one(int type, E& e) {
   if constexpr (std::is_same<T, double>::value) {
     switch (type) {
       case DT_R: load_resistor(e); break;
@@ -79,7 +79,7 @@ template <class T, class E> __device__ __forceinline__ void load_one(int type, E
       case DT_DIODE: load_diode(e); break;
       case DT_MOS0: load_mos0(e); break;
       case DT_MOS1: load_mos1(e); break;
-      case DT_BSIM4: load_bsim4(e); break;
+      case DT_BSIM4: if constexpr (B4) load_bsim4(e); break;
       default: break;
     }
   } else {

@@ -57,6 +57,7 @@ struct SolveCtl {
   double reltol, iabstol;  // real solve: |dx| <= reltol (absolute!) and |res| <= iabstol (analysis.rs:331-345)
   const double* omega;     // [B] AC only
   size_t par_inst_stride;  // 1: parameter/state instance == workspace instance; 0: all columns use instance 0 (AC sweep)
+  int has_bsim4 = 0;       // selects the kernel build that links the Bsim4 evaluation (kept out of the others: register pressure)
 };
 
 // Extra shared tables of the cooperative kernel (kernels/coop.cu): staged assembly + level schedules (host/symbolic.hpp).

@@ -37,7 +37,7 @@ constexpr int HY_WARPS = 8;
 constexpr int HY_LPI = 8;    // lanes per instance in the per-warp phases
 constexpr unsigned FULL = 0xffffffffu;
 
-template <class T, int KIND>
+template <class T, int KIND, bool B4>
 __global__ void __launch_bounds__(256, 2) k_hyb(DevTables d, PlanTables p, CoopTables ct, WorkTables<T> g, NewtonOut o, SolveCtl ctl,
                                                CoopArgs a) {
   typedef unsigned I;
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(256, 2) k_hyb(DevTables d, PlanTables p, CoopT
           e.x = x + ei; e.xstride = HY_P;
           e.S = S + (I)ct.stage_off[dev] * HY_P + ei;
           e.mode = ctl.mode; e.dt = ctl.dt; e.gmin = ctl.gmin; e.omega = omega;
-          load_one<T>(d.type[dev], e);
+          load_one<T, B4>(d.type[dev], e);
         }
       }
       PH_T(t1);
@@ -290,19 +290,28 @@ __global__ void __launch_bounds__(256, 2) k_hyb(DevTables d, PlanTables p, CoopT
 
 size_t hyb_ctrl_bytes() { return ((size_t)HY_GI * 4 + 8 + 15) / 16 * 16; }
 
-template <class T, int KIND>
-int launch(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<T>& w, const NewtonOut& o, const SolveCtl& c,
+template <class T, int KIND, bool B4>
+int launch_b4(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<T>& w, const NewtonOut& o, const SolveCtl& c,
            const CoopCfg& cfg, int T_points, const int* save_vars, int n_save, double* wave, void* stream) {
   CoopArgs a;
   a.lg_gi = 5; a.cold = cfg.cold ? 1 : 0; a.T_points = T_points; a.n_save = n_save; a.save_vars = save_vars; a.wave = wave;
   a.arena = cfg.arena; a.arena_bytes = (int)cfg.arena_bytes;
   const size_t smem = hyb_ctrl_bytes() + cfg.arena_bytes + cfg.smem_bytes;
   const int grid = (c.B + HY_GI - 1) / HY_GI;
-  auto kern = k_hyb<T, KIND>;
+  auto kern = k_hyb<T, KIND, B4>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   kern<<<grid, HY_WARPS * 32, smem, (cudaStream_t)stream>>>(d, p, ct, w, o, c, a);
   return (int)cudaGetLastError();
+}
+
+template <class T, int KIND>
+int launch(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<T>& w, const NewtonOut& o, const SolveCtl& c,
+           const CoopCfg& cfg, int T_points, const int* save_vars, int n_save, double* wave, void* stream) {
+  if constexpr (KIND != K_AC) {
+    if (c.has_bsim4) return launch_b4<T, KIND, true>(d, p, ct, w, o, c, cfg, T_points, save_vars, n_save, wave, stream);
+  }
+  return launch_b4<T, KIND, false>(d, p, ct, w, o, c, cfg, T_points, save_vars, n_save, wave, stream);
 }
 
 }  // namespace

@@ -67,11 +67,8 @@ template <> __device__ __forceinline__ double Env<cplx>::volt(int) const { retur
 
 // One pass of Solver::update (analysis.rs:153-168 / 237-252): every device, in component order.
 // Returns false when a device has no load function for this analysis (the reference panics: comps/mod.rs:86-88).
-template <class T>
-__device__ __forceinline__ bool load_sweep(const DevTables& d, Env<T>& e, double* st_op, double* st_guess);
-
-template <>
-__device__ __forceinline__ bool load_sweep<double>(const DevTables& d, Env<double>& e, double* st_op, double* st_guess) {
+template <bool B4>
+__device__ __forceinline__ bool load_sweep(const DevTables& d, Env<double>& e, double* st_op, double* st_guess) {
   for (int k = 0; k < d.n_dev; k++) {
     e.it = d.itab + __ldg(d.itab_off + k);
     e.pc = d.pcode + __ldg(d.par_off + k);
@@ -86,14 +83,14 @@ __device__ __forceinline__ bool load_sweep<double>(const DevTables& d, Env<doubl
       case DT_DIODE: load_diode(e); break;
       case DT_MOS0: load_mos0(e); break;
       case DT_MOS1: load_mos1(e); break;
-      case DT_BSIM4: load_bsim4(e); break;
+      case DT_BSIM4: if constexpr (B4) load_bsim4(e); else return false; break;
       default: return false;
     }
   }
   return true;
 }
-template <>
-__device__ __forceinline__ bool load_sweep<cplx>(const DevTables& d, Env<cplx>& e, double* st_op, double* st_guess) {
+template <bool B4>
+__device__ __forceinline__ bool load_sweep(const DevTables& d, Env<cplx>& e, double* st_op, double* st_guess) {
   for (int k = 0; k < d.n_dev; k++) {
     e.it = d.itab + __ldg(d.itab_off + k);
     e.pc = d.pcode + __ldg(d.par_off + k);
@@ -127,7 +124,7 @@ __device__ __forceinline__ void commit_state(const DevTables& d, double* st_op, 
 }
 
 // The Newton shell for one instance. Returns an S21 status; *n_solves / *n_loads are incremented.
-template <class T>
+template <class T, bool B4>
 __device__ int newton_solve(const DevTables& d, const PlanTables& p, const WorkTables<T>& wk, const SolveCtl& ctl, size_t inst,
                             double omega, double vtol, double itol, bool do_commit, int* n_solves, int* n_loads) {
   const size_t S = wk.stride;
@@ -147,7 +144,7 @@ __device__ int newton_solve(const DevTables& d, const PlanTables& p, const WorkT
     // Matrix::reset + fresh rhs (analysis.rs:178-179)
     for (int k = 0; k < p.nnz; k++) lu[(size_t)k * S] = Scalar<T>::zero();
     for (int k = 0; k < N; k++) rhs[(size_t)k * S] = Scalar<T>::zero();
-    if (!load_sweep<T>(d, e, wk.st_op, wk.st_guess)) return 6;  // S21_UNSUPPORTED
+    if (!load_sweep<B4>(d, e, wk.st_op, wk.st_guess)) return 6;  // S21_UNSUPPORTED
     *n_loads += 1;
     // Matrix::res (sparse21/mod.rs:298-327), produced directly in internal row order: c[k] = res[row_i2e[k]]
     bool res_ok = true;
@@ -220,16 +217,18 @@ __device__ int newton_solve(const DevTables& d, const PlanTables& p, const WorkT
 }
 
 // ------------------------------------------------------------------------------------------------ kernels
+template <bool B4>
 __global__ void __launch_bounds__(128) k_dcop(DevTables d, PlanTables p, WorkTables<double> w, NewtonOut o, SolveCtl ctl) {
   const size_t inst = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (inst >= (size_t)ctl.B) return;
   int ns = 0, nl = 0;
-  const int st = newton_solve<double>(d, p, w, ctl, inst, 0.0, ctl.reltol, ctl.iabstol, true, &ns, &nl);
+  const int st = newton_solve<double, B4>(d, p, w, ctl, inst, 0.0, ctl.reltol, ctl.iabstol, true, &ns, &nl);
   o.status[inst] = st;
   o.iters[inst] += ns;
   o.loads[inst] += nl;
 }
 
+template <bool B4>
 __global__ void __launch_bounds__(128) k_tran(DevTables d, PlanTables p, WorkTables<double> w, NewtonOut o, SolveCtl ctl, int T,
                                              const int* save_vars, int n_save, double* wave) {
   const size_t inst = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -239,7 +238,7 @@ __global__ void __launch_bounds__(128) k_tran(DevTables d, PlanTables p, WorkTab
   for (int s = 0; s < n_save; s++) wave[(size_t)s * B + inst] = w.x[(size_t)__ldg(save_vars + s) * w.stride + inst];
   int ns = 0, nl = 0;
   for (int tp = 1; tp < T; tp++) {
-    if (st == ST_OK_) st = newton_solve<double>(d, p, w, ctl, inst, 0.0, ctl.reltol, ctl.iabstol, true, &ns, &nl);
+    if (st == ST_OK_) st = newton_solve<double, B4>(d, p, w, ctl, inst, 0.0, ctl.reltol, ctl.iabstol, true, &ns, &nl);
     for (int s = 0; s < n_save; s++) {
       const double v = st == ST_OK_ ? w.x[(size_t)__ldg(save_vars + s) * w.stride + inst] : __longlong_as_double(0x7ff8000000000000LL);
       wave[((size_t)tp * n_save + s) * B + inst] = v;
@@ -255,7 +254,7 @@ __global__ void __launch_bounds__(128) k_ac(DevTables d, PlanTables p, WorkTable
   if (inst >= (size_t)ctl.B) return;
   int ns = 0, nl = 0;
   // hard-coded complex tolerances (analysis.rs:271-272); no commit is observable in AC (load_ac reads only `op`)
-  const int st = newton_solve<cplx>(d, p, w, ctl, inst, ctl.omega[inst], 1e-3, 1e-9, false, &ns, &nl);
+  const int st = newton_solve<cplx, false>(d, p, w, ctl, inst, ctl.omega[inst], 1e-3, 1e-9, false, &ns, &nl);
   o.status[inst] = st;
   o.iters[inst] += ns;
   o.loads[inst] += nl;
@@ -275,19 +274,21 @@ __global__ void k_probe(DevTables d, WorkTables<T> w, SolveCtl ctl, int n_elems,
   e.mode = ctl.mode; e.dt = ctl.dt; e.gmin = ctl.gmin; e.omega = ctl.omega ? ctl.omega[inst] : 0.0;
   for (int k = 0; k < n_elems; k++) w.lu[(size_t)k * w.stride + inst] = Scalar<T>::zero();
   for (int k = 0; k < N; k++) w.rhs[(size_t)k * w.stride + inst] = Scalar<T>::zero();
-  load_sweep<T>(d, e, w.st_op, w.st_guess);
+  load_sweep<true>(d, e, w.st_op, w.st_guess);
   for (int k = 0; k < n_elems; k++) out[k] = w.lu[(size_t)k * w.stride + inst];
 }
 
 static inline int grid_for(int B, int block) { return (B + block - 1) / block; }
 
 int launch_dcop(const DevTables& d, const PlanTables& p, const WorkTables<double>& w, const NewtonOut& o, const SolveCtl& c, void* stream) {
-  k_dcop<<<grid_for(c.B, 128), 128, 0, (cudaStream_t)stream>>>(d, p, w, o, c);
+  if (c.has_bsim4) k_dcop<true><<<grid_for(c.B, 128), 128, 0, (cudaStream_t)stream>>>(d, p, w, o, c);
+  else k_dcop<false><<<grid_for(c.B, 128), 128, 0, (cudaStream_t)stream>>>(d, p, w, o, c);
   return (int)cudaGetLastError();
 }
 int launch_tran(const DevTables& d, const PlanTables& p, const WorkTables<double>& w, const NewtonOut& o, const SolveCtl& c, int T,
                 const int* save_vars, int n_save, double* wave, void* stream) {
-  k_tran<<<grid_for(c.B, 128), 128, 0, (cudaStream_t)stream>>>(d, p, w, o, c, T, save_vars, n_save, wave);
+  if (c.has_bsim4) k_tran<true><<<grid_for(c.B, 128), 128, 0, (cudaStream_t)stream>>>(d, p, w, o, c, T, save_vars, n_save, wave);
+  else k_tran<false><<<grid_for(c.B, 128), 128, 0, (cudaStream_t)stream>>>(d, p, w, o, c, T, save_vars, n_save, wave);
   return (int)cudaGetLastError();
 }
 int launch_ac(const DevTables& d, const PlanTables& p, const WorkTables<cplx>& w, const NewtonOut& o, const SolveCtl& c, void* stream) {
