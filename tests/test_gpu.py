@@ -439,3 +439,39 @@ def test_bsim4_kernel_variants_bit_identical(s21, kernel, monkeypatch):
     monkeypatch.setenv("S21_KERNEL", kernel)
     got = s21.Batch(ck.to_s21().elaborate(ic={"1": 0.0}), 3).tran(1e-10, 2e-8)
     assert np.array_equal(ref[1], got[1]) and np.array_equal(ref[3], got[3])
+
+
+def test_c4_bsim4_ring_sweep_matches_oracle(s21, oracle):
+    """Config C4 (BASELINE.json configs[3]) at a size the oracle finishes in seconds: 21-stage BSIM4 ring, VDD sweep."""
+    B, npts, tstep = 24, 60, 1e-10
+    ck, ic = cc.bsim4_ring(21)
+    ovr = {k: v[::85][:B] for k, v in cc.c4_sweep(2048).items()}  # 24 instances spread over the VDD axis
+    c = ck.to_s21().elaborate(ic=ic)
+    b = s21.Batch(c, B)
+    for k, v in ovr.items():
+        b.override(k, v)
+    t, wave, status, iters = b.tran(tstep, npts * tstep)
+    o = oracle.Circuit(ck.to_text()).batch(1, B, overrides=ovr, tstep=tstep, tstop=npts * tstep, ic=ic, nthreads=8)
+    assert np.all(status == 0) and np.all(o["status"] == 0)
+    assert wave.shape == o["x"].shape
+    assert np.max(np.abs(wave - o["x"])) <= 1e-9
+    vdd = c.names.index("vdd")
+    assert np.allclose(wave[:, -1, vdd], ovr["V:vsup:dc"], rtol=0, atol=1e-12)  # every instance really ran at its own supply
+
+
+def test_c4_ptm65_statuses_match_oracle(s21, oracle):
+    """SURVEY's literal C4 cards (PTM 65 nm): under the reference's Newton loop some supply voltages do not converge.
+    The GPU path must report the same per-instance outcome as the oracle, and the same waveforms where it converges."""
+    B, npts, tstep = 17, 30, 1e-11
+    ck, ic = cc.bsim4_ring(7, cards="ptm65", l=65e-9, wn=200e-9, wp=400e-9)
+    ovr = {"V:vsup:dc": np.linspace(0.8, 1.2, B)}
+    c = ck.to_s21().elaborate(ic=ic)
+    b = s21.Batch(c, B)
+    for k, v in ovr.items():
+        b.override(k, v)
+    t, wave, status, iters = b.tran(tstep, npts * tstep)
+    o = oracle.Circuit(ck.to_text()).batch(1, B, overrides=ovr, tstep=tstep, tstop=npts * tstep, ic=ic, nthreads=8)
+    assert np.array_equal(status != 0, o["status"] != 0)
+    assert 0 < int(np.sum(status == 0)) < B  # the case is only interesting while it mixes outcomes
+    ok = status == 0
+    assert np.max(np.abs(wave[ok] - o["x"][ok])) <= 1e-9
