@@ -19,6 +19,15 @@ def test_abi_symbols_match_header(s21):
         assert hasattr(s21.lib(), sym), sym
 
 
+def test_rust_ffi_declares_every_symbol(s21):
+    """bindings/rust/spice21cu-sys (sources only; no cargo in this image) stays in step with the C header."""
+    import os
+    import re
+    src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "bindings", "rust", "spice21cu-sys", "src", "lib.rs")).read()
+    declared = set(re.findall(r"pub fn (s21_\w+)\(", src))
+    assert declared == set(s21.ABI_SYMBOLS)
+
+
 def test_no_cpu_fallback(s21):
     """Without a CUDA device the compute entry points must fail loudly (never fall back to a CPU path)."""
     if s21.cuda_device_count() > 0:
