@@ -11,6 +11,7 @@
 
 #include "../kernels/engine.hpp"
 #include "flatten.hpp"
+#include "jit.hpp"
 #include "staging.hpp"
 #include "symbolic.hpp"
 
@@ -61,6 +62,9 @@ struct PinnedBuf {  // page-locked host buffer
 struct PlanDevice {
   Plan host;
   bool valid = false;
+  std::vector<int> host_itab;         // itab with element handles translated to L+U slots
+  jit::Kernel jit_dcop, jit_tran;     // circuit-specialised kernels (host/jit.hpp), compiled on first use
+  bool jit_tried_dcop = false, jit_tried_tran = false;
   DBuf<int> row_i2e, col_i2e, col_e2i, rowptr, colidx, diag_slot, l_off, l_slot, l_row, upd_off, upd_t, upd_u, upd_l, itab;
   // cooperative kernel: every shared index table packed into one allocation ("arena") so that a CTA can bring all of
   // them into shared memory with a single TMA bulk copy. Offsets are in ints, each table 16-byte aligned.
@@ -139,6 +143,8 @@ class Batch {
       const std::string v(k);
       use_coop_ = v != "direct";
       allow_hybrid_ = v != "coop" && v != "direct";
+      allow_jit_ = v == "jit";
+      jit_forced_ = allow_jit_;
     }
     max_smem_ = (size_t)coop_max_smem_optin(device_);
     // workspace
@@ -262,6 +268,8 @@ class Batch {
     int rc = 0;
     if (tran_plan_.host.status != ST_OK) {
       throw S21Error(tran_plan_.host.status, status_text(tran_plan_.host.status));
+    } else if (const jit::Kernel* jk = jit_kernel(tran_plan_, true)) {
+      rc = launch_jit(*jk, AN_TRAN, tstep, false, T, d_save_.p, (int)n_save, d_wave_.p);
     } else if (CoopCfg hcfg; use_coop_ && use_hybrid(tran_plan_, 1, &hcfg)) {
       rc = launch_hybrid_tran(coop_dev(tran_plan_), tran_plan_.coop_plan(), tran_plan_.coop(), work(), out(), ctl, hcfg, T, d_save_.p,
                               (int)n_save, d_wave_.p, stream_);
@@ -425,13 +433,56 @@ class Batch {
   DBuf<int> d_stage_off_, d_eval_order_;
   DBuf<double> d_stage_;
   DBuf<cplx> zstage_;
-  bool use_coop_ = true, allow_hybrid_ = true;
+  bool use_coop_ = true, allow_hybrid_ = true, allow_jit_ = true, jit_forced_ = false;
+  std::string jit_error_;  // why the specialised kernel is not in use (empty when it is, or was never wanted)
   bool reset_pending_ = false;
   size_t max_smem_ = 0;
 
   // Launch geometry of the cooperative kernel: the largest instance group per CTA that still leaves >= 2 CTAs per SM
   // (148 SMs) and whose workspace fits in shared memory; HBM-resident workspace when even one instance does not fit.
   DevTables coop_dev(const PlanDevice& pd) const { return pd.coop_dev((int)flat_.devs.size(), d_pval_.p, flat_.n_state); }
+  // Circuit-specialised kernel (host/jit.hpp) for this plan, or nullptr: not wanted, not eligible, or NVRTC unavailable.
+  const jit::Kernel* jit_kernel(PlanDevice& pd, bool tran) {
+    // One thread per instance pays off only when there are enough warps to hide a dependent f64 chain (measured on C2:
+    // hybrid wins at 8192 instances, the specialised kernel from ~64k up; profiles/r01g_*). S21_KERNEL=jit forces it.
+    if (!allow_jit_ || pd.host.status != ST_OK || !jit::eligible(flat_, pd.host, max_smem_)) return nullptr;
+    // One thread per instance has the fewest instructions (no index tables, no synchronisation) but the longest
+    // dependent chain: it wins once there are enough warps to overlap chains. Measured on C2 (profiles/r01g_*): hybrid
+    // 0.229 ms vs 0.284 ms at 8192 instances, 0.87 vs 0.33 ms at 32768, 2.5 G iters/s vs 0.88 G at 1 M.
+    if (!jit_forced_ && B_ < (size_t)12288) return nullptr;
+    jit::Kernel& k = tran ? pd.jit_tran : pd.jit_dcop;
+    bool& tried = tran ? pd.jit_tried_tran : pd.jit_tried_dcop;
+    if (!tried) {
+      tried = true;
+      std::string err;
+      const int tpb = B_ >= (size_t)65536 ? 128 : 64;  // smaller CTAs spread a mid-sized batch over all SMs
+      const size_t smem = ((size_t)pd.host.nnzLU + 3 * (size_t)pd.host.N) * 8 * (size_t)tpb;
+      const std::string src = jit::source(flat_, pd.host, pd.host_itab, pcode_h_, tran, tpb);
+      if (const char* dump = std::getenv("S21_JIT_DUMP")) {
+        if (FILE* f = std::fopen(dump, "w")) { std::fwrite(src.data(), 1, src.size(), f); std::fclose(f); }
+      }
+      if (jit::compile(src, tran, tpb, smem, &k, &err)) {
+        k.inst_per_cta = tpb;
+      } else {
+        k = jit::Kernel();
+        jit_error_ = err;
+        if (jit_forced_) throw S21Error(ST_CUDA, "S21_KERNEL=jit requested but unavailable: " + err);
+      }
+    }
+    return k.fn ? &k : nullptr;
+  }
+  int launch_jit(const jit::Kernel& k, int mode, double dt, bool cold, int T, const int* save_vars, int n_save, double* wave) {
+    const double* pval = d_pval_.p;
+    double *gx = x_.p, *sop = st_op_.p, *sg = st_guess_.p;
+    int *st = status_.p, *it = iters_.p, *ld = loads_.p;
+    size_t stride = Bs_, st_stride = Bs_;
+    int B = (int)B_, n_state = flat_.n_state, md = mode, cold_i = cold ? 1 : 0, Tp = T, ns = n_save;
+    double gmin = flat_.opts.gmin, dtv = dt, reltol = flat_.opts.reltol, iabstol = flat_.opts.iabstol;
+    void* args[] = {&pval, &gx, &sop, &sg, &st, &it, &ld, &stride, &st_stride, &B, &n_state, &md, &gmin, &dtv, &reltol, &iabstol,
+                    &cold_i, &Tp, &ns, &save_vars, &wave};
+    const unsigned grid = (unsigned)((B_ + (size_t)k.inst_per_cta - 1) / (size_t)k.inst_per_cta);
+    return jit::api().cuLaunchKernel(k.fn, grid, 1, 1, (unsigned)k.tpb, 1, 1, (unsigned)k.smem, (void*)stream_, args, nullptr);
+  }
   CoopCfg coop_cfg(const PlanDevice& pd, size_t n_inst, int width) const {
     const Plan& P = pd.host;
     CoopCfg cfg;
@@ -532,7 +583,11 @@ class Batch {
     DevTables dt = dev_tables(op_plan_.itab.p);
     int rc;
     CoopCfg hcfg;
-    if (use_coop_ && use_hybrid(op_plan_, 1, &hcfg)) {
+    if (const jit::Kernel* jk = jit_kernel(op_plan_, false)) {
+      const bool cold = reset_pending_;
+      reset_pending_ = false;
+      rc = launch_jit(*jk, AN_OP, 0.0, cold, 2, nullptr, 0, nullptr);
+    } else if (use_coop_ && use_hybrid(op_plan_, 1, &hcfg)) {
       hcfg.cold = reset_pending_;
       reset_pending_ = false;
       rc = launch_hybrid_dcop(coop_dev(op_plan_), op_plan_.coop_plan(), op_plan_.coop(), work(), out(), make_ctl(AN_OP, 0.0), hcfg, stream_);
@@ -595,6 +650,8 @@ class Batch {
       }
     }
     pd.itab.upload(itab, stream_);
+    pd.host_itab = itab;
+    pd.jit_dcop = jit::Kernel(); pd.jit_tran = jit::Kernel(); pd.jit_tried_dcop = pd.jit_tried_tran = false;
     if (P.status == ST_OK) {
       build_gather(flat_, si_, mode, itab, P);
       std::vector<int> A;

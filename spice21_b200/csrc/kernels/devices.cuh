@@ -357,8 +357,10 @@ template <class Env> __device__ __forceinline__ void load_ac_mos1(Env& e) {
 }  // namespace s21
 
 // ---------------------------------------------------------------- Bsim4 (bsim4/bsim4_eval.hpp; the reference has no load_ac for it)
+#ifndef S21_JIT  // the run-time specialised kernel (host/jit.hpp) never meets a Bsim4 device
 #include "../bsim4/bsim4_eval.hpp"
 namespace s21 {
 // Not inlined: the model is ~3000 lines of straight-line arithmetic, shared by every kernel variant that can meet one.
 template <class Env> __device__ __noinline__ void load_bsim4(Env& e) { b4e::load_bsim4(e); }
 }  // namespace s21
+#endif  // S21_JIT

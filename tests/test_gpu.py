@@ -333,7 +333,7 @@ def test_ragged_batch_sizes(s21, oracle, B):
     assert np.all(st == 0) and rel_err(x, o["x"], floor=1e-9) <= 1e-9 and np.array_equal(it, o["iters"])
 
 
-@pytest.mark.parametrize("kernel", ["direct", "coop", "hybrid"])
+@pytest.mark.parametrize("kernel", ["direct", "coop", "hybrid", "jit"])
 def test_kernel_variants_bit_identical(s21, kernel, monkeypatch):
     """The three Newton kernels (one thread per instance, CTA-cooperative, hybrid) perform the same operations in the
     same order per value: identical bits, identical iteration counts — dcop and transient."""
