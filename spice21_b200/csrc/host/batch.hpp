@@ -224,24 +224,34 @@ class Batch {
     S21_CUDA(cudaSetDevice(device_));
     materialize_reset();
     const int N = flat_.n_vars();
-    if (x) {
-      hx_.alloc((size_t)N * Bs_);
-      S21_CUDA(cudaMemcpyAsync(hx_.p, x_.p, (size_t)N * Bs_ * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    const int32_t *hs, *hi, *hl;
+    if (x) {  // pack on the device ([instance][variable] rows + the three counters), then ONE contiguous copy
+      const size_t words = (size_t)N * B_ + (3 * B_ * sizeof(int32_t) + 7) / 8;
+      d_rows_.alloc(words);
+      hx_.alloc(words);
+      int rc = launch_pack_out(x_.p, status_.p, iters_.p, loads_.p, d_rows_.p, N, Bs_, (int)B_, stream_);
+      launches_++;
+      if (rc) throw S21Error(ST_CUDA, std::string("k_pack_out launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+      S21_CUDA(cudaMemcpyAsync(hx_.p, d_rows_.p, words * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+      S21_CUDA(cudaStreamSynchronize(stream_));
+      std::memcpy(x, hx_.p, (size_t)N * B_ * sizeof(double));
+      hs = reinterpret_cast<const int32_t*>(hx_.p + (size_t)N * B_);
+      hi = hs + B_;
+      hl = hi + B_;
+    } else {
+      hstatus_.alloc(Bs_); hiters_.alloc(Bs_); hloads_.alloc(Bs_);
+      S21_CUDA(cudaMemcpyAsync(hstatus_.p, status_.p, Bs_ * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+      S21_CUDA(cudaMemcpyAsync(hiters_.p, iters_.p, Bs_ * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+      S21_CUDA(cudaMemcpyAsync(hloads_.p, loads_.p, Bs_ * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+      S21_CUDA(cudaStreamSynchronize(stream_));
+      hs = hstatus_.p; hi = hiters_.p; hl = hloads_.p;
     }
-    hstatus_.alloc(Bs_); hiters_.alloc(Bs_); hloads_.alloc(Bs_);
-    S21_CUDA(cudaMemcpyAsync(hstatus_.p, status_.p, Bs_ * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
-    S21_CUDA(cudaMemcpyAsync(hiters_.p, iters_.p, Bs_ * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
-    S21_CUDA(cudaMemcpyAsync(hloads_.p, loads_.p, Bs_ * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
-    S21_CUDA(cudaStreamSynchronize(stream_));
-    if (x)
-      for (size_t i = 0; i < B_; i++)
-        for (int k = 0; k < N; k++) x[i * (size_t)N + (size_t)k] = hx_.p[(size_t)k * Bs_ + i];
     sum_iters_ = 0; sum_loads_ = 0;
     for (size_t i = 0; i < B_; i++) {
-      if (status) status[i] = hstatus_.p[i];
-      if (iters) iters[i] = hiters_.p[i];
-      sum_iters_ += hiters_.p[i];
-      sum_loads_ += hloads_.p[i];
+      if (status) status[i] = hs[i];
+      if (iters) iters[i] = hi[i];
+      sum_iters_ += hi[i];
+      sum_loads_ += hl[i];
     }
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, ev0_, ev1_) == cudaSuccess) last_ms_ = ms;
@@ -413,7 +423,7 @@ class Batch {
   cudaStream_t own_stream_ = nullptr, stream_ = nullptr;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
   DBuf<int> d_type_, d_ioff_, d_poff_, d_soff_, d_itab_raw_, d_pcode_, d_save_;
-  DBuf<double> d_pval_, x_, rhs_, c_, lu_, st_op_, st_guess_, d_wave_, d_omega_;
+  DBuf<double> d_pval_, x_, rhs_, c_, lu_, st_op_, st_guess_, d_wave_, d_omega_, d_rows_;
   DBuf<cplx> zx_, zrhs_, zc_, zlu_;
   DBuf<int32_t> status_, iters_, loads_, ac_status_, ac_iters_, ac_loads_;
   PinnedBuf<double> pval_h_, hx_, hwave_;

@@ -113,6 +113,9 @@ int launch_dcop(const DevTables& d, const PlanTables& p, const WorkTables<double
 int launch_tran(const DevTables& d, const PlanTables& p, const WorkTables<double>& w, const NewtonOut& o, const SolveCtl& c, int T,
                 const int* save_vars, int n_save, double* wave, void* stream);
 int launch_ac(const DevTables& d, const PlanTables& p, const WorkTables<cplx>& w, const NewtonOut& o, const SolveCtl& c, void* stream);
+// Result packing on the device: out = [x as [instance][variable], B*N f64][status B i32][iters B i32][loads B i32].
+int launch_pack_out(const double* x, const int32_t* status, const int32_t* iters, const int32_t* loads, double* out, int N, size_t stride, int B,
+                    void* stream);
 // First load sweep of instance `inst` in `mode`, assembled by raw element id into out[n_elems] (device memory).
 int launch_probe_real(const DevTables& d, const WorkTables<double>& w, const SolveCtl& c, int n_elems, int N, int inst, double* out, void* stream);
 int launch_probe_cplx(const DevTables& d, const WorkTables<cplx>& w, const SolveCtl& c, int n_elems, int N, int inst, cplx* out, void* stream);

@@ -295,6 +295,23 @@ int launch_ac(const DevTables& d, const PlanTables& p, const WorkTables<cplx>& w
   k_ac<<<grid_for(c.B, 128), 128, 0, (cudaStream_t)stream>>>(d, p, w, o, c);
   return (int)cudaGetLastError();
 }
+// Result packing on the device, so that the host needs ONE contiguous copy and no strided pass:
+//   out = [ x as row-major [instance][variable] : B*N f64 ][ status : B i32 ][ iters : B i32 ][ loads : B i32 ]
+__global__ void k_pack_out(const double* __restrict__ x, const int32_t* __restrict__ status, const int32_t* __restrict__ iters,
+                           const int32_t* __restrict__ loads, double* __restrict__ out, int N, size_t stride, int B) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B) return;
+  for (int k = 0; k < N; k++) out[i * (size_t)N + (size_t)k] = x[(size_t)k * stride + i];
+  int32_t* tail = reinterpret_cast<int32_t*>(out + (size_t)B * (size_t)N);
+  tail[i] = status[i];
+  tail[(size_t)B + i] = iters[i];
+  tail[2 * (size_t)B + i] = loads[i];
+}
+int launch_pack_out(const double* x, const int32_t* status, const int32_t* iters, const int32_t* loads, double* out, int N, size_t stride, int B,
+                    void* stream) {
+  k_pack_out<<<grid_for(B, 128), 128, 0, (cudaStream_t)stream>>>(x, status, iters, loads, out, N, stride, B);
+  return (int)cudaGetLastError();
+}
 int launch_probe_real(const DevTables& d, const WorkTables<double>& w, const SolveCtl& c, int n_elems, int N, int inst, double* out, void* stream) {
   k_probe<double><<<1, 32, 0, (cudaStream_t)stream>>>(d, w, c, n_elems, N, inst, out);
   return (int)cudaGetLastError();
