@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <thread>
 
@@ -129,8 +130,10 @@ class Batch {
     stream_ = own_stream_;
     S21_CUDA(cudaEventCreate(&ev0_));
     S21_CUDA(cudaEventCreate(&ev1_));
-    Bs_ = (B_ + 31) / 32 * 32;
     const int N = flat_.n_vars();
+    // Instance stride of every per-instance table. Rounded to a warp for batches; a single large circuit (C3) keeps its
+    // tables dense instead — with stride 32 its 4 M L+U values would be spread over 1 GB and miss L2 on every access.
+    Bs_ = (B_ == 1 && N > 96) ? 1 : (B_ + 31) / 32 * 32;
     // shared device tables
     std::vector<int> type, ioff, poff, soff;
     for (const FlatDev& d : flat_.devs) { type.push_back(d.type); ioff.push_back(d.itab_off); poff.push_back(d.par_off); soff.push_back(d.state_off); }
@@ -272,6 +275,7 @@ class Batch {
     ensure_plan(tran_plan_, AN_TRAN, tstep);
     std::vector<int> sv(save_vars, save_vars + n_save);
     d_save_.upload(sv, stream_);
+    S21_CUDA(cudaEventRecord(ev0_, stream_));  // time the transient kernel itself: the symbolic phase above is host work
     d_wave_.alloc((size_t)T * n_save * Bs_);
     DevTables dt = dev_tables(tran_plan_.itab.p);
     SolveCtl ctl = make_ctl(AN_TRAN, tstep);
@@ -283,6 +287,12 @@ class Batch {
     } else if (CoopCfg hcfg; use_coop_ && use_hybrid(tran_plan_, 1, &hcfg)) {
       rc = launch_hybrid_tran(coop_dev(tran_plan_), tran_plan_.coop_plan(), tran_plan_.coop(), work(), out(), ctl, hcfg, T, d_save_.p,
                               (int)n_save, d_wave_.p, stream_);
+    } else if (use_coop_ && use_grid()) {
+      CoopCfg cfg = coop_cfg(tran_plan_, B_, 1);
+      cfg.smem_bytes = 0;
+      d_gctl_.alloc(1);
+      rc = launch_grid_tran(coop_dev(tran_plan_), tran_plan_.coop_plan(), tran_plan_.coop(), work(), stage_for(cfg, tran_plan_.host), out(), ctl,
+                            d_gctl_.p, T, d_save_.p, (int)n_save, d_wave_.p, stream_);
     } else if (use_coop_) {
       CoopCfg cfg = coop_cfg(tran_plan_, B_, 1);
       rc = launch_coop_tran(coop_dev(tran_plan_), tran_plan_.coop_plan(), tran_plan_.coop(), work(), stage_for(cfg, tran_plan_.host),
@@ -424,6 +434,8 @@ class Batch {
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
   DBuf<int> d_type_, d_ioff_, d_poff_, d_soff_, d_itab_raw_, d_pcode_, d_save_;
   DBuf<double> d_pval_, x_, rhs_, c_, lu_, st_op_, st_guess_, d_wave_, d_omega_, d_rows_;
+  DBuf<GridCtl> d_gctl_;
+  double symbolic_s_ = 0.0;  // host time spent in build_plan (diagnostics)
   DBuf<cplx> zx_, zrhs_, zc_, zlu_;
   DBuf<int32_t> status_, iters_, loads_, ac_status_, ac_iters_, ac_loads_;
   PinnedBuf<double> pval_h_, hx_, hwave_;
@@ -493,6 +505,9 @@ class Batch {
     const unsigned grid = (unsigned)((B_ + (size_t)k.inst_per_cta - 1) / (size_t)k.inst_per_cta);
     return jit::api().cuLaunchKernel(k.fn, grid, 1, 1, (unsigned)k.tpb, 1, 1, (unsigned)k.smem, (void*)stream_, args, nullptr);
   }
+  // One large circuit (dense instance stride): all SMs work on it through the grid-wide kernel. S21_KERNEL=coop keeps it on
+  // the single-CTA cooperative kernel (the bit-identity tests compare the two).
+  bool use_grid() const { return Bs_ == 1 && allow_hybrid_; }
   CoopCfg coop_cfg(const PlanDevice& pd, size_t n_inst, int width) const {
     const Plan& P = pd.host;
     CoopCfg cfg;
@@ -601,6 +616,13 @@ class Batch {
       hcfg.cold = reset_pending_;
       reset_pending_ = false;
       rc = launch_hybrid_dcop(coop_dev(op_plan_), op_plan_.coop_plan(), op_plan_.coop(), work(), out(), make_ctl(AN_OP, 0.0), hcfg, stream_);
+    } else if (use_coop_ && use_grid()) {
+      materialize_reset();
+      CoopCfg cfg = coop_cfg(op_plan_, B_, 1);
+      cfg.smem_bytes = 0;
+      d_gctl_.alloc(1);
+      rc = launch_grid_dcop(coop_dev(op_plan_), op_plan_.coop_plan(), op_plan_.coop(), work(), stage_for(cfg, op_plan_.host), out(),
+                            make_ctl(AN_OP, 0.0), d_gctl_.p, stream_);
     } else if (use_coop_) {
       materialize_reset();
       CoopCfg cfg = coop_cfg(op_plan_, B_, 1);
@@ -627,8 +649,15 @@ class Batch {
     std::vector<double> vals((size_t)flat_.n_elems());
     S21_CUDA(cudaMemcpyAsync(vals.data(), probe.p, vals.size() * sizeof(double), cudaMemcpyDeviceToHost, stream_));
     S21_CUDA(cudaStreamSynchronize(stream_));
+    const auto t_sym0 = std::chrono::steady_clock::now();
     pd.host = build_plan<double>(N, flat_.elem_row, flat_.elem_col, vals.data());
+    const auto t_sym1 = std::chrono::steady_clock::now();
     upload_plan(pd, mode);
+    symbolic_s_ += std::chrono::duration<double>(t_sym1 - t_sym0).count();
+    if (std::getenv("S21_PLAN_INFO"))
+      std::fprintf(stderr, "[s21 plan] mode=%d host symbolic phase %.3f s, tables+upload %.3f s\n", mode,
+                   std::chrono::duration<double>(t_sym1 - t_sym0).count(),
+                   std::chrono::duration<double>(std::chrono::steady_clock::now() - t_sym1).count());
     ensure_lu_rows((size_t)pd.host.nnzLU);
   }
   void upload_plan(PlanDevice& pd, int mode) {
@@ -661,6 +690,10 @@ class Batch {
     }
     pd.itab.upload(itab, stream_);
     pd.host_itab = itab;
+    if (std::getenv("S21_PLAN_INFO"))
+      std::fprintf(stderr, "[s21 plan] mode=%d N=%d nnzLU=%d lu_ops=%zu lu_levels=%zu fw_ops=%zu fw_levels=%zu bw_levels=%zu\n", mode, P.N,
+                   P.nnzLU, P.lu_t.size(), P.lu_lvl_off.empty() ? 0 : P.lu_lvl_off.size() - 1, P.fw_k.size(),
+                   P.fw_lvl_off.empty() ? 0 : P.fw_lvl_off.size() - 1, P.bw_lvl_off.empty() ? 0 : P.bw_lvl_off.size() - 1);
     pd.jit_dcop = jit::Kernel(); pd.jit_tran = jit::Kernel(); pd.jit_tried_dcop = pd.jit_tried_tran = false;
     if (P.status == ST_OK) {
       build_gather(flat_, si_, mode, itab, P);

@@ -166,7 +166,12 @@ Plan build_plan(int N, const std::vector<int>& elem_row, const std::vector<int>&
     e2i[(size_t)i2e[(size_t)y]] = y;
   };
   // max |val| among the entries of external column c whose current internal row is >= n; ties -> smallest internal row
+  // Cached per column: the answer only changes when the column is touched by an elimination step (its entries are
+  // updated, filled in, or lose the pivot row) — the step below invalidates exactly those columns. Without the cache the
+  // diagonal search re-scans whole columns for every candidate of every pivot (20 s of host time for config C3).
+  std::vector<int> cmax_id((size_t)N, -2);  // -2 = not cached, -1 = no active entry
   auto col_max_from = [&](int c, int n) {
+    if (cmax_id[(size_t)c] != -2) return cmax_id[(size_t)c];
     int best = -1, best_ir = 0;
     double best_val = 0.0;
     for (int id : in_col[(size_t)c]) {
@@ -177,6 +182,7 @@ Plan build_plan(int N, const std::vector<int>& elem_row, const std::vector<int>&
       // value: the winner is the largest |val|, ties going to the smallest internal row (finite values).
       if (best < 0 || a > best_val || (a == best_val && ir < best_ir)) { best = id; best_val = a; best_ir = ir; }
     }
+    cmax_id[(size_t)c] = best;
     return best;
   };
 
@@ -267,8 +273,10 @@ Plan build_plan(int N, const std::vector<int>& elem_row, const std::vector<int>&
       for (auto& x : us) st.U.push_back(x.second);
     }
     for (int l : st.L) E[(size_t)l].val = s_div(E[(size_t)l].val, pivot_val);
+    cmax_id[(size_t)pc] = -2;
     for (int u : st.U) {
       const int uc = E[(size_t)u].c;
+      cmax_id[(size_t)uc] = -2;
       for (int l : st.L) {
         const int lr = E[(size_t)l].r;
         int t = lookup(lr, uc);

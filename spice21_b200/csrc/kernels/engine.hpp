@@ -108,6 +108,16 @@ int launch_hybrid_tran(const DevTables& d, const PlanTables& p, const CoopTables
                        const SolveCtl& c, const CoopCfg& cfg, int T, const int* save_vars, int n_save, double* wave, void* stream);
 int launch_hybrid_ac(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<cplx>& w, const NewtonOut& o,
                      const SolveCtl& c, const CoopCfg& cfg, void* stream);
+// Grid-wide variant (kernels/grid.cu) for ONE large circuit (B = 1, instance stride 1, workspace and staging in HBM/L2):
+// a cooperative launch with grid barriers between phases / dependency levels. `gc` is a device-resident control block.
+struct GridCtl {
+  int stat, nsol, nld, dxok, act, resok, sing, convnow;
+  unsigned long long maxabs;
+};
+int launch_grid_dcop(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<double>& w, double* stage, const NewtonOut& o,
+                     const SolveCtl& c, GridCtl* gc, void* stream);
+int launch_grid_tran(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<double>& w, double* stage, const NewtonOut& o,
+                     const SolveCtl& c, GridCtl* gc, int T, const int* save_vars, int n_save, double* wave, void* stream);
 int launch_dcop(const DevTables& d, const PlanTables& p, const WorkTables<double>& w, const NewtonOut& o, const SolveCtl& c, void* stream);
 // OP must already be solved and committed; runs points 1..T-1 of Tran::solve. wave: [T][n_save][w.stride] device (point 0 written too).
 int launch_tran(const DevTables& d, const PlanTables& p, const WorkTables<double>& w, const NewtonOut& o, const SolveCtl& c, int T,

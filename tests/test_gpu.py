@@ -478,3 +478,21 @@ def test_c4_ptm65_statuses_match_oracle(s21, oracle):
     assert 0 < int(np.sum(status == 0)) < B  # the case is only interesting while it mixes outcomes
     ok = status == 0
     assert np.max(np.abs(wave[ok] - o["x"][ok])) <= 1e-9
+
+
+def test_grid_kernel_single_large_circuit(s21, oracle, monkeypatch):
+    """Config C3's shape at a size the oracle can follow: one circuit, N > 96 -> the grid-wide kernel (all SMs on one
+    instance, grid barriers between dependency levels). Bit-identical to the single-CTA cooperative kernel; parity with
+    the oracle."""
+    ck, ic = cc.inverter_array(20, 5)
+    c = ck.to_s21().elaborate(ic=ic)
+    assert c.n_vars > 96
+    t, w, st, it = s21.Batch(c, 1).tran(1e-11, 1e-10)
+    monkeypatch.setenv("S21_KERNEL", "coop")
+    t2, w2, st2, it2 = s21.Batch(ck.to_s21().elaborate(ic=ic), 1).tran(1e-11, 1e-10)
+    assert st[0] == 0 and st2[0] == 0
+    assert np.array_equal(w, w2) and np.array_equal(it, it2)
+    o = oracle.Circuit(ck.to_text()).tran(1e-11, 1e-10, ic=ic)
+    assert np.max(np.abs(w[0] - o.data)) <= 1e-8
+    x, sd, _ = s21.Batch(cc.inverter_array(20, 5)[0].to_s21().elaborate(), 1).dcop()
+    assert sd[0] in (0, 1)  # without the IC the 100-iteration cap may hit, as in the reference; the launch must not hang
