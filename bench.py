@@ -125,6 +125,15 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+KERNEL_NAMES = {
+    "hybrid": "s21::k_hyb<double, dcop> (hybrid cooperative Newton kernel, kernels/hybrid.cu)",
+    "jit-team": "k_jit (run-time specialised team kernel: 8/16 lanes per instance, rows in registers; host/jit_team.hpp)",
+    "jit-thread": "k_jit (run-time specialised kernel, one thread per instance; host/jit.hpp)",
+    "coop": "s21::k_coop<double, dcop> (cooperative Newton kernel, kernels/coop.cu)",
+    "direct": "s21::k_dcop (one thread per instance, kernels/newton.cu)",
+}
+
+
 def run_ours(args):
     import torch
     import circuits as cc
@@ -166,6 +175,7 @@ def run_ours(args):
     assert np.all(status == 0), "non-converged instances in the benchmark batch"
     iters_per_step = int(iters.sum())
     st = batch.stats()
+    kname = batch.kernel_name()
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -230,7 +240,7 @@ def run_ours(args):
                        "n": st["n"], "nnz_a": st["nnz_a"], "nnz_lu": st["nnz_lu"], "stamp_slots": st["stamps"],
                        "l2": "256 MiB flush write between timed steps (untimed)", "step": "reset (cold start) + batched dcop kernel"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "peak_source": peak_src, "kernel": "s21::k_hyb<double, dcop> (hybrid cooperative Newton kernel)", "kernel_ms": kernel_ms_avg,
+                         "peak_source": peak_src, "kernel": KERNEL_NAMES.get(kname, kname), "kernel_ms": kernel_ms_avg,
                          "algorithmic_bytes_per_iteration": bi},
             "e2e": {"value": tot_iters * e2e_steps / tot_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * tot_e2e / e2e_steps, "steps": e2e_steps,

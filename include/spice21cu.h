@@ -138,6 +138,17 @@ int32_t s21_batch_pivot_order(const s21_batch* b, const int32_t** row_i2e, const
 /* Counters of the last solve: [0] kernel launches, [1] device milliseconds (CUDA events on the launch stream),
  * [2] sum of Newton iterations, [3] sum of device-load sweeps, [4] nnz(A), [5] nnz(L+U), [6] N, [7] stamp slots. */
 int32_t s21_batch_stats(const s21_batch* b, double* out8);
+/* Name of the Newton kernel the last solve was dispatched to ("hybrid", "jit-team", "jit-thread", "coop", "grid",
+ * "direct"); valid until the next solve. The choice depends on circuit size, device content and batch size. */
+const char* s21_batch_kernel_name(const s21_batch* b);
+
+/* Diagnostics of the run-time specialised kernels; neither needs a GPU. s21_jit_source returns the CUDA
+ * source generated for the plan that the given first-iteration matrix values (one per element of s21_ckt_stamp_map)
+ * produce in analysis `mode` (0 OP, 1 TRAN), shape 0 = one thread per instance, 1 = team of 8 lanes per instance;
+ * *out is malloc'ed (s21_free). s21_jit_check compiles a source for sm_100a with NVRTC and reports the log on error. */
+int32_t s21_jit_source(const s21_ckt* c, int32_t mode, int32_t shape, const double* vals, size_t n_vals, uint8_t** out, size_t* out_n,
+                       size_t* smem_bytes);
+int32_t s21_jit_check(const uint8_t* src, size_t n);
 
 /* Host-only: run the symbolic phase on an arbitrary matrix (COO, values real when width == 1, interleaved (re, im)
  * when width == 2) and report what s21_batch_pivot_order would. Needs no GPU; used to check pivot-order parity with

@@ -15,7 +15,11 @@ sizes = [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "8192,65536,2621
 for B in sizes:
     ref = None
     for k in kernels:
-        os.environ["S21_KERNEL"] = k
+        kk, _, lpi = k.partition(":")  # "jitteam:16" = team kernel with 16 lanes per instance
+        os.environ["S21_KERNEL"] = kk
+        os.environ.pop("S21_TEAM_LPI", None)
+        if lpi:
+            os.environ["S21_TEAM_LPI"] = lpi
         ck, ovr = cc.diffpair(), cc.diffpair_mc(B)
         b = s21.Batch(ck.to_s21().elaborate(), B)
         for key, v in ovr.items():
@@ -27,5 +31,5 @@ for B in sizes:
             best = min(best, b.stats()["device_ms"])
         if ref is None:
             ref = x
-        print(f"B={B:7d} kernel={k:7s} device_ms={best:8.3f} iters={int(it.sum()):9d} iters/s={it.sum() / best * 1e3:.3e} "
+        print(f"B={B:7d} kernel={k:10s} device_ms={best:8.3f} iters={int(it.sum()):9d} iters/s={it.sum() / best * 1e3:.3e} "
               f"ok={int(np.sum(st == 0))} same_bits={bool(np.array_equal(x, ref))}", flush=True)

@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "s21_ckt_num_vars", "s21_ckt_var_name", "s21_ckt_var_kind", "s21_ckt_num_devices", "s21_ckt_stamp_map", "s21_batch_create",
     "s21_batch_destroy", "s21_batch_set_stream", "s21_batch_override", "s21_batch_sync_params", "s21_batch_reset", "s21_batch_dcop",
     "s21_batch_dcop_device", "s21_batch_read", "s21_tran_num_points", "s21_batch_tran", "s21_ac_freqs", "s21_batch_ac",
-    "s21_batch_pivot_order", "s21_batch_stats", "s21_symbolic",
+    "s21_batch_pivot_order", "s21_batch_stats", "s21_batch_kernel_name", "s21_jit_source", "s21_jit_check", "s21_symbolic",
 ]
 
 
@@ -95,6 +95,10 @@ def lib():
         L.s21_batch_ac.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         L.s21_batch_pivot_order.argtypes = [C.c_void_p] + [C.c_void_p] * 7
         L.s21_batch_stats.argtypes = [C.c_void_p, C.c_void_p]
+        L.s21_batch_kernel_name.argtypes = [C.c_void_p]
+        L.s21_batch_kernel_name.restype = C.c_char_p
+        L.s21_jit_source.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.s21_jit_check.argtypes = [C.c_char_p, C.c_size_t]
         _lib = L
     return _lib
 
@@ -289,6 +293,24 @@ class Circuit:
                 "dev_elems": as_np(de, int(dev_off[-1]) if nd >= 0 else 0)}
 
 
+    def jit_source(self, vals, mode=0, shape=1):
+        """CUDA source of the run-time specialised Newton kernel for the plan these first-iteration matrix values give
+        (s21_jit_source; host only). Returns (source, dynamic shared-memory bytes)."""
+        v = np.ascontiguousarray(vals, dtype=np.float64)
+        out, n, smem = C.c_void_p(), C.c_size_t(), C.c_size_t()
+        _check(lib().s21_jit_source(self.h, mode, shape, v.ctypes.data_as(C.c_void_p), v.size, C.byref(out), C.byref(n), C.byref(smem)))
+        try:
+            return C.string_at(out, n.value).decode(), smem.value
+        finally:
+            lib().s21_free(out)
+
+
+def jit_check(source):
+    """Compile a generated kernel source for sm_100a with NVRTC (s21_jit_check; no GPU needed)."""
+    b = source.encode()
+    _check(lib().s21_jit_check(b, len(b)))
+
+
 class Batch:
     """``s21_batch``: B instances of one elaborated circuit resident on one GPU."""
 
@@ -372,6 +394,10 @@ class Batch:
         _check(lib().s21_batch_stats(self.h, s.ctypes.data_as(C.c_void_p)))
         return {"launches": int(s[0]), "device_ms": float(s[1]), "iters": int(s[2]), "loads": int(s[3]), "nnz_a": int(s[4]),
                 "nnz_lu": int(s[5]), "n": int(s[6]), "stamps": int(s[7])}
+
+    def kernel_name(self):
+        """Which Newton kernel the last solve ran on (s21_batch_kernel_name)."""
+        return lib().s21_batch_kernel_name(self.h).decode()
 
 
 def symbolic(n, rows, cols, vals):

@@ -378,6 +378,31 @@ int32_t s21_batch_stats(const s21_batch* b, double* out8) {
   S21_CATCH
 }
 
+const char* s21_batch_kernel_name(const s21_batch* b) { return b && b->b ? b->b->kernel_name() : ""; }
+
+int32_t s21_jit_source(const s21_ckt* c, int32_t mode, int32_t shape, const double* vals, size_t n_vals, uint8_t** out, size_t* out_n,
+                       size_t* smem_bytes) {
+  S21_TRY
+  if (!c->elaborated) throw S21Error(ST_OTHER, "circuit is not elaborated");
+  if (n_vals != c->flat.elem_row.size()) throw S21Error(ST_INVALID, "s21_jit_source: one value per matrix element expected");
+  size_t smem = 0;
+  const std::string src = debug_jit_source(c->flat, mode, shape, vals, &smem);
+  *out = (uint8_t*)std::malloc(src.size() + 1);
+  std::memcpy(*out, src.c_str(), src.size() + 1);
+  if (out_n) *out_n = src.size();
+  if (smem_bytes) *smem_bytes = smem;
+  return S21_OK;
+  S21_CATCH
+}
+int32_t s21_jit_check(const uint8_t* src, size_t n) {
+  S21_TRY
+  std::vector<char> cubin;
+  std::string err;
+  if (!jit::compile_cubin(std::string((const char*)src, n), &cubin, &err)) throw S21Error(ST_OTHER, err);
+  return S21_OK;
+  S21_CATCH
+}
+
 int32_t s21_symbolic(int32_t n, size_t nnz, const int32_t* rows, const int32_t* cols, const double* vals, int32_t width, int32_t* row_i2e,
                      int32_t* col_i2e, int32_t* lu_row, int32_t* lu_col, int32_t* lu_is_fill, size_t cap, size_t* nnz_lu) {
   S21_TRY

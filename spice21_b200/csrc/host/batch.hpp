@@ -13,6 +13,7 @@
 #include "../kernels/engine.hpp"
 #include "flatten.hpp"
 #include "jit.hpp"
+#include "jit_team.hpp"
 #include "staging.hpp"
 #include "symbolic.hpp"
 
@@ -60,12 +61,61 @@ struct PinnedBuf {  // page-locked host buffer
   }
 };
 
+// Device index table with element handles rewritten from raw element ids to L+U slots of plan `P`.
+inline std::vector<int> itab_with_slots(const FlatCkt& flat, const Plan& P) {
+  std::vector<int> itab = flat.itab;
+  for (const FlatDev& d : flat.devs) {
+    int first_elem = 0;
+    switch (d.type) {
+      case DT_R: case DT_C: first_elem = R_EPP; break;
+      case DT_I: first_elem = I_NI; break;
+      case DT_V: first_elem = V_EPI; break;
+      case DT_DIODE: first_elem = D_EPP; break;
+      case DT_MOS0: first_elem = M0_EDD; break;
+      case DT_MOS1: first_elem = M1_E0; break;
+      default: first_elem = d.n_itab;
+    }
+    for (int k = first_elem; k < d.n_itab; k++) {
+      int& h = itab[(size_t)d.itab_off + (size_t)k];
+      if (h >= 0) h = P.elem_slot[(size_t)h];
+    }
+    for (int k : d.push_g) {  // Bsim4: element handles are interleaved with variable slots
+      int& h = itab[(size_t)d.itab_off + (size_t)k];
+      if (h >= 0) h = P.elem_slot[(size_t)h];
+    }
+  }
+  return itab;
+}
+
+// Diagnostic, host-only: the CUDA source the run-time specialised kernels would be compiled from, for the plan that the
+// given first-iteration matrix values produce (all parameters taken as shared). shape 0 = one thread per instance
+// (host/jit.hpp), 1 = team (host/jit_team.hpp). Used by the CPU test-suite to check that the generators' output compiles.
+inline std::string debug_jit_source(const FlatCkt& flat, int mode, int shape, const double* vals, size_t* smem_out) {
+  Plan P = build_plan<double>(flat.n_vars(), flat.elem_row, flat.elem_col, vals);
+  if (P.status != ST_OK) throw S21Error(P.status, "the symbolic phase fails on these values");
+  const StageInfo si = make_stage_info(flat);
+  const std::vector<int> itab = itab_with_slots(flat, P);
+  build_gather(flat, si, mode, itab, P);
+  int n_par = 0;
+  for (const FlatDev& d : flat.devs) n_par = std::max(n_par, d.par_off + d.n_par);
+  std::vector<int> pcode((size_t)n_par);
+  for (int j = 0; j < n_par; j++) pcode[(size_t)j] = j << 1;
+  if (shape == 0) {
+    *smem_out = ((size_t)P.nnzLU + 3 * (size_t)P.N) * 8 * (size_t)jit::TPB;
+    return jit::source(flat, P, itab, pcode, mode == AN_TRAN);
+  }
+  if (!jit::team_eligible(flat, P, (size_t)227 * 1024)) throw S21Error(ST_UNSUPPORTED, "circuit not eligible for the team kernel");
+  return jit::team_source(flat, P, si, itab, pcode, mode == AN_TRAN, jit::team_lpi(P.N), smem_out);
+}
+
 struct PlanDevice {
   Plan host;
   bool valid = false;
   std::vector<int> host_itab;         // itab with element handles translated to L+U slots
   jit::Kernel jit_dcop, jit_tran;     // circuit-specialised kernels (host/jit.hpp), compiled on first use
   bool jit_tried_dcop = false, jit_tried_tran = false;
+  jit::Kernel jitt_dcop, jitt_tran;   // team-shaped specialised kernels (host/jit_team.hpp)
+  bool jitt_tried_dcop = false, jitt_tried_tran = false;
   DBuf<int> row_i2e, col_i2e, col_e2i, rowptr, colidx, diag_slot, l_off, l_slot, l_row, upd_off, upd_t, upd_u, upd_l, itab;
   // cooperative kernel: every shared index table packed into one allocation ("arena") so that a CTA can bring all of
   // them into shared memory with a single TMA bulk copy. Offsets are in ints, each table 16-byte aligned.
@@ -146,8 +196,9 @@ class Batch {
       const std::string v(k);
       use_coop_ = v != "direct";
       allow_hybrid_ = v != "coop" && v != "direct";
-      allow_jit_ = v == "jit";
+      allow_jit_ = v == "jit" || v == "jitteam";
       jit_forced_ = allow_jit_;
+      jit_team_forced_ = v == "jitteam";
     }
     max_smem_ = (size_t)coop_max_smem_optin(device_);
     // workspace
@@ -283,21 +334,26 @@ class Batch {
     if (tran_plan_.host.status != ST_OK) {
       throw S21Error(tran_plan_.host.status, status_text(tran_plan_.host.status));
     } else if (const jit::Kernel* jk = jit_kernel(tran_plan_, true)) {
+      last_kernel_ = jk->team ? "jit-team" : "jit-thread";
       rc = launch_jit(*jk, AN_TRAN, tstep, false, T, d_save_.p, (int)n_save, d_wave_.p);
     } else if (CoopCfg hcfg; use_coop_ && use_hybrid(tran_plan_, 1, &hcfg)) {
+      last_kernel_ = "hybrid";
       rc = launch_hybrid_tran(coop_dev(tran_plan_), tran_plan_.coop_plan(), tran_plan_.coop(), work(), out(), ctl, hcfg, T, d_save_.p,
                               (int)n_save, d_wave_.p, stream_);
     } else if (use_coop_ && use_grid()) {
       CoopCfg cfg = coop_cfg(tran_plan_, B_, 1);
       cfg.smem_bytes = 0;
       d_gctl_.alloc(1);
+      last_kernel_ = "grid";
       rc = launch_grid_tran(coop_dev(tran_plan_), tran_plan_.coop_plan(), tran_plan_.coop(), work(), stage_for(cfg, tran_plan_.host), out(), ctl,
                             d_gctl_.p, T, d_save_.p, (int)n_save, d_wave_.p, stream_);
     } else if (use_coop_) {
       CoopCfg cfg = coop_cfg(tran_plan_, B_, 1);
+      last_kernel_ = "coop";
       rc = launch_coop_tran(coop_dev(tran_plan_), tran_plan_.coop_plan(), tran_plan_.coop(), work(), stage_for(cfg, tran_plan_.host),
                             out(), ctl, cfg, T, d_save_.p, (int)n_save, d_wave_.p, stream_);
     } else {
+      last_kernel_ = "direct";
       rc = launch_tran(dt, tran_plan_.tables(), work(), out(), ctl, T, d_save_.p, (int)n_save, d_wave_.p, stream_);
     }
     launches_++;
@@ -411,6 +467,7 @@ class Batch {
   }
 
   const Plan* last_plan() const { return last_plan_ ? &last_plan_->host : nullptr; }
+  const char* kernel_name() const { return last_kernel_; }
   void stats(double* out8) const {
     out8[0] = launches_; out8[1] = last_ms_; out8[2] = (double)sum_iters_; out8[3] = (double)sum_loads_;
     out8[4] = flat_.n_elems(); out8[5] = last_plan_ ? last_plan_->host.nnzLU : 0; out8[6] = flat_.n_vars(); out8[7] = flat_.n_stamps;
@@ -449,13 +506,14 @@ class Batch {
   size_t lu_rows_ = 0;
   int launches_ = 0;
   float last_ms_ = 0.f;
+  const char* last_kernel_ = "";
   long long sum_iters_ = 0, sum_loads_ = 0;
 
   StageInfo si_;
   DBuf<int> d_stage_off_, d_eval_order_;
   DBuf<double> d_stage_;
   DBuf<cplx> zstage_;
-  bool use_coop_ = true, allow_hybrid_ = true, allow_jit_ = true, jit_forced_ = false;
+  bool use_coop_ = true, allow_hybrid_ = true, allow_jit_ = true, jit_forced_ = false, jit_team_forced_ = false;
   std::string jit_error_;  // why the specialised kernel is not in use (empty when it is, or was never wanted)
   bool reset_pending_ = false;
   size_t max_smem_ = 0;
@@ -465,13 +523,13 @@ class Batch {
   DevTables coop_dev(const PlanDevice& pd) const { return pd.coop_dev((int)flat_.devs.size(), d_pval_.p, flat_.n_state); }
   // Circuit-specialised kernel (host/jit.hpp) for this plan, or nullptr: not wanted, not eligible, or NVRTC unavailable.
   const jit::Kernel* jit_kernel(PlanDevice& pd, bool tran) {
-    // One thread per instance pays off only when there are enough warps to hide a dependent f64 chain (measured on C2:
-    // hybrid wins at 8192 instances, the specialised kernel from ~64k up; profiles/r01g_*). S21_KERNEL=jit forces it.
-    if (!allow_jit_ || pd.host.status != ST_OK || !jit::eligible(flat_, pd.host, max_smem_)) return nullptr;
-    // One thread per instance has the fewest instructions (no index tables, no synchronisation) but the longest
-    // dependent chain: it wins once there are enough warps to overlap chains. Measured on C2 (profiles/r01g_*): hybrid
-    // 0.229 ms vs 0.284 ms at 8192 instances, 0.87 vs 0.33 ms at 32768, 2.5 G iters/s vs 0.88 G at 1 M.
-    if (!jit_forced_ && B_ < (size_t)12288) return nullptr;
+    if (!allow_jit_ || pd.host.status != ST_OK) return nullptr;
+    // Two specialised shapes. One thread per instance (host/jit.hpp) has the fewest instructions but the longest
+    // dependent chain: it wins once there are enough warps to overlap chains (measured on C2, profiles/r01g_*: 2.5 G
+    // iters/s at 1 M instances, but 0.284 ms at 8192 where every warp sits alone on its scheduler). Below that the
+    // team shape (host/jit_team.hpp: 8 lanes per instance, rows in registers) is used. S21_KERNEL=jit / jitteam force one.
+    const bool thread_ok = !jit_team_forced_ && jit::eligible(flat_, pd.host, max_smem_) && (jit_forced_ || B_ >= jit_thread_min_b());
+    if (!thread_ok) return jit_team_kernel(pd, tran);
     jit::Kernel& k = tran ? pd.jit_tran : pd.jit_dcop;
     bool& tried = tran ? pd.jit_tried_tran : pd.jit_tried_dcop;
     if (!tried) {
@@ -489,6 +547,38 @@ class Batch {
         k = jit::Kernel();
         jit_error_ = err;
         if (jit_forced_) throw S21Error(ST_CUDA, "S21_KERNEL=jit requested but unavailable: " + err);
+      }
+    }
+    return k.fn ? &k : nullptr;
+  }
+  static size_t jit_thread_min_b() {
+    if (const char* e = std::getenv("S21_JIT_THREAD_MIN_B")) return (size_t)std::atoll(e);
+    return 12288;
+  }
+  const jit::Kernel* jit_team_kernel(PlanDevice& pd, bool tran) {
+    if (jit_forced_ && !jit_team_forced_) return nullptr;
+    if (!jit::team_eligible(flat_, pd.host, max_smem_)) {
+      if (jit_team_forced_) throw S21Error(ST_CUDA, "S21_KERNEL=jitteam requested but the circuit is not eligible (N <= 16, no Bsim4)");
+      return nullptr;
+    }
+    jit::Kernel& k = tran ? pd.jitt_tran : pd.jitt_dcop;
+    bool& tried = tran ? pd.jitt_tried_tran : pd.jitt_tried_dcop;
+    if (!tried) {
+      tried = true;
+      std::string err;
+      size_t smem = 0;
+      const int lpi = jit::team_lpi(pd.host.N);
+      const std::string src = jit::team_source(flat_, pd.host, si_, pd.host_itab, pcode_h_, tran, lpi, &smem);
+      if (const char* dump = std::getenv("S21_JIT_DUMP")) {
+        if (FILE* f = std::fopen(dump, "w")) { std::fwrite(src.data(), 1, src.size(), f); std::fclose(f); }
+      }
+      if (smem <= max_smem_ && jit::compile(src, tran, 32 * lpi, smem, &k, &err)) {
+        k.inst_per_cta = jit::TM_GI;
+        k.team = true;
+      } else {
+        k = jit::Kernel();
+        jit_error_ = err.empty() ? "team kernel: shared memory footprint too large" : err;
+        if (jit_team_forced_) throw S21Error(ST_CUDA, "S21_KERNEL=jitteam requested but unavailable: " + jit_error_);
       }
     }
     return k.fn ? &k : nullptr;
@@ -611,25 +701,30 @@ class Batch {
     if (const jit::Kernel* jk = jit_kernel(op_plan_, false)) {
       const bool cold = reset_pending_;
       reset_pending_ = false;
+      last_kernel_ = jk->team ? "jit-team" : "jit-thread";
       rc = launch_jit(*jk, AN_OP, 0.0, cold, 2, nullptr, 0, nullptr);
     } else if (use_coop_ && use_hybrid(op_plan_, 1, &hcfg)) {
       hcfg.cold = reset_pending_;
       reset_pending_ = false;
+      last_kernel_ = "hybrid";
       rc = launch_hybrid_dcop(coop_dev(op_plan_), op_plan_.coop_plan(), op_plan_.coop(), work(), out(), make_ctl(AN_OP, 0.0), hcfg, stream_);
     } else if (use_coop_ && use_grid()) {
       materialize_reset();
       CoopCfg cfg = coop_cfg(op_plan_, B_, 1);
       cfg.smem_bytes = 0;
       d_gctl_.alloc(1);
+      last_kernel_ = "grid";
       rc = launch_grid_dcop(coop_dev(op_plan_), op_plan_.coop_plan(), op_plan_.coop(), work(), stage_for(cfg, op_plan_.host), out(),
                             make_ctl(AN_OP, 0.0), d_gctl_.p, stream_);
     } else if (use_coop_) {
       materialize_reset();
       CoopCfg cfg = coop_cfg(op_plan_, B_, 1);
+      last_kernel_ = "coop";
       rc = launch_coop_dcop(coop_dev(op_plan_), op_plan_.coop_plan(), op_plan_.coop(), work(), stage_for(cfg, op_plan_.host), out(),
                             make_ctl(AN_OP, 0.0), cfg, stream_);
     } else {
       materialize_reset();
+      last_kernel_ = "direct";
       rc = launch_dcop(dt, op_plan_.tables(), work(), out(), make_ctl(AN_OP, 0.0), stream_);
     }
     launches_++;
@@ -666,28 +761,7 @@ class Batch {
     pd.rowptr.upload(P.rowptr, stream_); pd.colidx.upload(P.colidx, stream_); pd.diag_slot.upload(P.diag_slot, stream_);
     pd.l_off.upload(P.l_off, stream_); pd.l_slot.upload(P.l_slot, stream_); pd.l_row.upload(P.l_row, stream_);
     pd.upd_off.upload(P.upd_off, stream_); pd.upd_t.upload(P.upd_t, stream_); pd.upd_u.upload(P.upd_u, stream_); pd.upd_l.upload(P.upd_l, stream_);
-    // element handles -> L+U slots
-    std::vector<int> itab = flat_.itab;
-    for (const FlatDev& d : flat_.devs) {
-      int first_elem = 0;
-      switch (d.type) {
-        case DT_R: case DT_C: first_elem = R_EPP; break;
-        case DT_I: first_elem = I_NI; break;
-        case DT_V: first_elem = V_EPI; break;
-        case DT_DIODE: first_elem = D_EPP; break;
-        case DT_MOS0: first_elem = M0_EDD; break;
-        case DT_MOS1: first_elem = M1_E0; break;
-        default: first_elem = d.n_itab;
-      }
-      for (int k = first_elem; k < d.n_itab; k++) {
-        int& h = itab[(size_t)d.itab_off + (size_t)k];
-        if (h >= 0) h = P.elem_slot[(size_t)h];
-      }
-      for (int k : d.push_g) {  // Bsim4: element handles are interleaved with variable slots
-        int& h = itab[(size_t)d.itab_off + (size_t)k];
-        if (h >= 0) h = P.elem_slot[(size_t)h];
-      }
-    }
+    std::vector<int> itab = itab_with_slots(flat_, P);
     pd.itab.upload(itab, stream_);
     pd.host_itab = itab;
     if (std::getenv("S21_PLAN_INFO"))
@@ -695,6 +769,7 @@ class Batch {
                    P.nnzLU, P.lu_t.size(), P.lu_lvl_off.empty() ? 0 : P.lu_lvl_off.size() - 1, P.fw_k.size(),
                    P.fw_lvl_off.empty() ? 0 : P.fw_lvl_off.size() - 1, P.bw_lvl_off.empty() ? 0 : P.bw_lvl_off.size() - 1);
     pd.jit_dcop = jit::Kernel(); pd.jit_tran = jit::Kernel(); pd.jit_tried_dcop = pd.jit_tried_tran = false;
+    pd.jitt_dcop = jit::Kernel(); pd.jitt_tran = jit::Kernel(); pd.jitt_tried_dcop = pd.jitt_tried_tran = false;
     if (P.status == ST_OK) {
       build_gather(flat_, si_, mode, itab, P);
       std::vector<int> A;

@@ -1,0 +1,337 @@
+// Circuit-specialised TEAM kernel for small real circuits (dcop / tran), compiled at run time with NVRTC.
+//
+// Why a second specialised shape: one thread per instance (host/jit.hpp) has the fewest instructions but the longest
+// dependent chain, so it only pays once there are enough warps to overlap chains (~12 k instances). At the BASELINE
+// batch size (8192) the generic hybrid kernel (kernels/hybrid.cu) was the fastest, but it INTERPRETS the plan: every
+// gather, every L+U operation and every substitution step loads its indices from tables and round-trips its values
+// through shared memory (ncu: ~9 cycles per instruction per warp; assembly + residual + LU + substitution + update are
+// 80 % of an iteration). This generator keeps the hybrid kernel's thread mapping —
+//   * device evaluation: lane = instance, warp = device (full lanes on the expensive Mos1 evaluation),
+//   * linear algebra: a team of 8 lanes per instance, 4 instances per warp, warp-synchronous,
+// — and compiles the plan INTO the linear algebra: team member j owns pivoted rows j, j+8 (N <= 16) and keeps them in
+// REGISTERS as named scalars (one per column of the union pattern); pivot rows, substitution values and x travel
+// between members with warp shuffles; the L+U pattern, the level structure and the update triples are literals and
+// lane masks. Only the staged assembly still reads a table (the gather lists differ per lane). Two block barriers per
+// Newton iteration, as in the hybrid kernel.
+//
+// Arithmetic per value is in the reference's order (analysis.rs:169-210; sparse21/mod.rs:298-327 residual, 865-919
+// elimination, 947-979 substitution): per element the stamps are summed in component/push order, Schur updates arrive
+// in ascending pivot order, the back-substitution row sum runs over ascending columns — results are bit-identical to
+// the other kernels (tests/test_gpu.py::test_kernel_variants_bit_identical).
+#pragma once
+#include "jit.hpp"
+#include "staging.hpp"
+
+namespace s21 {
+namespace jit {
+
+constexpr int TM_P = 36;     // padded instance stride of the shared-memory columns (as kernels/hybrid.cu)
+constexpr int TM_GI = 32;    // instances per CTA
+constexpr int TM_MAXN = 16;  // rows per instance the register-resident linear algebra is generated for
+// Lanes per instance in the linear-algebra phase: 8 (4 instances per warp, 8 warps per CTA; rows beyond 8 become a
+// second register set) or 16 (2 instances per warp, 16 warps per CTA; one row per member up to N = 16).
+inline int team_lpi(int N) {
+  if (const char* e = std::getenv("S21_TEAM_LPI")) { const int v = std::atoi(e); if (v == 8 || v == 16) return v; }
+  return N > 8 ? 16 : 8;
+}
+
+struct TeamGather {
+  std::vector<int> table;  // [steps][lpi] staging offsets (slot * TM_P) or the zero row
+  int steps = 0;
+};
+
+inline size_t team_smem_bytes(const FlatCkt& flat, const Plan& P, int gather_steps) {
+  const size_t ints = (size_t)TM_GI + (size_t)gather_steps * 16;
+  const size_t ctrl = (ints * 4 + 15) / 16 * 16;
+  return ctrl + 8 * (size_t)TM_P * ((size_t)P.N + (size_t)P.n_stage + 1 + 2 * (size_t)std::max(flat.n_state, 1));
+}
+
+inline bool team_eligible(const FlatCkt& flat, const Plan& P, size_t max_smem) {
+  if (P.status != ST_OK || P.N > TM_MAXN || P.N < 2) return false;
+  if (flat.devs.size() > 64) return false;
+  for (const FlatDev& d : flat.devs)
+    if (d.type == DT_BSIM4) return false;
+  // the gather table is bounded by the stamp count
+  return team_smem_bytes(flat, P, (int)P.asm_src.size() + 2 * TM_MAXN) <= max_smem;
+}
+
+inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageInfo& si, const std::vector<int>& itab,
+                               const std::vector<int>& pcode, bool tran, int TM_LPI, size_t* smem_out) {
+  std::ostringstream o;
+  const int N = P.N, NST = P.n_stage, NSTATE = std::max(flat.n_state, 1), Q = (N + TM_LPI - 1) / TM_LPI;
+  const int IPW = 32 / TM_LPI;        // instances per warp in the linear-algebra phase
+  const int NW = TM_GI / IPW;         // warps per CTA
+  const int LG_IPW = IPW == 4 ? 2 : 1;
+  const unsigned FULLSET = TM_LPI == 16 ? 0xffffu : 0xffu;
+  auto qof = [&](int r) { return r / TM_LPI; };
+  auto jof = [&](int r) { return r % TM_LPI; };
+  // ---- pattern bookkeeping in pivoted coordinates
+  std::vector<std::vector<int>> slot((size_t)N, std::vector<int>((size_t)N, -1));
+  for (int r = 0; r < N; r++)
+    for (int s = P.rowptr[(size_t)r]; s < P.rowptr[(size_t)r + 1]; s++) slot[(size_t)r][(size_t)P.colidx[(size_t)s]] = s;
+  // M[q][c]: members of set q whose row has an entry in column c
+  std::vector<std::vector<unsigned>> M((size_t)Q, std::vector<unsigned>((size_t)N, 0u));
+  for (int r = 0; r < N; r++)
+    for (int c = 0; c < N; c++)
+      if (slot[(size_t)r][(size_t)c] >= 0) M[(size_t)qof(r)][(size_t)c] |= 1u << jof(r);
+  // LM[q][k]: members of set q whose row is below the diagonal in column k (the L entries of pivot k)
+  std::vector<std::vector<unsigned>> LM((size_t)Q, std::vector<unsigned>((size_t)N, 0u));
+  for (int k = 0; k < N; k++)
+    for (int jx = P.l_off[(size_t)k]; jx < P.l_off[(size_t)k + 1]; jx++) {
+      const int r = P.l_row[(size_t)jx];
+      LM[(size_t)qof(r)][(size_t)k] |= 1u << jof(r);
+    }
+  auto A = [&](int q, int c) { return "a" + std::to_string(q) + "_" + std::to_string(c); };
+  auto mask_test = [&](unsigned m) {
+    char buf[32];
+    std::snprintf(buf, sizeof buf, "0x%04xu", m);
+    return std::string("(") + buf + " & jbit)";
+  };
+  // valid members of set q (rows < N)
+  auto valid_mask = [&](int q) { const int n = std::min(TM_LPI, N - q * TM_LPI); return n >= TM_LPI ? FULLSET : ((1u << n) - 1u); };
+
+  // ---- gather table: step-major, 8 members per step
+  TeamGather G;
+  const int zero_off = NST * TM_P;
+  std::ostringstream gath;  // generated gather code
+  auto emit_gather = [&](const std::string& var, const std::vector<int>** lists) {
+    size_t maxlen = 0;
+    for (int j = 0; j < TM_LPI; j++)
+      if (lists[j]) maxlen = std::max(maxlen, lists[j]->size());
+    gath << "        double " << var << " = 0.0;\n";
+    for (size_t p = 0; p < maxlen; p++) {
+      for (int j = 0; j < TM_LPI; j++) G.table.push_back(lists[j] && p < lists[j]->size() ? (*lists[j])[p] * TM_P : zero_off);
+      gath << "        " << var << " = s_add(" << var << ", Sri[gtj[" << G.steps * TM_LPI << "]]);\n";
+      G.steps++;
+    }
+  };
+  std::vector<std::vector<int>> src((size_t)P.nnzLU + (size_t)N);
+  for (size_t t = 0; t + 1 < P.asm_off.size(); t++)
+    src[t].assign(P.asm_src.begin() + P.asm_off[t], P.asm_src.begin() + P.asm_off[t + 1]);
+  for (int q = 0; q < Q; q++) {
+    for (int c = 0; c < N; c++) {
+      if (!M[(size_t)q][(size_t)c]) continue;
+      const std::vector<int>* lists[16];
+      for (int j = 0; j < TM_LPI; j++) {
+        const int r = q * TM_LPI + j;
+        lists[j] = (r < N && slot[(size_t)r][(size_t)c] >= 0) ? &src[(size_t)slot[(size_t)r][(size_t)c]] : nullptr;
+      }
+      emit_gather(A(q, c), lists);
+    }
+    const std::vector<int>* lists[16];
+    for (int j = 0; j < TM_LPI; j++) {
+      const int r = q * TM_LPI + j;
+      lists[j] = r < N ? &src[(size_t)P.nnzLU + (size_t)P.row_i2e[(size_t)r]] : nullptr;
+    }
+    emit_gather("b" + std::to_string(q), lists);
+  }
+
+  // ---- source
+  o << "#define S21_JIT 1\n#include \"kernels/devices.cuh\"\nnamespace s21 {\n";
+  o << "#define PS " << TM_P << "\n#define FULLM 0xffffffffu\n#define BC(v, jj) __shfl_sync(FULLM, (v), base + " << IPW << " * (jj))\n";
+  o << "__device__ const int GT_G[" << std::max<size_t>(G.table.size(), 1) << "] = {";
+  for (size_t k = 0; k < G.table.size(); k++) o << (k ? "," : "") << G.table[k];
+  if (G.table.empty()) o << "0";
+  o << "};\n";
+  o << "__device__ const int XO_G[" << Q * TM_LPI << "] = {";
+  for (int k = 0; k < Q * TM_LPI; k++) o << (k ? "," : "") << (k < N ? P.col_i2e[(size_t)k] * TM_P : 0);
+  o << "};\n";
+  o << "struct JBase {\n  const double* pval; size_t pinst; double* sop; double* sguess; const double* X; double* S;\n"
+       "  int mode; double dt, gmin, omega;\n"
+       "  __device__ __forceinline__ double volt(int var) const { return var < 0 ? 0.0 : X[var * PS]; }\n};\n";
+  for (size_t k = 0; k < flat.devs.size(); k++) {
+    const FlatDev& d = flat.devs[k];
+    const int sto = si.stage_off[k];
+    o << "struct E" << k << " : JBase {\n";
+    o << "  __device__ __forceinline__ int node(int k) const { switch (k) {";
+    for (int j = 0; j < d.n_itab; j++) o << " case " << j << ": return " << itab[(size_t)d.itab_off + (size_t)j] << ";";
+    o << " default: return -1; } }\n";
+    o << "  __device__ __forceinline__ double par(int k) const { switch (k) {";
+    for (int j = 0; j < d.n_par; j++) {
+      const int c = pcode[(size_t)d.par_off + (size_t)j];
+      o << " case " << j << ": return __ldg(pval + " << (c >> 1) << ((c & 1) ? " + pinst" : "") << ");";
+    }
+    o << " default: return 0.0; } }\n";
+    o << "  __device__ __forceinline__ double op(int k) const { return sop[(" << d.state_off << " + k) * PS]; }\n";
+    o << "  __device__ __forceinline__ double guess(int k) const { return sguess[(" << d.state_off << " + k) * PS]; }\n";
+    o << "  __device__ __forceinline__ void set_guess(int k, double v) { sguess[(" << d.state_off << " + k) * PS] = v; }\n";
+    o << "  __device__ __forceinline__ void add_g_at(int pos, double v) { S[(" << sto << " + pos) * PS] = v; }\n";
+    o << "  __device__ __forceinline__ void add_b_at(int pos, double v) { S[(" << sto << " + pos) * PS] = v; }\n";
+    o << "  __device__ __forceinline__ void add_g_dup(int, int dup, double v) { S[(" << sto << " + dup) * PS] = v; }\n};\n";
+  }
+  const size_t n_gt = G.table.size();
+  const size_t ctrl_ints = (size_t)TM_GI + n_gt;
+  const size_t ctrl_bytes = (ctrl_ints * 4 + 15) / 16 * 16;
+  *smem_out = ctrl_bytes + 8 * (size_t)TM_P * ((size_t)N + (size_t)NST + 1 + 2 * (size_t)NSTATE);
+
+  o << "extern \"C\" __global__ void __launch_bounds__(" << NW * 32 << ", " << (NW == 8 ? 2 : 1) << ") k_jit(const double* __restrict__ pval, double* gx, double* st_op, double* st_guess,\n"
+       "    int* status, int* iters, int* loads, size_t stride, size_t st_stride, int B, int n_state_arg, int mode, double gmin, double dt,\n"
+       "    double reltol, double iabstol, int cold, int T_points, int n_save, const int* __restrict__ save_vars, double* wave) {\n"
+       "  extern __shared__ __align__(16) unsigned char smem_raw[];\n"
+       "  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;\n"
+       "  const int i0 = blockIdx.x * " << TM_GI << ";\n"
+       "  const int ni = min(" << TM_GI << ", B - i0);\n"
+       "  const int ei = lane, base = lane & " << IPW - 1 << ", j = lane >> " << LG_IPW << ", ri = warp * " << IPW << " + base;\n"
+       "  const unsigned imask = " << (IPW == 4 ? "0x11111111u" : "0x55555555u") << " << base, jbit = 1u << j;\n"
+       "  int* act_s = (int*)smem_raw;\n  int* gt = act_s + " << TM_GI << ";\n"
+       "  double* X = (double*)(smem_raw + " << ctrl_bytes << ");\n"
+       "  double* S = X + " << N * TM_P << ";\n"
+       "  double* sop = S + " << (NST + 1) * TM_P << ";\n"
+       "  double* sguess = sop + " << NSTATE * TM_P << ";\n"
+       "  for (int k = tid; k < " << n_gt << "; k += " << NW * 32 << ") gt[k] = GT_G[k];\n"
+       "  if (tid < PS) S[" << zero_off << " + tid] = 0.0;\n"
+       "  const bool evalid = ei < ni, rvalid = ri < ni;\n"
+       "  for (int k = warp; k < " << N << "; k += " << NW << ") X[k * PS + ei] = (evalid && !cold) ? gx[(size_t)k * stride + i0 + ei] : 0.0;\n"
+       "  for (int k = warp; k < " << flat.n_state << "; k += " << NW << ") {\n"
+       "    const size_t src = (size_t)k * st_stride + (size_t)i0 + (size_t)(evalid ? ei : 0);\n"
+       "    sop[k * PS + ei] = cold ? 0.0 : st_op[src];\n    sguess[k * PS + ei] = cold ? 0.0 : st_guess[src];\n  }\n"
+       "  int r_stat = " << (tran ? "rvalid ? status[i0 + ri] : 0" : "0") << ";\n"
+       "  int r_nsol = 0, r_nld = 0;\n"
+       "  __syncthreads();\n";
+  if (tran)
+    o << "  if (rvalid) for (int s = j; s < n_save; s += " << TM_LPI << ") wave[(size_t)s * stride + i0 + ri] = X[save_vars[s] * PS + ri];\n";
+  o << "  const int* gtj = gt + j;\n  const double* Sri = S + ri;\n";
+  for (int q = 0; q < Q; q++) {
+    o << "  const int xo" << q << " = XO_G[" << q * TM_LPI << " + j];\n";
+    o << "  const bool v" << q << " = " << (valid_mask(q) == FULLSET ? std::string("true") : "j < " + std::to_string(N - q * TM_LPI)) << ";\n";
+  }
+  o << "  JBase eb; eb.pval = pval; eb.pinst = (size_t)i0 + (size_t)ei; eb.sop = sop + ei; eb.sguess = sguess + ei; eb.X = X + ei; eb.S = S + ei;\n"
+       "  eb.mode = mode; eb.dt = dt; eb.gmin = gmin; eb.omega = 0.0;\n";
+  o << "  const int n_points = " << (tran ? "T_points" : "2") << ";\n"
+       "  for (int tp = 1; tp < n_points; tp++) {\n"
+       "    bool r_act = rvalid && r_stat == 0;\n    bool r_dxok = true;\n"
+       "    if (j == 0) act_s[ri] = r_act ? 1 : 0;\n"
+       "    __syncthreads();\n";
+  for (int q = 0; q < Q; q++) o << "    double xp" << q << " = v" << q << " ? X[xo" << q << " + ri] : 0.0;\n";
+  o << "    for (int iter = 0; iter < 100; iter++) {\n"
+       "      if (act_s[ei]) {\n        switch (warp) {\n";
+  // ---- device evaluation: eval_order position w, w+NW, ... on warp w
+  for (int w = 0; w < NW && w < (int)si.eval_order.size(); w++) {
+    o << "          case " << w << ": {\n";
+    for (size_t item = (size_t)w; item < si.eval_order.size(); item += (size_t)NW) {
+      const int dev = si.eval_order[item];
+      const char* fn = nullptr;
+      switch (flat.devs[(size_t)dev].type) {
+        case DT_R: fn = "load_resistor"; break;
+        case DT_C: fn = "load_capacitor"; break;
+        case DT_I: fn = "load_isrc"; break;
+        case DT_V: fn = "load_vsrc"; break;
+        case DT_DIODE: fn = "load_diode"; break;
+        case DT_MOS0: fn = "load_mos0"; break;
+        case DT_MOS1: fn = "load_mos1"; break;
+        default: fn = nullptr;
+      }
+      if (fn) o << "            { E" << dev << " e; static_cast<JBase&>(e) = eb; " << fn << "(e); }\n";
+    }
+    o << "          } break;\n";
+  }
+  o << "        }\n      }\n      __syncthreads();\n";
+  // ---- linear algebra, warp-synchronous
+  o << "      if (__any_sync(FULLM, r_act)) {\n";
+  o << gath.str();
+  // residual in pivoted row order; x by pivoted column comes from the member that owns it
+  for (int q = 0; q < Q; q++) o << "        double c" << q << " = 0.0;\n";
+  for (int c = 0; c < N; c++) {
+    bool any = false;
+    for (int q = 0; q < Q; q++) any = any || M[(size_t)q][(size_t)c];
+    if (!any) continue;
+    o << "        { const double xc = BC(xp" << qof(c) << ", " << jof(c) << ");\n";
+    for (int q = 0; q < Q; q++) {
+      const unsigned m = M[(size_t)q][(size_t)c];
+      if (!m) continue;
+      o << "          " << (m == FULLSET ? std::string("") : "if " + mask_test(m) + " ") << "c" << q << " = s_add(c" << q << ", s_mul(" << A(q, c)
+        << ", xc));\n";
+    }
+    o << "        }\n";
+  }
+  o << "        bool bad = false;\n";
+  for (int q = 0; q < Q; q++)
+    o << "        c" << q << " = s_sub(b" << q << ", c" << q << "); bad = bad || (v" << q << " && s_abs(c" << q << ") > iabstol);\n";
+  o << "        const bool resok = (__ballot_sync(FULLM, bad) & imask) == 0;\n"
+       "        if (r_act) {\n          r_nld += 1;\n          if (r_dxok && resok) {\n"
+       "            for (int k = j; k < " << flat.n_state << "; k += " << TM_LPI << ") sop[k * PS + ri] = sguess[k * PS + ri];\n"
+       "            r_act = false;\n          }\n        }\n";
+  o << "        if (__any_sync(FULLM, r_act)) {\n          bool sing = false;\n";
+  // numeric LU on the frozen pattern
+  for (int k = 0; k + 1 < N; k++) {
+    const int qk = qof(k), jk = jof(k);
+    o << "          { const double piv = BC(" << A(qk, k) << ", " << jk << "); sing = sing || (piv == 0.0);\n";
+    bool anyL = false;
+    for (int q = 0; q < Q; q++) anyL = anyL || LM[(size_t)q][(size_t)k];
+    if (anyL) {
+      for (int q = 0; q < Q; q++)
+        if (LM[(size_t)q][(size_t)k])
+          o << "            if " << mask_test(LM[(size_t)q][(size_t)k]) << " " << A(q, k) << " = s_div(" << A(q, k) << ", piv);\n";
+      for (int s = P.diag_slot[(size_t)k] + 1; s < P.rowptr[(size_t)k + 1]; s++) {
+        const int c = P.colidx[(size_t)s];
+        o << "            { const double u = BC(" << A(qk, c) << ", " << jk << ");\n";
+        for (int q = 0; q < Q; q++)
+          if (LM[(size_t)q][(size_t)k])
+            o << "              if " << mask_test(LM[(size_t)q][(size_t)k]) << " " << A(q, c) << " = s_sub(" << A(q, c) << ", s_mul(u, " << A(q, k)
+              << "));\n";
+        o << "            }\n";
+      }
+    }
+    o << "          }\n";
+  }
+  // forward substitution
+  for (int k = 0; k < N; k++) {
+    bool anyL = false;
+    for (int q = 0; q < Q; q++) anyL = anyL || LM[(size_t)q][(size_t)k];
+    if (!anyL) continue;
+    o << "          { const double ck = BC(c" << qof(k) << ", " << jof(k) << ");\n            if (!(ck == 0.0)) {\n";
+    for (int q = 0; q < Q; q++)
+      if (LM[(size_t)q][(size_t)k])
+        o << "              if " << mask_test(LM[(size_t)q][(size_t)k]) << " c" << q << " = s_sub(c" << q << ", s_mul(ck, " << A(q, k) << "));\n";
+    o << "            }\n          }\n";
+  }
+  // backward substitution: the owner of row k forms its sum over ascending columns, then broadcasts the result
+  std::vector<bool> need_bc((size_t)N, false);
+  for (int r = 0; r < N; r++)
+    for (int s = P.diag_slot[(size_t)r] + 1; s < P.rowptr[(size_t)r + 1]; s++) need_bc[(size_t)P.colidx[(size_t)s]] = true;
+  for (int k = N - 1; k >= 0; k--) {
+    const int qk = qof(k), jk = jof(k);
+    o << "          if (j == " << jk << ") { double ck = c" << qk << ";\n";
+    for (int s = P.diag_slot[(size_t)k] + 1; s < P.rowptr[(size_t)k + 1]; s++) {
+      const int c = P.colidx[(size_t)s];
+      o << "            ck = s_sub(ck, s_mul(cb" << c << ", " << A(qk, c) << "));\n";
+    }
+    o << "            c" << qk << " = s_div(ck, " << A(qk, k) << "); }\n";
+    if (need_bc[(size_t)k]) o << "          const double cb" << k << " = BC(c" << qk << ", " << jk << ");\n";
+  }
+  // max |dx| over the team, global step limit, update
+  o << "          double m = 0.0;\n";
+  for (int q = 0; q < Q; q++) o << "          if (v" << q << ") m = fmax(m, s_abs(c" << q << "));\n";
+  for (int off = IPW; off < 32; off *= 2) o << "          m = fmax(m, __shfl_xor_sync(FULLM, m, " << off << "));\n";
+  o << "          bool baddx = false;\n          if (r_act && !sing) {\n";
+  for (int q = 0; q < Q; q++)
+    o << "            if (v" << q << ") { double dxk = c" << q << "; if (m > 1.0) dxk = s_scale(dxk, 1.0, m); xp" << q << " = s_add(xp" << q
+      << ", dxk); X[xo" << q << " + ri] = xp" << q << "; baddx = baddx || (s_abs(dxk) > reltol); }\n";
+  o << "          }\n"
+       "          r_dxok = (__ballot_sync(FULLM, baddx) & imask) == 0;\n"
+       "          if (r_act) {\n            if (sing) { r_act = false; r_stat = 2; }\n            else r_nsol += 1;\n          }\n"
+       "        }\n      }\n"
+       "      if (j == 0) act_s[ri] = r_act ? 1 : 0;\n"
+       "      if (!__syncthreads_or(r_act)) break;\n"
+       "    }\n"
+       "    if (r_act) { r_stat = 1; r_act = false; }\n";
+  if (tran)
+    o << "    if (rvalid) {\n      const bool good = r_stat == 0;\n      for (int s = j; s < n_save; s += " << TM_LPI << ")\n"
+         "        wave[((size_t)tp * n_save + s) * stride + i0 + ri] = good ? X[save_vars[s] * PS + ri] : __longlong_as_double(0x7ff8000000000000LL);\n"
+         "    }\n";
+  o << "  }\n  __syncthreads();\n"
+       "  if (evalid) {\n"
+       "    for (int k = warp; k < " << N << "; k += " << NW << ") gx[(size_t)k * stride + i0 + ei] = X[k * PS + ei];\n"
+       "    for (int k = warp; k < " << flat.n_state << "; k += " << NW << ") {\n"
+       "      const size_t dst = (size_t)k * st_stride + i0 + ei;\n"
+       "      st_op[dst] = sop[k * PS + ei];\n      st_guess[dst] = sguess[k * PS + ei];\n    }\n  }\n"
+       "  if (rvalid && j == 0) {\n"
+       "    status[i0 + ri] = r_stat;\n"
+       "    iters[i0 + ri] = (cold ? 0 : iters[i0 + ri]) + r_nsol;\n"
+       "    loads[i0 + ri] = (cold ? 0 : loads[i0 + ri]) + r_nld;\n  }\n}\n";
+  o << "}  // namespace s21\n";
+  return o.str();
+}
+
+}  // namespace jit
+}  // namespace s21

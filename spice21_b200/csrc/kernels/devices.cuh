@@ -26,8 +26,8 @@ namespace s21 {
 struct Integ { double g, i, rhs; };
 __device__ __forceinline__ Integ integrate_be(double dt, double dq, double dq_dv, double vguess) {
   Integ r;
-  r.g = dq_dv / dt;
-  r.i = dq / dt;
+  r.g = s_div(dq_dv, dt);  // s_div: exact, with a shortcut for the (frequent) zero numerator
+  r.i = s_div(dq, dt);
   r.rhs = r.i - r.g * vguess;
   return r;
 }
@@ -75,7 +75,7 @@ template <class Env> __device__ __forceinline__ double diode_limit(Env& e, doubl
   const double vnew = vd;
   if (vnew <= vcrit || fabs(vnew - vold) <= 2.0 * vte) return vnew;
   if (vold > 0.0) {
-    const double arg = 1.0 + (vnew - vold) / vte;
+    const double arg = 1.0 + s_div(vnew - vold, vte);
     if (arg > 0.0) return vold + vte * log(arg);
     return vcrit;
   }
@@ -97,18 +97,18 @@ template <class Env> __device__ __forceinline__ void load_diode(Env& e) {
   }
   double id, gd;
   if (!has_bv || vd >= -bv) {
-    const double ex = exp(vd / vte);
+    const double ex = exp(s_div(vd, vte));
     id = isat * (ex - 1.0) + gmin * vd;
     gd = isat * ex / vte + gmin;
   } else {
-    const double ex = exp((vd - bv) / vte);
+    const double ex = exp(s_div(vd - bv, vte));
     id = -isat * ex + gmin * vd;
     gd = isat * ex / vte + gmin;
   }
   double qd, cd;
   const double dep = e.par(DP_DEPTH);
   if (vd < dep) {
-    const double a = 1.0 - vd / vj;
+    const double a = 1.0 - s_div(vd, vj);
     const double s = -m * log(a);
     qd = tt * vj * cz * (1.0 - a * s) / (1.0 - m);
     cd = tt * gd + cz * s;
@@ -212,11 +212,11 @@ template <class Env> __device__ __forceinline__ void load_mos1(Env& e) {
   const double vtherm = e.par(M1P_VTHERM);
   const int bs_j = reversed ? M1P_DJ : M1P_SJ, bd_j = reversed ? M1P_SJ : M1P_DJ;
   const double bs_isat = e.par(bs_j + MJ_ISAT), bd_isat = e.par(bd_j + MJ_ISAT);
-  const double ebs = exp(-vsb / vtherm);
+  const double ebs = exp(s_div(-vsb, vtherm));
   const double ibs = bs_isat * (ebs - 1.0);
   const double gbs = (bs_isat / vtherm) * ebs + gmin;
   const double ibs_rhs = ibs + vsb * gbs;
-  const double ebd = exp(-vdb / vtherm);
+  const double ebd = exp(s_div(-vdb, vtherm));
   const double ibd = bd_isat * (ebd - 1.0);
   const double gbd = (bd_isat / vtherm) * ebd + gmin;
   const double ibd_rhs = ibd + vdb * gbd;
@@ -226,19 +226,19 @@ template <class Env> __device__ __forceinline__ void load_mos1(Env& e) {
   if (vov <= -phi_t) {
     cgb1 = cox / 2.0; cgs1 = 0.0; cgd1 = 0.0;
   } else if (vov <= -phi_t / 2.0) {
-    cgb1 = -vov * cox / (2.0 * phi_t); cgs1 = 0.0; cgd1 = 0.0;
+    cgb1 = s_div(-vov * cox, 2.0 * phi_t); cgs1 = 0.0; cgd1 = 0.0;
   } else if (vov <= 0.0) {
-    cgb1 = -vov * cox / (2.0 * phi_t);
-    cgs1 = vov * cox / (1.5 * phi_t) + cox / 3.0;
+    cgb1 = s_div(-vov * cox, 2.0 * phi_t);
+    cgs1 = s_div(vov * cox, 1.5 * phi_t) + s_div(cox, 3.0);
     cgd1 = 0.0;
   } else if (vdsat <= vds) {
-    cgs1 = cox / 3.0; cgd1 = 0.0; cgb1 = 0.0;
+    cgs1 = s_div(cox, 3.0); cgd1 = 0.0; cgb1 = 0.0;
   } else {
     const double vddif = 2.0 * vdsat - vds;
     const double vddif1 = vdsat - vds;
     const double vddif2 = vddif * vddif;
-    cgd1 = cox * (1.0 - vdsat * vdsat / vddif2) / 3.0;
-    cgs1 = cox * (1.0 - vddif1 * vddif1 / vddif2) / 3.0;
+    cgd1 = s_div(cox * (1.0 - s_div(vdsat * vdsat, vddif2)), 3.0);
+    cgs1 = s_div(cox * (1.0 - s_div(vddif1 * vddif1, vddif2)), 3.0);
     cgb1 = 0.0;
   }
   // history averaging against the committed point (mos.rs:757-767)

@@ -333,26 +333,63 @@ def test_ragged_batch_sizes(s21, oracle, B):
     assert np.all(st == 0) and rel_err(x, o["x"], floor=1e-9) <= 1e-9 and np.array_equal(it, o["iters"])
 
 
-@pytest.mark.parametrize("kernel", ["direct", "coop", "hybrid", "jit"])
+@pytest.mark.parametrize("kernel", ["direct", "coop", "hybrid", "jit", "jitteam", "jitteam:8", "jitteam:16"])
 def test_kernel_variants_bit_identical(s21, kernel, monkeypatch):
-    """The three Newton kernels (one thread per instance, CTA-cooperative, hybrid) perform the same operations in the
-    same order per value: identical bits, identical iteration counts — dcop and transient."""
-    B = 96
+    """The Newton kernels (one thread per instance, CTA-cooperative, hybrid, and the two run-time specialised shapes)
+    perform the same operations in the same order per value: identical bits, identical iteration counts — dcop and
+    transient. B = 83 leaves a ragged last CTA / warp in every kernel."""
+    B = 83
     ck, ovr = cc.diffpair(), cc.diffpair_mc(B)
 
     def run(k):
+        k, _, lpi = k.partition(":")
         monkeypatch.setenv("S21_KERNEL", k)
+        if lpi:
+            monkeypatch.setenv("S21_TEAM_LPI", lpi)
         b = s21.Batch(ck.to_s21().elaborate(), B)
         for key, v in ovr.items():
             b.override(key, v)
         x, st, it = b.dcop()
         ro = cc.cmos_ro3(cc.add_mos1_defaults)
-        t, w, st2, it2 = s21.Batch(ro.to_s21().elaborate(ic={"1": 0.0}), 3).tran(1e-11, 5e-10)
-        return x, st, it, w, it2
+        b2 = s21.Batch(ro.to_s21().elaborate(ic={"1": 0.0}), 3)
+        t, w, st2, it2 = b2.tran(1e-11, 5e-10)
+        names = (b.kernel_name(), b2.kernel_name())
+        return (x, st, it, w, it2), names
 
-    ref, got = run("direct"), run(kernel)
+    (ref, _), (got, names) = run("direct"), run(kernel)
     for a, b_ in zip(ref, got):
         assert np.array_equal(a, b_)
+    if kernel.startswith("jit"):  # the forced specialised shape really ran (the others choose by circuit and batch size)
+        want = "jit-thread" if kernel == "jit" else "jit-team"
+        assert names == (want, want)
+
+
+def test_team_kernel_devices_and_limits(s21, monkeypatch):
+    """The team-shaped specialised kernel on every device type it accepts (R, C, I, V, Diode, Mos0, Mos1; dcop and
+    transient), bit for bit against the direct kernel; and its refusal of circuits it is not generated for."""
+    def circuits():
+        d = cc.add_diode_defaults(Ckt(signals=["a", "b"])).V("v", "a", GND, 0.75).R("r", "a", "b", 1e-2).D("d1", "b", GND, "default", "default")
+        d.C("c1", "b", GND, 1e-12).I("i1", GND, "b", 1e-4)
+        yield "diode", d, None, (1e-10, 2e-9)  # its transient hits the 100-iteration cap, as in the reference: same status, NaN rows
+        yield "mos0", cc.nmos_ro3(cc.add_mos0_defaults), {"1": 0.0}, (1e-11, 3e-10)
+        yield "mos1", cc.pmos_ro3(cc.add_mos1_defaults), {"1": 0.0}, (1e-11, 3e-10)
+
+    for name, ck, ic, (tstep, tstop) in circuits():
+        out = {}
+        for k in ("direct", "jitteam"):
+            monkeypatch.setenv("S21_KERNEL", k)
+            bd = s21.Batch(ck.to_s21().elaborate(), 5)
+            x, st, it = bd.dcop()
+            bt = s21.Batch(ck.to_s21().elaborate(ic=ic) if ic else ck.to_s21().elaborate(), 5)
+            t, w, st2, it2 = bt.tran(tstep, tstop)
+            out[k] = (x, st, it, w, st2, it2)
+            if k == "jitteam":
+                assert bd.kernel_name() == "jit-team" and bt.kernel_name() == "jit-team", name
+        for a, b_ in zip(out["direct"], out["jitteam"]):
+            assert np.array_equal(a, b_, equal_nan=True), name
+    monkeypatch.setenv("S21_KERNEL", "jitteam")
+    with pytest.raises(s21.Spice21Error):  # N = 68 > 16 rows
+        s21.Batch(cc.rc_opamp(8).to_s21().elaborate(), 2).dcop()
 
 
 # ------------------------------------------------------------------------------------------------ Bsim4
