@@ -231,6 +231,12 @@ def run_ours(args):
         per_inst_cols = (h2d // 8 - 0) // ((B + 31) // 32 * 32) if h2d else 0
         bi = algorithmic_bytes_per_iteration(st["n"], st["nnz_a"], st["nnz_lu"], per_inst_cols)
         kernel_ms_avg = tot_kern_ms / args.steps
+        traffic, traffic_src = None, None  # DRAM bytes per launch of this kernel from the committed ncu --set full capture
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(kname) or {}
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+        except (OSError, ValueError):
+            pass
         achieved = bi["total"] * iters_per_step / (kernel_ms_avg * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": tot_iters * args.steps / (tot_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -239,7 +245,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "instances_per_gpu": B, "newton_iters_per_step_per_gpu": iters_per_step,
                        "n": st["n"], "nnz_a": st["nnz_a"], "nnz_lu": st["nnz_lu"], "stamp_slots": st["stamps"],
                        "l2": "256 MiB flush write between timed steps (untimed)", "step": "reset (cold start) + batched dcop kernel"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src, "kernel": KERNEL_NAMES.get(kname, kname), "kernel_ms": kernel_ms_avg,
                          "algorithmic_bytes_per_iteration": bi},
             "e2e": {"value": tot_iters * e2e_steps / tot_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -66,5 +66,6 @@ extern "C" {
     pub fn s21_batch_kernel_name(b: *const s21_batch) -> *const c_char;
     pub fn s21_jit_source(c: *const s21_ckt, mode: i32, shape: i32, vals: *const f64, n_vals: usize, out: *mut *mut u8, out_n: *mut usize, smem_bytes: *mut usize) -> i32;
     pub fn s21_jit_check(src: *const u8, n: usize) -> i32;
+    pub fn s21_selftest_div(n: u64, seed: u64, mismatches: *mut u64, first4: *mut f64) -> i32;
     pub fn s21_symbolic(n: i32, nnz: usize, rows: *const i32, cols: *const i32, vals: *const f64, width: i32, row_i2e: *mut i32, col_i2e: *mut i32, lu_row: *mut i32, lu_col: *mut i32, lu_is_fill: *mut i32, cap: usize, nnz_lu: *mut usize) -> i32;
 }

@@ -149,6 +149,10 @@ const char* s21_batch_kernel_name(const s21_batch* b);
 int32_t s21_jit_source(const s21_ckt* c, int32_t mode, int32_t shape, const double* vals, size_t n_vals, uint8_t** out, size_t* out_n,
                        size_t* smem_bytes);
 int32_t s21_jit_check(const uint8_t* src, size_t n);
+/* GPU self-test: the kernels' f64 division (csrc/scalar.h: shared reciprocal + exact zero-numerator shortcut) against the
+ * compiler's IEEE `a / b` on ~n random and edge-case operand pairs, bit for bit. *mismatches must be 0;
+ * first4 = {a, b, ours, IEEE} of the first mismatch. */
+int32_t s21_selftest_div(uint64_t n, uint64_t seed, uint64_t* mismatches, double* first4);
 
 /* Host-only: run the symbolic phase on an arbitrary matrix (COO, values real when width == 1, interleaved (re, im)
  * when width == 2) and report what s21_batch_pivot_order would. Needs no GPU; used to check pivot-order parity with

@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "s21_ckt_num_vars", "s21_ckt_var_name", "s21_ckt_var_kind", "s21_ckt_num_devices", "s21_ckt_stamp_map", "s21_batch_create",
     "s21_batch_destroy", "s21_batch_set_stream", "s21_batch_override", "s21_batch_sync_params", "s21_batch_reset", "s21_batch_dcop",
     "s21_batch_dcop_device", "s21_batch_read", "s21_tran_num_points", "s21_batch_tran", "s21_ac_freqs", "s21_batch_ac",
-    "s21_batch_pivot_order", "s21_batch_stats", "s21_batch_kernel_name", "s21_jit_source", "s21_jit_check", "s21_symbolic",
+    "s21_batch_pivot_order", "s21_batch_stats", "s21_batch_kernel_name", "s21_jit_source", "s21_jit_check", "s21_selftest_div", "s21_symbolic",
 ]
 
 
@@ -99,6 +99,7 @@ def lib():
         L.s21_batch_kernel_name.restype = C.c_char_p
         L.s21_jit_source.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         L.s21_jit_check.argtypes = [C.c_char_p, C.c_size_t]
+        L.s21_selftest_div.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -303,6 +304,13 @@ class Circuit:
             return C.string_at(out, n.value).decode(), smem.value
         finally:
             lib().s21_free(out)
+
+
+def selftest_div(n=1 << 24, seed=1):
+    """(mismatches, [a, b, ours, ieee]) of the device division self-test (s21_selftest_div); needs a GPU."""
+    bad, first = C.c_uint64(), np.zeros(4)
+    _check(lib().s21_selftest_div(n, seed, C.byref(bad), first.ctypes.data_as(C.c_void_p)))
+    return bad.value, first
 
 
 def jit_check(source):

@@ -403,6 +403,18 @@ int32_t s21_jit_check(const uint8_t* src, size_t n) {
   S21_CATCH
 }
 
+int32_t s21_selftest_div(uint64_t n, uint64_t seed, uint64_t* mismatches, double* first4) {
+  S21_TRY
+  unsigned long long bad = 0;
+  double f4[4] = {0, 0, 0, 0};
+  const int rc = selftest_div(n, seed, &bad, f4);
+  if (rc) throw S21Error(ST_CUDA, std::string("selftest_div: ") + cudaGetErrorString((cudaError_t)rc));
+  if (mismatches) *mismatches = bad;
+  if (first4) std::memcpy(first4, f4, sizeof f4);
+  return S21_OK;
+  S21_CATCH
+}
+
 int32_t s21_symbolic(int32_t n, size_t nnz, const int32_t* rows, const int32_t* cols, const double* vals, int32_t width, int32_t* row_i2e,
                      int32_t* col_i2e, int32_t* lu_row, int32_t* lu_col, int32_t* lu_is_fill, size_t cap, size_t* nnz_lu) {
   S21_TRY

@@ -201,6 +201,7 @@ class Batch {
       jit_team_forced_ = v == "jitteam";
     }
     max_smem_ = (size_t)coop_max_smem_optin(device_);
+    if (cudaDeviceGetAttribute(&n_sm_, cudaDevAttrMultiProcessorCount, device_) != cudaSuccess || n_sm_ <= 0) n_sm_ = 148;
     // workspace
     x_.alloc((size_t)N * Bs_); rhs_.alloc((size_t)N * Bs_); c_.alloc((size_t)N * Bs_);
     st_op_.alloc((size_t)std::max(flat_.n_state, 1) * Bs_); st_guess_.alloc((size_t)std::max(flat_.n_state, 1) * Bs_);
@@ -517,6 +518,7 @@ class Batch {
   std::string jit_error_;  // why the specialised kernel is not in use (empty when it is, or was never wanted)
   bool reset_pending_ = false;
   size_t max_smem_ = 0;
+  int n_sm_ = 148;
 
   // Launch geometry of the cooperative kernel: the largest instance group per CTA that still leaves >= 2 CTAs per SM
   // (148 SMs) and whose workspace fits in shared memory; HBM-resident workspace when even one instance does not fit.
@@ -568,7 +570,7 @@ class Batch {
       std::string err;
       size_t smem = 0;
       const int lpi = jit::team_lpi(pd.host.N);
-      const std::string src = jit::team_source(flat_, pd.host, si_, pd.host_itab, pcode_h_, tran, lpi, &smem);
+      const std::string src = jit::team_source(flat_, pd.host, si_, pd.host_itab, pcode_h_, tran, lpi, &smem, n_sm_);
       if (const char* dump = std::getenv("S21_JIT_DUMP")) {
         if (FILE* f = std::fopen(dump, "w")) { std::fwrite(src.data(), 1, src.size(), f); std::fclose(f); }
       }

@@ -32,8 +32,12 @@ constexpr int TM_MAXN = 16;  // rows per instance the register-resident linear a
 // second register set) or 16 (2 instances per warp, 16 warps per CTA; one row per member up to N = 16).
 inline int team_lpi(int N) {
   if (const char* e = std::getenv("S21_TEAM_LPI")) { const int v = std::atoi(e); if (v == 8 || v == 16) return v; }
-  return N > 8 ? 16 : 8;
+  (void)N;
+  return 8;  // measured on C2 (N = 9): 0.133 ms with 8 lanes + a second register set, 0.179 ms with 16 lanes (profiles/r01l_*)
 }
+// S21_TEAM_PROFILE=1 adds clock64() probes at the phase boundaries of warp 0 (evaluates the heaviest device) and of the
+// last warp (idle during evaluation) of CTA 0 and prints the per-phase cycle sums when the kernel ends (diagnostic only).
+inline bool team_profile() { const char* e = std::getenv("S21_TEAM_PROFILE"); return e && std::atoi(e) != 0; }
 
 struct TeamGather {
   std::vector<int> table;  // [steps][lpi] staging offsets (slot * TM_P) or the zero row
@@ -56,7 +60,7 @@ inline bool team_eligible(const FlatCkt& flat, const Plan& P, size_t max_smem) {
 }
 
 inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageInfo& si, const std::vector<int>& itab,
-                               const std::vector<int>& pcode, bool tran, int TM_LPI, size_t* smem_out) {
+                               const std::vector<int>& pcode, bool tran, int TM_LPI, size_t* smem_out, int n_sm = 148) {
   std::ostringstream o;
   const int N = P.N, NST = P.n_stage, NSTATE = std::max(flat.n_state, 1), Q = (N + TM_LPI - 1) / TM_LPI;
   const int IPW = 32 / TM_LPI;        // instances per warp in the linear-algebra phase
@@ -127,7 +131,15 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
   }
 
   // ---- source
-  o << "#define S21_JIT 1\n#include \"kernels/devices.cuh\"\nnamespace s21 {\n";
+  const bool prof = team_profile();
+  o << "#define S21_JIT 1\n#include \"kernels/devices.cuh\"\n";
+  if (prof)
+    o << "extern \"C\" int printf(const char*, ...);\n"
+         "#define PH(n) if (lane == 0 && blockIdx.x == 0 && (warp == 0 || warp == " << NW - 1 << ")) { const long long t_ = clock64(); "
+         "prof_s[(warp ? 16 : 0) + (n)] += t_ - t_last; t_last = t_; }\n";
+  else
+    o << "#define PH(n)\n";
+  o << "namespace s21 {\n";
   o << "#define PS " << TM_P << "\n#define FULLM 0xffffffffu\n#define BC(v, jj) __shfl_sync(FULLM, (v), base + " << IPW << " * (jj))\n";
   o << "__device__ const int GT_G[" << std::max<size_t>(G.table.size(), 1) << "] = {";
   for (size_t k = 0; k < G.table.size(); k++) o << (k ? "," : "") << G.table[k];
@@ -164,7 +176,7 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
   const size_t ctrl_bytes = (ctrl_ints * 4 + 15) / 16 * 16;
   *smem_out = ctrl_bytes + 8 * (size_t)TM_P * ((size_t)N + (size_t)NST + 1 + 2 * (size_t)NSTATE);
 
-  o << "extern \"C\" __global__ void __launch_bounds__(" << NW * 32 << ", " << (NW == 8 ? 2 : 1) << ") k_jit(const double* __restrict__ pval, double* gx, double* st_op, double* st_guess,\n"
+  o << "extern \"C\" __global__ void __launch_bounds__(" << NW * 32 << ", " << 2 << ") k_jit(const double* __restrict__ pval, double* gx, double* st_op, double* st_guess,\n"
        "    int* status, int* iters, int* loads, size_t stride, size_t st_stride, int B, int n_state_arg, int mode, double gmin, double dt,\n"
        "    double reltol, double iabstol, int cold, int T_points, int n_save, const int* __restrict__ save_vars, double* wave) {\n"
        "  extern __shared__ __align__(16) unsigned char smem_raw[];\n"
@@ -196,14 +208,15 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
     o << "  const bool v" << q << " = " << (valid_mask(q) == FULLSET ? std::string("true") : "j < " + std::to_string(N - q * TM_LPI)) << ";\n";
   }
   o << "  JBase eb; eb.pval = pval; eb.pinst = (size_t)i0 + (size_t)ei; eb.sop = sop + ei; eb.sguess = sguess + ei; eb.X = X + ei; eb.S = S + ei;\n"
-       "  eb.mode = mode; eb.dt = dt; eb.gmin = gmin; eb.omega = 0.0;\n";
+       "  eb.mode = " << (tran ? "AN_TRAN" : "AN_OP") << "; eb.dt = dt; eb.gmin = gmin; eb.omega = 0.0;\n";  // literal: the other mode's code is dropped
+  if (prof) o << "  __shared__ long long prof_s[32];\n  if (tid < 32) prof_s[tid] = 0;\n  __syncthreads();\n  long long t_last = clock64();\n";
   o << "  const int n_points = " << (tran ? "T_points" : "2") << ";\n"
        "  for (int tp = 1; tp < n_points; tp++) {\n"
        "    bool r_act = rvalid && r_stat == 0;\n    bool r_dxok = true;\n"
        "    if (j == 0) act_s[ri] = r_act ? 1 : 0;\n"
        "    __syncthreads();\n";
   for (int q = 0; q < Q; q++) o << "    double xp" << q << " = v" << q << " ? X[xo" << q << " + ri] : 0.0;\n";
-  o << "    for (int iter = 0; iter < 100; iter++) {\n"
+  o << "    for (int iter = 0; iter < 100; iter++) {\n      PH(0)\n"
        "      if (act_s[ei]) {\n        switch (warp) {\n";
   // ---- device evaluation: eval_order position w, w+NW, ... on warp w
   for (int w = 0; w < NW && w < (int)si.eval_order.size(); w++) {
@@ -225,10 +238,10 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
     }
     o << "          } break;\n";
   }
-  o << "        }\n      }\n      __syncthreads();\n";
+  o << "        }\n      }\n      PH(1)\n      __syncthreads();\n      PH(2)\n";
   // ---- linear algebra, warp-synchronous
   o << "      if (__any_sync(FULLM, r_act)) {\n";
-  o << gath.str();
+  o << gath.str() << "        PH(3)\n";
   // residual in pivoted row order; x by pivoted column comes from the member that owns it
   for (int q = 0; q < Q; q++) o << "        double c" << q << " = 0.0;\n";
   for (int c = 0; c < N; c++) {
@@ -251,7 +264,7 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
        "        if (r_act) {\n          r_nld += 1;\n          if (r_dxok && resok) {\n"
        "            for (int k = j; k < " << flat.n_state << "; k += " << TM_LPI << ") sop[k * PS + ri] = sguess[k * PS + ri];\n"
        "            r_act = false;\n          }\n        }\n";
-  o << "        if (__any_sync(FULLM, r_act)) {\n          bool sing = false;\n";
+  o << "        PH(4)\n        if (__any_sync(FULLM, r_act)) {\n          bool sing = false;\n";
   // numeric LU on the frozen pattern
   for (int k = 0; k + 1 < N; k++) {
     const int qk = qof(k), jk = jof(k);
@@ -259,9 +272,10 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
     bool anyL = false;
     for (int q = 0; q < Q; q++) anyL = anyL || LM[(size_t)q][(size_t)k];
     if (anyL) {
+      o << "            const double rp = s_rcp(piv);\n";  // one reciprocal per pivot, shared by the column's entries (scalar.h)
       for (int q = 0; q < Q; q++)
         if (LM[(size_t)q][(size_t)k])
-          o << "            if " << mask_test(LM[(size_t)q][(size_t)k]) << " " << A(q, k) << " = s_div(" << A(q, k) << ", piv);\n";
+          o << "            if " << mask_test(LM[(size_t)q][(size_t)k]) << " " << A(q, k) << " = s_div_r(" << A(q, k) << ", piv, rp);\n";
       for (int s = P.diag_slot[(size_t)k] + 1; s < P.rowptr[(size_t)k + 1]; s++) {
         const int c = P.colidx[(size_t)s];
         o << "            { const double u = BC(" << A(qk, c) << ", " << jk << ");\n";
@@ -274,6 +288,7 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
     }
     o << "          }\n";
   }
+  o << "          PH(5)\n";
   // forward substitution
   for (int k = 0; k < N; k++) {
     bool anyL = false;
@@ -285,10 +300,18 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
         o << "              if " << mask_test(LM[(size_t)q][(size_t)k]) << " c" << q << " = s_sub(c" << q << ", s_mul(ck, " << A(q, k) << "));\n";
     o << "            }\n          }\n";
   }
+  o << "          PH(6)\n";
   // backward substitution: the owner of row k forms its sum over ascending columns, then broadcasts the result
   std::vector<bool> need_bc((size_t)N, false);
   for (int r = 0; r < N; r++)
     for (int s = P.diag_slot[(size_t)r] + 1; s < P.rowptr[(size_t)r + 1]; s++) need_bc[(size_t)P.colidx[(size_t)s]] = true;
+  // reciprocals of the diagonal, all rows of a set at once (off the substitution's dependent chain)
+  for (int q = 0; q < Q; q++) {
+    o << "          double dg" << q << " = 1.0;\n";
+    for (int jj = 0; jj < TM_LPI && q * TM_LPI + jj < N; jj++)
+      o << "          if (j == " << jj << ") dg" << q << " = " << A(q, q * TM_LPI + jj) << ";\n";
+    o << "          const double rd" << q << " = s_rcp(dg" << q << ");\n";
+  }
   for (int k = N - 1; k >= 0; k--) {
     const int qk = qof(k), jk = jof(k);
     o << "          if (j == " << jk << ") { double ck = c" << qk << ";\n";
@@ -296,23 +319,23 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
       const int c = P.colidx[(size_t)s];
       o << "            ck = s_sub(ck, s_mul(cb" << c << ", " << A(qk, c) << "));\n";
     }
-    o << "            c" << qk << " = s_div(ck, " << A(qk, k) << "); }\n";
+    o << "            c" << qk << " = s_div_r(ck, dg" << qk << ", rd" << qk << "); }\n";
     if (need_bc[(size_t)k]) o << "          const double cb" << k << " = BC(c" << qk << ", " << jk << ");\n";
   }
   // max |dx| over the team, global step limit, update
-  o << "          double m = 0.0;\n";
+  o << "          PH(7)\n          double m = 0.0;\n";
   for (int q = 0; q < Q; q++) o << "          if (v" << q << ") m = fmax(m, s_abs(c" << q << "));\n";
   for (int off = IPW; off < 32; off *= 2) o << "          m = fmax(m, __shfl_xor_sync(FULLM, m, " << off << "));\n";
-  o << "          bool baddx = false;\n          if (r_act && !sing) {\n";
+  o << "          bool baddx = false;\n          const double rm = s_rcp(m);\n          if (r_act && !sing) {\n";
   for (int q = 0; q < Q; q++)
-    o << "            if (v" << q << ") { double dxk = c" << q << "; if (m > 1.0) dxk = s_scale(dxk, 1.0, m); xp" << q << " = s_add(xp" << q
+    o << "            if (v" << q << ") { double dxk = c" << q << "; if (m > 1.0) dxk = s_div_r(s_mul(dxk, 1.0), m, rm); xp" << q << " = s_add(xp" << q
       << ", dxk); X[xo" << q << " + ri] = xp" << q << "; baddx = baddx || (s_abs(dxk) > reltol); }\n";
   o << "          }\n"
        "          r_dxok = (__ballot_sync(FULLM, baddx) & imask) == 0;\n"
        "          if (r_act) {\n            if (sing) { r_act = false; r_stat = 2; }\n            else r_nsol += 1;\n          }\n"
        "        }\n      }\n"
-       "      if (j == 0) act_s[ri] = r_act ? 1 : 0;\n"
-       "      if (!__syncthreads_or(r_act)) break;\n"
+       "      if (j == 0) act_s[ri] = r_act ? 1 : 0;\n      PH(8)\n"
+       "      const int any_ = __syncthreads_or(r_act);\n      PH(9)\n      if (!any_) break;\n"
        "    }\n"
        "    if (r_act) { r_stat = 1; r_act = false; }\n";
   if (tran)
@@ -328,7 +351,12 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
        "  if (rvalid && j == 0) {\n"
        "    status[i0 + ri] = r_stat;\n"
        "    iters[i0 + ri] = (cold ? 0 : iters[i0 + ri]) + r_nsol;\n"
-       "    loads[i0 + ri] = (cold ? 0 : loads[i0 + ri]) + r_nld;\n  }\n}\n";
+       "    loads[i0 + ri] = (cold ? 0 : loads[i0 + ri]) + r_nld;\n  }\n";
+  if (prof)
+    o << "  __syncthreads();\n  if (tid == 0 && blockIdx.x == 0) {\n"
+         "    const char* nm[10] = {\"loop/other\", \"eval\", \"barrier-after-eval\", \"gather\", \"residual+conv\", \"LU\", \"forward\", \"backward\", \"limit+update\", \"end-barrier\"};\n"
+         "    for (int k = 0; k < 10; k++) printf(\"[team profile] %-20s warp0 %10lld   last warp %10lld cycles\\n\", nm[k], prof_s[k], prof_s[16 + k]);\n  }\n";
+  o << "}\n";
   o << "}  // namespace s21\n";
   return o.str();
 }

@@ -130,4 +130,8 @@ int launch_pack_out(const double* x, const int32_t* status, const int32_t* iters
 int launch_probe_real(const DevTables& d, const WorkTables<double>& w, const SolveCtl& c, int n_elems, int N, int inst, double* out, void* stream);
 int launch_probe_cplx(const DevTables& d, const WorkTables<cplx>& w, const SolveCtl& c, int n_elems, int N, int inst, cplx* out, void* stream);
 
+// Device self-test of scalar.h's split division against the compiler's `a / b` on ~n random / edge-case pairs (three
+// quotients per pair); *mismatches must come back 0. first4 = {a, b, ours, compiler's} of the first mismatch.
+int selftest_div(unsigned long long n, unsigned long long seed, unsigned long long* mismatches, double* first4);
+
 }  // namespace s21

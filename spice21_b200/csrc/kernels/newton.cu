@@ -321,4 +321,60 @@ int launch_probe_cplx(const DevTables& d, const WorkTables<cplx>& w, const Solve
   return (int)cudaGetLastError();
 }
 
+// ---- self-test of the split division (scalar.h): s_div / s_rcp + s_div_r against the compiler's `a / b`, bit for bit
+__device__ __forceinline__ unsigned long long st_mix(unsigned long long& x) {
+  x += 0x9E3779B97F4A7C15ull;
+  unsigned long long z = x;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ double st_draw(unsigned long long& x, int kind) {
+  const unsigned long long r = st_mix(x);
+  const double u = (double)(r >> 11) * (1.0 / 9007199254740992.0);
+  switch (kind & 7) {
+    case 0: return __longlong_as_double((long long)r);                                     // any bit pattern (NaN, inf, denormals)
+    case 1: return (u - 0.5) * 4.0;                                                        // order 1
+    case 2: return (u - 0.5) * exp((double)((long long)(st_mix(x) % 1400) - 700));         // whole normal range
+    case 3: return __longlong_as_double((long long)(r & 0x800fffffffffffffull));           // denormals and zeros
+    case 4: return (r & 1) ? 0.0 : -0.0;
+    case 5: return __longlong_as_double((long long)((r & 0x800fffffffffffffull) | 0x7fe0000000000000ull));  // near overflow
+    case 6: return __longlong_as_double((long long)((r & 0x800fffffffffffffull) | 0x0360000000000000ull));  // at the fast-path edge
+    default: return (double)((long long)(r % 2001) - 1000) * 1e-3;                         // small grid incl. exact zero
+  }
+}
+__global__ void k_selftest_div(unsigned long long n_per_thread, unsigned long long seed, unsigned long long* bad, double* first_bad) {
+  unsigned long long x = seed + 0x632BE59BD9B4E019ull * (unsigned long long)(blockIdx.x * blockDim.x + threadIdx.x + 1);
+  for (unsigned long long i = 0; i < n_per_thread; i++) {
+    const int ka = (int)(st_mix(x) & 7), kb = (int)(st_mix(x) & 7);
+    const double a = st_draw(x, ka), a2 = st_draw(x, ka), b = st_draw(x, kb);
+    const double r = s_rcp(b);
+    const double q[3] = {s_div(a, b), s_div_r(a2, b, r), s_scale(a, 1.0, b)};
+    const double w[3] = {a / b, a2 / b, a * 1.0 / b};
+    for (int k = 0; k < 3; k++) {
+      const bool same = (q[k] != q[k] && w[k] != w[k]) || __double_as_longlong(q[k]) == __double_as_longlong(w[k]);
+      if (!same && atomicAdd(bad, 1ull) == 0ull) { first_bad[0] = k == 1 ? a2 : a; first_bad[1] = b; first_bad[2] = q[k]; first_bad[3] = w[k]; }
+    }
+  }
+}
+int selftest_div(unsigned long long n, unsigned long long seed, unsigned long long* mismatches, double* first4) {
+  unsigned long long* d_bad = nullptr;
+  double* d_first = nullptr;
+  cudaError_t e = cudaMalloc(&d_bad, sizeof(unsigned long long));
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMalloc(&d_first, 4 * sizeof(double));
+  if (e != cudaSuccess) { cudaFree(d_bad); return (int)e; }
+  cudaMemset(d_bad, 0, sizeof(unsigned long long));
+  cudaMemset(d_first, 0, 4 * sizeof(double));
+  const int threads = 256, blocks = 592;
+  const unsigned long long per = (n + (unsigned long long)threads * blocks - 1) / ((unsigned long long)threads * blocks);
+  k_selftest_div<<<blocks, threads>>>(per, seed, d_bad, d_first);
+  e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(mismatches, d_bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(first4, d_first, 4 * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d_bad);
+  cudaFree(d_first);
+  return (int)e;
+}
+
 }  // namespace s21

@@ -364,6 +364,13 @@ def test_kernel_variants_bit_identical(s21, kernel, monkeypatch):
         assert names == (want, want)
 
 
+def test_device_division_is_exact(s21):
+    """csrc/scalar.h splits f64 division into a shareable reciprocal and a quotient step (plus an exact shortcut for zero
+    numerators). It must be the IEEE quotient, bit for bit, on every operand class: 3 x 2^25 quotients against `a / b`."""
+    bad, first = s21.selftest_div(1 << 25, seed=20261017)
+    assert bad == 0, f"a={first[0]!r} b={first[1]!r} ours={first[2]!r} ieee={first[3]!r}"
+
+
 def test_team_kernel_devices_and_limits(s21, monkeypatch):
     """The team-shaped specialised kernel on every device type it accepts (R, C, I, V, Diode, Mos0, Mos1; dcop and
     transient), bit for bit against the direct kernel; and its refusal of circuits it is not generated for."""
