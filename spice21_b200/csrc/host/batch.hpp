@@ -187,6 +187,7 @@ class Batch {
     // shared device tables
     std::vector<int> type, ioff, poff, soff;
     for (const FlatDev& d : flat_.devs) { type.push_back(d.type); ioff.push_back(d.itab_off); poff.push_back(d.par_off); soff.push_back(d.state_off); }
+    poff_eff_ = poff;  // rebuild_param_pool() re-points devices with identical parameter blocks at one block
     d_type_.upload(type, stream_); d_ioff_.upload(ioff, stream_); d_poff_.upload(poff, stream_); d_soff_.upload(soff, stream_);
     d_itab_raw_.upload(flat_.itab, stream_);
     si_ = make_stage_info(flat_);
@@ -199,6 +200,7 @@ class Batch {
       allow_jit_ = v == "jit" || v == "jitteam";
       jit_forced_ = allow_jit_;
       jit_team_forced_ = v == "jitteam";
+      ac_kernel_forced_ = true;
     }
     max_smem_ = (size_t)coop_max_smem_optin(device_);
     if (cudaDeviceGetAttribute(&n_sm_, cudaDevAttrMultiProcessorCount, device_) != cudaSuccess || n_sm_ <= 0) n_sm_ = 148;
@@ -256,6 +258,7 @@ class Batch {
     if (rebuild_ || pcode_h_.empty()) { rebuild_param_pool(); rebuild_ = false; params_dirty_ = true; }
     if (params_dirty_ || force_upload) {
       d_pcode_.upload(pcode_h_, stream_);
+      d_poff_.upload(poff_eff_, stream_);
       d_pval_.alloc(pval_n_);
       S21_CUDA(cudaMemcpyAsync(d_pval_.p, pval_h_.p, pval_n_ * sizeof(double), cudaMemcpyHostToDevice, stream_));
       params_dirty_ = false;
@@ -431,14 +434,21 @@ class Batch {
     DevTables dt = dev_tables(ac_plan_.itab.p);
     int rc;
     CoopCfg hcfg;
-    if (use_coop_ && use_hybrid(ac_plan_, 2, &hcfg)) {
+    // A long sweep is a huge batch of independent points: one thread per point (kernels/newton.cu::k_ac, HBM-resident
+    // workspace, instance-fastest layout = coalesced) fills the GPU by itself and skips every barrier of the co-operative
+    // kernels. Measured on C5 (N = 73, nnzLU = 365, 100 000 points): 3.8 ms against 29.8 ms (profiles/r01p_c5.txt).
+    const bool ac_direct = !ac_kernel_forced_ && F >= (size_t)16384;
+    if (use_coop_ && !ac_direct && use_hybrid(ac_plan_, 2, &hcfg)) {
+      last_kernel_ = "hybrid";
       rc = launch_hybrid_ac(coop_dev(ac_plan_), ac_plan_.coop_plan(), ac_plan_.coop(), w, o, ctl, hcfg, stream_);
-    } else if (use_coop_) {
+    } else if (use_coop_ && !ac_direct) {
       CoopCfg cfg = coop_cfg(ac_plan_, F, 2);
       cplx* stage = nullptr;
       if (cfg.smem_bytes == 0) { zstage_.alloc((size_t)ac_plan_.host.n_stage * Fs); stage = zstage_.p; }
+      last_kernel_ = "coop";
       rc = launch_coop_ac(coop_dev(ac_plan_), ac_plan_.coop_plan(), ac_plan_.coop(), w, stage, o, ctl, cfg, stream_);
     } else {
+      last_kernel_ = "direct";
       rc = launch_ac(dt, ac_plan_.tables(), w, o, ctl, stream_);
     }
     launches_++;
@@ -498,7 +508,7 @@ class Batch {
   DBuf<int32_t> status_, iters_, loads_, ac_status_, ac_iters_, ac_loads_;
   PinnedBuf<double> pval_h_, hx_, hwave_;
   PinnedBuf<int32_t> hstatus_, hiters_, hloads_;
-  std::vector<int> pcode_h_;
+  std::vector<int> pcode_h_, poff_eff_;
   size_t pval_n_ = 0, h2d_bytes_ = 0;
   std::vector<Override> overrides_;
   bool params_dirty_ = true, rebuild_ = true;
@@ -514,7 +524,7 @@ class Batch {
   DBuf<int> d_stage_off_, d_eval_order_;
   DBuf<double> d_stage_;
   DBuf<cplx> zstage_;
-  bool use_coop_ = true, allow_hybrid_ = true, allow_jit_ = true, jit_forced_ = false, jit_team_forced_ = false;
+  bool use_coop_ = true, allow_hybrid_ = true, allow_jit_ = true, jit_forced_ = false, jit_team_forced_ = false, ac_kernel_forced_ = false;
   std::string jit_error_;  // why the specialised kernel is not in use (empty when it is, or was never wanted)
   bool reset_pending_ = false;
   size_t max_smem_ = 0;
@@ -781,8 +791,9 @@ class Batch {
         while (A.size() % 4) A.push_back(0);
         return at;
       };
-      std::vector<int> type, ioff, poff, soff;
-      for (const FlatDev& d : flat_.devs) { type.push_back(d.type); ioff.push_back(d.itab_off); poff.push_back(d.par_off); soff.push_back(d.state_off); }
+      std::vector<int> type, ioff, soff;
+      const std::vector<int>& poff = poff_eff_;
+      for (const FlatDev& d : flat_.devs) { type.push_back(d.type); ioff.push_back(d.itab_off); soff.push_back(d.state_off); }
       auto& o = pd.ao;
       o.type = put(type); o.itab_off = put(ioff); o.par_off = put(poff); o.state_off = put(soff); o.itab = put(itab); o.pcode = put(pcode_h_);
       o.row_i2e = put(P.row_i2e); o.col_i2e = put(P.col_i2e); o.col_e2i = put(P.col_e2i); o.rowptr = put(P.rowptr); o.colidx = put(P.colidx);
@@ -898,8 +909,34 @@ class Batch {
       for (size_t i = B_; i < Bs_; i++) dst[i] = columns[c][0];
       pcode_h_[column_target[c]] = (int)(((n_shared + c * Bs_) << 1) | 1);
     }
-    // a parameter change invalidates the frozen pivot orders
-    op_plan_.valid = false; tran_plan_.valid = false;
+    // Devices whose parameter blocks are identical (same model card, same size, nothing per-instance) share ONE block:
+    // a Bsim4 block is ~5 KB of values plus as many codes, and 42 private copies (config C4) overflow L1, so that every
+    // parameter read of the evaluation went to L2 (ncu r01f: long-scoreboard = 36 % of the stalls inside load_bsim4).
+    poff_eff_.resize(flat_.devs.size());
+    {
+      std::vector<size_t> firsts;  // device indices that own a distinct block
+      for (size_t k = 0; k < flat_.devs.size(); k++) {
+        const FlatDev& d = flat_.devs[k];
+        poff_eff_[k] = d.par_off;
+        if (d.n_par < 16) continue;  // only the big blocks matter
+        bool all_shared = true;
+        for (int j = 0; j < d.n_par && all_shared; j++) all_shared = (pcode_h_[(size_t)d.par_off + (size_t)j] & 1) == 0;
+        if (!all_shared) continue;
+        bool found = false;
+        for (size_t f : firsts) {
+          const FlatDev& e = flat_.devs[f];
+          if (e.type != d.type || e.n_par != d.n_par) continue;
+          if (std::memcmp(shared.data() + e.par_off, shared.data() + d.par_off, (size_t)d.n_par * sizeof(double)) == 0) {
+            poff_eff_[k] = e.par_off;
+            found = true;
+            break;
+          }
+        }
+        if (!found) firsts.push_back(k);
+      }
+    }
+    // a parameter change invalidates the frozen pivot orders (and the tables packed with them)
+    op_plan_.valid = false; tran_plan_.valid = false; ac_plan_.valid = false;
   }
 };
 

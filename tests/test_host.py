@@ -170,3 +170,26 @@ def test_time_and_frequency_axes(s21, oracle):
     assert np.array_equal(f, oracle.Circuit(c.to_text()).ac(fstart=1, fstop=10**9, npts=90).axis)
     assert len(s21.ac_freqs(1, 10**10, 99999)) == 100000
     assert len(s21.ac_freqs(0, 0, 0)) == 1
+
+
+@pytest.mark.parametrize("shape", [0, 1], ids=["thread", "team"])
+def test_specialised_kernel_sources_compile(s21, oracle, shape):
+    """The run-time specialised Newton kernels (host/jit.hpp, host/jit_team.hpp) are generated from the plan and compiled
+    with NVRTC on first use. Generation and compilation need no GPU: check here that the sources generated for an OP and
+    a transient plan compile for sm_100a, and that the team generator refuses what it is not written for."""
+    for ck, ic, mode in ((cc.diffpair(), None, 0), (cc.cmos_ro3(cc.add_mos1_defaults), {"1": 0.0}, 1)):
+        o = oracle.Circuit(ck.to_text()).structure(ic=ic)
+        c = ck.to_s21().elaborate(ic=ic) if ic else ck.to_s21().elaborate()
+        src, smem = c.jit_source(o["a0"], mode=mode, shape=shape)
+        assert "k_jit" in src and 0 < smem <= 227 * 1024
+        try:
+            s21.jit_check(src)
+        except s21.Spice21Error as e:
+            if "libnvrtc" in str(e):
+                pytest.skip("NVRTC is not installed here")
+            raise
+    if shape == 1:
+        ck = cc.rc_opamp(8)  # N = 28 rows: beyond the register-resident linear algebra
+        o = oracle.Circuit(ck.to_text()).structure()
+        with pytest.raises(s21.Spice21Error):
+            ck.to_s21().elaborate().jit_source(o["a0"], mode=0, shape=1)
