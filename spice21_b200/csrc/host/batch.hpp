@@ -633,9 +633,13 @@ class Batch {
     for (const FlatDev& d : flat_.devs) n_b4 += d.type == DT_BSIM4;
     const char* force_global = std::getenv("S21_COOP_GLOBAL");  // 1 / 0 overrides the choice
     const bool global_ws = force_global ? std::atoi(force_global) != 0 : n_b4 > 0;
-    if (n_b4 > 0 && !std::getenv("S21_COOP_GI")) {
-      gi = 8;
-      while (gi > 1 && (n_inst + (size_t)gi - 1) / (size_t)gi < 64) gi >>= 1;
+    if (n_b4 > 0) {
+      // One CTA per SM (the Bsim4 build of the kernel is compiled for 320 threads x 204 registers: the evaluation spills
+      // at 128), every SM the same number of instances, and evaluation rounds of equal size: gi = ceil(B / SMs), devices
+      // split evenly over ceil(n_b4 * gi / 320) rounds. C4 (2048 instances, 42 Bsim4 devices): 147 CTAs x 14 instances,
+      // 2 rounds of 21 devices x 14 instances = 294 threads.
+      if (const char* e = std::getenv("S21_COOP_GI")) gi = std::max(1, std::min(32, std::atoi(e)));
+      else gi = (int)std::max<size_t>(1, std::min<size_t>(16, (n_inst + (size_t)n_sm_ - 1) / (size_t)n_sm_));
     }
     while (!global_ws && gi > 1 && total(gi, false) > max_smem_) gi >>= 1;
     cfg.gi = gi;
@@ -647,8 +651,14 @@ class Batch {
     const size_t widest = (size_t)std::max(P.nnzLU + P.N, (int)flat_.devs.size()) * (size_t)gi;
     cfg.threads = widest <= 64 ? 64 : widest <= 1024 ? 128 : 256;
     if (const char* e = std::getenv("S21_COOP_THREADS")) cfg.threads = std::max(32, std::min(256, std::atoi(e) / 32 * 32));
-    if (n_b4 > 0 && !std::getenv("S21_COOP_THREADS")) cfg.threads = std::min(256, (n_b4 * gi + 31) / 32 * 32);
+    if (n_b4 > 0) {
+      const int max_items = std::max(1, 320 / gi);                         // devices one sweep of the CTA can take
+      const int rounds = (n_b4 + max_items - 1) / max_items;
+      cfg.threads = gi * ((n_b4 + rounds - 1) / rounds);
+      if (const char* e = std::getenv("S21_COOP_THREADS")) cfg.threads = std::max(gi, std::min(320, std::atoi(e)) / gi * gi);
+    }
     cfg.threads = std::max(cfg.threads, gi);
+    cfg.threads = cfg.threads / gi * gi;  // every thread keeps one instance column: blockDim.x must be a multiple of gi
     return cfg;
   }
   // Small circuits take the hybrid kernel: its whole footprint must leave room for >= 2 CTAs per SM.

@@ -29,15 +29,15 @@ using namespace coopk;
 namespace {
 
 template <class T, int KIND, bool SMEM, bool B4>
-__global__ void __launch_bounds__(256, 2) k_coop(DevTables d, PlanTables p, CoopTables ct, WorkTables<T> g, T* gstage, NewtonOut o,
+__global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d, PlanTables p, CoopTables ct, WorkTables<T> g, T* gstage, NewtonOut o,
                                                 SolveCtl ctl, CoopArgs a) {
   typedef typename std::conditional<SMEM, unsigned, size_t>::type I;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int lg_gi = a.lg_gi, gi = 1 << lg_gi;
-  const int li = tid & (gi - 1);        // this thread's instance column, fixed for the whole kernel (nt % gi == 0)
-  const int item0 = tid >> lg_gi;       // first item of this thread in every phase
-  const int istep = nt >> lg_gi;        // items handled per sweep of the CTA
+  const int gi = a.gi;
+  const int li = tid % gi;              // this thread's instance column, fixed for the whole kernel (nt % gi == 0)
+  const int item0 = tid / gi;           // first item of this thread in every phase
+  const int istep = nt / gi;            // items handled per sweep of the CTA
   const int i0 = blockIdx.x * gi;
   const int ni = min(gi, ctl.B - i0);
   const int N = p.N, nnz = p.nnz;
@@ -282,14 +282,13 @@ __global__ void __launch_bounds__(256, 2) k_coop(DevTables d, PlanTables p, Coop
   }
 }
 
-int lg2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
 size_t ctrl_bytes(int gi) { return ((8 + 8 * 4) * (size_t)gi + 8 + 15) / 16 * 16; }
 
 template <class T, int KIND, bool B4>
 int launch_b4(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<T>& w, T* stage, const NewtonOut& o,
            const SolveCtl& c, const CoopCfg& cfg, int T_points, const int* save_vars, int n_save, double* wave, void* stream) {
   CoopArgs a;
-  a.lg_gi = lg2(cfg.gi); a.cold = 0; a.T_points = T_points; a.n_save = n_save; a.save_vars = save_vars; a.wave = wave;
+  a.lg_gi = 0; a.gi = cfg.gi; a.cold = 0; a.T_points = T_points; a.n_save = n_save; a.save_vars = save_vars; a.wave = wave;
   a.arena = cfg.arena; a.arena_bytes = cfg.arena_in_smem ? (int)cfg.arena_bytes : 0;
   const size_t smem = ctrl_bytes(cfg.gi) + (size_t)a.arena_bytes + cfg.smem_bytes;
   const int grid = (c.B + cfg.gi - 1) / cfg.gi;

@@ -104,7 +104,8 @@ template <> struct TolC<cplx> {
 };
 
 struct CoopArgs {
-  int lg_gi;
+  int lg_gi;             // hybrid kernel (always 32 instances per CTA)
+  int gi;                // cooperative kernel: instances per CTA, any value >= 1 (blockDim.x is a multiple of it)
   int cold;              // 1: a pending reset is folded into this launch: x and device state start at zero, counters restart
   int T_points, n_save;
   const int* save_vars;

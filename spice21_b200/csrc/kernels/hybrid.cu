@@ -294,7 +294,7 @@ template <class T, int KIND, bool B4>
 int launch_b4(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<T>& w, const NewtonOut& o, const SolveCtl& c,
            const CoopCfg& cfg, int T_points, const int* save_vars, int n_save, double* wave, void* stream) {
   CoopArgs a;
-  a.lg_gi = 5; a.cold = cfg.cold ? 1 : 0; a.T_points = T_points; a.n_save = n_save; a.save_vars = save_vars; a.wave = wave;
+  a.lg_gi = 5; a.gi = HY_GI; a.cold = cfg.cold ? 1 : 0; a.T_points = T_points; a.n_save = n_save; a.save_vars = save_vars; a.wave = wave;
   a.arena = cfg.arena; a.arena_bytes = (int)cfg.arena_bytes;
   const size_t smem = hyb_ctrl_bytes() + cfg.arena_bytes + cfg.smem_bytes;
   const int grid = (c.B + HY_GI - 1) / HY_GI;
