@@ -38,6 +38,9 @@ inline int team_lpi(int N) {
 // S21_TEAM_PROFILE=1 adds clock64() probes at the phase boundaries of warp 0 (evaluates the heaviest device) and of the
 // last warp (idle during evaluation) of CTA 0 and prints the per-phase cycle sums when the kernel ends (diagnostic only).
 inline bool team_profile() { const char* e = std::getenv("S21_TEAM_PROFILE"); return e && std::atoi(e) != 0; }
+// S21_TEAM_FAST=0 generates the exact (branching) linear-algebra text only; default is the branch-free text with the exact
+// one as its redo path. Both give the same bits (tests/test_gpu.py::test_team_kernel_fast_and_exact_text_agree).
+inline bool team_fast() { const char* e = std::getenv("S21_TEAM_FAST"); return !e || std::atoi(e) != 0; }
 
 struct TeamGather {
   std::vector<int> table;  // [steps][lpi] staging offsets (slot * TM_P) or the zero row
@@ -132,6 +135,7 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
 
   // ---- source
   const bool prof = team_profile();
+  const bool fast_la = team_fast();
   o << "#define S21_JIT 1\n#include \"kernels/devices.cuh\"\n";
   if (prof)
     o << "extern \"C\" int printf(const char*, ...);\n"
@@ -151,10 +155,15 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
   o << "struct JBase {\n  const double* pval; size_t pinst; double* sop; double* sguess; const double* X; double* S;\n"
        "  int mode; double dt, gmin, omega;\n"
        "  __device__ __forceinline__ double volt(int var) const { return var < 0 ? 0.0 : X[var * PS]; }\n};\n";
+  // the Env base of the branch-free evaluation (kernels/devices.cuh math hooks): fast paths only, exceptions deferred
+  o << "struct JFast : JBase {\n  bool dbad;\n"
+       "  __device__ __forceinline__ double m_div(double a, double b) { return s_div_rf(a, b, s_rcp(b), dbad); }\n"
+       "  __device__ __forceinline__ double m_sqrt(double a) { return s_sqrt_f(a, dbad); }\n"
+       "  __device__ __forceinline__ double m_exp(double a) { return s_exp_f(a, dbad); }\n};\n";
   for (size_t k = 0; k < flat.devs.size(); k++) {
     const FlatDev& d = flat.devs[k];
     const int sto = si.stage_off[k];
-    o << "struct E" << k << " : JBase {\n";
+    o << "template <class Base> struct E" << k << " : Base {\n  using Base::pval; using Base::pinst; using Base::sop; using Base::sguess; using Base::S;\n";
     o << "  __device__ __forceinline__ int node(int k) const { switch (k) {";
     for (int j = 0; j < d.n_itab; j++) o << " case " << j << ": return " << itab[(size_t)d.itab_off + (size_t)j] << ";";
     o << " default: return -1; } }\n";
@@ -234,93 +243,143 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
         case DT_MOS1: fn = "load_mos1"; break;
         default: fn = nullptr;
       }
-      if (fn) o << "            { E" << dev << " e; static_cast<JBase&>(e) = eb; " << fn << "(e); }\n";
+      // Mos1 reads no in-flight state, so a flagged evaluation can simply be repeated on the exact path
+      if (fn && fast_la && flat.devs[(size_t)dev].type == DT_MOS1)
+        o << "            { E" << dev << "<JFast> e; static_cast<JBase&>(e) = eb; e.dbad = false; " << fn << "(e);\n"
+             "              if (e.dbad) { E" << dev << "<JBase> x; static_cast<JBase&>(x) = eb; " << fn << "(x); } }\n";
+      else if (fn)
+        o << "            { E" << dev << "<JBase> e; static_cast<JBase&>(e) = eb; " << fn << "(e); }\n";
     }
     o << "          } break;\n";
   }
   o << "        }\n      }\n      PH(1)\n      __syncthreads();\n      PH(2)\n";
   // ---- linear algebra, warp-synchronous
+  // residual in pivoted row order; x by pivoted column comes from the member that owns it
+  auto emit_residual = [&](std::ostream& o) {
+    for (int q = 0; q < Q; q++) o << "        c" << q << " = 0.0;\n";
+    for (int c = 0; c < N; c++) {
+      bool any = false;
+      for (int q = 0; q < Q; q++) any = any || M[(size_t)q][(size_t)c];
+      if (!any) continue;
+      o << "        { const double xc = BC(xp" << qof(c) << ", " << jof(c) << ");\n";
+      for (int q = 0; q < Q; q++) {
+        const unsigned m = M[(size_t)q][(size_t)c];
+        if (!m) continue;
+        o << "          " << (m == FULLSET ? std::string("") : "if " + mask_test(m) + " ") << "c" << q << " = s_add(c" << q << ", s_mul(" << A(q, c)
+          << ", xc));\n";
+      }
+      o << "        }\n";
+    }
+    for (int q = 0; q < Q; q++) o << "        c" << q << " = s_sub(b" << q << ", c" << q << ");\n";
+  };
+  // numeric LU on the frozen pattern + both substitutions. `fast` = branch-free text: every division is the fast path
+  // of scalar.h with its exception deferred into `dbad`, every lane mask and every zero test a select, so that the whole
+  // solve is one basic block (independent pivots, rows and columns overlap); the exact text is kept for the redo.
+  auto emit_solve = [&](std::ostream& o, bool fast) {
+    auto divide = [&](const std::string& dst, const std::string& num, const std::string& den, const std::string& rcp, const std::string& cond) {
+      if (fast)
+        o << "            { bool bd = false; const double t = s_div_rf(" << num << ", " << den << ", " << rcp << ", bd); const bool in = " << cond << "; "
+          << dst << " = in ? t : " << dst << "; dbad = dbad || (in && bd); }\n";
+      else
+        o << "            if (" << cond << ") " << dst << " = s_div_r(" << num << ", " << den << ", " << rcp << ");\n";
+    };
+    for (int k = 0; k + 1 < N; k++) {
+      const int qk = qof(k), jk = jof(k);
+      o << "          { const double piv = BC(" << A(qk, k) << ", " << jk << "); sing = sing || (piv == 0.0);\n";
+      bool anyL = false;
+      for (int q = 0; q < Q; q++) anyL = anyL || LM[(size_t)q][(size_t)k];
+      if (anyL) {
+        o << "            const double rp = s_rcp(piv);\n";  // one reciprocal per pivot, shared by the column's entries (scalar.h)
+        for (int q = 0; q < Q; q++)
+          if (LM[(size_t)q][(size_t)k]) divide(A(q, k), A(q, k), "piv", "rp", mask_test(LM[(size_t)q][(size_t)k]) + " != 0u");
+        for (int s = P.diag_slot[(size_t)k] + 1; s < P.rowptr[(size_t)k + 1]; s++) {
+          const int c = P.colidx[(size_t)s];
+          o << "            { const double u = BC(" << A(qk, c) << ", " << jk << ");\n";
+          for (int q = 0; q < Q; q++)
+            if (LM[(size_t)q][(size_t)k]) {
+              const std::string upd = "s_sub(" + A(q, c) + ", s_mul(u, " + A(q, k) + "))";
+              if (fast)
+                o << "              " << A(q, c) << " = " << mask_test(LM[(size_t)q][(size_t)k]) << " ? " << upd << " : " << A(q, c) << ";\n";
+              else
+                o << "              if " << mask_test(LM[(size_t)q][(size_t)k]) << " " << A(q, c) << " = " << upd << ";\n";
+            }
+          o << "            }\n";
+        }
+      }
+      o << "          }\n";
+    }
+    o << "          PH(5)\n";
+    // forward substitution
+    for (int k = 0; k < N; k++) {
+      bool anyL = false;
+      for (int q = 0; q < Q; q++) anyL = anyL || LM[(size_t)q][(size_t)k];
+      if (!anyL) continue;
+      o << "          { const double ck = BC(c" << qof(k) << ", " << jof(k) << ");\n";
+      if (fast) {
+        o << "            const bool nz = !(ck == 0.0);\n";
+        for (int q = 0; q < Q; q++)
+          if (LM[(size_t)q][(size_t)k])
+            o << "            c" << q << " = (nz && " << mask_test(LM[(size_t)q][(size_t)k]) << ") ? s_sub(c" << q << ", s_mul(ck, " << A(q, k) << ")) : c" << q
+              << ";\n";
+        o << "          }\n";
+      } else {
+        o << "            if (!(ck == 0.0)) {\n";
+        for (int q = 0; q < Q; q++)
+          if (LM[(size_t)q][(size_t)k])
+            o << "              if " << mask_test(LM[(size_t)q][(size_t)k]) << " c" << q << " = s_sub(c" << q << ", s_mul(ck, " << A(q, k) << "));\n";
+        o << "            }\n          }\n";
+      }
+    }
+    o << "          PH(6)\n";
+    // backward substitution: the owner of row k forms its sum over ascending columns, then broadcasts the result
+    std::vector<bool> need_bc((size_t)N, false);
+    for (int r = 0; r < N; r++)
+      for (int s = P.diag_slot[(size_t)r] + 1; s < P.rowptr[(size_t)r + 1]; s++) need_bc[(size_t)P.colidx[(size_t)s]] = true;
+    // reciprocals of the diagonal, all rows of a set at once (off the substitution's dependent chain)
+    for (int q = 0; q < Q; q++) {
+      o << "          double dg" << q << " = 1.0;\n";
+      for (int jj = 0; jj < TM_LPI && q * TM_LPI + jj < N; jj++)
+        o << "          if (j == " << jj << ") dg" << q << " = " << A(q, q * TM_LPI + jj) << ";\n";
+      o << "          const double rd" << q << " = s_rcp(dg" << q << ");\n";
+    }
+    for (int k = N - 1; k >= 0; k--) {
+      const int qk = qof(k), jk = jof(k);
+      o << "          { double ck = c" << qk << ";\n";
+      for (int s = P.diag_slot[(size_t)k] + 1; s < P.rowptr[(size_t)k + 1]; s++) {
+        const int c = P.colidx[(size_t)s];
+        o << "            ck = s_sub(ck, s_mul(cb" << c << ", " << A(qk, c) << "));\n";
+      }
+      divide("c" + std::to_string(qk), "ck", "dg" + std::to_string(qk), "rd" + std::to_string(qk), "j == " + std::to_string(jk));
+      o << "          }\n";
+      if (need_bc[(size_t)k]) o << "          const double cb" << k << " = BC(c" << qk << ", " << jk << ");\n";
+    }
+  };
   o << "      if (__any_sync(FULLM, r_act)) {\n";
   o << gath.str() << "        PH(3)\n";
-  // residual in pivoted row order; x by pivoted column comes from the member that owns it
-  for (int q = 0; q < Q; q++) o << "        double c" << q << " = 0.0;\n";
-  for (int c = 0; c < N; c++) {
-    bool any = false;
-    for (int q = 0; q < Q; q++) any = any || M[(size_t)q][(size_t)c];
-    if (!any) continue;
-    o << "        { const double xc = BC(xp" << qof(c) << ", " << jof(c) << ");\n";
-    for (int q = 0; q < Q; q++) {
-      const unsigned m = M[(size_t)q][(size_t)c];
-      if (!m) continue;
-      o << "          " << (m == FULLSET ? std::string("") : "if " + mask_test(m) + " ") << "c" << q << " = s_add(c" << q << ", s_mul(" << A(q, c)
-        << ", xc));\n";
-    }
-    o << "        }\n";
-  }
+  o << "        double c0";
+  for (int q = 1; q < Q; q++) o << ", c" << q;
+  o << ";\n";
+  emit_residual(o);
   o << "        bool bad = false;\n";
-  for (int q = 0; q < Q; q++)
-    o << "        c" << q << " = s_sub(b" << q << ", c" << q << "); bad = bad || (v" << q << " && s_abs(c" << q << ") > iabstol);\n";
+  for (int q = 0; q < Q; q++) o << "        bad = bad || (v" << q << " && s_abs(c" << q << ") > iabstol);\n";
   o << "        const bool resok = (__ballot_sync(FULLM, bad) & imask) == 0;\n"
        "        if (r_act) {\n          r_nld += 1;\n          if (r_dxok && resok) {\n"
        "            for (int k = j; k < " << flat.n_state << "; k += " << TM_LPI << ") sop[k * PS + ri] = sguess[k * PS + ri];\n"
        "            r_act = false;\n          }\n        }\n";
   o << "        PH(4)\n        if (__any_sync(FULLM, r_act)) {\n          bool sing = false;\n";
-  // numeric LU on the frozen pattern
-  for (int k = 0; k + 1 < N; k++) {
-    const int qk = qof(k), jk = jof(k);
-    o << "          { const double piv = BC(" << A(qk, k) << ", " << jk << "); sing = sing || (piv == 0.0);\n";
-    bool anyL = false;
-    for (int q = 0; q < Q; q++) anyL = anyL || LM[(size_t)q][(size_t)k];
-    if (anyL) {
-      o << "            const double rp = s_rcp(piv);\n";  // one reciprocal per pivot, shared by the column's entries (scalar.h)
-      for (int q = 0; q < Q; q++)
-        if (LM[(size_t)q][(size_t)k])
-          o << "            if " << mask_test(LM[(size_t)q][(size_t)k]) << " " << A(q, k) << " = s_div_r(" << A(q, k) << ", piv, rp);\n";
-      for (int s = P.diag_slot[(size_t)k] + 1; s < P.rowptr[(size_t)k + 1]; s++) {
-        const int c = P.colidx[(size_t)s];
-        o << "            { const double u = BC(" << A(qk, c) << ", " << jk << ");\n";
-        for (int q = 0; q < Q; q++)
-          if (LM[(size_t)q][(size_t)k])
-            o << "              if " << mask_test(LM[(size_t)q][(size_t)k]) << " " << A(q, c) << " = s_sub(" << A(q, c) << ", s_mul(u, " << A(q, k)
-              << "));\n";
-        o << "            }\n";
-      }
-    }
+  if (fast_la) {
+    o << "          bool dbad = false;\n          {\n";
+    emit_solve(o, true);
     o << "          }\n";
-  }
-  o << "          PH(5)\n";
-  // forward substitution
-  for (int k = 0; k < N; k++) {
-    bool anyL = false;
-    for (int q = 0; q < Q; q++) anyL = anyL || LM[(size_t)q][(size_t)k];
-    if (!anyL) continue;
-    o << "          { const double ck = BC(c" << qof(k) << ", " << jof(k) << ");\n            if (!(ck == 0.0)) {\n";
-    for (int q = 0; q < Q; q++)
-      if (LM[(size_t)q][(size_t)k])
-        o << "              if " << mask_test(LM[(size_t)q][(size_t)k]) << " c" << q << " = s_sub(c" << q << ", s_mul(ck, " << A(q, k) << "));\n";
-    o << "            }\n          }\n";
-  }
-  o << "          PH(6)\n";
-  // backward substitution: the owner of row k forms its sum over ascending columns, then broadcasts the result
-  std::vector<bool> need_bc((size_t)N, false);
-  for (int r = 0; r < N; r++)
-    for (int s = P.diag_slot[(size_t)r] + 1; s < P.rowptr[(size_t)r + 1]; s++) need_bc[(size_t)P.colidx[(size_t)s]] = true;
-  // reciprocals of the diagonal, all rows of a set at once (off the substitution's dependent chain)
-  for (int q = 0; q < Q; q++) {
-    o << "          double dg" << q << " = 1.0;\n";
-    for (int jj = 0; jj < TM_LPI && q * TM_LPI + jj < N; jj++)
-      o << "          if (j == " << jj << ") dg" << q << " = " << A(q, q * TM_LPI + jj) << ";\n";
-    o << "          const double rd" << q << " = s_rcp(dg" << q << ");\n";
-  }
-  for (int k = N - 1; k >= 0; k--) {
-    const int qk = qof(k), jk = jof(k);
-    o << "          if (j == " << jk << ") { double ck = c" << qk << ";\n";
-    for (int s = P.diag_slot[(size_t)k] + 1; s < P.rowptr[(size_t)k + 1]; s++) {
-      const int c = P.colidx[(size_t)s];
-      o << "            ck = s_sub(ck, s_mul(cb" << c << ", " << A(qk, c) << "));\n";
-    }
-    o << "            c" << qk << " = s_div_r(ck, dg" << qk << ", rd" << qk << "); }\n";
-    if (need_bc[(size_t)k]) o << "          const double cb" << k << " = BC(c" << qk << ", " << jk << ");\n";
+    // deferred exceptions: some quotient of this warp left the fast path's domain -> the exact text, from the stamps
+    o << "          if (__any_sync(FULLM, dbad)) {\n          sing = false;\n";
+    std::string g2 = gath.str();
+    o << g2;
+    emit_residual(o);
+    emit_solve(o, false);
+    o << "          }\n";
+  } else {
+    emit_solve(o, false);
   }
   // max |dx| over the team, global step limit, update
   o << "          PH(7)\n          double m = 0.0;\n";

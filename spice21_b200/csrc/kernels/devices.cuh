@@ -22,8 +22,28 @@
 
 namespace s21 {
 
+// Math hooks. An Env may bring its own division / sqrt / exp (m_div, m_sqrt, m_exp): the run-time specialised team
+// kernel (host/jit_team.hpp) uses that to evaluate Mos1 with the branch-free forms of scalar.h and a deferred
+// exception flag. Every other Env gets the exact s_div and the library calls — the same bits either way.
+template <class Env> __device__ __forceinline__ auto e_div_(Env& e, double a, double b, int) -> decltype(e.m_div(a, b)) { return e.m_div(a, b); }
+template <class Env> __device__ __forceinline__ double e_div_(Env&, double a, double b, long) { return s_div(a, b); }
+template <class Env> __device__ __forceinline__ auto e_sqrt_(Env& e, double a, int) -> decltype(e.m_sqrt(a)) { return e.m_sqrt(a); }
+template <class Env> __device__ __forceinline__ double e_sqrt_(Env&, double a, long) { return sqrt(a); }
+template <class Env> __device__ __forceinline__ auto e_exp_(Env& e, double a, int) -> decltype(e.m_exp(a)) { return e.m_exp(a); }
+template <class Env> __device__ __forceinline__ double e_exp_(Env&, double a, long) { return exp(a); }
+#define E_DIV(a, b) e_div_(e, (a), (b), 0)
+#define E_SQRT(a) e_sqrt_(e, (a), 0)
+#define E_EXP(a) e_exp_(e, (a), 0)
+
 // TranState::integrate, Backward Euler (analysis.rs:420-428): g = dq_dv/dt, i = dq/dt, rhs = i - g*vguess
 struct Integ { double g, i, rhs; };
+template <class Env> __device__ __forceinline__ Integ integrate_be_e(Env& e, double dt, double dq, double dq_dv, double vguess) {
+  Integ r;
+  r.g = E_DIV(dq_dv, dt);
+  r.i = E_DIV(dq, dt);
+  r.rhs = r.i - r.g * vguess;
+  return r;
+}
 __device__ __forceinline__ Integ integrate_be(double dt, double dq, double dq_dv, double vguess) {
   Integ r;
   r.g = s_div(dq_dv, dt);  // s_div: exact, with a shortcut for the (frequent) zero numerator
@@ -192,7 +212,7 @@ template <class Env> __device__ __forceinline__ void load_mos1(Env& e) {
   const double vdb = p * (vd - v_b);
   const double vt0_t = e.par(M1P_VT0T), phi_t = e.par(M1P_PHIT), gamma = e.par(M1P_GAMMA), beta = e.par(M1P_BETA);
   const double lambda = e.par(M1P_LAMBDA);
-  const double von = vsb > 0.0 ? vt0_t + gamma * (sqrt(phi_t + vsb) - sqrt(phi_t)) : vt0_t;
+  const double von = vsb > 0.0 ? vt0_t + gamma * (E_SQRT(phi_t + vsb) - E_SQRT(phi_t)) : vt0_t;
   const double vov = vgs - von;
   const double vdsat = fmax(vov, 0.0);
   double ids = 0.0, gm = 0.0, gds = 0.0, gmbs = 0.0;
@@ -206,19 +226,19 @@ template <class Env> __device__ __forceinline__ void load_mos1(Env& e) {
       gm = beta * vds * (1.0 + lambda * vds);
       gds = beta * ((vov - vds) * (1.0 + lambda * vds) + lambda * ((vov * vds) - (vds * vds) / 2.0));
     }
-    gmbs = (phi_t + vsb > 0.0) ? gm * gamma / 2.0 / sqrt(phi_t + vsb) : 0.0;
+    gmbs = (phi_t + vsb > 0.0) ? E_DIV(gm * gamma / 2.0, E_SQRT(phi_t + vsb)) : 0.0;
   }
   // bulk junction diodes; the junction parameter blocks swap with the channel direction (mos.rs:710-714)
   const double vtherm = e.par(M1P_VTHERM);
   const int bs_j = reversed ? M1P_DJ : M1P_SJ, bd_j = reversed ? M1P_SJ : M1P_DJ;
   const double bs_isat = e.par(bs_j + MJ_ISAT), bd_isat = e.par(bd_j + MJ_ISAT);
-  const double ebs = exp(s_div(-vsb, vtherm));
+  const double ebs = E_EXP(E_DIV(-vsb, vtherm));
   const double ibs = bs_isat * (ebs - 1.0);
-  const double gbs = (bs_isat / vtherm) * ebs + gmin;
+  const double gbs = E_DIV(bs_isat, vtherm) * ebs + gmin;
   const double ibs_rhs = ibs + vsb * gbs;
-  const double ebd = exp(s_div(-vdb, vtherm));
+  const double ebd = E_EXP(E_DIV(-vdb, vtherm));
   const double ibd = bd_isat * (ebd - 1.0);
-  const double gbd = (bd_isat / vtherm) * ebd + gmin;
+  const double gbd = E_DIV(bd_isat, vtherm) * ebd + gmin;
   const double ibd_rhs = ibd + vdb * gbd;
   // Meyer gate capacitances (mos.rs:725-752)
   const double cox = e.par(M1P_COX);
@@ -226,19 +246,19 @@ template <class Env> __device__ __forceinline__ void load_mos1(Env& e) {
   if (vov <= -phi_t) {
     cgb1 = cox / 2.0; cgs1 = 0.0; cgd1 = 0.0;
   } else if (vov <= -phi_t / 2.0) {
-    cgb1 = s_div(-vov * cox, 2.0 * phi_t); cgs1 = 0.0; cgd1 = 0.0;
+    cgb1 = E_DIV(-vov * cox, 2.0 * phi_t); cgs1 = 0.0; cgd1 = 0.0;
   } else if (vov <= 0.0) {
-    cgb1 = s_div(-vov * cox, 2.0 * phi_t);
-    cgs1 = s_div(vov * cox, 1.5 * phi_t) + s_div(cox, 3.0);
+    cgb1 = E_DIV(-vov * cox, 2.0 * phi_t);
+    cgs1 = E_DIV(vov * cox, 1.5 * phi_t) + E_DIV(cox, 3.0);
     cgd1 = 0.0;
   } else if (vdsat <= vds) {
-    cgs1 = s_div(cox, 3.0); cgd1 = 0.0; cgb1 = 0.0;
+    cgs1 = E_DIV(cox, 3.0); cgd1 = 0.0; cgb1 = 0.0;
   } else {
     const double vddif = 2.0 * vdsat - vds;
     const double vddif1 = vdsat - vds;
     const double vddif2 = vddif * vddif;
-    cgd1 = s_div(cox * (1.0 - s_div(vdsat * vdsat, vddif2)), 3.0);
-    cgs1 = s_div(cox * (1.0 - s_div(vddif1 * vddif1, vddif2)), 3.0);
+    cgd1 = E_DIV(cox * (1.0 - E_DIV(vdsat * vdsat, vddif2)), 3.0);
+    cgs1 = E_DIV(cox * (1.0 - E_DIV(vddif1 * vddif1, vddif2)), 3.0);
     cgb1 = 0.0;
   }
   // history averaging against the committed point (mos.rs:757-767)
@@ -252,11 +272,11 @@ template <class Env> __device__ __forceinline__ void load_mos1(Env& e) {
   const Integ tr_gd = {0.0, 0.0, 0.0};  // never assigned in the reference (mos.rs:801 writes tr.gs a second time)
   if (e.mode == AN_TRAN) {
     const double dqgs = same_dir ? (vgs - e.op(M1S_VGS)) * cgs : (vgs - e.op(M1S_VGD)) * cgs;
-    tr_gs = integrate_be(e.dt, dqgs, cgs, vgs);
+    tr_gs = integrate_be_e(e, e.dt, dqgs, cgs, vgs);
     const double dqgd = same_dir ? (vgd - e.op(M1S_VGD)) * cgd : (vgd - e.op(M1S_VGS)) * cgd;
-    tr_gs = integrate_be(e.dt, dqgd, cgd, vgd);  // overwrites the gate-source result, as the reference does
+    tr_gs = integrate_be_e(e, e.dt, dqgd, cgd, vgd);  // overwrites the gate-source result, as the reference does
     const double dqgb = (vgb - e.op(M1S_VGB)) * cgb;
-    tr_gb = integrate_be(e.dt, dqgb, cgb, vgb);
+    tr_gb = integrate_be_e(e, e.dt, dqgb, cgb, vgb);
     // tr.bs / tr.bd (mos.rs:808-827) are computed by the reference but never stamped nor read back: skipped.
   }
   const double irhs = ids - gm * vgs - gds * vds;

@@ -349,11 +349,16 @@ __global__ void k_selftest_div(unsigned long long n_per_thread, unsigned long lo
     const int ka = (int)(st_mix(x) & 7), kb = (int)(st_mix(x) & 7);
     const double a = st_draw(x, ka), a2 = st_draw(x, ka), b = st_draw(x, kb);
     const double r = s_rcp(b);
-    const double q[3] = {s_div(a, b), s_div_r(a2, b, r), s_scale(a, 1.0, b)};
-    const double w[3] = {a / b, a2 / b, a * 1.0 / b};
-    for (int k = 0; k < 3; k++) {
+    bool flagged = false;  // s_div_rf: whenever it does not raise its flag the value must be the IEEE quotient
+    const double qf = s_div_rf(a2, b, r, flagged);
+    bool fs = false, fe = false;  // likewise the branch-free sqrt / exp against the library calls
+    const double x_e = ka == 7 ? a * 700.0 : a;
+    const double sq = s_sqrt_f(a2, fs), ex = s_exp_f(x_e, fe);
+    const double q[6] = {s_div(a, b), s_div_r(a2, b, r), s_scale(a, 1.0, b), flagged ? a2 / b : qf, fs ? sqrt(a2) : sq, fe ? exp(x_e) : ex};
+    const double w[6] = {a / b, a2 / b, a * 1.0 / b, a2 / b, sqrt(a2), exp(x_e)};
+    for (int k = 0; k < 6; k++) {
       const bool same = (q[k] != q[k] && w[k] != w[k]) || __double_as_longlong(q[k]) == __double_as_longlong(w[k]);
-      if (!same && atomicAdd(bad, 1ull) == 0ull) { first_bad[0] = k == 1 ? a2 : a; first_bad[1] = b; first_bad[2] = q[k]; first_bad[3] = w[k]; }
+      if (!same && atomicAdd(bad, 1ull) == 0ull) { first_bad[0] = (k == 1 || k == 3 || k == 4) ? a2 : (k == 5 ? x_e : a); if (k >= 4) first_bad[1] = (double)k; first_bad[1] = b; first_bad[2] = q[k]; first_bad[3] = w[k]; }
     }
   }
 }

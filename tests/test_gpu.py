@@ -399,6 +399,34 @@ def test_team_kernel_devices_and_limits(s21, monkeypatch):
         s21.Batch(cc.rc_opamp(8).to_s21().elaborate(), 2).dcop()
 
 
+def test_team_kernel_fast_and_exact_text_agree(s21, monkeypatch):
+    """The team kernel's linear algebra is generated twice (host/jit_team.hpp): a branch-free text whose divisions defer
+    their exceptions, and the exact text it falls back to. Both, and the fallback itself — forced here by a 1e-300 S
+    resistor, whose L entries lie below the fast quotient's domain — give the direct kernel's bits."""
+    tiny = Ckt(signals=["a", "b", "c"]).V("v", "a", GND, 1.0).R("r1", "a", "b", 1e-3).R("rt", "b", "c", 1e-300).R("r2", "c", GND, 1e-3)
+    tiny.R("r3", "b", GND, 2e-3)
+    B = 83
+    dp, ovr = cc.diffpair(), cc.diffpair_mc(B)
+
+    def run(kernel, fast):
+        monkeypatch.setenv("S21_KERNEL", kernel)
+        monkeypatch.setenv("S21_TEAM_FAST", fast)
+        b = s21.Batch(dp.to_s21().elaborate(), B)
+        for key, v in ovr.items():
+            b.override(key, v)
+        bt = s21.Batch(tiny.to_s21().elaborate(), 5)
+        out = b.dcop() + bt.dcop()
+        return out, (b.kernel_name(), bt.kernel_name())
+
+    ref, _ = run("direct", "1")
+    assert np.all(ref[1] == 0) and np.all(ref[4] == 0)
+    for fast in ("1", "0"):
+        got, names = run("jitteam", fast)
+        assert names == ("jit-team", "jit-team")
+        for a, b_ in zip(ref, got):
+            assert np.array_equal(a, b_), fast
+
+
 # ------------------------------------------------------------------------------------------------ Bsim4
 def _bsim4_amp(nsel=None, psel=None, inst=None):
     """A CMOS stage with a resistive load and caps, Bsim4 cards given through the C ABI (the wire format carries none)."""
