@@ -202,18 +202,22 @@ def run_ours(args):
     # reset, solve, D2H of x / status / iteration counts — every step.
     e2e_steps = max(args.steps, 5)
     for _ in range(2):
-        batch.sync_params(force_upload=True); batch.reset(); batch.dcop()
+        batch.sync_params(force_upload=True); batch.reset(); batch.dcop_view()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         batch.sync_params(force_upload=True)
         batch.reset()
-        x, status, iters = batch.dcop()
+        x, status, iters = batch.dcop_view()  # results in the library's pinned host buffer (x[B][N], status[B], iters[B])
+        e2e_check = float(x[-1, 0]) + int(iters[-1])  # the host reads the step's result
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    assert np.all(status == 0) and int(iters.sum()) == iters_per_step and np.isfinite(e2e_check)
     sampler.stop_flag.set()
     sampler.join(timeout=2)
     d2h = B * c.n_vars * 8 + 3 * B * 4
+
+    tran = tran_metric(s21, cc, local, stream, rank)
 
     tot_ms, tot_kern_ms, tot_iters, tot_e2e = step_ms, kern_ms, iters_per_step, e2e_s
     if dist:
@@ -250,15 +254,48 @@ def run_ours(args):
                          "algorithmic_bytes_per_iteration": bi},
             "e2e": {"value": tot_iters * e2e_steps / tot_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * tot_e2e / e2e_steps, "steps": e2e_steps,
-                    "path": "s21_batch_sync_params(force) + s21_batch_reset + s21_batch_dcop (host buffers)"},
+                    "path": "s21_batch_sync_params(force: H2D of the parameter pool from pinned memory) + s21_batch_reset + s21_batch_dcop_view (D2H of x/status/iters into pinned host memory)"},
             "gpu_launches": args.steps * launches_per_step,
             "clocks": sampler.summary(),
         }
+        if tran is not None:
+            if dist:
+                tt = torch.tensor([tran["ms"]], dtype=torch.float64, device="cuda")
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                tran["ms"] = float(tt.item())
+            line["tran"] = {"metric": "tran_timepoints_per_sec", "value": world * tran["instances"] * tran["timepoints"] / (tran["ms"] * 1e-3),
+                            "unit": "timepoints/s", "newton_iters_per_sec": world * tran["iters"] / (tran["ms"] * 1e-3),
+                            "ms_per_transient": tran["ms"], "workload": tran["workload"], "kernel": tran["kernel"]}
         if world == 1:
             line["cpu_baseline"] = cpu_baseline(ck, ovr, B)
         print(json.dumps(line))
     if dist:
         dist.destroy_process_group()
+
+
+def tran_metric(s21, cc, local, stream, rank, B=B_PER_GPU):
+    """Second half of BASELINE.json's metric: transient timepoints/s. Workload = configs[0]'s circuit (the reference's Mos1
+    CMOS ring oscillator, tests.rs:889-912) as a supply sweep of B instances per GPU, 200 fixed Backward-Euler steps in one
+    launch (OP, IC release and the whole time loop on the device); device time from the library's CUDA events."""
+    try:
+        ro = cc.cmos_ro3(cc.add_mos1_defaults)
+        b = s21.Batch(ro.to_s21().elaborate(ic={"1": 0.0}), B, device=local)
+        b.set_stream(stream.cuda_stream)
+        b.override("V:v1:dc", np.linspace(0.9, 1.1, B) + 1e-4 * rank)
+        save = np.array([0, 1, 2], dtype=np.int32)
+        best, out = None, None
+        for _ in range(3):
+            b.reset()
+            t, w, st, it = b.tran(1e-11, 2e-9, save=save)
+            ms = b.stats()["device_ms"]
+            if best is None or ms < best:
+                best, out = ms, (len(t), int(it.sum()), bool(np.all(st == 0)))
+        assert out[2], "non-converged instances in the transient batch"
+        return {"ms": best, "instances": B, "timepoints": out[0] - 1, "iters": out[1], "kernel": b.kernel_name(),
+                "workload": f"C1 circuit (Mos1 CMOS ring oscillator, N=7) x {B} supply-sweep instances per GPU, tstep 1e-11, {out[0] - 1} points"}
+    except Exception as e:  # the headline metric must not depend on the secondary one
+        print(f"[bench] transient metric skipped: {e!r}", file=sys.stderr)
+        return None
 
 
 def cpu_baseline(ck, ovr, B):

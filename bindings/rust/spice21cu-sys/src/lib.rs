@@ -57,6 +57,7 @@ extern "C" {
     pub fn s21_batch_dcop(b: *mut s21_batch, x: *mut f64, status: *mut i32, iters: *mut i32) -> i32;
     pub fn s21_batch_dcop_device(b: *mut s21_batch) -> i32;
     pub fn s21_batch_read(b: *mut s21_batch, x: *mut f64, status: *mut i32, iters: *mut i32) -> i32;
+    pub fn s21_batch_dcop_view(b: *mut s21_batch, x: *mut *const f64, status: *mut *const i32, iters: *mut *const i32) -> i32;
     pub fn s21_tran_num_points(tstep: f64, tstop: f64) -> i64;
     pub fn s21_batch_tran(b: *mut s21_batch, tstep: f64, tstop: f64, save_vars: *const i32, n_save: usize, time: *mut f64, wave: *mut f64, status: *mut i32, iters: *mut i64) -> i32;
     pub fn s21_ac_freqs(fstart: u64, fstop: u64, npts: u64, freqs: *mut f64, cap: usize) -> i64;

@@ -106,6 +106,27 @@ impl<'c> Batch<'c> {
         Ok(r)
     }
 }
+/// Borrowed results of [`Batch::dcop_view`]: slices into the library's pinned staging buffer.
+pub struct DcopView<'b> {
+    pub x: &'b [f64],
+    pub status: &'b [i32],
+    pub iters: &'b [i32],
+}
+impl<'c> Batch<'c> {
+    /// `dcop` without the final host-side copy (`s21_batch_dcop_view`); the borrow ends before the next solve.
+    pub fn dcop_view(&mut self) -> SpResult<DcopView<'_>> {
+        let n = self.ckt.num_vars();
+        let (mut x, mut st, mut it) = (ptr::null(), ptr::null(), ptr::null());
+        check(unsafe { sys::s21_batch_dcop_view(self.h, &mut x, &mut st, &mut it) })?;
+        Ok(unsafe {
+            DcopView {
+                x: std::slice::from_raw_parts(x, n * self.b),
+                status: std::slice::from_raw_parts(st, self.b),
+                iters: std::slice::from_raw_parts(it, self.b),
+            }
+        })
+    }
+}
 impl<'c> Drop for Batch<'c> {
     fn drop(&mut self) {
         unsafe { sys::s21_batch_destroy(self.h) }

@@ -119,6 +119,11 @@ int32_t s21_batch_dcop(s21_batch* b, double* x, int32_t* status, int32_t* iters)
 /* Same solve with everything left resident in HBM (the timed kernel of bench.py); read back with s21_batch_read. */
 int32_t s21_batch_dcop_device(s21_batch* b);
 int32_t s21_batch_read(s21_batch* b, double* x, int32_t* status, int32_t* iters);
+/* s21_batch_dcop without the last host-side copy: the results stay in the library's pinned staging buffer and *x
+ * ([B][N] row-major; pass NULL to skip it), *status and *iters point into it. Valid until the next solve / read on this
+ * batch; the caller must not free or write them. (The reference returns an owned Vec, analysis.rs:383-388; a caller that
+ * needs ownership copies, which is what s21_batch_dcop does.) */
+int32_t s21_batch_dcop_view(s21_batch* b, const double** x, const int32_t** status, const int32_t** iters);
 /* Tran::solve (analysis.rs:526-573): OP at t=0, IC release, then fixed-step Backward Euler while t < tstop.
  * n_points_out = number of time points incl. t=0 (decided by the reference's floating-point `t += tstep`).
  * wave[B][T][n_save] and time[T] are host buffers sized by s21_tran_num_points; iters[B] counts all solves. */

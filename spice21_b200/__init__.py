@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "s21_ckt_num_vars", "s21_ckt_var_name", "s21_ckt_var_kind", "s21_ckt_num_devices", "s21_ckt_stamp_map", "s21_batch_create",
     "s21_batch_destroy", "s21_batch_set_stream", "s21_batch_override", "s21_batch_sync_params", "s21_batch_reset", "s21_batch_dcop",
     "s21_batch_dcop_device", "s21_batch_read", "s21_tran_num_points", "s21_batch_tran", "s21_ac_freqs", "s21_batch_ac",
-    "s21_batch_pivot_order", "s21_batch_stats", "s21_batch_kernel_name", "s21_jit_source", "s21_jit_check", "s21_selftest_div", "s21_symbolic",
+    "s21_batch_pivot_order", "s21_batch_dcop_view", "s21_batch_stats", "s21_batch_kernel_name", "s21_jit_source", "s21_jit_check", "s21_selftest_div", "s21_symbolic",
 ]
 
 
@@ -90,6 +90,7 @@ def lib():
         L.s21_batch_reset.argtypes = [C.c_void_p]
         L.s21_batch_dcop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.s21_batch_dcop_device.argtypes = [C.c_void_p]
+        L.s21_batch_dcop_view.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.s21_batch_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.s21_batch_tran.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.s21_batch_ac.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -356,6 +357,20 @@ class Batch:
         iters = np.zeros(self.B, dtype=np.int32)
         _check(lib().s21_batch_dcop(self.h, x.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p), iters.ctypes.data_as(C.c_void_p)))
         return x, status, iters
+
+    def dcop_view(self, want_x=True):
+        """dcop with the results left in the library's pinned staging buffer (s21_batch_dcop_view): the returned arrays are
+        read-only views, valid until the next solve or read on this batch — no host-side allocation or copy per call."""
+        px, ps, pi = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _check(lib().s21_batch_dcop_view(self.h, C.byref(px) if want_x else None, C.byref(ps), C.byref(pi)))
+
+        def view(p, ctype, shape):
+            a = np.ctypeslib.as_array(C.cast(p, C.POINTER(ctype)), shape=shape)
+            a.flags.writeable = False
+            return a
+
+        x = view(px, C.c_double, (self.B, self.N)) if want_x else None
+        return x, view(ps, C.c_int32, (self.B,)), view(pi, C.c_int32, (self.B,))
 
     def dcop_device(self):
         _check(lib().s21_batch_dcop_device(self.h))

@@ -335,6 +335,13 @@ int32_t s21_batch_dcop(s21_batch* b, double* x, int32_t* status, int32_t* iters)
   return S21_OK;
   S21_CATCH
 }
+int32_t s21_batch_dcop_view(s21_batch* b, const double** x, const int32_t** status, const int32_t** iters) {
+  S21_TRY
+  b->b->dcop_device();
+  b->b->read_view(x != nullptr, x, status, iters);
+  return S21_OK;
+  S21_CATCH
+}
 int64_t s21_tran_num_points(double tstep, double tstop) { return (int64_t)tran_times(tstep, tstop).size(); }
 int32_t s21_batch_tran(s21_batch* b, double tstep, double tstop, const int32_t* save_vars, size_t n_save, double* time, double* wave,
                        int32_t* status, int64_t* iters) {

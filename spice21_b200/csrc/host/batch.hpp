@@ -105,7 +105,8 @@ inline std::string debug_jit_source(const FlatCkt& flat, int mode, int shape, co
     return jit::source(flat, P, itab, pcode, mode == AN_TRAN);
   }
   if (!jit::team_eligible(flat, P, (size_t)227 * 1024)) throw S21Error(ST_UNSUPPORTED, "circuit not eligible for the team kernel");
-  return jit::team_source(flat, P, si, itab, pcode, mode == AN_TRAN, jit::team_lpi(P.N), smem_out);
+  const int lpi = jit::team_lpi(P.N);
+  return jit::team_source(flat, P, si, itab, pcode, mode == AN_TRAN, lpi, smem_out, 148, jit::team_gi(0, 0, lpi));
 }
 
 struct PlanDevice {
@@ -255,14 +256,19 @@ class Batch {
   // (Re)build the parameter pool on the host (derivations per instance where overridden) and upload it.
   void sync_params(bool force_upload) {
     S21_CUDA(cudaSetDevice(device_));
-    if (rebuild_ || pcode_h_.empty()) { rebuild_param_pool(); rebuild_ = false; params_dirty_ = true; }
+    if (rebuild_ || pcode_h_.empty()) { rebuild_param_pool(); rebuild_ = false; params_dirty_ = true; codes_dirty_ = true; }
     if (params_dirty_ || force_upload) {
-      d_pcode_.upload(pcode_h_, stream_);
-      d_poff_.upload(poff_eff_, stream_);
+      h2d_bytes_ = 0;
+      if (codes_dirty_) {  // the index tables only change with the pool's layout; a forced upload re-sends the values alone
+        d_pcode_.upload(pcode_h_, stream_);
+        d_poff_.upload(poff_eff_, stream_);
+        codes_dirty_ = false;
+        h2d_bytes_ += (pcode_h_.size() + poff_eff_.size()) * sizeof(int);
+      }
       d_pval_.alloc(pval_n_);
       S21_CUDA(cudaMemcpyAsync(d_pval_.p, pval_h_.p, pval_n_ * sizeof(double), cudaMemcpyHostToDevice, stream_));
       params_dirty_ = false;
-      h2d_bytes_ = pval_n_ * sizeof(double) + pcode_h_.size() * sizeof(int);
+      h2d_bytes_ += pval_n_ * sizeof(double);
     }
   }
   size_t last_h2d_bytes() const { return h2d_bytes_; }
@@ -278,12 +284,14 @@ class Batch {
     S21_CUDA(cudaEventRecord(ev1_, stream_));
     last_plan_ = &op_plan_;
   }
-  void read(double* x, int32_t* status, int32_t* iters) {
+  // Results of the last solve in the library's own pinned buffer: x rows [instance][variable] + status / iteration counts.
+  // Packed on the device, ONE contiguous D2H copy, no host-side copy; the pointers stay valid until the next read.
+  void read_view(bool want_x, const double** x, const int32_t** status, const int32_t** iters) {
     S21_CUDA(cudaSetDevice(device_));
     materialize_reset();
     const int N = flat_.n_vars();
     const int32_t *hs, *hi, *hl;
-    if (x) {  // pack on the device ([instance][variable] rows + the three counters), then ONE contiguous copy
+    if (want_x) {
       const size_t words = (size_t)N * B_ + (3 * B_ * sizeof(int32_t) + 7) / 8;
       d_rows_.alloc(words);
       hx_.alloc(words);
@@ -292,7 +300,6 @@ class Batch {
       if (rc) throw S21Error(ST_CUDA, std::string("k_pack_out launch failed: ") + cudaGetErrorString((cudaError_t)rc));
       S21_CUDA(cudaMemcpyAsync(hx_.p, d_rows_.p, words * sizeof(double), cudaMemcpyDeviceToHost, stream_));
       S21_CUDA(cudaStreamSynchronize(stream_));
-      std::memcpy(x, hx_.p, (size_t)N * B_ * sizeof(double));
       hs = reinterpret_cast<const int32_t*>(hx_.p + (size_t)N * B_);
       hi = hs + B_;
       hl = hi + B_;
@@ -306,13 +313,22 @@ class Batch {
     }
     sum_iters_ = 0; sum_loads_ = 0;
     for (size_t i = 0; i < B_; i++) {
-      if (status) status[i] = hs[i];
-      if (iters) iters[i] = hi[i];
       sum_iters_ += hi[i];
       sum_loads_ += hl[i];
     }
+    if (x) *x = want_x ? hx_.p : nullptr;
+    if (status) *status = hs;
+    if (iters) *iters = hi;
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, ev0_, ev1_) == cudaSuccess) last_ms_ = ms;
+  }
+  void read(double* x, int32_t* status, int32_t* iters) {
+    const double* hx = nullptr;
+    const int32_t *hs = nullptr, *hi = nullptr;
+    read_view(x != nullptr, &hx, &hs, &hi);
+    if (x) std::memcpy(x, hx, (size_t)flat_.n_vars() * B_ * sizeof(double));
+    if (status) std::memcpy(status, hs, B_ * sizeof(int32_t));
+    if (iters) std::memcpy(iters, hi, B_ * sizeof(int32_t));
   }
 
   // ---- tran -----------------------------------------------------------------------------------------------
@@ -511,7 +527,7 @@ class Batch {
   std::vector<int> pcode_h_, poff_eff_;
   size_t pval_n_ = 0, h2d_bytes_ = 0;
   std::vector<Override> overrides_;
-  bool params_dirty_ = true, rebuild_ = true;
+  bool params_dirty_ = true, rebuild_ = true, codes_dirty_ = true;
   PlanDevice op_plan_, tran_plan_, ac_plan_;
   const PlanDevice* last_plan_ = nullptr;
   size_t lu_rows_ = 0;
@@ -580,12 +596,13 @@ class Batch {
       std::string err;
       size_t smem = 0;
       const int lpi = jit::team_lpi(pd.host.N);
-      const std::string src = jit::team_source(flat_, pd.host, si_, pd.host_itab, pcode_h_, tran, lpi, &smem, n_sm_);
+      const int gi = jit::team_gi(B_, n_sm_, lpi);
+      const std::string src = jit::team_source(flat_, pd.host, si_, pd.host_itab, pcode_h_, tran, lpi, &smem, n_sm_, gi);
       if (const char* dump = std::getenv("S21_JIT_DUMP")) {
         if (FILE* f = std::fopen(dump, "w")) { std::fwrite(src.data(), 1, src.size(), f); std::fclose(f); }
       }
-      if (smem <= max_smem_ && jit::compile(src, tran, 32 * lpi, smem, &k, &err)) {
-        k.inst_per_cta = jit::TM_GI;
+      if (smem <= max_smem_ && jit::compile(src, tran, 32 * (gi / (32 / lpi)), smem, &k, &err)) {
+        k.inst_per_cta = gi;
         k.team = true;
       } else {
         k = jit::Kernel();

@@ -29,10 +29,13 @@ constexpr int TM_P = 36;     // padded instance stride of the shared-memory colu
 constexpr int TM_GI = 32;    // instances per CTA
 constexpr int TM_MAXN = 16;  // rows per instance the register-resident linear algebra is generated for
 // Lanes per instance in the linear-algebra phase: 8 (4 instances per warp, 8 warps per CTA; rows beyond 8 become a
-// second register set) or 16 (2 instances per warp, 16 warps per CTA; one row per member up to N = 16).
+// second register set), 10 (3 instances per warp) or 16 (2 instances per warp, 16 warps per CTA; one row per member).
 inline int team_lpi(int N) {
-  if (const char* e = std::getenv("S21_TEAM_LPI")) { const int v = std::atoi(e); if (v == 8 || v == 16) return v; }
+  if (const char* e = std::getenv("S21_TEAM_LPI")) { const int v = std::atoi(e); if (v == 8 || v == 10 || v == 16) return v; }
   (void)N;
+  // measured on C2 (N = 9, 8192 instances; profiles/r01t_team_shapes.txt): 8 lanes + a second register set 0.115 ms,
+  // 10 lanes (3 instances per warp, one row per member, 20 % fewer instructions) 0.123 ms, 16 lanes 0.160 ms — the
+  // launch follows the dependent chain of one iteration, which is the same in all three
   return 8;  // measured on C2 (N = 9): 0.133 ms with 8 lanes + a second register set, 0.179 ms with 16 lanes (profiles/r01l_*)
 }
 // S21_TEAM_PROFILE=1 adds clock64() probes at the phase boundaries of warp 0 (evaluates the heaviest device) and of the
@@ -40,6 +43,15 @@ inline int team_lpi(int N) {
 inline bool team_profile() { const char* e = std::getenv("S21_TEAM_PROFILE"); return e && std::atoi(e) != 0; }
 // S21_TEAM_FAST=0 generates the exact (branching) linear-algebra text only; default is the branch-free text with the exact
 // one as its redo path. Both give the same bits (tests/test_gpu.py::test_team_kernel_fast_and_exact_text_agree).
+// Instances per CTA: a full warp of instances in the evaluation phase (30 with 3 instances per warp). Smaller CTAs that
+// balance the SMs better (8192 instances: 293 CTAs of 28 -> 56 per SM instead of 64) measured the same 0.115 ms: the
+// launch is one dependent chain per CTA, not a throughput problem. S21_TEAM_GI overrides (experiments).
+inline int team_gi(size_t B, int n_sm, int lpi) {
+  const int ipw = 32 / lpi, gmax = TM_GI / ipw * ipw;
+  if (const char* e = std::getenv("S21_TEAM_GI")) { const int v = std::atoi(e); if (v >= ipw && v <= gmax && v % ipw == 0) return v; }
+  (void)B; (void)n_sm;
+  return gmax;
+}
 inline bool team_fast() { const char* e = std::getenv("S21_TEAM_FAST"); return !e || std::atoi(e) != 0; }
 
 struct TeamGather {
@@ -63,13 +75,16 @@ inline bool team_eligible(const FlatCkt& flat, const Plan& P, size_t max_smem) {
 }
 
 inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageInfo& si, const std::vector<int>& itab,
-                               const std::vector<int>& pcode, bool tran, int TM_LPI, size_t* smem_out, int n_sm = 148) {
+                               const std::vector<int>& pcode, bool tran, int TM_LPI, size_t* smem_out, int n_sm = 148, int GI = TM_GI) {
+  (void)n_sm;
   std::ostringstream o;
   const int N = P.N, NST = P.n_stage, NSTATE = std::max(flat.n_state, 1), Q = (N + TM_LPI - 1) / TM_LPI;
   const int IPW = 32 / TM_LPI;        // instances per warp in the linear-algebra phase
-  const int NW = TM_GI / IPW;         // warps per CTA
-  const int LG_IPW = IPW == 4 ? 2 : 1;
-  const unsigned FULLSET = TM_LPI == 16 ? 0xffffu : 0xffu;
+  const int NW = GI / IPW;         // warps per CTA
+  const bool POW2 = (TM_LPI & (TM_LPI - 1)) == 0;  // otherwise the last lanes of a warp belong to no instance (j >= TM_LPI)
+  const unsigned FULLSET = (1u << TM_LPI) - 1u;
+  unsigned IMASK = 0u;  // lanes of instance 0 of a warp
+  for (int jj = 0; jj < TM_LPI; jj++) IMASK |= 1u << (IPW * jj);
   auto qof = [&](int r) { return r / TM_LPI; };
   auto jof = [&](int r) { return r % TM_LPI; };
   // ---- pattern bookkeeping in pivoted coordinates
@@ -149,8 +164,8 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
   for (size_t k = 0; k < G.table.size(); k++) o << (k ? "," : "") << G.table[k];
   if (G.table.empty()) o << "0";
   o << "};\n";
-  o << "__device__ const int XO_G[" << Q * TM_LPI << "] = {";
-  for (int k = 0; k < Q * TM_LPI; k++) o << (k ? "," : "") << (k < N ? P.col_i2e[(size_t)k] * TM_P : 0);
+  o << "__device__ const int XO_G[" << Q * TM_LPI + 8 << "] = {";
+  for (int k = 0; k < Q * TM_LPI + 8; k++) o << (k ? "," : "") << (k < N ? P.col_i2e[(size_t)k] * TM_P : 0);
   o << "};\n";
   o << "struct JBase {\n  const double* pval; size_t pinst; double* sop; double* sguess; const double* X; double* S;\n"
        "  int mode; double dt, gmin, omega;\n"
@@ -180,8 +195,9 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
     o << "  __device__ __forceinline__ void add_b_at(int pos, double v) { S[(" << sto << " + pos) * PS] = v; }\n";
     o << "  __device__ __forceinline__ void add_g_dup(int, int dup, double v) { S[(" << sto << " + dup) * PS] = v; }\n};\n";
   }
+  for (int jj = 0; jj < TM_LPI; jj++) G.table.push_back(zero_off);  // idle lanes (j >= lanes per instance) read one row further
   const size_t n_gt = G.table.size();
-  const size_t ctrl_ints = (size_t)TM_GI + n_gt;
+  const size_t ctrl_ints = (size_t)GI + n_gt;
   const size_t ctrl_bytes = (ctrl_ints * 4 + 15) / 16 * 16;
   *smem_out = ctrl_bytes + 8 * (size_t)TM_P * ((size_t)N + (size_t)NST + 1 + 2 * (size_t)NSTATE);
 
@@ -190,18 +206,18 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
        "    double reltol, double iabstol, int cold, int T_points, int n_save, const int* __restrict__ save_vars, double* wave) {\n"
        "  extern __shared__ __align__(16) unsigned char smem_raw[];\n"
        "  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;\n"
-       "  const int i0 = blockIdx.x * " << TM_GI << ";\n"
-       "  const int ni = min(" << TM_GI << ", B - i0);\n"
-       "  const int ei = lane, base = lane & " << IPW - 1 << ", j = lane >> " << LG_IPW << ", ri = warp * " << IPW << " + base;\n"
-       "  const unsigned imask = " << (IPW == 4 ? "0x11111111u" : "0x55555555u") << " << base, jbit = 1u << j;\n"
-       "  int* act_s = (int*)smem_raw;\n  int* gt = act_s + " << TM_GI << ";\n"
+       "  const int i0 = blockIdx.x * " << GI << ";\n"
+       "  const int ni = min(" << GI << ", B - i0);\n"
+       "  const int ei = lane, base = lane % " << IPW << ", j = lane / " << IPW << ", ri = warp * " << IPW << " + base;\n"
+       "  const unsigned imask = " << IMASK << "u << base, jbit = 1u << j;\n"
+       "  int* act_s = (int*)smem_raw;\n  int* gt = act_s + " << GI << ";\n"
        "  double* X = (double*)(smem_raw + " << ctrl_bytes << ");\n"
        "  double* S = X + " << N * TM_P << ";\n"
        "  double* sop = S + " << (NST + 1) * TM_P << ";\n"
        "  double* sguess = sop + " << NSTATE * TM_P << ";\n"
        "  for (int k = tid; k < " << n_gt << "; k += " << NW * 32 << ") gt[k] = GT_G[k];\n"
        "  if (tid < PS) S[" << zero_off << " + tid] = 0.0;\n"
-       "  const bool evalid = ei < ni, rvalid = ri < ni;\n"
+       "  const bool evalid = ei < ni, rvalid = ri < ni" << (POW2 ? "" : " && j < " + std::to_string(TM_LPI)) << ";\n"
        "  for (int k = warp; k < " << N << "; k += " << NW << ") X[k * PS + ei] = (evalid && !cold) ? gx[(size_t)k * stride + i0 + ei] : 0.0;\n"
        "  for (int k = warp; k < " << flat.n_state << "; k += " << NW << ") {\n"
        "    const size_t src = (size_t)k * st_stride + (size_t)i0 + (size_t)(evalid ? ei : 0);\n"
@@ -214,7 +230,7 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
   o << "  const int* gtj = gt + j;\n  const double* Sri = S + ri;\n";
   for (int q = 0; q < Q; q++) {
     o << "  const int xo" << q << " = XO_G[" << q * TM_LPI << " + j];\n";
-    o << "  const bool v" << q << " = " << (valid_mask(q) == FULLSET ? std::string("true") : "j < " + std::to_string(N - q * TM_LPI)) << ";\n";
+    o << "  const bool v" << q << " = " << (valid_mask(q) == FULLSET && POW2 ? std::string("true") : "j < " + std::to_string(std::min(TM_LPI, N - q * TM_LPI))) << ";\n";
   }
   o << "  JBase eb; eb.pval = pval; eb.pinst = (size_t)i0 + (size_t)ei; eb.sop = sop + ei; eb.sguess = sguess + ei; eb.X = X + ei; eb.S = S + ei;\n"
        "  eb.mode = " << (tran ? "AN_TRAN" : "AN_OP") << "; eb.dt = dt; eb.gmin = gmin; eb.omega = 0.0;\n";  // literal: the other mode's code is dropped
@@ -226,7 +242,7 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
        "    __syncthreads();\n";
   for (int q = 0; q < Q; q++) o << "    double xp" << q << " = v" << q << " ? X[xo" << q << " + ri] : 0.0;\n";
   o << "    for (int iter = 0; iter < 100; iter++) {\n      PH(0)\n"
-       "      if (act_s[ei]) {\n        switch (warp) {\n";
+       "      if (ei < " << GI << " && act_s[ei]) {\n        switch (warp) {\n";
   // ---- device evaluation: eval_order position w, w+NW, ... on warp w
   for (int w = 0; w < NW && w < (int)si.eval_order.size(); w++) {
     o << "          case " << w << ": {\n";
@@ -276,10 +292,11 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
   // of scalar.h with its exception deferred into `dbad`, every lane mask and every zero test a select, so that the whole
   // solve is one basic block (independent pivots, rows and columns overlap); the exact text is kept for the redo.
   auto emit_solve = [&](std::ostream& o, bool fast) {
-    auto divide = [&](const std::string& dst, const std::string& num, const std::string& den, const std::string& rcp, const std::string& cond) {
+    auto divide = [&](const std::string& dst, const std::string& num, const std::string& den, const std::string& rcp, const std::string& bok,
+                      const std::string& cond) {
       if (fast)
-        o << "            { bool bd = false; const double t = s_div_rf(" << num << ", " << den << ", " << rcp << ", bd); const bool in = " << cond << "; "
-          << dst << " = in ? t : " << dst << "; dbad = dbad || (in && bd); }\n";
+        o << "            { bool bd = false; const double t = s_div_rp(" << num << ", " << den << ", " << rcp << ", " << bok << ", bd); if (" << cond << ") { "
+          << dst << " = t; dbad = dbad || bd; } }\n";
       else
         o << "            if (" << cond << ") " << dst << " = s_div_r(" << num << ", " << den << ", " << rcp << ");\n";
     };
@@ -290,18 +307,16 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
       for (int q = 0; q < Q; q++) anyL = anyL || LM[(size_t)q][(size_t)k];
       if (anyL) {
         o << "            const double rp = s_rcp(piv);\n";  // one reciprocal per pivot, shared by the column's entries (scalar.h)
+        if (fast) o << "            const bool pok = s_div_bok(piv);\n";
         for (int q = 0; q < Q; q++)
-          if (LM[(size_t)q][(size_t)k]) divide(A(q, k), A(q, k), "piv", "rp", mask_test(LM[(size_t)q][(size_t)k]) + " != 0u");
+          if (LM[(size_t)q][(size_t)k]) divide(A(q, k), A(q, k), "piv", "rp", "pok", mask_test(LM[(size_t)q][(size_t)k]));
         for (int s = P.diag_slot[(size_t)k] + 1; s < P.rowptr[(size_t)k + 1]; s++) {
           const int c = P.colidx[(size_t)s];
           o << "            { const double u = BC(" << A(qk, c) << ", " << jk << ");\n";
           for (int q = 0; q < Q; q++)
             if (LM[(size_t)q][(size_t)k]) {
               const std::string upd = "s_sub(" + A(q, c) + ", s_mul(u, " + A(q, k) + "))";
-              if (fast)
-                o << "              " << A(q, c) << " = " << mask_test(LM[(size_t)q][(size_t)k]) << " ? " << upd << " : " << A(q, c) << ";\n";
-              else
-                o << "              if " << mask_test(LM[(size_t)q][(size_t)k]) << " " << A(q, c) << " = " << upd << ";\n";
+              o << "              if " << mask_test(LM[(size_t)q][(size_t)k]) << " " << A(q, c) << " = " << upd << ";\n";
             }
           o << "            }\n";
         }
@@ -319,8 +334,7 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
         o << "            const bool nz = !(ck == 0.0);\n";
         for (int q = 0; q < Q; q++)
           if (LM[(size_t)q][(size_t)k])
-            o << "            c" << q << " = (nz && " << mask_test(LM[(size_t)q][(size_t)k]) << ") ? s_sub(c" << q << ", s_mul(ck, " << A(q, k) << ")) : c" << q
-              << ";\n";
+            o << "            if (nz && " << mask_test(LM[(size_t)q][(size_t)k]) << ") c" << q << " = s_sub(c" << q << ", s_mul(ck, " << A(q, k) << "));\n";
         o << "          }\n";
       } else {
         o << "            if (!(ck == 0.0)) {\n";
@@ -341,6 +355,7 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
       for (int jj = 0; jj < TM_LPI && q * TM_LPI + jj < N; jj++)
         o << "          if (j == " << jj << ") dg" << q << " = " << A(q, q * TM_LPI + jj) << ";\n";
       o << "          const double rd" << q << " = s_rcp(dg" << q << ");\n";
+      if (fast) o << "          const bool dok" << q << " = s_div_bok(dg" << q << ");\n";
     }
     for (int k = N - 1; k >= 0; k--) {
       const int qk = qof(k), jk = jof(k);
@@ -349,7 +364,7 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
         const int c = P.colidx[(size_t)s];
         o << "            ck = s_sub(ck, s_mul(cb" << c << ", " << A(qk, c) << "));\n";
       }
-      divide("c" + std::to_string(qk), "ck", "dg" + std::to_string(qk), "rd" + std::to_string(qk), "j == " + std::to_string(jk));
+      divide("c" + std::to_string(qk), "ck", "dg" + std::to_string(qk), "rd" + std::to_string(qk), "dok" + std::to_string(qk), "j == " + std::to_string(jk));
       o << "          }\n";
       if (need_bc[(size_t)k]) o << "          const double cb" << k << " = BC(c" << qk << ", " << jk << ");\n";
     }
@@ -372,7 +387,8 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
     emit_solve(o, true);
     o << "          }\n";
     // deferred exceptions: some quotient of this warp left the fast path's domain -> the exact text, from the stamps
-    o << "          if (__any_sync(FULLM, dbad)) {\n          sing = false;\n";
+    // (only of instances still iterating: finished and padding instances compute on stale or arbitrary data)
+    o << "          if (__any_sync(FULLM, dbad && r_act)) {\n          sing = false;\n";
     std::string g2 = gath.str();
     o << g2;
     emit_residual(o);
@@ -384,7 +400,13 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
   // max |dx| over the team, global step limit, update
   o << "          PH(7)\n          double m = 0.0;\n";
   for (int q = 0; q < Q; q++) o << "          if (v" << q << ") m = fmax(m, s_abs(c" << q << "));\n";
-  for (int off = IPW; off < 32; off *= 2) o << "          m = fmax(m, __shfl_xor_sync(FULLM, m, " << off << "));\n";
+  if (POW2) {
+    for (int off = IPW; off < 32; off *= 2) o << "          m = fmax(m, __shfl_xor_sync(FULLM, m, " << off << "));\n";
+  } else {  // reduce down to member 0, then broadcast
+    for (int off = 8; off >= 1; off /= 2)
+      o << "          m = fmax(m, __shfl_sync(FULLM, m, j + " << off << " < " << TM_LPI << " ? lane + " << IPW * off << " : lane));\n";
+    o << "          m = BC(m, 0);\n";
+  }
   o << "          bool baddx = false;\n          const double rm = s_rcp(m);\n          if (r_act && !sing) {\n";
   for (int q = 0; q < Q; q++)
     o << "            if (v" << q << ") { double dxk = c" << q << "; if (m > 1.0) dxk = s_div_r(s_mul(dxk, 1.0), m, rm); xp" << q << " = s_add(xp" << q

@@ -354,11 +354,13 @@ __global__ void k_selftest_div(unsigned long long n_per_thread, unsigned long lo
     bool fs = false, fe = false;  // likewise the branch-free sqrt / exp against the library calls
     const double x_e = ka == 7 ? a * 700.0 : a;
     const double sq = s_sqrt_f(a2, fs), ex = s_exp_f(x_e, fe);
-    const double q[6] = {s_div(a, b), s_div_r(a2, b, r), s_scale(a, 1.0, b), flagged ? a2 / b : qf, fs ? sqrt(a2) : sq, fe ? exp(x_e) : ex};
-    const double w[6] = {a / b, a2 / b, a * 1.0 / b, a2 / b, sqrt(a2), exp(x_e)};
-    for (int k = 0; k < 6; k++) {
+    bool fp = false;
+    const double qp = s_div_rp(a2, b, r, s_div_bok(b), fp);
+    const double q[7] = {s_div(a, b), s_div_r(a2, b, r), s_scale(a, 1.0, b), flagged ? a2 / b : qf, fs ? sqrt(a2) : sq, fe ? exp(x_e) : ex, fp ? a2 / b : qp};
+    const double w[7] = {a / b, a2 / b, a * 1.0 / b, a2 / b, sqrt(a2), exp(x_e), a2 / b};
+    for (int k = 0; k < 7; k++) {
       const bool same = (q[k] != q[k] && w[k] != w[k]) || __double_as_longlong(q[k]) == __double_as_longlong(w[k]);
-      if (!same && atomicAdd(bad, 1ull) == 0ull) { first_bad[0] = (k == 1 || k == 3 || k == 4) ? a2 : (k == 5 ? x_e : a); if (k >= 4) first_bad[1] = (double)k; first_bad[1] = b; first_bad[2] = q[k]; first_bad[3] = w[k]; }
+      if (!same && atomicAdd(bad, 1ull) == 0ull) { first_bad[0] = (k == 1 || k == 3 || k == 4 || k == 6) ? a2 : (k == 5 ? x_e : a); if (k >= 4) first_bad[1] = (double)k; first_bad[1] = b; first_bad[2] = q[k]; first_bad[3] = w[k]; }
     }
   }
 }

@@ -333,7 +333,7 @@ def test_ragged_batch_sizes(s21, oracle, B):
     assert np.all(st == 0) and rel_err(x, o["x"], floor=1e-9) <= 1e-9 and np.array_equal(it, o["iters"])
 
 
-@pytest.mark.parametrize("kernel", ["direct", "coop", "hybrid", "jit", "jitteam", "jitteam:8", "jitteam:16"])
+@pytest.mark.parametrize("kernel", ["direct", "coop", "hybrid", "jit", "jitteam", "jitteam:8", "jitteam:10", "jitteam:16"])
 def test_kernel_variants_bit_identical(s21, kernel, monkeypatch):
     """The Newton kernels (one thread per instance, CTA-cooperative, hybrid, and the two run-time specialised shapes)
     perform the same operations in the same order per value: identical bits, identical iteration counts — dcop and
@@ -397,6 +397,23 @@ def test_team_kernel_devices_and_limits(s21, monkeypatch):
     monkeypatch.setenv("S21_KERNEL", "jitteam")
     with pytest.raises(s21.Spice21Error):  # N = 68 > 16 rows
         s21.Batch(cc.rc_opamp(8).to_s21().elaborate(), 2).dcop()
+
+
+def test_dcop_view_matches_dcop(s21):
+    """s21_batch_dcop_view hands out the library's pinned result buffer instead of copying into caller arrays: same values,
+    read-only, and refreshed by the next solve."""
+    B = 100
+    b = s21.Batch(cc.diffpair().to_s21().elaborate(), B)
+    for key, v in cc.diffpair_mc(B).items():
+        b.override(key, v)
+    x, st, it = b.dcop()
+    b.reset()
+    xv, stv, itv = b.dcop_view()
+    assert xv.shape == (B, b.N) and not xv.flags.writeable
+    assert np.array_equal(x, xv) and np.array_equal(st, stv) and np.array_equal(it, itv)
+    b.reset()
+    _, st2, it2 = b.dcop_view(want_x=False)
+    assert np.array_equal(st, st2) and np.array_equal(it, it2)
 
 
 def test_team_kernel_fast_and_exact_text_agree(s21, monkeypatch):
