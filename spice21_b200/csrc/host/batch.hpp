@@ -105,7 +105,7 @@ inline std::string debug_jit_source(const FlatCkt& flat, int mode, int shape, co
     return jit::source(flat, P, itab, pcode, mode == AN_TRAN);
   }
   if (!jit::team_eligible(flat, P, (size_t)227 * 1024)) throw S21Error(ST_UNSUPPORTED, "circuit not eligible for the team kernel");
-  const int lpi = jit::team_lpi(P.N);
+  const int lpi = jit::team_lpi(P.N, jit::team_heavy_devices(flat));
   return jit::team_source(flat, P, si, itab, pcode, mode == AN_TRAN, lpi, smem_out, 148, jit::team_gi(0, 0, lpi));
 }
 
@@ -556,7 +556,11 @@ class Batch {
     // dependent chain: it wins once there are enough warps to overlap chains (measured on C2, profiles/r01g_*: 2.5 G
     // iters/s at 1 M instances, but 0.284 ms at 8192 where every warp sits alone on its scheduler). Below that the
     // team shape (host/jit_team.hpp: 8 lanes per instance, rows in registers) is used. S21_KERNEL=jit / jitteam force one.
-    const bool thread_ok = !jit_team_forced_ && jit::eligible(flat_, pd.host, max_smem_) && (jit_forced_ || B_ >= jit_thread_min_b());
+    // Since the team kernel runs with 2-4 lanes per instance it is ahead of the thread kernel at every batch size measured
+    // (C2: 0.084 vs 0.212 ms at 8192, 4.36 vs 3.24 G iters/s at 1 M; profiles/r01t_team_shapes.txt), so the thread kernel
+    // is only picked for circuits the team generator does not take.
+    const bool thread_ok = !jit_team_forced_ && jit::eligible(flat_, pd.host, max_smem_) &&
+                           (jit_forced_ || (B_ >= jit_thread_min_b() && !jit::team_eligible(flat_, pd.host, max_smem_)));
     if (!thread_ok) return jit_team_kernel(pd, tran);
     jit::Kernel& k = tran ? pd.jit_tran : pd.jit_dcop;
     bool& tried = tran ? pd.jit_tried_tran : pd.jit_tried_dcop;
@@ -595,13 +599,14 @@ class Batch {
       tried = true;
       std::string err;
       size_t smem = 0;
-      const int lpi = jit::team_lpi(pd.host.N);
+      const int lpi = jit::team_lpi(pd.host.N, jit::team_heavy_devices(flat_));
       const int gi = jit::team_gi(B_, n_sm_, lpi);
-      const std::string src = jit::team_source(flat_, pd.host, si_, pd.host_itab, pcode_h_, tran, lpi, &smem, n_sm_, gi);
+      int tpb = 0;
+      const std::string src = jit::team_source(flat_, pd.host, si_, pd.host_itab, pcode_h_, tran, lpi, &smem, n_sm_, gi, &tpb);
       if (const char* dump = std::getenv("S21_JIT_DUMP")) {
         if (FILE* f = std::fopen(dump, "w")) { std::fwrite(src.data(), 1, src.size(), f); std::fclose(f); }
       }
-      if (smem <= max_smem_ && jit::compile(src, tran, 32 * (gi / (32 / lpi)), smem, &k, &err)) {
+      if (smem <= max_smem_ && jit::compile(src, tran, tpb, smem, &k, &err)) {
         k.inst_per_cta = gi;
         k.team = true;
       } else {

@@ -30,13 +30,23 @@ constexpr int TM_GI = 32;    // instances per CTA
 constexpr int TM_MAXN = 16;  // rows per instance the register-resident linear algebra is generated for
 // Lanes per instance in the linear-algebra phase: 8 (4 instances per warp, 8 warps per CTA; rows beyond 8 become a
 // second register set), 10 (3 instances per warp) or 16 (2 instances per warp, 16 warps per CTA; one row per member).
-inline int team_lpi(int N) {
-  if (const char* e = std::getenv("S21_TEAM_LPI")) { const int v = std::atoi(e); if (v == 8 || v == 10 || v == 16) return v; }
+inline int team_lpi(int N, int n_heavy = 0) {
+  if (const char* e = std::getenv("S21_TEAM_LPI")) {
+    const int v = std::atoi(e);
+    if (v == 1 || v == 2 || v == 4 || v == 8 || v == 10 || v == 16) return v;
+  }
   (void)N;
-  // measured on C2 (N = 9, 8192 instances; profiles/r01t_team_shapes.txt): 8 lanes + a second register set 0.115 ms,
-  // 10 lanes (3 instances per warp, one row per member, 20 % fewer instructions) 0.123 ms, 16 lanes 0.160 ms — the
-  // launch follows the dependent chain of one iteration, which is the same in all three
-  return 8;  // measured on C2 (N = 9): 0.133 ms with 8 lanes + a second register set, 0.179 ms with 16 lanes (profiles/r01l_*)
+  // Fewer lanes per instance = more independent rows per lane (instruction-level parallelism inside the one dependent
+  // chain a Newton iteration is) and fewer warps per SM for the same batch. Measured on B200 (profiles/r01t_team_shapes.txt),
+  // C2 dcop (N = 9, 2 Mos1) at 8192 instances: 16 lanes 0.160 ms, 10 lanes 0.123, 8 lanes 0.116, 4 lanes 0.100,
+  // 2 lanes 0.085, 1 lane 0.106; C1 transient (N = 7, 6 Mos1, 200 points): 8 lanes 13.3 ms, 4 lanes 12.1, 2 lanes 12.7,
+  // 1 lane 15.1 — the evaluation phase wants a warp per expensive device, so device-heavy circuits keep 4 lanes.
+  return n_heavy <= 2 ? 2 : 4;
+}
+inline int team_heavy_devices(const FlatCkt& flat) {
+  int n = 0;
+  for (const FlatDev& d : flat.devs) n += (d.type == DT_MOS1 || d.type == DT_DIODE || d.type == DT_MOS0) ? 1 : 0;
+  return n;
 }
 // S21_TEAM_PROFILE=1 adds clock64() probes at the phase boundaries of warp 0 (evaluates the heaviest device) and of the
 // last warp (idle during evaluation) of CTA 0 and prints the per-phase cycle sums when the kernel ends (diagnostic only).
@@ -75,12 +85,16 @@ inline bool team_eligible(const FlatCkt& flat, const Plan& P, size_t max_smem) {
 }
 
 inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageInfo& si, const std::vector<int>& itab,
-                               const std::vector<int>& pcode, bool tran, int TM_LPI, size_t* smem_out, int n_sm = 148, int GI = TM_GI) {
+                               const std::vector<int>& pcode, bool tran, int TM_LPI, size_t* smem_out, int n_sm = 148, int GI = TM_GI, int* tpb_out = nullptr) {
   (void)n_sm;
   std::ostringstream o;
   const int N = P.N, NST = P.n_stage, NSTATE = std::max(flat.n_state, 1), Q = (N + TM_LPI - 1) / TM_LPI;
   const int IPW = 32 / TM_LPI;        // instances per warp in the linear-algebra phase
-  const int NW = GI / IPW;         // warps per CTA
+  const int NW_LA = GI / IPW;      // warps of the linear-algebra phase
+  // S21_TEAM_NW adds warps that only take part in the evaluation phase and sit out the linear algebra (ri >= GI).
+  int NW = NW_LA;  // measured: extra evaluation warps cost more at the barriers than they save (C2 0.086 -> 0.091 / 0.100 ms with 4 / 8)
+  if (const char* e = std::getenv("S21_TEAM_NW")) { const int v = std::atoi(e); if (v >= NW_LA && v <= 16) NW = v; }
+  if (tpb_out) *tpb_out = NW * 32;
   const bool POW2 = (TM_LPI & (TM_LPI - 1)) == 0;  // otherwise the last lanes of a warp belong to no instance (j >= TM_LPI)
   const unsigned FULLSET = (1u << TM_LPI) - 1u;
   unsigned IMASK = 0u;  // lanes of instance 0 of a warp
@@ -217,7 +231,7 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
        "  double* sguess = sop + " << NSTATE * TM_P << ";\n"
        "  for (int k = tid; k < " << n_gt << "; k += " << NW * 32 << ") gt[k] = GT_G[k];\n"
        "  if (tid < PS) S[" << zero_off << " + tid] = 0.0;\n"
-       "  const bool evalid = ei < ni, rvalid = ri < ni" << (POW2 ? "" : " && j < " + std::to_string(TM_LPI)) << ";\n"
+       "  const bool evalid = ei < ni, rvalid = ri < ni" << (POW2 ? "" : " && j < " + std::to_string(TM_LPI)) << ", rin = ri < " << GI << ";\n"
        "  for (int k = warp; k < " << N << "; k += " << NW << ") X[k * PS + ei] = (evalid && !cold) ? gx[(size_t)k * stride + i0 + ei] : 0.0;\n"
        "  for (int k = warp; k < " << flat.n_state << "; k += " << NW << ") {\n"
        "    const size_t src = (size_t)k * st_stride + (size_t)i0 + (size_t)(evalid ? ei : 0);\n"
@@ -238,9 +252,9 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
   o << "  const int n_points = " << (tran ? "T_points" : "2") << ";\n"
        "  for (int tp = 1; tp < n_points; tp++) {\n"
        "    bool r_act = rvalid && r_stat == 0;\n    bool r_dxok = true;\n"
-       "    if (j == 0) act_s[ri] = r_act ? 1 : 0;\n"
+       "    if (j == 0 && rin) act_s[ri] = r_act ? 1 : 0;\n"
        "    __syncthreads();\n";
-  for (int q = 0; q < Q; q++) o << "    double xp" << q << " = v" << q << " ? X[xo" << q << " + ri] : 0.0;\n";
+  for (int q = 0; q < Q; q++) o << "    double xp" << q << " = (v" << q << " && rin) ? X[xo" << q << " + ri] : 0.0;\n";
   o << "    for (int iter = 0; iter < 100; iter++) {\n      PH(0)\n"
        "      if (ei < " << GI << " && act_s[ei]) {\n        switch (warp) {\n";
   // ---- device evaluation: eval_order position w, w+NW, ... on warp w
@@ -415,7 +429,7 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
        "          r_dxok = (__ballot_sync(FULLM, baddx) & imask) == 0;\n"
        "          if (r_act) {\n            if (sing) { r_act = false; r_stat = 2; }\n            else r_nsol += 1;\n          }\n"
        "        }\n      }\n"
-       "      if (j == 0) act_s[ri] = r_act ? 1 : 0;\n      PH(8)\n"
+       "      if (j == 0 && rin) act_s[ri] = r_act ? 1 : 0;\n      PH(8)\n"
        "      const int any_ = __syncthreads_or(r_act);\n      PH(9)\n      if (!any_) break;\n"
        "    }\n"
        "    if (r_act) { r_stat = 1; r_act = false; }\n";

@@ -333,7 +333,7 @@ def test_ragged_batch_sizes(s21, oracle, B):
     assert np.all(st == 0) and rel_err(x, o["x"], floor=1e-9) <= 1e-9 and np.array_equal(it, o["iters"])
 
 
-@pytest.mark.parametrize("kernel", ["direct", "coop", "hybrid", "jit", "jitteam", "jitteam:8", "jitteam:10", "jitteam:16"])
+@pytest.mark.parametrize("kernel", ["direct", "coop", "hybrid", "jit", "jitteam", "jitteam:2", "jitteam:4", "jitteam:8", "jitteam:10", "jitteam:16"])
 def test_kernel_variants_bit_identical(s21, kernel, monkeypatch):
     """The Newton kernels (one thread per instance, CTA-cooperative, hybrid, and the two run-time specialised shapes)
     perform the same operations in the same order per value: identical bits, identical iteration counts — dcop and
