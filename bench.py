@@ -125,6 +125,27 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def aggregate(dist, world, device, times, iters, status, tran_ms):
+    """Every collective of the measurement in ONE place, executed by EVERY rank in the same order (a collective that only
+    some ranks reach hangs the job): MAX over ranks of the timed regions, the gather of per-instance iteration counts and
+    status flags (the path's only data exchange), and the transient metric's time — dropped on all ranks if
+    any rank could not measure it (tran_ms None). Returns (times, total_iters, all_ok, tran_ms). Runs on gloo/CPU in
+    tests/test_shard.py."""
+    import torch
+    from spice21_b200.shard import gather_instances
+    if dist is None or world == 1:
+        return list(times), int(np.sum(iters)), bool(np.all(np.asarray(status) == 0)), tran_ms
+    t = torch.tensor(list(times) + [tran_ms if tran_ms is not None else 0.0], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ok = torch.tensor([0.0 if tran_ms is None else 1.0], dtype=torch.float64, device=device)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    n = len(iters)
+    it_all = gather_instances(np.asarray(iters), n * world, device=device)
+    st_all = gather_instances(np.asarray(status), n * world, device=device)
+    vals = t.tolist()
+    return vals[:-1], int(it_all.sum()), bool(np.all(st_all == 0)), (vals[-1] if ok.item() > 0.5 else None)
+
+
 KERNEL_NAMES = {
     "hybrid": "s21::k_hyb<double, dcop> (hybrid cooperative Newton kernel, kernels/hybrid.cu)",
     "jit-team": "k_jit (run-time specialised team kernel: 8/16 lanes per instance, rows in registers; host/jit_team.hpp)",
@@ -149,7 +170,9 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # a collective that cannot complete fails after two minutes instead of hanging the job
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=120))
     B = B_PER_GPU
     ck = cc.diffpair()
     ovr = cc.diffpair_mc(B, first_instance=rank * B)  # each rank owns its own Monte-Carlo samples
@@ -219,17 +242,11 @@ def run_ours(args):
 
     tran = tran_metric(s21, cc, local, stream, rank)
 
-    tot_ms, tot_kern_ms, tot_iters, tot_e2e = step_ms, kern_ms, iters_per_step, e2e_s
-    if dist:
-        t = torch.tensor([step_ms, kern_ms, e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        tot_ms, tot_kern_ms, tot_e2e = t.tolist()
-        # the only collective of the path: gather per-instance iteration counts / status flags to every rank
-        from spice21_b200.shard import gather_instances
-        it_all = gather_instances(iters, B * world, device="cuda")
-        st_all = gather_instances(status, B * world, device="cuda")
-        assert np.all(st_all == 0)
-        tot_iters = int(it_all.sum())
+    (tot_ms, tot_kern_ms, tot_e2e), tot_iters, all_ok, tran_ms = aggregate(
+        dist, world, "cuda", (step_ms, kern_ms, e2e_s), iters, status, tran["ms"] if tran is not None else None)
+    assert all_ok, "non-converged instances on some rank"
+    if tran is not None:
+        tran = dict(tran, ms=tran_ms) if tran_ms is not None else None
     if rank == 0:
         peak, peak_src = measured_peak()
         per_inst_cols = (h2d // 8 - 0) // ((B + 31) // 32 * 32) if h2d else 0
@@ -259,10 +276,6 @@ def run_ours(args):
             "clocks": sampler.summary(),
         }
         if tran is not None:
-            if dist:
-                tt = torch.tensor([tran["ms"]], dtype=torch.float64, device="cuda")
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                tran["ms"] = float(tt.item())
             line["tran"] = {"metric": "tran_timepoints_per_sec", "value": world * tran["instances"] * tran["timepoints"] / (tran["ms"] * 1e-3),
                             "unit": "timepoints/s", "newton_iters_per_sec": world * tran["iters"] / (tran["ms"] * 1e-3),
                             "ms_per_transient": tran["ms"], "workload": tran["workload"], "kernel": tran["kernel"]}

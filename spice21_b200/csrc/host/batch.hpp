@@ -244,6 +244,7 @@ class Batch {
   void materialize_reset() {
     if (!reset_pending_) return;
     reset_pending_ = false;
+    rows_fresh_ = false;
     S21_CUDA(cudaSetDevice(device_));
     S21_CUDA(cudaMemsetAsync(x_.p, 0, x_.n * sizeof(double), stream_));
     S21_CUDA(cudaMemsetAsync(st_op_.p, 0, st_op_.n * sizeof(double), stream_));
@@ -292,12 +293,14 @@ class Batch {
     const int N = flat_.n_vars();
     const int32_t *hs, *hi, *hl;
     if (want_x) {
-      const size_t words = (size_t)N * B_ + (3 * B_ * sizeof(int32_t) + 7) / 8;
+      const size_t words = rows_words();
       d_rows_.alloc(words);
       hx_.alloc(words);
-      int rc = launch_pack_out(x_.p, status_.p, iters_.p, loads_.p, d_rows_.p, N, Bs_, (int)B_, stream_);
-      launches_++;
-      if (rc) throw S21Error(ST_CUDA, std::string("k_pack_out launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+      if (!rows_fresh_) {
+        int rc = launch_pack_out(x_.p, status_.p, iters_.p, loads_.p, d_rows_.p, N, Bs_, (int)B_, stream_);
+        launches_++;
+        if (rc) throw S21Error(ST_CUDA, std::string("k_pack_out launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+      }
       S21_CUDA(cudaMemcpyAsync(hx_.p, d_rows_.p, words * sizeof(double), cudaMemcpyDeviceToHost, stream_));
       S21_CUDA(cudaStreamSynchronize(stream_));
       hs = reinterpret_cast<const int32_t*>(hx_.p + (size_t)N * B_);
@@ -322,6 +325,7 @@ class Batch {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, ev0_, ev1_) == cudaSuccess) last_ms_ = ms;
   }
+  size_t rows_words() const { return (size_t)flat_.n_vars() * B_ + (3 * B_ * sizeof(int32_t) + 7) / 8; }
   void read(double* x, int32_t* status, int32_t* iters) {
     const double* hx = nullptr;
     const int32_t *hs = nullptr, *hi = nullptr;
@@ -343,6 +347,7 @@ class Batch {
     // The matrix changes character after the OP (capacitor companions appear, IC resistors are released):
     // take the pivot order again from the first transient iteration.
     tran_plan_.valid = false;
+    rows_fresh_ = false;  // the transient moves x on
     ensure_plan(tran_plan_, AN_TRAN, tstep);
     std::vector<int> sv(save_vars, save_vars + n_save);
     d_save_.upload(sv, stream_);
@@ -527,7 +532,7 @@ class Batch {
   std::vector<int> pcode_h_, poff_eff_;
   size_t pval_n_ = 0, h2d_bytes_ = 0;
   std::vector<Override> overrides_;
-  bool params_dirty_ = true, rebuild_ = true, codes_dirty_ = true;
+  bool params_dirty_ = true, rebuild_ = true, codes_dirty_ = true, rows_fresh_ = false;
   PlanDevice op_plan_, tran_plan_, ac_plan_;
   const PlanDevice* last_plan_ = nullptr;
   size_t lu_rows_ = 0;
@@ -617,7 +622,7 @@ class Batch {
     }
     return k.fn ? &k : nullptr;
   }
-  int launch_jit(const jit::Kernel& k, int mode, double dt, bool cold, int T, const int* save_vars, int n_save, double* wave) {
+  int launch_jit(const jit::Kernel& k, int mode, double dt, bool cold, int T, const int* save_vars, int n_save, double* wave, double* rows = nullptr) {
     const double* pval = d_pval_.p;
     double *gx = x_.p, *sop = st_op_.p, *sg = st_guess_.p;
     int *st = status_.p, *it = iters_.p, *ld = loads_.p;
@@ -625,7 +630,7 @@ class Batch {
     int B = (int)B_, n_state = flat_.n_state, md = mode, cold_i = cold ? 1 : 0, Tp = T, ns = n_save;
     double gmin = flat_.opts.gmin, dtv = dt, reltol = flat_.opts.reltol, iabstol = flat_.opts.iabstol;
     void* args[] = {&pval, &gx, &sop, &sg, &st, &it, &ld, &stride, &st_stride, &B, &n_state, &md, &gmin, &dtv, &reltol, &iabstol,
-                    &cold_i, &Tp, &ns, &save_vars, &wave};
+                    &cold_i, &Tp, &ns, &save_vars, &wave, &rows};  // `rows` is the team kernel's last parameter only
     const unsigned grid = (unsigned)((B_ + (size_t)k.inst_per_cta - 1) / (size_t)k.inst_per_cta);
     return jit::api().cuLaunchKernel(k.fn, grid, 1, 1, (unsigned)k.tpb, 1, 1, (unsigned)k.smem, (void*)stream_, args, nullptr);
   }
@@ -742,11 +747,18 @@ class Batch {
     DevTables dt = dev_tables(op_plan_.itab.p);
     int rc;
     CoopCfg hcfg;
+    rows_fresh_ = false;
     if (const jit::Kernel* jk = jit_kernel(op_plan_, false)) {
       const bool cold = reset_pending_;
       reset_pending_ = false;
       last_kernel_ = jk->team ? "jit-team" : "jit-thread";
-      rc = launch_jit(*jk, AN_OP, 0.0, cold, 2, nullptr, 0, nullptr);
+      double* rows = nullptr;
+      if (jk->team && jit::team_wp()) {  // (experimental build of the team kernel) it also leaves the host's result layout behind
+        d_rows_.alloc(rows_words());
+        rows = d_rows_.p;
+      }
+      rc = launch_jit(*jk, AN_OP, 0.0, cold, 2, nullptr, 0, nullptr, rows);
+      rows_fresh_ = rc == 0 && rows != nullptr;
     } else if (use_coop_ && use_hybrid(op_plan_, 1, &hcfg)) {
       hcfg.cold = reset_pending_;
       reset_pending_ = false;

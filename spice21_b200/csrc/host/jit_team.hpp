@@ -62,6 +62,13 @@ inline int team_gi(size_t B, int n_sm, int lpi) {
   (void)B; (void)n_sm;
   return gmax;
 }
+// S21_TEAM_WP=1 (EXPERIMENTAL, off by default: written after this round's GPU budget was spent, so it compiles for sm_100a
+// but has not run on a GPU yet — tests/test_gpu.py::test_team_kernel_warp_private is its acceptance test) generates the
+// warp-private loop: a warp evaluates the devices of its own instances (lane = (instance, device group)), so an iteration
+// needs no block barrier and same-type devices share one evaluation text; the CTA may then be a single warp (the
+// shared-memory stride follows S21_TEAM_GI), and the kernel leaves the host's result layout behind (no packing kernel).
+// With the flag off the generated source is exactly the one measured in profiles/r01u_*.
+inline bool team_wp() { const char* e = std::getenv("S21_TEAM_WP"); return e && std::atoi(e) != 0; }
 inline bool team_fast() { const char* e = std::getenv("S21_TEAM_FAST"); return !e || std::atoi(e) != 0; }
 
 struct TeamGather {
@@ -88,6 +95,8 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
                                const std::vector<int>& pcode, bool tran, int TM_LPI, size_t* smem_out, int n_sm = 148, int GI = TM_GI, int* tpb_out = nullptr) {
   (void)n_sm;
   std::ostringstream o;
+  const bool XP = team_wp();
+  const int PSV = XP ? GI + 4 : TM_P;  // padded instance stride of the shared-memory columns (36 for a full CTA, as kernels/hybrid.cu)
   const int N = P.N, NST = P.n_stage, NSTATE = std::max(flat.n_state, 1), Q = (N + TM_LPI - 1) / TM_LPI;
   const int IPW = 32 / TM_LPI;        // instances per warp in the linear-algebra phase
   const int NW_LA = GI / IPW;      // warps of the linear-algebra phase
@@ -128,7 +137,7 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
 
   // ---- gather table: step-major, 8 members per step
   TeamGather G;
-  const int zero_off = NST * TM_P;
+  const int zero_off = NST * PSV;
   std::ostringstream gath;  // generated gather code
   auto emit_gather = [&](const std::string& var, const std::vector<int>** lists) {
     size_t maxlen = 0;
@@ -136,7 +145,7 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
       if (lists[j]) maxlen = std::max(maxlen, lists[j]->size());
     gath << "        double " << var << " = 0.0;\n";
     for (size_t p = 0; p < maxlen; p++) {
-      for (int j = 0; j < TM_LPI; j++) G.table.push_back(lists[j] && p < lists[j]->size() ? (*lists[j])[p] * TM_P : zero_off);
+      for (int j = 0; j < TM_LPI; j++) G.table.push_back(lists[j] && p < lists[j]->size() ? (*lists[j])[p] * PSV : zero_off);
       gath << "        " << var << " = s_add(" << var << ", Sri[gtj[" << G.steps * TM_LPI << "]]);\n";
       G.steps++;
     }
@@ -173,16 +182,16 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
   else
     o << "#define PH(n)\n";
   o << "namespace s21 {\n";
-  o << "#define PS " << TM_P << "\n#define FULLM 0xffffffffu\n#define BC(v, jj) __shfl_sync(FULLM, (v), base + " << IPW << " * (jj))\n";
+  o << "#define PS " << PSV << "\n#define FULLM 0xffffffffu\n#define BC(v, jj) __shfl_sync(FULLM, (v), base + " << IPW << " * (jj))\n";
   o << "__device__ const int GT_G[" << std::max<size_t>(G.table.size(), 1) << "] = {";
   for (size_t k = 0; k < G.table.size(); k++) o << (k ? "," : "") << G.table[k];
   if (G.table.empty()) o << "0";
   o << "};\n";
   o << "__device__ const int XO_G[" << Q * TM_LPI + 8 << "] = {";
-  for (int k = 0; k < Q * TM_LPI + 8; k++) o << (k ? "," : "") << (k < N ? P.col_i2e[(size_t)k] * TM_P : 0);
+  for (int k = 0; k < Q * TM_LPI + 8; k++) o << (k ? "," : "") << (k < N ? P.col_i2e[(size_t)k] * PSV : 0);
   o << "};\n";
   o << "struct JBase {\n  const double* pval; size_t pinst; double* sop; double* sguess; const double* X; double* S;\n"
-       "  int mode; double dt, gmin, omega;\n"
+       "  int mode" << (XP ? ", j" : "") << "; double dt, gmin, omega;\n"
        "  __device__ __forceinline__ double volt(int var) const { return var < 0 ? 0.0 : X[var * PS]; }\n};\n";
   // the Env base of the branch-free evaluation (kernels/devices.cuh math hooks): fast paths only, exceptions deferred
   o << "struct JFast : JBase {\n  bool dbad;\n"
@@ -209,15 +218,69 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
     o << "  __device__ __forceinline__ void add_b_at(int pos, double v) { S[(" << sto << " + pos) * PS] = v; }\n";
     o << "  __device__ __forceinline__ void add_g_dup(int, int dup, double v) { S[(" << sto << " + dup) * PS] = v; }\n};\n";
   }
+  // ---- warp-private evaluation: slots of up to TM_LPI same-type devices, member j of a team evaluates slot[s][j]
+  const bool WP = XP && POW2 && NW == NW_LA;
+  std::vector<std::vector<int>> slots;
+  if (WP) {
+    std::vector<bool> used(flat.devs.size(), false);
+    for (size_t a = 0; a < si.eval_order.size(); a++) {
+      const int d0 = si.eval_order[a];
+      if (used[(size_t)d0]) continue;
+      std::vector<int> slot;
+      for (size_t b2 = a; b2 < si.eval_order.size() && (int)slot.size() < TM_LPI; b2++) {
+        const int d1 = si.eval_order[b2];
+        if (!used[(size_t)d1] && flat.devs[(size_t)d1].type == flat.devs[(size_t)d0].type && flat.devs[(size_t)d1].n_itab == flat.devs[(size_t)d0].n_itab &&
+            flat.devs[(size_t)d1].n_par == flat.devs[(size_t)d0].n_par) { slot.push_back(d1); used[(size_t)d1] = true; }
+      }
+      slots.push_back(slot);
+    }
+    auto selj = [&](const std::vector<long long>& v) {  // value of member j's device: a literal when all agree
+      bool same = true;
+      for (size_t k = 1; k < v.size(); k++) same = same && v[k] == v[0];
+      if (same) return std::to_string(v[0]);
+      std::string r;
+      for (size_t k = 0; k + 1 < v.size(); k++) r += "(j == " + std::to_string(k) + " ? " + std::to_string(v[k]) + " : ";
+      r += std::to_string(v.back());
+      for (size_t k = 0; k + 1 < v.size(); k++) r += ")";
+      return r;
+    };
+    for (size_t sidx = 0; sidx < slots.size(); sidx++) {
+      const std::vector<int>& sl = slots[sidx];
+      auto vals = [&](auto f) { std::vector<long long> v; for (int d : sl) v.push_back((long long)f(flat.devs[(size_t)d], d)); return v; };
+      const FlatDev& d0 = flat.devs[(size_t)sl[0]];
+      o << "template <class Base> struct P" << sidx << " : Base {\n  using Base::pval; using Base::pinst; using Base::sop; using Base::sguess; using Base::S; using Base::j;\n";
+      o << "  __device__ __forceinline__ int node(int k) const { switch (k) {";
+      for (int k = 0; k < d0.n_itab; k++)
+        o << " case " << k << ": return " << selj(vals([&](const FlatDev& d, int) { return itab[(size_t)d.itab_off + (size_t)k]; })) << ";";
+      o << " default: return -1; } }\n";
+      o << "  __device__ __forceinline__ double par(int k) const { switch (k) {";
+      for (int k = 0; k < d0.n_par; k++) {
+        const std::string off = selj(vals([&](const FlatDev& d, int) { return pcode[(size_t)d.par_off + (size_t)k] >> 1; }));
+        const std::vector<long long> fl = vals([&](const FlatDev& d, int) { return pcode[(size_t)d.par_off + (size_t)k] & 1; });
+        bool any = false, all = true;
+        for (long long f : fl) { any = any || f; all = all && f; }
+        o << " case " << k << ": return __ldg(pval + " << off << (all ? " + pinst" : any ? " + (" + selj(fl) + " ? pinst : (size_t)0)" : "") << ");";
+      }
+      o << " default: return 0.0; } }\n";
+      const std::string so = selj(vals([&](const FlatDev& d, int) { return d.state_off; }));
+      const std::string st = selj(vals([&](const FlatDev&, int d) { return si.stage_off[(size_t)d]; }));
+      o << "  __device__ __forceinline__ double op(int k) const { return sop[(" << so << " + k) * PS]; }\n";
+      o << "  __device__ __forceinline__ double guess(int k) const { return sguess[(" << so << " + k) * PS]; }\n";
+      o << "  __device__ __forceinline__ void set_guess(int k, double v) { sguess[(" << so << " + k) * PS] = v; }\n";
+      o << "  __device__ __forceinline__ void add_g_at(int pos, double v) { S[(" << st << " + pos) * PS] = v; }\n";
+      o << "  __device__ __forceinline__ void add_b_at(int pos, double v) { S[(" << st << " + pos) * PS] = v; }\n";
+      o << "  __device__ __forceinline__ void add_g_dup(int, int dup, double v) { S[(" << st << " + dup) * PS] = v; }\n};\n";
+    }
+  }
   for (int jj = 0; jj < TM_LPI; jj++) G.table.push_back(zero_off);  // idle lanes (j >= lanes per instance) read one row further
   const size_t n_gt = G.table.size();
   const size_t ctrl_ints = (size_t)GI + n_gt;
   const size_t ctrl_bytes = (ctrl_ints * 4 + 15) / 16 * 16;
-  *smem_out = ctrl_bytes + 8 * (size_t)TM_P * ((size_t)N + (size_t)NST + 1 + 2 * (size_t)NSTATE);
+  *smem_out = ctrl_bytes + 8 * (size_t)PSV * ((size_t)N + (size_t)NST + 1 + 2 * (size_t)NSTATE);
 
   o << "extern \"C\" __global__ void __launch_bounds__(" << NW * 32 << ", " << 2 << ") k_jit(const double* __restrict__ pval, double* gx, double* st_op, double* st_guess,\n"
        "    int* status, int* iters, int* loads, size_t stride, size_t st_stride, int B, int n_state_arg, int mode, double gmin, double dt,\n"
-       "    double reltol, double iabstol, int cold, int T_points, int n_save, const int* __restrict__ save_vars, double* wave) {\n"
+       "    double reltol, double iabstol, int cold, int T_points, int n_save, const int* __restrict__ save_vars, double* wave" << (XP ? ", double* rows" : "") << ") {\n"
        "  extern __shared__ __align__(16) unsigned char smem_raw[];\n"
        "  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;\n"
        "  const int i0 = blockIdx.x * " << GI << ";\n"
@@ -226,14 +289,14 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
        "  const unsigned imask = " << IMASK << "u << base, jbit = 1u << j;\n"
        "  int* act_s = (int*)smem_raw;\n  int* gt = act_s + " << GI << ";\n"
        "  double* X = (double*)(smem_raw + " << ctrl_bytes << ");\n"
-       "  double* S = X + " << N * TM_P << ";\n"
-       "  double* sop = S + " << (NST + 1) * TM_P << ";\n"
-       "  double* sguess = sop + " << NSTATE * TM_P << ";\n"
+       "  double* S = X + " << N * PSV << ";\n"
+       "  double* sop = S + " << (NST + 1) * PSV << ";\n"
+       "  double* sguess = sop + " << NSTATE * PSV << ";\n"
        "  for (int k = tid; k < " << n_gt << "; k += " << NW * 32 << ") gt[k] = GT_G[k];\n"
        "  if (tid < PS) S[" << zero_off << " + tid] = 0.0;\n"
        "  const bool evalid = ei < ni, rvalid = ri < ni" << (POW2 ? "" : " && j < " + std::to_string(TM_LPI)) << ", rin = ri < " << GI << ";\n"
-       "  for (int k = warp; k < " << N << "; k += " << NW << ") X[k * PS + ei] = (evalid && !cold) ? gx[(size_t)k * stride + i0 + ei] : 0.0;\n"
-       "  for (int k = warp; k < " << flat.n_state << "; k += " << NW << ") {\n"
+       "  " << (XP ? "if (ei < PS) " : "") << "for (int k = warp; k < " << N << "; k += " << NW << ") X[k * PS + ei] = (evalid && !cold) ? gx[(size_t)k * stride + i0 + ei] : 0.0;\n"
+       "  " << (XP ? "if (ei < PS) " : "") << "for (int k = warp; k < " << flat.n_state << "; k += " << NW << ") {\n"
        "    const size_t src = (size_t)k * st_stride + (size_t)i0 + (size_t)(evalid ? ei : 0);\n"
        "    sop[k * PS + ei] = cold ? 0.0 : st_op[src];\n    sguess[k * PS + ei] = cold ? 0.0 : st_guess[src];\n  }\n"
        "  int r_stat = " << (tran ? "rvalid ? status[i0 + ri] : 0" : "0") << ";\n"
@@ -246,43 +309,62 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
     o << "  const int xo" << q << " = XO_G[" << q * TM_LPI << " + j];\n";
     o << "  const bool v" << q << " = " << (valid_mask(q) == FULLSET && POW2 ? std::string("true") : "j < " + std::to_string(std::min(TM_LPI, N - q * TM_LPI))) << ";\n";
   }
-  o << "  JBase eb; eb.pval = pval; eb.pinst = (size_t)i0 + (size_t)ei; eb.sop = sop + ei; eb.sguess = sguess + ei; eb.X = X + ei; eb.S = S + ei;\n"
+  const char* ebi = WP ? "ri" : "ei";  // the instance a lane evaluates devices for
+  o << "  JBase eb; eb.pval = pval; eb.pinst = (size_t)i0 + (size_t)" << ebi << "; eb.sop = sop + " << ebi << "; eb.sguess = sguess + " << ebi
+    << "; eb.X = X + " << ebi << "; eb.S = S + " << ebi << ";" << (XP ? " eb.j = j;" : "") << "\n"
        "  eb.mode = " << (tran ? "AN_TRAN" : "AN_OP") << "; eb.dt = dt; eb.gmin = gmin; eb.omega = 0.0;\n";  // literal: the other mode's code is dropped
   if (prof) o << "  __shared__ long long prof_s[32];\n  if (tid < 32) prof_s[tid] = 0;\n  __syncthreads();\n  long long t_last = clock64();\n";
   o << "  const int n_points = " << (tran ? "T_points" : "2") << ";\n"
        "  for (int tp = 1; tp < n_points; tp++) {\n"
        "    bool r_act = rvalid && r_stat == 0;\n    bool r_dxok = true;\n"
-       "    if (j == 0 && rin) act_s[ri] = r_act ? 1 : 0;\n"
-       "    __syncthreads();\n";
+       << (WP ? "    __syncwarp();\n" : "    if (j == 0 && rin) act_s[ri] = r_act ? 1 : 0;\n    __syncthreads();\n");
   for (int q = 0; q < Q; q++) o << "    double xp" << q << " = (v" << q << " && rin) ? X[xo" << q << " + ri] : 0.0;\n";
-  o << "    for (int iter = 0; iter < 100; iter++) {\n      PH(0)\n"
-       "      if (ei < " << GI << " && act_s[ei]) {\n        switch (warp) {\n";
-  // ---- device evaluation: eval_order position w, w+NW, ... on warp w
-  for (int w = 0; w < NW && w < (int)si.eval_order.size(); w++) {
-    o << "          case " << w << ": {\n";
-    for (size_t item = (size_t)w; item < si.eval_order.size(); item += (size_t)NW) {
-      const int dev = si.eval_order[item];
-      const char* fn = nullptr;
-      switch (flat.devs[(size_t)dev].type) {
-        case DT_R: fn = "load_resistor"; break;
-        case DT_C: fn = "load_capacitor"; break;
-        case DT_I: fn = "load_isrc"; break;
-        case DT_V: fn = "load_vsrc"; break;
-        case DT_DIODE: fn = "load_diode"; break;
-        case DT_MOS0: fn = "load_mos0"; break;
-        case DT_MOS1: fn = "load_mos1"; break;
-        default: fn = nullptr;
-      }
-      // Mos1 reads no in-flight state, so a flagged evaluation can simply be repeated on the exact path
-      if (fn && fast_la && flat.devs[(size_t)dev].type == DT_MOS1)
-        o << "            { E" << dev << "<JFast> e; static_cast<JBase&>(e) = eb; e.dbad = false; " << fn << "(e);\n"
-             "              if (e.dbad) { E" << dev << "<JBase> x; static_cast<JBase&>(x) = eb; " << fn << "(x); } }\n";
-      else if (fn)
-        o << "            { E" << dev << "<JBase> e; static_cast<JBase&>(e) = eb; " << fn << "(e); }\n";
+  auto load_fn = [&](int dev) -> const char* {
+    switch (flat.devs[(size_t)dev].type) {
+      case DT_R: return "load_resistor";
+      case DT_C: return "load_capacitor";
+      case DT_I: return "load_isrc";
+      case DT_V: return "load_vsrc";
+      case DT_DIODE: return "load_diode";
+      case DT_MOS0: return "load_mos0";
+      case DT_MOS1: return "load_mos1";
+      default: return nullptr;
     }
-    o << "          } break;\n";
+  };
+  o << "    for (int iter = 0; iter < 100; iter++) {\n      PH(0)\n";
+  if (WP) {
+    // ---- device evaluation, warp-private: member j of instance `ri` evaluates device j of each slot
+    for (size_t sidx = 0; sidx < slots.size(); sidx++) {
+      const std::vector<int>& sl = slots[sidx];
+      const char* fn = load_fn(sl[0]);
+      if (!fn) continue;
+      const std::string cond = (int)sl.size() == TM_LPI ? "r_act" : "r_act && j < " + std::to_string(sl.size());
+      // Mos1 reads no in-flight state, so a flagged evaluation can simply be repeated on the exact path
+      if (fast_la && flat.devs[(size_t)sl[0]].type == DT_MOS1)
+        o << "      if (" << cond << ") { P" << sidx << "<JFast> e; static_cast<JBase&>(e) = eb; e.dbad = false; " << fn << "(e);\n"
+             "        if (e.dbad) { P" << sidx << "<JBase> x; static_cast<JBase&>(x) = eb; " << fn << "(x); } }\n";
+      else
+        o << "      if (" << cond << ") { P" << sidx << "<JBase> e; static_cast<JBase&>(e) = eb; " << fn << "(e); }\n";
+    }
+    o << "      PH(1)\n      __syncwarp();\n      PH(2)\n";
+  } else {
+    o << "      if (ei < " << GI << " && act_s[ei]) {\n        switch (warp) {\n";
+    // ---- device evaluation: eval_order position w, w+NW, ... on warp w
+    for (int w = 0; w < NW && w < (int)si.eval_order.size(); w++) {
+      o << "          case " << w << ": {\n";
+      for (size_t item = (size_t)w; item < si.eval_order.size(); item += (size_t)NW) {
+        const int dev = si.eval_order[item];
+        const char* fn = load_fn(dev);
+        if (fn && fast_la && flat.devs[(size_t)dev].type == DT_MOS1)
+          o << "            { E" << dev << "<JFast> e; static_cast<JBase&>(e) = eb; e.dbad = false; " << fn << "(e);\n"
+               "              if (e.dbad) { E" << dev << "<JBase> x; static_cast<JBase&>(x) = eb; " << fn << "(x); } }\n";
+        else if (fn)
+          o << "            { E" << dev << "<JBase> e; static_cast<JBase&>(e) = eb; " << fn << "(e); }\n";
+      }
+      o << "          } break;\n";
+    }
+    o << "        }\n      }\n      PH(1)\n      __syncthreads();\n      PH(2)\n";
   }
-  o << "        }\n      }\n      PH(1)\n      __syncthreads();\n      PH(2)\n";
   // ---- linear algebra, warp-synchronous
   // residual in pivoted row order; x by pivoted column comes from the member that owns it
   auto emit_residual = [&](std::ostream& o) {
@@ -429,8 +511,9 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
        "          r_dxok = (__ballot_sync(FULLM, baddx) & imask) == 0;\n"
        "          if (r_act) {\n            if (sing) { r_act = false; r_stat = 2; }\n            else r_nsol += 1;\n          }\n"
        "        }\n      }\n"
-       "      if (j == 0 && rin) act_s[ri] = r_act ? 1 : 0;\n      PH(8)\n"
-       "      const int any_ = __syncthreads_or(r_act);\n      PH(9)\n      if (!any_) break;\n"
+       << (WP ? "      PH(8)\n      __syncwarp();\n      const bool any_ = __any_sync(FULLM, r_act);\n      PH(9)\n      if (!any_) break;\n"
+              : "      if (j == 0 && rin) act_s[ri] = r_act ? 1 : 0;\n      PH(8)\n"
+                "      const int any_ = __syncthreads_or(r_act);\n      PH(9)\n      if (!any_) break;\n") <<
        "    }\n"
        "    if (r_act) { r_stat = 1; r_act = false; }\n";
   if (tran)
@@ -447,6 +530,11 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
        "    status[i0 + ri] = r_stat;\n"
        "    iters[i0 + ri] = (cold ? 0 : iters[i0 + ri]) + r_nsol;\n"
        "    loads[i0 + ri] = (cold ? 0 : loads[i0 + ri]) + r_nld;\n  }\n";
+  if (XP)  // the host's result layout (k_pack_out in kernels/newton.cu), written here so that a read needs no second kernel
+    o << "  if (rows) {\n    __syncthreads();\n"
+         "    if (rvalid && j == 0) { int* tail = (int*)(rows + (size_t)B * " << N << "); tail[i0 + ri] = r_stat; tail[(size_t)B + i0 + ri] = iters[i0 + ri];"
+         " tail[2 * (size_t)B + i0 + ri] = loads[i0 + ri]; }\n"
+         "    if (evalid) for (int k = warp; k < " << N << "; k += " << NW << ") rows[(size_t)(i0 + ei) * " << N << " + k] = X[k * PS + ei];\n  }\n";
   if (prof)
     o << "  __syncthreads();\n  if (tid == 0 && blockIdx.x == 0) {\n"
          "    const char* nm[10] = {\"loop/other\", \"eval\", \"barrier-after-eval\", \"gather\", \"residual+conv\", \"LU\", \"forward\", \"backward\", \"limit+update\", \"end-barrier\"};\n"

@@ -5,6 +5,8 @@ Tolerances (BASELINE.json north_star): dcop node voltages / branch currents with
 SPICE reltol = 1e-3 / vntol = 1e-6 — in practice both agree to ~1e-12, and the tests assert the tighter figure so a
 regression in operation order is caught. Integer structures (stamp map, pivot order, fill) are exact.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -416,32 +418,65 @@ def test_dcop_view_matches_dcop(s21):
     assert np.array_equal(st, st2) and np.array_equal(it, it2)
 
 
-def test_team_kernel_fast_and_exact_text_agree(s21, monkeypatch):
-    """The team kernel's linear algebra is generated twice (host/jit_team.hpp): a branch-free text whose divisions defer
-    their exceptions, and the exact text it falls back to. Both, and the fallback itself — forced here by a 1e-300 S
-    resistor, whose L entries lie below the fast quotient's domain — give the direct kernel's bits."""
+def _team_cases(s21, monkeypatch, variants):
+    """Direct kernel vs the team kernel generated under each (S21_TEAM_FAST, S21_TEAM_WP, S21_TEAM_GI) variant: C2 dcop at a
+    ragged batch size, a circuit whose L entries leave the fast quotient's domain (forces the exact redo), and — when asked —
+    the C1 ring as a transient supply sweep."""
     tiny = Ckt(signals=["a", "b", "c"]).V("v", "a", GND, 1.0).R("r1", "a", "b", 1e-3).R("rt", "b", "c", 1e-300).R("r2", "c", GND, 1e-3)
     tiny.R("r3", "b", GND, 2e-3)
     B = 83
     dp, ovr = cc.diffpair(), cc.diffpair_mc(B)
+    ro = cc.cmos_ro3(cc.add_mos1_defaults)
 
-    def run(kernel, fast):
+    def run(kernel, fast="1", wp=None, gi=None, with_tran=False):
         monkeypatch.setenv("S21_KERNEL", kernel)
         monkeypatch.setenv("S21_TEAM_FAST", fast)
+        for key, val in (("S21_TEAM_WP", wp), ("S21_TEAM_GI", gi)):
+            if val is None:
+                monkeypatch.delenv(key, raising=False)
+            else:
+                monkeypatch.setenv(key, val)
         b = s21.Batch(dp.to_s21().elaborate(), B)
         for key, v in ovr.items():
             b.override(key, v)
         bt = s21.Batch(tiny.to_s21().elaborate(), 5)
-        out = b.dcop() + bt.dcop()
-        return out, (b.kernel_name(), bt.kernel_name())
+        out, names = b.dcop() + bt.dcop(), [b.kernel_name(), bt.kernel_name()]
+        if with_tran:
+            br = s21.Batch(ro.to_s21().elaborate(ic={"1": 0.0}), 37)
+            br.override("V:v1:dc", np.linspace(0.9, 1.1, 37))
+            t, w, st2, it2 = br.tran(1e-11, 4e-10)
+            out, names = out + (w, st2, it2), names + [br.kernel_name()]
+        if wp == "1":  # the kernel-written result rows, through the zero-copy read the bench's end-to-end loop uses
+            b.reset()
+            xv, stv, itv = b.dcop_view()
+            assert np.array_equal(xv, out[0]) and np.array_equal(stv, out[1]) and np.array_equal(itv, out[2])
+        return out, names
 
-    ref, _ = run("direct", "1")
+    with_tran = any(v[3] for v in variants)
+    ref, _ = run("direct", with_tran=with_tran)
     assert np.all(ref[1] == 0) and np.all(ref[4] == 0)
-    for fast in ("1", "0"):
-        got, names = run("jitteam", fast)
-        assert names == ("jit-team", "jit-team")
+    for fast, wp, gi, tr in variants:
+        got, names = run("jitteam", fast, wp, gi, tr)
+        assert all(n == "jit-team" for n in names)
         for a, b_ in zip(ref, got):
-            assert np.array_equal(a, b_), fast
+            assert np.array_equal(a, b_), (fast, wp, gi)
+
+
+def test_team_kernel_fast_and_exact_text_agree(s21, monkeypatch):
+    """The team kernel's linear algebra is generated twice (host/jit_team.hpp): a branch-free text whose divisions defer
+    their exceptions, and the exact text it falls back to. Both, and the fallback itself — forced here by a 1e-300 S
+    resistor, whose L entries lie below the fast quotient's domain — give the direct kernel's bits."""
+    _team_cases(s21, monkeypatch, [("1", None, None, False), ("0", None, None, False)])
+
+
+@pytest.mark.skipif(os.environ.get("S21_TEST_EXPERIMENTAL") != "1", reason="S21_TEAM_WP=1 has not run on a GPU yet (written after "
+                    "the round's GPU budget was spent); run with S21_TEST_EXPERIMENTAL=1 to accept it")
+def test_team_kernel_warp_private(s21, monkeypatch):
+    """Acceptance test of the experimental warp-private team kernel (S21_TEAM_WP=1: no block barriers, shared evaluation
+    text for same-type devices, CTAs down to one warp, result rows written by the kernel): same bits as the direct kernel
+    for dcop, the forced exact redo and a transient, with both texts and several CTA sizes."""
+    _team_cases(s21, monkeypatch, [("1", "1", None, True), ("0", "1", None, True), ("1", "1", "16", True), ("1", "1", "8", True),
+                                   ("1", "0", "16", True)])
 
 
 # ------------------------------------------------------------------------------------------------ Bsim4

@@ -43,6 +43,43 @@ def test_shard_and_gather_gloo(world, n):
     assert len({s for _, _, s in res}) == 1  # every rank sees the same gathered totals
 
 
+def _agg_worker(rank, world, port, tran_fails_on, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import bench
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 64
+    iters = np.full(n, 10 + rank, dtype=np.int32)
+    status = np.zeros(n, dtype=np.int32)
+    tran_ms = None if rank == tran_fails_on else 5.0 + rank
+    times, tot, ok, tms = bench.aggregate(dist, world, None, (1.0 + rank, 0.5 + rank, 2.0 - rank), iters, status, tran_ms)
+    q.put((rank, times, tot, ok, tms))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,tran_fails_on", [(2, -1), (2, 1), (3, 0)])
+def test_bench_collectives_are_symmetric_gloo(world, tran_fails_on):
+    """bench.aggregate holds every collective of the multi-GPU measurement; every rank must come out of it with the same
+    totals — also when one rank could not measure the secondary (transient) metric, which then is dropped everywhere
+    instead of leaving the other ranks waiting in a collective (that hang cost a whole 8-GPU run)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() + world * 13 + tran_fails_on) % 2000
+    procs = [ctx.Process(target=_agg_worker, args=(r, world, port, tran_fails_on, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    want_times = [1.0 + world - 1, 0.5 + world - 1, 2.0]
+    want_tot = 64 * sum(10 + r for r in range(world))
+    for rank, times, tot, ok, tms in res:
+        assert times == want_times and tot == want_tot and ok
+        assert tms == (None if tran_fails_on >= 0 else 5.0 + world - 1)
+
+
 def test_shard_bounds_cover_everything():
     sys.path.insert(0, ROOT)
     from spice21_b200.shard import shard_bounds
