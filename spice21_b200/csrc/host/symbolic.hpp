@@ -11,6 +11,9 @@
 // kernels (refactorisation, forward/back substitution, residual SpMV), all in final internal coordinates.
 #pragma once
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <unordered_map>
 #include <vector>
@@ -150,6 +153,15 @@ Plan build_plan(int N, const std::vector<int>& elem_row, const std::vector<int>&
   P.row_i2e.resize((size_t)N); P.row_e2i.resize((size_t)N); P.col_i2e.resize((size_t)N); P.col_e2i.resize((size_t)N);
   for (int k = 0; k < N; k++) P.row_i2e[(size_t)k] = P.row_e2i[(size_t)k] = P.col_i2e[(size_t)k] = P.col_e2i[(size_t)k] = k;
   auto lookup = [&](int r, int c) { auto it = at.find(rc_key(r, c)); return it == at.end() ? -1 : it->second; };
+  // diag[k] = id of the entry at internal (k, k), or -1 (the reference keeps the same array, mod.rs:225). Maintained under
+  // the two swaps of a step and under fill-in creation, so the diagonal search reads an array instead of hashing N
+  // coordinates per pivot (the search was 2/3 of the symbolic phase of config C3).
+  // dabs[k] = |value| of that entry, kept current by the elimination step: the search then touches only small arrays
+  // (the entry table is tens of MB for C3 and was read at random for every candidate).
+  std::vector<int> diag((size_t)N, -1);
+  std::vector<double> dabs((size_t)N, 0.0);
+  auto set_diag = [&](int k, int id) { diag[(size_t)k] = id; dabs[(size_t)k] = id < 0 ? 0.0 : s_abs(E[(size_t)id].val); };
+  for (int k = 0; k < N; k++) set_diag(k, lookup(k, k));
 
   // mod.rs:649-658 — an empty row or column is "Singular Matrix"
   for (int k = 0; k < N; k++)
@@ -166,51 +178,111 @@ Plan build_plan(int N, const std::vector<int>& elem_row, const std::vector<int>&
     e2i[(size_t)i2e[(size_t)y]] = y;
   };
   // max |val| among the entries of external column c whose current internal row is >= n; ties -> smallest internal row
-  // Cached per column: the answer only changes when the column is touched by an elimination step (its entries are
-  // updated, filled in, or lose the pivot row) — the step below invalidates exactly those columns. Without the cache the
-  // diagonal search re-scans whole columns for every candidate of every pivot (20 s of host time for config C3).
+  // (max_after_loc walks the column in ascending internal row and replaces its best only on a strictly larger value).
+  // Cached per column, and inside a column per block of BS list positions: an elimination step marks exactly the blocks
+  // whose answer can have changed — entries it updated or created, the entries of the pivot row (they leave the active
+  // part) and of the row that the row swap moved (its internal index, hence its rank in a tie, changed). A long column
+  // that every step touches in a few places (the shared supply node of config C3: ~N entries, N steps) then costs a few
+  // blocks plus one pass over the block winners per step instead of a full walk — that walk was most of the symbolic
+  // phase of C3 after the diagonal search itself had been reduced to array reads.
+  constexpr int BS = 16;
+  size_t n_recomp = 0, n_visit = 0;  // statistics for S21_PLAN_INFO
+  std::vector<int> epos(E.size());  // position of an entry in its column's list
+  {
+    std::vector<int> fillc((size_t)N, 0);
+    for (size_t e = 0; e < E.size(); e++) epos[e] = fillc[(size_t)E[e].c]++;
+  }
+  std::vector<std::vector<int>> blk_best((size_t)N), blk_ir((size_t)N);  // winner of a block, its internal row and |value|
+  std::vector<std::vector<double>> blk_val((size_t)N);
+  std::vector<std::vector<char>> blk_dirty((size_t)N);
+  for (int c = 0; c < N; c++) {
+    const size_t nb = (in_col[(size_t)c].size() + BS - 1) / BS;
+    blk_best[(size_t)c].assign(nb, -1);
+    blk_ir[(size_t)c].assign(nb, 0);
+    blk_val[(size_t)c].assign(nb, 0.0);
+    blk_dirty[(size_t)c].assign(nb, 1);
+  }
   std::vector<int> cmax_id((size_t)N, -2);  // -2 = not cached, -1 = no active entry
+  std::vector<double> cmax_abs((size_t)N, 0.0);
+  auto touch = [&](int id) {
+    const int c = E[(size_t)id].c;
+    blk_dirty[(size_t)c][(size_t)(epos[(size_t)id] / BS)] = 1;
+    cmax_id[(size_t)c] = -2;
+  };
   auto col_max_from = [&](int c, int n) {
     if (cmax_id[(size_t)c] != -2) return cmax_id[(size_t)c];
+    n_recomp++;
+    const std::vector<int>& lst = in_col[(size_t)c];
     int best = -1, best_ir = 0;
     double best_val = 0.0;
-    for (int id : in_col[(size_t)c]) {
-      int ir = P.row_e2i[(size_t)E[(size_t)id].r];
-      if (ir < n) continue;
-      double a = s_abs(E[(size_t)id].val);
-      // max_after_loc walks the column in ascending internal row and replaces `best` only on a strictly larger
-      // value: the winner is the largest |val|, ties going to the smallest internal row (finite values).
-      if (best < 0 || a > best_val || (a == best_val && ir < best_ir)) { best = id; best_val = a; best_ir = ir; }
+    for (size_t blk = 0; blk < blk_best[(size_t)c].size(); blk++) {
+      int bb = -1, bb_ir = 0;
+      double bb_val = 0.0;
+      if (blk_dirty[(size_t)c][blk]) {
+        const size_t hi = std::min(lst.size(), (blk + 1) * (size_t)BS);
+        for (size_t p = blk * (size_t)BS; p < hi; p++) {
+          n_visit++;
+          const int id = lst[p];
+          const int ir = P.row_e2i[(size_t)E[(size_t)id].r];
+          if (ir < n) continue;
+          const double a = s_abs(E[(size_t)id].val);
+          if (bb < 0 || a > bb_val || (a == bb_val && ir < bb_ir)) { bb = id; bb_val = a; bb_ir = ir; }
+        }
+        blk_best[(size_t)c][blk] = bb;
+        blk_ir[(size_t)c][blk] = bb_ir;
+        blk_val[(size_t)c][blk] = bb_val;
+        blk_dirty[(size_t)c][blk] = 0;
+      } else {
+        bb = blk_best[(size_t)c][blk];
+        bb_ir = blk_ir[(size_t)c][blk];
+        bb_val = blk_val[(size_t)c][blk];
+      }
+      if (bb >= 0 && (best < 0 || bb_val > best_val || (bb_val == best_val && bb_ir < best_ir))) { best = bb; best_val = bb_val; best_ir = bb_ir; }
     }
     cmax_id[(size_t)c] = best;
+    cmax_abs[(size_t)c] = best_val;
     return best;
   };
 
+  const bool info = std::getenv("S21_PLAN_INFO") != nullptr;
+  using clk = std::chrono::steady_clock;
+  double t_search = 0.0, t_elim = 0.0;
+  size_t n_upd = 0, n_cand = 0;
+  const auto t_begin = clk::now();
   for (int n = 0; n + 1 < N && P.status == ST_OK; n++) {
     int pivot = -1;
+    const auto t_s0 = clk::now();
     {  // ---- markowitz_search_diagonal
       long best_mark = -1;  // -1 stands for usize::MAX
       double best_ratio = 0.0;
       long num_ties = 0;
       bool done = false;
       for (int k = n; k < N && !done; k++) {
-        int d = lookup(P.row_i2e[(size_t)k], P.col_i2e[(size_t)k]);
+        n_cand++;
+        int d = diag[(size_t)k];
         if (d < 0) continue;
-        int mx = col_max_from(E[(size_t)d].c, n);
+        const int ec = P.col_i2e[(size_t)k];
+        int mx = col_max_from(ec, n);
         if (mx < 0) continue;
-        double threshold = 1e-3 * s_abs(E[(size_t)mx].val) + 0.0;
-        if (s_abs(E[(size_t)d].val) < threshold) continue;
-        long mr = mrow[(size_t)E[(size_t)d].r], mc = mcol[(size_t)E[(size_t)d].c];
+        const double mabs = cmax_abs[(size_t)ec], da = dabs[(size_t)k];
+        double threshold = 1e-3 * mabs + 0.0;
+        if (da < threshold) continue;
+        long mr = mrow[(size_t)P.row_i2e[(size_t)k]], mc = mcol[(size_t)ec];
         if (!(mr > 0 && mc > 0)) throw S21Error(ST_OTHER, "markowitz count underflow");
         long mark = (mr - 1) * (mc - 1);
+        // |d / m|: for real values the quotient of the magnitudes, bit for bit; complex values take the num-style quotient
+        auto ratio_of = [&]() {
+          if (Scalar<T>::width == 1) return s_div(da, mabs);
+          return s_abs(s_div(E[(size_t)d].val, E[(size_t)mx].val));
+        };
         if (best_mark < 0 || mark < best_mark) {
           num_ties = 0;
           pivot = d;
           best_mark = mark;
-          best_ratio = s_abs(s_div(E[(size_t)d].val, E[(size_t)mx].val));
+          best_ratio = ratio_of();
         } else if (mark == best_mark) {
           num_ties += 1;
-          double ratio = s_abs(s_div(E[(size_t)d].val, E[(size_t)mx].val));
+          double ratio = ratio_of();
           if (ratio > best_ratio) { pivot = d; best_ratio = ratio; }
           if (num_ties >= best_mark * 5) done = true;
         }
@@ -253,10 +325,22 @@ Plan build_plan(int N, const std::vector<int>& elem_row, const std::vector<int>&
       }
     }
     if (pivot < 0) { P.status = ST_PIVOT; break; }
+    const auto t_s1 = clk::now();
+    t_search += std::chrono::duration<double>(t_s1 - t_s0).count();
 
     // ---- swap the pivot to (n, n)
-    swap_int(P.row_i2e, P.row_e2i, P.row_e2i[(size_t)E[(size_t)pivot].r], n);
-    swap_int(P.col_i2e, P.col_e2i, P.col_e2i[(size_t)E[(size_t)pivot].c], n);
+    {
+      const int xr = P.row_e2i[(size_t)E[(size_t)pivot].r], xc = P.col_e2i[(size_t)E[(size_t)pivot].c];
+      for (int id : in_row[(size_t)P.row_i2e[(size_t)xr]]) touch(id);  // the pivot row leaves the active part
+      if (xr != n)  // the row at n moves to xr: it held the smallest active index, so it won every tie it was part of —
+        for (int id : in_row[(size_t)P.row_i2e[(size_t)n]]) {  // only where it is the recorded winner can the answer change
+          const int c = E[(size_t)id].c;
+          if (blk_best[(size_t)c][(size_t)(epos[(size_t)id] / BS)] == id || cmax_id[(size_t)c] == id) touch(id);
+        }
+      swap_int(P.row_i2e, P.row_e2i, xr, n);
+      swap_int(P.col_i2e, P.col_e2i, xc, n);
+      for (int k : {xr, xc, n}) set_diag(k, lookup(P.row_i2e[(size_t)k], P.col_i2e[(size_t)k]));
+    }
 
     // ---- row_col_elim
     const int pr = E[(size_t)pivot].r, pc = E[(size_t)pivot].c;
@@ -273,10 +357,8 @@ Plan build_plan(int N, const std::vector<int>& elem_row, const std::vector<int>&
       for (auto& x : us) st.U.push_back(x.second);
     }
     for (int l : st.L) E[(size_t)l].val = s_div(E[(size_t)l].val, pivot_val);
-    cmax_id[(size_t)pc] = -2;
     for (int u : st.U) {
       const int uc = E[(size_t)u].c;
-      cmax_id[(size_t)uc] = -2;
       for (int l : st.L) {
         const int lr = E[(size_t)l].r;
         int t = lookup(lr, uc);
@@ -284,19 +366,29 @@ Plan build_plan(int N, const std::vector<int>& elem_row, const std::vector<int>&
           t = (int)E.size();
           E.push_back({lr, uc, Scalar<T>::zero(), true});
           in_row[(size_t)lr].push_back(t);
+          epos.push_back((int)in_col[(size_t)uc].size());
           in_col[(size_t)uc].push_back(t);
+          if (blk_best[(size_t)uc].size() * (size_t)BS < in_col[(size_t)uc].size()) {
+            blk_best[(size_t)uc].push_back(-1); blk_ir[(size_t)uc].push_back(0); blk_val[(size_t)uc].push_back(0.0); blk_dirty[(size_t)uc].push_back(1);
+          }
           at.emplace(rc_key(lr, uc), t);
+          if (P.row_e2i[(size_t)lr] == P.col_e2i[(size_t)uc]) diag[(size_t)P.row_e2i[(size_t)lr]] = t;
           mrow[(size_t)lr] += 1;
           mcol[(size_t)uc] += 1;
         }
         E[(size_t)t].val = s_sub(E[(size_t)t].val, s_mul(E[(size_t)u].val, E[(size_t)l].val));
+        touch(t);
+        if (P.row_e2i[(size_t)lr] == P.col_e2i[(size_t)uc]) dabs[(size_t)P.row_e2i[(size_t)lr]] = s_abs(E[(size_t)t].val);
       }
       mcol[(size_t)uc] -= 1;
     }
     mrow[(size_t)pr] -= 1;
     mcol[(size_t)pc] -= 1;
     for (int l : st.L) mrow[(size_t)E[(size_t)l].r] -= 1;
+    n_upd += st.L.size() * st.U.size();
+    t_elim += std::chrono::duration<double>(clk::now() - t_s1).count();
   }
+  const auto t_fact = clk::now();
 
   // ---- freeze: slots in final internal coordinates
   P.nnzLU = (int)E.size();
@@ -347,7 +439,14 @@ Plan build_plan(int N, const std::vector<int>& elem_row, const std::vector<int>&
     P.l_off[(size_t)n + 1] = (int)P.l_slot.size();
     P.upd_off[(size_t)n + 1] = (int)P.upd_t.size();
   }
+  const auto t_frozen = clk::now();
   if (P.status == ST_OK) build_levels(P);
+  if (info)
+    std::fprintf(stderr, "[s21 symbolic] N=%d nnzLU=%d candidates=%zu updates=%zu | search %.2f s, elimination %.2f s, freeze+op lists %.2f s, levels %.2f s\n", N,
+                 P.nnzLU, n_cand, n_upd, t_search, t_elim, std::chrono::duration<double>(t_frozen - t_fact).count(),
+                 std::chrono::duration<double>(clk::now() - t_frozen).count());
+  if (info) std::fprintf(stderr, "[s21 symbolic] column maxima recomputed %zu times, %zu entries visited\n", n_recomp, n_visit);
+  (void)t_begin;
   return P;
 }
 

@@ -137,6 +137,29 @@ def test_pivot_order_random_matrices(s21, oracle):
         assert _same_plan(oracle.lu_order(n, r, c, v), s21.symbolic(n, r, c, v)), trial
 
 
+def test_pivot_order_tie_heavy_matrices(s21, oracle):
+    """Larger matrices whose values come from a handful of magnitudes: many exact ties in the column maxima and in the
+    Markowitz products, columns several cache blocks long (host/symbolic.hpp keeps column maxima per block of 16 list
+    positions), dense rows/columns that every elimination step touches, like the supply node of config C3."""
+    rng = np.random.default_rng(2026)
+    for trial in range(60):
+        n = int(rng.integers(40, 140))
+        mask = rng.random((n, n)) < rng.uniform(0.02, 0.12)
+        mask |= np.eye(n, dtype=bool)
+        for _ in range(int(rng.integers(0, 3))):  # a few (nearly) full rows / columns
+            k = int(rng.integers(0, n))
+            mask[k, :] |= rng.random(n) < 0.9
+            mask[:, k] |= rng.random(n) < 0.9
+        r, c = np.nonzero(mask)
+        perm = rng.permutation(len(r))
+        r, c = r[perm], c[perm]
+        v = rng.choice([1.0, -1.0, 2.0, -2.0, 0.5, 1e-4], size=len(r))
+        v[r == c] *= rng.choice([1.0, 4.0, 1e-3], size=int(np.sum(r == c)))
+        if trial % 5 == 4:
+            v = v + 1j * rng.choice([0.0, 1.0, -1.0], size=len(r))
+        assert _same_plan(oracle.lu_order(n, r, c, v), s21.symbolic(n, r, c, v)), trial
+
+
 def test_proto_decode_errors(s21):
     with pytest.raises(s21.Spice21Error) as e:
         s21.Circuit(b"\x0a\xff\xff\xff\xff\x0f")  # truncated length-delimited field
