@@ -15,7 +15,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
-#include <unordered_map>
 #include <vector>
 
 #include "../scalar.h"
@@ -129,6 +128,56 @@ struct SymEntry {
   bool fill;
 };
 inline uint64_t rc_key(int r, int c) { return ((uint64_t)(uint32_t)r << 32) | (uint32_t)c; }
+// (row, col) -> entry id: open addressing with linear probing (the elimination step looks up one coordinate per Schur
+// update and inserts one per fill-in; std::unordered_map spent most of that step in allocation and pointer chasing).
+class CoordMap {
+ public:
+  explicit CoordMap(size_t expect) {
+    size_t cap = 64;
+    while (cap < expect * 2) cap <<= 1;
+    keys_.assign(cap, kEmpty);
+    vals_.assign(cap, -1);
+  }
+  int find(uint64_t key) const {
+    const size_t mask = keys_.size() - 1;
+    for (size_t h = hash(key) & mask;; h = (h + 1) & mask) {
+      if (keys_[h] == key) return vals_[h];
+      if (keys_[h] == kEmpty) return -1;
+    }
+  }
+  void insert(uint64_t key, int val) {  // key must not be present
+    if ((n_ + 1) * 2 > keys_.size()) grow();
+    put(key, val);
+    n_++;
+  }
+
+ private:
+  static constexpr uint64_t kEmpty = ~0ull;  // (row, col) = (-1, -1) never occurs
+  static size_t hash(uint64_t k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33;
+    return (size_t)k;
+  }
+  void put(uint64_t key, int val) {
+    const size_t mask = keys_.size() - 1;
+    size_t h = hash(key) & mask;
+    while (keys_[h] != kEmpty) h = (h + 1) & mask;
+    keys_[h] = key;
+    vals_[h] = val;
+  }
+  void grow() {
+    std::vector<uint64_t> ok;
+    std::vector<int> ov;
+    ok.swap(keys_);
+    ov.swap(vals_);
+    keys_.assign(ok.size() * 2, kEmpty);
+    vals_.assign(ok.size() * 2, -1);
+    for (size_t i = 0; i < ok.size(); i++)
+      if (ok[i] != kEmpty) put(ok[i], ov[i]);
+  }
+  std::vector<uint64_t> keys_;
+  std::vector<int> vals_;
+  size_t n_ = 0;
+};
 }  // namespace detail
 
 // vals[e] = assembled value of element e after the first device-load sweep.
@@ -142,17 +191,16 @@ Plan build_plan(int N, const std::vector<int>& elem_row, const std::vector<int>&
   std::vector<SymEntry<T>> E;
   E.reserve(elem_row.size() * 2);
   std::vector<std::vector<int>> in_row((size_t)N), in_col((size_t)N);
-  std::unordered_map<uint64_t, int> at;
-  at.reserve(elem_row.size() * 2);
+  detail::CoordMap at(elem_row.size() * 2);
   for (size_t e = 0; e < elem_row.size(); e++) {
     E.push_back({elem_row[e], elem_col[e], vals[e], false});
     in_row[(size_t)elem_row[e]].push_back((int)e);
     in_col[(size_t)elem_col[e]].push_back((int)e);
-    at.emplace(rc_key(elem_row[e], elem_col[e]), (int)e);
+    if (at.find(rc_key(elem_row[e], elem_col[e])) < 0) at.insert(rc_key(elem_row[e], elem_col[e]), (int)e);
   }
   P.row_i2e.resize((size_t)N); P.row_e2i.resize((size_t)N); P.col_i2e.resize((size_t)N); P.col_e2i.resize((size_t)N);
   for (int k = 0; k < N; k++) P.row_i2e[(size_t)k] = P.row_e2i[(size_t)k] = P.col_i2e[(size_t)k] = P.col_e2i[(size_t)k] = k;
-  auto lookup = [&](int r, int c) { auto it = at.find(rc_key(r, c)); return it == at.end() ? -1 : it->second; };
+  auto lookup = [&](int r, int c) { return at.find(rc_key(r, c)); };
   // diag[k] = id of the entry at internal (k, k), or -1 (the reference keeps the same array, mod.rs:225). Maintained under
   // the two swaps of a step and under fill-in creation, so the diagonal search reads an array instead of hashing N
   // coordinates per pivot (the search was 2/3 of the symbolic phase of config C3).
@@ -371,7 +419,7 @@ Plan build_plan(int N, const std::vector<int>& elem_row, const std::vector<int>&
           if (blk_best[(size_t)uc].size() * (size_t)BS < in_col[(size_t)uc].size()) {
             blk_best[(size_t)uc].push_back(-1); blk_ir[(size_t)uc].push_back(0); blk_val[(size_t)uc].push_back(0.0); blk_dirty[(size_t)uc].push_back(1);
           }
-          at.emplace(rc_key(lr, uc), t);
+          at.insert(rc_key(lr, uc), t);
           if (P.row_e2i[(size_t)lr] == P.col_e2i[(size_t)uc]) diag[(size_t)P.row_e2i[(size_t)lr]] = t;
           mrow[(size_t)lr] += 1;
           mcol[(size_t)uc] += 1;
