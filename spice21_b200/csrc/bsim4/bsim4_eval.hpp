@@ -29,6 +29,18 @@
 namespace s21 {
 namespace b4e {
 
+// Every f64 division of the evaluation goes through this one macro (scripts/b4_route_divisions.py rewrote the ~450
+// `X / Y` sites, keeping C++'s grouping: B4_DIV(whole multiplicative chain to the left, next unary expression)). The
+// default is the plain quotient, i.e. exactly the code there was before. Building the device side with -DS21_B4_SDIV
+// routes them through the split exact division of csrc/scalar.h instead (same bits; the compiler's own sequence sends
+// every zero numerator — frequent in a model with this many optional terms — to a ~100-instruction slow path). Not
+// enabled by default: it has not been measured on a GPU yet.
+#if defined(S21_B4_SDIV) && defined(__CUDA_ARCH__)
+#define B4_DIV(a, b) ::s21::s_div((double)(a), (double)(b))
+#else
+#define B4_DIV(a, b) ((a) / (b))
+#endif
+
 // bsim4/mod.rs:35-63 and comps/consts
 #define B4C_EXPL_THRESHOLD 100.0
 #define B4C_EXP_THRESHOLD 34.0
@@ -72,7 +84,7 @@ B4_HD double b4_limvds(double vnew, double vold) {
 }
 B4_HD double b4_fetlim(double vnew, double vold, double vto) {
   const double vtsthi = fabs(2.0 * (vold - vto)) + 2.0;
-  const double vtstlo = vtsthi / 2.0 + 2.0;
+  const double vtstlo = B4_DIV(vtsthi, 2.0) + 2.0;
   const double vtox = vto + 3.5;
   const double delv = vnew - vold;
   if (vold >= vto) {
@@ -99,26 +111,26 @@ B4_HD double b4_fetlim(double vnew, double vold, double vto) {
 B4_HD double b4_pnjlim(double vnew, double vold, double vt, double vcrit) {
   if (vnew > vcrit && fabs(vnew - vold) > (vt + vt)) {
     if (vold > 0.0) {
-      const double arg = 1.0 + (vnew - vold) / vt;
+      const double arg = 1.0 + B4_DIV((vnew - vold), vt);
       return arg > 0.0 ? vold + vt * log(arg) : vcrit;
     }
-    return vt * log(vnew / vt);
+    return vt * log(B4_DIV(vnew, vt));
   }
   return vnew;
 }
 // poly-gate depletion (bsim4solver.rs:3771-3787): effective gate voltage and its derivative
 B4_HD void b4_poly_depletion(double phi, double ngate, double epsgate, double coxe, double Vgs, double* Vgs_eff, double* dVgs_eff_dVg) {
   if (ngate > 1.0e18 && ngate < 1.0e25 && Vgs > phi && epsgate != 0.0) {
-    const double T1 = 1.0e6 * B4C_Q * epsgate * ngate / (coxe * coxe);
+    const double T1 = B4_DIV(1.0e6 * B4C_Q * epsgate * ngate, (coxe * coxe));
     const double T8 = Vgs - phi;
-    const double T4 = sqrt(1.0 + 2.0 * T8 / T1);
-    const double T2 = 2.0 * T8 / (T4 + 1.0);
-    const double T3 = 0.5 * T2 * T2 / T1;
+    const double T4 = sqrt(1.0 + B4_DIV(2.0 * T8, T1));
+    const double T2 = B4_DIV(2.0 * T8, (T4 + 1.0));
+    const double T3 = B4_DIV(0.5 * T2 * T2, T1);
     const double T7 = 1.12 - T3 - 0.05;
     const double T6 = sqrt(T7 * T7 + 0.224);
     const double T5 = 1.12 - 0.5 * (T7 + T6);
     *Vgs_eff = Vgs - T5;
-    *dVgs_eff_dVg = 1.0 - (0.5 - 0.5 / T4) * (1.0 + T7 / T6);
+    *dVgs_eff_dVg = 1.0 - (0.5 - B4_DIV(0.5, T4)) * (1.0 + B4_DIV(T7, T6));
   } else {
     *Vgs_eff = Vgs;
     *dVgs_eff_dVg = 1.0;
@@ -261,21 +273,21 @@ B4_HD void b4_junction_iv(int diomod, const B4JunctionSide& j, double vj, double
     return;
   }
   if (diomod == 0) {
-    const double ev = exp(vj / j.Nvtm);
-    const double T1 = j.xjbv * exp(-(j.bv + vj) / j.Nvtm);
-    *g = j.Isat * (ev + T1) / j.Nvtm + gmin;
+    const double ev = exp(B4_DIV(vj, j.Nvtm));
+    const double T1 = j.xjbv * exp(B4_DIV(-(j.bv + vj), j.Nvtm));
+    *g = B4_DIV(j.Isat * (ev + T1), j.Nvtm) + gmin;
     *c = j.Isat * (ev + j.XExpBV - T1 - 1.0) + gmin * vj;
   } else if (diomod == 1) {
-    const double T2 = vj / j.Nvtm;
+    const double T2 = B4_DIV(vj, j.Nvtm);
     if (T2 < -B4C_EXP_THRESHOLD) {
       *g = gmin;
       *c = j.Isat * (B4C_MIN_EXP - 1.0) + gmin * vj;
     } else if (vj <= j.vjmFwd) {
       const double ev = exp(T2);
-      *g = j.Isat * ev / j.Nvtm + gmin;
+      *g = B4_DIV(j.Isat * ev, j.Nvtm) + gmin;
       *c = j.Isat * (ev - 1.0) + gmin * vj;
     } else {
-      const double T0 = j.IVjmFwd / j.Nvtm;
+      const double T0 = B4_DIV(j.IVjmFwd, j.Nvtm);
       *g = T0 + gmin;
       *c = j.IVjmFwd - j.Isat + T0 * (vj - j.vjmFwd) + gmin * vj;
     }
@@ -285,20 +297,20 @@ B4_HD void b4_junction_iv(int diomod, const B4JunctionSide& j, double vj, double
       *c = j.IVjmFwd + j.slpFwd * (vj - j.vjmFwd) + gmin * vj;
       return;
     }
-    const double T0 = vj / j.Nvtm;
+    const double T0 = B4_DIV(vj, j.Nvtm);
     double ev, dev;
     if (T0 < -B4C_EXP_THRESHOLD) { ev = B4C_MIN_EXP; dev = 0.0; }
-    else { ev = exp(T0); dev = ev / j.Nvtm; }
+    else { ev = exp(T0); dev = B4_DIV(ev, j.Nvtm); }
     if (vj < j.vjmRev) {
       const double T1 = ev - 1.0;
       const double T2 = j.IVjmRev + j.slpRev * (vj - j.vjmRev);
       *g = dev * T2 + T1 * j.slpRev + gmin;
       *c = T1 * T2 + gmin * vj;
     } else {
-      const double T1 = (j.bv + vj) / j.Nvtm;
+      const double T1 = B4_DIV((j.bv + vj), j.Nvtm);
       double T2, T3;
       if (T1 > B4C_EXP_THRESHOLD) { T2 = B4C_MIN_EXP; T3 = 0.0; }
-      else { T2 = exp(-T1); T3 = -T2 / j.Nvtm; }
+      else { T2 = exp(-T1); T3 = B4_DIV(-T2, j.Nvtm); }
       *g = j.Isat * (dev - j.xjbv * T3) + gmin;
       *c = j.Isat * (ev + j.XExpBV - 1.0 - j.xjbv * T2) + gmin * vj;
     }
@@ -308,13 +320,13 @@ B4_HD void b4_junction_iv(int diomod, const B4JunctionSide& j, double vj, double
 B4_HD void b4_tat_factor(double vts, double Nvtmr, double vj, double* f, double* df) {
   if ((vts - vj) < (vts * 1e-3)) {
     const double T9 = 1.0e3;
-    const double T0 = -vj / Nvtmr * T9;
+    const double T0 = B4_DIV(-vj, Nvtmr) * T9;
     *f = b4_dexpb(T0);
-    *df = b4_dexpc(T0) / Nvtmr * T9;
+    *df = B4_DIV(b4_dexpc(T0), Nvtmr) * T9;
   } else {
-    const double T9 = 1.0 / (vts - vj);
-    const double T0 = -vj / Nvtmr * vts * T9;
-    const double dT0 = vts / Nvtmr * (T9 + vj * T9 * T9);
+    const double T9 = B4_DIV(1.0, (vts - vj));
+    const double T0 = B4_DIV(-vj, Nvtmr) * vts * T9;
+    const double dT0 = B4_DIV(vts, Nvtmr) * (T9 + vj * T9 * T9);
     *f = b4_dexpb(T0);
     *df = b4_dexpc(T0) * dT0;
   }

@@ -27,11 +27,11 @@ B4_HD void b4_sce_rolloff(double x, double dlt_dVb, double lt, double* theta, do
     const double T2 = T1 - 1.0;
     const double T3 = T2 * T2;
     const double T4 = T3 + 2.0 * T1 * B4C_MIN_EXP;
-    *theta = T1 / T4;
-    const double dT1_dVb = -x * T1 * dlt_dVb / lt;
-    *dtheta_dVb = dT1_dVb * (T4 - 2.0 * T1 * (T2 + B4C_MIN_EXP)) / T4 / T4;
+    *theta = B4_DIV(T1, T4);
+    const double dT1_dVb = B4_DIV(-x * T1 * dlt_dVb, lt);
+    *dtheta_dVb = B4_DIV(B4_DIV(dT1_dVb * (T4 - 2.0 * T1 * (T2 + B4C_MIN_EXP)), T4), T4);
   } else {
-    *theta = 1.0 / (B4C_MAX_EXP - 2.0);
+    *theta = B4_DIV(1.0, (B4C_MAX_EXP - 2.0));
     *dtheta_dVb = 0.0;
   }
 }
@@ -65,22 +65,22 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
   T1 = sqrt(T0 * T0 - 0.004 * vbsc);
   if (T0 >= 0.0) {
     Vbseff = vbsc + 0.5 * (T0 + T1);
-    dVbseff_dVb = 0.5 * (1.0 + T0 / T1);
+    dVbseff_dVb = 0.5 * (1.0 + B4_DIV(T0, T1));
   } else {
-    T2 = -0.002 / (T1 - T0);
+    T2 = B4_DIV(-0.002, (T1 - T0));
     Vbseff = vbsc * (1.0 + T2);
-    dVbseff_dVb = T2 * vbsc / T1;
+    dVbseff_dVb = B4_DIV(T2 * vbsc, T1);
   }
   T9 = 0.95 * phi;
   T0 = T9 - Vbseff - 0.001;
   T1 = sqrt(T0 * T0 + 0.004 * T9);
   Vbseff = T9 - 0.5 * (T0 + T1);
-  dVbseff_dVb *= 0.5 * (1.0 + T0 / T1);
+  dVbseff_dVb *= 0.5 * (1.0 + B4_DIV(T0, T1));
   const double Phis = phi - Vbseff;
   const double sqrtPhis = sqrt(Phis);
-  const double dsqrtPhis_dVb = -0.5 / sqrtPhis;
-  const double Xdep = S_(Xdep0) * sqrtPhis / sqrtPhi;
-  const double dXdep_dVb = (S_(Xdep0) / sqrtPhi) * dsqrtPhis_dVb;
+  const double dsqrtPhis_dVb = B4_DIV(-0.5, sqrtPhis);
+  const double Xdep = B4_DIV(S_(Xdep0) * sqrtPhis, sqrtPhi);
+  const double dXdep_dVb = (B4_DIV(S_(Xdep0), sqrtPhi)) * dsqrtPhis_dVb;
   const double Leff = S_(leff), Vtm = D_(vtm), Vtm0 = D_(vtm0);
 
   // ---- threshold voltage (:826-976)
@@ -89,36 +89,36 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
   const double factor1 = D_(factor1);
   T0 = S_(dvt2) * Vbseff;
   if (T0 >= -0.5) { T1 = 1.0 + T0; T2 = S_(dvt2); }
-  else { T4 = 1.0 / (3.0 + 8.0 * T0); T1 = (1.0 + 3.0 * T0) * T4; T2 = S_(dvt2) * T4 * T4; }
+  else { T4 = B4_DIV(1.0, (3.0 + 8.0 * T0)); T1 = (1.0 + 3.0 * T0) * T4; T2 = S_(dvt2) * T4 * T4; }
   const double lt1 = factor1 * T3 * T1;
-  const double dlt1_dVb = factor1 * (0.5 / T3 * T1 * dXdep_dVb + T3 * T2);
+  const double dlt1_dVb = factor1 * (B4_DIV(0.5, T3) * T1 * dXdep_dVb + T3 * T2);
   T0 = S_(dvt2w) * Vbseff;
   if (T0 >= -0.5) { T1 = 1.0 + T0; T2 = S_(dvt2w); }
-  else { T4 = 1.0 / (3.0 + 8.0 * T0); T1 = (1.0 + 3.0 * T0) * T4; T2 = S_(dvt2w) * T4 * T4; }
+  else { T4 = B4_DIV(1.0, (3.0 + 8.0 * T0)); T1 = (1.0 + 3.0 * T0) * T4; T2 = S_(dvt2w) * T4 * T4; }
   const double ltw = factor1 * T3 * T1;
-  const double dltw_dVb = factor1 * (0.5 / T3 * T1 * dXdep_dVb + T3 * T2);
+  const double dltw_dVb = factor1 * (B4_DIV(0.5, T3) * T1 * dXdep_dVb + T3 * T2);
 
   double Theta0, dTheta0_dVb;
-  b4_sce_rolloff(S_(dvt1) * Leff / lt1, dlt1_dVb, lt1, &Theta0, &dTheta0_dVb);
+  b4_sce_rolloff(B4_DIV(S_(dvt1) * Leff, lt1), dlt1_dVb, lt1, &Theta0, &dTheta0_dVb);
   const double thetavth = S_(dvt0) * Theta0;
   const double Delt_vth = thetavth * V0;
   const double dDelt_vth_dVb = S_(dvt0) * dTheta0_dVb * V0;
-  b4_sce_rolloff(S_(dvt1w) * S_(weff) * Leff / ltw, dltw_dVb, ltw, &T5, &dT5_dVb);
+  b4_sce_rolloff(B4_DIV(S_(dvt1w) * S_(weff) * Leff, ltw), dltw_dVb, ltw, &T5, &dT5_dVb);
   T0 = S_(dvt0w) * T5;
   T2 = T0 * V0;
   dT2_dVb = S_(dvt0w) * dT5_dVb * V0;
 
   const double TempRatio = D_(TempRatio);
-  T0 = sqrt(1.0 + S_(lpe0) / Leff);
-  T1 = S_(k1ox) * (T0 - 1.0) * sqrtPhi + (S_(kt1) + S_(kt1l) / Leff + S_(kt2) * Vbseff) * (TempRatio - 1.0);
-  const double Vth_NarrowW = toxe * phi / (S_(weff) + S_(w0));
+  T0 = sqrt(1.0 + B4_DIV(S_(lpe0), Leff));
+  T1 = S_(k1ox) * (T0 - 1.0) * sqrtPhi + (S_(kt1) + B4_DIV(S_(kt1l), Leff) + S_(kt2) * Vbseff) * (TempRatio - 1.0);
+  const double Vth_NarrowW = B4_DIV(toxe * phi, (S_(weff) + S_(w0)));
 
   T3 = I_(eta0) + S_(etab) * Vbseff;
-  if (T3 < 1.0e-4) { T9 = 1.0 / (3.0 - 2.0e4 * T3); T3 = (2.0e-4 - T3) * T9; T4 = T9 * T9; }
+  if (T3 < 1.0e-4) { T9 = B4_DIV(1.0, (3.0 - 2.0e4 * T3)); T3 = (2.0e-4 - T3) * T9; T4 = T9 * T9; }
   else T4 = 1.0;
   const double dDIBL_Sft_dVd = T3 * S_(theta0vb0);
   const double DIBL_Sft = dDIBL_Sft_dVd * Vds;
-  const double Lpe_Vb = sqrt(1.0 + S_(lpeb) / Leff);
+  const double Lpe_Vb = sqrt(1.0 + B4_DIV(S_(lpeb), Leff));
 
   double Vth = tp * I_(vth0) + (S_(k1ox) * sqrtPhis - S_(k1) * sqrtPhi) * Lpe_Vb - I_(k2ox) * Vbseff - Delt_vth - T2
                + (S_(k3) + S_(k3b) * Vbseff) * Vth_NarrowW + T1 - DIBL_Sft;
@@ -128,20 +128,20 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
 
   // subthreshold swing factor n
   double n, dn_dVb, dn_dVd;
-  tmp1 = epssub / Xdep;
+  tmp1 = B4_DIV(epssub, Xdep);
   tmp2 = S_(nfactor) * tmp1;
   tmp3 = S_(cdsc) + S_(cdscb) * Vbseff + S_(cdscd) * Vds;
-  tmp4 = (tmp2 + tmp3 * Theta0 + S_(cit)) / coxe;
+  tmp4 = B4_DIV((tmp2 + tmp3 * Theta0 + S_(cit)), coxe);
   if (tmp4 >= -0.5) {
     n = 1.0 + tmp4;
-    dn_dVb = (-tmp2 / Xdep * dXdep_dVb + tmp3 * dTheta0_dVb + S_(cdscb) * Theta0) / coxe;
-    dn_dVd = S_(cdscd) * Theta0 / coxe;
+    dn_dVb = B4_DIV((B4_DIV(-tmp2, Xdep) * dXdep_dVb + tmp3 * dTheta0_dVb + S_(cdscb) * Theta0), coxe);
+    dn_dVd = B4_DIV(S_(cdscd) * Theta0, coxe);
   } else {
-    T0 = 1.0 / (3.0 + 8.0 * tmp4);
+    T0 = B4_DIV(1.0, (3.0 + 8.0 * tmp4));
     n = (1.0 + 3.0 * tmp4) * T0;
     T0 *= T0;
-    dn_dVb = (-tmp2 / Xdep * dXdep_dVb + tmp3 * dTheta0_dVb + S_(cdscb) * Theta0) / coxe * T0;
-    dn_dVd = S_(cdscd) * Theta0 / coxe * T0;
+    dn_dVb = B4_DIV((B4_DIV(-tmp2, Xdep) * dXdep_dVb + tmp3 * dTheta0_dVb + S_(cdscb) * Theta0), coxe) * T0;
+    dn_dVd = B4_DIV(S_(cdscd) * Theta0, coxe) * T0;
   }
 
   if (S_(dvtp0) > 0.0) {  // pocket-implant (DITS) threshold shift
@@ -150,8 +150,8 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
     else { T2 = exp(T0); dT2_dVd = -S_(dvtp1) * T2; }
     T3 = Leff + S_(dvtp0) * (1.0 + T2);
     dT3_dVd = S_(dvtp0) * dT2_dVd;
-    if (tempmod < 2) { T4 = Vtm * log(Leff / T3); dT4_dVd = -Vtm * dT3_dVd / T3; }
-    else { T4 = Vtm0 * log(Leff / T3); dT4_dVd = -Vtm0 * dT3_dVd / T3; }
+    if (tempmod < 2) { T4 = Vtm * log(B4_DIV(Leff, T3)); dT4_dVd = B4_DIV(-Vtm * dT3_dVd, T3); }
+    else { T4 = Vtm0 * log(B4_DIV(Leff, T3)); dT4_dVd = B4_DIV(-Vtm0 * dT3_dVd, T3); }
     const double dDITS_Sft_dVd = dn_dVd * T4 + n * dT4_dVd;
     const double dDITS_Sft_dVb = T4 * dn_dVb;
     Vth -= n * T4;
@@ -162,8 +162,8 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
     T1 = 2.0 * S_(dvtp4) * Vds;
     T0 = b4_dexpb(T1);
     T10 = b4_dexpc(T1);
-    const double DITS_Sft2 = S_(dvtp2factor) * (T0 - 1.0) / (T0 + 1.0);
-    const double dDITS_Sft2_dVd = S_(dvtp2factor) * S_(dvtp4) * 4.0 * T10 / ((T0 + 1.0) * (T0 + 1.0));
+    const double DITS_Sft2 = B4_DIV(S_(dvtp2factor) * (T0 - 1.0), (T0 + 1.0));
+    const double dDITS_Sft2_dVd = B4_DIV(S_(dvtp2factor) * S_(dvtp4) * 4.0 * T10, ((T0 + 1.0) * (T0 + 1.0)));
     Vth -= DITS_Sft2;
     dVth_dVd -= dDITS_Sft2_dVd;
   }
@@ -182,7 +182,7 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
 
   T0 = n * Vtm;
   T1 = mstar * Vgst;
-  T2 = T1 / T0;
+  T2 = B4_DIV(T1, T0);
   if (T2 > B4C_EXP_THRESHOLD) {
     T10 = T1;
     dT10_dVg = mstar * dVgs_eff_dVg;
@@ -198,37 +198,37 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
     const double ExpVgst = exp(T2);
     T3 = Vtm * log(1.0 + ExpVgst);
     T10 = n * T3;
-    dT10_dVg = mstar * ExpVgst / (1.0 + ExpVgst);
-    dT10_dVb = T3 * dn_dVb - dT10_dVg * (dVth_dVb + Vgst * dn_dVb / n);
-    dT10_dVd = T3 * dn_dVd - dT10_dVg * (dVth_dVd + Vgst * dn_dVd / n);
+    dT10_dVg = B4_DIV(mstar * ExpVgst, (1.0 + ExpVgst));
+    dT10_dVb = T3 * dn_dVb - dT10_dVg * (dVth_dVb + B4_DIV(Vgst * dn_dVb, n));
+    dT10_dVd = T3 * dn_dVd - dT10_dVg * (dVth_dVd + B4_DIV(Vgst * dn_dVd, n));
     dT10_dVg *= dVgs_eff_dVg;
   }
   T1 = S_(voffcbn) - (1.0 - mstar) * Vgst;
-  T2 = T1 / T0;
+  T2 = B4_DIV(T1, T0);
   if (T2 < -B4C_EXP_THRESHOLD) {
-    T3 = coxe * B4C_MIN_EXP / S_(cdep0);
+    T3 = B4_DIV(coxe * B4C_MIN_EXP, S_(cdep0));
     T9 = mstar + T3 * n;
     dT9_dVg = 0.0; dT9_dVd = dn_dVd * T3; dT9_dVb = dn_dVb * T3;
   } else if (T2 > B4C_EXP_THRESHOLD) {
-    T3 = coxe * B4C_MAX_EXP / S_(cdep0);
+    T3 = B4_DIV(coxe * B4C_MAX_EXP, S_(cdep0));
     T9 = mstar + T3 * n;
     dT9_dVg = 0.0; dT9_dVd = dn_dVd * T3; dT9_dVb = dn_dVb * T3;
   } else {
     const double ExpVgst = exp(T2);
-    T3 = coxe / S_(cdep0);
+    T3 = B4_DIV(coxe, S_(cdep0));
     T4 = T3 * ExpVgst;
-    T5 = T1 * T4 / T0;
+    T5 = B4_DIV(T1 * T4, T0);
     T9 = mstar + n * T4;
-    dT9_dVg = T3 * (mstar - 1.0) * ExpVgst / Vtm;
+    dT9_dVg = B4_DIV(T3 * (mstar - 1.0) * ExpVgst, Vtm);
     dT9_dVb = T4 * dn_dVb - dT9_dVg * dVth_dVb - T5 * dn_dVb;
     dT9_dVd = T4 * dn_dVd - dT9_dVg * dVth_dVd - T5 * dn_dVd;
     dT9_dVg *= dVgs_eff_dVg;
   }
-  const double Vgsteff = T10 / T9;
+  const double Vgsteff = B4_DIV(T10, T9);
   T11 = T9 * T9;
-  const double dVgsteff_dVg = (T9 * dT10_dVg - T10 * dT9_dVg) / T11;
-  const double dVgsteff_dVd = (T9 * dT10_dVd - T10 * dT9_dVd) / T11;
-  const double dVgsteff_dVb = (T9 * dT10_dVb - T10 * dT9_dVb) / T11;
+  const double dVgsteff_dVg = B4_DIV((T9 * dT10_dVg - T10 * dT9_dVg), T11);
+  const double dVgsteff_dVd = B4_DIV((T9 * dT10_dVd - T10 * dT9_dVd), T11);
+  const double dVgsteff_dVb = B4_DIV((T9 * dT10_dVb - T10 * dT9_dVb), T11);
 
   // ---- effective width; the reference never enables the internal bias-dependent Rds (:1064-1104)
   T9 = sqrtPhis - sqrtPhi;
@@ -236,7 +236,7 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
   double dWeff_dVg = -2.0 * S_(dwg);
   double dWeff_dVb = -2.0 * S_(dwb) * dsqrtPhis_dVb;
   if (Weff < 2.0e-8) {
-    T0 = 1.0 / (6.0e-8 - 2.0 * Weff);
+    T0 = B4_DIV(1.0, (6.0e-8 - 2.0 * Weff));
     Weff = 2.0e-8 * (4.0e-8 - Weff) * T0;
     T0 *= T0 * 4.0e-16;
     dWeff_dVg *= T0;
@@ -245,17 +245,17 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
   const double Rds = 0.0, dRds_dVg = 0.0, dRds_dVb = 0.0;  // `rdsmod > 1` cannot hold: the selector is clamped to {0, 1}
 
   // ---- bulk charge factor (:1106-1159)
-  T9 = 0.5 * S_(k1ox) * Lpe_Vb / sqrtPhis;
+  T9 = B4_DIV(0.5 * S_(k1ox) * Lpe_Vb, sqrtPhis);
   T1 = T9 + I_(k2ox) - S_(k3b) * Vth_NarrowW;
-  dT1_dVb = -T9 / sqrtPhis * dsqrtPhis_dVb;
+  dT1_dVb = B4_DIV(-T9, sqrtPhis) * dsqrtPhis_dVb;
   T9 = sqrt(S_(xj) * Xdep);
   tmp1 = Leff + 2.0 * T9;
-  T5 = Leff / tmp1;
+  T5 = B4_DIV(Leff, tmp1);
   tmp2 = S_(a0) * T5;
   tmp3 = S_(weff) + S_(b1);
-  tmp4 = S_(b0) / tmp3;
+  tmp4 = B4_DIV(S_(b0), tmp3);
   T2 = tmp2 + tmp4;
-  dT2_dVb = -T9 / tmp1 / Xdep * dXdep_dVb;
+  dT2_dVb = B4_DIV(B4_DIV(-T9, tmp1), Xdep) * dXdep_dVb;
   T6 = T5 * T5;
   T7 = T5 * T6;
   double Abulk0 = 1.0 + T1 * T2;
@@ -265,20 +265,20 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
   double Abulk = Abulk0 + dAbulk_dVg * Vgsteff;
   double dAbulk_dVb = dAbulk0_dVb - T8 * Vgsteff * (dT1_dVb + 3.0 * T1 * dT2_dVb);
   if (Abulk0 < 0.1) {
-    T9 = 1.0 / (3.0 - 20.0 * Abulk0);
+    T9 = B4_DIV(1.0, (3.0 - 20.0 * Abulk0));
     Abulk0 = (0.2 - Abulk0) * T9;
     dAbulk0_dVb *= T9 * T9;
   }
   if (Abulk < 0.1) {
-    T9 = 1.0 / (3.0 - 20.0 * Abulk);
+    T9 = B4_DIV(1.0, (3.0 - 20.0 * Abulk));
     Abulk = (0.2 - Abulk) * T9;
     T10 = T9 * T9;
     dAbulk_dVb *= T10;
     dAbulk_dVg *= T10;
   }
   T2 = S_(keta) * Vbseff;
-  if (T2 >= -0.9) { T0 = 1.0 / (1.0 + T2); dT0_dVb = -S_(keta) * T0 * T0; }
-  else { T1 = 1.0 / (0.8 + T2); T0 = (17.0 + 20.0 * T2) * T1; dT0_dVb = -S_(keta) * T1 * T1; }
+  if (T2 >= -0.9) { T0 = B4_DIV(1.0, (1.0 + T2)); dT0_dVb = -S_(keta) * T0 * T0; }
+  else { T1 = B4_DIV(1.0, (0.8 + T2)); T0 = (17.0 + 20.0 * T2) * T1; dT0_dVb = -S_(keta) * T1 * T1; }
   dAbulk_dVg *= T0;
   dAbulk_dVb = dAbulk_dVb * T0 + Abulk * dT0_dVb;
   dAbulk0_dVb = dAbulk0_dVb * T0 + Abulk0 * dT0_dVb;
@@ -295,18 +295,18 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
     const double Vx = vth_ref ? Vth : I_(vtfbphi1);
     T0 = vth_ref ? Vgsteff + Vth + Vth - T14 : Vgsteff + I_(vtfbphi1) - T14;
     T2 = mult ? 1.0 + uc * Vbseff : ua + uc * Vbseff;
-    T3 = T0 / toxe;
+    T3 = B4_DIV(T0, toxe);
     T4 = T3 * (ua + ub * T3);  // used by the multiplicative forms only
     T12 = sqrt(Vx * Vx + 0.0001);
-    T9 = 1.0 / (Vgsteff + 2.0 * T12);
+    T9 = B4_DIV(1.0, (Vgsteff + 2.0 * T12));
     T10 = T9 * toxe;
     T8 = ud * T10 * T10 * Vx;
     T6 = T8 * Vx;
     T5 = mult ? T4 * T2 + T6 : T3 * (T2 + ub * T3) + T6;
     T7 = -2.0 * T6 * T9;
-    dDenomi_dVg = mult ? (ua + 2.0 * ub * T3) * T2 / toxe : (T2 + 2.0 * ub * T3) / toxe;
+    dDenomi_dVg = mult ? B4_DIV((ua + 2.0 * ub * T3) * T2, toxe) : B4_DIV((T2 + 2.0 * ub * T3), toxe);
     if (vth_ref) {
-      T11 = T7 * Vth / T12;
+      T11 = B4_DIV(T7 * Vth, T12);
       T13 = 2.0 * (dDenomi_dVg + T11 + T8);
       dDenomi_dVd = T13 * dVth_dVd;
       dDenomi_dVb = T13 * dVth_dVb + (mult ? uc * T4 : uc * T3);
@@ -316,13 +316,13 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
     }
     dDenomi_dVg += T7;
   } else if (mobmod == 2 || mobmod == 6) {
-    T0 = (Vgsteff + I_(vtfbphi1)) / toxe;
+    T0 = B4_DIV((Vgsteff + I_(vtfbphi1)), toxe);
     T1 = exp(S_(eu) * log(T0));
-    dT1_dVg = T1 * S_(eu) / T0 / toxe;
+    dT1_dVg = B4_DIV(B4_DIV(T1 * S_(eu), T0), toxe);
     T2 = ua + uc * Vbseff;
     const double Vx = mobmod == 2 ? Vth : I_(vtfbphi1);
     T12 = sqrt(Vx * Vx + 0.0001);
-    T9 = 1.0 / (Vgsteff + 2.0 * T12);
+    T9 = B4_DIV(1.0, (Vgsteff + 2.0 * T12));
     T10 = T9 * toxe;
     T8 = ud * T10 * T10 * Vx;
     T6 = T8 * Vx;
@@ -330,7 +330,7 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
     T7 = -2.0 * T6 * T9;
     dDenomi_dVg = T2 * dT1_dVg + T7;
     if (mobmod == 2) {
-      T11 = T7 * Vth / T12;
+      T11 = B4_DIV(T7 * Vth, T12);
       T13 = 2.0 * (T11 + T8);
       dDenomi_dVd = T13 * dVth_dVd;
       dDenomi_dVb = T13 * dVth_dVb + T1 * uc;
@@ -339,14 +339,14 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
       dDenomi_dVb = T1 * uc;
     }
   } else {  // mobmod 3: universal + Coulomb scattering for high-k stacks
-    T0 = (Vgsteff + I_(vtfbphi1)) * 1.0e-8 / toxe / 6.0;
+    T0 = B4_DIV(B4_DIV((Vgsteff + I_(vtfbphi1)) * 1.0e-8, toxe), 6.0);
     T1 = exp(S_(eu) * log(T0));
-    dT1_dVg = T1 * S_(eu) * 1.0e-8 / T0 / toxe / 6.0;
+    dT1_dVg = B4_DIV(B4_DIV(B4_DIV(T1 * S_(eu) * 1.0e-8, T0), toxe), 6.0);
     T2 = ua + uc * Vbseff;
     const double VgsteffVth = S_(VgsteffVth);
-    T10 = exp(S_(ucs) * log(0.5 + 0.5 * Vgsteff / VgsteffVth));
-    T11 = ud / T10;
-    const double dT11_dVg = -0.5 * S_(ucs) * T11 / (0.5 + 0.5 * Vgsteff / VgsteffVth) / VgsteffVth;
+    T10 = exp(S_(ucs) * log(0.5 + B4_DIV(0.5 * Vgsteff, VgsteffVth)));
+    T11 = B4_DIV(ud, T10);
+    const double dT11_dVg = B4_DIV(B4_DIV(-0.5 * S_(ucs) * T11, (0.5 + B4_DIV(0.5 * Vgsteff, VgsteffVth))), VgsteffVth);
     dDenomi_dVg = T2 * dT1_dVg + dT11_dVg;
     dDenomi_dVd = 0.0;
     dDenomi_dVb = T1 * uc;
@@ -355,22 +355,22 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
   if (T5 >= -0.8) {
     Denomi = 1.0 + T5;
   } else {
-    T9 = 1.0 / (7.0 + 10.0 * T5);
+    T9 = B4_DIV(1.0, (7.0 + 10.0 * T5));
     Denomi = (0.6 + T5) * T9;
     T9 *= T9;
     dDenomi_dVg *= T9; dDenomi_dVd *= T9; dDenomi_dVb *= T9;
   }
-  const double ueff = I_(u0temp) / Denomi;
-  T9 = -ueff / Denomi;
+  const double ueff = B4_DIV(I_(u0temp), Denomi);
+  T9 = B4_DIV(-ueff, Denomi);
   const double dueff_dVg = T9 * dDenomi_dVg, dueff_dVd = T9 * dDenomi_dVd, dueff_dVb = T9 * dDenomi_dVb;
 
   // ---- saturation voltage (:1313-1400)
   const double vsattemp = I_(vsattemp);
   const double WVCox = Weff * vsattemp * coxe;
   const double WVCoxRds = WVCox * Rds;
-  double Esat = 2.0 * vsattemp / ueff;
+  double Esat = B4_DIV(2.0 * vsattemp, ueff);
   double EsatL = Esat * Leff;
-  T0 = -EsatL / ueff;
+  T0 = B4_DIV(-EsatL, ueff);
   double dEsatL_dVg = T0 * dueff_dVg, dEsatL_dVd = T0 * dueff_dVd, dEsatL_dVb = T0 * dueff_dVb;
 
   double Lambda, dLambda_dVg;
@@ -383,20 +383,20 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
     T1 = T0 - a1 * Vgsteff - 0.0001;
     T2 = sqrt(T1 * T1 + 0.0004 * T0);
     Lambda = a2 + T0 - 0.5 * (T1 + T2);
-    dLambda_dVg = 0.5 * a1 * (1.0 + T1 / T2);
+    dLambda_dVg = 0.5 * a1 * (1.0 + B4_DIV(T1, T2));
   } else {
     T1 = a2 + a1 * Vgsteff - 0.0001;
     T2 = sqrt(T1 * T1 + 0.0004 * a2);
     Lambda = 0.5 * (T1 + T2);
-    dLambda_dVg = 0.5 * a1 * (1.0 + T1 / T2);
+    dLambda_dVg = 0.5 * a1 * (1.0 + B4_DIV(T1, T2));
   }
 
   const double Vgst2Vtm = Vgsteff + 2.0 * Vtm;
-  if (Rds > 0.0) { tmp2 = dRds_dVg / Rds + dWeff_dVg / Weff; tmp3 = dRds_dVb / Rds + dWeff_dVb / Weff; }
-  else { tmp2 = dWeff_dVg / Weff; tmp3 = dWeff_dVb / Weff; }
+  if (Rds > 0.0) { tmp2 = B4_DIV(dRds_dVg, Rds) + B4_DIV(dWeff_dVg, Weff); tmp3 = B4_DIV(dRds_dVb, Rds) + B4_DIV(dWeff_dVb, Weff); }
+  else { tmp2 = B4_DIV(dWeff_dVg, Weff); tmp3 = B4_DIV(dWeff_dVb, Weff); }
   double Vdsat, dVdsat_dVg, dVdsat_dVd, dVdsat_dVb;
   if (Rds == 0.0 && Lambda == 1.0) {
-    T0 = 1.0 / (Abulk * EsatL + Vgst2Vtm);
+    T0 = B4_DIV(1.0, (Abulk * EsatL + Vgst2Vtm));
     tmp1 = 0.0;
     T1 = T0 * T0;
     T2 = Vgst2Vtm * T0;
@@ -409,17 +409,17 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
     dVdsat_dVd = T3 * dT0_dVd + T2 * dEsatL_dVd;
     dVdsat_dVb = T3 * dT0_dVb + T2 * dEsatL_dVb;
   } else {
-    tmp1 = dLambda_dVg / (Lambda * Lambda);
+    tmp1 = B4_DIV(dLambda_dVg, (Lambda * Lambda));
     T9 = Abulk * WVCoxRds;
     T8 = Abulk * T9;
     T7 = Vgst2Vtm * T9;
     T6 = Vgst2Vtm * WVCoxRds;
-    T0 = 2.0 * Abulk * (T9 - 1.0 + 1.0 / Lambda);
-    dT0_dVg = 2.0 * (T8 * tmp2 - Abulk * tmp1 + (2.0 * T9 + 1.0 / Lambda - 1.0) * dAbulk_dVg);
-    dT0_dVb = 2.0 * (T8 * (2.0 / Abulk * dAbulk_dVb + tmp3) + (1.0 / Lambda - 1.0) * dAbulk_dVb);
+    T0 = 2.0 * Abulk * (T9 - 1.0 + B4_DIV(1.0, Lambda));
+    dT0_dVg = 2.0 * (T8 * tmp2 - Abulk * tmp1 + (2.0 * T9 + B4_DIV(1.0, Lambda) - 1.0) * dAbulk_dVg);
+    dT0_dVb = 2.0 * (T8 * (B4_DIV(2.0, Abulk) * dAbulk_dVb + tmp3) + (B4_DIV(1.0, Lambda) - 1.0) * dAbulk_dVb);
     dT0_dVd = 0.0;
-    T1 = Vgst2Vtm * (2.0 / Lambda - 1.0) + Abulk * EsatL + 3.0 * T7;
-    dT1_dVg = (2.0 / Lambda - 1.0) - 2.0 * Vgst2Vtm * tmp1 + Abulk * dEsatL_dVg + EsatL * dAbulk_dVg + 3.0 * (T9 + T7 * tmp2 + T6 * dAbulk_dVg);
+    T1 = Vgst2Vtm * (B4_DIV(2.0, Lambda) - 1.0) + Abulk * EsatL + 3.0 * T7;
+    dT1_dVg = (B4_DIV(2.0, Lambda) - 1.0) - 2.0 * Vgst2Vtm * tmp1 + Abulk * dEsatL_dVg + EsatL * dAbulk_dVg + 3.0 * (T9 + T7 * tmp2 + T6 * dAbulk_dVg);
     dT1_dVb = Abulk * dEsatL_dVb + EsatL * dAbulk_dVb + 3.0 * (T6 * dAbulk_dVb + T7 * tmp3);
     dT1_dVd = Abulk * dEsatL_dVd;
     T2 = Vgst2Vtm * (EsatL + 2.0 * T6);
@@ -427,14 +427,14 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
     dT2_dVb = Vgst2Vtm * (dEsatL_dVb + 2.0 * T6 * tmp3);
     dT2_dVd = Vgst2Vtm * dEsatL_dVd;
     T3 = sqrt(T1 * T1 - 2.0 * T0 * T2);
-    Vdsat = (T1 - T3) / T0;
-    dT3_dVg = (T1 * dT1_dVg - 2.0 * (T0 * dT2_dVg + T2 * dT0_dVg)) / T3;
-    dT3_dVd = (T1 * dT1_dVd - 2.0 * (T0 * dT2_dVd + T2 * dT0_dVd)) / T3;
-    dT3_dVb = (T1 * dT1_dVb - 2.0 * (T0 * dT2_dVb + T2 * dT0_dVb)) / T3;
+    Vdsat = B4_DIV((T1 - T3), T0);
+    dT3_dVg = B4_DIV((T1 * dT1_dVg - 2.0 * (T0 * dT2_dVg + T2 * dT0_dVg)), T3);
+    dT3_dVd = B4_DIV((T1 * dT1_dVd - 2.0 * (T0 * dT2_dVd + T2 * dT0_dVd)), T3);
+    dT3_dVb = B4_DIV((T1 * dT1_dVb - 2.0 * (T0 * dT2_dVb + T2 * dT0_dVb)), T3);
     (void)dT3_dVg; (void)dT3_dVd; (void)dT3_dVb;
-    dVdsat_dVg = (dT1_dVg - (T1 * dT1_dVg - dT0_dVg * T2 - T0 * dT2_dVg) / T3 - Vdsat * dT0_dVg) / T0;
-    dVdsat_dVb = (dT1_dVb - (T1 * dT1_dVb - dT0_dVb * T2 - T0 * dT2_dVb) / T3 - Vdsat * dT0_dVb) / T0;
-    dVdsat_dVd = (dT1_dVd - (T1 * dT1_dVd - T0 * dT2_dVd) / T3) / T0;
+    dVdsat_dVg = B4_DIV((dT1_dVg - B4_DIV((T1 * dT1_dVg - dT0_dVg * T2 - T0 * dT2_dVg), T3) - Vdsat * dT0_dVg), T0);
+    dVdsat_dVb = B4_DIV((dT1_dVb - B4_DIV((T1 * dT1_dVb - dT0_dVb * T2 - T0 * dT2_dVb), T3) - Vdsat * dT0_dVb), T0);
+    dVdsat_dVd = B4_DIV((dT1_dVd - B4_DIV((T1 * dT1_dVd - T0 * dT2_dVd), T3)), T0);
   }
 
   // ---- effective Vds, smoothly limited to Vdsat (:1402-1441)
@@ -442,9 +442,9 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
   T1 = Vdsat - Vds - delta;
   dT1_dVg = dVdsat_dVg; dT1_dVd = dVdsat_dVd - 1.0; dT1_dVb = dVdsat_dVb;
   T2 = sqrt(T1 * T1 + 4.0 * delta * Vdsat);
-  T0 = T1 / T2;
+  T0 = B4_DIV(T1, T2);
   T9 = 2.0 * delta;
-  T3 = T9 / T2;
+  T3 = B4_DIV(T9, T2);
   dT2_dVg = T0 * dT1_dVg + T3 * dVdsat_dVg;
   dT2_dVd = T0 * dT1_dVd + T3 * dVdsat_dVd;
   dT2_dVb = T0 * dT1_dVb + T3 * dVdsat_dVb;
@@ -455,9 +455,9 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
     dVdseff_dVd = dVdsat_dVd - 0.5 * (dT1_dVd + dT2_dVd);
     dVdseff_dVb = dVdsat_dVb - 0.5 * (dT1_dVb + dT2_dVb);
   } else {
-    T4 = T9 / (T2 - T1);
+    T4 = B4_DIV(T9, (T2 - T1));
     T5 = 1.0 - T4;
-    T6 = Vdsat * T4 / (T2 - T1);
+    T6 = B4_DIV(Vdsat * T4, (T2 - T1));
     Vdseff = Vdsat * T5;
     dVdseff_dVg = dVdsat_dVg * T5 + T6 * (dT2_dVg - dT1_dVg);
     dVdseff_dVd = dVdsat_dVd * T5 + T6 * (dT2_dVd - dT1_dVd);
@@ -470,17 +470,17 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
   // ---- velocity overshoot (:1443-1484)
   if (M_(lambda) > 0.0) {
     T1 = Leff * ueff;
-    T2 = S_(lambda) / T1;
-    T3 = -T2 / T1 * Leff;
+    T2 = B4_DIV(S_(lambda), T1);
+    T3 = B4_DIV(-T2, T1) * Leff;
     dT2_dVd = T3 * dueff_dVd; dT2_dVg = T3 * dueff_dVg; dT2_dVb = T3 * dueff_dVb;
-    T5 = 1.0 / (Esat * S_(litl));
-    T4 = -T5 / EsatL;
+    T5 = B4_DIV(1.0, (Esat * S_(litl)));
+    T4 = B4_DIV(-T5, EsatL);
     dT5_dVg = dEsatL_dVg * T4; dT5_dVd = dEsatL_dVd * T4; dT5_dVb = dEsatL_dVb * T4;
     T6 = 1.0 + diffVds * T5;
     dT6_dVg = dT5_dVg * diffVds - dVdseff_dVg * T5;
     dT6_dVd = dT5_dVd * diffVds + (1.0 - dVdseff_dVd) * T5;
     dT6_dVb = dT5_dVb * diffVds - dVdseff_dVb * T5;
-    T7 = 2.0 / (T6 * T6 + 1.0);
+    T7 = B4_DIV(2.0, (T6 * T6 + 1.0));
     T8 = 1.0 - T7;
     T9 = T6 * T7 * T7;
     dT8_dVg = T9 * dT6_dVg; dT8_dVd = T9 * dT6_dVd; dT8_dVb = T9 * dT6_dVb;
@@ -493,66 +493,66 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
     dEsatL_dVd *= T10; dEsatL_dVd += EsatL * dT10_dVd;
     dEsatL_dVb *= T10; dEsatL_dVb += EsatL * dT10_dVb;
     EsatL *= T10;
-    Esat = EsatL / Leff;
+    Esat = B4_DIV(EsatL, Leff);
   }
 
   // ---- Early voltage at saturation (:1486-1506)
-  tmp4 = 1.0 - 0.5 * Abulk * Vdsat / Vgst2Vtm;
+  tmp4 = 1.0 - B4_DIV(0.5 * Abulk * Vdsat, Vgst2Vtm);
   T9 = WVCoxRds * Vgsteff;
-  T8 = T9 / Vgst2Vtm;
+  T8 = B4_DIV(T9, Vgst2Vtm);
   T0 = EsatL + Vdsat + 2.0 * T9 * tmp4;
   T7 = 2.0 * WVCoxRds * tmp4;
-  dT0_dVg = dEsatL_dVg + dVdsat_dVg + T7 * (1.0 + tmp2 * Vgsteff) - T8 * (Abulk * dVdsat_dVg - Abulk * Vdsat / Vgst2Vtm + Vdsat * dAbulk_dVg);
+  dT0_dVg = dEsatL_dVg + dVdsat_dVg + T7 * (1.0 + tmp2 * Vgsteff) - T8 * (Abulk * dVdsat_dVg - B4_DIV(Abulk * Vdsat, Vgst2Vtm) + Vdsat * dAbulk_dVg);
   dT0_dVb = dEsatL_dVb + dVdsat_dVb + T7 * tmp3 * Vgsteff - T8 * (dAbulk_dVb * Vdsat + Abulk * dVdsat_dVb);
   dT0_dVd = dEsatL_dVd + dVdsat_dVd - T8 * Abulk * dVdsat_dVd;
   T9 = WVCoxRds * Abulk;
-  T1 = 2.0 / Lambda - 1.0 + T9;
+  T1 = B4_DIV(2.0, Lambda) - 1.0 + T9;
   dT1_dVg = -2.0 * tmp1 + WVCoxRds * (Abulk * tmp2 + dAbulk_dVg);
   dT1_dVb = dAbulk_dVb * WVCoxRds + T9 * tmp3;
-  const double Vasat = T0 / T1;
-  const double dVasat_dVg = (dT0_dVg - Vasat * dT1_dVg) / T1;
-  const double dVasat_dVb = (dT0_dVb - Vasat * dT1_dVb) / T1;
-  const double dVasat_dVd = dT0_dVd / T1;
+  const double Vasat = B4_DIV(T0, T1);
+  const double dVasat_dVg = B4_DIV((dT0_dVg - Vasat * dT1_dVg), T1);
+  const double dVasat_dVb = B4_DIV((dT0_dVb - Vasat * dT1_dVb), T1);
+  const double dVasat_dVd = B4_DIV(dT0_dVd, T1);
 
   // ---- linear-region current with the inversion-layer centroid correction (:1508-1559)
   tmp1 = I_(vtfbphi2);
   tmp2 = 2.0e8 * I_(toxp);
-  dT0_dVg = 1.0 / tmp2;
+  dT0_dVg = B4_DIV(1.0, tmp2);
   T0 = (Vgsteff + tmp1) * dT0_dVg;
   tmp3 = exp(M_(bdos) * 0.7 * log(T0));
   T1 = 1.0 + tmp3;
-  T2 = M_(bdos) * 0.7 * tmp3 / T0;
-  const double Tcen = M_(ados) * 1.9e-9 / T1;
-  const double dTcen_dVg = -Tcen * T2 * dT0_dVg / T1;
+  T2 = B4_DIV(M_(bdos) * 0.7 * tmp3, T0);
+  const double Tcen = B4_DIV(M_(ados) * 1.9e-9, T1);
+  const double dTcen_dVg = B4_DIV(-Tcen * T2 * dT0_dVg, T1);
   const double coxp = I_(coxp);
-  const double Coxeff = epssub * coxp / (epssub + coxp * Tcen);
-  const double dCoxeff_dVg = -Coxeff * Coxeff * dTcen_dVg / epssub;
-  const double CoxeffWovL = Coxeff * Weff / Leff;
+  const double Coxeff = B4_DIV(epssub * coxp, (epssub + coxp * Tcen));
+  const double dCoxeff_dVg = B4_DIV(-Coxeff * Coxeff * dTcen_dVg, epssub);
+  const double CoxeffWovL = B4_DIV(Coxeff * Weff, Leff);
   const double beta = ueff * CoxeffWovL;
-  T3 = ueff / Leff;
+  T3 = B4_DIV(ueff, Leff);
   const double dbeta_dVg = CoxeffWovL * dueff_dVg + T3 * (Weff * dCoxeff_dVg + Coxeff * dWeff_dVg);
   const double dbeta_dVd = CoxeffWovL * dueff_dVd;
   const double dbeta_dVb = CoxeffWovL * dueff_dVb + T3 * Coxeff * dWeff_dVb;
 
-  const double AbovVgst2Vtm = Abulk / Vgst2Vtm;
+  const double AbovVgst2Vtm = B4_DIV(Abulk, Vgst2Vtm);
   T0 = 1.0 - 0.5 * Vdseff * AbovVgst2Vtm;
-  dT0_dVg = -0.5 * (Abulk * dVdseff_dVg - Abulk * Vdseff / Vgst2Vtm + Vdseff * dAbulk_dVg) / Vgst2Vtm;
-  dT0_dVd = -0.5 * Abulk * dVdseff_dVd / Vgst2Vtm;
-  dT0_dVb = -0.5 * (Abulk * dVdseff_dVb + dAbulk_dVb * Vdseff) / Vgst2Vtm;
+  dT0_dVg = B4_DIV(-0.5 * (Abulk * dVdseff_dVg - B4_DIV(Abulk * Vdseff, Vgst2Vtm) + Vdseff * dAbulk_dVg), Vgst2Vtm);
+  dT0_dVd = B4_DIV(-0.5 * Abulk * dVdseff_dVd, Vgst2Vtm);
+  dT0_dVb = B4_DIV(-0.5 * (Abulk * dVdseff_dVb + dAbulk_dVb * Vdseff), Vgst2Vtm);
   const double fgche1 = Vgsteff * T0;
   const double dfgche1_dVg = Vgsteff * dT0_dVg + T0, dfgche1_dVd = Vgsteff * dT0_dVd, dfgche1_dVb = Vgsteff * dT0_dVb;
-  T9 = Vdseff / EsatL;
+  T9 = B4_DIV(Vdseff, EsatL);
   const double fgche2 = 1.0 + T9;
-  const double dfgche2_dVg = (dVdseff_dVg - T9 * dEsatL_dVg) / EsatL;
-  const double dfgche2_dVd = (dVdseff_dVd - T9 * dEsatL_dVd) / EsatL;
-  const double dfgche2_dVb = (dVdseff_dVb - T9 * dEsatL_dVb) / EsatL;
-  const double gche = beta * fgche1 / fgche2;
-  const double dgche_dVg = (beta * dfgche1_dVg + fgche1 * dbeta_dVg - gche * dfgche2_dVg) / fgche2;
-  const double dgche_dVd = (beta * dfgche1_dVd + fgche1 * dbeta_dVd - gche * dfgche2_dVd) / fgche2;
-  const double dgche_dVb = (beta * dfgche1_dVb + fgche1 * dbeta_dVb - gche * dfgche2_dVb) / fgche2;
+  const double dfgche2_dVg = B4_DIV((dVdseff_dVg - T9 * dEsatL_dVg), EsatL);
+  const double dfgche2_dVd = B4_DIV((dVdseff_dVd - T9 * dEsatL_dVd), EsatL);
+  const double dfgche2_dVb = B4_DIV((dVdseff_dVb - T9 * dEsatL_dVb), EsatL);
+  const double gche = B4_DIV(beta * fgche1, fgche2);
+  const double dgche_dVg = B4_DIV((beta * dfgche1_dVg + fgche1 * dbeta_dVg - gche * dfgche2_dVg), fgche2);
+  const double dgche_dVd = B4_DIV((beta * dfgche1_dVd + fgche1 * dbeta_dVd - gche * dfgche2_dVd), fgche2);
+  const double dgche_dVb = B4_DIV((beta * dfgche1_dVb + fgche1 * dbeta_dVb - gche * dfgche2_dVb), fgche2);
   T0 = 1.0 + gche * Rds;
-  const double Idl = gche / T0;
-  T1 = (1.0 - Idl * Rds) / T0;
+  const double Idl = B4_DIV(gche, T0);
+  T1 = B4_DIV((1.0 - Idl * Rds), T0);
   T2 = Idl * Idl;
   const double dIdl_dVg = T1 * dgche_dVg - T2 * dRds_dVg;
   const double dIdl_dVd = T1 * dgche_dVd;
@@ -562,24 +562,24 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
   double FP, dFP_dVg;
   if (S_(fprout) <= 0.0) { FP = 1.0; dFP_dVg = 0.0; }
   else {
-    T9 = S_(fprout) * sqrt(Leff) / Vgst2Vtm;
-    FP = 1.0 / (1.0 + T9);
-    dFP_dVg = FP * FP * T9 / Vgst2Vtm;
+    T9 = B4_DIV(S_(fprout) * sqrt(Leff), Vgst2Vtm);
+    FP = B4_DIV(1.0, (1.0 + T9));
+    dFP_dVg = B4_DIV(FP * FP * T9, Vgst2Vtm);
   }
-  T8 = S_(pvag) / EsatL;
+  T8 = B4_DIV(S_(pvag), EsatL);
   T9 = T8 * Vgsteff;
   double PvagTerm, dPvagTerm_dVg, dPvagTerm_dVd, dPvagTerm_dVb;
   if (T9 > -0.9) {
     PvagTerm = 1.0 + T9;
-    dPvagTerm_dVg = T8 * (1.0 - Vgsteff * dEsatL_dVg / EsatL);
-    dPvagTerm_dVb = -T9 * dEsatL_dVb / EsatL;
-    dPvagTerm_dVd = -T9 * dEsatL_dVd / EsatL;
+    dPvagTerm_dVg = T8 * (1.0 - B4_DIV(Vgsteff * dEsatL_dVg, EsatL));
+    dPvagTerm_dVb = B4_DIV(-T9 * dEsatL_dVb, EsatL);
+    dPvagTerm_dVd = B4_DIV(-T9 * dEsatL_dVd, EsatL);
   } else {
-    T4 = 1.0 / (17.0 + 20.0 * T9);
+    T4 = B4_DIV(1.0, (17.0 + 20.0 * T9));
     PvagTerm = (0.8 + T9) * T4;
     T4 *= T4;
-    dPvagTerm_dVg = T8 * (1.0 - Vgsteff * dEsatL_dVg / EsatL) * T4;
-    T9 *= T4 / EsatL;
+    dPvagTerm_dVg = T8 * (1.0 - B4_DIV(Vgsteff * dEsatL_dVg, EsatL)) * T4;
+    T9 *= B4_DIV(T4, EsatL);
     dPvagTerm_dVb = -T9 * dEsatL_dVb;
     dPvagTerm_dVd = -T9 * dEsatL_dVd;
   }
@@ -589,15 +589,15 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
     dT0_dVg = dRds_dVg * Idl + Rds * dIdl_dVg;
     dT0_dVd = Rds * dIdl_dVd;
     dT0_dVb = dRds_dVb * Idl + Rds * dIdl_dVb;
-    T2 = Vdsat / Esat;
+    T2 = B4_DIV(Vdsat, Esat);
     T1 = Leff + T2;
-    dT1_dVg = (dVdsat_dVg - T2 * dEsatL_dVg / Leff) / Esat;
-    dT1_dVd = (dVdsat_dVd - T2 * dEsatL_dVd / Leff) / Esat;
-    dT1_dVb = (dVdsat_dVb - T2 * dEsatL_dVb / Leff) / Esat;
-    Cclm = FP * PvagTerm * T0 * T1 / (S_(pclm) * S_(litl));
-    dCclm_dVg = Cclm * (dFP_dVg / FP + dPvagTerm_dVg / PvagTerm + dT0_dVg / T0 + dT1_dVg / T1);
-    dCclm_dVb = Cclm * (dPvagTerm_dVb / PvagTerm + dT0_dVb / T0 + dT1_dVb / T1);
-    dCclm_dVd = Cclm * (dPvagTerm_dVd / PvagTerm + dT0_dVd / T0 + dT1_dVd / T1);
+    dT1_dVg = B4_DIV((dVdsat_dVg - B4_DIV(T2 * dEsatL_dVg, Leff)), Esat);
+    dT1_dVd = B4_DIV((dVdsat_dVd - B4_DIV(T2 * dEsatL_dVd, Leff)), Esat);
+    dT1_dVb = B4_DIV((dVdsat_dVb - B4_DIV(T2 * dEsatL_dVb, Leff)), Esat);
+    Cclm = B4_DIV(FP * PvagTerm * T0 * T1, (S_(pclm) * S_(litl)));
+    dCclm_dVg = Cclm * (B4_DIV(dFP_dVg, FP) + B4_DIV(dPvagTerm_dVg, PvagTerm) + B4_DIV(dT0_dVg, T0) + B4_DIV(dT1_dVg, T1));
+    dCclm_dVb = Cclm * (B4_DIV(dPvagTerm_dVb, PvagTerm) + B4_DIV(dT0_dVb, T0) + B4_DIV(dT1_dVb, T1));
+    dCclm_dVd = Cclm * (B4_DIV(dPvagTerm_dVd, PvagTerm) + B4_DIV(dT0_dVd, T0) + B4_DIV(dT1_dVd, T1));
     VACLM = Cclm * diffVds;
     dVACLM_dVg = dCclm_dVg * diffVds - dVdseff_dVg * Cclm;
     dVACLM_dVb = dCclm_dVb * diffVds - dVdseff_dVb * Cclm;
@@ -620,19 +620,19 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
     dT1_dVd = Abulk * dVdsat_dVd;
     T9 = T1 * T1;
     T2 = S_(thetaRout);
-    VADIBL = (Vgst2Vtm - T0 / T1) / T2;
-    dVADIBL_dVg = (1.0 - dT0_dVg / T1 + T0 * dT1_dVg / T9) / T2;
-    dVADIBL_dVb = (-dT0_dVb / T1 + T0 * dT1_dVb / T9) / T2;
-    dVADIBL_dVd = (-dT0_dVd / T1 + T0 * dT1_dVd / T9) / T2;
+    VADIBL = B4_DIV((Vgst2Vtm - B4_DIV(T0, T1)), T2);
+    dVADIBL_dVg = B4_DIV((1.0 - B4_DIV(dT0_dVg, T1) + B4_DIV(T0 * dT1_dVg, T9)), T2);
+    dVADIBL_dVb = B4_DIV((B4_DIV(-dT0_dVb, T1) + B4_DIV(T0 * dT1_dVb, T9)), T2);
+    dVADIBL_dVd = B4_DIV((B4_DIV(-dT0_dVd, T1) + B4_DIV(T0 * dT1_dVd, T9)), T2);
     T7 = S_(pdiblb) * Vbseff;
     if (T7 >= -0.9) {
-      T3 = 1.0 / (1.0 + T7);
+      T3 = B4_DIV(1.0, (1.0 + T7));
       VADIBL *= T3;
       dVADIBL_dVg *= T3;
       dVADIBL_dVb = (dVADIBL_dVb - VADIBL * S_(pdiblb)) * T3;
       dVADIBL_dVd *= T3;
     } else {
-      T4 = 1.0 / (0.8 + T7);
+      T4 = B4_DIV(1.0, (0.8 + T7));
       T3 = (17.0 + 20.0 * T7) * T4;
       dVADIBL_dVg *= T3;
       dVADIBL_dVb = dVADIBL_dVb * T3 - VADIBL * S_(pdiblb) * T4 * T4;
@@ -656,49 +656,49 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
   else { T1 = exp(T0); dT1_dVd = T1 * S_(pditsd); }
   if (S_(pdits) > B4C_MIN_EXP) {
     T2 = 1.0 + M_(pditsl) * Leff;
-    VADITS = (1.0 + T2 * T1) / S_(pdits);
+    VADITS = B4_DIV((1.0 + T2 * T1), S_(pdits));
     dVADITS_dVg = VADITS * dFP_dVg;
-    dVADITS_dVd = FP * T2 * dT1_dVd / S_(pdits);
+    dVADITS_dVd = B4_DIV(FP * T2 * dT1_dVd, S_(pdits));
     VADITS *= FP;
   } else {
     VADITS = B4C_MAX_EXP; dVADITS_dVg = 0.0; dVADITS_dVd = 0.0;
   }
   double VASCBE = B4C_MAX_EXP, dVASCBE_dVg = 0.0, dVASCBE_dVd = 0.0, dVASCBE_dVb = 0.0;
   if (S_(pscbe2) > 0.0 && S_(pscbe1) >= 0.0) {
-    if (diffVds > S_(pscbe1) * S_(litl) / B4C_EXP_THRESHOLD) {
-      T0 = S_(pscbe1) * S_(litl) / diffVds;
-      VASCBE = Leff * exp(T0) / S_(pscbe2);
-      T1 = T0 * VASCBE / diffVds;
+    if (diffVds > B4_DIV(S_(pscbe1) * S_(litl), B4C_EXP_THRESHOLD)) {
+      T0 = B4_DIV(S_(pscbe1) * S_(litl), diffVds);
+      VASCBE = B4_DIV(Leff * exp(T0), S_(pscbe2));
+      T1 = B4_DIV(T0 * VASCBE, diffVds);
       dVASCBE_dVg = T1 * dVdseff_dVg;
       dVASCBE_dVd = -T1 * (1.0 - dVdseff_dVd);
       dVASCBE_dVb = T1 * dVdseff_dVb;
     } else {
-      VASCBE = B4C_MAX_EXP * Leff / S_(pscbe2);
+      VASCBE = B4_DIV(B4C_MAX_EXP * Leff, S_(pscbe2));
     }
   }
 
   // ---- assemble Ids/Vdseff with DIBL, DITS and CLM (:1734-1764)
-  T9 = diffVds / VADIBL;
+  T9 = B4_DIV(diffVds, VADIBL);
   T0 = 1.0 + T9;
   double Idsa = Idl * T0;
-  double dIdsa_dVg = T0 * dIdl_dVg - Idl * (dVdseff_dVg + T9 * dVADIBL_dVg) / VADIBL;
-  double dIdsa_dVd = T0 * dIdl_dVd + Idl * (1.0 - dVdseff_dVd - T9 * dVADIBL_dVd) / VADIBL;
-  double dIdsa_dVb = T0 * dIdl_dVb - Idl * (dVdseff_dVb + T9 * dVADIBL_dVb) / VADIBL;
-  T9 = diffVds / VADITS;
+  double dIdsa_dVg = T0 * dIdl_dVg - B4_DIV(Idl * (dVdseff_dVg + T9 * dVADIBL_dVg), VADIBL);
+  double dIdsa_dVd = T0 * dIdl_dVd + B4_DIV(Idl * (1.0 - dVdseff_dVd - T9 * dVADIBL_dVd), VADIBL);
+  double dIdsa_dVb = T0 * dIdl_dVb - B4_DIV(Idl * (dVdseff_dVb + T9 * dVADIBL_dVb), VADIBL);
+  T9 = B4_DIV(diffVds, VADITS);
   T0 = 1.0 + T9;
-  dIdsa_dVg = T0 * dIdsa_dVg - Idsa * (dVdseff_dVg + T9 * dVADITS_dVg) / VADITS;
-  dIdsa_dVd = T0 * dIdsa_dVd + Idsa * (1.0 - dVdseff_dVd - T9 * dVADITS_dVd) / VADITS;
-  dIdsa_dVb = T0 * dIdsa_dVb - Idsa * dVdseff_dVb / VADITS;
+  dIdsa_dVg = T0 * dIdsa_dVg - B4_DIV(Idsa * (dVdseff_dVg + T9 * dVADITS_dVg), VADITS);
+  dIdsa_dVd = T0 * dIdsa_dVd + B4_DIV(Idsa * (1.0 - dVdseff_dVd - T9 * dVADITS_dVd), VADITS);
+  dIdsa_dVb = T0 * dIdsa_dVb - B4_DIV(Idsa * dVdseff_dVb, VADITS);
   Idsa *= T0;
-  T0 = log(Va / Vasat);
-  dT0_dVg = dVa_dVg / Va - dVasat_dVg / Vasat;
-  dT0_dVb = dVa_dVb / Va - dVasat_dVb / Vasat;
-  dT0_dVd = dVa_dVd / Va - dVasat_dVd / Vasat;
-  T1 = T0 / Cclm;
+  T0 = log(B4_DIV(Va, Vasat));
+  dT0_dVg = B4_DIV(dVa_dVg, Va) - B4_DIV(dVasat_dVg, Vasat);
+  dT0_dVb = B4_DIV(dVa_dVb, Va) - B4_DIV(dVasat_dVb, Vasat);
+  dT0_dVd = B4_DIV(dVa_dVd, Va) - B4_DIV(dVasat_dVd, Vasat);
+  T1 = B4_DIV(T0, Cclm);
   T9 = 1.0 + T1;
-  dT9_dVg = (dT0_dVg - T1 * dCclm_dVg) / Cclm;
-  dT9_dVb = (dT0_dVb - T1 * dCclm_dVb) / Cclm;
-  dT9_dVd = (dT0_dVd - T1 * dCclm_dVd) / Cclm;
+  dT9_dVg = B4_DIV((dT0_dVg - T1 * dCclm_dVg), Cclm);
+  dT9_dVb = B4_DIV((dT0_dVb - T1 * dCclm_dVb), Cclm);
+  dT9_dVd = B4_DIV((dT0_dVd - T1 * dCclm_dVd), Cclm);
   dIdsa_dVg = dIdsa_dVg * T9 + Idsa * dT9_dVg;
   dIdsa_dVb = dIdsa_dVb * T9 + Idsa * dT9_dVb;
   dIdsa_dVd = dIdsa_dVd * T9 + Idsa * dT9_dVd;
@@ -710,11 +710,11 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
   if (tmp <= 0.0 || S_(beta0) <= 0.0) {
     Isub = 0.0; Gbd = 0.0; Gbb = 0.0; Gbg = 0.0;
   } else {
-    T2 = tmp / Leff;
-    if (diffVds > S_(beta0) / B4C_EXP_THRESHOLD) {
-      T0 = -S_(beta0) / diffVds;
+    T2 = B4_DIV(tmp, Leff);
+    if (diffVds > B4_DIV(S_(beta0), B4C_EXP_THRESHOLD)) {
+      T0 = B4_DIV(-S_(beta0), diffVds);
       T1 = T2 * diffVds * exp(T0);
-      T3 = T1 / diffVds * (T0 - 1.0);
+      T3 = B4_DIV(T1, diffVds) * (T0 - 1.0);
       dT1_dVg = T3 * dVdseff_dVg;
       dT1_dVd = T3 * (dVdseff_dVd - 1.0);
       dT1_dVb = T3 * dVdseff_dVb;
@@ -738,12 +738,12 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
   o.csub = Isub; o.gbbs = Gbb; o.gbgs = Gbg; o.gbds = Gbd;
 
   // ---- SCBE, chain rule to terminal voltages, drain current (:1805-1868)
-  T9 = diffVds / VASCBE;
+  T9 = B4_DIV(diffVds, VASCBE);
   T0 = 1.0 + T9;
   const double Ids = Idsa * T0;
-  double Gm = T0 * dIdsa_dVg - Idsa * (dVdseff_dVg + T9 * dVASCBE_dVg) / VASCBE;
-  double Gds = T0 * dIdsa_dVd + Idsa * (1.0 - dVdseff_dVd - T9 * dVASCBE_dVd) / VASCBE;
-  double Gmb = T0 * dIdsa_dVb - Idsa * (dVdseff_dVb + T9 * dVASCBE_dVb) / VASCBE;
+  double Gm = T0 * dIdsa_dVg - B4_DIV(Idsa * (dVdseff_dVg + T9 * dVASCBE_dVg), VASCBE);
+  double Gds = T0 * dIdsa_dVd + B4_DIV(Idsa * (1.0 - dVdseff_dVd - T9 * dVASCBE_dVd), VASCBE);
+  double Gmb = T0 * dIdsa_dVb - B4_DIV(Idsa * (dVdseff_dVb + T9 * dVASCBE_dVb), VASCBE);
   tmp1 = Gds + Gm * dVgsteff_dVd;
   tmp2 = Gmb + Gm * dVgsteff_dVb;
   tmp3 = Gm;
@@ -753,20 +753,20 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
   double cdrain = Ids * Vdseff;
 
   if (M_(vtl_given) != 0.0 && M_(vtl) > 0.0) {  // source-end velocity limit
-    T12 = 1.0 / Leff / CoxeffWovL;
-    T11 = T12 / Vgsteff;
-    T10 = -T11 / Vgsteff;
+    T12 = B4_DIV(B4_DIV(1.0, Leff), CoxeffWovL);
+    T11 = B4_DIV(T12, Vgsteff);
+    T10 = B4_DIV(-T11, Vgsteff);
     const double vs = cdrain * T11;
     const double dvs_dVg = Gm * T11 + cdrain * T10 * dVgsteff_dVg;
     const double dvs_dVd = Gds * T11 + cdrain * T10 * dVgsteff_dVd;
     const double dvs_dVb = Gmb * T11 + cdrain * T10 * dVgsteff_dVb;
     T0 = 6.0;
-    T1 = vs / (S_(vtl) * S_(tfactor));
+    T1 = B4_DIV(vs, (S_(vtl) * S_(tfactor)));
     if (T1 > 0.0) {
       T2 = 1.0 + exp(T0 * log(T1));
-      T3 = (T2 - 1.0) * T0 / vs;
-      const double Fsevl = 1.0 / exp(log(T2) / T0);
-      T4 = -1.0 / T0 * Fsevl / T2;
+      T3 = B4_DIV((T2 - 1.0) * T0, vs);
+      const double Fsevl = B4_DIV(1.0, exp(B4_DIV(log(T2), T0)));
+      T4 = B4_DIV(B4_DIV(-1.0, T0) * Fsevl, T2);
       const double dFsevl_dVg = T4 * (T3 * dvs_dVg), dFsevl_dVd = T4 * (T3 * dvs_dVd), dFsevl_dVb = T4 * (T3 * dvs_dVb);
       Gm *= Fsevl;  Gm += cdrain * dFsevl_dVg;
       Gmb *= Fsevl; Gmb += cdrain * dFsevl_dVb;
@@ -794,8 +794,8 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
       const double grgeltd = I_(grgeltd);
       T10 = grgeltd * grgeltd;
       T11 = grgeltd + o.gcrg;
-      o.gcrg = grgeltd * o.gcrg / T11;
-      T12 = T10 / T11 / T11;
+      o.gcrg = B4_DIV(grgeltd * o.gcrg, T11);
+      T12 = B4_DIV(B4_DIV(T10, T11), T11);
       o.gcrgg *= T12; o.gcrgd *= T12; o.gcrgb *= T12;
     }
     o.gcrgs = -(o.gcrgg + o.gcrgd + o.gcrgb);
@@ -808,21 +808,21 @@ template <class E> B4_HD void b4_channel_dc(E& e, const B4Bias& v, B4Op& o, B4Ch
       double t0 = vg - vfbsd;
       double t1 = sqrt(t0 * t0 + 1.0e-4);
       const double vg_eff = 0.5 * (t0 + t1);
-      const double dvg_eff = vg_eff / t1;
+      const double dvg_eff = B4_DIV(vg_eff, t1);
       t0 = 1.0 + prwg * vg_eff;
-      const double dt0_dvg = -prwg / t0 / t0 * dvg_eff;
+      const double dt0_dvg = B4_DIV(B4_DIV(-prwg, t0), t0) * dvg_eff;
       t1 = -prwb * vb;
       const double dt1_dvb = -prwb;
-      const double t2 = 1.0 / t0 + t1;
+      const double t2 = B4_DIV(1.0, t0) + t1;
       const double t3 = t2 + sqrt(t2 * t2 + 0.01);
-      const double dt3_dvg = t3 / (t3 - t2);
+      const double dt3_dvg = B4_DIV(t3, (t3 - t2));
       const double dt3_dvb = dt3_dvg * dt1_dvb;
       const double dt3_dvg2 = dt3_dvg * dt0_dvg;
       const double t4 = r0 * 0.5;
       const double R = rmin + t3 * t4;
       const double dR_dvg = t4 * dt3_dvg2, dR_dvb = t4 * dt3_dvb;
       t0 = 1.0 + gend * R;
-      *gtot = gend / t0;
+      *gtot = B4_DIV(gend, t0);
       t0 = -*gtot * *gtot;
       *dg_dvg = t0 * dR_dvg;
       *dg_dvb = t0 * dR_dvb;

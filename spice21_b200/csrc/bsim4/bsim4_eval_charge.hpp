@@ -13,10 +13,10 @@ struct B4VgsteffCV { double v, dVg, dVd, dVb; };
 // depletion charge and capacitance of one junction component (bottom, sidewall or gate-edge sidewall), reverse bias
 B4_HD void b4_jct_component(double cz, double phi, double mj, double vj, bool first, double* q, double* cap) {
   if (cz > 0.0) {
-    const double arg = 1.0 - vj / phi;
-    const double sarg = mj == 0.5 ? 1.0 / sqrt(arg) : exp(-mj * log(arg));
-    if (first) { *q = phi * cz * (1.0 - arg * sarg) / (1.0 - mj); *cap = cz * sarg; }
-    else { *q += phi * cz * (1.0 - arg * sarg) / (1.0 - mj); *cap += cz * sarg; }
+    const double arg = 1.0 - B4_DIV(vj, phi);
+    const double sarg = mj == 0.5 ? B4_DIV(1.0, sqrt(arg)) : exp(-mj * log(arg));
+    if (first) { *q = B4_DIV(phi * cz * (1.0 - arg * sarg), (1.0 - mj)); *cap = cz * sarg; }
+    else { *q += B4_DIV(phi * cz * (1.0 - arg * sarg), (1.0 - mj)); *cap += cz * sarg; }
   } else if (first) {
     *q = 0.0;
     *cap = 0.0;
@@ -33,7 +33,7 @@ B4_HD void b4_junction_charge(double vj, double cz, double czsw, double czswg, d
     b4_jct_component(czswg, phiswg, mjswg, vj, false, q, cap);
   } else {
     const double T0 = cz + czsw + czswg;
-    const double T1 = vj * (cz * mj / phi + czsw * mjsw / phisw + czswg * mjswg / phiswg);
+    const double T1 = vj * (B4_DIV(cz * mj, phi) + B4_DIV(czsw * mjsw, phisw) + B4_DIV(czswg * mjswg, phiswg));
     *q = vj * (T0 + 0.5 * T1);
     *cap = T0 + T1;
   }
@@ -44,8 +44,8 @@ B4_HD void b4_overlap(double vg, double cov, double weffCV, double cl, double ck
   const double T1 = sqrt(T0 * T0 + 4.0 * B4C_DELTA_1);
   const double T2 = 0.5 * (T0 - T1);
   const double T3 = weffCV * cl;
-  const double T4 = sqrt(1.0 - 4.0 * T2 / ckappa);
-  *c = cov + T3 - T3 * (1.0 - 1.0 / T4) * (0.5 - 0.5 * T0 / T1);
+  const double T4 = sqrt(1.0 - B4_DIV(4.0 * T2, ckappa));
+  *c = cov + T3 - T3 * (1.0 - B4_DIV(1.0, T4)) * (0.5 - B4_DIV(0.5 * T0, T1));
   *q = (cov + T3) * vg - T3 * (T2 + 0.5 * ckappa * (T4 - 1.0));
 }
 
@@ -95,7 +95,7 @@ template <class E> B4_HD void b4_charge(E& e, const B4Bias& v, B4Op& o, const B4
         qgate = CoxWL * k1ox * (T2 - T1);
         qbulk = -qgate;
         qdrn = 0.0;
-        T0 = CoxWL * T1 / T2;
+        T0 = B4_DIV(CoxWL * T1, T2);
         o.cggb = T0 * dVgs_eff_dVg;
         o.cgdb = 0.0;
         o.cgsb = T0 * (dVbseffCV_dVb - dVgs_eff_dVg);
@@ -104,16 +104,16 @@ template <class E> B4_HD void b4_charge(E& e, const B4Bias& v, B4Op& o, const B4
         o.cbdb = 0.0;
         o.cbsb = -o.cgsb;
       } else {  // inversion
-        const double One_Third_CoxWL = CoxWL / 3.0;
+        const double One_Third_CoxWL = B4_DIV(CoxWL, 3.0);
         const double Two_Third_CoxWL = 2.0 * One_Third_CoxWL;
         const double AbulkCV = Abulk0 * abulkCVfactor;
         const double dAbulkCV_dVb = abulkCVfactor * dAbulk0_dVb * dVbseff_dVb;
-        const double dVdsat_dVg = 1.0 / AbulkCV;
+        const double dVdsat_dVg = B4_DIV(1.0, AbulkCV);
         const double Vdsat = Vgst * dVdsat_dVg;
         const double dVdsat_dVb = -(Vdsat * dAbulkCV_dVb + dVth_dVb) * dVdsat_dVg;
         const bool saturated = xpart > 0.5 ? Vdsat <= Vds : Vds >= Vdsat;
         if (saturated) {
-          T1 = Vdsat / 3.0;
+          T1 = B4_DIV(Vdsat, 3.0);
           qgate = CoxWL * (Vgs_eff - Vfb - phi - T1);
           T2 = -Two_Third_CoxWL * Vgst;
           qbulk = -(qgate + T2);
@@ -143,14 +143,14 @@ template <class E> B4_HD void b4_charge(E& e, const B4Bias& v, B4Op& o, const B4
           o.cbsb = -(o.cbgb + T3);
           o.cbdb = 0.0;
         } else {  // linear region
-          const double Alphaz = Vgst / Vdsat;
+          const double Alphaz = B4_DIV(Vgst, Vdsat);
           T1 = 2.0 * Vdsat - Vds;
-          T2 = Vds / (3.0 * T1);
+          T2 = B4_DIV(Vds, (3.0 * T1));
           T3 = T2 * Vds;
           T9 = 0.25 * CoxWL;
           T4 = T9 * Alphaz;
           qgate = CoxWL * (Vgs_eff - Vfb - phi - 0.5 * (Vds - T3));
-          T5 = T3 / T1;
+          T5 = B4_DIV(T3, T1);
           o.cggb = CoxWL * (1.0 - T5 * dVdsat_dVg) * dVgs_eff_dVg;
           o.cgdb = CoxWL * (T2 - 0.5 + 0.5 * T5);
           if (xpart > 0.5) {  // 0/100
@@ -161,7 +161,7 @@ template <class E> B4_HD void b4_charge(E& e, const B4Bias& v, B4Op& o, const B4
             qbulk = -(qgate + qdrn + T10);
             T11 = -CoxWL * T5 * dVdsat_dVb;
             o.cgsb = -(o.cggb + T11 + o.cgdb);
-            T6 = 1.0 / Vdsat;
+            T6 = B4_DIV(1.0, Vdsat);
             const double dAlphaz_dVg = T6 * (1.0 - Alphaz * dVdsat_dVg);
             const double dAlphaz_dVb = -T6 * (dVth_dVb + Alphaz * dVdsat_dVb);
             T7 = T9 * T7;
@@ -182,19 +182,19 @@ template <class E> B4_HD void b4_charge(E& e, const B4Bias& v, B4Op& o, const B4
           } else if (xpart < 0.5) {  // 40/60
             tmp = -CoxWL * T5 * dVdsat_dVb;
             o.cgsb = -(o.cggb + o.cgdb + tmp);
-            T6 = 1.0 / Vdsat;
+            T6 = B4_DIV(1.0, Vdsat);
             const double dAlphaz_dVg = T6 * (1.0 - Alphaz * dVdsat_dVg);
             const double dAlphaz_dVb = -T6 * (dVth_dVb + Alphaz * dVdsat_dVb);
             T6 = 8.0 * Vdsat * Vdsat - 6.0 * Vdsat * Vds + 1.2 * Vds * Vds;
-            T8 = T2 / T1;
+            T8 = B4_DIV(T2, T1);
             T7 = Vds - T1 - T8 * T6;
             qdrn = T4 * T7;
             T7 *= T9;
-            tmp = T8 / T1;
+            tmp = B4_DIV(T8, T1);
             tmp1 = T4 * (2.0 - 4.0 * tmp * T6 + T8 * (16.0 * Vdsat - 6.0 * Vds));
             o.cdgb = (T7 * dAlphaz_dVg - tmp1 * dVdsat_dVg) * dVgs_eff_dVg;
             T10 = T7 * dAlphaz_dVb - tmp1 * dVdsat_dVb;
-            o.cddb = T4 * (2.0 - (1.0 / (3.0 * T1 * T1) + 2.0 * tmp) * T6 + T8 * (6.0 * Vdsat - 2.4 * Vds));
+            o.cddb = T4 * (2.0 - (B4_DIV(1.0, (3.0 * T1 * T1)) + 2.0 * tmp) * T6 + T8 * (6.0 * Vdsat - 2.4 * Vds));
             o.cdsb = -(o.cdgb + T10 + o.cddb);
             T7 = 2.0 * (T1 + T3);
             qbulk = -(qgate - T4 * T7);
@@ -210,7 +210,7 @@ template <class E> B4_HD void b4_charge(E& e, const B4Bias& v, B4Op& o, const B4
           } else {  // 50/50
             tmp = -CoxWL * T5 * dVdsat_dVb;
             o.cgsb = -(o.cggb + o.cgdb + tmp);
-            T6 = 1.0 / Vdsat;
+            T6 = B4_DIV(1.0, Vdsat);
             const double dAlphaz_dVg = T6 * (1.0 - Alphaz * dVdsat_dVg);
             const double dAlphaz_dVb = -T6 * (dVth_dVb + Alphaz * dVdsat_dVb);
             T7 = T1 + T3;
@@ -240,22 +240,22 @@ template <class E> B4_HD void b4_charge(E& e, const B4Bias& v, B4Op& o, const B4
         const double dnoff_dVd = S_(noff) * dn_dVd, dnoff_dVb = S_(noff) * dn_dVb;
         T0 = Vtm * noff;
         const double voffcv = S_(voffcv);
-        const double VgstNVt = (Vgst - voffcv) / T0;
+        const double VgstNVt = B4_DIV((Vgst - voffcv), T0);
         if (VgstNVt > B4C_EXP_THRESHOLD) {
           Vgsteff = Vgst - voffcv;
           dVgsteff_dVg = dVgs_eff_dVg; dVgsteff_dVd = -dVth_dVd; dVgsteff_dVb = -dVth_dVb;
         } else if (VgstNVt < -B4C_EXP_THRESHOLD) {
           Vgsteff = T0 * log(1.0 + B4C_MIN_EXP);
           dVgsteff_dVg = 0.0;
-          dVgsteff_dVd = Vgsteff / noff;
+          dVgsteff_dVd = B4_DIV(Vgsteff, noff);
           dVgsteff_dVb = dVgsteff_dVd * dnoff_dVb;
           dVgsteff_dVd *= dnoff_dVd;
         } else {
           const double ExpVgst = exp(VgstNVt);
           Vgsteff = T0 * log(1.0 + ExpVgst);
-          dVgsteff_dVg = ExpVgst / (1.0 + ExpVgst);
-          dVgsteff_dVd = -dVgsteff_dVg * (dVth_dVd + (Vgst - voffcv) / noff * dnoff_dVd) + Vgsteff / noff * dnoff_dVd;
-          dVgsteff_dVb = -dVgsteff_dVg * (dVth_dVb + (Vgst - voffcv) / noff * dnoff_dVb) + Vgsteff / noff * dnoff_dVb;
+          dVgsteff_dVg = B4_DIV(ExpVgst, (1.0 + ExpVgst));
+          dVgsteff_dVd = -dVgsteff_dVg * (dVth_dVd + B4_DIV((Vgst - voffcv), noff) * dnoff_dVd) + B4_DIV(Vgsteff, noff) * dnoff_dVd;
+          dVgsteff_dVb = -dVgsteff_dVg * (dVth_dVb + B4_DIV((Vgst - voffcv), noff) * dnoff_dVb) + B4_DIV(Vgsteff, noff) * dnoff_dVb;
           dVgsteff_dVg *= dVgs_eff_dVg;
         }
       } else {
@@ -263,7 +263,7 @@ template <class E> B4_HD void b4_charge(E& e, const B4Bias& v, B4Op& o, const B4
         double dT10_dVg, dT10_dVd, dT10_dVb, dT9_dVg, dT9_dVd, dT9_dVb;
         T0 = n * Vtm;
         T1 = mstarcv * Vgst;
-        T2 = T1 / T0;
+        T2 = B4_DIV(T1, T0);
         if (T2 > B4C_EXP_THRESHOLD) {
           T10 = T1;
           dT10_dVg = mstarcv * dVgs_eff_dVg; dT10_dVd = -dVth_dVd * mstarcv; dT10_dVb = -dVth_dVb * mstarcv;
@@ -275,44 +275,44 @@ template <class E> B4_HD void b4_charge(E& e, const B4Bias& v, B4Op& o, const B4
           const double ExpVgst = exp(T2);
           T3 = Vtm * log(1.0 + ExpVgst);
           T10 = n * T3;
-          dT10_dVg = mstarcv * ExpVgst / (1.0 + ExpVgst);
-          dT10_dVb = T3 * dn_dVb - dT10_dVg * (dVth_dVb + Vgst * dn_dVb / n);
-          dT10_dVd = T3 * dn_dVd - dT10_dVg * (dVth_dVd + Vgst * dn_dVd / n);
+          dT10_dVg = B4_DIV(mstarcv * ExpVgst, (1.0 + ExpVgst));
+          dT10_dVb = T3 * dn_dVb - dT10_dVg * (dVth_dVb + B4_DIV(Vgst * dn_dVb, n));
+          dT10_dVd = T3 * dn_dVd - dT10_dVg * (dVth_dVd + B4_DIV(Vgst * dn_dVd, n));
           dT10_dVg *= dVgs_eff_dVg;
         }
         T1 = S_(voffcbncv) - (1.0 - mstarcv) * Vgst;
-        T2 = T1 / T0;
+        T2 = B4_DIV(T1, T0);
         if (T2 < -B4C_EXP_THRESHOLD) {
-          T3 = coxe * B4C_MIN_EXP / S_(cdep0);
+          T3 = B4_DIV(coxe * B4C_MIN_EXP, S_(cdep0));
           T9 = mstarcv + T3 * n;
           dT9_dVg = 0.0; dT9_dVd = dn_dVd * T3; dT9_dVb = dn_dVb * T3;
         } else if (T2 > B4C_EXP_THRESHOLD) {
-          T3 = coxe * B4C_MAX_EXP / S_(cdep0);
+          T3 = B4_DIV(coxe * B4C_MAX_EXP, S_(cdep0));
           T9 = mstarcv + T3 * n;
           dT9_dVg = 0.0; dT9_dVd = dn_dVd * T3; dT9_dVb = dn_dVb * T3;
         } else {
           const double ExpVgst = exp(T2);
-          T3 = coxe / S_(cdep0);
+          T3 = B4_DIV(coxe, S_(cdep0));
           T4 = T3 * ExpVgst;
-          T5 = T1 * T4 / T0;
+          T5 = B4_DIV(T1 * T4, T0);
           T9 = mstarcv + n * T4;
-          dT9_dVg = T3 * (mstarcv - 1.0) * ExpVgst / Vtm;
+          dT9_dVg = B4_DIV(T3 * (mstarcv - 1.0) * ExpVgst, Vtm);
           dT9_dVb = T4 * dn_dVb - dT9_dVg * dVth_dVb - T5 * dn_dVb;
           dT9_dVd = T4 * dn_dVd - dT9_dVg * dVth_dVd - T5 * dn_dVd;
           dT9_dVg *= dVgs_eff_dVg;
         }
-        Vgsteff = T10 / T9;
+        Vgsteff = B4_DIV(T10, T9);
         T11 = T9 * T9;
-        dVgsteff_dVg = (T9 * dT10_dVg - T10 * dT9_dVg) / T11;
-        dVgsteff_dVd = (T9 * dT10_dVd - T10 * dT9_dVd) / T11;
-        dVgsteff_dVb = (T9 * dT10_dVb - T10 * dT9_dVb) / T11;
+        dVgsteff_dVg = B4_DIV((T9 * dT10_dVg - T10 * dT9_dVg), T11);
+        dVgsteff_dVd = B4_DIV((T9 * dT10_dVd - T10 * dT9_dVd), T11);
+        dVgsteff_dVb = B4_DIV((T9 * dT10_dVb - T10 * dT9_dVb), T11);
       }
 
       // effective flat band (accumulation charge) — common to capmod 1 and 2
       const double vfbzb = I_(vfbzb);
       const double V3 = vfbzb - Vgs_eff + VbseffCV - B4C_DELTA_3;
       T0 = vfbzb <= 0.0 ? sqrt(V3 * V3 - 4.0 * B4C_DELTA_3 * vfbzb) : sqrt(V3 * V3 + 4.0 * B4C_DELTA_3 * vfbzb);
-      T1 = 0.5 * (1.0 + V3 / T0);
+      T1 = 0.5 * (1.0 + B4_DIV(V3, T0));
       const double Vfbeff = vfbzb - 0.5 * (V3 + T0);
       const double dVfbeff_dVg = T1 * dVgs_eff_dVg;
       const double dVfbeff_dVb = -T1 * dVbseffCV_dVb;
@@ -329,20 +329,20 @@ template <class E> B4_HD void b4_charge(E& e, const B4Bias& v, B4Op& o, const B4
         T0 = 0.5 * k1ox;
         T3 = Vgs_eff - Vfbeff - VbseffCV - Vgsteff;
         if (k1ox == 0.0) { T1 = 0.0; T2 = 0.0; }
-        else if (T3 < 0.0) { T1 = T0 + T3 / k1ox; T2 = CoxWL; }
-        else { T1 = sqrt(T0 * T0 + T3); T2 = CoxWL * T0 / T1; }
+        else if (T3 < 0.0) { T1 = T0 + B4_DIV(T3, k1ox); T2 = CoxWL; }
+        else { T1 = sqrt(T0 * T0 + T3); T2 = B4_DIV(CoxWL * T0, T1); }
         Qsub0 = CoxWL * k1ox * (T1 - T0);
         dQsub0_dVg = T2 * (dVgs_eff_dVg - dVfbeff_dVg - dVgsteff_dVg);
         dQsub0_dVd = -T2 * dVgsteff_dVd;
         dQsub0_dVb = -T2 * (dVfbeff_dVb + dVbseffCV_dVb + dVgsteff_dVb);
 
-        const double VdsatCV = Vgsteff / AbulkCV;
+        const double VdsatCV = B4_DIV(Vgsteff, AbulkCV);
         T0 = VdsatCV - Vds - B4C_DELTA_4;
-        dT0_dVg = 1.0 / AbulkCV;
-        dT0_dVb = -VdsatCV * dAbulkCV_dVb / AbulkCV;
+        dT0_dVg = B4_DIV(1.0, AbulkCV);
+        dT0_dVb = B4_DIV(-VdsatCV * dAbulkCV_dVb, AbulkCV);
         T1 = sqrt(T0 * T0 + 4.0 * B4C_DELTA_4 * VdsatCV);
-        dT1_dVg = (T0 + B4C_DELTA_4 + B4C_DELTA_4) / T1;
-        dT1_dVd = -T0 / T1;
+        dT1_dVg = B4_DIV((T0 + B4C_DELTA_4 + B4C_DELTA_4), T1);
+        dT1_dVd = B4_DIV(-T0, T1);
         dT1_dVb = dT1_dVg * dT0_dVb;
         dT1_dVg *= dT0_dVg;
         if (T0 >= 0.0) {
@@ -351,9 +351,9 @@ template <class E> B4_HD void b4_charge(E& e, const B4Bias& v, B4Op& o, const B4
           dVdseffCV_dVd = 0.5 * (1.0 - dT1_dVd);
           dVdseffCV_dVb = 0.5 * (dT0_dVb - dT1_dVb);
         } else {
-          T3 = (B4C_DELTA_4 + B4C_DELTA_4) / (T1 - T0);
+          T3 = B4_DIV((B4C_DELTA_4 + B4C_DELTA_4), (T1 - T0));
           T4 = 1.0 - T3;
-          T5 = VdsatCV * T3 / (T1 - T0);
+          T5 = B4_DIV(VdsatCV * T3, (T1 - T0));
           VdseffCV = VdsatCV * T4;
           dVdseffCV_dVg = dT0_dVg * T4 + T5 * (dT1_dVg - dT0_dVg);
           dVdseffCV_dVd = T5 * (dT1_dVd + 1.0);
@@ -363,10 +363,10 @@ template <class E> B4_HD void b4_charge(E& e, const B4Bias& v, B4Op& o, const B4
 
         T0 = AbulkCV * VdseffCV;
         T1 = 12.0 * (Vgsteff - 0.5 * T0 + 1.0e-20);
-        T2 = VdseffCV / T1;
+        T2 = B4_DIV(VdseffCV, T1);
         T3 = T0 * T2;
         T4 = (1.0 - 12.0 * T2 * T2 * AbulkCV);
-        T5 = (6.0 * T0 * (4.0 * Vgsteff - T0) / (T1 * T1) - 0.5);
+        T5 = (B4_DIV(6.0 * T0 * (4.0 * Vgsteff - T0), (T1 * T1)) - 0.5);
         T6 = 12.0 * T2 * T2 * Vgsteff;
         qgate = CoxWL * (Vgsteff - 0.5 * VdseffCV + T3);
         Cgg1 = CoxWL * (T4 + T5 * dVdseffCV_dVg);
@@ -384,9 +384,9 @@ template <class E> B4_HD void b4_charge(E& e, const B4Bias& v, B4Op& o, const B4
         Cbg1 *= dVgsteff_dVg;
         if (xpart > 0.5) {
           T1 = T1 + T1;
-          qsrc = -CoxWL * (0.5 * Vgsteff + 0.25 * T0 - T0 * T0 / T1);
-          T7 = (4.0 * Vgsteff - T0) / (T1 * T1);
-          T4 = -(0.5 + 24.0 * T0 * T0 / (T1 * T1));
+          qsrc = -CoxWL * (0.5 * Vgsteff + 0.25 * T0 - B4_DIV(T0 * T0, T1));
+          T7 = B4_DIV((4.0 * Vgsteff - T0), (T1 * T1));
+          T4 = -(0.5 + B4_DIV(24.0 * T0 * T0, (T1 * T1)));
           T5 = -(0.25 * AbulkCV - 12.0 * AbulkCV * T0 * T7);
           T6 = -(0.25 * VdseffCV - 12.0 * T0 * VdseffCV * T7);
           Csg = CoxWL * (T4 + T5 * dVdseffCV_dVg);
@@ -394,14 +394,14 @@ template <class E> B4_HD void b4_charge(E& e, const B4Bias& v, B4Op& o, const B4
           Csb = CoxWL * (T5 * dVdseffCV_dVb + T6 * dAbulkCV_dVb) + Csg * dVgsteff_dVb;
           Csg *= dVgsteff_dVg;
         } else if (xpart < 0.5) {
-          T1 = T1 / 12.0;
-          T2 = 0.5 * CoxWL / (T1 * T1);
-          T3 = Vgsteff * (2.0 * T0 * T0 / 3.0 + Vgsteff * (Vgsteff - 4.0 * T0 / 3.0)) - 2.0 * T0 * T0 * T0 / 15.0;
+          T1 = B4_DIV(T1, 12.0);
+          T2 = B4_DIV(0.5 * CoxWL, (T1 * T1));
+          T3 = Vgsteff * (B4_DIV(2.0 * T0 * T0, 3.0) + Vgsteff * (Vgsteff - B4_DIV(4.0 * T0, 3.0))) - B4_DIV(2.0 * T0 * T0 * T0, 15.0);
           qsrc = -T2 * T3;
-          T7 = 4.0 / 3.0 * Vgsteff * (Vgsteff - T0) + 0.4 * T0 * T0;
-          T4 = -2.0 * qsrc / T1 - T2 * (Vgsteff * (3.0 * Vgsteff - 8.0 * T0 / 3.0) + 2.0 * T0 * T0 / 3.0);
-          T5 = (qsrc / T1 + T2 * T7) * AbulkCV;
-          T6 = (qsrc / T1 * VdseffCV + T2 * T7 * VdseffCV);
+          T7 = B4_DIV(4.0, 3.0) * Vgsteff * (Vgsteff - T0) + 0.4 * T0 * T0;
+          T4 = B4_DIV(-2.0 * qsrc, T1) - T2 * (Vgsteff * (3.0 * Vgsteff - B4_DIV(8.0 * T0, 3.0)) + B4_DIV(2.0 * T0 * T0, 3.0));
+          T5 = (B4_DIV(qsrc, T1) + T2 * T7) * AbulkCV;
+          T6 = (B4_DIV(qsrc, T1) * VdseffCV + T2 * T7 * VdseffCV);
           Csg = (T4 + T5 * dVdseffCV_dVg);
           Csd = T5 * dVdseffCV_dVd + Csg * dVgsteff_dVd;
           Csb = (T5 * dVdseffCV_dVb + T6 * dAbulkCV_dVb) + Csg * dVgsteff_dVb;
@@ -425,9 +425,9 @@ template <class E> B4_HD void b4_charge(E& e, const B4Bias& v, B4Op& o, const B4
         // charge-thickness model: finite inversion/accumulation layer thickness lowers the effective oxide capacitance
         const double Cox = I_(coxp);
         double Tox = 1.0e8 * I_(toxp);
-        T0 = (Vgs_eff - VbseffCV - vfbzb) / Tox;
-        dT0_dVg = dVgs_eff_dVg / Tox;
-        dT0_dVb = -dVbseffCV_dVb / Tox;
+        T0 = B4_DIV((Vgs_eff - VbseffCV - vfbzb), Tox);
+        dT0_dVg = B4_DIV(dVgs_eff_dVg, Tox);
+        dT0_dVb = B4_DIV(-dVbseffCV_dVb, Tox);
         const double ldeb = S_(ldeb), acde = S_(acde);
         tmp = T0 * acde;
         double Tcen, dTcen_dVg, dTcen_dVb;
@@ -445,28 +445,28 @@ template <class E> B4_HD void b4_charge(E& e, const B4Bias& v, B4Op& o, const B4
         const double V3c = ldeb - Tcen - LINK;
         const double V4c = sqrt(V3c * V3c + 4.0 * LINK * ldeb);
         Tcen = ldeb - 0.5 * (V3c + V4c);
-        T1 = 0.5 * (1.0 + V3c / V4c);
+        T1 = 0.5 * (1.0 + B4_DIV(V3c, V4c));
         dTcen_dVg *= T1;
         dTcen_dVb *= T1;
-        double Ccen = epssub / Tcen;
-        T2 = Cox / (Cox + Ccen);
+        double Ccen = B4_DIV(epssub, Tcen);
+        T2 = B4_DIV(Cox, (Cox + Ccen));
         double Coxeff = T2 * Ccen;
-        T3 = -Ccen / Tcen;
+        T3 = B4_DIV(-Ccen, Tcen);
         double dCoxeff_base = T2 * T2 * T3;
         double dCoxeff_dVb = dCoxeff_base * dTcen_dVb;
         double dCoxeff_dVg = dCoxeff_base * dTcen_dVg;
-        double CoxWLcen = CoxWL * Coxeff / coxe;
+        double CoxWLcen = B4_DIV(CoxWL * Coxeff, coxe);
         Qac0 = CoxWLcen * (Vfbeff - vfbzb);
-        double QovCox = Qac0 / Coxeff;
+        double QovCox = B4_DIV(Qac0, Coxeff);
         dQac0_dVg = CoxWLcen * dVfbeff_dVg + QovCox * dCoxeff_dVg;
         dQac0_dVb = CoxWLcen * dVfbeff_dVb + QovCox * dCoxeff_dVb;
         T0 = 0.5 * k1ox;
         T3 = Vgs_eff - Vfbeff - VbseffCV - Vgsteff;
         if (k1ox == 0.0) { T1 = 0.0; T2 = 0.0; }
-        else if (T3 < 0.0) { T1 = T0 + T3 / k1ox; T2 = CoxWLcen; }
-        else { T1 = sqrt(T0 * T0 + T3); T2 = CoxWLcen * T0 / T1; }
+        else if (T3 < 0.0) { T1 = T0 + B4_DIV(T3, k1ox); T2 = CoxWLcen; }
+        else { T1 = sqrt(T0 * T0 + T3); T2 = B4_DIV(CoxWLcen * T0, T1); }
         Qsub0 = CoxWLcen * k1ox * (T1 - T0);
-        QovCox = Qsub0 / Coxeff;
+        QovCox = B4_DIV(Qsub0, Coxeff);
         dQsub0_dVg = T2 * (dVgs_eff_dVg - dVfbeff_dVg - dVgsteff_dVg) + QovCox * dCoxeff_dVg;
         dQsub0_dVd = -T2 * dVgsteff_dVd;
         dQsub0_dVb = -T2 * (dVfbeff_dVb + dVbseffCV_dVb + dVgsteff_dVb) + QovCox * dCoxeff_dVb;
@@ -476,42 +476,42 @@ template <class E> B4_HD void b4_charge(E& e, const B4Bias& v, B4Op& o, const B4
         if (k1ox <= 0.0) { Denomi = 0.25 * S_(moin) * Vtm; T0 = 0.5 * S_(sqrtPhi); }
         else { Denomi = S_(moin) * Vtm * k1ox * k1ox; T0 = k1ox * S_(sqrtPhi); }
         T1 = 2.0 * T0 + Vgsteff;
-        const double DeltaPhi = Vtm * log(1.0 + T1 * Vgsteff / Denomi);
-        const double dDeltaPhi_dVg = 2.0 * Vtm * (T1 - T0) / (Denomi + T1 * Vgsteff);
+        const double DeltaPhi = Vtm * log(1.0 + B4_DIV(T1 * Vgsteff, Denomi));
+        const double dDeltaPhi_dVg = B4_DIV(2.0 * Vtm * (T1 - T0), (Denomi + T1 * Vgsteff));
         T0 = Vgsteff - DeltaPhi - 0.001;
         dT0_dVg = 1.0 - dDeltaPhi_dVg;
         T1 = sqrt(T0 * T0 + Vgsteff * 0.004);
         const double VgDP = 0.5 * (T0 + T1);
-        const double dVgDP_dVg = 0.5 * (dT0_dVg + (T0 * dT0_dVg + 0.002) / T1);
+        const double dVgDP_dVg = 0.5 * (dT0_dVg + B4_DIV((T0 * dT0_dVg + 0.002), T1));
 
         // inversion-layer centroid
         Tox += Tox;
-        T0 = (Vgsteff + I_(vtfbphi2)) / Tox;
+        T0 = B4_DIV((Vgsteff + I_(vtfbphi2)), Tox);
         tmp = exp(M_(bdos) * 0.7 * log(T0));
         T1 = 1.0 + tmp;
-        T2 = M_(bdos) * 0.7 * tmp / (T0 * Tox);
-        Tcen = M_(ados) * 1.9e-9 / T1;
-        dTcen_dVg = -Tcen * T2 / T1;
+        T2 = B4_DIV(M_(bdos) * 0.7 * tmp, (T0 * Tox));
+        Tcen = B4_DIV(M_(ados) * 1.9e-9, T1);
+        dTcen_dVg = B4_DIV(-Tcen * T2, T1);
         const double dTcen_dVd = dTcen_dVg * dVgsteff_dVd;
         dTcen_dVb = dTcen_dVg * dVgsteff_dVb;
         dTcen_dVg *= dVgsteff_dVg;
-        Ccen = epssub / Tcen;
-        T0 = Cox / (Cox + Ccen);
+        Ccen = B4_DIV(epssub, Tcen);
+        T0 = B4_DIV(Cox, (Cox + Ccen));
         Coxeff = T0 * Ccen;
-        T1 = -Ccen / Tcen;
+        T1 = B4_DIV(-Ccen, Tcen);
         dCoxeff_base = T0 * T0 * T1;
         const double dCoxeff_dVd = dCoxeff_base * dTcen_dVd;
         dCoxeff_dVb = dCoxeff_base * dTcen_dVb;
         dCoxeff_dVg = dCoxeff_base * dTcen_dVg;
-        CoxWLcen = CoxWL * Coxeff / coxe;
+        CoxWLcen = B4_DIV(CoxWL * Coxeff, coxe);
 
-        const double VdsatCV = VgDP / AbulkCV;
+        const double VdsatCV = B4_DIV(VgDP, AbulkCV);
         T0 = VdsatCV - Vds - B4C_DELTA_4;
-        dT0_dVg = dVgDP_dVg / AbulkCV;
-        dT0_dVb = -VdsatCV * dAbulkCV_dVb / AbulkCV;
+        dT0_dVg = B4_DIV(dVgDP_dVg, AbulkCV);
+        dT0_dVb = B4_DIV(-VdsatCV * dAbulkCV_dVb, AbulkCV);
         T1 = sqrt(T0 * T0 + 4.0 * B4C_DELTA_4 * VdsatCV);
-        dT1_dVg = (T0 + B4C_DELTA_4 + B4C_DELTA_4) / T1;
-        dT1_dVd = -T0 / T1;
+        dT1_dVg = B4_DIV((T0 + B4C_DELTA_4 + B4C_DELTA_4), T1);
+        dT1_dVd = B4_DIV(-T0, T1);
         dT1_dVb = dT1_dVg * dT0_dVb;
         dT1_dVg *= dT0_dVg;
         if (T0 >= 0.0) {
@@ -520,9 +520,9 @@ template <class E> B4_HD void b4_charge(E& e, const B4Bias& v, B4Op& o, const B4
           dVdseffCV_dVd = 0.5 * (1.0 - dT1_dVd);
           dVdseffCV_dVb = 0.5 * (dT0_dVb - dT1_dVb);
         } else {
-          T3 = (B4C_DELTA_4 + B4C_DELTA_4) / (T1 - T0);
+          T3 = B4_DIV((B4C_DELTA_4 + B4C_DELTA_4), (T1 - T0));
           T4 = 1.0 - T3;
-          T5 = VdsatCV * T3 / (T1 - T0);
+          T5 = B4_DIV(VdsatCV * T3, (T1 - T0));
           VdseffCV = VdsatCV * T4;
           dVdseffCV_dVg = dT0_dVg * T4 + T5 * (dT1_dVg - dT0_dVg);
           dVdseffCV_dVd = T5 * (dT1_dVd + 1.0);
@@ -533,35 +533,35 @@ template <class E> B4_HD void b4_charge(E& e, const B4Bias& v, B4Op& o, const B4
         T0 = AbulkCV * VdseffCV;
         T1 = VgDP;
         T2 = 12.0 * (T1 - 0.5 * T0 + 1.0e-20);
-        T3 = T0 / T2;
+        T3 = B4_DIV(T0, T2);
         T4 = 1.0 - 12.0 * T3 * T3;
-        T5 = AbulkCV * (6.0 * T0 * (4.0 * T1 - T0) / (T2 * T2) - 0.5);
-        T6 = T5 * VdseffCV / AbulkCV;
+        T5 = AbulkCV * (B4_DIV(6.0 * T0 * (4.0 * T1 - T0), (T2 * T2)) - 0.5);
+        T6 = B4_DIV(T5 * VdseffCV, AbulkCV);
         qgate = CoxWLcen * (T1 - T0 * (0.5 - T3));
-        QovCox = qgate / Coxeff;
+        QovCox = B4_DIV(qgate, Coxeff);
         Cgg1 = CoxWLcen * (T4 * dVgDP_dVg + T5 * dVdseffCV_dVg);
         Cgd1 = CoxWLcen * T5 * dVdseffCV_dVd + Cgg1 * dVgsteff_dVd + QovCox * dCoxeff_dVd;
         Cgb1 = CoxWLcen * (T5 * dVdseffCV_dVb + T6 * dAbulkCV_dVb) + Cgg1 * dVgsteff_dVb + QovCox * dCoxeff_dVb;
         Cgg1 = Cgg1 * dVgsteff_dVg + QovCox * dCoxeff_dVg;
         T7 = 1.0 - AbulkCV;
         T8 = T2 * T2;
-        T9 = 12.0 * T7 * T0 * T0 / (T8 * AbulkCV);
+        T9 = B4_DIV(12.0 * T7 * T0 * T0, (T8 * AbulkCV));
         T10 = T9 * dVgDP_dVg;
-        T11 = -T7 * T5 / AbulkCV;
-        T12 = -(T9 * T1 / AbulkCV + VdseffCV * (0.5 - T0 / T2));
-        qbulk = CoxWLcen * T7 * (0.5 * VdseffCV - T0 * VdseffCV / T2);
-        QovCox = qbulk / Coxeff;
+        T11 = B4_DIV(-T7 * T5, AbulkCV);
+        T12 = -(B4_DIV(T9 * T1, AbulkCV) + VdseffCV * (0.5 - B4_DIV(T0, T2)));
+        qbulk = CoxWLcen * T7 * (0.5 * VdseffCV - B4_DIV(T0 * VdseffCV, T2));
+        QovCox = B4_DIV(qbulk, Coxeff);
         Cbg1 = CoxWLcen * (T10 + T11 * dVdseffCV_dVg);
         Cbd1 = CoxWLcen * T11 * dVdseffCV_dVd + Cbg1 * dVgsteff_dVd + QovCox * dCoxeff_dVd;
         Cbb1 = CoxWLcen * (T11 * dVdseffCV_dVb + T12 * dAbulkCV_dVb) + Cbg1 * dVgsteff_dVb + QovCox * dCoxeff_dVb;
         Cbg1 = Cbg1 * dVgsteff_dVg + QovCox * dCoxeff_dVg;
         if (xpart > 0.5) {
-          qsrc = -CoxWLcen * (T1 / 2.0 + T0 / 4.0 - 0.5 * T0 * T0 / T2);
-          QovCox = qsrc / Coxeff;
+          qsrc = -CoxWLcen * (B4_DIV(T1, 2.0) + B4_DIV(T0, 4.0) - B4_DIV(0.5 * T0 * T0, T2));
+          QovCox = B4_DIV(qsrc, Coxeff);
           T2 += T2;
           T3 = T2 * T2;
-          T7 = -(0.25 - 12.0 * T0 * (4.0 * T1 - T0) / T3);
-          T4 = -(0.5 + 24.0 * T0 * T0 / T3) * dVgDP_dVg;
+          T7 = -(0.25 - B4_DIV(12.0 * T0 * (4.0 * T1 - T0), T3));
+          T4 = -(0.5 + B4_DIV(24.0 * T0 * T0, T3)) * dVgDP_dVg;
           T5 = T7 * AbulkCV;
           T6 = T7 * VdseffCV;
           Csg = CoxWLcen * (T4 + T5 * dVdseffCV_dVg);
@@ -569,15 +569,15 @@ template <class E> B4_HD void b4_charge(E& e, const B4Bias& v, B4Op& o, const B4
           Csb = CoxWLcen * (T5 * dVdseffCV_dVb + T6 * dAbulkCV_dVb) + Csg * dVgsteff_dVb + QovCox * dCoxeff_dVb;
           Csg = Csg * dVgsteff_dVg + QovCox * dCoxeff_dVg;
         } else if (xpart < 0.5) {
-          T2 = T2 / 12.0;
-          T3 = 0.5 * CoxWLcen / (T2 * T2);
-          T4 = T1 * (2.0 * T0 * T0 / 3.0 + T1 * (T1 - 4.0 * T0 / 3.0)) - 2.0 * T0 * T0 * T0 / 15.0;
+          T2 = B4_DIV(T2, 12.0);
+          T3 = B4_DIV(0.5 * CoxWLcen, (T2 * T2));
+          T4 = T1 * (B4_DIV(2.0 * T0 * T0, 3.0) + T1 * (T1 - B4_DIV(4.0 * T0, 3.0))) - B4_DIV(2.0 * T0 * T0 * T0, 15.0);
           qsrc = -T3 * T4;
-          QovCox = qsrc / Coxeff;
-          T8 = 4.0 / 3.0 * T1 * (T1 - T0) + 0.4 * T0 * T0;
-          T5 = -2.0 * qsrc / T2 - T3 * (T1 * (3.0 * T1 - 8.0 * T0 / 3.0) + 2.0 * T0 * T0 / 3.0);
-          T6 = AbulkCV * (qsrc / T2 + T3 * T8);
-          T7 = T6 * VdseffCV / AbulkCV;
+          QovCox = B4_DIV(qsrc, Coxeff);
+          T8 = B4_DIV(4.0, 3.0) * T1 * (T1 - T0) + 0.4 * T0 * T0;
+          T5 = B4_DIV(-2.0 * qsrc, T2) - T3 * (T1 * (3.0 * T1 - B4_DIV(8.0 * T0, 3.0)) + B4_DIV(2.0 * T0 * T0, 3.0));
+          T6 = AbulkCV * (B4_DIV(qsrc, T2) + T3 * T8);
+          T7 = B4_DIV(T6 * VdseffCV, AbulkCV);
           Csg = T5 * dVgDP_dVg + T6 * dVdseffCV_dVg;
           Csd = Csg * dVgsteff_dVd + T6 * dVdseffCV_dVd + QovCox * dCoxeff_dVd;
           Csb = Csg * dVgsteff_dVb + T6 * dVdseffCV_dVb + T7 * dAbulkCV_dVb + QovCox * dCoxeff_dVb;
@@ -639,7 +639,7 @@ template <class E> B4_HD void b4_charge(E& e, const B4Bias& v, B4Op& o, const B4
   // ---- NQS time constant (:3629-3635)
   if (trnqsmod != 0) {
     const double CoxWL = coxe * S_(weffCV) * nf * S_(leffCV);
-    T1 = o.gcrg / CoxWL;
+    T1 = B4_DIV(o.gcrg, CoxWL);
     o.gtau = T1 * 1.0e-9;
   } else {
     o.gtau = 0.0;

@@ -11,17 +11,17 @@ B4_HD void b4_edge_leak(bool legacy, int mtrlmod, const B4EdgeLeakPar& p, double
                         double dvg_eff_dvg, double vb, double* I, double* Gd, double* Gg, double* Gb) {
   double T1, T2, T3, T4, T5, T6, T7, T8;
   if (legacy) {
-    T1 = mtrlmod == 0 ? (vde - vg_eff - p.e) / T0 : (vde - vg_eff - p.e + vfbsd) / T0;
+    T1 = mtrlmod == 0 ? B4_DIV((vde - vg_eff - p.e), T0) : B4_DIV((vde - vg_eff - p.e + vfbsd), T0);
     if (p.a <= 0.0 || p.b <= 0.0 || T1 <= 0.0 || p.c <= 0.0 || vb > 0.0) {
       *I = 0.0; *Gd = 0.0; *Gg = 0.0; *Gb = 0.0;
       return;
     }
-    const double dT1_dVd = 1.0 / T0;
+    const double dT1_dVd = B4_DIV(1.0, T0);
     const double dT1_dVg = -dvg_eff_dvg * dT1_dVd;
-    T2 = p.b / T1;
+    T2 = B4_DIV(p.b, T1);
     if (T2 < 100.0) {
       *I = p.a * weffCJ * T1 * exp(-T2);
-      T3 = *I * (1.0 + T2) / T1;
+      T3 = B4_DIV(*I * (1.0 + T2), T1);
       *Gd = T3 * dT1_dVd;
       *Gg = T3 * dT1_dVg;
     } else {
@@ -33,25 +33,25 @@ B4_HD void b4_edge_leak(bool legacy, int mtrlmod, const B4EdgeLeakPar& p, double
     T4 = vb * vb;
     T5 = -vb * T4;
     T6 = p.c + T5;
-    T7 = T5 / T6;
-    T8 = 3.0 * p.c * T4 / T6 / T6;
+    T7 = B4_DIV(T5, T6);
+    T8 = B4_DIV(B4_DIV(3.0 * p.c * T4, T6), T6);
     *Gd = *Gd * T7 + *I * T8;
     *Gg = *Gg * T7;
     *Gb = -*I * T8;
     *I *= T7;
     return;
   }
-  T1 = mtrlmod == 0 ? (vde - p.r * vg_eff - p.e) / T0 : (vde - p.r * vg_eff - p.e + vfbsd) / T0;
+  T1 = mtrlmod == 0 ? B4_DIV((vde - p.r * vg_eff - p.e), T0) : B4_DIV((vde - p.r * vg_eff - p.e + vfbsd), T0);
   if (p.a <= 0.0 || p.b <= 0.0 || T1 <= 0.0 || p.c < 0.0) {
     *I = 0.0; *Gd = 0.0; *Gg = 0.0; *Gb = 0.0;
     return;
   }
-  const double dT1_dVd = 1.0 / T0;
+  const double dT1_dVd = B4_DIV(1.0, T0);
   const double dT1_dVg = -p.r * dT1_dVd * dvg_eff_dvg;
-  T2 = p.b / T1;
+  T2 = B4_DIV(p.b, T1);
   if (T2 < B4C_EXPL_THRESHOLD) {
     *I = weffCJ * p.a * T1 * exp(-T2);
-    T3 = *I / T1 * (T2 + 1.0);
+    T3 = B4_DIV(*I, T1) * (T2 + 1.0);
     *Gd = T3 * dT1_dVd;
     *Gg = T3 * dT1_dVg;
   } else {
@@ -61,10 +61,10 @@ B4_HD void b4_edge_leak(bool legacy, int mtrlmod, const B4EdgeLeakPar& p, double
     *Gg = T3 * dT1_dVg;
   }
   T4 = vb - p.f;
-  T5 = T4 == 0.0 ? B4C_EXPL_THRESHOLD : p.k / T4;
+  T5 = T4 == 0.0 ? B4C_EXPL_THRESHOLD : B4_DIV(p.k, T4);
   if (T5 < B4C_EXPL_THRESHOLD) {
     T6 = exp(T5);
-    *Gb = -*I * T6 * T5 / T4;
+    *Gb = B4_DIV(-*I * T6 * T5, T4);
   } else {
     T6 = B4C_MAX_EXPL;
     *Gb = 0.0;
@@ -92,7 +92,7 @@ template <class E> B4_HD void b4_leakage(E& e, const B4Bias& v, B4Op& o, B4Chan&
   double dT9_dVg, dT9_dVd, dT9_dVb, dT10_dVg, dT10_dVd, dT10_dVb;
 
   // ---- GIDL / GISL (:1987-2187)
-  T0 = mtrlmod == 0 ? 3.0 * toxe : M_(epsrsub) * toxe / M_(epsrox);
+  T0 = mtrlmod == 0 ? 3.0 * toxe : B4_DIV(M_(epsrsub) * toxe, M_(epsrox));
   {
     const bool legacy = (int)M_(gidlmod) == 0;
     const double vfbsd = S_(vfbsd), weffCJ = S_(weffCJ);
@@ -113,7 +113,7 @@ template <class E> B4_HD void b4_leakage(E& e, const B4Bias& v, B4Op& o, B4Chan&
     t.Vfb = Vfb;
     const double V3 = Vfb - Vgs_eff + Vbseff - B4C_DELTA_3;
     T0 = Vfb <= 0.0 ? sqrt(V3 * V3 - 4.0 * B4C_DELTA_3 * Vfb) : sqrt(V3 * V3 + 4.0 * B4C_DELTA_3 * Vfb);
-    T1 = 0.5 * (1.0 + V3 / T0);
+    T1 = 0.5 * (1.0 + B4_DIV(V3, T0));
     const double Vfbeff = Vfb - 0.5 * (V3 + T0);
     const double dVfbeff_dVg = T1 * dVgs_eff_dVg;
     const double dVfbeff_dVb = -T1;
@@ -133,7 +133,7 @@ template <class E> B4_HD void b4_leakage(E& e, const B4Bias& v, B4Op& o, B4Chan&
       t.dVoxdepinv_dVb = dVfbeff_dVb + 1.0 + dVgsteff_dVb;
     } else {
       T1 = sqrt(T0 * T0 + T3);
-      T2 = T0 / T1;
+      T2 = B4_DIV(T0, T1);
       t.Voxdepinv = k1ox * (T1 - T0);
       t.dVoxdepinv_dVg = T2 * (dVgs_eff_dVg - dVfbeff_dVg - dVgsteff_dVg);
       t.dVoxdepinv_dVd = -T2 * dVgsteff_dVd;
@@ -153,10 +153,10 @@ template <class E> B4_HD void b4_leakage(E& e, const B4Bias& v, B4Op& o, B4Chan&
     T0 = vt_tun * S_(nigc);
     double VxNVt;
     if (igcmod == 1) {
-      VxNVt = (Vgs_eff - tp * I_(vth0)) / T0;
+      VxNVt = B4_DIV((Vgs_eff - tp * I_(vth0)), T0);
       if (VxNVt > B4C_EXP_THRESHOLD) { Vaux = Vgs_eff - tp * I_(vth0); dVaux_dVg = dVgs_eff_dVg; dVaux_dVd = 0.0; dVaux_dVb = 0.0; }
     } else {
-      VxNVt = (Vgs_eff - o.von) / T0;
+      VxNVt = B4_DIV((Vgs_eff - o.von), T0);
       if (VxNVt > B4C_EXP_THRESHOLD) { Vaux = Vgs_eff - o.von; dVaux_dVg = dVgs_eff_dVg; dVaux_dVd = -c.dVth_dVd; dVaux_dVb = -c.dVth_dVb; }
     }
     if (VxNVt < -B4C_EXP_THRESHOLD) {
@@ -165,7 +165,7 @@ template <class E> B4_HD void b4_leakage(E& e, const B4Bias& v, B4Op& o, B4Chan&
     } else if (VxNVt >= -B4C_EXP_THRESHOLD && VxNVt <= B4C_EXP_THRESHOLD) {
       const double ExpVxNVt = exp(VxNVt);
       Vaux = T0 * log(1.0 + ExpVxNVt);
-      dVaux_dVg = ExpVxNVt / (1.0 + ExpVxNVt);
+      dVaux_dVg = B4_DIV(ExpVxNVt, (1.0 + ExpVxNVt));
       if (igcmod == 1) { dVaux_dVd = 0.0; dVaux_dVb = 0.0; }
       else { dVaux_dVd = -dVaux_dVg * c.dVth_dVd; dVaux_dVb = -dVaux_dVg * c.dVth_dVb; }
       dVaux_dVg *= dVgs_eff_dVg;
@@ -194,10 +194,10 @@ template <class E> B4_HD void b4_leakage(E& e, const B4Bias& v, B4Op& o, B4Chan&
     } else {
       T11 = -S_(Bechvb);
       T12 = Vgsteff + 1.0e-20;
-      T13 = T11 / T12 / T12;
-      T14 = -T13 / T12;
-      Pigcd = T13 * (1.0 - 0.5 * Vdseff / T12);
-      dPigcd_dVg = T14 * (2.0 + 0.5 * (dVdseff_dVg - 3.0 * Vdseff / T12));
+      T13 = B4_DIV(B4_DIV(T11, T12), T12);
+      T14 = B4_DIV(-T13, T12);
+      Pigcd = T13 * (1.0 - B4_DIV(0.5 * Vdseff, T12));
+      dPigcd_dVg = T14 * (2.0 + 0.5 * (dVdseff_dVg - B4_DIV(3.0 * Vdseff, T12)));
       dPigcd_dVd = 0.5 * T14 * dVdseff_dVd;
       dPigcd_dVb = 0.5 * T14 * dVdseff_dVb;
     }
@@ -215,19 +215,19 @@ template <class E> B4_HD void b4_leakage(E& e, const B4Bias& v, B4Op& o, B4Chan&
     else if (T7 < -B4C_EXP_THRESHOLD) { T9 = B4C_MIN_EXP; dT9_dVg = 0.0; dT9_dVd = 0.0; dT9_dVb = 0.0; }
     else { T9 = exp(T7); dT9_dVg = T9 * dT7_dVg; dT9_dVd = T9 * dT7_dVd; dT9_dVb = T9 * dT7_dVb; }
     T1 = T9 - 1.0 + 1.0e-4;
-    T10 = (T1 - T7) / T8;
-    dT10_dVg = (dT9_dVg - dT7_dVg - T10 * dT8_dVg) / T8;
-    dT10_dVd = (dT9_dVd - dT7_dVd - T10 * dT8_dVd) / T8;
-    dT10_dVb = (dT9_dVb - dT7_dVb - T10 * dT8_dVb) / T8;
+    T10 = B4_DIV((T1 - T7), T8);
+    dT10_dVg = B4_DIV((dT9_dVg - dT7_dVg - T10 * dT8_dVg), T8);
+    dT10_dVd = B4_DIV((dT9_dVd - dT7_dVd - T10 * dT8_dVd), T8);
+    dT10_dVb = B4_DIV((dT9_dVb - dT7_dVb - T10 * dT8_dVb), T8);
     o.Igcs = Igc * T10;
     o.gIgcsg = dIgc_dVg * T10 + Igc * dT10_dVg;
     o.gIgcsd = dIgc_dVd * T10 + Igc * dT10_dVd;
     o.gIgcsb = (dIgc_dVb * T10 + Igc * dT10_dVb) * dVbseff_dVb;
     T1 = T9 - 1.0 - 1.0e-4;
-    T10 = (T7 * T9 - T1) / T8;
-    dT10_dVg = (dT7_dVg * T9 + (T7 - 1.0) * dT9_dVg - T10 * dT8_dVg) / T8;
-    dT10_dVd = (dT7_dVd * T9 + (T7 - 1.0) * dT9_dVd - T10 * dT8_dVd) / T8;
-    dT10_dVb = (dT7_dVb * T9 + (T7 - 1.0) * dT9_dVb - T10 * dT8_dVb) / T8;
+    T10 = B4_DIV((T7 * T9 - T1), T8);
+    dT10_dVg = B4_DIV((dT7_dVg * T9 + (T7 - 1.0) * dT9_dVg - T10 * dT8_dVg), T8);
+    dT10_dVd = B4_DIV((dT7_dVd * T9 + (T7 - 1.0) * dT9_dVd - T10 * dT8_dVd), T8);
+    dT10_dVb = B4_DIV((dT7_dVb * T9 + (T7 - 1.0) * dT9_dVb - T10 * dT8_dVb), T8);
     o.Igcd = Igc * T10;
     o.gIgcdg = dIgc_dVg * T10 + Igc * dT10_dVg;
     o.gIgcdd = dIgc_dVd * T10 + Igc * dT10_dVd;
@@ -239,7 +239,7 @@ template <class E> B4_HD void b4_leakage(E& e, const B4Bias& v, B4Op& o, B4Chan&
     {
       T0 = v.vgs - vfbsd_tot;
       const double vgs_eff = sqrt(T0 * T0 + 1.0e-4);
-      const double dvgs_eff_dvg = T0 / vgs_eff;
+      const double dvgs_eff_dvg = B4_DIV(T0, vgs_eff);
       T2 = v.vgs * vgs_eff;
       dT2_dVg = v.vgs * dvgs_eff_dvg + vgs_eff;
       T11 = S_(AechvbEdgeS);
@@ -256,7 +256,7 @@ template <class E> B4_HD void b4_leakage(E& e, const B4Bias& v, B4Op& o, B4Chan&
     {
       T0 = v.vgd - vfbsd_tot;
       const double vgd_eff = sqrt(T0 * T0 + 1.0e-4);
-      const double dvgd_eff_dvg = T0 / vgd_eff;
+      const double dvgd_eff_dvg = B4_DIV(T0, vgd_eff);
       T2 = v.vgd * vgd_eff;
       dT2_dVg = v.vgd * dvgd_eff_dvg + vgd_eff;
       T11 = S_(AechvbEdgeD);
@@ -281,13 +281,13 @@ template <class E> B4_HD void b4_leakage(E& e, const B4Bias& v, B4Op& o, B4Chan&
     const double Vfb = t.Vfb, Voxacc = t.Voxacc;
     T0 = vt_tun * S_(nigbacc);
     T1 = -Vgs_eff + Vbseff + Vfb;
-    double VxNVt = T1 / T0;
+    double VxNVt = B4_DIV(T1, T0);
     if (VxNVt > B4C_EXP_THRESHOLD) { Vaux = T1; dVaux_dVg = -dVgs_eff_dVg; dVaux_dVb = 1.0; }
     else if (VxNVt < -B4C_EXP_THRESHOLD) { Vaux = T0 * log(1.0 + B4C_MIN_EXP); dVaux_dVg = 0.0; dVaux_dVb = 0.0; }
     else {
       const double ExpVxNVt = exp(VxNVt);
       Vaux = T0 * log(1.0 + ExpVxNVt);
-      dVaux_dVb = ExpVxNVt / (1.0 + ExpVxNVt);
+      dVaux_dVb = B4_DIV(ExpVxNVt, (1.0 + ExpVxNVt));
       dVaux_dVg = -dVaux_dVb * dVgs_eff_dVg;
     }
     T2 = (Vgs_eff - Vbseff) * Vaux;
@@ -307,7 +307,7 @@ template <class E> B4_HD void b4_leakage(E& e, const B4Bias& v, B4Op& o, B4Chan&
 
     T0 = vt_tun * S_(nigbinv);
     T1 = Voxdepinv - S_(eigbinv);
-    VxNVt = T1 / T0;
+    VxNVt = B4_DIV(T1, T0);
     if (VxNVt > B4C_EXP_THRESHOLD) {
       Vaux = T1; dVaux_dVg = dVoxdepinv_dVg; dVaux_dVd = dVoxdepinv_dVd; dVaux_dVb = dVoxdepinv_dVb;
     } else if (VxNVt < -B4C_EXP_THRESHOLD) {
@@ -315,7 +315,7 @@ template <class E> B4_HD void b4_leakage(E& e, const B4Bias& v, B4Op& o, B4Chan&
     } else {
       const double ExpVxNVt = exp(VxNVt);
       Vaux = T0 * log(1.0 + ExpVxNVt);
-      dVaux_dVg = ExpVxNVt / (1.0 + ExpVxNVt);
+      dVaux_dVg = B4_DIV(ExpVxNVt, (1.0 + ExpVxNVt));
       dVaux_dVd = dVaux_dVg * dVoxdepinv_dVd;
       dVaux_dVb = dVaux_dVg * dVoxdepinv_dVb;
       dVaux_dVg *= dVoxdepinv_dVg;

@@ -18,7 +18,7 @@ struct B4Dyn {
 template <class E> B4_HD void b4_tran_caps(E& e, const B4Bias& v, const B4Op& o, B4Dyn& y) {
   const int trnqsmod = (int)M_(trnqsmod), rgatemod = (int)M_(rgatemod), rbodymod = (int)M_(rbodymod);
   const double nqs_scaling_factor = 1.0e-9;
-  const double ag0 = 1.0 / e.dt;
+  const double ag0 = B4_DIV(1.0, e.dt);
   const double cgdo = o.cgdo, cgso = o.cgso, cgbo = S_(cgbo);
   const bool fwd = o.mode > 0;
   double gcdbdb = 0.0;  // used for the equivalent currents below, but never carried into the stamp (tran.rs:497-549)
@@ -103,7 +103,7 @@ template <class E> B4_HD void b4_tran_caps(E& e, const B4Bias& v, const B4Op& o,
     // non-quasi-static: the channel charge lives on the internal q node; terminals only see overlap + junction caps
     const double qcheq = o.qchqs;
     const double CoxWL = D_(coxe) * S_(weffCV) * I_(nf) * S_(leffCV);
-    const double T0 = v.qdef * nqs_scaling_factor / CoxWL;
+    const double T0 = B4_DIV(v.qdef * nqs_scaling_factor, CoxWL);
     y.ggtg = T0 * o.gcrgg;
     y.ggtb = T0 * o.gcrgb;
     if (fwd) { y.ggtd = T0 * o.gcrgd; y.ggts = T0 * o.gcrgs; }
@@ -120,16 +120,16 @@ template <class E> B4_HD void b4_tran_caps(E& e, const B4Bias& v, const B4Op& o,
       p_ = xpart < 0.5 ? 0.4 : (xpart > 0.5 ? 0.0 : 0.5);
       dp_dVd = 0.0; dp_dVg = 0.0; dp_dVb = 0.0; dp_dVs = 0.0;
     } else {
-      p_ = o.qdrn / qcheq;
+      p_ = B4_DIV(o.qdrn, qcheq);
       const double Cdd = o.cddb;
       const double Csd = -(o.cgdb + o.cddb + o.cbdb);
-      dp_dVd = (Cdd - p_ * (Cdd + Csd)) / qcheq;
+      dp_dVd = B4_DIV((Cdd - p_ * (Cdd + Csd)), qcheq);
       const double Cdg = o.cdgb;
       const double Csg = -(o.cggb + o.cdgb + o.cbgb);
-      dp_dVg = (Cdg - p_ * (Cdg + Csg)) / qcheq;
+      dp_dVg = B4_DIV((Cdg - p_ * (Cdg + Csg)), qcheq);
       const double Cds = o.cdsb;
       const double Css = fwd ? -(o.cgsb + o.cdsb + o.cbsb) : -(o.cgsb + o.cdsb + o.cbs);  // reverse mode reads the junction current (tran.rs:358)
-      dp_dVs = (Cds - p_ * (Cds + Css)) / qcheq;
+      dp_dVs = B4_DIV((Cds - p_ * (Cds + Css)), qcheq);
       dp_dVb = -(dp_dVd + dp_dVg + dp_dVs);
     }
     if (fwd) {
@@ -174,15 +174,15 @@ template <class E> B4_HD void b4_tran_caps(E& e, const B4Bias& v, const B4Op& o,
 
   // terminal currents i = dq/dt by Backward Euler against the committed charges (tran.rs:449-470)
   const double dt = e.dt;
-  const double cqb = (o.qb - e.op(B4S_QB)) / dt;
-  const double cqg = (o.qg - e.op(B4S_QG)) / dt;
-  const double cqd = (o.qd - e.op(B4S_QD)) / dt;
+  const double cqb = B4_DIV((o.qb - e.op(B4S_QB)), dt);
+  const double cqg = B4_DIV((o.qg - e.op(B4S_QG)), dt);
+  const double cqd = B4_DIV((o.qd - e.op(B4S_QD)), dt);
   double cqcdump = 0.0, cqgmid = 0.0, cqbs = 0.0, cqbd = 0.0;
-  if (trnqsmod != 0) cqcdump = (o.qdef_dump - e.op(B4S_QCDUMP)) / dt;
-  if (rgatemod == 3) cqgmid = (o.qgmid - e.op(B4S_QGMID)) / dt;
+  if (trnqsmod != 0) cqcdump = B4_DIV((o.qdef_dump - e.op(B4S_QCDUMP)), dt);
+  if (rgatemod == 3) cqgmid = B4_DIV((o.qgmid - e.op(B4S_QGMID)), dt);
   if (rbodymod != 0) {
-    cqbs = (o.qbs - e.op(B4S_QBS)) / dt;
-    cqbd = (o.qbd - e.op(B4S_QBD)) / dt;
+    cqbs = B4_DIV((o.qbs - e.op(B4S_QBS)), dt);
+    cqbd = B4_DIV((o.qbd - e.op(B4S_QBD)), dt);
   }
   const double vgb = v.vgb, vbd = v.vbd, vbs = v.vbs, vgmb = v.vgmb;
   y.ceqqg = cqg - y.gcggb * vgb + y.gcgdb * vbd + y.gcgsb * vbs;
@@ -194,7 +194,7 @@ template <class E> B4_HD void b4_tran_caps(E& e, const B4Bias& v, const B4Op& o,
     y.ceqqjd = cqbd + gcdbdb * v.vbd_jct;
   }
   if (trnqsmod != 0) {
-    const double cqcheq_i = (o.qcheq - e.op(B4S_QCHEQ)) / dt;
+    const double cqcheq_i = B4_DIV((o.qcheq - e.op(B4S_QCHEQ)), dt);
     const double T0 = y.ggtg * vgb - y.ggtd * vbd - y.ggts * vbs;
     y.ceqqg += T0;
     const double T1 = v.qdef * o.gtau;
