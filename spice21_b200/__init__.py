@@ -19,7 +19,7 @@ from . import protos
 from .protos import (Capacitor, Resistor, Diode, Mos, Isrc, Vsrc, MosType, TranOptions, Bsim4Model, Bsim4InstParams)  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libspice21cu.so")
+LIB_PATH = os.environ.get("S21_LIB") or os.path.join(_HERE, "libspice21cu.so")  # S21_LIB: an experimental build (e.g. make B4_SDIV=1 OUT=...)
 
 S21_OK, S21_CONVERGENCE_FAILED, S21_SINGULAR_MATRIX, S21_PIVOT_SEARCH_FAIL, S21_DECODE_ERROR, S21_INVALID_CIRCUIT, \
     S21_UNSUPPORTED, S21_CUDA_ERROR, S21_OTHER = range(9)
