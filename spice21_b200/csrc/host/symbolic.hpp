@@ -440,11 +440,15 @@ Plan build_plan(int N, const std::vector<int>& elem_row, const std::vector<int>&
 
   // ---- freeze: slots in final internal coordinates
   P.nnzLU = (int)E.size();
-  std::vector<int> order((size_t)P.nnzLU);
-  for (int k = 0; k < P.nnzLU; k++) order[(size_t)k] = k;
   auto irow = [&](int id) { return P.row_e2i[(size_t)E[(size_t)id].r]; };
   auto icol = [&](int id) { return P.col_e2i[(size_t)E[(size_t)id].c]; };
-  std::sort(order.begin(), order.end(), [&](int a, int b) { return irow(a) != irow(b) ? irow(a) < irow(b) : icol(a) < icol(b); });
+  std::vector<int> order((size_t)P.nnzLU);
+  {  // sort by (internal row, internal column): the keys are materialised once, the sort then runs on contiguous memory
+    std::vector<std::pair<uint64_t, int>> keyed((size_t)P.nnzLU);
+    for (int k = 0; k < P.nnzLU; k++) keyed[(size_t)k] = {detail::rc_key(irow(k), icol(k)), k};
+    std::sort(keyed.begin(), keyed.end());
+    for (int k = 0; k < P.nnzLU; k++) order[(size_t)k] = keyed[(size_t)k].second;
+  }
   std::vector<int> slot_of((size_t)P.nnzLU);
   P.rowptr.assign((size_t)N + 1, 0);
   P.colidx.resize((size_t)P.nnzLU);

@@ -1,7 +1,9 @@
 """Host logic of the product, no GPU needed: the C-ABI library loads and exports every declared symbol, the protobuf
 decoder and the builder produce the reference's variable numbering and stamp map, and the symbolic phase picks the
 reference's pivot order and fill pattern integer for integer (checked against the oracle)."""
+import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -158,6 +160,23 @@ def test_pivot_order_tie_heavy_matrices(s21, oracle):
         if trial % 5 == 4:
             v = v + 1j * rng.choice([0.0, 1.0, -1.0], size=len(r))
         assert _same_plan(oracle.lu_order(n, r, c, v), s21.symbolic(n, r, c, v)), trial
+
+
+def test_bsim4_divisions_stay_routed():
+    """Every division of the BSIM4 evaluation goes through B4_DIV (bsim4/bsim4_eval.hpp) so that the device build can
+    route them through csrc/scalar.h with one definition. The rewriting tool must keep C++'s grouping (self-test on random
+    expressions: identical values), and a dry run over the headers must find nothing left to rewrite."""
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import b4_route_divisions as tool
+    tool.selftest(trials=400, seed=11)
+    d = os.path.join(ROOT, "spice21_b200", "csrc", "bsim4")
+    for f in tool.FILES:
+        out, n = tool.rewrite(open(os.path.join(d, f)).read())
+        assert n == 0, f"{f}: {n} plain divisions; run scripts/b4_route_divisions.py --apply"
+    assert tool.rewrite("x = -a * b / c / (d + 1.0) * e;")[0] == "x = B4_DIV(B4_DIV(-a * b, c), (d + 1.0)) * e;"
+    assert tool.rewrite("y = *p * (1.0 + t) / q;")[0] == "y = B4_DIV(*p * (1.0 + t), q);"
+    assert tool.rewrite("z = a + f(b / c, 2.0) / s.m[1];")[0] == "z = a + B4_DIV(f(B4_DIV(b, c), 2.0), s.m[1]);"
 
 
 def test_proto_decode_errors(s21):
