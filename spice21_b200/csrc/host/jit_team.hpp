@@ -35,13 +35,13 @@ inline int team_lpi(int N, int n_heavy = 0) {
     const int v = std::atoi(e);
     if (v == 1 || v == 2 || v == 4 || v == 8 || v == 10 || v == 16) return v;
   }
-  (void)N;
   // Fewer lanes per instance = more independent rows per lane (instruction-level parallelism inside the one dependent
   // chain a Newton iteration is) and fewer warps per SM for the same batch. Measured on B200 (profiles/r01t_team_shapes.txt),
   // C2 dcop (N = 9, 2 Mos1) at 8192 instances: 16 lanes 0.160 ms, 10 lanes 0.123, 8 lanes 0.116, 4 lanes 0.100,
   // 2 lanes 0.085, 1 lane 0.106; C1 transient (N = 7, 6 Mos1, 200 points): 8 lanes 13.3 ms, 4 lanes 12.1, 2 lanes 12.7,
   // 1 lane 15.1 — the evaluation phase wants a warp per expensive device, so device-heavy circuits keep 4 lanes.
-  return n_heavy <= 2 ? 2 : 4;
+  // (2 lanes were measured up to N = 9, i.e. five register sets per lane; beyond ten rows stay with 4 lanes until measured)
+  return (n_heavy <= 2 && N <= 10) ? 2 : 4;
 }
 inline int team_heavy_devices(const FlatCkt& flat) {
   int n = 0;
