@@ -4,6 +4,7 @@
 #   gpurun --timeout 900 -- 'bash scripts/r02_gpu_plan.sh accept'        # 1 GPU
 #   gpurun --timeout 900 -- 'bash scripts/r02_gpu_plan.sh wp'            # 1 GPU
 #   gpurun --timeout 1500 -- 'bash scripts/r02_gpu_plan.sh sdiv'         # 1 GPU (builds a second library, ~2 min)
+#   gpurun --timeout 1200 -- 'bash scripts/r02_gpu_plan.sh cache'        # 1 GPU
 #   gpurun --gpus 2 --timeout 300 -- 'bash scripts/r02_gpu_plan.sh scale 2'   # then 4, then 8: ~1 min of box time each
 set -u
 mkdir -p gpurun_out
@@ -22,10 +23,13 @@ case "${1:-}" in
     timeout 600 python scripts/run_c4.py 2048 21 100 2>&1 | tail -6 | tee gpurun_out/r02_c4_default.txt
     S21_LIB=/tmp/libspice21cu_sdiv.so timeout 600 python scripts/run_c4.py 2048 21 100 2>&1 | tail -6 | tee gpurun_out/r02_c4_sdiv.txt
     S21_LIB=/tmp/libspice21cu_sdiv.so timeout 900 python -m pytest tests/test_gpu.py -m gpu -x -q -k "bsim4" 2>&1 | tail -3 ;;
+  cache)   # transient plan kept when the probe values repeat (S21_PLAN_CACHE=1): same results, second run without the symbolic phase
+    S21_PLAN_CACHE=1 timeout 900 python -m pytest tests/test_gpu.py -m gpu -x -q -k "tran or golden or variants or grid" 2>&1 | tail -3
+    for c in 0 1; do echo "PLAN_CACHE=$c"; S21_PLAN_CACHE=$c S21_PLAN_INFO=1 timeout 600 python scripts/run_c3.py 400 5 2e-10 2>&1 | grep -E "second run|symbolic phase|rings=" ; done | tee gpurun_out/r02_plan_cache.txt ;;
   scale)   # multi-GPU bench, one N per call; 120 s NCCL timeout inside bench.py, 240 s here
     n="${2:?number of GPUs}"
     timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port $((29600 + n)) \
       bench.py --gpus "$n" --steps 20 --warmup 5 > "gpurun_out/r02_bench_n$n.json" 2> "gpurun_out/r02_bench_n$n.err"
     echo "rc=$?"; cut -c1-300 "gpurun_out/r02_bench_n$n.json"; tail -3 "gpurun_out/r02_bench_n$n.err" ;;
-  *) echo "usage: $0 accept | wp | sdiv | scale N"; exit 2 ;;
+  *) echo "usage: $0 accept | wp | sdiv | cache | scale N"; exit 2 ;;
 esac
