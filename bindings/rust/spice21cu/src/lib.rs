@@ -132,3 +132,69 @@ impl<'c> Drop for Batch<'c> {
         unsafe { sys::s21_batch_destroy(self.h) }
     }
 }
+
+/// `b` instances split over several GPUs of THIS process (`s21_sweep_*`: one host thread and stream per GPU inside the
+/// library, contiguous blocks of `ceil(b / n_devices)` instances, results gathered into one pinned host buffer).
+pub struct Sweep<'c> {
+    h: *mut sys::s21_sweep,
+    ckt: &'c Circuit,
+    b: usize,
+}
+impl<'c> Sweep<'c> {
+    /// `n_devices <= 0` takes every visible CUDA device.
+    pub fn new(ckt: &'c Circuit, n_devices: i32, b: usize) -> SpResult<Self> {
+        let mut h = ptr::null_mut();
+        check(unsafe { sys::s21_sweep_create(ckt.h, n_devices, ptr::null(), b, &mut h) })?;
+        Ok(Sweep { h, ckt, b })
+    }
+    pub fn num_devices(&self) -> usize {
+        unsafe { sys::s21_sweep_num_devices(self.h) as usize }
+    }
+    /// `(first, count)` of shard `g` of `n_devices`: the partition rule, usable without a GPU.
+    pub fn partition(b: usize, n_devices: i32, g: i32) -> SpResult<(usize, usize)> {
+        let (mut first, mut count) = (0usize, 0usize);
+        check(unsafe { sys::s21_sweep_partition(b, n_devices, g, &mut first, &mut count) })?;
+        Ok((first, count))
+    }
+    pub fn set(&mut self, spec: &str, values: &[f64]) -> SpResult<()> {
+        assert_eq!(values.len(), self.b);
+        let s = CString::new(spec).unwrap();
+        check(unsafe { sys::s21_sweep_override(self.h, s.as_ptr(), values.as_ptr()) })
+    }
+    pub fn reset(&mut self) -> SpResult<()> {
+        check(unsafe { sys::s21_sweep_reset(self.h) })
+    }
+    pub fn dcop(&mut self) -> SpResult<DcopResult> {
+        let n = self.ckt.num_vars();
+        let mut r = DcopResult { x: vec![0.0; n * self.b], status: vec![0; self.b], iters: vec![0; self.b] };
+        check(unsafe { sys::s21_sweep_dcop(self.h, r.x.as_mut_ptr(), r.status.as_mut_ptr(), r.iters.as_mut_ptr()) })?;
+        Ok(r)
+    }
+    pub fn dcop_view(&mut self) -> SpResult<DcopView<'_>> {
+        let n = self.ckt.num_vars();
+        let (mut x, mut st, mut it) = (ptr::null(), ptr::null(), ptr::null());
+        check(unsafe { sys::s21_sweep_dcop_view(self.h, &mut x, &mut st, &mut it) })?;
+        Ok(unsafe {
+            DcopView {
+                x: std::slice::from_raw_parts(x, n * self.b),
+                status: std::slice::from_raw_parts(st, self.b),
+                iters: std::slice::from_raw_parts(it, self.b),
+            }
+        })
+    }
+    /// `Tran::solve` for every instance; `wave` is `[instance][timepoint][saved variable]`.
+    pub fn tran(&mut self, tstep: f64, tstop: f64, save: &[i32]) -> SpResult<(Vec<f64>, Vec<f64>, Vec<i32>, Vec<i64>)> {
+        let t = unsafe { sys::s21_tran_num_points(tstep, tstop) } as usize;
+        let (mut time, mut wave) = (vec![0.0; t], vec![0.0; self.b * t * save.len()]);
+        let (mut status, mut iters) = (vec![0i32; self.b], vec![0i64; self.b]);
+        check(unsafe {
+            sys::s21_sweep_tran(self.h, tstep, tstop, save.as_ptr(), save.len(), time.as_mut_ptr(), wave.as_mut_ptr(), status.as_mut_ptr(), iters.as_mut_ptr())
+        })?;
+        Ok((time, wave, status, iters))
+    }
+}
+impl<'c> Drop for Sweep<'c> {
+    fn drop(&mut self) {
+        unsafe { sys::s21_sweep_destroy(self.h) }
+    }
+}

@@ -124,6 +124,13 @@ int32_t s21_batch_read(s21_batch* b, double* x, int32_t* status, int32_t* iters)
  * batch; the caller must not free or write them. (The reference returns an owned Vec, analysis.rs:383-388; a caller that
  * needs ownership copies, which is what s21_batch_dcop does.) */
 int32_t s21_batch_dcop_view(s21_batch* b, const double** x, const int32_t** status, const int32_t** iters);
+/* Results of the last solve left in HBM in the host's layout — [x as [B][N] f64][status B i32][iters B i32][loads B i32],
+ * *n_words f64 words in all — for a caller that hands them to a collective (bench.py: NCCL gather of per-instance solutions
+ * and convergence flags across ranks) instead of copying them to the host first. Device pointer, owned
+ * by the batch, valid until its next solve; work is enqueued on the batch's stream. */
+int32_t s21_batch_packed_device(s21_batch* b, const double** dev_ptr, size_t* n_words);
+/* Waveforms of the last s21_batch_tran as the kernel left them in HBM: [T][n_save][stride] f64, instance fastest. */
+int32_t s21_batch_wave_device(const s21_batch* b, const double** dev_ptr, size_t* T, size_t* n_save, size_t* stride);
 /* Tran::solve (analysis.rs:526-573): OP at t=0, IC release, then fixed-step Backward Euler while t < tstop.
  * n_points_out = number of time points incl. t=0 (decided by the reference's floating-point `t += tstep`).
  * wave[B][T][n_save] and time[T] are host buffers sized by s21_tran_num_points; iters[B] counts all solves. */
@@ -146,6 +153,39 @@ int32_t s21_batch_stats(const s21_batch* b, double* out8);
 /* Name of the Newton kernel the last solve was dispatched to ("hybrid", "jit-team", "jit-thread", "coop", "grid",
  * "direct"); valid until the next solve. The choice depends on circuit size, device content and batch size. */
 const char* s21_batch_kernel_name(const s21_batch* b);
+
+/* Setup cost behind the solves of this process (none of it is per Newton iteration): [0] host seconds this batch spent in
+ * the symbolic phase (Markowitz order + fill + level schedules), [1] seconds spent inside NVRTC by the whole process,
+ * [2] NVRTC compilations, [3] kernels taken from the on-disk cubin cache ($S21_CACHE_DIR, default ~/.cache/spice21cu;
+ * "off" disables), [4] from the in-process cache; [5..7] reserved (0). */
+int32_t s21_batch_setup_stats(const s21_batch* b, double* out8);
+
+/* ---- multi-GPU sweeps: ONE process, one host thread + CUDA stream per GPU ---------------------
+ * The B instances of a sweep are split into contiguous blocks of ceil(B / n_devices) per device (s21_sweep_partition is
+ * that rule, host-only); every device holds its own copy of the shared structure. Instances never exchange data during
+ * a solve; at the end every device copies its block of results into its slice of one pinned host buffer, concurrently.
+ * The reference has no multi-device path (a Solver is single-threaded, analysis.rs:308-388); the calls mirror the
+ * s21_batch_* ones, with [B]-sized host arrays covering the whole sweep. devices == NULL means CUDA devices
+ * 0..n_devices-1; n_devices <= 0 means all visible devices. A sweep handle is driven from one host thread. */
+typedef struct s21_sweep s21_sweep;
+int32_t s21_sweep_partition(size_t B, int32_t n_devices, int32_t g, size_t* first, size_t* count);
+int32_t s21_sweep_create(const s21_ckt* c, int32_t n_devices, const int32_t* devices, size_t B, s21_sweep** out);
+void s21_sweep_destroy(s21_sweep* s);
+int32_t s21_sweep_num_devices(const s21_sweep* s);
+int32_t s21_sweep_shard(const s21_sweep* s, int32_t g, int32_t* cuda_device, size_t* first, size_t* count);
+int32_t s21_sweep_override(s21_sweep* s, const char* spec, const double* values /* [B] */);
+int32_t s21_sweep_sync_params(s21_sweep* s, int32_t force_upload, size_t* h2d_bytes /* sum over devices */);
+int32_t s21_sweep_reset(s21_sweep* s);
+int32_t s21_sweep_dcop(s21_sweep* s, double* x /* [B][N] */, int32_t* status /* [B] */, int32_t* iters /* [B] */);
+/* as s21_batch_dcop_view: pointers into the sweep's pinned gather buffer, valid until the next solve on this sweep */
+int32_t s21_sweep_dcop_view(s21_sweep* s, const double** x, const int32_t** status, const int32_t** iters);
+int32_t s21_sweep_tran(s21_sweep* s, double tstep, double tstop, const int32_t* save_vars, size_t n_save, double* time,
+                       double* wave /* [B][T][n_save] */, int32_t* status, int64_t* iters);
+/* the frequency axis sharded over the devices (blocks of ceil(F / n_devices) points), instance 0 of the circuit */
+int32_t s21_sweep_ac(s21_sweep* s, const double* freqs, size_t F, double* x /* [F][N][2] */, int32_t* status, int32_t* iters);
+/* [0] kernel launches (sum over devices), [1] device milliseconds (max over devices), [2] Newton iterations (sum),
+ * [3] load sweeps (sum), [4] nnz(A), [5] nnz(L+U), [6] N, [7] stamp slots */
+int32_t s21_sweep_stats(const s21_sweep* s, double* out8);
 
 /* Diagnostics of the run-time specialised kernels; neither needs a GPU. s21_jit_source returns the CUDA
  * source generated for the plan that the given first-iteration matrix values (one per element of s21_ckt_stamp_map)

@@ -33,6 +33,9 @@ ABI_SYMBOLS = [
     "s21_batch_destroy", "s21_batch_set_stream", "s21_batch_override", "s21_batch_sync_params", "s21_batch_reset", "s21_batch_dcop",
     "s21_batch_dcop_device", "s21_batch_read", "s21_tran_num_points", "s21_batch_tran", "s21_ac_freqs", "s21_batch_ac",
     "s21_batch_pivot_order", "s21_batch_dcop_view", "s21_batch_stats", "s21_batch_kernel_name", "s21_jit_source", "s21_jit_check", "s21_selftest_div", "s21_symbolic",
+    "s21_batch_setup_stats", "s21_batch_packed_device", "s21_batch_wave_device", "s21_sweep_partition", "s21_sweep_create", "s21_sweep_destroy", "s21_sweep_num_devices", "s21_sweep_shard",
+    "s21_sweep_override", "s21_sweep_sync_params", "s21_sweep_reset", "s21_sweep_dcop", "s21_sweep_dcop_view", "s21_sweep_tran", "s21_sweep_ac",
+    "s21_sweep_stats",
 ]
 
 
@@ -101,6 +104,22 @@ def lib():
         L.s21_jit_source.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         L.s21_jit_check.argtypes = [C.c_char_p, C.c_size_t]
         L.s21_selftest_div.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.s21_batch_setup_stats.argtypes = [C.c_void_p, C.c_void_p]
+        L.s21_batch_packed_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        L.s21_batch_wave_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        L.s21_sweep_partition.argtypes = [C.c_size_t, C.c_int32, C.c_int32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        L.s21_sweep_create.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.s21_sweep_destroy.argtypes = [C.c_void_p]
+        L.s21_sweep_num_devices.argtypes = [C.c_void_p]
+        L.s21_sweep_shard.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        L.s21_sweep_override.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+        L.s21_sweep_sync_params.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_size_t)]
+        L.s21_sweep_reset.argtypes = [C.c_void_p]
+        L.s21_sweep_dcop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.s21_sweep_dcop_view.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.s21_sweep_tran.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.s21_sweep_ac.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.s21_sweep_stats.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -375,6 +394,19 @@ class Batch:
     def dcop_device(self):
         _check(lib().s21_batch_dcop_device(self.h))
 
+    def packed_device(self):
+        """(device pointer, f64 words) of the last solve's results packed in HBM (s21_batch_packed_device): x rows [B][N], then
+        status / iters / loads as int32. For handing to a collective without a host round trip."""
+        p, n = C.c_void_p(), C.c_size_t()
+        _check(lib().s21_batch_packed_device(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def wave_device(self):
+        """(device pointer, T, n_save, stride) of the last transient's waveforms in HBM, [T][n_save][stride] f64."""
+        p, T, ns, st = C.c_void_p(), C.c_size_t(), C.c_size_t(), C.c_size_t()
+        _check(lib().s21_batch_wave_device(self.h, C.byref(p), C.byref(T), C.byref(ns), C.byref(st)))
+        return p.value, T.value, ns.value, st.value
+
     def read(self, want_x=True):
         x = np.zeros((self.B, self.N)) if want_x else None
         status = np.zeros(self.B, dtype=np.int32)
@@ -383,15 +415,17 @@ class Batch:
                                     iters.ctypes.data_as(C.c_void_p)))
         return x, status, iters
 
-    def tran(self, tstep, tstop, save=None):
+    def tran(self, tstep, tstop, save=None, want_wave=True):
+        """want_wave=False leaves the waveforms in HBM (wave_device) and returns None for them."""
         T = lib().s21_tran_num_points(tstep, tstop)
         save = np.arange(self.N, dtype=np.int32) if save is None else np.ascontiguousarray(save, dtype=np.int32)
         time = np.zeros(T)
-        wave = np.zeros((self.B, T, len(save)))
+        wave = np.zeros((self.B, T, len(save))) if want_wave else None
         status = np.zeros(self.B, dtype=np.int32)
         iters = np.zeros(self.B, dtype=np.int64)
         _check(lib().s21_batch_tran(self.h, tstep, tstop, save.ctypes.data_as(C.c_void_p), len(save), time.ctypes.data_as(C.c_void_p),
-                                    wave.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p), iters.ctypes.data_as(C.c_void_p)))
+                                    wave.ctypes.data_as(C.c_void_p) if want_wave else None, status.ctypes.data_as(C.c_void_p),
+                                    iters.ctypes.data_as(C.c_void_p)))
         return time, wave, status, iters
 
     def ac(self, freqs):
@@ -421,6 +455,108 @@ class Batch:
     def kernel_name(self):
         """Which Newton kernel the last solve ran on (s21_batch_kernel_name)."""
         return lib().s21_batch_kernel_name(self.h).decode()
+
+    def setup_stats(self):
+        """Setup cost behind the solves (s21_batch_setup_stats): host symbolic seconds of this batch, NVRTC seconds / runs and
+        cubin-cache hits of the process."""
+        s = np.zeros(8)
+        _check(lib().s21_batch_setup_stats(self.h, s.ctypes.data_as(C.c_void_p)))
+        return {"symbolic_s": float(s[0]), "nvrtc_s": float(s[1]), "nvrtc_runs": int(s[2]), "disk_hits": int(s[3]), "mem_hits": int(s[4])}
+
+
+def sweep_partition(B, n_devices, g):
+    """(first, count) of shard g: contiguous blocks of ceil(B / n_devices) instances (s21_sweep_partition; host only)."""
+    f, c = C.c_size_t(), C.c_size_t()
+    _check(lib().s21_sweep_partition(B, n_devices, g, C.byref(f), C.byref(c)))
+    return f.value, c.value
+
+
+class Sweep:
+    """``s21_sweep``: B instances of one elaborated circuit split over several GPUs of this process (one host thread and
+    stream per GPU inside the library); same calls as ``Batch`` with arrays covering the whole sweep."""
+
+    def __init__(self, ckt, B, devices=None, n_devices=0):
+        self.ckt, self.B, self.N = ckt, B, ckt.n_vars
+        self.h = C.c_void_p()
+        if devices is not None:
+            d = np.ascontiguousarray(devices, dtype=np.int32)
+            _check(lib().s21_sweep_create(ckt.h, len(d), d.ctypes.data_as(C.c_void_p), B, C.byref(self.h)))
+        else:
+            _check(lib().s21_sweep_create(ckt.h, n_devices, None, B, C.byref(self.h)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().s21_sweep_destroy(self.h)
+            self.h = None
+
+    @property
+    def n_devices(self):
+        return lib().s21_sweep_num_devices(self.h)
+
+    def shards(self):
+        out = []
+        for g in range(self.n_devices):
+            d, f, c = C.c_int32(), C.c_size_t(), C.c_size_t()
+            _check(lib().s21_sweep_shard(self.h, g, C.byref(d), C.byref(f), C.byref(c)))
+            out.append((d.value, f.value, c.value))
+        return out
+
+    def override(self, spec, values):
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        assert v.shape == (self.B,)
+        _check(lib().s21_sweep_override(self.h, _b(spec), v.ctypes.data_as(C.c_void_p)))
+
+    def sync_params(self, force_upload=False):
+        n = C.c_size_t()
+        _check(lib().s21_sweep_sync_params(self.h, 1 if force_upload else 0, C.byref(n)))
+        return n.value
+
+    def reset(self):
+        _check(lib().s21_sweep_reset(self.h))
+
+    def dcop(self):
+        x = np.zeros((self.B, self.N))
+        status = np.zeros(self.B, dtype=np.int32)
+        iters = np.zeros(self.B, dtype=np.int32)
+        _check(lib().s21_sweep_dcop(self.h, x.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p), iters.ctypes.data_as(C.c_void_p)))
+        return x, status, iters
+
+    def dcop_view(self):
+        px, ps, pi = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _check(lib().s21_sweep_dcop_view(self.h, C.byref(px), C.byref(ps), C.byref(pi)))
+
+        def view(p, ctype, shape):
+            a = np.ctypeslib.as_array(C.cast(p, C.POINTER(ctype)), shape=shape)
+            a.flags.writeable = False
+            return a
+
+        return view(px, C.c_double, (self.B, self.N)), view(ps, C.c_int32, (self.B,)), view(pi, C.c_int32, (self.B,))
+
+    def tran(self, tstep, tstop, save=None):
+        T = lib().s21_tran_num_points(tstep, tstop)
+        save = np.arange(self.N, dtype=np.int32) if save is None else np.ascontiguousarray(save, dtype=np.int32)
+        time = np.zeros(T)
+        wave = np.zeros((self.B, T, len(save)))
+        status = np.zeros(self.B, dtype=np.int32)
+        iters = np.zeros(self.B, dtype=np.int64)
+        _check(lib().s21_sweep_tran(self.h, tstep, tstop, save.ctypes.data_as(C.c_void_p), len(save), time.ctypes.data_as(C.c_void_p),
+                                    wave.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p), iters.ctypes.data_as(C.c_void_p)))
+        return time, wave, status, iters
+
+    def ac(self, freqs):
+        f = np.ascontiguousarray(freqs, dtype=np.float64)
+        x = np.zeros((len(f), self.N, 2))
+        status = np.zeros(len(f), dtype=np.int32)
+        iters = np.zeros(len(f), dtype=np.int32)
+        _check(lib().s21_sweep_ac(self.h, f.ctypes.data_as(C.c_void_p), len(f), x.ctypes.data_as(C.c_void_p),
+                                  status.ctypes.data_as(C.c_void_p), iters.ctypes.data_as(C.c_void_p)))
+        return x.view(np.complex128).reshape(len(f), self.N), status, iters
+
+    def stats(self):
+        s = np.zeros(8)
+        _check(lib().s21_sweep_stats(self.h, s.ctypes.data_as(C.c_void_p)))
+        return {"launches": int(s[0]), "device_ms": float(s[1]), "iters": int(s[2]), "loads": int(s[3]), "nnz_a": int(s[4]),
+                "nnz_lu": int(s[5]), "n": int(s[6]), "stamps": int(s[7])}
 
 
 def symbolic(n, rows, cols, vals):

@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "host/batch.hpp"
+#include "host/sweep.hpp"
 
 using namespace s21;
 
@@ -17,6 +18,10 @@ struct s21_ckt {
 };
 struct s21_batch {
   std::unique_ptr<Batch> b;
+  const s21_ckt* ckt = nullptr;
+};
+struct s21_sweep {
+  std::unique_ptr<Sweep> s;
   const s21_ckt* ckt = nullptr;
 };
 
@@ -342,6 +347,18 @@ int32_t s21_batch_dcop_view(s21_batch* b, const double** x, const int32_t** stat
   return S21_OK;
   S21_CATCH
 }
+int32_t s21_batch_packed_device(s21_batch* b, const double** dev_ptr, size_t* n_words) {
+  S21_TRY
+  b->b->packed_device(dev_ptr, n_words);
+  return S21_OK;
+  S21_CATCH
+}
+int32_t s21_batch_wave_device(const s21_batch* b, const double** dev_ptr, size_t* T, size_t* n_save, size_t* stride) {
+  S21_TRY
+  b->b->wave_device(dev_ptr, T, n_save, stride);
+  return S21_OK;
+  S21_CATCH
+}
 int64_t s21_tran_num_points(double tstep, double tstop) { return (int64_t)tran_times(tstep, tstop).size(); }
 int32_t s21_batch_tran(s21_batch* b, double tstep, double tstop, const int32_t* save_vars, size_t n_save, double* time, double* wave,
                        int32_t* status, int64_t* iters) {
@@ -387,6 +404,115 @@ int32_t s21_batch_stats(const s21_batch* b, double* out8) {
 
 const char* s21_batch_kernel_name(const s21_batch* b) { return b && b->b ? b->b->kernel_name() : ""; }
 
+int32_t s21_batch_setup_stats(const s21_batch* b, double* out8) {
+  S21_TRY
+  const jit::CacheStats& cs = jit::cache_stats();
+  out8[0] = b && b->b ? b->b->symbolic_seconds() : 0.0;
+  out8[1] = cs.nvrtc_seconds; out8[2] = (double)cs.nvrtc_runs; out8[3] = (double)cs.disk_hits; out8[4] = (double)cs.mem_hits;
+  out8[5] = out8[6] = out8[7] = 0.0;
+  return S21_OK;
+  S21_CATCH
+}
+
+// ------------------------------------------------------------------------------------------------ multi-GPU sweeps
+int32_t s21_sweep_partition(size_t B, int32_t n_devices, int32_t g, size_t* first, size_t* count) {
+  S21_TRY
+  if (n_devices <= 0 || g < 0 || g >= n_devices) throw S21Error(ST_OTHER, "s21_sweep_partition: 0 <= g < n_devices required");
+  size_t f = 0, c = 0;
+  sweep_partition(B, n_devices, g, &f, &c);
+  if (first) *first = f;
+  if (count) *count = c;
+  return S21_OK;
+  S21_CATCH
+}
+int32_t s21_sweep_create(const s21_ckt* c, int32_t n_devices, const int32_t* devices, size_t B, s21_sweep** out) {
+  S21_TRY
+  if (!c->elaborated) throw S21Error(ST_OTHER, "circuit is not elaborated");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    throw S21Error(ST_CUDA, "no CUDA device available: libspice21cu has no CPU fallback (" + std::string(cudaGetErrorString(e)) + ")");
+  if (n_devices <= 0) n_devices = count;  // all visible devices
+  std::vector<int> devs;
+  for (int g = 0; g < n_devices; g++) {
+    const int d = devices ? devices[g] : g;
+    if (d < 0 || d >= count) throw S21Error(ST_CUDA, "invalid CUDA device index in s21_sweep_create");
+    devs.push_back(d);
+  }
+  auto* s = new s21_sweep();
+  try { s->s.reset(new Sweep(c->spec, c->flat, devs, B)); } catch (...) { delete s; throw; }
+  s->ckt = c;
+  *out = s;
+  return S21_OK;
+  S21_CATCH
+}
+void s21_sweep_destroy(s21_sweep* s) { delete s; }
+int32_t s21_sweep_num_devices(const s21_sweep* s) { return s && s->s ? s->s->n_devices() : 0; }
+int32_t s21_sweep_shard(const s21_sweep* s, int32_t g, int32_t* cuda_device, size_t* first, size_t* count) {
+  S21_TRY
+  if (g < 0 || g >= s->s->n_devices()) throw S21Error(ST_OTHER, "shard index out of range");
+  int d = 0;
+  size_t f = 0, c = 0;
+  s->s->shard_range(g, &d, &f, &c);
+  if (cuda_device) *cuda_device = d;
+  if (first) *first = f;
+  if (count) *count = c;
+  return S21_OK;
+  S21_CATCH
+}
+int32_t s21_sweep_override(s21_sweep* s, const char* spec, const double* values) {
+  S21_TRY
+  s->s->add_override(nz(spec), values);
+  return S21_OK;
+  S21_CATCH
+}
+int32_t s21_sweep_sync_params(s21_sweep* s, int32_t force_upload, size_t* h2d_bytes) {
+  S21_TRY
+  const size_t n = s->s->sync_params(force_upload != 0);
+  if (h2d_bytes) *h2d_bytes = n;
+  return S21_OK;
+  S21_CATCH
+}
+int32_t s21_sweep_reset(s21_sweep* s) {
+  S21_TRY
+  s->s->reset();
+  return S21_OK;
+  S21_CATCH
+}
+int32_t s21_sweep_dcop(s21_sweep* s, double* x, int32_t* status, int32_t* iters) {
+  S21_TRY
+  s->s->dcop(x, status, iters);
+  return S21_OK;
+  S21_CATCH
+}
+int32_t s21_sweep_dcop_view(s21_sweep* s, const double** x, const int32_t** status, const int32_t** iters) {
+  S21_TRY
+  s->s->dcop_view(x, status, iters);
+  return S21_OK;
+  S21_CATCH
+}
+int32_t s21_sweep_tran(s21_sweep* s, double tstep, double tstop, const int32_t* save_vars, size_t n_save, double* time, double* wave,
+                       int32_t* status, int64_t* iters) {
+  S21_TRY
+  std::vector<double> t = tran_times(tstep, tstop);
+  if (time) std::memcpy(time, t.data(), t.size() * sizeof(double));
+  s->s->tran(tstep, (int)t.size(), save_vars, n_save, wave, status, iters);
+  return S21_OK;
+  S21_CATCH
+}
+int32_t s21_sweep_ac(s21_sweep* s, const double* freqs, size_t F, double* x, int32_t* status, int32_t* iters) {
+  S21_TRY
+  s->s->ac(freqs, F, x, status, iters);
+  return S21_OK;
+  S21_CATCH
+}
+int32_t s21_sweep_stats(const s21_sweep* s, double* out8) {
+  S21_TRY
+  s->s->stats(out8);
+  return S21_OK;
+  S21_CATCH
+}
+
 int32_t s21_jit_source(const s21_ckt* c, int32_t mode, int32_t shape, const double* vals, size_t n_vals, uint8_t** out, size_t* out_n,
                        size_t* smem_bytes) {
   S21_TRY
@@ -405,7 +531,7 @@ int32_t s21_jit_check(const uint8_t* src, size_t n) {
   S21_TRY
   std::vector<char> cubin;
   std::string err;
-  if (!jit::compile_cubin(std::string((const char*)src, n), &cubin, &err)) throw S21Error(ST_OTHER, err);
+  if (!jit::cubin_for(std::string((const char*)src, n), &cubin, &err)) throw S21Error(ST_OTHER, err);
   return S21_OK;
   S21_CATCH
 }

@@ -299,15 +299,22 @@ class Batch {
     if (want_x) {
       const size_t words = rows_words();
       d_rows_.alloc(words);
-      hx_.alloc(words);
+      if (!ext_x_) hx_.alloc(words);
       if (!rows_fresh_) {
         int rc = launch_pack_out(x_.p, status_.p, iters_.p, loads_.p, d_rows_.p, N, Bs_, (int)B_, stream_);
         launches_++;
         if (rc) throw S21Error(ST_CUDA, std::string("k_pack_out launch failed: ") + cudaGetErrorString((cudaError_t)rc));
       }
-      S21_CUDA(cudaMemcpyAsync(hx_.p, d_rows_.p, words * sizeof(double), cudaMemcpyDeviceToHost, stream_));
-      S21_CUDA(cudaStreamSynchronize(stream_));
-      hs = reinterpret_cast<const int32_t*>(hx_.p + (size_t)N * B_);
+      if (ext_x_) {  // a multi-GPU sweep owns one pinned buffer for all shards: x rows land in this shard's slice of it
+        S21_CUDA(cudaMemcpyAsync(ext_x_, d_rows_.p, (size_t)N * B_ * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        S21_CUDA(cudaMemcpyAsync(ext_tail_, d_rows_.p + (size_t)N * B_, 3 * B_ * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+        S21_CUDA(cudaStreamSynchronize(stream_));
+        hs = ext_tail_;
+      } else {
+        S21_CUDA(cudaMemcpyAsync(hx_.p, d_rows_.p, words * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        S21_CUDA(cudaStreamSynchronize(stream_));
+        hs = reinterpret_cast<const int32_t*>(hx_.p + (size_t)N * B_);
+      }
       hi = hs + B_;
       hl = hi + B_;
     } else {
@@ -323,12 +330,37 @@ class Batch {
       sum_iters_ += hi[i];
       sum_loads_ += hl[i];
     }
-    if (x) *x = want_x ? hx_.p : nullptr;
+    if (x) *x = want_x ? (ext_x_ ? ext_x_ : hx_.p) : nullptr;
     if (status) *status = hs;
     if (iters) *iters = hi;
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, ev0_, ev1_) == cudaSuccess) last_ms_ = ms;
   }
+  // Device-resident results of the last solve in the host's layout ([x rows B*N f64][status B][iters B][loads B] i32, packed by
+  // k_pack_out): what a multi-process job hands to its collective (NCCL gather of per-instance solutions and convergence
+  // flags) without a detour through host memory. Valid until the next solve on this batch.
+  void packed_device(const double** dptr, size_t* words) {
+    S21_CUDA(cudaSetDevice(device_));
+    materialize_reset();
+    d_rows_.alloc(rows_words());
+    if (!rows_fresh_) {
+      int rc = launch_pack_out(x_.p, status_.p, iters_.p, loads_.p, d_rows_.p, flat_.n_vars(), Bs_, (int)B_, stream_);
+      launches_++;
+      if (rc) throw S21Error(ST_CUDA, std::string("k_pack_out launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+      rows_fresh_ = true;
+    }
+    *dptr = d_rows_.p;
+    *words = rows_words();
+  }
+  // Waveforms of the last transient as the kernel left them in HBM: [T][n_save][stride] f64, instance fastest.
+  void wave_device(const double** dptr, size_t* T, size_t* n_save, size_t* stride) const {
+    *dptr = d_wave_.p; *T = wave_T_; *n_save = wave_ns_; *stride = Bs_;
+  }
+  // Results of read_view go to caller-provided pinned memory instead of the batch's own buffer: x rows [B][N] to x_dst,
+  // status / iters / loads (3 x B int32) to tail_dst. Used by the multi-GPU sweep (host/sweep.hpp); nullptr restores.
+  void set_result_target(double* x_dst, int32_t* tail_dst) { ext_x_ = x_dst; ext_tail_ = tail_dst; }
+  int device() const { return device_; }
+  double symbolic_seconds() const { return symbolic_s_; }
   size_t rows_words() const { return (size_t)flat_.n_vars() * B_ + (3 * B_ * sizeof(int32_t) + 7) / 8; }
   void read(double* x, int32_t* status, int32_t* iters) {
     const double* hx = nullptr;
@@ -357,6 +389,7 @@ class Batch {
     d_save_.upload(sv, stream_);
     S21_CUDA(cudaEventRecord(ev0_, stream_));  // time the transient kernel itself: the symbolic phase above is host work
     d_wave_.alloc((size_t)T * n_save * Bs_);
+    wave_T_ = (size_t)T; wave_ns_ = n_save;
     DevTables dt = dev_tables(tran_plan_.itab.p);
     SolveCtl ctl = make_ctl(AN_TRAN, tstep);
     int rc = 0;
@@ -532,6 +565,9 @@ class Batch {
   DBuf<cplx> zx_, zrhs_, zc_, zlu_;
   DBuf<int32_t> status_, iters_, loads_, ac_status_, ac_iters_, ac_loads_;
   PinnedBuf<double> pval_h_, hx_, hwave_;
+  double* ext_x_ = nullptr;       // set_result_target
+  size_t wave_T_ = 0, wave_ns_ = 0;
+  int32_t* ext_tail_ = nullptr;
   PinnedBuf<int32_t> hstatus_, hiters_, hloads_;
   std::vector<int> pcode_h_, poff_eff_;
   size_t pval_n_ = 0, h2d_bytes_ = 0;
@@ -582,7 +618,7 @@ class Batch {
       if (const char* dump = std::getenv("S21_JIT_DUMP")) {
         if (FILE* f = std::fopen(dump, "w")) { std::fwrite(src.data(), 1, src.size(), f); std::fclose(f); }
       }
-      if (jit::compile(src, tran, tpb, smem, &k, &err)) {
+      if (jit::compile(src, tran, tpb, smem, device_, &k, &err)) {
         k.inst_per_cta = tpb;
       } else {
         k = jit::Kernel();
@@ -608,14 +644,14 @@ class Batch {
       tried = true;
       std::string err;
       size_t smem = 0;
-      const int lpi = jit::team_lpi(pd.host.N, jit::team_heavy_devices(flat_));
+      const int lpi = jit::team_lpi(pd.host.N, jit::team_heavy_devices(flat_), B_);
       const int gi = jit::team_gi(B_, n_sm_, lpi);
       int tpb = 0;
       const std::string src = jit::team_source(flat_, pd.host, si_, pd.host_itab, pcode_h_, tran, lpi, &smem, n_sm_, gi, &tpb);
       if (const char* dump = std::getenv("S21_JIT_DUMP")) {
         if (FILE* f = std::fopen(dump, "w")) { std::fwrite(src.data(), 1, src.size(), f); std::fclose(f); }
       }
-      if (smem <= max_smem_ && jit::compile(src, tran, tpb, smem, &k, &err)) {
+      if (smem <= max_smem_ && jit::compile(src, tran, tpb, smem, device_, &k, &err)) {
         k.inst_per_cta = gi;
         k.team = true;
       } else {
@@ -757,7 +793,7 @@ class Batch {
       reset_pending_ = false;
       last_kernel_ = jk->team ? "jit-team" : "jit-thread";
       double* rows = nullptr;
-      if (jk->team && jit::team_wp()) {  // (experimental build of the team kernel) it also leaves the host's result layout behind
+      if (jk->team && jit::team_wp()) {  // the warp-private team kernel also leaves the host's result layout behind
         d_rows_.alloc(rows_words());
         rows = d_rows_.p;
       }

@@ -30,7 +30,8 @@ constexpr int TM_GI = 32;    // instances per CTA
 constexpr int TM_MAXN = 16;  // rows per instance the register-resident linear algebra is generated for
 // Lanes per instance in the linear-algebra phase: 8 (4 instances per warp, 8 warps per CTA; rows beyond 8 become a
 // second register set), 10 (3 instances per warp) or 16 (2 instances per warp, 16 warps per CTA; one row per member).
-inline int team_lpi(int N, int n_heavy = 0) {
+inline bool team_wp();
+inline int team_lpi(int N, int n_heavy = 0, size_t B = 0) {
   if (const char* e = std::getenv("S21_TEAM_LPI")) {
     const int v = std::atoi(e);
     if (v == 1 || v == 2 || v == 4 || v == 8 || v == 10 || v == 16) return v;
@@ -41,6 +42,10 @@ inline int team_lpi(int N, int n_heavy = 0) {
   // 2 lanes 0.085, 1 lane 0.106; C1 transient (N = 7, 6 Mos1, 200 points): 8 lanes 13.3 ms, 4 lanes 12.1, 2 lanes 12.7,
   // 1 lane 15.1 — the evaluation phase wants a warp per expensive device, so device-heavy circuits keep 4 lanes.
   // (2 lanes were measured up to N = 9, i.e. five register sets per lane; beyond ten rows stay with 4 lanes until measured)
+  // Small shards of a strong-scaled sweep (<= 2048 instances per GPU) leave most SMs with one CTA: there the warp-private
+  // loop with 8 lanes per instance and 16-instance CTAs is the shortest chain (profiles/r02a_wp_sweep.txt: 0.075 ms against
+  // 0.078-0.081 at 1024 / 2048 instances of C2).
+  if (B > 0 && B <= 2048 && team_wp() && n_heavy <= 2 && N <= 10) return 8;
   return (n_heavy <= 2 && N <= 10) ? 2 : 4;
 }
 inline int team_heavy_devices(const FlatCkt& flat) {
@@ -59,16 +64,16 @@ inline bool team_profile() { const char* e = std::getenv("S21_TEAM_PROFILE"); re
 inline int team_gi(size_t B, int n_sm, int lpi) {
   const int ipw = 32 / lpi, gmax = TM_GI / ipw * ipw;
   if (const char* e = std::getenv("S21_TEAM_GI")) { const int v = std::atoi(e); if (v >= ipw && v <= gmax && v % ipw == 0) return v; }
-  (void)B; (void)n_sm;
+  (void)n_sm;
+  if (B > 0 && B <= 2048 && lpi == 8 && team_wp()) return 16;  // see team_lpi
   return gmax;
 }
-// S21_TEAM_WP=1 (EXPERIMENTAL, off by default: written after this round's GPU budget was spent, so it compiles for sm_100a
-// but has not run on a GPU yet — tests/test_gpu.py::test_team_kernel_warp_private is its acceptance test) generates the
-// warp-private loop: a warp evaluates the devices of its own instances (lane = (instance, device group)), so an iteration
-// needs no block barrier and same-type devices share one evaluation text; the CTA may then be a single warp (the
-// shared-memory stride follows S21_TEAM_GI), and the kernel leaves the host's result layout behind (no packing kernel).
-// With the flag off the generated source is exactly the one measured in profiles/r01u_*.
-inline bool team_wp() { const char* e = std::getenv("S21_TEAM_WP"); return e && std::atoi(e) != 0; }
+// Warp-private loop (default; S21_TEAM_WP=0 restores the CTA-wide evaluation phase of round 1): a warp evaluates the
+// devices of its own instances (lane = (instance, device group)), so an iteration needs no block barrier and same-type
+// devices share one evaluation text; the CTA may then be a single warp (the shared-memory stride follows the instances
+// per CTA), and the kernel leaves the host's result layout behind (no packing kernel before the D2H copy). Measured
+// (profiles/r02a_wp_*): C1-circuit transient x 8192, 4 lanes: 12.08 -> 8.98 ms; C2 dcop x 8192: 0.083 ms either way.
+inline bool team_wp() { const char* e = std::getenv("S21_TEAM_WP"); return !e || std::atoi(e) != 0; }
 inline bool team_fast() { const char* e = std::getenv("S21_TEAM_FAST"); return !e || std::atoi(e) != 0; }
 
 struct TeamGather {

@@ -214,6 +214,83 @@ def test_monte_carlo_dcop_full_size_properties(s21):
     assert np.array_equal(x2, x[perm]) and np.array_equal(it2, it[perm])
 
 
+def test_monte_carlo_dcop_full_size_matches_oracle(s21, oracle):
+    """BASELINE config 2 at full size, compared outright: x within 1e-9 relative and the Newton iteration count of every one
+    of the 8192 instances against the CPU restatement (which re-pivots every iteration; 15 ms of host time)."""
+    B = 8192
+    ck, ovr = cc.diffpair(), cc.diffpair_mc(B)
+    o = oracle.Circuit(ck.to_text()).batch(0, B, overrides=ovr, nthreads=8)
+    b = s21.Batch(ck.to_s21().elaborate(), B)
+    for k, v in ovr.items():
+        b.override(k, v)
+    x, st, it = b.dcop()
+    assert np.all(st == 0) and np.all(o["status"] == 0)
+    assert rel_err(x, o["x"], floor=1e-9) <= 1e-9
+    assert np.array_equal(it, o["iters"])
+
+
+def test_sweep_single_process_matches_batch(s21):
+    """s21_sweep_* (one process, one host thread + stream per GPU) over every visible device: the gathered x / status / iters
+    of a dcop, a transient and an AC sweep equal one Batch's, bit for bit; shard bounds follow s21_sweep_partition."""
+    G = s21.cuda_device_count()
+    B = 1000  # ragged: not a multiple of the device count times 32
+    dp, ovr = cc.diffpair(), cc.diffpair_mc(B)
+    c = dp.to_s21().elaborate()
+    ref = s21.Batch(c, B)
+    sw = s21.Sweep(c, B, n_devices=G)
+    assert sw.n_devices == G
+    for g, (dev, first, count) in enumerate(sw.shards()):
+        assert (first, count) == s21.sweep_partition(B, G, g) and dev == g
+    for k, v in ovr.items():
+        ref.override(k, v)
+        sw.override(k, v)
+    x, st, it = ref.dcop()
+    xs, sts, its = sw.dcop()
+    assert np.array_equal(x, xs) and np.array_equal(st, sts) and np.array_equal(it, its)
+    sw.reset()
+    assert sw.sync_params(force_upload=True) > 0
+    xv, stv, itv = sw.dcop_view()
+    assert np.array_equal(x, xv) and np.array_equal(st, stv) and np.array_equal(it, itv)
+    assert sw.stats()["iters"] == int(it.sum())
+    # transient: the C1 ring as a supply sweep
+    ro = cc.cmos_ro3(cc.add_mos1_defaults).to_s21().elaborate(ic={"1": 0.0})
+    Bt = 70
+    vs = np.linspace(0.9, 1.1, Bt)
+    rb, rs = s21.Batch(ro, Bt), s21.Sweep(ro, Bt, n_devices=G)
+    rb.override("V:v1:dc", vs)
+    rs.override("V:v1:dc", vs)
+    t, w, st, it = rb.tran(1e-11, 3e-10)
+    t2, w2, st2, it2 = rs.tran(1e-11, 3e-10)
+    assert np.array_equal(t, t2) and np.array_equal(w, w2) and np.array_equal(st, st2) and np.array_equal(it, it2)
+    # AC: the frequency axis is what shards
+    oc = cc.rc_opamp(8).to_s21().elaborate()
+    f = s21.ac_freqs(1, 10**9, 500)
+    xa, sa, ia = s21.Batch(oc, 1).ac(f)
+    xb, sb, ib = s21.Sweep(oc, 1, n_devices=G).ac(f)
+    assert np.all(sa == 0) and np.array_equal(sa, sb) and np.array_equal(ia, ib)
+    assert np.max(np.abs(xa - xb)) <= 1e-12 * max(1.0, float(np.max(np.abs(xa))))  # each shard pivots on its own first point
+
+
+def test_packed_device_results(s21):
+    """s21_batch_packed_device: the device-resident result block a multi-rank job hands to NCCL equals what dcop returns."""
+    torch = pytest.importorskip("torch")
+    B = 96
+    b = s21.Batch(cc.diffpair().to_s21().elaborate(), B)
+    for k, v in cc.diffpair_mc(B).items():
+        b.override(k, v)
+    x, st, it = b.dcop()
+    ptr, words = b.packed_device()
+
+    class Dev:
+        __cuda_array_interface__ = {"shape": (words,), "typestr": "<f8", "data": (ptr, True), "version": 2}
+
+    torch.cuda.synchronize()
+    host = torch.as_tensor(Dev(), device="cuda").cpu().numpy()
+    assert np.array_equal(host[: B * b.N].reshape(B, b.N), x)
+    tail = host[B * b.N:].view(np.int32)
+    assert np.array_equal(tail[:B], st) and np.array_equal(tail[B:2 * B], it)
+
+
 def test_per_instance_failure_is_contained(s21, oracle):
     """One non-converging Monte-Carlo sample must not take the batch down (per-instance status vector)."""
     B = 64
@@ -469,14 +546,34 @@ def test_team_kernel_fast_and_exact_text_agree(s21, monkeypatch):
     _team_cases(s21, monkeypatch, [("1", None, None, False), ("0", None, None, False)])
 
 
-@pytest.mark.skipif(os.environ.get("S21_TEST_EXPERIMENTAL") != "1", reason="S21_TEAM_WP=1 has not run on a GPU yet (written after "
-                    "the round's GPU budget was spent); run with S21_TEST_EXPERIMENTAL=1 to accept it")
 def test_team_kernel_warp_private(s21, monkeypatch):
-    """Acceptance test of the experimental warp-private team kernel (S21_TEAM_WP=1: no block barriers, shared evaluation
-    text for same-type devices, CTAs down to one warp, result rows written by the kernel): same bits as the direct kernel
-    for dcop, the forced exact redo and a transient, with both texts and several CTA sizes."""
+    """The warp-private team kernel (default since round 2; S21_TEAM_WP=0 = the CTA-wide evaluation phase of round 1): no
+    block barriers, shared evaluation text for same-type devices, CTAs down to one warp, result rows written by the kernel.
+    Same bits as the direct kernel for dcop, the forced exact redo and a transient, with both texts and several CTA sizes."""
     _team_cases(s21, monkeypatch, [("1", "1", None, True), ("0", "1", None, True), ("1", "1", "16", True), ("1", "1", "8", True),
-                                   ("1", "0", "16", True)])
+                                   ("1", "0", "16", True), ("1", "0", None, True)])
+
+
+def test_strong_scaling_shard_shape_same_bits(s21, monkeypatch):
+    """Shards of <= 2048 instances take the 8-lane / 16-instance shape of the team kernel (host/jit_team.hpp::team_lpi):
+    same bits as the 2-lane shape a full-size batch uses."""
+    B = 1024
+    dp, ovr = cc.diffpair(), cc.diffpair_mc(B)
+
+    def run(lpi):
+        if lpi:
+            monkeypatch.setenv("S21_TEAM_LPI", lpi)
+        else:
+            monkeypatch.delenv("S21_TEAM_LPI", raising=False)
+        b = s21.Batch(dp.to_s21().elaborate(), B)
+        for k, v in ovr.items():
+            b.override(k, v)
+        return b.dcop(), b.kernel_name()
+
+    (x8, st8, it8), name = run(None)
+    (x2, st2, it2), _ = run("2")
+    assert name == "jit-team" and np.all(st8 == 0)
+    assert np.array_equal(x8, x2) and np.array_equal(it8, it2)
 
 
 # ------------------------------------------------------------------------------------------------ Bsim4

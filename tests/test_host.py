@@ -43,6 +43,49 @@ def test_no_cpu_fallback(s21):
     assert e.value.status == s21.S21_CUDA_ERROR
 
 
+def test_sweep_partition_and_no_gpu(s21):
+    """s21_sweep_partition (contiguous blocks of ceil(B / G)) covers [0, B) exactly once for every
+    (B, G); without a CUDA device a sweep fails as loudly as a batch."""
+    for B in (1, 3, 31, 1000, 2048, 8192, 100000):
+        for G in (1, 2, 3, 4, 8):
+            blocks = [s21.sweep_partition(B, G, g) for g in range(G)]
+            per = -(-B // G)
+            assert blocks[0][0] == 0 and sum(c for _, c in blocks) == B
+            for g in range(G):
+                assert blocks[g][0] == min(B, g * per) and blocks[g][1] <= per
+                if g:
+                    assert blocks[g][0] == blocks[g - 1][0] + blocks[g - 1][1]
+    assert [s21.sweep_partition(8192, 8, g)[1] for g in range(8)] == [1024] * 8
+    assert [s21.sweep_partition(2048, 8, g)[1] for g in range(8)] == [256] * 8
+    with pytest.raises(s21.Spice21Error):
+        s21.sweep_partition(10, 2, 2)
+    if s21.cuda_device_count() == 0:
+        c = Ckt(signals=["vdd"]).I("i1", "vdd", GND, 1e-3).R("r1", "vdd", GND, 1e-3).to_s21().elaborate()
+        with pytest.raises(s21.Spice21Error) as e:
+            s21.Sweep(c, 64, n_devices=2)
+        assert e.value.status == s21.S21_CUDA_ERROR
+
+
+def test_cubin_disk_cache(s21, tmp_path, monkeypatch):
+    """The run-time specialised kernels' cubins are cached on disk keyed on the generated source (host/jit.hpp): a second
+    compilation of the same source is a file read, a different source is a different file, a corrupt file is a miss."""
+    import time
+    monkeypatch.setenv("S21_CACHE_DIR", str(tmp_path))
+    src = 'extern "C" __global__ void k_jit(double* x) { x[threadIdx.x] = x[threadIdx.x] * 3.0 + 1.0; }\n// %d\n' % os.getpid()
+    t0 = time.time(); s21.jit_check(src); t1 = time.time(); s21.jit_check(src); t2 = time.time()
+    files = sorted(os.listdir(tmp_path))
+    assert len(files) == 1 and files[0].endswith(".cubin")
+    blob = open(os.path.join(tmp_path, files[0]), "rb").read()
+    assert src.encode() in blob and b"\x7fELF" in blob
+    assert (t2 - t1) < (t1 - t0) or (t2 - t1) < 0.05
+    s21.jit_check(src + "// other\n")
+    assert len(os.listdir(tmp_path)) == 2
+    open(os.path.join(tmp_path, files[0]), "wb").write(blob[: len(blob) // 2])  # truncated file: recompiled and replaced
+    monkeypatch.setenv("S21_JIT_NO_MEMCACHE", "1")
+    s21.jit_check(src)
+    assert open(os.path.join(tmp_path, files[0]), "rb").read() == blob
+
+
 def test_product_does_not_touch_oracle():
     import os
     root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "spice21_b200")
