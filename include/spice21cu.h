@@ -157,7 +157,10 @@ const char* s21_batch_kernel_name(const s21_batch* b);
 /* Setup cost behind the solves of this process (none of it is per Newton iteration): [0] host seconds this batch spent in
  * the symbolic phase (Markowitz order + fill + level schedules), [1] seconds spent inside NVRTC by the whole process,
  * [2] NVRTC compilations, [3] kernels taken from the on-disk cubin cache ($S21_CACHE_DIR, default ~/.cache/spice21cu;
- * "off" disables), [4] from the in-process cache; [5..7] reserved (0). */
+ * "off" disables), [4] from the in-process cache; [5] instances whose solves met a weak frozen pivot (|pivot| < 1e-3 x an
+ * entry below it: the reference, which re-pivots every iteration (sparse21/mod.rs:735-783), would have chosen otherwise) or
+ * an exactly zero one, [6] instances re-solved with a symbolic phase of their own because of it (dcop; S21_PIVOT_REPAIR=0
+ * disables); [7] reserved (0). */
 int32_t s21_batch_setup_stats(const s21_batch* b, double* out8);
 
 /* ---- multi-GPU sweeps: ONE process, one host thread + CUDA stream per GPU ---------------------

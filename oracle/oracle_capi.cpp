@@ -326,6 +326,24 @@ int orc_run_ac(void* ckt, const double* opts5, unsigned long long fstart, unsign
   } catch (const std::exception& e) { return fail(classify(e), e, err, errlen); }
 }
 
+int orc_run_ac_at(void* ckt, const double* opts5, const double* freqs, long n, void** out, char* err, int errlen) {
+  try {
+    Options o = make_opts(opts5);
+    Ckt c = build_ckt(*(CktSpec*)ckt, {}, nullptr, &o);
+    SolveStats st_ac;
+    AcResult r = ac_at(c, o, std::vector<double>(freqs, freqs + n), &st_ac);
+    auto* res = new Result();
+    set_names(res, r.signals);
+    res->npts = (int)r.freq.size();
+    res->width = 2;
+    res->axis = r.freq;
+    for (auto& row : r.data) for (auto& z : row) { res->data.push_back(z.re); res->data.push_back(z.im); }
+    res->loads = st_ac.loads; res->solves = st_ac.solves; res->seconds = st_ac.seconds;
+    *out = res;
+    return ST_OK;
+  } catch (const std::exception& e) { return fail(classify(e), e, err, errlen); }
+}
+
 int orc_res_nsig(void* r) { return ((Result*)r)->nsig; }
 int orc_res_npts(void* r) { return ((Result*)r)->npts; }
 int orc_res_width(void* r) { return ((Result*)r)->width; }

@@ -144,6 +144,16 @@ class Circuit:
         self._check(f(self.h, o.ctypes.data_as(C.c_void_p), int(fstart), int(fstop), int(npts), int(max_points), C.byref(out), err, 512), err)
         return Result(out)
 
+    def ac_at(self, freqs, opts=None):
+        """Oracle-only: cold-start AC solves at the given frequencies (what a one-point sweep computes at each of them)."""
+        out, err = C.c_void_p(), C.create_string_buffer(512)
+        o = _opts5(opts)
+        fr = np.ascontiguousarray(freqs, dtype=np.float64)
+        f = lib().orc_run_ac_at
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.POINTER(C.c_void_p), C.c_char_p, C.c_int]
+        self._check(f(self.h, o.ctypes.data_as(C.c_void_p), fr.ctypes.data_as(C.c_void_p), len(fr), C.byref(out), err, 512), err)
+        return Result(out)
+
     def structure(self, ic=None, opts=None):
         """Variable numbering, element creation order (stamp map) and first-factorisation pivot order / fill."""
         out, err = C.c_void_p(), C.create_string_buffer(512)

@@ -247,4 +247,31 @@ inline AcResult ac(const Ckt& ckt, const Options& opts, const AcOptions& args, S
   return results;
 }
 
+// ORACLE-ONLY extension (no counterpart in the reference): the body of the sweep loop above (analysis.rs:797-819) at
+// caller-given frequencies, every point started cold — solver.vars zeroed as Variables::from leaves them (analysis.rs:59-65)
+// — which is exactly what a one-point sweep `ac(fstart = fstop = f)` computes, without repeating elaboration and the OP.
+// Lets the tests compare a strided subset of a long batched sweep (config C5) point by point.
+inline AcResult ac_at(const Ckt& ckt, const Options& opts, const std::vector<double>& freqs, SolveStats* ac_stats = nullptr) {
+  Solver<double> re = Solver<double>::make(ckt, opts);
+  AnalysisInfo op;
+  op.kind = AnalysisInfo::OP;
+  solve(re, op);
+  Solver<Cplx> solver = to_complex(re);
+  AcState state;
+  AcResult results;
+  results.signals = solver.vars.names;
+  for (double f : freqs) {
+    for (auto& v : solver.vars.values) v = Cplx();
+    state.omega = 2.0 * consts::PI * f;
+    AnalysisInfo an;
+    an.kind = AnalysisInfo::AC;
+    an.ac = &state;
+    std::vector<Cplx> fsoln = solve(solver, an);
+    results.freq.push_back(f);
+    results.data.push_back(fsoln);
+  }
+  if (ac_stats) *ac_stats = solver.stats;
+  return results;
+}
+
 }  // namespace orc

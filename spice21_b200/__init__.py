@@ -461,7 +461,8 @@ class Batch:
         cubin-cache hits of the process."""
         s = np.zeros(8)
         _check(lib().s21_batch_setup_stats(self.h, s.ctypes.data_as(C.c_void_p)))
-        return {"symbolic_s": float(s[0]), "nvrtc_s": float(s[1]), "nvrtc_runs": int(s[2]), "disk_hits": int(s[3]), "mem_hits": int(s[4])}
+        return {"symbolic_s": float(s[0]), "nvrtc_s": float(s[1]), "nvrtc_runs": int(s[2]), "disk_hits": int(s[3]), "mem_hits": int(s[4]),
+                "weak_pivot_instances": int(s[5]), "repaired_instances": int(s[6])}
 
 
 def sweep_partition(B, n_devices, g):

@@ -31,14 +31,26 @@ namespace b4e {
 
 // Every f64 division of the evaluation goes through this one macro (scripts/b4_route_divisions.py rewrote the ~450
 // `X / Y` sites, keeping C++'s grouping: B4_DIV(whole multiplicative chain to the left, next unary expression)). The
-// default is the plain quotient, i.e. exactly the code there was before. Building the device side with -DS21_B4_SDIV
-// routes them through the split exact division of csrc/scalar.h instead (same bits; the compiler's own sequence sends
-// every zero numerator — frequent in a model with this many optional terms — to a ~100-instruction slow path). Not
-// enabled by default: it has not been measured on a GPU yet.
-#if defined(S21_B4_SDIV) && defined(__CUDA_ARCH__)
-#define B4_DIV(a, b) ::s21::s_div((double)(a), (double)(b))
+// default is the plain quotient. Two device-side variants were measured on C4 (2048 instances x 100 points, B200):
+//   * through the split exact division of csrc/scalar.h, inlined: 252 ms against 219 ms — slower, removed
+//     (profiles/r02a_c4_sdiv.txt);
+//   * -DS21_B4_NIDIV: ONE out-of-line copy of the compiler's division per kernel (a call per site): the evaluation's
+//     text shrinks by the ~460 inlined fast-path/slow-path sequences (ncu: 20 % of the stall samples of the C4 kernel
+//     are instruction-cache misses, its text is 39.6 k instructions);
+//   * -DS21_B4_NIMATH: the same for exp / log / sqrt.
+#if defined(__CUDACC__) && defined(S21_B4_NIDIV)
+static __device__ __noinline__ double b4_ddiv_ool(double a, double b) { return __ddiv_rn(a, b); }  // IEEE quotient
+#endif
+#if defined(__CUDA_ARCH__) && defined(S21_B4_NIDIV)
+#define B4_DIV(a, b) ::s21::b4e::b4_ddiv_ool((double)(a), (double)(b))
 #else
 #define B4_DIV(a, b) ((a) / (b))
+#endif
+#if defined(__CUDACC__) && defined(S21_B4_NIMATH)
+// unqualified exp / log / sqrt inside this namespace resolve to these (inner scope hides ::exp): one copy per kernel
+static __host__ __device__ __noinline__ double exp(double x) { return ::exp(x); }
+static __host__ __device__ __noinline__ double log(double x) { return ::log(x); }
+static __host__ __device__ __noinline__ double sqrt(double x) { return ::sqrt(x); }
 #endif
 
 // bsim4/mod.rs:35-63 and comps/consts

@@ -409,7 +409,9 @@ int32_t s21_batch_setup_stats(const s21_batch* b, double* out8) {
   const jit::CacheStats& cs = jit::cache_stats();
   out8[0] = b && b->b ? b->b->symbolic_seconds() : 0.0;
   out8[1] = cs.nvrtc_seconds; out8[2] = (double)cs.nvrtc_runs; out8[3] = (double)cs.disk_hits; out8[4] = (double)cs.mem_hits;
-  out8[5] = out8[6] = out8[7] = 0.0;
+  out8[5] = b && b->b ? (double)b->b->weak_seen() : 0.0;
+  out8[6] = b && b->b ? (double)b->b->repaired() : 0.0;
+  out8[7] = 0.0;
   return S21_OK;
   S21_CATCH
 }

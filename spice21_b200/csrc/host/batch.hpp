@@ -127,14 +127,14 @@ struct PlanDevice {
   DBuf<int> arena;
   size_t arena_bytes = 0;
   struct ArenaOffsets {
-    size_t type, itab_off, par_off, state_off, itab, pcode, row_i2e, col_i2e, col_e2i, rowptr, colidx, diag_slot, stage_off, eval_order,
+    size_t type, itab_off, par_off, state_off, itab, pcode, par_direct, row_i2e, col_i2e, col_e2i, rowptr, colidx, diag_slot, stage_off, eval_order,
         asm_off, asm_src, lu_lvl_off, lu_t, lu_u, lu_l, fw_lvl_off, fw_k, fw_row, fw_slot, bw_lvl_off, bw_row;
   } ao;
   DevTables coop_dev(int n_dev, const double* pval, int n_state) const {
     DevTables d;
     d.n_dev = n_dev; d.n_state = n_state; d.pval = pval;
     d.type = arena.p + ao.type; d.itab_off = arena.p + ao.itab_off; d.par_off = arena.p + ao.par_off; d.state_off = arena.p + ao.state_off;
-    d.itab = arena.p + ao.itab; d.pcode = arena.p + ao.pcode;
+    d.itab = arena.p + ao.itab; d.pcode = arena.p + ao.pcode; d.par_direct = arena.p + ao.par_direct;
     return d;
   }
   PlanTables coop_plan() const {
@@ -267,6 +267,7 @@ class Batch {
       if (codes_dirty_) {  // the index tables only change with the pool's layout; a forced upload re-sends the values alone
         d_pcode_.upload(pcode_h_, stream_);
         d_poff_.upload(poff_eff_, stream_);
+        d_pdirect_.upload(pdirect_h_, stream_);
         codes_dirty_ = false;
         h2d_bytes_ += (pcode_h_.size() + poff_eff_.size()) * sizeof(int);
       }
@@ -295,7 +296,7 @@ class Batch {
     S21_CUDA(cudaSetDevice(device_));
     materialize_reset();
     const int N = flat_.n_vars();
-    const int32_t *hs, *hi, *hl;
+    int32_t *hs, *hi, *hl;
     if (want_x) {
       const size_t words = rows_words();
       d_rows_.alloc(words);
@@ -313,7 +314,7 @@ class Batch {
       } else {
         S21_CUDA(cudaMemcpyAsync(hx_.p, d_rows_.p, words * sizeof(double), cudaMemcpyDeviceToHost, stream_));
         S21_CUDA(cudaStreamSynchronize(stream_));
-        hs = reinterpret_cast<const int32_t*>(hx_.p + (size_t)N * B_);
+        hs = reinterpret_cast<int32_t*>(hx_.p + (size_t)N * B_);
       }
       hi = hs + B_;
       hl = hi + B_;
@@ -325,6 +326,20 @@ class Batch {
       S21_CUDA(cudaStreamSynchronize(stream_));
       hs = hstatus_.p; hi = hiters_.p; hl = hloads_.p;
     }
+    // Pivot health. Bit 8 of a status word = during some factorisation of that instance a frozen pivot was smaller than
+    // 1e-3 x an entry below it, i.e. the reference — which re-runs its Markowitz search every iteration
+    // (sparse21/mod.rs:929-932, 735-783) — would not have taken it; S21_SINGULAR_MATRIX from a kernel = an exactly zero
+    // frozen pivot. Both mean "the order taken from instance 0 does not suit this instance". The flag is stripped here;
+    // after a dcop the instances concerned are re-solved with a symbolic phase of their own (repair_dcop).
+    std::vector<size_t> flagged;
+    for (size_t i = 0; i < B_; i++) {
+      const int32_t st = hs[i];
+      if (st & 0x100) { hs[i] = st & 0xff; flagged.push_back(i); }
+      else if (st == ST_SINGULAR && last_plan_ && last_plan_->host.status == ST_OK) flagged.push_back(i);
+    }
+    weak_seen_ += (long long)flagged.size();
+    if (!flagged.empty() && want_x && last_plan_ == &op_plan_ && pivot_repair_enabled() && repair_depth_ < 4)
+      repair_dcop(flagged, ext_x_ ? ext_x_ : hx_.p, hs, hi, hl);
     sum_iters_ = 0; sum_loads_ = 0;
     for (size_t i = 0; i < B_; i++) {
       sum_iters_ += hi[i];
@@ -336,6 +351,48 @@ class Batch {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, ev0_, ev1_) == cudaSuccess) last_ms_ = ms;
   }
+  static bool pivot_repair_enabled() { const char* e = std::getenv("S21_PIVOT_REPAIR"); return !e || std::atoi(e) != 0; }
+  // Per-instance re-pivoting (first half). The flagged instances of the last dcop are gathered into a batch
+  // of their own — same circuit, their slices of every override — whose symbolic phase runs on ITS first instance's
+  // values; the kernels that interpret plan tables are used (a specialised kernel would cost an NVRTC run per pivot
+  // order). Instances still flagged under that order recurse with the next instance leading, so in the worst case every
+  // outlier ends up with its own order, as in the reference. Results replace the rows of the host buffer and the x
+  // columns in HBM (so that a following warm solve starts from them). A repaired instance is solved from a cold start.
+  void repair_dcop(const std::vector<size_t>& flagged, double* hx, int32_t* hs, int32_t* hi, int32_t* hl) {
+    const int N = flat_.n_vars();
+    std::vector<size_t> todo = flagged;
+    // the leader of a repair batch that is itself still flagged keeps its result: its own first-iteration order IS what
+    // this design can offer it (the matrix moved away from it during the Newton loop)
+    if (repair_depth_ > 0 && !todo.empty() && todo[0] == 0) todo.erase(todo.begin());
+    if (todo.empty()) return;
+    Batch sub(spec_, flat_, device_, todo.size());
+    sub.repair_depth_ = repair_depth_ + 1;
+    sub.allow_jit_ = false;
+    sub.set_stream(stream_);
+    std::vector<double> vals(todo.size());
+    for (const Override& o : overrides_) {
+      for (size_t k = 0; k < todo.size(); k++) vals[k] = o.values[todo[k]];
+      sub.add_override(o.kind + ":" + o.name + ":" + o.param, vals.data());
+    }
+    sub.dcop_device();
+    const double* sx = nullptr;
+    const int32_t *ss = nullptr, *si = nullptr;
+    sub.read_view(true, &sx, &ss, &si);  // recurses for instances the new order does not suit either
+    const int32_t* sl = si + todo.size();
+    for (size_t k = 0; k < todo.size(); k++) {
+      const size_t i = todo[k];
+      std::memcpy(hx + i * (size_t)N, sx + k * (size_t)N, (size_t)N * sizeof(double));
+      hs[i] = ss[k]; hi[i] = si[k]; hl[i] = sl[k];
+      S21_CUDA(cudaMemcpy2DAsync(x_.p + i, Bs_ * sizeof(double), sx + k * (size_t)N, sizeof(double), sizeof(double), (size_t)N,
+                                 cudaMemcpyHostToDevice, stream_));
+      S21_CUDA(cudaMemcpyAsync(status_.p + i, hs + i, sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
+    }
+    S21_CUDA(cudaStreamSynchronize(stream_));
+    rows_fresh_ = false;
+    repaired_ += (long long)todo.size() + sub.repaired_;
+  }
+  long long weak_seen() const { return weak_seen_; }
+  long long repaired() const { return repaired_; }
   // Device-resident results of the last solve in the host's layout ([x rows B*N f64][status B][iters B][loads B] i32, packed by
   // k_pack_out): what a multi-process job hands to its collective (NCCL gather of per-instance solutions and convergence
   // flags) without a detour through host memory. Valid until the next solve on this batch.
@@ -451,6 +508,7 @@ class Batch {
       int32_t st0 = 0;
       S21_CUDA(cudaMemcpyAsync(&st0, status_.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
       S21_CUDA(cudaStreamSynchronize(stream_));
+      st0 &= 0xff;  // bit 8 = pivot-health flag
       if (st0 != ST_OK) throw S21Error(st0, status_text(st0));
     }
     const size_t Fs = (F + 31) / 32 * 32;
@@ -471,6 +529,9 @@ class Batch {
     w.st_op = st_op_.p; w.st_guess = st_guess_.p; w.st_stride = Bs_;
     SolveCtl ctl = make_ctl(AN_AC, 0.0);
     ctl.B = (int)F; ctl.omega = d_omega_.p; ctl.par_inst_stride = 0;
+    // Direct solve per frequency point by default (engine.hpp SolveCtl::ac_direct); S21_AC_NEWTON=1 keeps the reference's shell.
+    const char* ac_newton = std::getenv("S21_AC_NEWTON");
+    ctl.ac_direct = (ac_newton && std::atoi(ac_newton) != 0) ? 0 : 1;
     // symbolic phase on the first frequency point
     {
       DevTables dt = dev_tables(d_itab_raw_.p);
@@ -522,6 +583,7 @@ class Batch {
     S21_CUDA(cudaStreamSynchronize(stream_));
     sum_iters_ = 0; sum_loads_ = 0;
     for (size_t f = 0; f < F; f++) {
+      if (hs[f] & 0x100) { hs[f] &= 0xff; weak_seen_++; }
       if (status) status[f] = hs[f];
       if (iters) iters[f] = hi[f];
       sum_iters_ += hi[f]; sum_loads_ += hl[f];
@@ -558,7 +620,7 @@ class Batch {
   size_t B_, Bs_ = 0;
   cudaStream_t own_stream_ = nullptr, stream_ = nullptr;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
-  DBuf<int> d_type_, d_ioff_, d_poff_, d_soff_, d_itab_raw_, d_pcode_, d_save_;
+  DBuf<int> d_type_, d_ioff_, d_poff_, d_soff_, d_itab_raw_, d_pcode_, d_pdirect_, d_save_;
   DBuf<double> d_pval_, x_, rhs_, c_, lu_, st_op_, st_guess_, d_wave_, d_omega_, d_rows_;
   DBuf<GridCtl> d_gctl_;
   double symbolic_s_ = 0.0;  // host time spent in build_plan (diagnostics)
@@ -567,9 +629,11 @@ class Batch {
   PinnedBuf<double> pval_h_, hx_, hwave_;
   double* ext_x_ = nullptr;       // set_result_target
   size_t wave_T_ = 0, wave_ns_ = 0;
+  int repair_depth_ = 0;
+  long long weak_seen_ = 0, repaired_ = 0;
   int32_t* ext_tail_ = nullptr;
   PinnedBuf<int32_t> hstatus_, hiters_, hloads_;
-  std::vector<int> pcode_h_, poff_eff_;
+  std::vector<int> pcode_h_, poff_eff_, pdirect_h_;
   size_t pval_n_ = 0, h2d_bytes_ = 0;
   std::vector<Override> overrides_;
   bool params_dirty_ = true, rebuild_ = true, codes_dirty_ = true, rows_fresh_ = false;
@@ -755,6 +819,7 @@ class Batch {
     d.n_dev = (int)flat_.devs.size();
     d.type = d_type_.p; d.itab_off = d_ioff_.p; d.par_off = d_poff_.p; d.state_off = d_soff_.p;
     d.itab = itab; d.pcode = d_pcode_.p; d.pval = d_pval_.p; d.n_state = flat_.n_state;
+    d.par_direct = d_pdirect_.p;
     return d;
   }
   WorkTables<double> work() const {
@@ -886,7 +951,7 @@ class Batch {
       const std::vector<int>& poff = poff_eff_;
       for (const FlatDev& d : flat_.devs) { type.push_back(d.type); ioff.push_back(d.itab_off); soff.push_back(d.state_off); }
       auto& o = pd.ao;
-      o.type = put(type); o.itab_off = put(ioff); o.par_off = put(poff); o.state_off = put(soff); o.itab = put(itab); o.pcode = put(pcode_h_);
+      o.type = put(type); o.itab_off = put(ioff); o.par_off = put(poff); o.state_off = put(soff); o.itab = put(itab); o.pcode = put(pcode_h_); o.par_direct = put(pdirect_h_);
       o.row_i2e = put(P.row_i2e); o.col_i2e = put(P.col_i2e); o.col_e2i = put(P.col_e2i); o.rowptr = put(P.rowptr); o.colidx = put(P.colidx);
       o.diag_slot = put(P.diag_slot); o.stage_off = put(si_.stage_off); o.eval_order = put(si_.eval_order);
       o.asm_off = put(P.asm_off); o.asm_src = put(P.asm_src);
@@ -1025,6 +1090,16 @@ class Batch {
         }
         if (!found) firsts.push_back(k);
       }
+    }
+    // devices whose whole block is shared values: the kernels read it directly (engine.hpp DevTables::par_direct)
+    pdirect_h_.assign(flat_.devs.size(), 0);
+    static const bool allow_direct = [] { const char* e = std::getenv("S21_PAR_DIRECT"); return !e || std::atoi(e) != 0; }();
+    for (size_t k = 0; k < flat_.devs.size() && allow_direct; k++) {
+      const FlatDev& d = flat_.devs[k];
+      if (d.type != DT_BSIM4) continue;  // only the Bsim4 evaluation has a direct-block instantiation
+      bool all_shared = true;
+      for (int j = 0; j < d.n_par && all_shared; j++) all_shared = pcode_h_[(size_t)poff_eff_[k] + (size_t)j] == (int)(((size_t)poff_eff_[k] + (size_t)j) << 1);
+      pdirect_h_[k] = all_shared ? 1 : 0;
     }
     // a parameter change invalidates the frozen pivot orders (and the tables packed with them)
     op_plan_.valid = false; tran_plan_.valid = false; ac_plan_.valid = false;

@@ -305,6 +305,7 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
        "    const size_t src = (size_t)k * st_stride + (size_t)i0 + (size_t)(evalid ? ei : 0);\n"
        "    sop[k * PS + ei] = cold ? 0.0 : st_op[src];\n    sguess[k * PS + ei] = cold ? 0.0 : st_guess[src];\n  }\n"
        "  int r_stat = " << (tran ? "rvalid ? status[i0 + ri] : 0" : "0") << ";\n"
+       "  bool r_weak = (r_stat >> 8) & 1;\n  r_stat &= 0xff;\n"
        "  int r_nsol = 0, r_nld = 0;\n"
        "  __syncthreads();\n";
   if (tran)
@@ -409,8 +410,12 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
       if (anyL) {
         o << "            const double rp = s_rcp(piv);\n";  // one reciprocal per pivot, shared by the column's entries (scalar.h)
         if (fast) o << "            const bool pok = s_div_bok(piv);\n";
+        o << "            const double pth = fabs(piv) * 1e3;\n";  // pivot health: |pivot| < 1e-3 x an entry below it (kernels/newton.cu)
         for (int q = 0; q < Q; q++)
-          if (LM[(size_t)q][(size_t)k]) divide(A(q, k), A(q, k), "piv", "rp", "pok", mask_test(LM[(size_t)q][(size_t)k]));
+          if (LM[(size_t)q][(size_t)k]) {
+            o << "            r_weak = r_weak || (r_act && " << mask_test(LM[(size_t)q][(size_t)k]) << " != 0 && pth < fabs(" << A(q, k) << "));\n";
+            divide(A(q, k), A(q, k), "piv", "rp", "pok", mask_test(LM[(size_t)q][(size_t)k]));
+          }
         for (int s = P.diag_slot[(size_t)k] + 1; s < P.rowptr[(size_t)k + 1]; s++) {
           const int c = P.colidx[(size_t)s];
           o << "            { const double u = BC(" << A(qk, c) << ", " << jk << ");\n";
@@ -525,19 +530,19 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
     o << "    if (rvalid) {\n      const bool good = r_stat == 0;\n      for (int s = j; s < n_save; s += " << TM_LPI << ")\n"
          "        wave[((size_t)tp * n_save + s) * stride + i0 + ri] = good ? X[save_vars[s] * PS + ri] : __longlong_as_double(0x7ff8000000000000LL);\n"
          "    }\n";
-  o << "  }\n  __syncthreads();\n"
+  o << "  }\n  const bool weak_any = (__ballot_sync(FULLM, r_weak && rvalid) & imask) != 0;\n  __syncthreads();\n"
        "  if (evalid) {\n"
        "    for (int k = warp; k < " << N << "; k += " << NW << ") gx[(size_t)k * stride + i0 + ei] = X[k * PS + ei];\n"
        "    for (int k = warp; k < " << flat.n_state << "; k += " << NW << ") {\n"
        "      const size_t dst = (size_t)k * st_stride + i0 + ei;\n"
        "      st_op[dst] = sop[k * PS + ei];\n      st_guess[dst] = sguess[k * PS + ei];\n    }\n  }\n"
        "  if (rvalid && j == 0) {\n"
-       "    status[i0 + ri] = r_stat;\n"
+       "    status[i0 + ri] = r_stat | (weak_any ? 0x100 : 0);\n"
        "    iters[i0 + ri] = (cold ? 0 : iters[i0 + ri]) + r_nsol;\n"
        "    loads[i0 + ri] = (cold ? 0 : loads[i0 + ri]) + r_nld;\n  }\n";
   if (XP)  // the host's result layout (k_pack_out in kernels/newton.cu), written here so that a read needs no second kernel
     o << "  if (rows) {\n    __syncthreads();\n"
-         "    if (rvalid && j == 0) { int* tail = (int*)(rows + (size_t)B * " << N << "); tail[i0 + ri] = r_stat; tail[(size_t)B + i0 + ri] = iters[i0 + ri];"
+         "    if (rvalid && j == 0) { int* tail = (int*)(rows + (size_t)B * " << N << "); tail[i0 + ri] = r_stat | (weak_any ? 0x100 : 0); tail[(size_t)B + i0 + ri] = iters[i0 + ri];"
          " tail[2 * (size_t)B + i0 + ri] = loads[i0 + ri]; }\n"
          "    if (evalid) for (int k = warp; k < " << N << "; k += " << NW << ") rows[(size_t)(i0 + ei) * " << N << " + k] = X[k * PS + ei];\n  }\n";
   if (prof)

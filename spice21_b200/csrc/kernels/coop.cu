@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
   int* nsol = stat + gi;
   int* nld = nsol + gi;
   int* convnow = nld + gi;
-  uint64_t* mbar = (uint64_t*)(convnow + gi);
+  int* weak = convnow + gi;  // pivot health: a frozen pivot the reference's threshold test would have refused (mod.rs:735-783)
+  uint64_t* mbar = (uint64_t*)(weak + gi);
   size_t off = ((size_t)((unsigned char*)(mbar + 1) - smem_raw) + 15) / 16 * 16;
   if (a.arena_bytes > 0) {
     int* sa = (int*)(smem_raw + off);
@@ -67,7 +68,7 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
     // Rebase every table pointer onto the shared-memory copy. The new pointer must be DERIVED FROM `sa`: nvcc assumes
     // pointers that come from kernel arguments address global memory and would emit ld.global for them.
 #define RB(ptr) ptr = sa + ((ptr) - a.arena)
-    RB(d.type); RB(d.itab_off); RB(d.par_off); RB(d.state_off); RB(d.itab); RB(d.pcode);
+    RB(d.type); RB(d.itab_off); RB(d.par_off); RB(d.state_off); RB(d.itab); RB(d.pcode); if (d.par_direct) RB(d.par_direct);
     RB(p.row_i2e); RB(p.col_i2e); RB(p.col_e2i); RB(p.rowptr); RB(p.colidx); RB(p.diag_slot);
     RB(ct.stage_off); RB(ct.eval_order); RB(ct.asm_off); RB(ct.asm_src);
     RB(ct.lu_lvl_off); RB(ct.lu_t); RB(ct.lu_u); RB(ct.lu_l);
@@ -96,7 +97,8 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
 
   // ---- prologue
   if (tid < gi) {
-    stat[tid] = (tid < ni && KIND == K_TRAN) ? o.status[i0 + tid] : 0;
+    const int st0 = (tid < ni && KIND == K_TRAN) ? o.status[i0 + tid] : 0;
+    stat[tid] = st0 & 0xff; weak[tid] = (st0 >> 8) & 1;
     nsol[tid] = 0; nld[tid] = 0; convnow[tid] = 0; dxok[tid] = 1; act[tid] = 0;
   }
   if constexpr (SMEM) {
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
           e.x = x + col; e.xstride = ws;
           e.S = S + (I)ct.stage_off[dev] * ws + col;
           e.mode = ctl.mode; e.dt = ctl.dt; e.gmin = ctl.gmin; e.omega = omega;
-          load_one<T, B4>(d.type[dev], e);
+          load_one<T, B4>(d.type[dev], e, (d.par_direct && d.par_direct[dev]) ? d.pval + d.par_off[dev] : nullptr);
         }
       }
       if (tid < gi) { resok[tid] = 1; sing[tid] = 0; maxabs[tid] = 0.0; }
@@ -189,8 +191,12 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
             const int l = ct.lu_l[op];
             T* t = lu + (I)ct.lu_t[op] * ws + col;
             const T u = lu[(I)ct.lu_u[op] * ws + col];
-            if (l < 0) *t = s_div(*t, u);
-            else *t = s_sub(*t, s_mul(u, lu[(I)l * ws + col]));
+            if (l < 0) {
+              if (s_abs(u) * 1e3 < s_abs(*t)) weak[li] = 1;
+              *t = s_div(*t, u);
+            } else {
+              *t = s_sub(*t, s_mul(u, lu[(I)l * ws + col]));
+            }
           }
         }
         __syncthreads();
@@ -238,7 +244,7 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
         const double m = maxabs[li];
         for (int k = item0; k < N; k += istep) {
           T dxk = c[(I)p.col_e2i[k] * ws + col];
-          if (m > 1.0) dxk = s_scale(dxk, 1.0, m);
+          if (m > 1.0 && !(KIND == K_AC && ctl.ac_direct)) dxk = s_scale(dxk, 1.0, m);
           T* xv = x + (I)k * ws + col;
           *xv = s_add(*xv, dxk);
           if (!TolC<T>::ok(s_abs(dxk), vtol)) dxok[li] = 0;
@@ -247,7 +253,10 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
       __syncthreads();
       if (tid < gi && act[tid]) {
         if (sing[tid]) { act[tid] = 0; stat[tid] = CST_SINGULAR; }
-        else nsol[tid] += 1;
+        else {
+          nsol[tid] += 1;
+          if (KIND == K_AC && ctl.ac_direct) act[tid] = 0;  // linear system: x = A^-1 b is the answer (engine.hpp SolveCtl::ac_direct)
+        }
       }
       __syncthreads();
     }
@@ -276,13 +285,13 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
     }
   }
   if (tid < ni) {
-    o.status[i0 + tid] = stat[tid];
+    o.status[i0 + tid] = stat[tid] | (weak[tid] << 8);
     o.iters[i0 + tid] += nsol[tid];
     o.loads[i0 + tid] += nld[tid];
   }
 }
 
-size_t ctrl_bytes(int gi) { return ((8 + 8 * 4) * (size_t)gi + 8 + 15) / 16 * 16; }
+size_t ctrl_bytes(int gi) { return ((8 + 9 * 4) * (size_t)gi + 8 + 15) / 16 * 16; }
 
 template <class T, int KIND, bool B4>
 int launch_b4(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<T>& w, T* stage, const NewtonOut& o,

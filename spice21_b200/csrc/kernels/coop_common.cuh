@@ -69,7 +69,14 @@ struct EnvS {  // staged Env (see devices.cuh): stamps go to this device's priva
   __device__ __forceinline__ void add_g_dup(int, int dup, T v) { S[(I)dup * xstride] = v; }
 };
 
-template <class T, bool B4, class E> __device__ __forceinline__ void load_one(int type, E& e) {
+// Env of a device whose parameter block is all shared values: par(k) is one load at a literal offset from the block.
+template <class T, class I>
+struct EnvSD : EnvS<T, I> {
+  const double* pblk;
+  __device__ __forceinline__ double par(int k) const { return __ldg(pblk + k); }
+};
+
+template <class T, bool B4, class E> __device__ __forceinline__ void load_one(int type, E& e, const double* pblk = nullptr) {
   if constexpr (std::is_same<T, double>::value) {
     switch (type) {
       case DT_R: load_resistor(e); break;
@@ -79,7 +86,18 @@ template <class T, bool B4, class E> __device__ __forceinline__ void load_one(in
       case DT_DIODE: load_diode(e); break;
       case DT_MOS0: load_mos0(e); break;
       case DT_MOS1: load_mos1(e); break;
-      case DT_BSIM4: if constexpr (B4) load_bsim4(e); break;
+      case DT_BSIM4:
+        if constexpr (B4) {
+          if (pblk) {
+            EnvSD<T, decltype(e.xstride)> ed;
+            static_cast<E&>(ed) = e;
+            ed.pblk = pblk;
+            load_bsim4(ed);
+          } else {
+            load_bsim4(e);
+          }
+        }
+        break;
       default: break;
     }
   } else {

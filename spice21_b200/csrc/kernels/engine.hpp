@@ -20,6 +20,11 @@ struct DevTables {
   const int* pcode;     // (offset << 1) | per_instance
   const double* pval;   // parameter value pool
   int n_state;
+  // [n_dev] 1 when every parameter of the device is a shared value (no per-instance column): its block is then the
+  // contiguous run pval[par_off .. par_off + n_par) and can be read with ONE load at a literal offset instead of the
+  // code lookup + address arithmetic + load (ncu, C4: 37 % of the executed instructions of a Bsim4 evaluation were that
+  // arithmetic). nullptr = no device is direct.
+  const int* par_direct = nullptr;
 };
 
 // Static plan of the sparse LU (host/symbolic.hpp), in internal (pivoted) coordinates.
@@ -57,6 +62,10 @@ struct SolveCtl {
   double reltol, iabstol;  // real solve: |dx| <= reltol (absolute!) and |res| <= iabstol (analysis.rs:331-345)
   const double* omega;     // [B] AC only
   size_t par_inst_stride;  // 1: parameter/state instance == workspace instance; 0: all columns use instance 0 (AC sweep)
+  // AC only. 1 (default): the small-signal system is linear, so each frequency point is ONE factorisation + solve from
+  // x = 0 with no step limit (x = A^-1 b). 0: the reference's Newton shell (analysis.rs:253-303: 1.0 step limit, <= 20
+  // iterations, a second factorisation to confirm) — kept for iteration-count parity; it cannot reach |x| > ~19 from a cold start.
+  int ac_direct = 0;
   int has_bsim4 = 0;       // selects the kernel build that links the Bsim4 evaluation (kept out of the others: register pressure)
 };
 

@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256, B4 ? 1 : 2) k_grid(DevTables d, PlanTable
   const double vtol = ctl.reltol, itol = ctl.iabstol;
 
   if (tid == 0) {
-    gc->stat = KIND == K_TRAN ? o.status[0] : 0;
+    gc->stat = KIND == K_TRAN ? (o.status[0] & 0xff) : 0;
     gc->nsol = 0; gc->nld = 0; gc->dxok = 1; gc->act = 0; gc->resok = 1; gc->sing = 0; gc->maxabs = 0ull;
   }
   if constexpr (KIND == K_TRAN) {
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256, B4 ? 1 : 2) k_grid(DevTables d, PlanTable
         e.x = x; e.xstride = 1;
         e.S = S + (size_t)ct.stage_off[dev];
         e.mode = ctl.mode; e.dt = ctl.dt; e.gmin = ctl.gmin; e.omega = 0.0;
-        load_one<double, B4>(d.type[dev], e);
+        load_one<double, B4>(d.type[dev], e, (d.par_direct && d.par_direct[dev]) ? d.pval + d.par_off[dev] : nullptr);
       }
       if (tid == 0) { gc->resok = 1; gc->sing = 0; gc->maxabs = 0ull; }
       grid.sync();

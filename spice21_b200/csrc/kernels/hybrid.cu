@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256, 2) k_hyb(DevTables d, PlanTables p, CoopT
     }
     off += (size_t)a.arena_bytes;
 #define RB(ptr) ptr = sa + ((ptr) - a.arena)  // derived from the shared base on purpose (see coop.cu)
-    RB(d.type); RB(d.itab_off); RB(d.par_off); RB(d.state_off); RB(d.itab); RB(d.pcode);
+    RB(d.type); RB(d.itab_off); RB(d.par_off); RB(d.state_off); RB(d.itab); RB(d.pcode); if (d.par_direct) RB(d.par_direct);
     RB(p.row_i2e); RB(p.col_i2e); RB(p.col_e2i); RB(p.rowptr); RB(p.colidx); RB(p.diag_slot);
     RB(ct.stage_off); RB(ct.eval_order); RB(ct.asm_off); RB(ct.asm_src);
     RB(ct.lu_lvl_off); RB(ct.lu_t); RB(ct.lu_u); RB(ct.lu_l);
@@ -97,6 +97,8 @@ __global__ void __launch_bounds__(256, 2) k_hyb(DevTables d, PlanTables p, CoopT
   // per-instance control state lives in registers, replicated over the 8 lanes of the instance
   const bool rvalid = ri < ni;
   int r_stat = (rvalid && KIND == K_TRAN) ? o.status[i0 + ri] : 0;
+  bool r_weak = (r_stat >> 8) & 1;  // pivot health (bit 8 of the status word, see coop.cu)
+  r_stat &= 0xff;
   int r_nsol = 0, r_nld = 0;
   mbar_wait(mbar, 0);
   __syncthreads();
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(256, 2) k_hyb(DevTables d, PlanTables p, CoopT
           e.x = x + ei; e.xstride = HY_P;
           e.S = S + (I)ct.stage_off[dev] * HY_P + ei;
           e.mode = ctl.mode; e.dt = ctl.dt; e.gmin = ctl.gmin; e.omega = omega;
-          load_one<T, B4>(d.type[dev], e);
+          load_one<T, B4>(d.type[dev], e, (d.par_direct && d.par_direct[dev]) ? d.pval + d.par_off[dev] : nullptr);
         }
       }
       PH_T(t1);
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(256, 2) k_hyb(DevTables d, PlanTables p, CoopT
             const int l = ct.lu_l[op];
             T* t = lu + (I)ct.lu_t[op] * HY_P + ri;
             const T u = lu[(I)ct.lu_u[op] * HY_P + ri];
-            if (l < 0) *t = s_div(*t, u);
+            if (l < 0) { r_weak = r_weak || (s_abs(u) * 1e3 < s_abs(*t)); *t = s_div(*t, u); }
             else *t = s_sub(*t, s_mul(u, lu[(I)l * HY_P + ri]));
           }
         }
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(256, 2) k_hyb(DevTables d, PlanTables p, CoopT
       if (r_act && !sing) {
         for (int k = q; k < N; k += HY_LPI) {
           T dxk = c[(I)p.col_e2i[k] * HY_P + ri];
-          if (m > 1.0) dxk = s_scale(dxk, 1.0, m);
+          if (m > 1.0 && !(KIND == K_AC && ctl.ac_direct)) dxk = s_scale(dxk, 1.0, m);
           T* xv = x + (I)k * HY_P + ri;
           *xv = s_add(*xv, dxk);
           baddx = baddx || !TolC<T>::ok(s_abs(dxk), vtol);
@@ -249,7 +251,10 @@ __global__ void __launch_bounds__(256, 2) k_hyb(DevTables d, PlanTables p, CoopT
       r_dxok = (__ballot_sync(FULL, baddx) & imask) == 0;
       if (r_act) {
         if (sing) { r_act = false; r_stat = CST_SINGULAR; }
-        else r_nsol += 1;
+        else {
+          r_nsol += 1;
+          if (KIND == K_AC && ctl.ac_direct) r_act = false;  // linear system: one solve is the answer
+        }
       }
       if (q == 0) act_s[ri] = r_act ? 1 : 0;
       PH_T(t7);
@@ -270,6 +275,7 @@ __global__ void __launch_bounds__(256, 2) k_hyb(DevTables d, PlanTables p, CoopT
       }
     }
   }
+  const bool weak_any = (__ballot_sync(0xffffffffu, r_weak) & imask) != 0;  // any of the instance's lanes saw a weak pivot
   __syncthreads();
   // ---- epilogue: results back to HBM (lane = instance: coalesced)
   if (evalid) {
@@ -282,7 +288,7 @@ __global__ void __launch_bounds__(256, 2) k_hyb(DevTables d, PlanTables p, CoopT
       }
   }
   if (rvalid && q == 0) {
-    o.status[i0 + ri] = r_stat;
+    o.status[i0 + ri] = r_stat | (weak_any ? 0x100 : 0);
     o.iters[i0 + ri] = (cold ? 0 : o.iters[i0 + ri]) + r_nsol;
     o.loads[i0 + ri] = (cold ? 0 : o.loads[i0 + ri]) + r_nld;
   }

@@ -16,6 +16,8 @@
 // -fmad=false, so results differ from the CPU restatement only through libm's exp/log.
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "devices.cuh"
 #include "engine.hpp"
 
@@ -126,7 +128,7 @@ __device__ __forceinline__ void commit_state(const DevTables& d, double* st_op, 
 // The Newton shell for one instance. Returns an S21 status; *n_solves / *n_loads are incremented.
 template <class T, bool B4>
 __device__ int newton_solve(const DevTables& d, const PlanTables& p, const WorkTables<T>& wk, const SolveCtl& ctl, size_t inst,
-                            double omega, double vtol, double itol, bool do_commit, int* n_solves, int* n_loads) {
+                            double omega, double vtol, double itol, bool do_commit, int* n_solves, int* n_loads, int* weak) {
   const size_t S = wk.stride;
   T* x = wk.x + inst;
   T* rhs = wk.rhs + inst;
@@ -168,8 +170,11 @@ __device__ int newton_solve(const DevTables& d, const PlanTables& p, const WorkT
       const T piv = lu[(size_t)__ldg(p.diag_slot + k) * S];
       if (s_is_zero(piv)) return ST_SINGULAR_;
       const int lb = __ldg(p.l_off + k), le = __ldg(p.l_off + k + 1);
+      const double pth = s_abs(piv) * 1e3;
       for (int j = lb; j < le; j++) {
         T* a = lu + (size_t)__ldg(p.l_slot + j) * S;
+        // pivot health: the reference would not have taken this diagonal (|d| < 1e-3 * column max, mod.rs:735-783)
+        if (pth < s_abs(*a)) *weak = 1;
         *a = s_div(*a, piv);
       }
       const int ub = __ldg(p.upd_off + k), ue = __ldg(p.upd_off + k + 1);
@@ -204,7 +209,8 @@ __device__ int newton_solve(const DevTables& d, const PlanTables& p, const WorkT
       const double a = s_abs(c[(size_t)__ldg(p.col_e2i + k) * S]);
       if (a > max_abs) max_abs = a;
     }
-    const bool limit = max_abs > 1.0;
+    const bool direct = !std::is_same<T, double>::value && ctl.ac_direct;  // linear AC system: one solve is the answer
+    const bool limit = max_abs > 1.0 && !direct;
     dx_ok = true;
     for (int k = 0; k < N; k++) {
       T dxk = c[(size_t)__ldg(p.col_e2i + k) * S];
@@ -212,6 +218,7 @@ __device__ int newton_solve(const DevTables& d, const PlanTables& p, const WorkT
       x[(size_t)k * S] = s_add(x[(size_t)k * S], dxk);
       dx_ok = dx_ok && Tol<T>::ok(s_abs(dxk), vtol);
     }
+    if (direct) return ST_OK_;
   }
   return ST_CONV_;
 }
@@ -222,8 +229,9 @@ __global__ void __launch_bounds__(128) k_dcop(DevTables d, PlanTables p, WorkTab
   const size_t inst = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (inst >= (size_t)ctl.B) return;
   int ns = 0, nl = 0;
-  const int st = newton_solve<double, B4>(d, p, w, ctl, inst, 0.0, ctl.reltol, ctl.iabstol, true, &ns, &nl);
-  o.status[inst] = st;
+  int weak = 0;
+  const int st = newton_solve<double, B4>(d, p, w, ctl, inst, 0.0, ctl.reltol, ctl.iabstol, true, &ns, &nl, &weak);
+  o.status[inst] = st | (weak << 8);
   o.iters[inst] += ns;
   o.loads[inst] += nl;
 }
@@ -236,15 +244,16 @@ __global__ void __launch_bounds__(128) k_tran(DevTables d, PlanTables p, WorkTab
   const size_t B = w.stride;  // wave is [T][n_save][stride], instance fastest, like every other per-instance table
   int st = o.status[inst];  // status of the OP solve
   for (int s = 0; s < n_save; s++) wave[(size_t)s * B + inst] = w.x[(size_t)__ldg(save_vars + s) * w.stride + inst];
-  int ns = 0, nl = 0;
+  int ns = 0, nl = 0, weak = (st >> 8) & 1;
+  st &= 0xff;
   for (int tp = 1; tp < T; tp++) {
-    if (st == ST_OK_) st = newton_solve<double, B4>(d, p, w, ctl, inst, 0.0, ctl.reltol, ctl.iabstol, true, &ns, &nl);
+    if (st == ST_OK_) st = newton_solve<double, B4>(d, p, w, ctl, inst, 0.0, ctl.reltol, ctl.iabstol, true, &ns, &nl, &weak);
     for (int s = 0; s < n_save; s++) {
       const double v = st == ST_OK_ ? w.x[(size_t)__ldg(save_vars + s) * w.stride + inst] : __longlong_as_double(0x7ff8000000000000LL);
       wave[((size_t)tp * n_save + s) * B + inst] = v;
     }
   }
-  o.status[inst] = st;
+  o.status[inst] = st | (weak << 8);
   o.iters[inst] += ns;
   o.loads[inst] += nl;
 }
@@ -254,8 +263,9 @@ __global__ void __launch_bounds__(128) k_ac(DevTables d, PlanTables p, WorkTable
   if (inst >= (size_t)ctl.B) return;
   int ns = 0, nl = 0;
   // hard-coded complex tolerances (analysis.rs:271-272); no commit is observable in AC (load_ac reads only `op`)
-  const int st = newton_solve<cplx, false>(d, p, w, ctl, inst, ctl.omega[inst], 1e-3, 1e-9, false, &ns, &nl);
-  o.status[inst] = st;
+  int weak = 0;
+  const int st = newton_solve<cplx, false>(d, p, w, ctl, inst, ctl.omega[inst], 1e-3, 1e-9, false, &ns, &nl, &weak);
+  o.status[inst] = st | (weak << 8);
   o.iters[inst] += ns;
   o.loads[inst] += nl;
 }

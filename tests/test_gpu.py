@@ -282,13 +282,65 @@ def test_packed_device_results(s21):
     ptr, words = b.packed_device()
 
     class Dev:
-        __cuda_array_interface__ = {"shape": (words,), "typestr": "<f8", "data": (ptr, True), "version": 2}
+        __cuda_array_interface__ = {"shape": (words,), "typestr": "<f8", "data": (ptr, False), "version": 2}
 
     torch.cuda.synchronize()
     host = torch.as_tensor(Dev(), device="cuda").cpu().numpy()
     assert np.array_equal(host[: B * b.N].reshape(B, b.N), x)
     tail = host[B * b.N:].view(np.int32)
     assert np.array_equal(tail[:B], st) and np.array_equal(tail[B:2 * B], it)
+
+
+def _outlier_circuit():
+    """A stage whose gate node `x` hangs on the bias source through a resistor gx: the diagonal (x, x) is gx, the column
+    below it carries gm. With gx = 1 S the diagonal is a fine pivot; with gx = 1e-15 S it is 11 orders below gm, and the
+    reference's threshold test (|d| >= 1e-3 column max, mod.rs:735-783) refuses it."""
+    ck = Ckt().define("mos1model", "m", 0, **cc.C2_MODEL).define("mos1inst", "wl", **cc.C2_INST)
+    ck.V("vd", "vdd", GND, 1.8).V("vg", "g0", GND, 0.9).R("rg", "g0", "x", 1.0).R("rl", "vdd", "d", 5e-5).R("rs", "s", GND, 2e-4)
+    ck.M("m1", "m", "wl", d="d", g="x", s="s", b=GND)
+    return ck
+
+
+def test_outlier_instance_zero_pivot_order_is_repaired(s21, oracle, monkeypatch):
+    """The frozen pivot order comes from instance 0. Here instance 0 is the outlier (gx = 1 S) and every other instance has
+    gx = 1e-15 S, for which that order divides by a pivot far below the reference's 1e-3 threshold. The kernels flag it
+    (bit 8 of the status word), the host re-solves the flagged instances with a symbolic phase of their own, and the
+    results agree with the CPU restatement (which re-pivots every iteration) for every instance. With the repair switched
+    off the flag is still counted and the error of the frozen order is visible."""
+    B = 40
+    gx = np.full(B, 1e-15)
+    gx[0] = 1.0
+    gx[17] = 1.0
+    ck = _outlier_circuit()
+    o = oracle.Circuit(ck.to_text()).batch(0, B, overrides={"R:rg:g": gx})
+    assert np.all(o["status"] == 0)
+    c = ck.to_s21().elaborate()
+    b = s21.Batch(c, B)
+    b.override("R:rg:g", gx)
+    x, st, it = b.dcop()
+    ss = b.setup_stats()
+    print("pivot repair stats:", ss, b.kernel_name())
+    assert np.all(st == 0)
+    assert rel_err(x, o["x"], floor=1e-9) <= 1e-9
+    assert np.array_equal(it, o["iters"])
+    assert ss["weak_pivot_instances"] >= B - 2 and ss["repaired_instances"] >= B - 2
+    # the view path (what bench.py's end-to-end loop uses) repairs too
+    b.reset()
+    xv, stv, itv = b.dcop_view()
+    assert np.array_equal(xv, x) and np.all(stv == 0)
+    monkeypatch.setenv("S21_PIVOT_REPAIR", "0")
+    b2 = s21.Batch(c, B)
+    b2.override("R:rg:g", gx)
+    x2, st2, it2 = b2.dcop()
+    s2 = b2.setup_stats()
+    assert s2["weak_pivot_instances"] >= B - 2 and s2["repaired_instances"] == 0 and np.all(st2 < 0x100)
+    # an ordinary Monte-Carlo batch raises no flag
+    monkeypatch.delenv("S21_PIVOT_REPAIR")
+    b3 = s21.Batch(cc.diffpair().to_s21().elaborate(), 256)
+    for k, v in cc.diffpair_mc(256).items():
+        b3.override(k, v)
+    b3.dcop()
+    assert b3.setup_stats()["weak_pivot_instances"] == 0
 
 
 def test_per_instance_failure_is_contained(s21, oracle):
@@ -348,6 +400,55 @@ def test_ac_mos1_common_source(s21, oracle):  # tests.rs:1296-1325 (the referenc
     assert x0.shape == (1, c.n_vars)
 
 
+@pytest.mark.parametrize("pmos", [False, True], ids=["nmos", "pmos"])
+def test_ac_mos1_second_referee(s21, pmos):
+    """Row a18: Mos1::load_ac on the GPU against tests/mos1_referee.py, a numpy transcription of mos.rs written independently
+    of oracle/ (the reference pins no AC value): DC operating point, iteration count and the complex response over 7 decades."""
+    from test_oracle import _cs_amp
+    ck, dense = _cs_amp(pmos)
+    c = ck.to_s21().elaborate()
+    x, iters, ops = dense.dcop()
+    xg, st, it = s21.Batch(c, 1).dcop()
+    assert st[0] == 0 and it[0] == iters
+    for n in dense.names:
+        assert abs(xg[0, c.names.index(n)] - x[dense.ix[n]]) <= 1e-9 * max(1.0, abs(x[dense.ix[n]])), n
+    freqs = np.array([1e3, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10])
+    xa = dense.ac(ops, freqs)
+    xga, sta, _ = s21.Batch(c, 1).ac(freqs)
+    assert np.all(sta == 0)
+    for n in dense.names:
+        ref = xa[:, dense.ix[n]]
+        assert np.all(np.abs(xga[:, c.names.index(n)] - ref) <= 1e-9 * np.maximum(1.0, np.abs(ref))), n
+
+
+def test_ac_high_gain_needs_no_step_limit(s21, monkeypatch):
+    """A response above ~19 is out of reach of the reference's Newton shell from a cold start (1.0 step limit x 20
+    iterations, analysis.rs:253-303; the reference gets there only by warm-starting along the sweep). The batched sweep
+    solves each point directly (SolveCtl::ac_direct): gain ~ 100 comes back exact; S21_AC_NEWTON=1 restores the shell,
+    which reports Convergence Failed for those points."""
+    import mos1_referee as mr
+    model = mr.resolve_model(0, **cc.C2_MODEL)
+    ip = mr.derive(model, mr.resolve_inst(**cc.C2_INST))
+    ck = Ckt().define("mos1model", "m", 0, **cc.C2_MODEL).define("mos1inst", "wl", **cc.C2_INST)
+    ck.V("vd", "vdd", GND, 3.0).V("vg", "g", GND, 0.53, acm=1.0).R("rl", "vdd", "d", 5e-7).C("cl", "d", GND, 1e-13)
+    ck.M("m1", "m", "wl", d="d", g="g", s=GND, b=GND)
+    dense = mr.Dense([("V", "vd", "vdd", "", 3.0, 0.0), ("V", "vg", "g", "", 0.53, 1.0), ("R", "vdd", "d", 5e-7), ("C", "d", "", 1e-13),
+                      ("M", model, ip, "d", "g", "", "")])
+    x, iters, ops = dense.dcop()
+    freqs = np.array([1.0, 1e3, 1e5, 1e7, 1e9])
+    ref = dense.ac(ops, freqs, direct=True)
+    assert abs(ref[0, dense.ix["d"]]) > 50.0
+    c = ck.to_s21().elaborate()
+    xa, st, it = s21.Batch(c, 1).ac(freqs)
+    assert np.all(st == 0) and np.all(it == 1)
+    for n in dense.names:
+        r = ref[:, dense.ix[n]]
+        assert np.all(np.abs(xa[:, c.names.index(n)] - r) <= 1e-9 * np.maximum(1.0, np.abs(r))), n
+    monkeypatch.setenv("S21_AC_NEWTON", "1")
+    xb, stb, itb = s21.Batch(c, 1).ac(freqs)
+    assert stb[0] == s21.S21_CONVERGENCE_FAILED and stb[-1] == 0 and itb[-1] == 2  # low-frequency gain unreachable; 1 GHz point is small
+
+
 def test_ac_unsupported(s21):
     c = Ckt().R("r1", "a", GND, 1e-3).I("i1", "a", GND, 1e-3).to_s21().elaborate()
     with pytest.raises(s21.Spice21Error) as e:
@@ -394,6 +495,11 @@ def test_ac_rc_opamp_full_sweep_properties(s21, oracle):
     # the first points of the long sweep are the same frequencies the reference would visit: compare with the oracle
     o = oracle.Circuit(ck.to_text()).ac(fstart=1, fstop=10**10, npts=99999, max_points=1500)
     assert np.array_equal(o.axis, f[:1500]) and np.all(np.abs(x[:1500] - o.data) <= 1e-3 * np.abs(o.data) + 1e-6)
+    # every 10th point of the sweep (10 000 points) against the oracle's cold-start solve at the same frequency
+    # (oracle ac_at = what a one-point reference sweep computes there): round-off agreement
+    oa = oracle.Circuit(ck.to_text()).ac_at(f[::10])
+    assert oa.data.shape == (10000, c.n_vars)
+    assert np.max(np.abs(x[::10] - oa.data) / np.maximum(1.0, np.abs(oa.data))) <= 1e-9
     # frequency points are independent: a shuffled batch gives the shuffled answer bit for bit
     perm = np.random.default_rng(5).permutation(4096)
     x2, st2, _ = b.ac(f[:4096][perm])

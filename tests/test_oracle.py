@@ -174,3 +174,43 @@ def test_ac_unsupported_device(oracle):  # comps/mod.rs:86-88: Isrc has no load_
     with pytest.raises(oracle.OracleError) as e:
         oracle.Circuit(c.to_text()).ac(fstart=1, fstop=10, npts=2)
     assert e.value.status == 6
+
+
+# ------------------------------------------------------------------------------------------------ second referee (row a18)
+def _cs_amp(pmos=False):
+    """A common-source stage with a resistive load and a load capacitor, C2's Mos1 model (tox given: non-zero Meyer
+    capacitances, overlaps, body effect through a source degeneration resistor)."""
+    import mos1_referee as mr
+    sign = -1.0 if pmos else 1.0
+    ck = Ckt().define("mos1model", "m", 1 if pmos else 0, **dict(cc.C2_MODEL, vt0=sign * cc.C2_MODEL["vt0"])).define("mos1inst", "wl", **cc.C2_INST)
+    ck.V("vd", "vdd", GND, sign * 1.8).V("vg", "g", GND, sign * 0.9, acm=1.0)
+    ck.R("rl", "vdd", "d", 5e-5).R("rs", "s", GND, 2e-4).C("cl", "d", GND, 1e-13)
+    ck.M("m1", "m", "wl", d="d", g="g", s="s", b=GND)
+    model = mr.resolve_model(1 if pmos else 0, **dict(cc.C2_MODEL, vt0=sign * cc.C2_MODEL["vt0"]))
+    ip = mr.derive(model, mr.resolve_inst(**cc.C2_INST))
+    dense = mr.Dense([("V", "vd", "vdd", "", sign * 1.8, 0.0), ("V", "vg", "g", "", sign * 0.9, 1.0), ("R", "vdd", "d", 5e-5),
+                      ("R", "s", "", 2e-4), ("C", "d", "", 1e-13), ("M", model, ip, "d", "g", "s", "")])
+    return ck, dense
+
+
+@pytest.mark.parametrize("pmos", [False, True], ids=["nmos", "pmos"])
+def test_mos1_second_referee_agrees_with_oracle(oracle, pmos):
+    """tests/mos1_referee.py (numpy, written from mos.rs independently of oracle/) against the C++ restatement: the DC
+    operating point, its iteration count, and the AC response of Mos1::load_ac incl. its duplicated (G,dr) stamp."""
+    ck, dense = _cs_amp(pmos)
+    x, iters, ops = dense.dcop()
+    o = oracle.Circuit(ck.to_text()).dcop()
+    om = dict(zip(o.names, o.data[0]))
+    assert abs(ops[0]["ids"]) > 1e-5 and ops[0]["gmbs"] > 0.0  # the stage is biased on, with body effect (source degeneration)
+    for n in dense.names:
+        assert abs(x[dense.ix[n]] - om[n]) <= 1e-9 * max(1.0, abs(om[n])), n
+    assert iters == o.solves
+    freqs = [1e3, 1e6, 1e8, 1e9, 1e10]
+    xa = dense.ac(ops, freqs)
+    for k, f in enumerate(freqs):
+        oa = oracle.Circuit(ck.to_text()).ac(fstart=int(f), fstop=int(f), npts=1)
+        for n in dense.names:
+            ref = oa.get(n)[0]
+            assert abs(xa[k, dense.ix[n]] - ref) <= 1e-9 * max(1.0, abs(ref)), (f, n)
+    if not pmos:
+        assert abs(xa[0, dense.ix["d"]]) > 1.0 and abs(xa[-1, dense.ix["d"]]) < abs(xa[0, dense.ix["d"]])  # gain, then roll-off

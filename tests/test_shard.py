@@ -43,31 +43,36 @@ def test_shard_and_gather_gloo(world, n):
     assert len({s for _, _, s in res}) == 1  # every rank sees the same gathered totals
 
 
-def _agg_worker(rank, world, port, tran_fails_on, q):
-    import torch.distributed as dist
+def _agg_worker(rank, world, port, fails_on, q):
     sys.path.insert(0, ROOT)
+    import torch
     import bench
-    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    D = bench.Dist(backend="gloo", device="cpu")
     n = 64
-    iters = np.full(n, 10 + rank, dtype=np.int32)
-    status = np.zeros(n, dtype=np.int32)
-    tran_ms = None if rank == tran_fails_on else 5.0 + rank
-    times, tot, ok, tms = bench.aggregate(dist, world, None, (1.0 + rank, 0.5 + rank, 2.0 - rank), iters, status, tran_ms)
-    q.put((rank, times, tot, ok, tms))
-    dist.destroy_process_group()
+    # strong-scaling shard of a 200-instance problem, the device-side gather of equal blocks, and the reductions
+    lo, hi = bench.shard(200, rank, world, "strong")
+    wlo, whi = bench.shard(200, rank, world, "weak")
+    block = torch.full((n,), float(rank), dtype=torch.float64)
+    full = D.gather_device(block)
+    times = D.max_f([1.0 + rank, 0.5 + rank, 2.0 - rank])
+    maybe = D.max_f([None if rank == fails_on else 5.0 + rank])  # a value one rank could not measure is dropped everywhere
+    (tot,) = D.sum_i([n * (10 + rank)])
+    D.barrier()
+    q.put((rank, times, tot, maybe[0], full.tolist(), (lo, hi), (wlo, whi)))
+    D.close()
 
 
-@pytest.mark.parametrize("world,tran_fails_on", [(2, -1), (2, 1), (3, 0)])
-def test_bench_collectives_are_symmetric_gloo(world, tran_fails_on):
-    """bench.aggregate holds every collective of the multi-GPU measurement; every rank must come out of it with the same
-    totals — also when one rank could not measure the secondary (transient) metric, which then is dropped everywhere
-    instead of leaving the other ranks waiting in a collective (that hang cost a whole 8-GPU run)."""
+@pytest.mark.parametrize("world,fails_on", [(2, -1), (2, 1), (3, 0)])
+def test_bench_collectives_are_symmetric_gloo(world, fails_on):
+    """bench.Dist holds every collective of the multi-GPU measurement; every rank must come out of each with the same
+    totals — also when one rank could not measure a secondary configuration, which then is dropped everywhere instead of
+    leaving the other ranks waiting in a collective (that hang cost a whole 8-GPU run in round 1)."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 31500 + (os.getpid() + world * 13 + tran_fails_on) % 2000
-    procs = [ctx.Process(target=_agg_worker, args=(r, world, port, tran_fails_on, q)) for r in range(world)]
+    port = 31500 + (os.getpid() + world * 13 + fails_on) % 2000
+    procs = [ctx.Process(target=_agg_worker, args=(r, world, port, fails_on, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=120) for _ in range(world))
@@ -75,9 +80,12 @@ def test_bench_collectives_are_symmetric_gloo(world, tran_fails_on):
         p.join(timeout=60)
     want_times = [1.0 + world - 1, 0.5 + world - 1, 2.0]
     want_tot = 64 * sum(10 + r for r in range(world))
-    for rank, times, tot, ok, tms in res:
-        assert times == want_times and tot == want_tot and ok
-        assert tms == (None if tran_fails_on >= 0 else 5.0 + world - 1)
+    want_full = [float(r) for r in range(world) for _ in range(64)]
+    per = -(-200 // world)
+    for rank, times, tot, maybe, full, (lo, hi), (wlo, whi) in res:
+        assert times == want_times and tot == want_tot and full == want_full
+        assert maybe == (None if fails_on >= 0 else 5.0 + world - 1)
+        assert (lo, hi) == (min(200, rank * per), min(200, (rank + 1) * per)) and (wlo, whi) == (rank * 200, (rank + 1) * 200)
 
 
 def test_shard_bounds_cover_everything():
