@@ -520,13 +520,14 @@ def measure_c3(args, D, s21, cc, torch, stream, rings, points=20):
     save = np.array([c.names.index(n) for n in ("vddi", "r0s0", "r0s1")], dtype=np.int32)
     t, w, st_, it = b.tran(1e-11, points * 1e-11, save=save)
     wall1 = time.perf_counter() - t0
-    ms1, stt, ss = b.stats()["device_ms"], b.stats(), b.setup_stats()
+    ms1, stt, ss, pi = b.stats()["device_ms"], b.stats(), b.setup_stats(), b.plan_info()
     assert st_[0] == 0
     return {"workload": f"C3: ONE circuit of {rings} five-stage Mos1 ring oscillators on a shared supply node = {rings * 10} transistors, "
                         f"N={stt['n']}, transient {len(t) - 1} points of 1e-11 s (replicas only: not sharded)",
             "metric": "tran_timepoints_per_sec", "value": (len(t) - 1) / (ms1 * 1e-3), "unit": "timepoints/s", "ms_per_timepoint": ms1 / (len(t) - 1),
             "newton_iters_per_sec": int(it[0]) / (ms1 * 1e-3), "newton_iters": int(it[0]), "n": stt["n"], "nnz_a": stt["nnz_a"], "nnz_lu": stt["nnz_lu"],
             "kernel": KERNEL_NAMES.get(b.kernel_name(), b.kernel_name()), "host_symbolic_s": ss["symbolic_s"], "first_call_wall_s": wall1,
+            "plan": pi, "grid_barriers_per_newton_iter": pi["lu_levels"] + pi["fw_levels"] + pi["bw_levels"] + 8,
             "_ms": ms1, "_iters": int(it[0])}
 
 

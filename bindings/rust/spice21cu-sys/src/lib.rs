@@ -58,6 +58,7 @@ extern "C" {
     pub fn s21_batch_set_stream(b: *mut s21_batch, cuda_stream: *mut c_void) -> i32;
     pub fn s21_batch_override(b: *mut s21_batch, spec: *const c_char, values: *const f64) -> i32;
     pub fn s21_batch_sync_params(b: *mut s21_batch, force_upload: i32, h2d_bytes: *mut usize) -> i32;
+    pub fn s21_batch_set_aids(b: *mut s21_batch, flags: i32) -> i32;
     pub fn s21_batch_reset(b: *mut s21_batch) -> i32;
     pub fn s21_batch_dcop(b: *mut s21_batch, x: *mut f64, status: *mut i32, iters: *mut i32) -> i32;
     pub fn s21_batch_dcop_device(b: *mut s21_batch) -> i32;
@@ -67,11 +68,13 @@ extern "C" {
     pub fn s21_batch_wave_device(b: *const s21_batch, dev_ptr: *mut *const f64, T: *mut usize, n_save: *mut usize, stride: *mut usize) -> i32;
     pub fn s21_tran_num_points(tstep: f64, tstop: f64) -> i64;
     pub fn s21_batch_tran(b: *mut s21_batch, tstep: f64, tstop: f64, save_vars: *const i32, n_save: usize, time: *mut f64, wave: *mut f64, status: *mut i32, iters: *mut i64) -> i32;
+    pub fn s21_batch_tran_adaptive(b: *mut s21_batch, tstep: f64, tstop: f64, ctl7: *const f64, save_vars: *const i32, n_save: usize, time: *mut f64, wave: *mut f64, status: *mut i32, iters: *mut i64, accepted: *mut i32, rejected: *mut i32) -> i32;
     pub fn s21_ac_freqs(fstart: u64, fstop: u64, npts: u64, freqs: *mut f64, cap: usize) -> i64;
     pub fn s21_batch_ac(b: *mut s21_batch, freqs: *const f64, F: usize, x: *mut f64, status: *mut i32, iters: *mut i32) -> i32;
     pub fn s21_batch_pivot_order(b: *const s21_batch, row_i2e: *mut *const i32, col_i2e: *mut *const i32, n: *mut usize, lu_row: *mut *const i32, lu_col: *mut *const i32, lu_is_fill: *mut *const i32, nnz_lu: *mut usize) -> i32;
     pub fn s21_batch_stats(b: *const s21_batch, out8: *mut f64) -> i32;
     pub fn s21_batch_kernel_name(b: *const s21_batch) -> *const c_char;
+    pub fn s21_batch_plan_info(b: *const s21_batch, out8: *mut i64) -> i32;
     pub fn s21_batch_setup_stats(b: *const s21_batch, out8: *mut f64) -> i32;
     pub fn s21_sweep_partition(B: usize, n_devices: i32, g: i32, first: *mut usize, count: *mut usize) -> i32;
     pub fn s21_sweep_create(c: *const s21_ckt, n_devices: i32, devices: *const i32, B: usize, out: *mut *mut s21_sweep) -> i32;

@@ -110,6 +110,12 @@ int32_t s21_batch_override(s21_batch* b, const char* spec, const double* values)
  * the host->device copy is repeated even when nothing changed (the per-step input transfer of an end-to-end run).
  * *h2d_bytes (may be NULL) receives the bytes copied. The solves call this implicitly with force_upload = 0. */
 int32_t s21_batch_sync_params(s21_batch* b, int32_t force_upload, size_t* h2d_bytes);
+/* Convergence aids for s21_batch_dcop / _dcop_view (opt-in, default 0 = the reference's behaviour:
+ * its `src_factor` / `diag_gmin` options are dead fields, analysis.rs:659-660, and a solve that exceeds 100 iterations is
+ * "Convergence Failed"). flags bit 0: gmin stepping (junction gmin from 1e-2 S down a decade per warm-started solve to
+ * Options.gmin); bit 1: source stepping (all independent sources at 0.1, 0.2 ... 1.0 of their value, warm-started).
+ * Only the instances that failed are continued, in a batch of their own; the others keep their result. */
+int32_t s21_batch_set_aids(s21_batch* b, int32_t flags);
 /* Zero the solution guess and all device state (a fresh Solver: x = 0, op = guess = default). */
 int32_t s21_batch_reset(s21_batch* b);
 
@@ -137,6 +143,16 @@ int32_t s21_batch_wave_device(const s21_batch* b, const double** dev_ptr, size_t
 int64_t s21_tran_num_points(double tstep, double tstop);
 int32_t s21_batch_tran(s21_batch* b, double tstep, double tstop, const int32_t* save_vars, size_t n_save, double* time,
                        double* wave, int32_t* status, int64_t* iters);
+/* Adaptive-step transient (opt-in; SURVEY section 8 f1 — the reference integrates with a fixed step only, analysis.rs:553-570,
+ * and never reads its own `trtol` / `chgtol` options, :650-656): OP at t = 0, IC release, then every instance advances on
+ * its own time axis with Backward Euler, a local-truncation-error estimate per step (the BE solution against the linear
+ * extrapolation of the two previous accepted points), step rejection and step-size control — all on the device. Results
+ * are returned on the SAME print grid as s21_batch_tran (t_k = k * tstep), by linear interpolation between accepted
+ * points. ctl7 (may be NULL) = {h0 first step, hmin, hmax, trtol, reltol, vntol, reserved}; entries <= 0 take the
+ * defaults tstep/16, tstep*1e-9, 4*tstep, 7, 1e-3, 1e-6. accepted / rejected [B] (may be NULL) count each instance's
+ * steps. The fixed-step entry point above stays the parity path. */
+int32_t s21_batch_tran_adaptive(s21_batch* b, double tstep, double tstop, const double* ctl7, const int32_t* save_vars, size_t n_save,
+                                double* time, double* wave, int32_t* status, int64_t* iters, int32_t* accepted, int32_t* rejected);
 /* ac (analysis.rs:761-832) with the frequency points as the batch axis of ONE circuit instance (B is ignored;
  * the DC operating point is solved first). freqs[F] in Hz as produced by s21_ac_freqs; x[F][N][2] = (re, im). */
 int64_t s21_ac_freqs(uint64_t fstart, uint64_t fstop, uint64_t npts, double* freqs, size_t cap);
@@ -154,13 +170,19 @@ int32_t s21_batch_stats(const s21_batch* b, double* out8);
  * "direct"); valid until the next solve. The choice depends on circuit size, device content and batch size. */
 const char* s21_batch_kernel_name(const s21_batch* b);
 
+/* Shape of the numeric plan the last solve ran on (host/symbolic.hpp): [0] N, [1] nnz(L+U), [2] LU operations,
+ * [3] LU dependency levels, [4] forward-substitution operations, [5] forward levels, [6] backward levels, [7] 1 when the
+ * level schedules are in tolerance mode (same-target updates share a level and are applied atomically; the default for one
+ * large circuit on the grid-wide kernel, S21_PLAN_EXACT=1 restores the reference's per-value order). The level counts are
+ * the barriers per Newton iteration of the level-scheduled kernels. */
+int32_t s21_batch_plan_info(const s21_batch* b, int64_t* out8);
 /* Setup cost behind the solves of this process (none of it is per Newton iteration): [0] host seconds this batch spent in
  * the symbolic phase (Markowitz order + fill + level schedules), [1] seconds spent inside NVRTC by the whole process,
  * [2] NVRTC compilations, [3] kernels taken from the on-disk cubin cache ($S21_CACHE_DIR, default ~/.cache/spice21cu;
  * "off" disables), [4] from the in-process cache; [5] instances whose solves met a weak frozen pivot (|pivot| < 1e-3 x an
  * entry below it: the reference, which re-pivots every iteration (sparse21/mod.rs:735-783), would have chosen otherwise) or
  * an exactly zero one, [6] instances re-solved with a symbolic phase of their own because of it (dcop; S21_PIVOT_REPAIR=0
- * disables); [7] reserved (0). */
+ * disables); [7] instances rescued by the convergence aids (s21_batch_set_aids). */
 int32_t s21_batch_setup_stats(const s21_batch* b, double* out8);
 
 /* ---- multi-GPU sweeps: ONE process, one host thread + CUDA stream per GPU ---------------------

@@ -33,7 +33,7 @@ ABI_SYMBOLS = [
     "s21_batch_destroy", "s21_batch_set_stream", "s21_batch_override", "s21_batch_sync_params", "s21_batch_reset", "s21_batch_dcop",
     "s21_batch_dcop_device", "s21_batch_read", "s21_tran_num_points", "s21_batch_tran", "s21_ac_freqs", "s21_batch_ac",
     "s21_batch_pivot_order", "s21_batch_dcop_view", "s21_batch_stats", "s21_batch_kernel_name", "s21_jit_source", "s21_jit_check", "s21_selftest_div", "s21_symbolic",
-    "s21_batch_setup_stats", "s21_batch_packed_device", "s21_batch_wave_device", "s21_sweep_partition", "s21_sweep_create", "s21_sweep_destroy", "s21_sweep_num_devices", "s21_sweep_shard",
+    "s21_batch_setup_stats", "s21_batch_plan_info", "s21_batch_tran_adaptive", "s21_batch_set_aids", "s21_batch_packed_device", "s21_batch_wave_device", "s21_sweep_partition", "s21_sweep_create", "s21_sweep_destroy", "s21_sweep_num_devices", "s21_sweep_shard",
     "s21_sweep_override", "s21_sweep_sync_params", "s21_sweep_reset", "s21_sweep_dcop", "s21_sweep_dcop_view", "s21_sweep_tran", "s21_sweep_ac",
     "s21_sweep_stats",
 ]
@@ -105,6 +105,9 @@ def lib():
         L.s21_jit_check.argtypes = [C.c_char_p, C.c_size_t]
         L.s21_selftest_div.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
         L.s21_batch_setup_stats.argtypes = [C.c_void_p, C.c_void_p]
+        L.s21_batch_plan_info.argtypes = [C.c_void_p, C.c_void_p]
+        L.s21_batch_set_aids.argtypes = [C.c_void_p, C.c_int32]
+        L.s21_batch_tran_adaptive.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_size_t] + [C.c_void_p] * 6
         L.s21_batch_packed_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.s21_batch_wave_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
         L.s21_sweep_partition.argtypes = [C.c_size_t, C.c_int32, C.c_int32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
@@ -370,6 +373,10 @@ class Batch:
     def reset(self):
         _check(lib().s21_batch_reset(self.h))
 
+    def set_aids(self, gmin_stepping=False, source_stepping=False):
+        """Opt-in convergence aids for dcop (s21_batch_set_aids); the reference has none."""
+        _check(lib().s21_batch_set_aids(self.h, (1 if gmin_stepping else 0) | (2 if source_stepping else 0)))
+
     def dcop(self):
         x = np.zeros((self.B, self.N))
         status = np.zeros(self.B, dtype=np.int32)
@@ -428,6 +435,19 @@ class Batch:
                                     iters.ctypes.data_as(C.c_void_p)))
         return time, wave, status, iters
 
+    def tran_adaptive(self, tstep, tstop, save=None, h0=0.0, hmin=0.0, hmax=0.0, trtol=0.0, reltol=0.0, vntol=0.0):
+        """LTE-controlled adaptive-step transient on the print grid k * tstep (s21_batch_tran_adaptive). Returns
+        (time, wave[B][T][n_save], status, iters, accepted_steps, rejected_steps); 0 = default for every control."""
+        T = lib().s21_tran_num_points(tstep, tstop)
+        save = np.arange(self.N, dtype=np.int32) if save is None else np.ascontiguousarray(save, dtype=np.int32)
+        ctl = np.array([h0, hmin, hmax, trtol, reltol, vntol, 0.0])
+        time, wave = np.zeros(T), np.zeros((self.B, T, len(save)))
+        status, iters = np.zeros(self.B, dtype=np.int32), np.zeros(self.B, dtype=np.int64)
+        acc, rej = np.zeros(self.B, dtype=np.int32), np.zeros(self.B, dtype=np.int32)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        _check(lib().s21_batch_tran_adaptive(self.h, tstep, tstop, p(ctl), p(save), len(save), p(time), p(wave), p(status), p(iters), p(acc), p(rej)))
+        return time, wave, status, iters, acc, rej
+
     def ac(self, freqs):
         f = np.ascontiguousarray(freqs, dtype=np.float64)
         x = np.zeros((len(f), self.N, 2))
@@ -456,13 +476,20 @@ class Batch:
         """Which Newton kernel the last solve ran on (s21_batch_kernel_name)."""
         return lib().s21_batch_kernel_name(self.h).decode()
 
+    def plan_info(self):
+        """Shape of the numeric plan of the last solve (s21_batch_plan_info): sizes, operation and level counts."""
+        v = np.zeros(8, dtype=np.int64)
+        _check(lib().s21_batch_plan_info(self.h, v.ctypes.data_as(C.c_void_p)))
+        return {"n": int(v[0]), "nnz_lu": int(v[1]), "lu_ops": int(v[2]), "lu_levels": int(v[3]), "fw_ops": int(v[4]), "fw_levels": int(v[5]),
+                "bw_levels": int(v[6]), "relaxed": bool(v[7])}
+
     def setup_stats(self):
         """Setup cost behind the solves (s21_batch_setup_stats): host symbolic seconds of this batch, NVRTC seconds / runs and
         cubin-cache hits of the process."""
         s = np.zeros(8)
         _check(lib().s21_batch_setup_stats(self.h, s.ctypes.data_as(C.c_void_p)))
         return {"symbolic_s": float(s[0]), "nvrtc_s": float(s[1]), "nvrtc_runs": int(s[2]), "disk_hits": int(s[3]), "mem_hits": int(s[4]),
-                "weak_pivot_instances": int(s[5]), "repaired_instances": int(s[6])}
+                "weak_pivot_instances": int(s[5]), "repaired_instances": int(s[6]), "aided_instances": int(s[7])}
 
 
 def sweep_partition(B, n_devices, g):

@@ -315,6 +315,12 @@ int32_t s21_batch_sync_params(s21_batch* b, int32_t force_upload, size_t* h2d_by
   return S21_OK;
   S21_CATCH
 }
+int32_t s21_batch_set_aids(s21_batch* b, int32_t flags) {
+  S21_TRY
+  b->b->set_aids(flags);
+  return S21_OK;
+  S21_CATCH
+}
 int32_t s21_batch_reset(s21_batch* b) {
   S21_TRY
   b->b->reset();
@@ -369,6 +375,15 @@ int32_t s21_batch_tran(s21_batch* b, double tstep, double tstop, const int32_t* 
   return S21_OK;
   S21_CATCH
 }
+int32_t s21_batch_tran_adaptive(s21_batch* b, double tstep, double tstop, const double* ctl7, const int32_t* save_vars, size_t n_save, double* time,
+                                double* wave, int32_t* status, int64_t* iters, int32_t* accepted, int32_t* rejected) {
+  S21_TRY
+  std::vector<double> t = tran_times(tstep, tstop);
+  if (time) std::memcpy(time, t.data(), t.size() * sizeof(double));
+  b->b->tran_adaptive(tstep, (int)t.size(), ctl7, save_vars, n_save, wave, status, iters, accepted, rejected);
+  return S21_OK;
+  S21_CATCH
+}
 int64_t s21_ac_freqs(uint64_t fstart, uint64_t fstop, uint64_t npts, double* freqs, size_t cap) {
   std::vector<double> f = ac_freqs(fstart, fstop, npts);
   if (freqs) for (size_t k = 0; k < f.size() && k < cap; k++) freqs[k] = f[k];
@@ -404,6 +419,16 @@ int32_t s21_batch_stats(const s21_batch* b, double* out8) {
 
 const char* s21_batch_kernel_name(const s21_batch* b) { return b && b->b ? b->b->kernel_name() : ""; }
 
+int32_t s21_batch_plan_info(const s21_batch* b, int64_t* out8) {
+  S21_TRY
+  const Plan* p = b->b->last_plan();
+  if (!p) throw S21Error(ST_OTHER, "no solve has run on this batch yet");
+  auto levels = [](const std::vector<int>& off) { return off.empty() ? (int64_t)0 : (int64_t)off.size() - 1; };
+  out8[0] = p->N; out8[1] = p->nnzLU; out8[2] = (int64_t)p->lu_t.size(); out8[3] = levels(p->lu_lvl_off);
+  out8[4] = (int64_t)p->fw_k.size(); out8[5] = levels(p->fw_lvl_off); out8[6] = levels(p->bw_lvl_off); out8[7] = p->relaxed ? 1 : 0;
+  return S21_OK;
+  S21_CATCH
+}
 int32_t s21_batch_setup_stats(const s21_batch* b, double* out8) {
   S21_TRY
   const jit::CacheStats& cs = jit::cache_stats();
@@ -411,7 +436,7 @@ int32_t s21_batch_setup_stats(const s21_batch* b, double* out8) {
   out8[1] = cs.nvrtc_seconds; out8[2] = (double)cs.nvrtc_runs; out8[3] = (double)cs.disk_hits; out8[4] = (double)cs.mem_hits;
   out8[5] = b && b->b ? (double)b->b->weak_seen() : 0.0;
   out8[6] = b && b->b ? (double)b->b->repaired() : 0.0;
-  out8[7] = 0.0;
+  out8[7] = b && b->b ? (double)b->b->aided() : 0.0;
   return S21_OK;
   S21_CATCH
 }

@@ -8,6 +8,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <functional>
+#include <memory>
 #include <thread>
 
 #include "../kernels/engine.hpp"
@@ -340,6 +342,11 @@ class Batch {
     weak_seen_ += (long long)flagged.size();
     if (!flagged.empty() && want_x && last_plan_ == &op_plan_ && pivot_repair_enabled() && repair_depth_ < 4)
       repair_dcop(flagged, ext_x_ ? ext_x_ : hx_.p, hs, hi, hl);
+    if (aids_ && want_x && last_plan_ == &op_plan_ && repair_depth_ == 0) {
+      std::vector<size_t> failed;
+      for (size_t i = 0; i < B_; i++) if (hs[i] == ST_CONV) failed.push_back(i);
+      if (!failed.empty()) aid_dcop(failed, ext_x_ ? ext_x_ : hx_.p, hs, hi, hl);
+    }
     sum_iters_ = 0; sum_loads_ = 0;
     for (size_t i = 0; i < B_; i++) {
       sum_iters_ += hi[i];
@@ -350,6 +357,122 @@ class Batch {
     if (iters) *iters = hi;
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, ev0_, ev1_) == cudaSuccess) last_ms_ = ms;
+  }
+  // ---- convergence aids (second half; opt-in — the reference has neither: `src_factor` and `diag_gmin` are
+  // dead fields, analysis.rs:659-660, so with the aids off a failing instance reports Convergence Failed exactly as the
+  // reference does). Instances that failed a dcop are gathered into a batch of their own and continued:
+  //   bit 0, gmin stepping: the junction gmin of every device (Options.gmin, read by Mos1 / Diode / Bsim4) starts at 1e-2 S
+  //     and falls a decade per solve down to its target, every solve warm-started from the previous one;
+  //   bit 1, source stepping: every independent source is scaled by 0.1, 0.2, ... 1.0, warm-started likewise — each solve
+  //     has the reference's 100 iterations and 1 V step limit, so a chain that needs more than 100 iterations to settle
+  //     (a long ring released from one IC) gets there in stages.
+  // x and the committed device state of the rescued instances replace the failed ones (host rows and HBM columns).
+  void set_aids(int flags) { aids_ = flags; }
+  // The operating point that opens a transient: with aids on, instances whose OP failed are continued before the time loop
+  // (their x and device state columns are replaced in HBM, their status cleared).
+  void rescue_op() {
+    if (!aids_ || repair_depth_ != 0) return;
+    last_plan_ = &op_plan_;
+    const double* hx; const int32_t *hs, *hi;
+    read_view(true, &hx, &hs, &hi);
+  }
+  long long aided() const { return aided_; }
+  void copy_instance_from(const Batch& sub, size_t k, size_t i) {
+    const int N = flat_.n_vars();
+    S21_CUDA(cudaMemcpy2DAsync(x_.p + i, Bs_ * sizeof(double), sub.x_.p + k, sub.Bs_ * sizeof(double), sizeof(double), (size_t)N,
+                               cudaMemcpyDeviceToDevice, stream_));
+    if (flat_.n_state > 0) {
+      S21_CUDA(cudaMemcpy2DAsync(st_op_.p + i, Bs_ * sizeof(double), sub.st_op_.p + k, sub.Bs_ * sizeof(double), sizeof(double),
+                                 (size_t)flat_.n_state, cudaMemcpyDeviceToDevice, stream_));
+      S21_CUDA(cudaMemcpy2DAsync(st_guess_.p + i, Bs_ * sizeof(double), sub.st_guess_.p + k, sub.Bs_ * sizeof(double), sizeof(double),
+                                 (size_t)flat_.n_state, cudaMemcpyDeviceToDevice, stream_));
+    }
+  }
+  void aid_dcop(const std::vector<size_t>& failed, double* hx, int32_t* hs, int32_t* hi, int32_t* hl) {
+    const int N = flat_.n_vars();
+    std::vector<size_t> todo = failed;
+    auto make_sub = [&](const std::vector<size_t>& list, double src_factor) {
+      std::unique_ptr<Batch> sub(new Batch(spec_, flat_, device_, list.size()));
+      sub->repair_depth_ = 1;  // no nested aids; pivot repair stays available
+      sub->allow_jit_ = false;
+      sub->set_stream(stream_);
+      std::vector<double> vals(list.size());
+      for (const Override& o : overrides_) {
+        const bool is_src = (o.kind == "V" || o.kind == "I") && o.param != "acm";
+        for (size_t k = 0; k < list.size(); k++) vals[k] = o.values[list[k]] * (is_src ? src_factor : 1.0);
+        sub->add_override(o.kind + ":" + o.name + ":" + o.param, vals.data());
+      }
+      if (src_factor != 1.0)  // sources without a per-instance override: scale their shared value
+        for (const FlatDev& d : flat_.devs) {
+          if ((d.type != DT_V && d.type != DT_I) || d.is_ic) continue;
+          bool has = false;
+          for (const Override& o : overrides_) has = has || ((o.kind == (d.type == DT_V ? "V" : "I")) && o.name == d.path && o.param != "acm");
+          if (has) continue;
+          const double base = flat_.par[(size_t)d.par_off + (size_t)(d.type == DT_V ? VP_V_OP : IP_I)];
+          std::fill(vals.begin(), vals.end(), base * src_factor);
+          sub->add_override(std::string(d.type == DT_V ? "V:" : "I:") + d.path + ":dc", vals.data());
+        }
+      return sub;
+    };
+    auto harvest = [&](Batch& sub, const std::vector<size_t>& list, const int32_t* ss, const int64_t* it_sum, const int64_t* ld_sum,
+                       const double* sx) {
+      std::vector<size_t> still;
+      for (size_t k = 0; k < list.size(); k++) {
+        const size_t i = list[k];
+        if (ss[k] != ST_OK) { still.push_back(i); continue; }
+        std::memcpy(hx + i * (size_t)N, sx + k * (size_t)N, (size_t)N * sizeof(double));
+        hs[i] = ST_OK;
+        hi[i] += (int32_t)it_sum[k];
+        hl[i] += (int32_t)ld_sum[k];
+        copy_instance_from(sub, k, i);
+        S21_CUDA(cudaMemcpyAsync(status_.p + i, hs + i, sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
+        aided_++;
+      }
+      S21_CUDA(cudaStreamSynchronize(stream_));
+      return still;
+    };
+    // run a ladder of warm-started solves on `sub`; per-instance iteration totals accumulate over the rungs
+    auto ladder = [&](Batch& sub, size_t n, int rungs, const std::function<void(int)>& set_rung, std::vector<int32_t>* st_out,
+                      std::vector<int64_t>* it_sum, std::vector<int64_t>* ld_sum, std::vector<double>* x_out) {
+      it_sum->assign(n, 0); ld_sum->assign(n, 0);
+      for (int r = 0; r < rungs; r++) {
+        set_rung(r);
+        sub.dcop_device();  // warm: no reset between rungs
+        const double* sx; const int32_t *ss, *si;
+        sub.read_view(true, &sx, &ss, &si);
+        const int32_t* sl = si + n;
+        for (size_t k = 0; k < n; k++) { (*it_sum)[k] += si[k]; (*ld_sum)[k] += sl[k]; }
+        if (r == rungs - 1) { st_out->assign(ss, ss + n); x_out->assign(sx, sx + n * (size_t)N); }
+      }
+    };
+    std::vector<int32_t> st;
+    std::vector<int64_t> its, lds;
+    std::vector<double> xs;
+    if ((aids_ & 1) && !todo.empty()) {
+      std::unique_ptr<Batch> sub = make_sub(todo, 1.0);
+      const double target = flat_.opts.gmin;
+      std::vector<double> gs;
+      for (double g = 1e-2; g > target * 1.0001; g *= 0.1) gs.push_back(g);
+      gs.push_back(target);
+      ladder(*sub, todo.size(), (int)gs.size(), [&](int r) { sub->gmin_eff_ = gs[(size_t)r]; }, &st, &its, &lds, &xs);
+      todo = harvest(*sub, todo, st.data(), its.data(), lds.data(), xs.data());
+    }
+    if ((aids_ & 2) && !todo.empty()) {
+      // the source values live in the parameter pool: one sub-batch per rung would lose the warm start, so the rungs
+      // rewrite the overrides of ONE sub-batch (which re-derives its pool and symbolic phase; x and device state stay)
+      std::unique_ptr<Batch> sub = make_sub(todo, 0.1);
+      const std::vector<size_t> list = todo;
+      ladder(*sub, list.size(), 10,
+             [&](int r) {
+               if (r == 0) return;
+               std::unique_ptr<Batch> next = make_sub(list, 0.1 * (double)(r + 1));
+               sub->overrides_ = next->overrides_;
+               sub->params_dirty_ = true; sub->rebuild_ = true;
+             },
+             &st, &its, &lds, &xs);
+      todo = harvest(*sub, list, st.data(), its.data(), lds.data(), xs.data());
+    }
+    rows_fresh_ = false;
   }
   static bool pivot_repair_enabled() { const char* e = std::getenv("S21_PIVOT_REPAIR"); return !e || std::atoi(e) != 0; }
   // Per-instance re-pivoting (first half). The flagged instances of the last dcop are gathered into a batch
@@ -437,6 +560,7 @@ class Batch {
     ensure_plan(op_plan_, AN_OP, 0.0);
     S21_CUDA(cudaEventRecord(ev0_, stream_));
     run_op();
+    rescue_op();
     // The matrix changes character after the OP (capacitor companions appear, IC resistors are released):
     // take the pivot order again from the first transient iteration.
     tran_plan_.valid = false;
@@ -490,6 +614,65 @@ class Batch {
       for (size_t i = 0; i < B_; i++)
         for (int t = 0; t < T; t++)
           for (size_t s = 0; s < n_save; s++) wave[(i * (size_t)T + (size_t)t) * n_save + s] = hwave_.p[((size_t)t * n_save + s) * Bs_ + i];
+  }
+
+  // ---- adaptive transient (opt-in) -------------------------------------------------------------------
+  // OP, IC release, then per-instance LTE-controlled Backward Euler on the device (kernels/newton.cu::k_tran_adaptive),
+  // waveforms on the print grid k * tstep. ctl7 = {h0, hmin, hmax, trtol, reltol, vntol, reserved}; a non-positive / NaN
+  // entry takes its default (tstep / 16, tstep * 1e-9, 4 * tstep, 7, 1e-3, 1e-6 — SPICE's trtol / reltol / vntol).
+  void tran_adaptive(double tstep, int T, const double* ctl7, const int32_t* save_vars, size_t n_save, double* wave, int32_t* status,
+                     int64_t* iters, int32_t* accepted, int32_t* rejected) {
+    S21_CUDA(cudaSetDevice(device_));
+    materialize_reset();
+    sync_params(false);
+    launches_ = 0;
+    ensure_plan(op_plan_, AN_OP, 0.0);
+    run_op();
+    rescue_op();
+    auto pick = [&](int k, double dflt) { return (ctl7 && ctl7[k] > 0.0) ? ctl7[k] : dflt; };
+    AdaptiveArgs g;
+    g.tstep = tstep; g.T = T;
+    g.h0 = pick(0, tstep / 16.0); g.hmin = pick(1, tstep * 1e-9); g.hmax = pick(2, 4.0 * tstep);
+    g.trtol = pick(3, 7.0); g.reltol = pick(4, 1e-3); g.vntol = pick(5, 1e-6);
+    // the frozen pivot order is taken at the first step size; the companion conductances C/h move with h, so the pivot-health
+    // flag (bit 8 of the status word) is what tells whether the order stayed adequate
+    tran_plan_.valid = false;
+    rows_fresh_ = false;
+    ensure_plan(tran_plan_, AN_TRAN, g.h0);
+    if (tran_plan_.host.status != ST_OK) throw S21Error(tran_plan_.host.status, status_text(tran_plan_.host.status));
+    std::vector<int> sv(save_vars, save_vars + n_save);
+    d_save_.upload(sv, stream_);
+    const int N = flat_.n_vars();
+    d_wave_.alloc((size_t)T * n_save * Bs_);
+    wave_T_ = (size_t)T; wave_ns_ = n_save;
+    ad_x1_.alloc((size_t)N * Bs_); ad_xs_.alloc((size_t)N * Bs_); ad_st_.alloc((size_t)std::max(flat_.n_state, 1) * Bs_);
+    ad_acc_.alloc(Bs_); ad_rej_.alloc(Bs_);
+    g.x1 = ad_x1_.p; g.xs = ad_xs_.p; g.st_save = ad_st_.p; g.accepted = ad_acc_.p; g.rejected = ad_rej_.p;
+    S21_CUDA(cudaEventRecord(ev0_, stream_));
+    last_kernel_ = "direct-adaptive";
+    int rc = launch_tran_adaptive(dev_tables(tran_plan_.itab.p), tran_plan_.tables(), work(), out(), make_ctl(AN_TRAN, g.h0), g, d_save_.p, (int)n_save,
+                                  d_wave_.p, stream_);
+    launches_++;
+    if (rc) throw S21Error(ST_CUDA, std::string("adaptive tran kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+    S21_CUDA(cudaEventRecord(ev1_, stream_));
+    last_plan_ = &tran_plan_;
+    if (wave) {
+      hwave_.alloc((size_t)T * n_save * Bs_);
+      S21_CUDA(cudaMemcpyAsync(hwave_.p, d_wave_.p, (size_t)T * n_save * Bs_ * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    }
+    std::vector<int32_t> acc(Bs_), rej(Bs_), it32(B_);
+    S21_CUDA(cudaMemcpyAsync(acc.data(), ad_acc_.p, Bs_ * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+    S21_CUDA(cudaMemcpyAsync(rej.data(), ad_rej_.p, Bs_ * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+    read(nullptr, status, it32.data());
+    for (size_t i = 0; i < B_; i++) {
+      if (iters) iters[i] = it32[i];
+      if (accepted) accepted[i] = acc[i];
+      if (rejected) rejected[i] = rej[i];
+    }
+    if (wave)
+      for (size_t i = 0; i < B_; i++)
+        for (int t = 0; t < T; t++)
+          for (size_t s2 = 0; s2 < n_save; s2++) wave[(i * (size_t)T + (size_t)t) * n_save + s2] = hwave_.p[((size_t)t * n_save + s2) * Bs_ + i];
   }
 
   // ---- ac: frequency points are the batch axis of circuit instance 0 ------------------------------------------
@@ -623,6 +806,8 @@ class Batch {
   DBuf<int> d_type_, d_ioff_, d_poff_, d_soff_, d_itab_raw_, d_pcode_, d_pdirect_, d_save_;
   DBuf<double> d_pval_, x_, rhs_, c_, lu_, st_op_, st_guess_, d_wave_, d_omega_, d_rows_;
   DBuf<GridCtl> d_gctl_;
+  DBuf<double> ad_x1_, ad_xs_, ad_st_;   // adaptive transient scratch
+  DBuf<int32_t> ad_acc_, ad_rej_;
   double symbolic_s_ = 0.0;  // host time spent in build_plan (diagnostics)
   DBuf<cplx> zx_, zrhs_, zc_, zlu_;
   DBuf<int32_t> status_, iters_, loads_, ac_status_, ac_iters_, ac_loads_;
@@ -630,6 +815,9 @@ class Batch {
   double* ext_x_ = nullptr;       // set_result_target
   size_t wave_T_ = 0, wave_ns_ = 0;
   int repair_depth_ = 0;
+  int aids_ = 0;                 // set_aids: bit 0 gmin stepping, bit 1 source stepping (both off: the reference has neither)
+  double gmin_eff_ = -1.0;       // >= 0: overrides Options.gmin for the next solves (gmin stepping)
+  long long aided_ = 0;
   long long weak_seen_ = 0, repaired_ = 0;
   int32_t* ext_tail_ = nullptr;
   PinnedBuf<int32_t> hstatus_, hiters_, hloads_;
@@ -708,10 +896,10 @@ class Batch {
       tried = true;
       std::string err;
       size_t smem = 0;
-      const int lpi = jit::team_lpi(pd.host.N, jit::team_heavy_devices(flat_), B_);
-      const int gi = jit::team_gi(B_, n_sm_, lpi);
+      const int lpi = jit::team_lpi(pd.host.N, jit::team_heavy_devices(flat_), B_, tran);
+      const int gi = jit::team_gi(B_, n_sm_, lpi, tran);
       int tpb = 0;
-      const std::string src = jit::team_source(flat_, pd.host, si_, pd.host_itab, pcode_h_, tran, lpi, &smem, n_sm_, gi, &tpb);
+      const std::string src = jit::team_source(flat_, pd.host, si_, pd.host_itab, pcode_h_, tran, lpi, &smem, n_sm_, gi, &tpb, B_);
       if (const char* dump = std::getenv("S21_JIT_DUMP")) {
         if (FILE* f = std::fopen(dump, "w")) { std::fwrite(src.data(), 1, src.size(), f); std::fclose(f); }
       }
@@ -732,7 +920,7 @@ class Batch {
     int *st = status_.p, *it = iters_.p, *ld = loads_.p;
     size_t stride = Bs_, st_stride = Bs_;
     int B = (int)B_, n_state = flat_.n_state, md = mode, cold_i = cold ? 1 : 0, Tp = T, ns = n_save;
-    double gmin = flat_.opts.gmin, dtv = dt, reltol = flat_.opts.reltol, iabstol = flat_.opts.iabstol;
+    double gmin = gmin_eff_ >= 0.0 ? gmin_eff_ : flat_.opts.gmin, dtv = dt, reltol = flat_.opts.reltol, iabstol = flat_.opts.iabstol;
     void* args[] = {&pval, &gx, &sop, &sg, &st, &it, &ld, &stride, &st_stride, &B, &n_state, &md, &gmin, &dtv, &reltol, &iabstol,
                     &cold_i, &Tp, &ns, &save_vars, &wave, &rows};  // `rows` is the team kernel's last parameter only
     const unsigned grid = (unsigned)((B_ + (size_t)k.inst_per_cta - 1) / (size_t)k.inst_per_cta);
@@ -835,10 +1023,11 @@ class Batch {
   }
   SolveCtl make_ctl(int mode, double dt) const {
     SolveCtl c;
-    c.B = (int)B_; c.mode = mode; c.gmin = flat_.opts.gmin; c.dt = dt;
+    c.B = (int)B_; c.mode = mode; c.gmin = gmin_eff_ >= 0.0 ? gmin_eff_ : flat_.opts.gmin; c.dt = dt;
     c.reltol = flat_.opts.reltol; c.iabstol = flat_.opts.iabstol; c.omega = nullptr; c.par_inst_stride = 1;
     c.has_bsim4 = 0;
     for (const FlatDev& d : flat_.devs) if (d.type == DT_BSIM4) { c.has_bsim4 = 1; break; }
+    c.relaxed = (mode == AN_OP ? op_plan_ : mode == AN_TRAN ? tran_plan_ : ac_plan_).host.relaxed ? 1 : 0;
     return c;
   }
   void run_op() {
@@ -858,7 +1047,7 @@ class Batch {
       reset_pending_ = false;
       last_kernel_ = jk->team ? "jit-team" : "jit-thread";
       double* rows = nullptr;
-      if (jk->team && jit::team_wp()) {  // the warp-private team kernel also leaves the host's result layout behind
+      if (jk->team && jit::team_wp(false, B_)) {  // the warp-private team kernel also leaves the host's result layout behind
         d_rows_.alloc(rows_words());
         rows = d_rows_.p;
       }
@@ -913,7 +1102,11 @@ class Batch {
     }
     if (plan_cache) pd.probe_vals = vals;
     const auto t_sym0 = std::chrono::steady_clock::now();
-    pd.host = build_plan<double>(N, flat_.elem_row, flat_.elem_col, vals.data());
+    // One large circuit on the grid-wide kernel: tolerance-mode level schedules (host/symbolic.hpp build_levels) unless
+    // S21_PLAN_EXACT=1 asks for the bit-identical chains.
+    const char* exact = std::getenv("S21_PLAN_EXACT");
+    const bool relaxed = use_coop_ && use_grid() && !(exact && std::atoi(exact) != 0);
+    pd.host = build_plan<double>(N, flat_.elem_row, flat_.elem_col, vals.data(), relaxed);
     const auto t_sym1 = std::chrono::steady_clock::now();
     upload_plan(pd, mode);
     symbolic_s_ += std::chrono::duration<double>(t_sym1 - t_sym0).count();

@@ -30,8 +30,8 @@ constexpr int TM_GI = 32;    // instances per CTA
 constexpr int TM_MAXN = 16;  // rows per instance the register-resident linear algebra is generated for
 // Lanes per instance in the linear-algebra phase: 8 (4 instances per warp, 8 warps per CTA; rows beyond 8 become a
 // second register set), 10 (3 instances per warp) or 16 (2 instances per warp, 16 warps per CTA; one row per member).
-inline bool team_wp();
-inline int team_lpi(int N, int n_heavy = 0, size_t B = 0) {
+inline bool team_wp(bool tran, size_t B);
+inline int team_lpi(int N, int n_heavy = 0, size_t B = 0, bool tran = false) {
   if (const char* e = std::getenv("S21_TEAM_LPI")) {
     const int v = std::atoi(e);
     if (v == 1 || v == 2 || v == 4 || v == 8 || v == 10 || v == 16) return v;
@@ -45,7 +45,7 @@ inline int team_lpi(int N, int n_heavy = 0, size_t B = 0) {
   // Small shards of a strong-scaled sweep (<= 2048 instances per GPU) leave most SMs with one CTA: there the warp-private
   // loop with 8 lanes per instance and 16-instance CTAs is the shortest chain (profiles/r02a_wp_sweep.txt: 0.075 ms against
   // 0.078-0.081 at 1024 / 2048 instances of C2).
-  if (B > 0 && B <= 2048 && team_wp() && n_heavy <= 2 && N <= 10) return 8;
+  if (!tran && B > 0 && B <= 2048 && team_wp(tran, B) && n_heavy <= 2 && N <= 10) return 8;
   return (n_heavy <= 2 && N <= 10) ? 2 : 4;
 }
 inline int team_heavy_devices(const FlatCkt& flat) {
@@ -61,19 +61,32 @@ inline bool team_profile() { const char* e = std::getenv("S21_TEAM_PROFILE"); re
 // Instances per CTA: a full warp of instances in the evaluation phase (30 with 3 instances per warp). Smaller CTAs that
 // balance the SMs better (8192 instances: 293 CTAs of 28 -> 56 per SM instead of 64) measured the same 0.115 ms: the
 // launch is one dependent chain per CTA, not a throughput problem. S21_TEAM_GI overrides (experiments).
-inline int team_gi(size_t B, int n_sm, int lpi) {
+inline int team_gi(size_t B, int n_sm, int lpi, bool tran = false) {
   const int ipw = 32 / lpi, gmax = TM_GI / ipw * ipw;
   if (const char* e = std::getenv("S21_TEAM_GI")) { const int v = std::atoi(e); if (v >= ipw && v <= gmax && v % ipw == 0) return v; }
   (void)n_sm;
-  if (B > 0 && B <= 2048 && lpi == 8 && team_wp()) return 16;  // see team_lpi
+  if (!tran && B > 0 && B <= 2048 && lpi == 8 && team_wp(tran, B)) return 16;  // see team_lpi
   return gmax;
 }
-// Warp-private loop (default; S21_TEAM_WP=0 restores the CTA-wide evaluation phase of round 1): a warp evaluates the
-// devices of its own instances (lane = (instance, device group)), so an iteration needs no block barrier and same-type
-// devices share one evaluation text; the CTA may then be a single warp (the shared-memory stride follows the instances
-// per CTA), and the kernel leaves the host's result layout behind (no packing kernel before the D2H copy). Measured
-// (profiles/r02a_wp_*): C1-circuit transient x 8192, 4 lanes: 12.08 -> 8.98 ms; C2 dcop x 8192: 0.083 ms either way.
-inline bool team_wp() { const char* e = std::getenv("S21_TEAM_WP"); return !e || std::atoi(e) != 0; }
+// Warp-private loop (S21_TEAM_WP=1 / 0 forces it on / off for both analyses): a warp evaluates the devices of its own
+// instances (lane = (instance, device group)), so an iteration needs no block barrier and same-type devices share one
+// evaluation text; the CTA may then be a single warp (the shared-memory stride follows the instances per CTA), and the
+// kernel leaves the host's result layout behind (no packing kernel before the D2H copy). Measured (profiles/r02a_wp_*,
+// r02d_*): the C1-circuit transient x 8192 (6 Mos1, 4 lanes) goes from 12.08 to 8.98 ms, so transients take it by
+// default; the C2 dcop x 8192 does not gain (0.083 ms either way back to back, and with the L2 flushed between steps the
+// result rows it writes cost more than the packing kernel they replace: 0.0948 against 0.0887 ms), so a dcop of a
+// full-size batch keeps the CTA-wide evaluation phase. Small shards (<= 2048 instances) take it for the 8-lane shape.
+inline bool team_wp_env(int* forced) {
+  const char* e = std::getenv("S21_TEAM_WP");
+  if (!e) return false;
+  *forced = std::atoi(e) != 0 ? 1 : 0;
+  return true;
+}
+inline bool team_wp(bool tran = true, size_t B = 0) {
+  int f = 0;
+  if (team_wp_env(&f)) return f != 0;
+  return tran || (B > 0 && B <= 2048);
+}
 inline bool team_fast() { const char* e = std::getenv("S21_TEAM_FAST"); return !e || std::atoi(e) != 0; }
 
 struct TeamGather {
@@ -97,10 +110,11 @@ inline bool team_eligible(const FlatCkt& flat, const Plan& P, size_t max_smem) {
 }
 
 inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageInfo& si, const std::vector<int>& itab,
-                               const std::vector<int>& pcode, bool tran, int TM_LPI, size_t* smem_out, int n_sm = 148, int GI = TM_GI, int* tpb_out = nullptr) {
+                               const std::vector<int>& pcode, bool tran, int TM_LPI, size_t* smem_out, int n_sm = 148, int GI = TM_GI, int* tpb_out = nullptr,
+                               size_t B = 0) {
   (void)n_sm;
   std::ostringstream o;
-  const bool XP = team_wp();
+  const bool XP = team_wp(tran, B);
   const int PSV = XP ? GI + 4 : TM_P;  // padded instance stride of the shared-memory columns (36 for a full CTA, as kernels/hybrid.cu)
   const int N = P.N, NST = P.n_stage, NSTATE = std::max(flat.n_state, 1), Q = (N + TM_LPI - 1) / TM_LPI;
   const int IPW = 32 / TM_LPI;        // instances per warp in the linear-algebra phase
@@ -305,7 +319,7 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
        "    const size_t src = (size_t)k * st_stride + (size_t)i0 + (size_t)(evalid ? ei : 0);\n"
        "    sop[k * PS + ei] = cold ? 0.0 : st_op[src];\n    sguess[k * PS + ei] = cold ? 0.0 : st_guess[src];\n  }\n"
        "  int r_stat = " << (tran ? "rvalid ? status[i0 + ri] : 0" : "0") << ";\n"
-       "  bool r_weak = (r_stat >> 8) & 1;\n  r_stat &= 0xff;\n"
+       "  int r_wk = ((r_stat >> 8) & 1) ? 0x7ff00000 : 0;\n  r_stat &= 0xff;\n"
        "  int r_nsol = 0, r_nld = 0;\n"
        "  __syncthreads();\n";
   if (tran)
@@ -410,11 +424,16 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
       if (anyL) {
         o << "            const double rp = s_rcp(piv);\n";  // one reciprocal per pivot, shared by the column's entries (scalar.h)
         if (fast) o << "            const bool pok = s_div_bok(piv);\n";
-        o << "            const double pth = fabs(piv) * 1e3;\n";  // pivot health: |pivot| < 1e-3 x an entry below it (kernels/newton.cu)
+        // pivot health (kernels/newton.cu): |pivot| < 1e-3 x an entry below it <=> a multiplier above 1e3 — tested on the
+        // quotient that is computed anyway, as a running integer maximum of the high words (FP64 compares with a live
+        // predicate cost 6-13 % of the C2 kernel, profiles/r02f_health_cost.txt). S21_PIVOT_HEALTH=0 leaves the test out
+        // of the generated text (to measure what it costs; the interpreted kernels always test).
+        static const bool health = [] { const char* e = std::getenv("S21_PIVOT_HEALTH"); return !e || std::atoi(e) != 0; }();
         for (int q = 0; q < Q; q++)
           if (LM[(size_t)q][(size_t)k]) {
-            o << "            r_weak = r_weak || (r_act && " << mask_test(LM[(size_t)q][(size_t)k]) << " != 0 && pth < fabs(" << A(q, k) << "));\n";
             divide(A(q, k), A(q, k), "piv", "rp", "pok", mask_test(LM[(size_t)q][(size_t)k]));
+            if (health)  // integer max of the multipliers' high words (monotonic in |l|): ALU pipe, no predicate kept alive
+              o << "            if (" << mask_test(LM[(size_t)q][(size_t)k]) << ") r_wk = max(r_wk, __double2hiint(" << A(q, k) << ") & 0x7fffffff);\n";
           }
         for (int s = P.diag_slot[(size_t)k] + 1; s < P.rowptr[(size_t)k + 1]; s++) {
           const int c = P.colidx[(size_t)s];
@@ -530,7 +549,7 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
     o << "    if (rvalid) {\n      const bool good = r_stat == 0;\n      for (int s = j; s < n_save; s += " << TM_LPI << ")\n"
          "        wave[((size_t)tp * n_save + s) * stride + i0 + ri] = good ? X[save_vars[s] * PS + ri] : __longlong_as_double(0x7ff8000000000000LL);\n"
          "    }\n";
-  o << "  }\n  const bool weak_any = (__ballot_sync(FULLM, r_weak && rvalid) & imask) != 0;\n  __syncthreads();\n"
+  o << "  }\n  const bool weak_any = (__ballot_sync(FULLM, r_wk > 0x408f3fff && rvalid) & imask) != 0  /* a multiplier >= 1000 */;\n  __syncthreads();\n"
        "  if (evalid) {\n"
        "    for (int k = warp; k < " << N << "; k += " << NW << ") gx[(size_t)k * stride + i0 + ei] = X[k * PS + ei];\n"
        "    for (int k = warp; k < " << flat.n_state << "; k += " << NW << ") {\n"

@@ -47,6 +47,10 @@ struct Plan {
   // nnzLU + v is rhs[v]; asm_src lists the staging slots to sum, in the reference's accumulation order.
   std::vector<int> asm_off, asm_src;
   int n_stage = 0;
+  // Level schedules built in "tolerance" mode (build_levels): Schur updates / forward-substitution updates that hit the
+  // same target no longer wait for each other, so several may sit in one level and the kernel must apply them with
+  // atomic adds (their order, hence the last bits of the sum, is then not fixed).
+  bool relaxed = false;
 };
 
 // Group operations by dependency level. `lev[j]` >= 1 for every op; returns offsets of the stable level sort.
@@ -64,8 +68,15 @@ inline std::vector<int> level_sort(const std::vector<int>& lev, std::vector<int>
   return offs;  // offs[q] = first op of the q-th level (q = 0 .. nl), offs[nl] = total
 }
 
-inline void build_levels(Plan& P) {
+// relaxed = false: every value sees its updates in the reference's order (ascending pivot index), so results are
+// bit-identical to the one-thread kernel — but all updates into one target form a chain. On config C3 (2000 rings on one
+// supply node) the 10 000 contributions to the supply node's diagonal serialise the whole factorisation: 10 k LU levels
+// and 12 k forward levels, one grid barrier each. relaxed = true ("tolerance" mode, SPICE reltol is 1e-3): an update
+// waits only for its two factors; updates into one target commute, land in the same level and are applied atomically.
+// The level count falls to the depth of the elimination DAG.
+inline void build_levels(Plan& P, bool relaxed = false) {
   const int N = P.N;
+  P.relaxed = relaxed;
   // ---- LU
   {
     std::vector<int> ready((size_t)P.nnzLU, 0), t, u, l, lev;
@@ -80,9 +91,9 @@ inline void build_levels(Plan& P) {
       }
       for (int j = P.upd_off[(size_t)k]; j < P.upd_off[(size_t)k + 1]; j++) {
         const int tt = P.upd_t[(size_t)j], uu = P.upd_u[(size_t)j], ll = P.upd_l[(size_t)j];
-        const int lv = std::max(ready[(size_t)tt], std::max(ready[(size_t)uu], ready[(size_t)ll])) + 1;
+        const int lv = std::max(relaxed ? 0 : ready[(size_t)tt], std::max(ready[(size_t)uu], ready[(size_t)ll])) + 1;
         t.push_back(tt); u.push_back(uu); l.push_back(ll); lev.push_back(lv);
-        ready[(size_t)tt] = lv;
+        ready[(size_t)tt] = std::max(ready[(size_t)tt], lv);
       }
     }
     std::vector<int> order;
@@ -95,9 +106,9 @@ inline void build_levels(Plan& P) {
     for (int k = 0; k < N; k++)
       for (int j = P.l_off[(size_t)k]; j < P.l_off[(size_t)k + 1]; j++) {
         const int row = P.l_row[(size_t)j];
-        const int lv = std::max(ready[(size_t)k], ready[(size_t)row]) + 1;
+        const int lv = std::max(ready[(size_t)k], relaxed ? 0 : ready[(size_t)row]) + 1;
         kk.push_back(k); rr.push_back(row); ss.push_back(P.l_slot[(size_t)j]); lev.push_back(lv);
-        ready[(size_t)row] = lv;
+        ready[(size_t)row] = std::max(ready[(size_t)row], lv);
       }
     std::vector<int> order;
     P.fw_lvl_off = level_sort(lev, &order);
@@ -182,7 +193,7 @@ class CoordMap {
 
 // vals[e] = assembled value of element e after the first device-load sweep.
 template <class T>
-Plan build_plan(int N, const std::vector<int>& elem_row, const std::vector<int>& elem_col, const T* vals) {
+Plan build_plan(int N, const std::vector<int>& elem_row, const std::vector<int>& elem_col, const T* vals, bool relaxed = false) {
   using detail::SymEntry;
   using detail::rc_key;
   Plan P;
@@ -492,7 +503,7 @@ Plan build_plan(int N, const std::vector<int>& elem_row, const std::vector<int>&
     P.upd_off[(size_t)n + 1] = (int)P.upd_t.size();
   }
   const auto t_frozen = clk::now();
-  if (P.status == ST_OK) build_levels(P);
+  if (P.status == ST_OK) build_levels(P, relaxed);
   if (info)
     std::fprintf(stderr, "[s21 symbolic] N=%d nnzLU=%d candidates=%zu updates=%zu | search %.2f s, elimination %.2f s, freeze+op lists %.2f s, levels %.2f s\n", N,
                  P.nnzLU, n_cand, n_upd, t_search, t_elim, std::chrono::duration<double>(t_frozen - t_fact).count(),

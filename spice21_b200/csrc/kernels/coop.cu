@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
   int* nld = nsol + gi;
   int* convnow = nld + gi;
   int* weak = convnow + gi;  // pivot health: a frozen pivot the reference's threshold test would have refused (mod.rs:735-783)
-  uint64_t* mbar = (uint64_t*)(weak + gi);
+  uint64_t* mbar = (uint64_t*)(((size_t)(weak + gi) + 7) & ~(size_t)7);  // 9 int arrays: 8-byte alignment is not automatic
   size_t off = ((size_t)((unsigned char*)(mbar + 1) - smem_raw) + 15) / 16 * 16;
   if (a.arena_bytes > 0) {
     int* sa = (int*)(smem_raw + off);
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
   }
 }
 
-size_t ctrl_bytes(int gi) { return ((8 + 9 * 4) * (size_t)gi + 8 + 15) / 16 * 16; }
+size_t ctrl_bytes(int gi) { return ((8 + 9 * 4) * (size_t)gi + 8 + 8 + 15) / 16 * 16; }
 
 template <class T, int KIND, bool B4>
 int launch_b4(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<T>& w, T* stage, const NewtonOut& o,

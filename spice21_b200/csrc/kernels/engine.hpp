@@ -66,6 +66,7 @@ struct SolveCtl {
   // x = 0 with no step limit (x = A^-1 b). 0: the reference's Newton shell (analysis.rs:253-303: 1.0 step limit, <= 20
   // iterations, a second factorisation to confirm) — kept for iteration-count parity; it cannot reach |x| > ~19 from a cold start.
   int ac_direct = 0;
+  int relaxed = 0;         // the plan's level schedules are in tolerance mode (host/symbolic.hpp build_levels): apply updates atomically
   int has_bsim4 = 0;       // selects the kernel build that links the Bsim4 evaluation (kept out of the others: register pressure)
 };
 
@@ -131,6 +132,16 @@ int launch_dcop(const DevTables& d, const PlanTables& p, const WorkTables<double
 // OP must already be solved and committed; runs points 1..T-1 of Tran::solve. wave: [T][n_save][w.stride] device (point 0 written too).
 int launch_tran(const DevTables& d, const PlanTables& p, const WorkTables<double>& w, const NewtonOut& o, const SolveCtl& c, int T,
                 const int* save_vars, int n_save, double* wave, void* stream);
+// Adaptive-step transient (kernels/newton.cu::k_tran_adaptive; opt-in): per-instance step control by local truncation
+// error on the device. Scratch arrays are device memory sized like the workspace.
+struct AdaptiveArgs {
+  double tstep, h0, hmin, hmax, trtol, reltol, vntol;
+  int T;
+  double *x1, *xs, *st_save;
+  int32_t *accepted, *rejected;
+};
+int launch_tran_adaptive(const DevTables& d, const PlanTables& p, const WorkTables<double>& w, const NewtonOut& o, const SolveCtl& c,
+                         const AdaptiveArgs& g, const int* save_vars, int n_save, double* wave, void* stream);
 int launch_ac(const DevTables& d, const PlanTables& p, const WorkTables<cplx>& w, const NewtonOut& o, const SolveCtl& c, void* stream);
 // Result packing on the device: out = [x as [instance][variable], B*N f64][status B i32][iters B i32][loads B i32].
 int launch_pack_out(const double* x, const int32_t* status, const int32_t* iters, const int32_t* loads, double* out, int N, size_t stride, int B,

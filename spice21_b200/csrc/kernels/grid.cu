@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(256, B4 ? 1 : 2) k_grid(DevTables d, PlanTable
           double* t = lu + ct.lu_t[op];
           const double u = lu[ct.lu_u[op]];
           if (l < 0) *t = s_div(*t, u);
+          else if (ctl.relaxed) atomicAdd(t, -s_mul(u, lu[l]));  // several updates of one level may share the target
           else *t = s_sub(*t, s_mul(u, lu[l]));
         }
         grid.sync();
@@ -117,7 +118,8 @@ __global__ void __launch_bounds__(256, B4 ? 1 : 2) k_grid(DevTables d, PlanTable
           const double ck = c[ct.fw_k[op]];
           if (s_is_zero(ck)) continue;
           double* t = c + ct.fw_row[op];
-          *t = s_sub(*t, s_mul(ck, lu[ct.fw_slot[op]]));
+          if (ctl.relaxed) atomicAdd(t, -s_mul(ck, lu[ct.fw_slot[op]]));
+          else *t = s_sub(*t, s_mul(ck, lu[ct.fw_slot[op]]));
         }
         grid.sync();
       }

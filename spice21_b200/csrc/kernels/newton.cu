@@ -258,6 +258,96 @@ __global__ void __launch_bounds__(128) k_tran(DevTables d, PlanTables p, WorkTab
   o.loads[inst] += nl;
 }
 
+// ---- adaptive transient (opt-in, the fixed-step kernels above are the parity path) ------------------
+// One thread per instance runs its OWN time axis: Backward Euler with a local-truncation-error estimate per step, step
+// rejection and step-size control on the device, no host round trip. The reference has none of this (fixed step only,
+// analysis.rs:553-570; `trtol` / `chgtol` are dead fields, :650-656).
+//   LTE estimate: the BE solution against the linear extrapolation x_p through the two previous accepted points;
+//     x_BE - x_p = x''/2 * h (2h + h1)  =>  LTE = x''/2 * h^2 = (x_BE - x_p) * h / (2h + h1)
+//   accepted when  max_i |LTE_i| / (trtol * (reltol_lte * max(|x_i|, |x_i,prev|) + vntol))  <= 1,
+//   next step h * clamp(0.9 / sqrt(ratio), 0.1, 2), at most hmax; a Newton failure retries with h / 8; below hmin the
+//   instance reports Convergence Failed.
+// Output is on the caller's print grid t_k = k * tstep (the fixed-step axis), by linear interpolation between accepted
+// points — every instance fills the same [T][n_save] block whatever steps it took.
+struct AdaptCtl {
+  double tstep, h0, hmin, hmax, trtol, reltol, vntol;
+  int T;                  // print points incl. t = 0
+  double *x1, *xs;        // [N][stride] previous accepted solution / solution at the start of the attempt
+  double *st_save;        // [n_state][st_stride] committed device state at the start of the attempt
+  int32_t *accepted, *rejected;  // [B]
+};
+template <bool B4>
+__global__ void __launch_bounds__(128) k_tran_adaptive(DevTables d, PlanTables p, WorkTables<double> w, NewtonOut o, SolveCtl ctl, AdaptCtl a,
+                                                      const int* save_vars, int n_save, double* wave) {
+  const size_t inst = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= (size_t)ctl.B) return;
+  const size_t S = w.stride, SS = w.st_stride;
+  const int N = p.N;
+  int st = o.status[inst];
+  int weak = (st >> 8) & 1;
+  st &= 0xff;
+  double* x = w.x + inst;
+  double* x1 = a.x1 + inst;
+  double* xs = a.xs + inst;
+  for (int s = 0; s < n_save; s++) wave[(size_t)s * S + inst] = x[(size_t)__ldg(save_vars + s) * S];
+  for (int k = 0; k < N; k++) x1[(size_t)k * S] = x[(size_t)k * S];
+  int ns = 0, nl = 0, nacc = 0, nrej = 0, kp = 1;
+  double t = 0.0, h = a.h0, h1 = 0.0;
+  while (kp < a.T && st == ST_OK_) {
+    // start of an attempt: keep x_n and the committed device state
+    for (int k = 0; k < N; k++) xs[(size_t)k * S] = x[(size_t)k * S];
+    for (int k = 0; k < d.n_state; k++) a.st_save[(size_t)k * SS + inst] = w.st_op[(size_t)k * SS + inst];
+    SolveCtl c = ctl;
+    c.dt = h;
+    int rc = newton_solve<double, B4>(d, p, w, c, inst, 0.0, ctl.reltol, ctl.iabstol, true, &ns, &nl, &weak);
+    double ratio = 0.0;
+    if (rc == ST_OK_ && nacc >= 1) {
+      const double coef = h / (2.0 * h + h1);
+      for (int k = 0; k < N; k++) {
+        const double xn = xs[(size_t)k * S], xo = x1[(size_t)k * S], xb = x[(size_t)k * S];
+        const double xp = xn + (xn - xo) * (h / h1);
+        const double lte = fabs(xb - xp) * coef;
+        const double tol = a.trtol * (a.reltol * fmax(fabs(xb), fabs(xn)) + a.vntol);
+        ratio = fmax(ratio, lte / tol);
+      }
+    }
+    if (rc != ST_OK_ || ratio > 1.0) {  // reject: back to x_n and its device state, smaller step
+      for (int k = 0; k < N; k++) x[(size_t)k * S] = xs[(size_t)k * S];
+      for (int k = 0; k < d.n_state; k++) {  // after a commit op == guess: both go back (the limiters read the in-flight copy)
+        const double v = a.st_save[(size_t)k * SS + inst];
+        w.st_op[(size_t)k * SS + inst] = v;
+        w.st_guess[(size_t)k * SS + inst] = v;
+      }
+      nrej++;
+      h = rc != ST_OK_ ? h * 0.125 : h * fmax(0.1, 0.9 / sqrt(ratio));
+      if (h < a.hmin) st = rc == ST_SINGULAR_ ? ST_SINGULAR_ : ST_CONV_;
+      continue;
+    }
+    // accept: emit the print points passed, shift the history
+    const double tn = t + h;
+    while (kp < a.T && (double)kp * a.tstep <= tn * (1.0 + 1e-12)) {
+      const double f = fmin(1.0, fmax(0.0, ((double)kp * a.tstep - t) / h));
+      for (int s = 0; s < n_save; s++) {
+        const size_t v = (size_t)__ldg(save_vars + s) * S;
+        wave[((size_t)kp * n_save + s) * S + inst] = xs[v] + (x[v] - xs[v]) * f;
+      }
+      kp++;
+    }
+    for (int k = 0; k < N; k++) x1[(size_t)k * S] = xs[(size_t)k * S];
+    h1 = h;
+    t = tn;
+    nacc++;
+    h = fmin(a.hmax, h * fmin(2.0, fmax(0.1, 0.9 / sqrt(fmax(ratio, 1e-4)))));
+  }
+  for (; kp < a.T; kp++)  // a failed instance: NaN for the points it never reached (as the fixed-step kernels do)
+    for (int s = 0; s < n_save; s++) wave[((size_t)kp * n_save + s) * S + inst] = __longlong_as_double(0x7ff8000000000000LL);
+  o.status[inst] = st | (weak << 8);
+  o.iters[inst] += ns;
+  o.loads[inst] += nl;
+  a.accepted[inst] = nacc;
+  a.rejected[inst] = nrej;
+}
+
 __global__ void __launch_bounds__(128) k_ac(DevTables d, PlanTables p, WorkTables<cplx> w, NewtonOut o, SolveCtl ctl) {
   const size_t inst = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (inst >= (size_t)ctl.B) return;
@@ -299,6 +389,15 @@ int launch_tran(const DevTables& d, const PlanTables& p, const WorkTables<double
                 const int* save_vars, int n_save, double* wave, void* stream) {
   if (c.has_bsim4) k_tran<true><<<grid_for(c.B, 128), 128, 0, (cudaStream_t)stream>>>(d, p, w, o, c, T, save_vars, n_save, wave);
   else k_tran<false><<<grid_for(c.B, 128), 128, 0, (cudaStream_t)stream>>>(d, p, w, o, c, T, save_vars, n_save, wave);
+  return (int)cudaGetLastError();
+}
+int launch_tran_adaptive(const DevTables& d, const PlanTables& p, const WorkTables<double>& w, const NewtonOut& o, const SolveCtl& c,
+                         const AdaptiveArgs& g, const int* save_vars, int n_save, double* wave, void* stream) {
+  AdaptCtl a;
+  a.tstep = g.tstep; a.h0 = g.h0; a.hmin = g.hmin; a.hmax = g.hmax; a.trtol = g.trtol; a.reltol = g.reltol; a.vntol = g.vntol; a.T = g.T;
+  a.x1 = g.x1; a.xs = g.xs; a.st_save = g.st_save; a.accepted = g.accepted; a.rejected = g.rejected;
+  if (c.has_bsim4) k_tran_adaptive<true><<<grid_for(c.B, 128), 128, 0, (cudaStream_t)stream>>>(d, p, w, o, c, a, save_vars, n_save, wave);
+  else k_tran_adaptive<false><<<grid_for(c.B, 128), 128, 0, (cudaStream_t)stream>>>(d, p, w, o, c, a, save_vars, n_save, wave);
   return (int)cudaGetLastError();
 }
 int launch_ac(const DevTables& d, const PlanTables& p, const WorkTables<cplx>& w, const NewtonOut& o, const SolveCtl& c, void* stream) {
