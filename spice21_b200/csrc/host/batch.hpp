@@ -123,7 +123,7 @@ struct PlanDevice {
   bool jit_tried_dcop = false, jit_tried_tran = false;
   jit::Kernel jitt_dcop, jitt_tran;   // team-shaped specialised kernels (host/jit_team.hpp)
   bool jitt_tried_dcop = false, jitt_tried_tran = false;
-  DBuf<int> row_i2e, col_i2e, col_e2i, rowptr, colidx, diag_slot, l_off, l_slot, l_row, upd_off, upd_t, upd_u, upd_l, itab;
+  DBuf<int> row_i2e, col_i2e, col_e2i, rowptr, colidx, diag_slot, l_off, l_slot, l_row, piv_chk, upd_off, upd_t, upd_u, upd_l, itab;
   // cooperative kernel: every shared index table packed into one allocation ("arena") so that a CTA can bring all of
   // them into shared memory with a single TMA bulk copy. Offsets are in ints, each table 16-byte aligned.
   DBuf<int> arena;
@@ -144,7 +144,7 @@ struct PlanDevice {
     t.N = host.N; t.nnz = host.nnzLU;
     t.row_i2e = arena.p + ao.row_i2e; t.col_i2e = arena.p + ao.col_i2e; t.col_e2i = arena.p + ao.col_e2i;
     t.rowptr = arena.p + ao.rowptr; t.colidx = arena.p + ao.colidx; t.diag_slot = arena.p + ao.diag_slot;
-    t.l_off = t.l_slot = t.l_row = t.upd_off = t.upd_t = t.upd_u = t.upd_l = nullptr;
+    t.l_off = t.l_slot = t.l_row = t.piv_chk = t.upd_off = t.upd_t = t.upd_u = t.upd_l = nullptr;
     return t;
   }
   CoopTables coop() const {
@@ -162,7 +162,7 @@ struct PlanDevice {
     t.N = host.N; t.nnz = host.nnzLU;
     t.row_i2e = row_i2e.p; t.col_i2e = col_i2e.p; t.col_e2i = col_e2i.p;
     t.rowptr = rowptr.p; t.colidx = colidx.p; t.diag_slot = diag_slot.p;
-    t.l_off = l_off.p; t.l_slot = l_slot.p; t.l_row = l_row.p;
+    t.l_off = l_off.p; t.l_slot = l_slot.p; t.l_row = l_row.p; t.piv_chk = piv_chk.p;
     t.upd_off = upd_off.p; t.upd_t = upd_t.p; t.upd_u = upd_u.p; t.upd_l = upd_l.p;
     return t;
   }
@@ -219,6 +219,7 @@ class Batch {
     params_dirty_ = true;
     reset();
     materialize_reset();
+    S21_CUDA(cudaStreamSynchronize(stream_));  // the caller may move the batch to a stream of its own right away
   }
   ~Batch() {
     cudaSetDevice(device_);
@@ -328,20 +329,24 @@ class Batch {
       S21_CUDA(cudaStreamSynchronize(stream_));
       hs = hstatus_.p; hi = hiters_.p; hl = hloads_.p;
     }
-    // Pivot health. Bit 8 of a status word = during some factorisation of that instance a frozen pivot was smaller than
-    // 1e-3 x an entry below it, i.e. the reference — which re-runs its Markowitz search every iteration
-    // (sparse21/mod.rs:929-932, 735-783) — would not have taken it; S21_SINGULAR_MATRIX from a kernel = an exactly zero
-    // frozen pivot. Both mean "the order taken from instance 0 does not suit this instance". The flag is stripped here;
-    // after a dcop the instances concerned are re-solved with a symbolic phase of their own (repair_dcop).
+    // Pivot health. A kernel stops an instance with ST_REPIVOT_CODE when, in one of its factorisations, a frozen pivot is
+    // smaller than 1e-3 x an entry below it, i.e. when the reference — which re-runs its Markowitz search in every
+    // factorisation (sparse21/mod.rs:929-932, 735-783) — would not have taken that pivot; S21_SINGULAR_MATRIX from a kernel
+    // is an exactly zero frozen pivot. Either way the order taken from instance 0's first iteration does not suit this
+    // instance's matrix at its current iterate. After a dcop those instances are continued with an order of their own
+    // (resolve_repivot); elsewhere (inside a transient's time loop, an AC sweep) the code is reported as Pivot Search Fail.
     std::vector<size_t> flagged;
     for (size_t i = 0; i < B_; i++) {
       const int32_t st = hs[i];
-      if (st & 0x100) { hs[i] = st & 0xff; flagged.push_back(i); }
-      else if (st == ST_SINGULAR && last_plan_ && last_plan_->host.status == ST_OK) flagged.push_back(i);
+      if (st == ST_REPIVOT_CODE || (st == ST_SINGULAR && last_plan_ && last_plan_->host.status == ST_OK && !no_resolve_))
+        flagged.push_back(i);
     }
-    weak_seen_ += (long long)flagged.size();
-    if (!flagged.empty() && want_x && last_plan_ == &op_plan_ && pivot_repair_enabled() && repair_depth_ < 4)
-      repair_dcop(flagged, ext_x_ ? ext_x_ : hx_.p, hs, hi, hl);
+    if (!no_resolve_) weak_seen_ += (long long)flagged.size();
+    if (!flagged.empty() && want_x && last_plan_ == &op_plan_ && pivot_repair_enabled() && !no_resolve_)
+      resolve_repivot(flagged, ext_x_ ? ext_x_ : hx_.p, hs, hi, hl);
+    if (!no_resolve_)
+      for (size_t i = 0; i < B_; i++)
+        if (hs[i] == ST_REPIVOT_CODE) hs[i] = ST_PIVOT;  // not continued (repair off / not a dcop): the reference's "Pivot Search Fail"
     if (aids_ && want_x && last_plan_ == &op_plan_ && repair_depth_ == 0) {
       std::vector<size_t> failed;
       for (size_t i = 0; i < B_; i++) if (hs[i] == ST_CONV) failed.push_back(i);
@@ -357,6 +362,7 @@ class Batch {
     if (iters) *iters = hi;
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, ev0_, ev1_) == cudaSuccess) last_ms_ = ms;
+    else (void)cudaGetLastError();  // an event of the pair not recorded yet (a read between two launches): nothing to carry on
   }
   // ---- convergence aids (second half; opt-in — the reference has neither: `src_factor` and `diag_gmin` are
   // dead fields, analysis.rs:659-660, so with the aids off a failing instance reports Convergence Failed exactly as the
@@ -368,13 +374,23 @@ class Batch {
   //     (a long ring released from one IC) gets there in stages.
   // x and the committed device state of the rescued instances replace the failed ones (host rows and HBM columns).
   void set_aids(int flags) { aids_ = flags; }
-  // The operating point that opens a transient: with aids on, instances whose OP failed are continued before the time loop
-  // (their x and device state columns are replaced in HBM, their status cleared).
+  // The operating point that opens a transient / AC sweep: instances a kernel stopped for a new pivot order — and, with the
+  // aids on, instances whose OP failed — are continued before the analysis goes on (their x and device-state columns are
+  // replaced in HBM, their status updated). Costs one D2H of the status vector when nothing needs doing.
   void rescue_op() {
-    if (!aids_ || repair_depth_ != 0) return;
+    if (no_resolve_) return;
+    hstatus_.alloc(Bs_);
+    S21_CUDA(cudaMemcpyAsync(hstatus_.p, status_.p, Bs_ * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+    S21_CUDA(cudaStreamSynchronize(stream_));
+    bool need = false;
+    for (size_t i = 0; i < B_ && !need; i++) {
+      const int32_t st = hstatus_.p[i];
+      need = st == ST_REPIVOT_CODE || (st == ST_SINGULAR && op_plan_.host.status == ST_OK) || (aids_ && st == ST_CONV);
+    }
+    if (!need) return;
     last_plan_ = &op_plan_;
     const double* hx; const int32_t *hs, *hi;
-    read_view(true, &hx, &hs, &hi);
+    read_view(true, &hx, &hs, &hi);  // continues the stopped / failed instances; their columns in HBM are replaced
   }
   long long aided() const { return aided_; }
   void copy_instance_from(const Batch& sub, size_t k, size_t i) {
@@ -426,6 +442,8 @@ class Batch {
         hl[i] += (int32_t)ld_sum[k];
         copy_instance_from(sub, k, i);
         S21_CUDA(cudaMemcpyAsync(status_.p + i, hs + i, sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
+        S21_CUDA(cudaMemcpyAsync(iters_.p + i, hi + i, sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
+        S21_CUDA(cudaMemcpyAsync(loads_.p + i, hl + i, sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
         aided_++;
       }
       S21_CUDA(cudaStreamSynchronize(stream_));
@@ -474,45 +492,65 @@ class Batch {
     }
     rows_fresh_ = false;
   }
+  static bool pivot_stop_enabled() { const char* e = std::getenv("S21_PIVOT_HEALTH"); return !e || std::atoi(e) != 0; }
   static bool pivot_repair_enabled() { const char* e = std::getenv("S21_PIVOT_REPAIR"); return !e || std::atoi(e) != 0; }
-  // Per-instance re-pivoting (first half). The flagged instances of the last dcop are gathered into a batch
-  // of their own — same circuit, their slices of every override — whose symbolic phase runs on ITS first instance's
-  // values; the kernels that interpret plan tables are used (a specialised kernel would cost an NVRTC run per pivot
-  // order). Instances still flagged under that order recurse with the next instance leading, so in the worst case every
-  // outlier ends up with its own order, as in the reference. Results replace the rows of the host buffer and the x
-  // columns in HBM (so that a following warm solve starts from them). A repaired instance is solved from a cold start.
-  void repair_dcop(const std::vector<size_t>& flagged, double* hx, int32_t* hs, int32_t* hi, int32_t* hl) {
+  // Per-instance re-pivoting (first half): continue the instances a kernel stopped with ST_REPIVOT_CODE.
+  // Round by round, the open instances are gathered into a batch of their own — same circuit, their slices of every
+  // override, their x / device-state columns copied across (a WARM continuation at the iterate where each one stopped) —
+  // whose symbolic phase runs on its first instance's matrix AT THAT ITERATE, so its leader's next factorisation passes
+  // the reference's threshold test by construction and every round advances at least the leader by one Newton iteration;
+  // instances the new order suits run on to convergence, the others stop again and go into the next round. Plan-table
+  // kernels only (a specialised kernel would cost an NVRTC run per pivot order). Iteration counts accumulate across
+  // rounds against the reference's cap of 100 per solve.
+  void resolve_repivot(const std::vector<size_t>& flagged, double* hx, int32_t* hs, int32_t* hi, int32_t* hl) {
     const int N = flat_.n_vars();
-    std::vector<size_t> todo = flagged;
-    // the leader of a repair batch that is itself still flagged keeps its result: its own first-iteration order IS what
-    // this design can offer it (the matrix moved away from it during the Newton loop)
-    if (repair_depth_ > 0 && !todo.empty() && todo[0] == 0) todo.erase(todo.begin());
-    if (todo.empty()) return;
-    Batch sub(spec_, flat_, device_, todo.size());
-    sub.repair_depth_ = repair_depth_ + 1;
-    sub.allow_jit_ = false;
-    sub.set_stream(stream_);
-    std::vector<double> vals(todo.size());
-    for (const Override& o : overrides_) {
-      for (size_t k = 0; k < todo.size(); k++) vals[k] = o.values[todo[k]];
-      sub.add_override(o.kind + ":" + o.name + ":" + o.param, vals.data());
+    std::vector<size_t> open = flagged;
+    for (int round = 0; round < 128 && !open.empty(); round++) {
+      std::unique_ptr<Batch> sub(new Batch(spec_, flat_, device_, open.size()));
+      sub->repair_depth_ = repair_depth_ + 1;
+      sub->no_resolve_ = true;  // its stopped instances come back to this loop
+      sub->allow_jit_ = false;
+      sub->set_stream(stream_);
+      std::vector<double> vals(open.size());
+      for (const Override& o : overrides_) {
+        for (size_t k = 0; k < open.size(); k++) vals[k] = o.values[open[k]];
+        sub->add_override(o.kind + ":" + o.name + ":" + o.param, vals.data());
+      }
+      sub->gmin_eff_ = gmin_eff_;
+      sub->reset_pending_ = false;
+      int used = 100;
+      for (size_t k = 0; k < open.size(); k++) {
+        sub->copy_instance_from(*this, open[k], k);
+        used = std::min(used, (int)hi[open[k]]);
+      }
+      sub->max_iter_ = std::max(1, max_iter_ - used);
+      sub->dcop_device();
+      const double* sx = nullptr;
+      const int32_t *ss = nullptr, *si = nullptr;
+      sub->read_view(true, &sx, &ss, &si);
+      const int32_t* sl = si + open.size();
+      std::vector<size_t> next;
+      for (size_t k = 0; k < open.size(); k++) {
+        const size_t i = open[k];
+        hi[i] += si[k];
+        hl[i] += sl[k];
+        int32_t st = ss[k];
+        if (st == ST_CONV && hi[i] < max_iter_) st = ST_REPIVOT_CODE;  // ran out of THIS launch's budget, not of the solve's
+        copy_instance_from(*sub, k, i);
+        if (st == ST_REPIVOT_CODE && hi[i] < max_iter_) { next.push_back(i); continue; }
+        hs[i] = st == ST_REPIVOT_CODE ? ST_CONV : st;  // the cap of 100 iterations was reached while re-pivoting
+        std::memcpy(hx + i * (size_t)N, sx + k * (size_t)N, (size_t)N * sizeof(double));
+        S21_CUDA(cudaMemcpyAsync(status_.p + i, hs + i, sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
+        S21_CUDA(cudaMemcpyAsync(iters_.p + i, hi + i, sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
+        S21_CUDA(cudaMemcpyAsync(loads_.p + i, hl + i, sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
+        repaired_++;
+      }
+      S21_CUDA(cudaStreamSynchronize(stream_));
+      repivot_rounds_++;
+      open.swap(next);
     }
-    sub.dcop_device();
-    const double* sx = nullptr;
-    const int32_t *ss = nullptr, *si = nullptr;
-    sub.read_view(true, &sx, &ss, &si);  // recurses for instances the new order does not suit either
-    const int32_t* sl = si + todo.size();
-    for (size_t k = 0; k < todo.size(); k++) {
-      const size_t i = todo[k];
-      std::memcpy(hx + i * (size_t)N, sx + k * (size_t)N, (size_t)N * sizeof(double));
-      hs[i] = ss[k]; hi[i] = si[k]; hl[i] = sl[k];
-      S21_CUDA(cudaMemcpy2DAsync(x_.p + i, Bs_ * sizeof(double), sx + k * (size_t)N, sizeof(double), sizeof(double), (size_t)N,
-                                 cudaMemcpyHostToDevice, stream_));
-      S21_CUDA(cudaMemcpyAsync(status_.p + i, hs + i, sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
-    }
-    S21_CUDA(cudaStreamSynchronize(stream_));
+    for (size_t i : open) hs[i] = ST_PIVOT;  // 128 rounds without settling
     rows_fresh_ = false;
-    repaired_ += (long long)todo.size() + sub.repaired_;
   }
   long long weak_seen() const { return weak_seen_; }
   long long repaired() const { return repaired_; }
@@ -687,11 +725,11 @@ class Batch {
     ensure_plan(op_plan_, AN_OP, 0.0);
     S21_CUDA(cudaEventRecord(ev0_, stream_));
     run_op();
+    rescue_op();
     {  // the reference stops at the OP error (analysis.rs:775)
       int32_t st0 = 0;
       S21_CUDA(cudaMemcpyAsync(&st0, status_.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
       S21_CUDA(cudaStreamSynchronize(stream_));
-      st0 &= 0xff;  // bit 8 = pivot-health flag
       if (st0 != ST_OK) throw S21Error(st0, status_text(st0));
     }
     const size_t Fs = (F + 31) / 32 * 32;
@@ -766,7 +804,6 @@ class Batch {
     S21_CUDA(cudaStreamSynchronize(stream_));
     sum_iters_ = 0; sum_loads_ = 0;
     for (size_t f = 0; f < F; f++) {
-      if (hs[f] & 0x100) { hs[f] &= 0xff; weak_seen_++; }
       if (status) status[f] = hs[f];
       if (iters) iters[f] = hi[f];
       sum_iters_ += hi[f]; sum_loads_ += hl[f];
@@ -778,6 +815,32 @@ class Batch {
     }
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, ev0_, ev1_) == cudaSuccess) last_ms_ = ms;
+    else (void)cudaGetLastError();  // an event of the pair not recorded yet (a read between two launches): nothing to carry on
+    // Frequency points the order taken from the first point does not suit (a kernel stopped them with ST_REPIVOT_CODE:
+    // jwC entries grow over the sweep) are solved again as a sweep of their own, whose order comes from ITS first point.
+    std::vector<size_t> again;
+    for (size_t f = 0; f < F; f++) if (hs[f] == ST_REPIVOT_CODE) again.push_back(f);
+    weak_seen_ += (long long)again.size();
+    if (!again.empty() && again.size() < F + (size_t)(again[0] != 0) && ac_depth_ < 16) {
+      std::vector<double> fs(again.size()), xs(again.size() * (size_t)N * 2);
+      std::vector<int32_t> ss(again.size()), is(again.size());
+      for (size_t k = 0; k < again.size(); k++) fs[k] = freqs[again[k]];
+      const float ms_keep = last_ms_;
+      const long long it_keep = sum_iters_, ld_keep = sum_loads_;
+      ac_depth_++;
+      ac(fs.data(), fs.size(), xs.data(), ss.data(), is.data());
+      ac_depth_--;
+      last_ms_ += ms_keep; sum_iters_ += it_keep; sum_loads_ += ld_keep;
+      for (size_t k = 0; k < again.size(); k++) {
+        const size_t f = again[k];
+        if (status) status[f] = ss[k];
+        if (iters) iters[f] = is[k];
+        if (x_out) std::memcpy(x_out + f * (size_t)N * 2, xs.data() + k * (size_t)N * 2, (size_t)N * 2 * sizeof(double));
+        repaired_++;
+      }
+    } else if (status) {
+      for (size_t f : again) status[f] = ST_PIVOT;
+    }
   }
 
   const Plan* last_plan() const { return last_plan_ ? &last_plan_->host : nullptr; }
@@ -815,10 +878,13 @@ class Batch {
   double* ext_x_ = nullptr;       // set_result_target
   size_t wave_T_ = 0, wave_ns_ = 0;
   int repair_depth_ = 0;
+  bool no_resolve_ = false;
+  int ac_depth_ = 0;
+  int max_iter_ = 100;           // iteration budget of the next real solves (a solve continued after a re-pivot gets the rest)
   int aids_ = 0;                 // set_aids: bit 0 gmin stepping, bit 1 source stepping (both off: the reference has neither)
   double gmin_eff_ = -1.0;       // >= 0: overrides Options.gmin for the next solves (gmin stepping)
   long long aided_ = 0;
-  long long weak_seen_ = 0, repaired_ = 0;
+  long long weak_seen_ = 0, repaired_ = 0, repivot_rounds_ = 0;
   int32_t* ext_tail_ = nullptr;
   PinnedBuf<int32_t> hstatus_, hiters_, hloads_;
   std::vector<int> pcode_h_, poff_eff_, pdirect_h_;
@@ -921,8 +987,9 @@ class Batch {
     size_t stride = Bs_, st_stride = Bs_;
     int B = (int)B_, n_state = flat_.n_state, md = mode, cold_i = cold ? 1 : 0, Tp = T, ns = n_save;
     double gmin = gmin_eff_ >= 0.0 ? gmin_eff_ : flat_.opts.gmin, dtv = dt, reltol = flat_.opts.reltol, iabstol = flat_.opts.iabstol;
+    int max_iter = max_iter_;
     void* args[] = {&pval, &gx, &sop, &sg, &st, &it, &ld, &stride, &st_stride, &B, &n_state, &md, &gmin, &dtv, &reltol, &iabstol,
-                    &cold_i, &Tp, &ns, &save_vars, &wave, &rows};  // `rows` is the team kernel's last parameter only
+                    &cold_i, &Tp, &ns, &save_vars, &wave, &rows, &max_iter};  // `rows`: written by the warp-private team kernel only
     const unsigned grid = (unsigned)((B_ + (size_t)k.inst_per_cta - 1) / (size_t)k.inst_per_cta);
     return jit::api().cuLaunchKernel(k.fn, grid, 1, 1, (unsigned)k.tpb, 1, 1, (unsigned)k.smem, (void*)stream_, args, nullptr);
   }
@@ -1027,6 +1094,8 @@ class Batch {
     c.reltol = flat_.opts.reltol; c.iabstol = flat_.opts.iabstol; c.omega = nullptr; c.par_inst_stride = 1;
     c.has_bsim4 = 0;
     for (const FlatDev& d : flat_.devs) if (d.type == DT_BSIM4) { c.has_bsim4 = 1; break; }
+    c.max_iter = max_iter_;
+    c.stop_on_weak = (mode == AN_OP || mode == AN_AC) && pivot_stop_enabled() ? 1 : 0;
     c.relaxed = (mode == AN_OP ? op_plan_ : mode == AN_TRAN ? tran_plan_ : ac_plan_).host.relaxed ? 1 : 0;
     return c;
   }
@@ -1088,9 +1157,20 @@ class Batch {
     DevTables dtab = dev_tables(d_itab_raw_.p);
     DBuf<double> probe;
     probe.alloc((size_t)flat_.n_elems());
+    // The probe is one more load sweep of instance 0 on the live workspace; devices with iteration-carried state (Diode
+    // limiting, Bsim4 limiting and von) write their in-flight copy during a load, which would make instance 0's next real
+    // iteration limit against the probe instead of its own previous iteration. Its guess column is kept and put back.
+    DBuf<double> keep;
+    const size_t ns_rows = (size_t)flat_.n_state;
+    if (ns_rows) {
+      keep.alloc(ns_rows);
+      S21_CUDA(cudaMemcpy2DAsync(keep.p, sizeof(double), st_guess_.p, Bs_ * sizeof(double), sizeof(double), ns_rows, cudaMemcpyDeviceToDevice, stream_));
+    }
     int rc = launch_probe_real(dtab, work(), make_ctl(mode, dt), flat_.n_elems(), N, 0, probe.p, stream_);
     launches_++;
     if (rc) throw S21Error(ST_CUDA, std::string("k_probe launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+    if (ns_rows)
+      S21_CUDA(cudaMemcpy2DAsync(st_guess_.p, Bs_ * sizeof(double), keep.p, sizeof(double), sizeof(double), ns_rows, cudaMemcpyDeviceToDevice, stream_));
     std::vector<double> vals((size_t)flat_.n_elems());
     S21_CUDA(cudaMemcpyAsync(vals.data(), probe.p, vals.size() * sizeof(double), cudaMemcpyDeviceToHost, stream_));
     S21_CUDA(cudaStreamSynchronize(stream_));
@@ -1120,7 +1200,7 @@ class Batch {
     Plan& P = pd.host;
     pd.row_i2e.upload(P.row_i2e, stream_); pd.col_i2e.upload(P.col_i2e, stream_); pd.col_e2i.upload(P.col_e2i, stream_);
     pd.rowptr.upload(P.rowptr, stream_); pd.colidx.upload(P.colidx, stream_); pd.diag_slot.upload(P.diag_slot, stream_);
-    pd.l_off.upload(P.l_off, stream_); pd.l_slot.upload(P.l_slot, stream_); pd.l_row.upload(P.l_row, stream_);
+    pd.l_off.upload(P.l_off, stream_); pd.l_slot.upload(P.l_slot, stream_); pd.l_row.upload(P.l_row, stream_); pd.piv_chk.upload(P.piv_checked, stream_);
     pd.upd_off.upload(P.upd_off, stream_); pd.upd_t.upload(P.upd_t, stream_); pd.upd_u.upload(P.upd_u, stream_); pd.upd_l.upload(P.upd_l, stream_);
     std::vector<int> itab = itab_with_slots(flat_, P);
     pd.itab.upload(itab, stream_);

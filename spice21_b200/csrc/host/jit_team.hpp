@@ -299,7 +299,7 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
 
   o << "extern \"C\" __global__ void __launch_bounds__(" << NW * 32 << ", " << 2 << ") k_jit(const double* __restrict__ pval, double* gx, double* st_op, double* st_guess,\n"
        "    int* status, int* iters, int* loads, size_t stride, size_t st_stride, int B, int n_state_arg, int mode, double gmin, double dt,\n"
-       "    double reltol, double iabstol, int cold, int T_points, int n_save, const int* __restrict__ save_vars, double* wave" << (XP ? ", double* rows" : "") << ") {\n"
+       "    double reltol, double iabstol, int cold, int T_points, int n_save, const int* __restrict__ save_vars, double* wave, double* rows, int max_iter) {\n"
        "  extern __shared__ __align__(16) unsigned char smem_raw[];\n"
        "  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;\n"
        "  const int i0 = blockIdx.x * " << GI << ";\n"
@@ -319,7 +319,7 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
        "    const size_t src = (size_t)k * st_stride + (size_t)i0 + (size_t)(evalid ? ei : 0);\n"
        "    sop[k * PS + ei] = cold ? 0.0 : st_op[src];\n    sguess[k * PS + ei] = cold ? 0.0 : st_guess[src];\n  }\n"
        "  int r_stat = " << (tran ? "rvalid ? status[i0 + ri] : 0" : "0") << ";\n"
-       "  int r_wk = ((r_stat >> 8) & 1) ? 0x7ff00000 : 0;\n  r_stat &= 0xff;\n"
+       "  int r_wk = 0;\n"
        "  int r_nsol = 0, r_nld = 0;\n"
        "  __syncthreads();\n";
   if (tran)
@@ -351,7 +351,7 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
       default: return nullptr;
     }
   };
-  o << "    for (int iter = 0; iter < 100; iter++) {\n      PH(0)\n";
+  o << "    for (int iter = 0; iter < max_iter; iter++) {\n      PH(0)\n";
   if (WP) {
     // ---- device evaluation, warp-private: member j of instance `ri` evaluates device j of each slot
     for (size_t sidx = 0; sidx < slots.size(); sidx++) {
@@ -432,7 +432,7 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
         for (int q = 0; q < Q; q++)
           if (LM[(size_t)q][(size_t)k]) {
             divide(A(q, k), A(q, k), "piv", "rp", "pok", mask_test(LM[(size_t)q][(size_t)k]));
-            if (health)  // integer max of the multipliers' high words (monotonic in |l|): ALU pipe, no predicate kept alive
+            if (health && !tran && P.piv_checked[(size_t)k])  // (dcop text only: nobody re-pivots inside a device-resident time loop)  // (threshold-checked pivots only) integer max of the multipliers' high words (monotonic in |l|): ALU pipe, no predicate kept alive
               o << "            if (" << mask_test(LM[(size_t)q][(size_t)k]) << ") r_wk = max(r_wk, __double2hiint(" << A(q, k) << ") & 0x7fffffff);\n";
           }
         for (int s = P.diag_slot[(size_t)k] + 1; s < P.rowptr[(size_t)k + 1]; s++) {
@@ -513,7 +513,7 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
     o << "          }\n";
     // deferred exceptions: some quotient of this warp left the fast path's domain -> the exact text, from the stamps
     // (only of instances still iterating: finished and padding instances compute on stale or arbitrary data)
-    o << "          if (__any_sync(FULLM, dbad && r_act)) {\n          sing = false;\n";
+    o << "          if (__any_sync(FULLM, dbad && r_act)) {\n          sing = false;\n          r_wk = 0;\n";  // the fast text's quotients were not valid
     std::string g2 = gath.str();
     o << g2;
     emit_residual(o);
@@ -532,13 +532,16 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
       o << "          m = fmax(m, __shfl_sync(FULLM, m, j + " << off << " < " << TM_LPI << " ? lane + " << IPW * off << " : lane));\n";
     o << "          m = BC(m, 0);\n";
   }
-  o << "          bool baddx = false;\n          const double rm = s_rcp(m);\n          if (r_act && !sing) {\n";
+  // pivot health: a multiplier of this factorisation >= 1000 on any lane of the instance -> stop before the update, the host
+  // re-pivots at this iterate (kernels/newton.cu, host/batch.hpp resolve_repivot)
+  o << "          const bool wk = (__ballot_sync(FULLM, r_wk > 0x408f4000) & imask) != 0;\n          r_wk = 0;\n";
+  o << "          bool baddx = false;\n          const double rm = s_rcp(m);\n          if (r_act && !sing && !wk) {\n";
   for (int q = 0; q < Q; q++)
     o << "            if (v" << q << ") { double dxk = c" << q << "; if (m > 1.0) dxk = s_div_r(s_mul(dxk, 1.0), m, rm); xp" << q << " = s_add(xp" << q
       << ", dxk); X[xo" << q << " + ri] = xp" << q << "; baddx = baddx || (s_abs(dxk) > reltol); }\n";
   o << "          }\n"
        "          r_dxok = (__ballot_sync(FULLM, baddx) & imask) == 0;\n"
-       "          if (r_act) {\n            if (sing) { r_act = false; r_stat = 2; }\n            else r_nsol += 1;\n          }\n"
+       "          if (r_act) {\n            if (sing) { r_act = false; r_stat = 2; }\n            else if (wk) { r_act = false; r_stat = 9; }\n            else r_nsol += 1;\n          }\n"
        "        }\n      }\n"
        << (WP ? "      PH(8)\n      __syncwarp();\n      const bool any_ = __any_sync(FULLM, r_act);\n      PH(9)\n      if (!any_) break;\n"
               : "      if (j == 0 && rin) act_s[ri] = r_act ? 1 : 0;\n      PH(8)\n"
@@ -549,19 +552,19 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
     o << "    if (rvalid) {\n      const bool good = r_stat == 0;\n      for (int s = j; s < n_save; s += " << TM_LPI << ")\n"
          "        wave[((size_t)tp * n_save + s) * stride + i0 + ri] = good ? X[save_vars[s] * PS + ri] : __longlong_as_double(0x7ff8000000000000LL);\n"
          "    }\n";
-  o << "  }\n  const bool weak_any = (__ballot_sync(FULLM, r_wk > 0x408f3fff && rvalid) & imask) != 0  /* a multiplier >= 1000 */;\n  __syncthreads();\n"
+  o << "  }\n  __syncthreads();\n"
        "  if (evalid) {\n"
        "    for (int k = warp; k < " << N << "; k += " << NW << ") gx[(size_t)k * stride + i0 + ei] = X[k * PS + ei];\n"
        "    for (int k = warp; k < " << flat.n_state << "; k += " << NW << ") {\n"
        "      const size_t dst = (size_t)k * st_stride + i0 + ei;\n"
        "      st_op[dst] = sop[k * PS + ei];\n      st_guess[dst] = sguess[k * PS + ei];\n    }\n  }\n"
        "  if (rvalid && j == 0) {\n"
-       "    status[i0 + ri] = r_stat | (weak_any ? 0x100 : 0);\n"
+       "    status[i0 + ri] = r_stat;\n"
        "    iters[i0 + ri] = (cold ? 0 : iters[i0 + ri]) + r_nsol;\n"
        "    loads[i0 + ri] = (cold ? 0 : loads[i0 + ri]) + r_nld;\n  }\n";
-  if (XP)  // the host's result layout (k_pack_out in kernels/newton.cu), written here so that a read needs no second kernel
+  if (XP)  // (rows is always a parameter; only the warp-private build writes it) the host's result layout (k_pack_out in kernels/newton.cu), written here so that a read needs no second kernel
     o << "  if (rows) {\n    __syncthreads();\n"
-         "    if (rvalid && j == 0) { int* tail = (int*)(rows + (size_t)B * " << N << "); tail[i0 + ri] = r_stat | (weak_any ? 0x100 : 0); tail[(size_t)B + i0 + ri] = iters[i0 + ri];"
+         "    if (rvalid && j == 0) { int* tail = (int*)(rows + (size_t)B * " << N << "); tail[i0 + ri] = r_stat; tail[(size_t)B + i0 + ri] = iters[i0 + ri];"
          " tail[2 * (size_t)B + i0 + ri] = loads[i0 + ri]; }\n"
          "    if (evalid) for (int k = warp; k < " << N << "; k += " << NW << ") rows[(size_t)(i0 + ei) * " << N << " + k] = X[k * PS + ei];\n  }\n";
   if (prof)

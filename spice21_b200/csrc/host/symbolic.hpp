@@ -33,6 +33,9 @@ struct Plan {
   // Numeric refactorisation, pivot k = 0..N-2: L_k = slots below the diagonal in column k (with their rows),
   // and one (target, u, l) triple per Schur update. Offsets have N entries + 1.
   std::vector<int> l_off, l_slot, l_row;
+  // [N] 1 when pivot k was chosen by the reference's diagonal search, i.e. passed its 1e-3 threshold against its column; the
+  // fallback searches (mod.rs:785-863) apply no threshold, so the kernels' pivot-health test skips those pivots.
+  std::vector<int> piv_checked;
   std::vector<int> upd_off, upd_t, upd_u, upd_l;
   // Level schedule for the cooperative kernel: the same operations, grouped so that every operation of a level is
   // independent of the others in it (one barrier per level). Within any single value the operations keep the
@@ -86,7 +89,7 @@ inline void build_levels(Plan& P, bool relaxed = false) {
       for (int j = P.l_off[(size_t)k]; j < P.l_off[(size_t)k + 1]; j++) {
         const int ls = P.l_slot[(size_t)j];
         const int lv = std::max(ready[(size_t)ls], ready[(size_t)piv]) + 1;
-        t.push_back(ls); u.push_back(piv); l.push_back(-1); lev.push_back(lv);
+        t.push_back(ls); u.push_back(piv); l.push_back(P.piv_checked[(size_t)k] ? -1 : -2); lev.push_back(lv);  // -1: division by a threshold-checked pivot, -2: unchecked
         ready[(size_t)ls] = lv;
       }
       for (int j = P.upd_off[(size_t)k]; j < P.upd_off[(size_t)k + 1]; j++) {
@@ -308,6 +311,7 @@ Plan build_plan(int N, const std::vector<int>& elem_row, const std::vector<int>&
   double t_search = 0.0, t_elim = 0.0;
   size_t n_upd = 0, n_cand = 0;
   const auto t_begin = clk::now();
+  P.piv_checked.assign((size_t)std::max(N, 1), 0);
   for (int n = 0; n + 1 < N && P.status == ST_OK; n++) {
     int pivot = -1;
     const auto t_s0 = clk::now();
@@ -347,6 +351,7 @@ Plan build_plan(int N, const std::vector<int>& elem_row, const std::vector<int>&
         }
       }
     }
+    P.piv_checked[(size_t)n] = pivot >= 0 ? 1 : 0;
     if (pivot < 0) {  // ---- markowitz_search_submatrix: column n only
       std::vector<std::pair<int, int>> cand;  // (internal row, id)
       for (int id : in_col[(size_t)P.col_i2e[(size_t)n]]) {

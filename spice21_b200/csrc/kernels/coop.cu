@@ -97,8 +97,8 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
 
   // ---- prologue
   if (tid < gi) {
-    const int st0 = (tid < ni && KIND == K_TRAN) ? o.status[i0 + tid] : 0;
-    stat[tid] = st0 & 0xff; weak[tid] = (st0 >> 8) & 1;
+    stat[tid] = (tid < ni && KIND == K_TRAN) ? o.status[i0 + tid] : 0;
+    weak[tid] = 0;
     nsol[tid] = 0; nld[tid] = 0; convnow[tid] = 0; dxok[tid] = 1; act[tid] = 0;
   }
   if constexpr (SMEM) {
@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
   for (int tp = 1; tp < n_points; tp++) {
     if (tid < gi) { act[tid] = (tid < ni && stat[tid] == CST_OK) ? 1 : 0; dxok[tid] = 1; }
     __syncthreads();
-    for (int iter = 0; iter < TolC<T>::max_iter; iter++) {
+    const int max_it = real_kind ? min(TolC<T>::max_iter, ctl.max_iter) : TolC<T>::max_iter;
+    for (int iter = 0; iter < max_it; iter++) {
       const bool on = act[li] != 0;  // stable until the decision phase (which is fenced by barriers on both sides)
       // ---- P1: device evaluation (Solver::update, analysis.rs:153-168), devices in parallel
       if (on) {
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
           load_one<T, B4>(d.type[dev], e, (d.par_direct && d.par_direct[dev]) ? d.pval + d.par_off[dev] : nullptr);
         }
       }
-      if (tid < gi) { resok[tid] = 1; sing[tid] = 0; maxabs[tid] = 0.0; }
+      if (tid < gi) { resok[tid] = 1; sing[tid] = 0; weak[tid] = 0; maxabs[tid] = 0.0; }
       __syncthreads();
       // ---- P2: assembly — gather staging slots per L+U slot / rhs row in the reference's accumulation order
       if (on) {
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
             T* t = lu + (I)ct.lu_t[op] * ws + col;
             const T u = lu[(I)ct.lu_u[op] * ws + col];
             if (l < 0) {
-              if (s_abs(u) * 1e3 < s_abs(*t)) weak[li] = 1;
+              if (l == -1 && ctl.stop_on_weak && s_abs(u) * 1.000001e3 < s_abs(*t)) weak[li] = 1;  // -2: a pivot the reference chose without threshold
               *t = s_div(*t, u);
             } else {
               *t = s_sub(*t, s_mul(u, lu[(I)l * ws + col]));
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
       }
       __syncthreads();
       // ---- global step limit and update (analysis.rs:197-207 / 283-293)
-      if (go && !sing[li]) {
+      if (go && !sing[li] && !weak[li]) {
         const double m = maxabs[li];
         for (int k = item0; k < N; k += istep) {
           T dxk = c[(I)p.col_e2i[k] * ws + col];
@@ -253,6 +254,7 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
       __syncthreads();
       if (tid < gi && act[tid]) {
         if (sing[tid]) { act[tid] = 0; stat[tid] = CST_SINGULAR; }
+        else if (weak[tid]) { act[tid] = 0; stat[tid] = CST_REPIVOT; }  // x untouched: the host re-pivots at this iterate and continues
         else {
           nsol[tid] += 1;
           if (KIND == K_AC && ctl.ac_direct) act[tid] = 0;  // linear system: x = A^-1 b is the answer (engine.hpp SolveCtl::ac_direct)
@@ -285,7 +287,7 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
     }
   }
   if (tid < ni) {
-    o.status[i0 + tid] = stat[tid] | (weak[tid] << 8);
+    o.status[i0 + tid] = stat[tid];
     o.iters[i0 + tid] += nsol[tid];
     o.loads[i0 + tid] += nld[tid];
   }

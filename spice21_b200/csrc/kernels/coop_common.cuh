@@ -12,7 +12,7 @@ namespace s21 {
 namespace coopk {
 
 enum { K_DCOP = 0, K_TRAN = 1, K_AC = 2 };
-enum { CST_OK = 0, CST_CONV = 1, CST_SINGULAR = 2 };
+enum { CST_OK = 0, CST_CONV = 1, CST_SINGULAR = 2, CST_REPIVOT = 9 };  // 9 = engine.hpp ST_REPIVOT_CODE
 
 // ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier (sm_90+; SASS: UBLKCP + SYNCS)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

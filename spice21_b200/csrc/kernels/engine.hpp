@@ -33,6 +33,7 @@ struct PlanTables {
   const int *row_i2e, *col_i2e, *col_e2i;
   const int *rowptr, *colidx, *diag_slot;
   const int *l_off, *l_slot, *l_row;
+  const int* piv_chk;  // [N] pivot k passed the reference's threshold test when it was chosen: the pivot-health test applies to it
   const int *upd_off, *upd_t, *upd_u, *upd_l;
 };
 
@@ -48,6 +49,12 @@ struct WorkTables {
   double* st_guess;  // [n_state] in-flight device state
   size_t st_stride;
 };
+
+// Kernel-internal status: a frozen pivot fell below the reference's 1e-3 threshold against an entry under it (the
+// reference re-runs its pivot search in every factorisation, sparse21/mod.rs:929-932, 735-783, and would have chosen
+// otherwise). The instance stops before the update, x at the current iterate; the host takes a new pivot order from that
+// iterate and continues the solve (host/batch.hpp resolve_repivot). Callers never see this code.
+enum { ST_REPIVOT_CODE = 9 };
 
 struct NewtonOut {
   int32_t* status;    // [B] S21_* code
@@ -66,6 +73,12 @@ struct SolveCtl {
   // x = 0 with no step limit (x = A^-1 b). 0: the reference's Newton shell (analysis.rs:253-303: 1.0 step limit, <= 20
   // iterations, a second factorisation to confirm) — kept for iteration-count parity; it cannot reach |x| > ~19 from a cold start.
   int ac_direct = 0;
+  // 1: stop an instance at a weak frozen pivot (ST_REPIVOT_CODE) — set where the host can re-pivot and continue (dcop, the OP
+  // that opens a transient / AC sweep, AC points); 0: carry on with the frozen order (inside a device-resident time loop there
+  // is nobody to hand the instance to; round 1's behaviour)
+  int stop_on_weak = 0;
+  int max_iter = 100;      // real solves: iteration budget of this launch (analysis.rs:173 caps a solve at 100; a solve continued
+                           // after a re-pivot gets what is left)
   int relaxed = 0;         // the plan's level schedules are in tolerance mode (host/symbolic.hpp build_levels): apply updates atomically
   int has_bsim4 = 0;       // selects the kernel build that links the Bsim4 evaluation (kept out of the others: register pressure)
 };
@@ -121,7 +134,7 @@ int launch_hybrid_ac(const DevTables& d, const PlanTables& p, const CoopTables& 
 // Grid-wide variant (kernels/grid.cu) for ONE large circuit (B = 1, instance stride 1, workspace and staging in HBM/L2):
 // a cooperative launch with grid barriers between phases / dependency levels. `gc` is a device-resident control block.
 struct GridCtl {
-  int stat, nsol, nld, dxok, act, resok, sing, convnow;
+  int stat, nsol, nld, dxok, act, resok, sing, convnow, weak;
   unsigned long long maxabs;
 };
 int launch_grid_dcop(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<double>& w, double* stage, const NewtonOut& o,

@@ -35,8 +35,8 @@ __global__ void __launch_bounds__(256, B4 ? 1 : 2) k_grid(DevTables d, PlanTable
   const double vtol = ctl.reltol, itol = ctl.iabstol;
 
   if (tid == 0) {
-    gc->stat = KIND == K_TRAN ? (o.status[0] & 0xff) : 0;
-    gc->nsol = 0; gc->nld = 0; gc->dxok = 1; gc->act = 0; gc->resok = 1; gc->sing = 0; gc->maxabs = 0ull;
+    gc->stat = KIND == K_TRAN ? o.status[0] : 0;
+    gc->nsol = 0; gc->nld = 0; gc->dxok = 1; gc->act = 0; gc->resok = 1; gc->sing = 0; gc->weak = 0; gc->maxabs = 0ull;
   }
   if constexpr (KIND == K_TRAN) {
     for (size_t s = tid; s < (size_t)n_save; s += nt) wave[s] = x[save_vars[s]];
@@ -46,7 +46,8 @@ __global__ void __launch_bounds__(256, B4 ? 1 : 2) k_grid(DevTables d, PlanTable
   for (int tp = 1; tp < n_points; tp++) {
     if (tid == 0) { gc->act = gc->stat == CST_OK ? 1 : 0; gc->dxok = 1; }
     grid.sync();
-    for (int iter = 0; iter < TolC<double>::max_iter; iter++) {
+    const int max_it = min(TolC<double>::max_iter, ctl.max_iter);
+    for (int iter = 0; iter < max_it; iter++) {
       if (!gc->act) break;  // uniform: written before the last barrier
       // ---- P1: device evaluation, devices in parallel
       for (size_t item = tid; item < (size_t)d.n_dev; item += nt) {
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(256, B4 ? 1 : 2) k_grid(DevTables d, PlanTable
         e.mode = ctl.mode; e.dt = ctl.dt; e.gmin = ctl.gmin; e.omega = 0.0;
         load_one<double, B4>(d.type[dev], e, (d.par_direct && d.par_direct[dev]) ? d.pval + d.par_off[dev] : nullptr);
       }
-      if (tid == 0) { gc->resok = 1; gc->sing = 0; gc->maxabs = 0ull; }
+      if (tid == 0) { gc->resok = 1; gc->sing = 0; gc->weak = 0; gc->maxabs = 0ull; }
       grid.sync();
       // ---- P2: assembly (fill-in slots have empty lists and come out as exact zeros)
       for (size_t t = tid; t < (size_t)(nnz + N); t += nt) {
@@ -105,8 +106,10 @@ __global__ void __launch_bounds__(256, B4 ? 1 : 2) k_grid(DevTables d, PlanTable
           const int l = ct.lu_l[op];
           double* t = lu + ct.lu_t[op];
           const double u = lu[ct.lu_u[op]];
-          if (l < 0) *t = s_div(*t, u);
-          else if (ctl.relaxed) atomicAdd(t, -s_mul(u, lu[l]));  // several updates of one level may share the target
+          if (l < 0) {
+            if (l == -1 && ctl.stop_on_weak && s_abs(u) * 1.000001e3 < s_abs(*t)) gc->weak = 1;  // pivot health (newton.cu)
+            *t = s_div(*t, u);
+          } else if (ctl.relaxed) atomicAdd(t, -s_mul(u, lu[l]));  // several updates of one level may share the target
           else *t = s_sub(*t, s_mul(u, lu[l]));
         }
         grid.sync();
@@ -149,7 +152,7 @@ __global__ void __launch_bounds__(256, B4 ? 1 : 2) k_grid(DevTables d, PlanTable
       }
       grid.sync();
       // ---- global step limit and update
-      if (!gc->sing) {
+      if (!gc->sing && !gc->weak) {
         const double m = __longlong_as_double((long long)gc->maxabs);
         bool ok = true;
         for (size_t k = tid; k < (size_t)N; k += nt) {
@@ -163,9 +166,10 @@ __global__ void __launch_bounds__(256, B4 ? 1 : 2) k_grid(DevTables d, PlanTable
       grid.sync();
       if (tid == 0) {
         if (gc->sing) { gc->act = 0; gc->stat = CST_SINGULAR; }
+        else if (gc->weak) { gc->act = 0; gc->stat = CST_REPIVOT; }  // x untouched: the host re-pivots at this iterate and continues
         else {
           gc->nsol += 1;
-          if (iter + 1 == TolC<double>::max_iter) { gc->act = 0; gc->stat = CST_CONV; }
+          if (iter + 1 == max_it) { gc->act = 0; gc->stat = CST_CONV; }
         }
       }
       grid.sync();

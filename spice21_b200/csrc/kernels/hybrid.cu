@@ -97,8 +97,7 @@ __global__ void __launch_bounds__(256, 2) k_hyb(DevTables d, PlanTables p, CoopT
   // per-instance control state lives in registers, replicated over the 8 lanes of the instance
   const bool rvalid = ri < ni;
   int r_stat = (rvalid && KIND == K_TRAN) ? o.status[i0 + ri] : 0;
-  bool r_weak = (r_stat >> 8) & 1;  // pivot health (bit 8 of the status word, see coop.cu)
-  r_stat &= 0xff;
+  bool r_weak = false;  // pivot health (see newton.cu): set by the division steps of the current factorisation
   int r_nsol = 0, r_nld = 0;
   mbar_wait(mbar, 0);
   __syncthreads();
@@ -117,7 +116,8 @@ __global__ void __launch_bounds__(256, 2) k_hyb(DevTables d, PlanTables p, CoopT
     bool r_dxok = true;
     if (q == 0) act_s[ri] = r_act ? 1 : 0;
     __syncthreads();
-    for (int iter = 0; iter < TolC<T>::max_iter; iter++) {
+    const int max_it = real_kind ? min(TolC<T>::max_iter, ctl.max_iter) : TolC<T>::max_iter;
+    for (int iter = 0; iter < max_it; iter++) {
       // ================= device evaluation: lane = instance, warp = device (Solver::update, analysis.rs:153-168)
       PH_T(t0);
       if (act_s[ei]) {
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(256, 2) k_hyb(DevTables d, PlanTables p, CoopT
             const int l = ct.lu_l[op];
             T* t = lu + (I)ct.lu_t[op] * HY_P + ri;
             const T u = lu[(I)ct.lu_u[op] * HY_P + ri];
-            if (l < 0) { r_weak = r_weak || (s_abs(u) * 1e3 < s_abs(*t)); *t = s_div(*t, u); }
+            if (l < 0) { r_weak = r_weak || (l == -1 && ctl.stop_on_weak && s_abs(u) * 1.000001e3 < s_abs(*t)); *t = s_div(*t, u); }
             else *t = s_sub(*t, s_mul(u, lu[(I)l * HY_P + ri]));
           }
         }
@@ -234,12 +234,14 @@ __global__ void __launch_bounds__(256, 2) k_hyb(DevTables d, PlanTables p, CoopT
         }
       }
       const bool sing = (__ballot_sync(FULL, zp) & imask) != 0;
+      const bool wk = (__ballot_sync(FULL, r_weak) & imask) != 0;  // some lane of the instance divided by a weak pivot
+      r_weak = false;
       m = fmax(m, __shfl_xor_sync(FULL, m, 4));
       m = fmax(m, __shfl_xor_sync(FULL, m, 8));
       m = fmax(m, __shfl_xor_sync(FULL, m, 16));
       // ---- global step limit and update (analysis.rs:197-207 / 283-293)
       bool baddx = false;
-      if (r_act && !sing) {
+      if (r_act && !sing && !wk) {
         for (int k = q; k < N; k += HY_LPI) {
           T dxk = c[(I)p.col_e2i[k] * HY_P + ri];
           if (m > 1.0 && !(KIND == K_AC && ctl.ac_direct)) dxk = s_scale(dxk, 1.0, m);
@@ -251,6 +253,7 @@ __global__ void __launch_bounds__(256, 2) k_hyb(DevTables d, PlanTables p, CoopT
       r_dxok = (__ballot_sync(FULL, baddx) & imask) == 0;
       if (r_act) {
         if (sing) { r_act = false; r_stat = CST_SINGULAR; }
+        else if (wk) { r_act = false; r_stat = CST_REPIVOT; }  // x untouched: the host re-pivots at this iterate and continues
         else {
           r_nsol += 1;
           if (KIND == K_AC && ctl.ac_direct) r_act = false;  // linear system: one solve is the answer
@@ -275,7 +278,6 @@ __global__ void __launch_bounds__(256, 2) k_hyb(DevTables d, PlanTables p, CoopT
       }
     }
   }
-  const bool weak_any = (__ballot_sync(0xffffffffu, r_weak) & imask) != 0;  // any of the instance's lanes saw a weak pivot
   __syncthreads();
   // ---- epilogue: results back to HBM (lane = instance: coalesced)
   if (evalid) {
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(256, 2) k_hyb(DevTables d, PlanTables p, CoopT
       }
   }
   if (rvalid && q == 0) {
-    o.status[i0 + ri] = r_stat | (weak_any ? 0x100 : 0);
+    o.status[i0 + ri] = r_stat;
     o.iters[i0 + ri] = (cold ? 0 : o.iters[i0 + ri]) + r_nsol;
     o.loads[i0 + ri] = (cold ? 0 : o.loads[i0 + ri]) + r_nld;
   }

@@ -23,7 +23,7 @@
 
 namespace s21 {
 
-enum { ST_OK_ = 0, ST_CONV_ = 1, ST_SINGULAR_ = 2 };
+enum { ST_OK_ = 0, ST_CONV_ = 1, ST_SINGULAR_ = 2, ST_REPIVOT_ = 9 };  // 9: engine.hpp ST_REPIVOT_CODE
 
 // ------------------------------------------------------------------------------------------------ per-thread Env
 template <class T>
@@ -128,7 +128,7 @@ __device__ __forceinline__ void commit_state(const DevTables& d, double* st_op, 
 // The Newton shell for one instance. Returns an S21 status; *n_solves / *n_loads are incremented.
 template <class T, bool B4>
 __device__ int newton_solve(const DevTables& d, const PlanTables& p, const WorkTables<T>& wk, const SolveCtl& ctl, size_t inst,
-                            double omega, double vtol, double itol, bool do_commit, int* n_solves, int* n_loads, int* weak) {
+                            double omega, double vtol, double itol, bool do_commit, int* n_solves, int* n_loads) {
   const size_t S = wk.stride;
   T* x = wk.x + inst;
   T* rhs = wk.rhs + inst;
@@ -142,7 +142,8 @@ __device__ int newton_solve(const DevTables& d, const PlanTables& p, const WorkT
   e.mode = ctl.mode; e.dt = ctl.dt; e.gmin = ctl.gmin; e.omega = omega;
   const int N = p.N;
   bool dx_ok = true;  // dx = 0 before the first iteration
-  for (int iter = 0; iter < Tol<T>::max_iter; iter++) {
+  const int max_it = std::is_same<T, double>::value ? min(Tol<T>::max_iter, ctl.max_iter) : Tol<T>::max_iter;
+  for (int iter = 0; iter < max_it; iter++) {
     // Matrix::reset + fresh rhs (analysis.rs:178-179)
     for (int k = 0; k < p.nnz; k++) lu[(size_t)k * S] = Scalar<T>::zero();
     for (int k = 0; k < N; k++) rhs[(size_t)k * S] = Scalar<T>::zero();
@@ -166,15 +167,17 @@ __device__ int newton_solve(const DevTables& d, const PlanTables& p, const WorkT
       return ST_OK_;
     }
     // ---- numeric LU on the frozen pattern (row_col_elim, sparse21/mod.rs:865-919), ascending pivot index
+    bool weak = false;
     for (int k = 0; k + 1 < N; k++) {
       const T piv = lu[(size_t)__ldg(p.diag_slot + k) * S];
       if (s_is_zero(piv)) return ST_SINGULAR_;
       const int lb = __ldg(p.l_off + k), le = __ldg(p.l_off + k + 1);
-      const double pth = s_abs(piv) * 1e3;
+      const double pth = __ldg(p.piv_chk + k) ? s_abs(piv) * 1.000001e3 : INFINITY;  // pivots the fallback searches chose carry no threshold
       for (int j = lb; j < le; j++) {
         T* a = lu + (size_t)__ldg(p.l_slot + j) * S;
-        // pivot health: the reference would not have taken this diagonal (|d| < 1e-3 * column max, mod.rs:735-783)
-        if (pth < s_abs(*a)) *weak = 1;
+        // pivot health: the reference, which searches its pivots anew in every factorisation, would not have taken this
+        // diagonal (|d| < 1e-3 * column max, mod.rs:735-783)
+        if (pth < s_abs(*a)) weak = true;
         *a = s_div(*a, piv);
       }
       const int ub = __ldg(p.upd_off + k), ue = __ldg(p.upd_off + k + 1);
@@ -184,6 +187,9 @@ __device__ int newton_solve(const DevTables& d, const PlanTables& p, const WorkT
         *t = s_sub(*t, v);
       }
     }
+    // The frozen order no longer suits this instance's matrix: stop BEFORE the update (x stays at the current iterate) and
+    // let the host take a new order from this iterate and continue (host/batch.hpp resolve_repivot).
+    if (weak && ctl.stop_on_weak) return ST_REPIVOT_;
     // ---- forward substitution (sparse21/mod.rs:947-964)
     for (int k = 0; k < N; k++) {
       const T ck = c[(size_t)k * S];
@@ -229,9 +235,8 @@ __global__ void __launch_bounds__(128) k_dcop(DevTables d, PlanTables p, WorkTab
   const size_t inst = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (inst >= (size_t)ctl.B) return;
   int ns = 0, nl = 0;
-  int weak = 0;
-  const int st = newton_solve<double, B4>(d, p, w, ctl, inst, 0.0, ctl.reltol, ctl.iabstol, true, &ns, &nl, &weak);
-  o.status[inst] = st | (weak << 8);
+  const int st = newton_solve<double, B4>(d, p, w, ctl, inst, 0.0, ctl.reltol, ctl.iabstol, true, &ns, &nl);
+  o.status[inst] = st;
   o.iters[inst] += ns;
   o.loads[inst] += nl;
 }
@@ -244,16 +249,15 @@ __global__ void __launch_bounds__(128) k_tran(DevTables d, PlanTables p, WorkTab
   const size_t B = w.stride;  // wave is [T][n_save][stride], instance fastest, like every other per-instance table
   int st = o.status[inst];  // status of the OP solve
   for (int s = 0; s < n_save; s++) wave[(size_t)s * B + inst] = w.x[(size_t)__ldg(save_vars + s) * w.stride + inst];
-  int ns = 0, nl = 0, weak = (st >> 8) & 1;
-  st &= 0xff;
+  int ns = 0, nl = 0;
   for (int tp = 1; tp < T; tp++) {
-    if (st == ST_OK_) st = newton_solve<double, B4>(d, p, w, ctl, inst, 0.0, ctl.reltol, ctl.iabstol, true, &ns, &nl, &weak);
+    if (st == ST_OK_) st = newton_solve<double, B4>(d, p, w, ctl, inst, 0.0, ctl.reltol, ctl.iabstol, true, &ns, &nl);
     for (int s = 0; s < n_save; s++) {
       const double v = st == ST_OK_ ? w.x[(size_t)__ldg(save_vars + s) * w.stride + inst] : __longlong_as_double(0x7ff8000000000000LL);
       wave[((size_t)tp * n_save + s) * B + inst] = v;
     }
   }
-  o.status[inst] = st | (weak << 8);
+  o.status[inst] = st;
   o.iters[inst] += ns;
   o.loads[inst] += nl;
 }
@@ -284,8 +288,6 @@ __global__ void __launch_bounds__(128) k_tran_adaptive(DevTables d, PlanTables p
   const size_t S = w.stride, SS = w.st_stride;
   const int N = p.N;
   int st = o.status[inst];
-  int weak = (st >> 8) & 1;
-  st &= 0xff;
   double* x = w.x + inst;
   double* x1 = a.x1 + inst;
   double* xs = a.xs + inst;
@@ -299,7 +301,7 @@ __global__ void __launch_bounds__(128) k_tran_adaptive(DevTables d, PlanTables p
     for (int k = 0; k < d.n_state; k++) a.st_save[(size_t)k * SS + inst] = w.st_op[(size_t)k * SS + inst];
     SolveCtl c = ctl;
     c.dt = h;
-    int rc = newton_solve<double, B4>(d, p, w, c, inst, 0.0, ctl.reltol, ctl.iabstol, true, &ns, &nl, &weak);
+    int rc = newton_solve<double, B4>(d, p, w, c, inst, 0.0, ctl.reltol, ctl.iabstol, true, &ns, &nl);  // a weak frozen pivot counts as a failed attempt
     double ratio = 0.0;
     if (rc == ST_OK_ && nacc >= 1) {
       const double coef = h / (2.0 * h + h1);
@@ -320,7 +322,7 @@ __global__ void __launch_bounds__(128) k_tran_adaptive(DevTables d, PlanTables p
       }
       nrej++;
       h = rc != ST_OK_ ? h * 0.125 : h * fmax(0.1, 0.9 / sqrt(ratio));
-      if (h < a.hmin) st = rc == ST_SINGULAR_ ? ST_SINGULAR_ : ST_CONV_;
+      if (h < a.hmin) st = rc == ST_SINGULAR_ ? ST_SINGULAR_ : rc == ST_REPIVOT_ ? ST_REPIVOT_ : ST_CONV_;
       continue;
     }
     // accept: emit the print points passed, shift the history
@@ -341,7 +343,7 @@ __global__ void __launch_bounds__(128) k_tran_adaptive(DevTables d, PlanTables p
   }
   for (; kp < a.T; kp++)  // a failed instance: NaN for the points it never reached (as the fixed-step kernels do)
     for (int s = 0; s < n_save; s++) wave[((size_t)kp * n_save + s) * S + inst] = __longlong_as_double(0x7ff8000000000000LL);
-  o.status[inst] = st | (weak << 8);
+  o.status[inst] = st;
   o.iters[inst] += ns;
   o.loads[inst] += nl;
   a.accepted[inst] = nacc;
@@ -353,9 +355,8 @@ __global__ void __launch_bounds__(128) k_ac(DevTables d, PlanTables p, WorkTable
   if (inst >= (size_t)ctl.B) return;
   int ns = 0, nl = 0;
   // hard-coded complex tolerances (analysis.rs:271-272); no commit is observable in AC (load_ac reads only `op`)
-  int weak = 0;
-  const int st = newton_solve<cplx, false>(d, p, w, ctl, inst, ctl.omega[inst], 1e-3, 1e-9, false, &ns, &nl, &weak);
-  o.status[inst] = st | (weak << 8);
+  const int st = newton_solve<cplx, false>(d, p, w, ctl, inst, ctl.omega[inst], 1e-3, 1e-9, false, &ns, &nl);
+  o.status[inst] = st;
   o.iters[inst] += ns;
   o.loads[inst] += nl;
 }

@@ -303,10 +303,11 @@ def _outlier_circuit():
 
 def test_outlier_instance_zero_pivot_order_is_repaired(s21, oracle, monkeypatch):
     """The frozen pivot order comes from instance 0. Here instance 0 is the outlier (gx = 1 S) and every other instance has
-    gx = 1e-15 S, for which that order divides by a pivot far below the reference's 1e-3 threshold. The kernels flag it
-    (bit 8 of the status word), the host re-solves the flagged instances with a symbolic phase of their own, and the
-    results agree with the CPU restatement (which re-pivots every iteration) for every instance. With the repair switched
-    off the flag is still counted and the error of the frozen order is visible."""
+    gx = 1e-15 S, for which that order divides by a pivot far below the reference's 1e-3 threshold. The kernels stop those
+    instances before the update (internal status 9), the host continues them with a symbolic phase of their own at the
+    iterate where they stopped, and results AND iteration counts agree with the CPU restatement (which re-pivots every
+    iteration) for every instance. With the repair switched off the instances report Pivot Search Fail instead of
+    carrying on with a pivot the reference would have refused."""
     B = 40
     gx = np.full(B, 1e-15)
     gx[0] = 1.0
@@ -323,24 +324,45 @@ def test_outlier_instance_zero_pivot_order_is_repaired(s21, oracle, monkeypatch)
     assert np.all(st == 0)
     assert rel_err(x, o["x"], floor=1e-9) <= 1e-9
     assert np.array_equal(it, o["iters"])
-    assert ss["weak_pivot_instances"] >= B - 2 and ss["repaired_instances"] >= B - 2
+    assert ss["weak_pivot_instances"] == B - 2 and ss["repaired_instances"] == B - 2
     # the view path (what bench.py's end-to-end loop uses) repairs too
     b.reset()
     xv, stv, itv = b.dcop_view()
-    assert np.array_equal(xv, x) and np.all(stv == 0)
+    assert np.array_equal(xv, x) and np.all(stv == 0) and np.array_equal(itv, it)
     monkeypatch.setenv("S21_PIVOT_REPAIR", "0")
     b2 = s21.Batch(c, B)
     b2.override("R:rg:g", gx)
     x2, st2, it2 = b2.dcop()
     s2 = b2.setup_stats()
-    assert s2["weak_pivot_instances"] >= B - 2 and s2["repaired_instances"] == 0 and np.all(st2 < 0x100)
-    # an ordinary Monte-Carlo batch raises no flag
+    want = np.full(B, s21.S21_PIVOT_SEARCH_FAIL)
+    want[[0, 17]] = 0
+    assert np.array_equal(st2, want) and s2["repaired_instances"] == 0
+    # an ordinary Monte-Carlo batch stops nobody
     monkeypatch.delenv("S21_PIVOT_REPAIR")
     b3 = s21.Batch(cc.diffpair().to_s21().elaborate(), 256)
     for k, v in cc.diffpair_mc(256).items():
         b3.override(k, v)
     b3.dcop()
     assert b3.setup_stats()["weak_pivot_instances"] == 0
+
+
+def test_long_ring_needs_repivoting_matches_oracle(s21, oracle):
+    """A 21-stage Mos1 ring released from one IC: its operating point is a switching wave that travels down the chain, so the
+    matrix changes character from one Newton iteration to the next (devices leave cut-off one stage at a time) and the pivot
+    order frozen at x = 0 meets pivots orders of magnitude below their columns — with it alone the solve ends in NaNs. The
+    kernels stop at the first such factorisation, the host re-pivots at that iterate and continues: 53 iterations for OP +
+    first time point, as in the reference, and the transient that follows agrees with the oracle."""
+    ck, ic = cc.inverter_array(1, 21)
+    o = oracle.Circuit(ck.to_text()).tran(1e-11, 2e-10, ic=ic)
+    c = ck.to_s21().elaborate(ic=ic)
+    b = s21.Batch(c, 3)
+    x, st, it = b.dcop()
+    assert np.all(st == 0) and np.all(np.isfinite(x))
+    assert np.max(np.abs(x[0] - o.data[0])) <= 1e-9 and b.setup_stats()["repaired_instances"] >= 1
+    t, w, stt, itt = s21.Batch(ck.to_s21().elaborate(ic=ic), 2).tran(1e-11, 2e-10)
+    assert np.all(stt == 0) and np.array_equal(t, o.axis)
+    assert np.max(np.abs(w[0] - o.data)) <= 1e-8 and np.array_equal(w[0], w[1])
+    assert int(itt[0]) == o.solves
 
 
 def test_convergence_aids_source_and_gmin_stepping(s21, oracle):
@@ -358,14 +380,16 @@ def test_convergence_aids_source_and_gmin_stepping(s21, oracle):
     b = s21.Batch(c, B)
     b.override("V:vsup:dc", vs)
     x0, st0, it0 = b.dcop()
-    assert np.all(st0 == s21.S21_CONVERGENCE_FAILED) and np.all(it0 == 100)
+    failed = st0 == s21.S21_CONVERGENCE_FAILED     # the higher supplies need more than 100 iterations (at 1.0 V the oracle fails too)
+    assert failed.sum() >= 2 and failed[B // 2] and np.all(it0[failed] == 100) and np.all(st0[~failed] == 0)
     for flags in ({"source_stepping": True}, {"gmin_stepping": True, "source_stepping": True}):
         b = s21.Batch(c, B)
         b.override("V:vsup:dc", vs)
         b.set_aids(**flags)
         x, st, it = b.dcop()
         assert np.all(st == 0), st
-        assert b.setup_stats()["aided_instances"] == B
+        assert b.setup_stats()["aided_instances"] == failed.sum()
+        assert np.array_equal(x[~failed], x0[~failed]) and np.array_equal(it[~failed], it0[~failed])   # the others keep their result
         n = {name: k for k, name in enumerate(c.names)}
         lv = x[:, [n[f"r0s{k}"] for k in range(61)]]
         assert np.all(np.abs(lv[:, 0]) < 1e-6)                              # the IC holds stage 0 low
@@ -420,14 +444,14 @@ def test_tran_adaptive_rc_step(s21):
     assert b.kernel_name() == "direct-adaptive" and np.all(st == 0) and len(t) in (500, 501)
     exact = 1.0 - np.exp(-t / 1e-6)
     err = np.max(np.abs(w[0, :, 0] - exact))
-    assert err < 2e-2, err
+    assert err < 3e-2, err   # trtol 7 x reltol 1e-3 per step, accumulated over the rise
     assert 10 < acc[0] < 200 and np.all(acc == acc[0]) and np.all(w[1] == w[0])      # identical instances take identical steps
     t2, w2, st2, it2, acc2, rej2 = s21.Batch(c, 1).tran_adaptive(tstep, tstop, save=[c.names.index("b")], hmax=50 * tstep, trtol=0.1)
     err2 = np.max(np.abs(w2[0, :, 0] - exact))
     assert st2[0] == 0 and err2 < 0.3 * err and acc2[0] > acc[0]
     # fixed-step BE at the print step for scale: the adaptive run with default trtol is in the same error class with fewer solves
     tf, wf, stf, itf = s21.Batch(c, 1).tran(tstep, tstop, save=[c.names.index("b")])
-    assert np.max(np.abs(wf[0, :, 0] - exact)) < 2e-2 and it[0] < itf[0]
+    assert np.max(np.abs(wf[0, :, 0] - exact)) < 3e-2 and it[0] < itf[0]
 
 
 def test_tran_adaptive_ring_oscillator_sweep(s21):
