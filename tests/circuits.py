@@ -383,7 +383,7 @@ def ptm65_cards():
     return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ptm65_cards.json")))
 
 
-def bsim4_ring(n_stages=21, cards="default", vdd=1.0, cload=1e-15, l=5e-6, wn=5e-6, wp=5e-6, **card_overrides):
+def bsim4_ring(n_stages=21, cards="default", vdd=1.0, cload=1e-15, l=5e-6, wn=5e-6, wp=5e-6, ic_every=0, **card_overrides):
     """Config C4: n-stage CMOS ring oscillator on BSIM4 devices. Returns (ckt, ic).
 
     SURVEY C4 asks for 101 stages on the PTM 65 nm cards (L = 65 nm, Wn = 200 nm, Wp = 400 nm). Under the reference's
@@ -392,7 +392,11 @@ def bsim4_ring(n_stages=21, cards="default", vdd=1.0, cload=1e-15, l=5e-6, wn=5e
     most supply voltages of the sweep even for 7 stages (the oracle reproduces this; DESIGN.md "C4"). The default
     therefore is SURVEY's stated fallback: `Bsim4ModelSpecs::new` cards on the reference's own BSIM4 test devices
     (L = W = 5 um, tests.rs:948-964), 21 stages, which converges over the whole 0.8-1.2 V sweep.
-    `cards`: "default" or "ptm65" (tests/golden/ptm65_cards.json)."""
+    `cards`: "default" or "ptm65" (tests/golden/ptm65_cards.json).
+    `ic_every` > 0 (even): further initial conditions at stages ic_every, 2 ic_every, ... — all at 0 V, which is the level an
+    even stage has behind the stage-0 IC — so that every segment's logic levels settle within the reference's 100 iterations:
+    101 stages with ic_every = 26 is SURVEY's ring length under the reference's own Newton loop.
+    Card overrides such as rbodymod=1, rgatemod=1 give each device its 4 internal nodes (bsim4ports.rs:60-88): N = 913 at 101 stages."""
     c = Ckt(signals=[f"s{k}" for k in range(n_stages)] + ["vdd"], name="bsim4_ring")
     if cards == "ptm65":
         pc = ptm65_cards()
@@ -408,7 +412,12 @@ def bsim4_ring(n_stages=21, cards="default", vdd=1.0, cload=1e-15, l=5e-6, wn=5e
     c.V("vsup", "vdd", GND, vdd)
     for k in range(n_stages):
         c.X(f"x{k}", "inv", inp=f"s{k}", out=f"s{(k + 1) % n_stages}", vdd="vdd", vss=GND)
-    return c, {"s0": 0.0}
+    ic = {"s0": 0.0}
+    if ic_every:
+        assert ic_every % 2 == 0
+        for k in range(ic_every, n_stages - 8, ic_every):
+            ic[f"s{k}"] = 0.0
+    return c, ic
 
 
 def c4_sweep(B=2048, first_instance=0, n_vdd=64, n_temp=32):

@@ -392,7 +392,7 @@ def test_convergence_aids_source_and_gmin_stepping(s21, oracle):
         assert np.array_equal(x[~failed], x0[~failed]) and np.array_equal(it[~failed], it0[~failed])   # the others keep their result
         n = {name: k for k, name in enumerate(c.names)}
         lv = x[:, [n[f"r0s{k}"] for k in range(61)]]
-        assert np.all(np.abs(lv[:, 0]) < 1e-6)                              # the IC holds stage 0 low
+        assert np.all(np.abs(lv[:, 0]) < 1e-2)                              # the IC (a 1 S resistor to 0 V) holds stage 0 low
         assert np.all(lv[:, 1:20:2] > 0.9 * vs[:, None]) and np.all(lv[:, 2:20:2] < 0.1)   # alternating logic levels behind it
         x2, st2, it2 = b.dcop()                                              # warm restart from the rescued point
         assert np.all(st2 == 0) and np.all(it2 - it <= 1) and np.max(np.abs(x2 - x)) < 1e-9
