@@ -127,7 +127,7 @@ struct PlanDevice {
   // cooperative kernel: every shared index table packed into one allocation ("arena") so that a CTA can bring all of
   // them into shared memory with a single TMA bulk copy. Offsets are in ints, each table 16-byte aligned.
   DBuf<int> arena;
-  size_t arena_bytes = 0;
+  size_t arena_bytes = 0, arena_core_bytes = 0;  // core = all tables but the parameter codes (packed last)
   struct ArenaOffsets {
     size_t type, itab_off, par_off, state_off, itab, pcode, par_direct, row_i2e, col_i2e, col_e2i, rowptr, colidx, diag_slot, stage_off, eval_order,
         asm_off, asm_src, lu_lvl_off, lu_t, lu_u, lu_l, fw_lvl_off, fw_k, fw_row, fw_slot, bw_lvl_off, bw_row;
@@ -288,9 +288,9 @@ class Batch {
     sync_params(false);
     launches_ = 0;
     ensure_plan(op_plan_, AN_OP, 0.0);
-    S21_CUDA(cudaEventRecord(ev0_, stream_));
+    S21_CUDA(cudaEventRecord(ev0_, stream_)); ev_pair_ = false;
     run_op();
-    S21_CUDA(cudaEventRecord(ev1_, stream_));
+    S21_CUDA(cudaEventRecord(ev1_, stream_)); ev_pair_ = true;
     last_plan_ = &op_plan_;
   }
   // Results of the last solve in the library's own pinned buffer: x rows [instance][variable] + status / iteration counts.
@@ -361,8 +361,9 @@ class Batch {
     if (status) *status = hs;
     if (iters) *iters = hi;
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, ev0_, ev1_) == cudaSuccess) last_ms_ = ms;
-    else (void)cudaGetLastError();  // an event of the pair not recorded yet (a read between two launches): nothing to carry on
+    // only a closed pair is queried (a read between two launches — the OP rescue inside tran / ac — has none to report)
+    if (ev_pair_ && cudaEventElapsedTime(&ms, ev0_, ev1_) == cudaSuccess) last_ms_ = ms;
+    else if (ev_pair_) (void)cudaGetLastError();
   }
   // ---- convergence aids (second half; opt-in — the reference has neither: `src_factor` and `diag_gmin` are
   // dead fields, analysis.rs:659-660, so with the aids off a failing instance reports Convergence Failed exactly as the
@@ -596,7 +597,7 @@ class Batch {
     sync_params(false);
     launches_ = 0;
     ensure_plan(op_plan_, AN_OP, 0.0);
-    S21_CUDA(cudaEventRecord(ev0_, stream_));
+    S21_CUDA(cudaEventRecord(ev0_, stream_)); ev_pair_ = false;
     run_op();
     rescue_op();
     // The matrix changes character after the OP (capacitor companions appear, IC resistors are released):
@@ -606,7 +607,7 @@ class Batch {
     ensure_plan(tran_plan_, AN_TRAN, tstep);
     std::vector<int> sv(save_vars, save_vars + n_save);
     d_save_.upload(sv, stream_);
-    S21_CUDA(cudaEventRecord(ev0_, stream_));  // time the transient kernel itself: the symbolic phase above is host work
+    S21_CUDA(cudaEventRecord(ev0_, stream_)); ev_pair_ = false;  // time the transient kernel itself: the symbolic phase above is host work
     d_wave_.alloc((size_t)T * n_save * Bs_);
     wave_T_ = (size_t)T; wave_ns_ = n_save;
     DevTables dt = dev_tables(tran_plan_.itab.p);
@@ -623,7 +624,7 @@ class Batch {
                               (int)n_save, d_wave_.p, stream_);
     } else if (use_coop_ && use_grid()) {
       CoopCfg cfg = coop_cfg(tran_plan_, B_, 1);
-      cfg.smem_bytes = 0;
+      cfg.smem_bytes = 0; cfg.mixed = false;
       d_gctl_.alloc(1);
       last_kernel_ = "grid";
       rc = launch_grid_tran(coop_dev(tran_plan_), tran_plan_.coop_plan(), tran_plan_.coop(), work(), stage_for(cfg, tran_plan_.host), out(), ctl,
@@ -639,7 +640,7 @@ class Batch {
     }
     launches_++;
     if (rc) throw S21Error(ST_CUDA, std::string("tran kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
-    S21_CUDA(cudaEventRecord(ev1_, stream_));
+    S21_CUDA(cudaEventRecord(ev1_, stream_)); ev_pair_ = true;
     last_plan_ = &tran_plan_;
     if (wave) {
       hwave_.alloc((size_t)T * n_save * Bs_);
@@ -686,13 +687,13 @@ class Batch {
     ad_x1_.alloc((size_t)N * Bs_); ad_xs_.alloc((size_t)N * Bs_); ad_st_.alloc((size_t)std::max(flat_.n_state, 1) * Bs_);
     ad_acc_.alloc(Bs_); ad_rej_.alloc(Bs_);
     g.x1 = ad_x1_.p; g.xs = ad_xs_.p; g.st_save = ad_st_.p; g.accepted = ad_acc_.p; g.rejected = ad_rej_.p;
-    S21_CUDA(cudaEventRecord(ev0_, stream_));
+    S21_CUDA(cudaEventRecord(ev0_, stream_)); ev_pair_ = false;
     last_kernel_ = "direct-adaptive";
     int rc = launch_tran_adaptive(dev_tables(tran_plan_.itab.p), tran_plan_.tables(), work(), out(), make_ctl(AN_TRAN, g.h0), g, d_save_.p, (int)n_save,
                                   d_wave_.p, stream_);
     launches_++;
     if (rc) throw S21Error(ST_CUDA, std::string("adaptive tran kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
-    S21_CUDA(cudaEventRecord(ev1_, stream_));
+    S21_CUDA(cudaEventRecord(ev1_, stream_)); ev_pair_ = true;
     last_plan_ = &tran_plan_;
     if (wave) {
       hwave_.alloc((size_t)T * n_save * Bs_);
@@ -723,7 +724,7 @@ class Batch {
     sync_params(false);
     launches_ = 0;
     ensure_plan(op_plan_, AN_OP, 0.0);
-    S21_CUDA(cudaEventRecord(ev0_, stream_));
+    S21_CUDA(cudaEventRecord(ev0_, stream_)); ev_pair_ = false;
     run_op();
     rescue_op();
     {  // the reference stops at the OP error (analysis.rs:775)
@@ -784,7 +785,7 @@ class Batch {
     } else if (use_coop_ && !ac_direct) {
       CoopCfg cfg = coop_cfg(ac_plan_, F, 2);
       cplx* stage = nullptr;
-      if (cfg.smem_bytes == 0) { zstage_.alloc((size_t)ac_plan_.host.n_stage * Fs); stage = zstage_.p; }
+      if (cfg.smem_bytes == 0 || cfg.mixed) { zstage_.alloc((size_t)ac_plan_.host.n_stage * Fs); stage = zstage_.p; }
       last_kernel_ = "coop";
       rc = launch_coop_ac(coop_dev(ac_plan_), ac_plan_.coop_plan(), ac_plan_.coop(), w, stage, o, ctl, cfg, stream_);
     } else {
@@ -793,7 +794,7 @@ class Batch {
     }
     launches_++;
     if (rc) throw S21Error(ST_CUDA, std::string("ac kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
-    S21_CUDA(cudaEventRecord(ev1_, stream_));
+    S21_CUDA(cudaEventRecord(ev1_, stream_)); ev_pair_ = true;
     last_plan_ = &ac_plan_;
     std::vector<cplx> hx((size_t)N * Fs);
     std::vector<int32_t> hs(Fs), hi(Fs), hl(Fs);
@@ -814,8 +815,9 @@ class Batch {
         }
     }
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, ev0_, ev1_) == cudaSuccess) last_ms_ = ms;
-    else (void)cudaGetLastError();  // an event of the pair not recorded yet (a read between two launches): nothing to carry on
+    // only a closed pair is queried (a read between two launches — the OP rescue inside tran / ac — has none to report)
+    if (ev_pair_ && cudaEventElapsedTime(&ms, ev0_, ev1_) == cudaSuccess) last_ms_ = ms;
+    else if (ev_pair_) (void)cudaGetLastError();
     // Frequency points the order taken from the first point does not suit (a kernel stopped them with ST_REPIVOT_CODE:
     // jwC entries grow over the sweep) are solved again as a sweep of their own, whose order comes from ITS first point.
     std::vector<size_t> again;
@@ -866,6 +868,7 @@ class Batch {
   size_t B_, Bs_ = 0;
   cudaStream_t own_stream_ = nullptr, stream_ = nullptr;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+  bool ev_pair_ = false;  // ev0_ and ev1_ bracket a finished launch sequence
   DBuf<int> d_type_, d_ioff_, d_poff_, d_soff_, d_itab_raw_, d_pcode_, d_pdirect_, d_save_;
   DBuf<double> d_pval_, x_, rhs_, c_, lu_, st_op_, st_guess_, d_wave_, d_omega_, d_rows_;
   DBuf<GridCtl> d_gctl_;
@@ -1033,7 +1036,28 @@ class Batch {
     cfg.smem_bytes = work_fits ? coop_work_bytes(P.N, P.nnzLU, P.n_stage, flat_.n_state, gi, width) : 0;
     // the arena rides along in shared memory when it is small next to what the CTA already uses (occupancy first)
     cfg.arena_in_smem = pd.arena_bytes <= 48 * 1024 && (work_fits ? total(gi, true) : coop_ctrl_bytes(gi) + pd.arena_bytes) <= max_smem_;
-    if (const char* e = std::getenv("S21_COOP_ARENA")) cfg.arena_in_smem = cfg.arena_in_smem && std::atoi(e) != 0;
+    size_t arena_copy = cfg.arena_in_smem ? pd.arena_bytes : 0;
+    // A Bsim4 device has ~380 parameter codes: 42 devices make the code table 64 KB while every other table together is half
+    // of that, and a device whose block is read directly (par_direct) never looks its codes up. When the whole arena is too
+    // large to ride along, its core (device tables, gather lists, level schedules) still does — the Bsim4 build runs one
+    // CTA per SM, so up to 96 KB cost no occupancy; the level loops then read their indices from shared memory.
+    if (!cfg.arena_in_smem && n_b4 > 0 && !work_fits && pd.arena_core_bytes <= 96 * 1024 && coop_ctrl_bytes(gi) + pd.arena_core_bytes <= max_smem_) {
+      cfg.arena_in_smem = true;
+      cfg.arena_core_bytes = pd.arena_core_bytes;
+      arena_copy = pd.arena_core_bytes;
+    }
+    if (const char* e = std::getenv("S21_COOP_ARENA")) { if (std::atoi(e) == 0) { cfg.arena_in_smem = false; cfg.arena_core_bytes = 0; arena_copy = 0; } }
+    // Mixed workspace: when the whole footprint stays in HBM/L2 (Bsim4: one staging slot per stamp), x / rhs / residual and
+    // the L+U values still go to shared memory if they fit — the per-level barriers of the factorisation and of the
+    // substitutions then wait on shared-memory latencies instead of L2 round trips (S21_COOP_MIXED=0: all in HBM/L2).
+    if (!work_fits) {
+      const char* mx = std::getenv("S21_COOP_MIXED");
+      const size_t mb = coop_mixed_bytes(P.N, P.nnzLU, gi, width);
+      if ((!mx || std::atoi(mx) != 0) && coop_ctrl_bytes(gi) + arena_copy + mb <= max_smem_) {
+        cfg.smem_bytes = mb;
+        cfg.mixed = true;
+      }
+    }
     const size_t widest = (size_t)std::max(P.nnzLU + P.N, (int)flat_.devs.size()) * (size_t)gi;
     cfg.threads = widest <= 64 ? 64 : widest <= 1024 ? 128 : 256;
     if (const char* e = std::getenv("S21_COOP_THREADS")) cfg.threads = std::max(32, std::min(256, std::atoi(e) / 32 * 32));
@@ -1059,7 +1083,7 @@ class Batch {
     return true;
   }
   double* stage_for(const CoopCfg& cfg, const Plan& P) {
-    if (cfg.smem_bytes) return nullptr;
+    if (cfg.smem_bytes && !cfg.mixed) return nullptr;
     d_stage_.alloc((size_t)P.n_stage * Bs_);
     return d_stage_.p;
   }
@@ -1097,6 +1121,10 @@ class Batch {
     c.max_iter = max_iter_;
     c.stop_on_weak = (mode == AN_OP || mode == AN_AC) && pivot_stop_enabled() ? 1 : 0;
     c.relaxed = (mode == AN_OP ? op_plan_ : mode == AN_TRAN ? tran_plan_ : ac_plan_).host.relaxed ? 1 : 0;
+    if (c.relaxed) {
+      c.weak_mult = 1e9;
+      if (const char* e = std::getenv("S21_GRID_WEAK_MULT")) { const double v = std::atof(e); if (v >= 1.0) c.weak_mult = v; }
+    }
     return c;
   }
   void run_op() {
@@ -1130,7 +1158,7 @@ class Batch {
     } else if (use_coop_ && use_grid()) {
       materialize_reset();
       CoopCfg cfg = coop_cfg(op_plan_, B_, 1);
-      cfg.smem_bytes = 0;
+      cfg.smem_bytes = 0; cfg.mixed = false;
       d_gctl_.alloc(1);
       last_kernel_ = "grid";
       rc = launch_grid_dcop(coop_dev(op_plan_), op_plan_.coop_plan(), op_plan_.coop(), work(), stage_for(cfg, op_plan_.host), out(),
@@ -1224,13 +1252,15 @@ class Batch {
       const std::vector<int>& poff = poff_eff_;
       for (const FlatDev& d : flat_.devs) { type.push_back(d.type); ioff.push_back(d.itab_off); soff.push_back(d.state_off); }
       auto& o = pd.ao;
-      o.type = put(type); o.itab_off = put(ioff); o.par_off = put(poff); o.state_off = put(soff); o.itab = put(itab); o.pcode = put(pcode_h_); o.par_direct = put(pdirect_h_);
+      o.type = put(type); o.itab_off = put(ioff); o.par_off = put(poff); o.state_off = put(soff); o.itab = put(itab); o.par_direct = put(pdirect_h_);
       o.row_i2e = put(P.row_i2e); o.col_i2e = put(P.col_i2e); o.col_e2i = put(P.col_e2i); o.rowptr = put(P.rowptr); o.colidx = put(P.colidx);
       o.diag_slot = put(P.diag_slot); o.stage_off = put(si_.stage_off); o.eval_order = put(si_.eval_order);
       o.asm_off = put(P.asm_off); o.asm_src = put(P.asm_src);
       o.lu_lvl_off = put(P.lu_lvl_off); o.lu_t = put(P.lu_t); o.lu_u = put(P.lu_u); o.lu_l = put(P.lu_l);
       o.fw_lvl_off = put(P.fw_lvl_off); o.fw_k = put(P.fw_k); o.fw_row = put(P.fw_row); o.fw_slot = put(P.fw_slot);
       o.bw_lvl_off = put(P.bw_lvl_off); o.bw_row = put(P.bw_row);
+      pd.arena_core_bytes = A.size() * sizeof(int);
+      o.pcode = put(pcode_h_);
       pd.arena_bytes = A.size() * sizeof(int);
       pd.arena.upload(A, stream_);
     }

@@ -202,6 +202,10 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
     o << "#define PH(n)\n";
   o << "namespace s21 {\n";
   o << "#define PS " << PSV << "\n#define FULLM 0xffffffffu\n#define BC(v, jj) __shfl_sync(FULLM, (v), base + " << IPW << " * (jj))\n";
+  // idle lanes (j >= lanes per instance) read one row further: the row must be part of the emitted array (it used to be
+  // appended after GT_G had been written out, so the copy into shared memory read TM_LPI ints past its end — found by
+  // compute-sanitizer memcheck, tests/test_gpu.py::test_compute_sanitizer_clean)
+  for (int jj = 0; jj < TM_LPI; jj++) G.table.push_back(zero_off);
   o << "__device__ const int GT_G[" << std::max<size_t>(G.table.size(), 1) << "] = {";
   for (size_t k = 0; k < G.table.size(); k++) o << (k ? "," : "") << G.table[k];
   if (G.table.empty()) o << "0";
@@ -291,7 +295,6 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
       o << "  __device__ __forceinline__ void add_g_dup(int, int dup, double v) { S[(" << st << " + dup) * PS] = v; }\n};\n";
     }
   }
-  for (int jj = 0; jj < TM_LPI; jj++) G.table.push_back(zero_off);  // idle lanes (j >= lanes per instance) read one row further
   const size_t n_gt = G.table.size();
   const size_t ctrl_ints = (size_t)GI + n_gt;
   const size_t ctrl_bytes = (ctrl_ints * 4 + 15) / 16 * 16;

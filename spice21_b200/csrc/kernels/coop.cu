@@ -28,10 +28,14 @@ using namespace coopk;
 
 namespace {
 
-template <class T, int KIND, bool SMEM, bool B4>
+// WS: where the per-instance workspace lives. 0 = all of it in HBM/L2; 1 = all of it in shared memory; 2 = mixed — x, rhs,
+// residual and the L+U values in shared memory (the linear algebra's barriers then wait on on-chip latencies), the stamp
+// staging area and the device state in HBM/L2 (Bsim4 circuits: one staging slot per stamp is 20 KB per instance).
+template <class T, int KIND, int WS, bool B4>
 __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d, PlanTables p, CoopTables ct, WorkTables<T> g, T* gstage, NewtonOut o,
                                                 SolveCtl ctl, CoopArgs a) {
-  typedef typename std::conditional<SMEM, unsigned, size_t>::type I;
+  typedef typename std::conditional<WS != 0, unsigned, size_t>::type I;    // x, rhs, c, lu
+  typedef typename std::conditional<WS == 1, unsigned, size_t>::type IS;   // stamp staging, device state
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int gi = a.gi;
@@ -68,7 +72,7 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
     // Rebase every table pointer onto the shared-memory copy. The new pointer must be DERIVED FROM `sa`: nvcc assumes
     // pointers that come from kernel arguments address global memory and would emit ld.global for them.
 #define RB(ptr) ptr = sa + ((ptr) - a.arena)
-    RB(d.type); RB(d.itab_off); RB(d.par_off); RB(d.state_off); RB(d.itab); RB(d.pcode); if (d.par_direct) RB(d.par_direct);
+    RB(d.type); RB(d.itab_off); RB(d.par_off); RB(d.state_off); RB(d.itab); if (!a.pcode_global) RB(d.pcode); if (d.par_direct) RB(d.par_direct);
     RB(p.row_i2e); RB(p.col_i2e); RB(p.col_e2i); RB(p.rowptr); RB(p.colidx); RB(p.diag_slot);
     RB(ct.stage_off); RB(ct.eval_order); RB(ct.asm_off); RB(ct.asm_src);
     RB(ct.lu_lvl_off); RB(ct.lu_t); RB(ct.lu_u); RB(ct.lu_l);
@@ -78,20 +82,27 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
   // ---- workspace views: entry k of this thread's instance is a[k * ws + col]
   T *x, *rhs, *c, *lu, *S;
   double *sop, *sguess;
-  I ws, col, ss, scol;
-  if constexpr (SMEM) {
+  I ws, col;
+  IS wS, colS, ss, scol;
+  if constexpr (WS != 0) {
     x = (T*)(smem_raw + off); off += sizeof(T) * (size_t)N * gi;
     rhs = (T*)(smem_raw + off); off += sizeof(T) * (size_t)N * gi;
     c = (T*)(smem_raw + off); off += sizeof(T) * (size_t)N * gi;
     lu = (T*)(smem_raw + off); off += sizeof(T) * (size_t)nnz * gi;
+    ws = (I)gi; col = (I)li;
+  } else {
+    x = g.x; rhs = g.rhs; c = g.c; lu = g.lu;
+    ws = (I)g.stride; col = (I)i0 + (I)li;
+  }
+  if constexpr (WS == 1) {
     S = (T*)(smem_raw + off); off += sizeof(T) * (size_t)ct.n_stage * gi;
     sop = (double*)(smem_raw + off); off += sizeof(double) * (size_t)d.n_state * gi;
     sguess = (double*)(smem_raw + off);
-    ws = (I)gi; col = (I)li; ss = (I)gi; scol = (I)li;
+    wS = (IS)gi; colS = (IS)li; ss = (IS)gi; scol = (IS)li;
   } else {
-    x = g.x; rhs = g.rhs; c = g.c; lu = g.lu; S = gstage;
+    S = gstage;
     sop = g.st_op; sguess = g.st_guess;
-    ws = (I)g.stride; col = (I)i0 + (I)li; ss = (I)g.st_stride; scol = ((I)i0 + (I)li) * (I)ctl.par_inst_stride;
+    wS = (IS)g.stride; colS = (IS)i0 + (IS)li; ss = (IS)g.st_stride; scol = ((IS)i0 + (IS)li) * (IS)ctl.par_inst_stride;
   }
   const bool valid = li < ni;
 
@@ -101,12 +112,14 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
     weak[tid] = 0;
     nsol[tid] = 0; nld[tid] = 0; convnow[tid] = 0; dxok[tid] = 1; act[tid] = 0;
   }
-  if constexpr (SMEM) {
+  if constexpr (WS != 0) {
     for (int k = item0; k < N; k += istep) x[(I)k * ws + col] = valid ? g.x[(size_t)k * g.stride + i0 + li] : Scalar<T>::zero();
+  }
+  if constexpr (WS == 1) {
     for (int k = item0; k < d.n_state; k += istep) {
       const size_t src = (size_t)k * g.st_stride + ((size_t)i0 + (size_t)(valid ? li : 0)) * ctl.par_inst_stride;
-      sop[(I)k * ss + scol] = g.st_op[src];
-      sguess[(I)k * ss + scol] = g.st_guess[src];
+      sop[(IS)k * ss + scol] = g.st_op[src];
+      sguess[(IS)k * ss + scol] = g.st_guess[src];
     }
   }
   if (a.arena_bytes > 0) mbar_wait(mbar, 0);
@@ -131,15 +144,15 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
       if (on) {
         for (int item = item0; item < d.n_dev; item += istep) {
           const int dev = ct.eval_order[item];
-          EnvS<T, I> e;
+          EnvS<T, I, IS> e;
           e.it = d.itab + d.itab_off[dev];
           e.pc = d.pcode + d.par_off[dev];
           e.pval = d.pval;
           e.pinst = pinst;
-          const I so = (I)d.state_off[dev] * ss + scol;
+          const IS so = (IS)d.state_off[dev] * ss + scol;
           e.sop = sop + so; e.sguess = sguess + so; e.sstride = ss;
           e.x = x + col; e.xstride = ws;
-          e.S = S + (I)ct.stage_off[dev] * ws + col;
+          e.S = S + (IS)ct.stage_off[dev] * wS + colS; e.Sstride = wS;
           e.mode = ctl.mode; e.dt = ctl.dt; e.gmin = ctl.gmin; e.omega = omega;
           load_one<T, B4>(d.type[dev], e, (d.par_direct && d.par_direct[dev]) ? d.pval + d.par_off[dev] : nullptr);
         }
@@ -150,7 +163,16 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
       if (on) {
         for (int t = item0; t < nnz + N; t += istep) {
           T acc = Scalar<T>::zero();
-          for (int q = ct.asm_off[t]; q < ct.asm_off[t + 1]; q++) acc = s_add(acc, S[(I)ct.asm_src[q] * ws + col]);
+          int q = ct.asm_off[t];
+          const int qe = ct.asm_off[t + 1];
+          // four loads in flight, the additions in list order (when the staging area is in HBM/L2 the chain of dependent
+          // load -> add pairs was the whole cost of this phase)
+          for (; q + 4 <= qe; q += 4) {
+            const T v0 = S[(IS)ct.asm_src[q] * wS + colS], v1 = S[(IS)ct.asm_src[q + 1] * wS + colS];
+            const T v2 = S[(IS)ct.asm_src[q + 2] * wS + colS], v3 = S[(IS)ct.asm_src[q + 3] * wS + colS];
+            acc = s_add(s_add(s_add(s_add(acc, v0), v1), v2), v3);
+          }
+          for (; q < qe; q++) acc = s_add(acc, S[(IS)ct.asm_src[q] * wS + colS]);
           if (t < nnz) lu[(I)t * ws + col] = acc;
           else rhs[(I)(t - nnz) * ws + col] = acc;
         }
@@ -180,7 +202,7 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
       }
       __syncthreads();
       if (real_kind && convnow[li]) {  // Component::commit on convergence: op <- guess
-        for (int k = item0; k < d.n_state; k += istep) sop[(I)k * ss + scol] = sguess[(I)k * ss + scol];
+        for (int k = item0; k < d.n_state; k += istep) sop[(IS)k * ss + scol] = sguess[(IS)k * ss + scol];
       }
       if (!__syncthreads_or(tid < gi && act[tid])) break;
       const bool go = act[li] != 0;
@@ -275,15 +297,17 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
   }
 
   // ---- epilogue: results back to HBM
-  if constexpr (SMEM) {
+  if constexpr (WS != 0) {
     if (valid) {
       for (int k = item0; k < N; k += istep) g.x[(size_t)k * g.stride + i0 + li] = x[(I)k * ws + col];
-      if (real_kind)
-        for (int k = item0; k < d.n_state; k += istep) {
-          const size_t dst = (size_t)k * g.st_stride + i0 + li;
-          g.st_op[dst] = sop[(I)k * ss + scol];
-          g.st_guess[dst] = sguess[(I)k * ss + scol];
-        }
+      if constexpr (WS == 1) {
+        if (real_kind)
+          for (int k = item0; k < d.n_state; k += istep) {
+            const size_t dst = (size_t)k * g.st_stride + i0 + li;
+            g.st_op[dst] = sop[(IS)k * ss + scol];
+            g.st_guess[dst] = sguess[(IS)k * ss + scol];
+          }
+      }
     }
   }
   if (tid < ni) {
@@ -300,17 +324,24 @@ int launch_b4(const DevTables& d, const PlanTables& p, const CoopTables& ct, con
            const SolveCtl& c, const CoopCfg& cfg, int T_points, const int* save_vars, int n_save, double* wave, void* stream) {
   CoopArgs a;
   a.lg_gi = 0; a.gi = cfg.gi; a.cold = 0; a.T_points = T_points; a.n_save = n_save; a.save_vars = save_vars; a.wave = wave;
-  a.arena = cfg.arena; a.arena_bytes = cfg.arena_in_smem ? (int)cfg.arena_bytes : 0;
+  a.arena = cfg.arena;
+  a.pcode_global = cfg.arena_in_smem && cfg.arena_core_bytes > 0 ? 1 : 0;
+  a.arena_bytes = cfg.arena_in_smem ? (int)(a.pcode_global ? cfg.arena_core_bytes : cfg.arena_bytes) : 0;
   const size_t smem = ctrl_bytes(cfg.gi) + (size_t)a.arena_bytes + cfg.smem_bytes;
   const int grid = (c.B + cfg.gi - 1) / cfg.gi;
   cudaError_t e;
-  if (cfg.smem_bytes > 0) {
-    auto kern = k_coop<T, KIND, true, B4>;
+  if (cfg.smem_bytes > 0 && cfg.mixed) {
+    auto kern = k_coop<T, KIND, 2, B4>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<grid, cfg.threads, smem, (cudaStream_t)stream>>>(d, p, ct, w, stage, o, c, a);
+  } else if (cfg.smem_bytes > 0) {
+    auto kern = k_coop<T, KIND, 1, B4>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<grid, cfg.threads, smem, (cudaStream_t)stream>>>(d, p, ct, w, stage, o, c, a);
   } else {
-    auto kern = k_coop<T, KIND, false, B4>;
+    auto kern = k_coop<T, KIND, 0, B4>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<grid, cfg.threads, smem, (cudaStream_t)stream>>>(d, p, ct, w, stage, o, c, a);
@@ -330,6 +361,7 @@ int launch(const DevTables& d, const PlanTables& p, const CoopTables& ct, const 
 }  // namespace
 
 size_t coop_ctrl_bytes(int gi) { return ctrl_bytes(gi); }
+size_t coop_mixed_bytes(int N, int nnz, int gi, int scalar_width) { return 8 * (size_t)scalar_width * (size_t)gi * (3 * (size_t)N + (size_t)nnz); }
 size_t coop_work_bytes(int N, int nnz, int n_stage, int n_state, int gi, int scalar_width) {
   const size_t ts = 8 * (size_t)scalar_width;
   return ts * (size_t)gi * (3 * (size_t)N + (size_t)nnz + (size_t)n_stage) + 8 * (size_t)gi * 2 * (size_t)n_state;

@@ -38,7 +38,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-template <class T, class I>
+template <class T, class I, class IS = I>
 struct EnvS {  // staged Env (see devices.cuh): stamps go to this device's private staging slots
   const int* it;
   const int* pc;
@@ -46,10 +46,11 @@ struct EnvS {  // staged Env (see devices.cuh): stamps go to this device's priva
   size_t pinst;
   double* sop;      // already offset to (state_off, instance); element k at sop[k * sstride]
   double* sguess;
-  I sstride;
+  IS sstride;
   const T* x;       // already offset to the instance column; variable v at x[v * xstride]
-  T* S;             // already offset to (stage_off, instance); position p at S[p * xstride]
+  T* S;             // already offset to (stage_off, instance); position p at S[p * Sstride]
   I xstride;
+  IS Sstride;       // the staging area may live elsewhere than x (cooperative kernel, mixed workspace: x on chip, staging in HBM)
   int mode;
   double dt, gmin, omega;
   __device__ __forceinline__ int node(int k) const { return it[k]; }
@@ -61,17 +62,17 @@ struct EnvS {  // staged Env (see devices.cuh): stamps go to this device's priva
     if constexpr (std::is_same<T, double>::value) return var < 0 ? 0.0 : x[(I)var * xstride];
     else return 0.0;  // load_ac never reads the guess
   }
-  __device__ __forceinline__ double op(int k) const { return sop[(I)k * sstride]; }
-  __device__ __forceinline__ double guess(int k) const { return sguess[(I)k * sstride]; }
-  __device__ __forceinline__ void set_guess(int k, double v) { sguess[(I)k * sstride] = v; }
-  __device__ __forceinline__ void add_g_at(int pos, T v) { S[(I)pos * xstride] = v; }
-  __device__ __forceinline__ void add_b_at(int pos, T v) { S[(I)pos * xstride] = v; }
-  __device__ __forceinline__ void add_g_dup(int, int dup, T v) { S[(I)dup * xstride] = v; }
+  __device__ __forceinline__ double op(int k) const { return sop[(IS)k * sstride]; }
+  __device__ __forceinline__ double guess(int k) const { return sguess[(IS)k * sstride]; }
+  __device__ __forceinline__ void set_guess(int k, double v) { sguess[(IS)k * sstride] = v; }
+  __device__ __forceinline__ void add_g_at(int pos, T v) { S[(IS)pos * Sstride] = v; }
+  __device__ __forceinline__ void add_b_at(int pos, T v) { S[(IS)pos * Sstride] = v; }
+  __device__ __forceinline__ void add_g_dup(int, int dup, T v) { S[(IS)dup * Sstride] = v; }
 };
 
 // Env of a device whose parameter block is all shared values: par(k) is one load at a literal offset from the block.
-template <class T, class I>
-struct EnvSD : EnvS<T, I> {
+template <class T, class I, class IS = I>
+struct EnvSD : EnvS<T, I, IS> {
   const double* pblk;
   __device__ __forceinline__ double par(int k) const { return __ldg(pblk + k); }
 };
@@ -89,7 +90,7 @@ template <class T, bool B4, class E> __device__ __forceinline__ void load_one(in
       case DT_BSIM4:
         if constexpr (B4) {
           if (pblk) {
-            EnvSD<T, decltype(e.xstride)> ed;
+            EnvSD<T, decltype(e.xstride), decltype(e.Sstride)> ed;
             static_cast<E&>(ed) = e;
             ed.pblk = pblk;
             load_bsim4(ed);
@@ -130,6 +131,7 @@ struct CoopArgs {
   double* wave;
   const int* arena;      // packed index tables in HBM (all table pointers point into it)
   int arena_bytes;       // > 0: copy the arena into shared memory with TMA and rebase the pointers
+  int pcode_global;      // cooperative kernel: the copy stops short of the parameter-code table (last in the arena), which stays in HBM
 };
 
 

@@ -79,6 +79,12 @@ struct SolveCtl {
   int stop_on_weak = 0;
   int max_iter = 100;      // real solves: iteration budget of this launch (analysis.rs:173 caps a solve at 100; a solve continued
                            // after a re-pivot gets what is left)
+  // A frozen pivot is "weak" when |pivot| * weak_mult < |an entry below it|. 1e3 (+ a margin that keeps a pivot AT the host's
+  // threshold unflagged) is the reference's own acceptance test (sparse21/mod.rs:735-783): iteration counts then follow the
+  // reference's. Tolerance-mode plans (one large circuit on the grid-wide kernel, where a re-pivot costs a whole host symbolic
+  // phase) only stop for pivots that endanger the solve itself: an inexact factorisation is an inexact Newton step, and the
+  // convergence test is on the true residual. Read by kernels/grid.cu; the batched kernels keep the reference's figure.
+  double weak_mult = 1.000001e3;
   int relaxed = 0;         // the plan's level schedules are in tolerance mode (host/symbolic.hpp build_levels): apply updates atomically
   int has_bsim4 = 0;       // selects the kernel build that links the Bsim4 evaluation (kept out of the others: register pressure)
 };
@@ -105,11 +111,18 @@ struct CoopCfg {
   const int* arena;
   size_t arena_bytes;  // multiple of 16
   bool arena_in_smem;
+  // cooperative kernel: > 0 = copy only this prefix of the arena (everything but the parameter-code table, which is last and,
+  // for Bsim4 circuits, larger than all the other tables together) — multiple of 16
+  size_t arena_core_bytes = 0;
   bool cold = false;   // hybrid kernel only: start from x = 0 / zero device state instead of loading them (a folded reset)
+  // cooperative kernel: smem_bytes covers x, rhs, residual and the L+U values only (coop_mixed_bytes); the stamp staging area
+  // (`stage` must be given) and the device state stay in HBM/L2
+  bool mixed = false;
 };
 // Shared-memory budget of one CTA: control words + (optional) arena copy + workspace.
 size_t coop_ctrl_bytes(int gi);
 size_t coop_work_bytes(int N, int nnz, int n_stage, int n_state, int gi, int scalar_width);
+size_t coop_mixed_bytes(int N, int nnz, int gi, int scalar_width);
 int coop_max_smem_optin(int device);
 
 // All launchers enqueue on `stream` (a cudaStream_t) and return a cudaError_t as int.

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256, B4 ? 1 : 2) k_grid(DevTables d, PlanTable
         e.pinst = 0;
         const size_t so = (size_t)d.state_off[dev];
         e.sop = sop + so; e.sguess = sguess + so; e.sstride = 1;
-        e.x = x; e.xstride = 1;
+        e.x = x; e.xstride = 1; e.Sstride = 1;
         e.S = S + (size_t)ct.stage_off[dev];
         e.mode = ctl.mode; e.dt = ctl.dt; e.gmin = ctl.gmin; e.omega = 0.0;
         load_one<double, B4>(d.type[dev], e, (d.par_direct && d.par_direct[dev]) ? d.pval + d.par_off[dev] : nullptr);
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256, B4 ? 1 : 2) k_grid(DevTables d, PlanTable
           double* t = lu + ct.lu_t[op];
           const double u = lu[ct.lu_u[op]];
           if (l < 0) {
-            if (l == -1 && ctl.stop_on_weak && s_abs(u) * 1.000001e3 < s_abs(*t)) gc->weak = 1;  // pivot health (newton.cu)
+            if (l == -1 && ctl.stop_on_weak && s_abs(u) * ctl.weak_mult < s_abs(*t)) gc->weak = 1;  // pivot health (newton.cu)
             *t = s_div(*t, u);
           } else if (ctl.relaxed) atomicAdd(t, -s_mul(u, lu[l]));  // several updates of one level may share the target
           else *t = s_sub(*t, s_mul(u, lu[l]));

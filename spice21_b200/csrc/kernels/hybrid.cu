@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256, 2) k_hyb(DevTables d, PlanTables p, CoopT
           e.pinst = pinst;
           const I so = (I)d.state_off[dev] * HY_P + ei;
           e.sop = sop + so; e.sguess = sguess + so; e.sstride = HY_P;
-          e.x = x + ei; e.xstride = HY_P;
+          e.x = x + ei; e.xstride = HY_P; e.Sstride = HY_P;
           e.S = S + (I)ct.stage_off[dev] * HY_P + ei;
           e.mode = ctl.mode; e.dt = ctl.dt; e.gmin = ctl.gmin; e.omega = omega;
           load_one<T, B4>(d.type[dev], e, (d.par_direct && d.par_direct[dev]) ? d.pval + d.par_off[dev] : nullptr);
@@ -303,7 +303,7 @@ int launch_b4(const DevTables& d, const PlanTables& p, const CoopTables& ct, con
            const CoopCfg& cfg, int T_points, const int* save_vars, int n_save, double* wave, void* stream) {
   CoopArgs a;
   a.lg_gi = 5; a.gi = HY_GI; a.cold = cfg.cold ? 1 : 0; a.T_points = T_points; a.n_save = n_save; a.save_vars = save_vars; a.wave = wave;
-  a.arena = cfg.arena; a.arena_bytes = (int)cfg.arena_bytes;
+  a.arena = cfg.arena; a.arena_bytes = (int)cfg.arena_bytes; a.pcode_global = 0;
   const size_t smem = hyb_ctrl_bytes() + cfg.arena_bytes + cfg.smem_bytes;
   const int grid = (c.B + HY_GI - 1) / HY_GI;
   auto kern = k_hyb<T, KIND, B4>;

@@ -940,3 +940,28 @@ def test_grid_kernel_single_large_circuit(s21, oracle, monkeypatch):
     assert np.max(np.abs(w[0] - o.data)) <= 1e-8
     x, sd, _ = s21.Batch(cc.inverter_array(20, 5)[0].to_s21().elaborate(), 1).dcop()
     assert sd[0] in (0, 1)  # without the IC the 100-iteration cap may hit, as in the reference; the launch must not hang
+
+
+# ------------------------------------------------------------------------------------------------ hygiene
+@pytest.mark.parametrize("tool,parts", [("memcheck", "all"), ("racecheck", "team"), ("racecheck", "bsim4"), ("synccheck", "team")])
+def test_compute_sanitizer_clean(s21, tool, parts):
+    """tests/sanitize_target.py — one small pass through every kernel family (specialised team / thread kernels with a
+    ragged batch, hybrid, cooperative with shared-memory and HBM workspace, direct dcop / tran / adaptive / AC, grid-wide,
+    probe, pack) — under compute-sanitizer: memcheck over everything, racecheck and synccheck over the kernels that
+    communicate through shared memory, warp shuffles with lane masks and the deferred-exception redo paths. Skipped when
+    the tool is not installed on the box."""
+    import shutil
+    import subprocess
+    import sys
+    exe = shutil.which("compute-sanitizer") or "/usr/local/cuda/bin/compute-sanitizer"
+    if not os.path.exists(exe):
+        pytest.skip("compute-sanitizer not installed")
+    target = os.path.join(os.path.dirname(os.path.abspath(__file__)), "sanitize_target.py")
+    env = dict(os.environ)
+    env.pop("S21_KERNEL", None)
+    p = subprocess.run([exe, "--tool", tool, "--error-exitcode", "86", "--print-limit", "5", sys.executable, target, parts],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1500, env=env)
+    tail = "\n".join(p.stdout.splitlines()[-40:])
+    assert "SANITIZE_TARGET_OK" in p.stdout, tail
+    assert p.returncode == 0, tail
+    assert "ERROR SUMMARY: 0 errors" in p.stdout or "RACECHECK SUMMARY: 0 hazards" in p.stdout, tail
