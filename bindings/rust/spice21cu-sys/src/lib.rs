@@ -64,6 +64,7 @@ extern "C" {
     pub fn s21_batch_dcop_device(b: *mut s21_batch) -> i32;
     pub fn s21_batch_read(b: *mut s21_batch, x: *mut f64, status: *mut i32, iters: *mut i32) -> i32;
     pub fn s21_batch_dcop_view(b: *mut s21_batch, x: *mut *const f64, status: *mut *const i32, iters: *mut *const i32) -> i32;
+    pub fn s21_batch_step_dcop_view(b: *mut s21_batch, flags: i32, x: *mut *const f64, status: *mut *const i32, iters: *mut *const i32, h2d_bytes: *mut usize) -> i32;
     pub fn s21_batch_packed_device(b: *mut s21_batch, dev_ptr: *mut *const f64, n_words: *mut usize) -> i32;
     pub fn s21_batch_wave_device(b: *const s21_batch, dev_ptr: *mut *const f64, T: *mut usize, n_save: *mut usize, stride: *mut usize) -> i32;
     pub fn s21_tran_num_points(tstep: f64, tstop: f64) -> i64;

@@ -127,6 +127,27 @@ impl<'c> Batch<'c> {
         })
     }
 }
+impl<'c> Batch<'c> {
+    /// One sweep step in one call (`s21_batch_step_dcop_view`): forced upload of the parameter pool, cold start, dcop;
+    /// the result rows are written by the kernel into the library's pinned buffer. Returns the view and the bytes uploaded.
+    pub fn step_dcop_view(&mut self, upload: bool, reset: bool) -> SpResult<(DcopView<'_>, usize)> {
+        let n = self.ckt.num_vars();
+        let (mut x, mut st, mut it) = (ptr::null(), ptr::null(), ptr::null());
+        let mut h2d: usize = 0;
+        let flags = (upload as i32) | ((reset as i32) << 1);
+        check(unsafe { sys::s21_batch_step_dcop_view(self.h, flags, &mut x, &mut st, &mut it, &mut h2d) })?;
+        Ok((
+            unsafe {
+                DcopView {
+                    x: std::slice::from_raw_parts(x, n * self.b),
+                    status: std::slice::from_raw_parts(st, self.b),
+                    iters: std::slice::from_raw_parts(it, self.b),
+                }
+            },
+            h2d,
+        ))
+    }
+}
 impl<'c> Drop for Batch<'c> {
     fn drop(&mut self) {
         unsafe { sys::s21_batch_destroy(self.h) }

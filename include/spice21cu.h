@@ -101,10 +101,12 @@ void s21_batch_destroy(s21_batch* b);
 /* Launch on a caller-owned stream (a cudaStream_t passed as void*); NULL = the library's own stream. */
 int32_t s21_batch_set_stream(s21_batch* b, void* cuda_stream);
 /* Per-instance values for one reference-level parameter: spec is "<kind>:<name>:<param>" with kind one of
- * mos1model | mos1inst | diodemodel | diodeinst | R | C | I | V | opt  (R/C/I/V take the flattened instance
- * path, param g | c | dc | acm; opt takes temp | gmin with an empty name). The host re-runs the reference's
- * once-per-(model,inst) derivation (mos.rs:320-476, diode.rs:146-212) per instance and keeps only the columns
- * that actually vary. values[B] is host memory. Takes effect at the next solve. */
+ * mos1model | mos1inst | diodemodel | diodeinst | bsim4model | bsim4inst | R | C | I | V | opt  (the model / inst kinds
+ * take the card's name, R/C/I/V the flattened instance path with param g | c | dc | dc or acm; opt takes temp with an
+ * empty name — Options.gmin is one value per solve, s21_options). The host re-runs the reference's
+ * once-per-(model,inst) derivation (mos.rs:320-476, diode.rs:146-212, bsim4inst.rs:9-1378) per instance and keeps only
+ * the columns that actually vary. values[B] is host memory. Takes effect at the next solve. An unknown kind, a name that
+ * matches no device, or a param the kind does not have is refused with S21_ERROR (nothing is recorded). */
 int32_t s21_batch_override(s21_batch* b, const char* spec, const double* values);
 /* Rebuild (if overrides changed) and upload the parameter pool from pinned host memory to HBM; with force_upload != 0
  * the host->device copy is repeated even when nothing changed (the per-step input transfer of an end-to-end run).
@@ -130,6 +132,13 @@ int32_t s21_batch_read(s21_batch* b, double* x, int32_t* status, int32_t* iters)
  * batch; the caller must not free or write them. (The reference returns an owned Vec, analysis.rs:383-388; a caller that
  * needs ownership copies, which is what s21_batch_dcop does.) */
 int32_t s21_batch_dcop_view(s21_batch* b, const double** x, const int32_t** status, const int32_t** iters);
+/* One Monte-Carlo / sweep step in ONE call: [flags bit 0] s21_batch_sync_params(force_upload = 1) — the host->device copy of
+ * the parameter pool from pinned memory —, [bit 1] s21_batch_reset (cold start), then s21_batch_dcop_view. What a host loop
+ * that re-draws its parameters every step calls (the reference's equivalent is a fresh `dcop(ckt, opts)` per sample,
+ * analysis.rs:383-388). With a specialised team kernel the result rows are written by the kernel straight into the pinned
+ * host buffer (no packing kernel, no separate D2H copy). *h2d_bytes (may be NULL) = bytes uploaded. */
+int32_t s21_batch_step_dcop_view(s21_batch* b, int32_t flags, const double** x, const int32_t** status, const int32_t** iters,
+                                 size_t* h2d_bytes);
 /* Results of the last solve left in HBM in the host's layout — [x as [B][N] f64][status B i32][iters B i32][loads B i32],
  * *n_words f64 words in all — for a caller that hands them to a collective (bench.py: NCCL gather of per-instance solutions
  * and convergence flags across ranks) instead of copying them to the host first. Device pointer, owned

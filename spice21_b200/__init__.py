@@ -33,7 +33,7 @@ ABI_SYMBOLS = [
     "s21_batch_destroy", "s21_batch_set_stream", "s21_batch_override", "s21_batch_sync_params", "s21_batch_reset", "s21_batch_dcop",
     "s21_batch_dcop_device", "s21_batch_read", "s21_tran_num_points", "s21_batch_tran", "s21_ac_freqs", "s21_batch_ac",
     "s21_batch_pivot_order", "s21_batch_dcop_view", "s21_batch_stats", "s21_batch_kernel_name", "s21_jit_source", "s21_jit_check", "s21_selftest_div", "s21_symbolic",
-    "s21_batch_setup_stats", "s21_batch_plan_info", "s21_batch_tran_adaptive", "s21_batch_set_aids", "s21_batch_packed_device", "s21_batch_wave_device", "s21_sweep_partition", "s21_sweep_create", "s21_sweep_destroy", "s21_sweep_num_devices", "s21_sweep_shard",
+    "s21_batch_setup_stats", "s21_batch_plan_info", "s21_batch_tran_adaptive", "s21_batch_set_aids", "s21_batch_packed_device", "s21_batch_wave_device", "s21_batch_step_dcop_view", "s21_sweep_partition", "s21_sweep_create", "s21_sweep_destroy", "s21_sweep_num_devices", "s21_sweep_shard",
     "s21_sweep_override", "s21_sweep_sync_params", "s21_sweep_reset", "s21_sweep_dcop", "s21_sweep_dcop_view", "s21_sweep_tran", "s21_sweep_ac",
     "s21_sweep_stats",
 ]
@@ -95,6 +95,7 @@ def lib():
         L.s21_batch_dcop_device.argtypes = [C.c_void_p]
         L.s21_batch_dcop_view.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.s21_batch_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.s21_batch_step_dcop_view.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.s21_batch_tran.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.s21_batch_ac.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         L.s21_batch_pivot_order.argtypes = [C.c_void_p] + [C.c_void_p] * 7
@@ -350,6 +351,7 @@ class Batch:
         self.B = B
         self.N = ckt.n_vars
         self.h = C.c_void_p()
+        self._views = None  # numpy views of the pinned result buffer, rebuilt only when the library moves it
         _check(lib().s21_batch_create(ckt.h, device, B, C.byref(self.h)))
 
     def __del__(self):
@@ -397,6 +399,19 @@ class Batch:
 
         x = view(px, C.c_double, (self.B, self.N)) if want_x else None
         return x, view(ps, C.c_int32, (self.B,)), view(pi, C.c_int32, (self.B,))
+
+    def step_dcop_view(self, upload=True, reset=True):
+        """One sweep step in one call (s21_batch_step_dcop_view): forced H2D of the parameter pool, cold start, dcop, results
+        as read-only views into the library's pinned buffer. Returns (x, status, iters, h2d_bytes)."""
+        px, ps, pi, nb = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_size_t()
+        _check(lib().s21_batch_step_dcop_view(self.h, (1 if upload else 0) | (2 if reset else 0), C.byref(px), C.byref(ps), C.byref(pi), C.byref(nb)))
+        if self._views is None or self._views[0] != (px.value, ps.value, pi.value):
+            def view(p, ctype, shape):
+                a = np.ctypeslib.as_array(C.cast(p, C.POINTER(ctype)), shape=shape)
+                a.flags.writeable = False
+                return a
+            self._views = ((px.value, ps.value, pi.value), view(px, C.c_double, (self.B, self.N)), view(ps, C.c_int32, (self.B,)), view(pi, C.c_int32, (self.B,)))
+        return self._views[1], self._views[2], self._views[3], nb.value
 
     def dcop_device(self):
         _check(lib().s21_batch_dcop_device(self.h))

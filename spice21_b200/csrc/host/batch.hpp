@@ -237,6 +237,7 @@ class Batch {
     size_t a = spec.find(':'), b = a == std::string::npos ? a : spec.find(':', a + 1);
     if (a == std::string::npos || b == std::string::npos) throw S21Error(ST_OTHER, "bad override spec: " + spec);
     o.kind = spec.substr(0, a); o.name = spec.substr(a + 1, b - a - 1); o.param = spec.substr(b + 1);
+    validate_override(o, spec);  // an override that could never take effect is refused here, not at the next solve
     o.values.assign(values, values + B_);
     for (Override& x : overrides_)
       if (x.kind == o.kind && x.name == o.name && x.param == o.param) { x.values = o.values; params_dirty_ = true; rebuild_ = true; return; }
@@ -245,13 +246,47 @@ class Batch {
     rebuild_ = true;
   }
 
+  // kind must be known, name must match a device (card name for the model / instance kinds, flattened path for R / C / I / V),
+  // param must be one that kind has: otherwise the override would silently do nothing — or, for an unknown kind, fail every
+  // later solve of this batch with no way to remove it.
+  void validate_override(const Override& o, const std::string& spec) const {
+    auto bad = [&](const std::string& why) { throw S21Error(ST_OTHER, "bad override \"" + spec + "\": " + why); };
+    if (o.kind == "opt") {
+      if (o.param != "temp") bad("opt takes temp only (Options.gmin is one value per solve: use s21_options)");
+      return;
+    }
+    int type = -1;
+    bool by_model = false, by_inst = false;
+    if (o.kind == "mos1model") { type = DT_MOS1; by_model = true; }
+    else if (o.kind == "mos1inst") { type = DT_MOS1; by_inst = true; }
+    else if (o.kind == "diodemodel") { type = DT_DIODE; by_model = true; }
+    else if (o.kind == "diodeinst") { type = DT_DIODE; by_inst = true; }
+    else if (o.kind == "bsim4model") { type = DT_BSIM4; by_model = true; }
+    else if (o.kind == "bsim4inst") { type = DT_BSIM4; by_inst = true; }
+    else if (o.kind == "R") type = DT_R;
+    else if (o.kind == "C") type = DT_C;
+    else if (o.kind == "I") type = DT_I;
+    else if (o.kind == "V") type = DT_V;
+    else bad("unknown kind (mos1model | mos1inst | diodemodel | diodeinst | bsim4model | bsim4inst | R | C | I | V | opt)");
+    bool hit = false;
+    for (const FlatDev& d : flat_.devs) {
+      if (d.is_ic || d.type != type) continue;
+      if (by_model ? d.model == o.name : by_inst ? d.params == o.name : d.path == o.name) { hit = true; break; }
+    }
+    if (!hit) bad("no device of that kind is named \"" + o.name + "\"");
+    const char* want = type == DT_R ? "g" : type == DT_C ? "c" : type == DT_I ? "dc" : nullptr;
+    if (want && o.param != want) bad(std::string("param must be ") + want);
+    if (type == DT_V && o.param != "dc" && o.param != "acm") bad("param must be dc or acm");
+    if (o.param.empty()) bad("empty parameter name");
+  }
+
   // A fresh Solver: x = 0, op = guess = Default (all zeros), counters cleared. Lazy: the hybrid dcop kernel folds the
   // reset into its prologue (it then never reads the old x / state from HBM); every other consumer materialises it.
   void reset() { reset_pending_ = true; }
   void materialize_reset() {
     if (!reset_pending_) return;
     reset_pending_ = false;
-    rows_fresh_ = false;
+    rows_fresh_ = false; host_rows_fresh_ = false;
     S21_CUDA(cudaSetDevice(device_));
     S21_CUDA(cudaMemsetAsync(x_.p, 0, x_.n * sizeof(double), stream_));
     S21_CUDA(cudaMemsetAsync(st_op_.p, 0, st_op_.n * sizeof(double), stream_));
@@ -275,7 +310,9 @@ class Batch {
         h2d_bytes_ += (pcode_h_.size() + poff_eff_.size()) * sizeof(int);
       }
       d_pval_.alloc(pval_n_);
+      trace_mark(0);
       S21_CUDA(cudaMemcpyAsync(d_pval_.p, pval_h_.p, pval_n_ * sizeof(double), cudaMemcpyHostToDevice, stream_));
+      trace_mark(1);
       params_dirty_ = false;
       h2d_bytes_ += pval_n_ * sizeof(double);
     }
@@ -283,8 +320,13 @@ class Batch {
   size_t last_h2d_bytes() const { return h2d_bytes_; }
 
   // ---- dcop -----------------------------------------------------------------------------------------------
-  void dcop_device() {
+  // dcop_device(true): the caller is about to read the results on the host (dcop / dcop_view) — a specialised team kernel then
+  // writes its result rows straight into the pinned host buffer (mapped: the same pointer is valid on the device), the
+  // packing kernel and the D2H copy of a read fall away. S21_HOST_ROWS=0 keeps the rows in HBM (pack + one D2H copy).
+  static bool host_rows_enabled() { static const bool on = [] { const char* e = std::getenv("S21_HOST_ROWS"); return !e || std::atoi(e) != 0; }(); return on; }
+  void dcop_device(bool read_follows = false) {
     S21_CUDA(cudaSetDevice(device_));
+    want_host_rows_ = read_follows && host_rows_enabled() && !ext_x_;
     sync_params(false);
     launches_ = 0;
     ensure_plan(op_plan_, AN_OP, 0.0);
@@ -300,7 +342,14 @@ class Batch {
     materialize_reset();
     const int N = flat_.n_vars();
     int32_t *hs, *hi, *hl;
-    if (want_x) {
+    if (want_x && host_rows_fresh_ && !ext_x_) {  // the kernel wrote the rows into hx_ itself: only wait for it
+      trace_mark(2); trace_mark(3);
+      S21_CUDA(cudaStreamSynchronize(stream_));
+      trace_report();
+      hs = reinterpret_cast<int32_t*>(hx_.p + (size_t)N * B_);
+      hi = hs + B_;
+      hl = hi + B_;
+    } else if (want_x) {
       const size_t words = rows_words();
       d_rows_.alloc(words);
       if (!ext_x_) hx_.alloc(words);
@@ -315,8 +364,11 @@ class Batch {
         S21_CUDA(cudaStreamSynchronize(stream_));
         hs = ext_tail_;
       } else {
+        trace_mark(2);
         S21_CUDA(cudaMemcpyAsync(hx_.p, d_rows_.p, words * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        trace_mark(3);
         S21_CUDA(cudaStreamSynchronize(stream_));
+        trace_report();
         hs = reinterpret_cast<int32_t*>(hx_.p + (size_t)N * B_);
       }
       hi = hs + B_;
@@ -491,7 +543,7 @@ class Batch {
              &st, &its, &lds, &xs);
       todo = harvest(*sub, list, st.data(), its.data(), lds.data(), xs.data());
     }
-    rows_fresh_ = false;
+    rows_fresh_ = false; host_rows_fresh_ = false;
   }
   static bool pivot_stop_enabled() { const char* e = std::getenv("S21_PIVOT_HEALTH"); return !e || std::atoi(e) != 0; }
   static bool pivot_repair_enabled() { const char* e = std::getenv("S21_PIVOT_REPAIR"); return !e || std::atoi(e) != 0; }
@@ -551,7 +603,7 @@ class Batch {
       open.swap(next);
     }
     for (size_t i : open) hs[i] = ST_PIVOT;  // 128 rounds without settling
-    rows_fresh_ = false;
+    rows_fresh_ = false; host_rows_fresh_ = false;
   }
   long long weak_seen() const { return weak_seen_; }
   long long repaired() const { return repaired_; }
@@ -593,18 +645,33 @@ class Batch {
   // ---- tran -----------------------------------------------------------------------------------------------
   void tran(double tstep, int T, const int32_t* save_vars, size_t n_save, double* wave, int32_t* status, int64_t* iters) {
     S21_CUDA(cudaSetDevice(device_));
+    const bool info = std::getenv("S21_PLAN_INFO") != nullptr;
+    auto t_ph = std::chrono::steady_clock::now();
+    auto phase = [&](const char* what) {  // S21_PLAN_INFO: host wall clock per phase of the call (synchronises: diagnostics only)
+      if (!info) return;
+      cudaStreamSynchronize(stream_);
+      const auto now = std::chrono::steady_clock::now();
+      std::fprintf(stderr, "[s21 tran] %-28s %9.3f ms (weak %lld, repaired %lld, re-pivot rounds %lld)\n", what,
+                   std::chrono::duration<double>(now - t_ph).count() * 1e3, weak_seen_, repaired_, repivot_rounds_);
+      t_ph = now;
+    };
     materialize_reset();
     sync_params(false);
     launches_ = 0;
+    phase("reset + parameters");
     ensure_plan(op_plan_, AN_OP, 0.0);
+    phase("OP plan (probe + symbolic)");
     S21_CUDA(cudaEventRecord(ev0_, stream_)); ev_pair_ = false;
     run_op();
+    phase("OP solve");
     rescue_op();
+    phase("OP rescue");
     // The matrix changes character after the OP (capacitor companions appear, IC resistors are released):
     // take the pivot order again from the first transient iteration.
     tran_plan_.valid = false;
-    rows_fresh_ = false;  // the transient moves x on
+    rows_fresh_ = false; host_rows_fresh_ = false;  // the transient moves x on
     ensure_plan(tran_plan_, AN_TRAN, tstep);
+    phase("TRAN plan (probe + symbolic)");
     std::vector<int> sv(save_vars, save_vars + n_save);
     d_save_.upload(sv, stream_);
     S21_CUDA(cudaEventRecord(ev0_, stream_)); ev_pair_ = false;  // time the transient kernel itself: the symbolic phase above is host work
@@ -641,6 +708,7 @@ class Batch {
     launches_++;
     if (rc) throw S21Error(ST_CUDA, std::string("tran kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
     S21_CUDA(cudaEventRecord(ev1_, stream_)); ev_pair_ = true;
+    phase("time loop kernel");
     last_plan_ = &tran_plan_;
     if (wave) {
       hwave_.alloc((size_t)T * n_save * Bs_);
@@ -676,7 +744,7 @@ class Batch {
     // the frozen pivot order is taken at the first step size; the companion conductances C/h move with h, so the pivot-health
     // flag (bit 8 of the status word) is what tells whether the order stayed adequate
     tran_plan_.valid = false;
-    rows_fresh_ = false;
+    rows_fresh_ = false; host_rows_fresh_ = false;
     ensure_plan(tran_plan_, AN_TRAN, g.h0);
     if (tran_plan_.host.status != ST_OK) throw S21Error(tran_plan_.host.status, status_text(tran_plan_.host.status));
     std::vector<int> sv(save_vars, save_vars + n_save);
@@ -869,6 +937,27 @@ class Batch {
   cudaStream_t own_stream_ = nullptr, stream_ = nullptr;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
   bool ev_pair_ = false;  // ev0_ and ev1_ bracket a finished launch sequence
+  // S21_TRACE_E2E=1 (diagnostics): device time stamps around the H2D copy of the parameter pool, the solve and the D2H copy
+  // of the result rows, and the host clock from the first mark to the return of the synchronise, printed per read.
+  cudaEvent_t tr_ev_[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::chrono::steady_clock::time_point tr_t0_;
+  static bool trace_on() { static const bool on = [] { const char* e = std::getenv("S21_TRACE_E2E"); return e && std::atoi(e) != 0; }(); return on; }
+  void trace_mark(int k) {
+    if (!trace_on()) return;
+    if (!tr_ev_[k]) cudaEventCreate(&tr_ev_[k]);
+    if (k == 0) tr_t0_ = std::chrono::steady_clock::now();
+    cudaEventRecord(tr_ev_[k], stream_);
+  }
+  void trace_report() {
+    if (!trace_on() || !tr_ev_[0] || !tr_ev_[3] || !ev_pair_) return;
+    const double host_us = std::chrono::duration<double>(std::chrono::steady_clock::now() - tr_t0_).count() * 1e6;
+    float h2d = 0, gap1 = 0, kern = 0, gap2 = 0, d2h = 0;
+    cudaEventElapsedTime(&h2d, tr_ev_[0], tr_ev_[1]); cudaEventElapsedTime(&gap1, tr_ev_[1], ev0_); cudaEventElapsedTime(&kern, ev0_, ev1_);
+    cudaEventElapsedTime(&gap2, ev1_, tr_ev_[2]); cudaEventElapsedTime(&d2h, tr_ev_[2], tr_ev_[3]);
+    std::fprintf(stderr, "[s21 e2e] h2d %.1f us, gap %.1f, solve %.1f, gap(+pack) %.1f, d2h %.1f; host first mark -> sync return %.1f us\n", h2d * 1e3,
+                 gap1 * 1e3, kern * 1e3, gap2 * 1e3, d2h * 1e3, host_us);
+    (void)cudaGetLastError();
+  }
   DBuf<int> d_type_, d_ioff_, d_poff_, d_soff_, d_itab_raw_, d_pcode_, d_pdirect_, d_save_;
   DBuf<double> d_pval_, x_, rhs_, c_, lu_, st_op_, st_guess_, d_wave_, d_omega_, d_rows_;
   DBuf<GridCtl> d_gctl_;
@@ -894,6 +983,7 @@ class Batch {
   size_t pval_n_ = 0, h2d_bytes_ = 0;
   std::vector<Override> overrides_;
   bool params_dirty_ = true, rebuild_ = true, codes_dirty_ = true, rows_fresh_ = false;
+  bool host_rows_fresh_ = false, want_host_rows_ = false;  // result rows of the last solve already in hx_ (written by the kernel) host_rows_fresh_ = false;
   PlanDevice op_plan_, tran_plan_, ac_plan_;
   const PlanDevice* last_plan_ = nullptr;
   size_t lu_rows_ = 0;
@@ -1122,7 +1212,7 @@ class Batch {
     c.stop_on_weak = (mode == AN_OP || mode == AN_AC) && pivot_stop_enabled() ? 1 : 0;
     c.relaxed = (mode == AN_OP ? op_plan_ : mode == AN_TRAN ? tran_plan_ : ac_plan_).host.relaxed ? 1 : 0;
     if (c.relaxed) {
-      c.weak_mult = 1e9;
+      c.weak_mult = INFINITY;  // |pivot| * inf < |entry| is never true (and NaN for a zero pivot, which the singular test catches)
       if (const char* e = std::getenv("S21_GRID_WEAK_MULT")) { const double v = std::atof(e); if (v >= 1.0) c.weak_mult = v; }
     }
     return c;
@@ -1138,18 +1228,24 @@ class Batch {
     DevTables dt = dev_tables(op_plan_.itab.p);
     int rc;
     CoopCfg hcfg;
-    rows_fresh_ = false;
+    rows_fresh_ = false; host_rows_fresh_ = false;
     if (const jit::Kernel* jk = jit_kernel(op_plan_, false)) {
       const bool cold = reset_pending_;
       reset_pending_ = false;
       last_kernel_ = jk->team ? "jit-team" : "jit-thread";
       double* rows = nullptr;
-      if (jk->team && jit::team_wp(false, B_)) {  // the warp-private team kernel also leaves the host's result layout behind
+      bool to_host = false;
+      if (jk->team && want_host_rows_) {  // result rows straight into the pinned host buffer (see dcop_device)
+        hx_.alloc(rows_words());
+        rows = hx_.p;
+        to_host = true;
+      } else if (jk->team && jit::team_wp(false, B_)) {  // the warp-private team kernel leaves the host's result layout behind in HBM
         d_rows_.alloc(rows_words());
         rows = d_rows_.p;
       }
       rc = launch_jit(*jk, AN_OP, 0.0, cold, 2, nullptr, 0, nullptr, rows);
-      rows_fresh_ = rc == 0 && rows != nullptr;
+      rows_fresh_ = rc == 0 && rows != nullptr && !to_host;
+      host_rows_fresh_ = rc == 0 && to_host;
     } else if (use_coop_ && use_hybrid(op_plan_, 1, &hcfg)) {
       hcfg.cold = reset_pending_;
       reset_pending_ = false;
@@ -1214,7 +1310,9 @@ class Batch {
     // S21_PLAN_EXACT=1 asks for the bit-identical chains.
     const char* exact = std::getenv("S21_PLAN_EXACT");
     const bool relaxed = use_coop_ && use_grid() && !(exact && std::atoi(exact) != 0);
-    pd.host = build_plan<double>(N, flat_.elem_row, flat_.elem_col, vals.data(), relaxed);
+    // a re-pivot attempt (a sub-batch of resolve_repivot) works under an update budget; the primary plans never do
+    const size_t budget = repair_depth_ > 0 ? std::max<size_t>(10000000, (size_t)4000 * (size_t)N) : 0;
+    pd.host = build_plan<double>(N, flat_.elem_row, flat_.elem_col, vals.data(), relaxed, budget);
     const auto t_sym1 = std::chrono::steady_clock::now();
     upload_plan(pd, mode);
     symbolic_s_ += std::chrono::duration<double>(t_sym1 - t_sym0).count();

@@ -565,11 +565,15 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
        "    status[i0 + ri] = r_stat;\n"
        "    iters[i0 + ri] = (cold ? 0 : iters[i0 + ri]) + r_nsol;\n"
        "    loads[i0 + ri] = (cold ? 0 : loads[i0 + ri]) + r_nld;\n  }\n";
-  if (XP)  // (rows is always a parameter; only the warp-private build writes it) the host's result layout (k_pack_out in kernels/newton.cu), written here so that a read needs no second kernel
-    o << "  if (rows) {\n    __syncthreads();\n"
-         "    if (rvalid && j == 0) { int* tail = (int*)(rows + (size_t)B * " << N << "); tail[i0 + ri] = r_stat; tail[(size_t)B + i0 + ri] = iters[i0 + ri];"
-         " tail[2 * (size_t)B + i0 + ri] = loads[i0 + ri]; }\n"
-         "    if (evalid) for (int k = warp; k < " << N << "; k += " << NW << ") rows[(size_t)(i0 + ei) * " << N << " + k] = X[k * PS + ei];\n  }\n";
+  // The host's result layout ([instance][variable] rows, then status / iters / loads as int32 — k_pack_out in kernels/newton.cu),
+  // written by the kernel itself when `rows` is given, so that a read needs no packing kernel. A CTA's rows are one contiguous
+  // block: they leave shared memory as flat, fully coalesced 8-byte stores (the destination may be mapped pinned HOST memory —
+  // the result then crosses PCIe while other CTAs still iterate, and a read is only a stream synchronise).
+  o << "  if (rows) {\n    __syncthreads();\n"
+       "    if (rvalid && j == 0) { int* tail = (int*)(rows + (size_t)B * " << N << "); tail[i0 + ri] = r_stat; tail[(size_t)B + i0 + ri] = iters[i0 + ri];"
+       " tail[2 * (size_t)B + i0 + ri] = loads[i0 + ri]; }\n"
+       "    double* rb = rows + (size_t)i0 * " << N << ";\n"
+       "    for (int f = tid; f < ni * " << N << "; f += " << NW * 32 << ") rb[f] = X[(f % " << N << ") * PS + f / " << N << "];\n  }\n";
   if (prof)
     o << "  __syncthreads();\n  if (tid == 0 && blockIdx.x == 0) {\n"
          "    const char* nm[10] = {\"loop/other\", \"eval\", \"barrier-after-eval\", \"gather\", \"residual+conv\", \"LU\", \"forward\", \"backward\", \"limit+update\", \"end-barrier\"};\n"

@@ -82,8 +82,10 @@ struct SolveCtl {
   // A frozen pivot is "weak" when |pivot| * weak_mult < |an entry below it|. 1e3 (+ a margin that keeps a pivot AT the host's
   // threshold unflagged) is the reference's own acceptance test (sparse21/mod.rs:735-783): iteration counts then follow the
   // reference's. Tolerance-mode plans (one large circuit on the grid-wide kernel, where a re-pivot costs a whole host symbolic
-  // phase) only stop for pivots that endanger the solve itself: an inexact factorisation is an inexact Newton step, and the
-  // convergence test is on the true residual. Read by kernels/grid.cu; the batched kernels keep the reference's figure.
+  // phase — and the reference's value-driven order taken at an intermediate iterate can fill the matrix, host/symbolic.hpp
+  // build_plan) do not stop for weak pivots at all (weak_mult = inf): an inexact factorisation is an inexact Newton step, and
+  // the convergence test is on the true residual; an exactly zero pivot still goes to the host. Read by kernels/grid.cu; the
+  // batched kernels keep the reference's figure.
   double weak_mult = 1.000001e3;
   int relaxed = 0;         // the plan's level schedules are in tolerance mode (host/symbolic.hpp build_levels): apply updates atomically
   int has_bsim4 = 0;       // selects the kernel build that links the Bsim4 evaluation (kept out of the others: register pressure)

@@ -214,3 +214,48 @@ def test_mos1_second_referee_agrees_with_oracle(oracle, pmos):
             assert abs(xa[k, dense.ix[n]] - ref) <= 1e-9 * max(1.0, abs(ref)), (f, n)
     if not pmos:
         assert abs(xa[0, dense.ix["d"]]) > 1.0 and abs(xa[-1, dense.ix["d"]]) < abs(xa[0, dense.ix["d"]])  # gain, then roll-off
+
+
+# ------------------------------------------------------------------------------------------------ Bsim4 invariants
+BSIM4_TOPOLOGY_VARIANTS = [
+    {}, {"rgatemod": 1}, {"rgatemod": 2}, {"rgatemod": 3}, {"rbodymod": 1}, {"rdsmod": 1}, {"trnqsmod": 1},
+    {"rgatemod": 3, "rbodymod": 1, "rdsmod": 1, "trnqsmod": 1}, {"rgatemod": 1, "rbodymod": 1, "igcmod": 1, "igbmod": 1},
+    {"capmod": 0}, {"mobmod": 1}, {"mobmod": 4}, {"igcmod": 1, "igbmod": 1}, {"gidlmod": 1}, {"diomod": 0}, {"diomod": 2},
+]
+
+
+def test_bsim4_terminal_current_invariants(oracle):
+    """The Bsim4 equations exist once in this repository (oracle/bsim4.hpp compiles the product's headers), so the reference
+    pins them only through its goldens and known answers, all on the default card. These checks need no transcription to
+    compare against: for one device driven by four voltage sources (NMOS and PMOS, forward and swapped bias)
+    (1) the four source currents sum to zero up to the gmin leakage — the stamp conserves charge on every topology the
+        selectors create (rgatemod 1-3, rbodymod, rdsmod, trnqsmod, and the PTM-65 combination rgatemod = rbodymod = igcmod = 1);
+    (2) a gate resistance carries no DC current (currents equal to rgatemod = 0 to round-off), a body network only junction
+        leakage (1e-8 relative), series resistances of this size move the drain current by < 1e-5 relative;
+    (3) with a 1.2 nm oxide, igcmod / igbmod produce a gate current of the right sign, and conservation still holds.
+    The same test runs on the GPU path (tests/test_gpu.py)."""
+    def currents(sel, typ, bias):
+        c = Ckt().define("bsim4model", "m", typ, **sel).define("bsim4inst", "i", l=1e-6, w=4e-6)
+        c.M("m1", "m", "i", d="d", g="g", s="s", b="b")
+        for n, v in zip("dgsb", bias):
+            c.V("v" + n, n, GND, v)
+        m = oracle.Circuit(c.to_text()).dcop().as_map()
+        return np.array([float(np.ravel(m["v" + n])[0]) for n in "dgsb"])
+
+    for typ, bias in ((0, (0.7, 0.9, 0.05, -0.1)), (1, (-0.7, -0.9, -0.05, 0.1)), (0, (0.05, 0.9, 0.7, -0.1))):
+        base = currents({}, typ, bias)
+        assert abs(base[0]) > 1e-5 and abs(base.sum()) < 1e-11
+        for sel in BSIM4_TOPOLOGY_VARIANTS:
+            cur = currents(sel, typ, bias)
+            assert abs(cur.sum()) < 1e-11, (sel, typ, cur)
+            if set(sel) <= {"rgatemod", "trnqsmod"}:
+                assert np.max(np.abs(cur - base)) <= 1e-12 * np.max(np.abs(base)) + 1e-15, (sel, cur, base)
+            elif set(sel) == {"rbodymod"}:
+                assert np.max(np.abs(cur - base)) <= 1e-8 * np.max(np.abs(base)) + 1e-11, (sel, cur, base)  # + gmin leakage of the network
+            elif "rdsmod" in sel:
+                assert np.max(np.abs(cur - base)) <= 1e-5 * np.max(np.abs(base)), (sel, cur, base)
+    thin = {"igcmod": 1, "igbmod": 1, "toxe": 1.2e-9, "toxp": 1.2e-9, "toxm": 1.2e-9}
+    cur = currents(thin, 0, (0.7, 0.9, 0.05, -0.1))
+    off = currents(dict(thin, igcmod=0, igbmod=0), 0, (0.7, 0.9, 0.05, -0.1))
+    assert abs(cur.sum()) < 1e-11 and abs(off[1]) < 1e-15
+    assert -cur[1] > 1e-10  # current flows from the source vg INTO the gate: the branch current of vg is negative
