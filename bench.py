@@ -273,12 +273,14 @@ def measure_dcop(args, D, s21, cc, torch, wl, scaling, stream, flush, full=True)
 
     def e2e_step():
         nonlocal chk
-        batch.sync_params(force_upload=True)
-        batch.reset()
         if D.world == 1:
-            xv, stv, itv = batch.dcop_view()  # results in the library's pinned host buffer
+            # one C-ABI call: forced H2D of the parameter pool from pinned memory, cold start, solve, result rows written by the
+            # kernel into the library's pinned host buffer (mapped), stream synchronise
+            xv, stv, itv, _ = batch.step_dcop_view(upload=True, reset=True)
             chk = float(xv[-1, 0]) + int(itv[-1])
             return stv, itv
+        batch.sync_params(force_upload=True)
+        batch.reset()
         batch.dcop_device()
         ptr, nw = batch.packed_device()
         full_t = D.gather_device(torch.as_tensor(DevArray(ptr, nw), device="cuda"))
@@ -737,9 +739,11 @@ def run_ours(args):
                     "data": "synthetic", "config": cfg, "roofline": c2_roofline(m, P, facts),
                     "e2e": {"value": m["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"],
                             "ms_per_step": m["e2e_ms"], "steps": m["e2e_steps"],
-                            "path": ("s21_batch_sync_params(force: H2D of the parameter pool from pinned memory) + s21_batch_reset + "
-                                     + ("s21_batch_dcop_view (D2H of x/status/iters into pinned host memory)" if D.world == 1 else
-                                        "s21_batch_dcop_device + s21_batch_packed_device + NCCL all-gather of every rank's x/status/iters block + D2H of the gathered block on every rank"))},
+                            "path": ("s21_batch_step_dcop_view: H2D of the parameter pool from pinned memory (cudaMemcpyAsync) + cold start + solve; "
+                                     "the kernel writes x/status/iters rows straight into the library's mapped pinned host buffer (the D2H bytes "
+                                     "cross PCIe as kernel stores), stream synchronise" if D.world == 1 else
+                                     "s21_batch_sync_params(force: H2D of the parameter pool from pinned memory) + s21_batch_reset + "
+                                     "s21_batch_dcop_device + s21_batch_packed_device + NCCL all-gather of every rank's x/status/iters block + D2H of the gathered block on every rank")},
                     "gpu_launches": args.steps * m["launches_per_step"], "setup": m["setup"], "clocks": sampler.summary()}
             if w:
                 line["weak"] = {"value": w["value"], "ms_per_step": w["ms_per_step"], "e2e_value": w["e2e_value"], "e2e_ms_per_step": w["e2e_ms"],

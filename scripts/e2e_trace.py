@@ -20,8 +20,6 @@ b.dcop()
 ts = []
 for rep in range(60):
     t0 = time.perf_counter()
-    b.sync_params(True)
-    b.reset()
-    x, st, it = b.dcop_view()
+    x, st, it, nb = b.step_dcop_view(upload=True, reset=True)
     ts.append(time.perf_counter() - t0)
 print(f"python wall per step: median {np.median(ts) * 1e6:.1f} us, min {np.min(ts) * 1e6:.1f} us; kernel {b.kernel_name()} device_ms {b.stats()['device_ms']:.4f}")

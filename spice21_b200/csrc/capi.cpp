@@ -356,10 +356,9 @@ int32_t s21_batch_dcop_view(s21_batch* b, const double** x, const int32_t** stat
 int32_t s21_batch_step_dcop_view(s21_batch* b, int32_t flags, const double** x, const int32_t** status, const int32_t** iters,
                                  size_t* h2d_bytes) {
   S21_TRY
-  if (flags & 1) b->b->sync_params(true);
-  if (h2d_bytes) *h2d_bytes = (flags & 1) ? b->b->last_h2d_bytes() : 0;
   if (flags & 2) b->b->reset();
-  b->b->dcop_device(x != nullptr);
+  b->b->dcop_device(x != nullptr, (flags & 1) != 0);
+  if (h2d_bytes) *h2d_bytes = (flags & 1) ? b->b->last_h2d_bytes() : 0;
   b->b->read_view(x != nullptr, x, status, iters);
   return S21_OK;
   S21_CATCH

@@ -324,12 +324,17 @@ class Batch {
   // writes its result rows straight into the pinned host buffer (mapped: the same pointer is valid on the device), the
   // packing kernel and the D2H copy of a read fall away. S21_HOST_ROWS=0 keeps the rows in HBM (pack + one D2H copy).
   static bool host_rows_enabled() { static const bool on = [] { const char* e = std::getenv("S21_HOST_ROWS"); return !e || std::atoi(e) != 0; }(); return on; }
-  void dcop_device(bool read_follows = false) {
+  // force_upload: this step's parameter pool crosses PCIe again (the per-step input transfer of an end-to-end run) — a
+  // cudaMemcpyAsync from the pinned pool. Letting the kernel read the pool from the mapped host copy instead was measured and
+  // dropped: the values are re-read every Newton iteration and host memory is not held in L1/L2 across them (kernel 0.099 ->
+  // 0.180 ms, profiles/r02p_host_params.txt).
+  void dcop_device(bool read_follows = false, bool force_upload = false) {
     S21_CUDA(cudaSetDevice(device_));
     want_host_rows_ = read_follows && host_rows_enabled() && !ext_x_;
     sync_params(false);
     launches_ = 0;
     ensure_plan(op_plan_, AN_OP, 0.0);
+    if (force_upload) sync_params(true);
     S21_CUDA(cudaEventRecord(ev0_, stream_)); ev_pair_ = false;
     run_op();
     S21_CUDA(cudaEventRecord(ev1_, stream_)); ev_pair_ = true;
@@ -547,63 +552,69 @@ class Batch {
   }
   static bool pivot_stop_enabled() { const char* e = std::getenv("S21_PIVOT_HEALTH"); return !e || std::atoi(e) != 0; }
   static bool pivot_repair_enabled() { const char* e = std::getenv("S21_PIVOT_REPAIR"); return !e || std::atoi(e) != 0; }
-  // Per-instance re-pivoting (first half): continue the instances a kernel stopped with ST_REPIVOT_CODE.
-  // Round by round, the open instances are gathered into a batch of their own — same circuit, their slices of every
-  // override, their x / device-state columns copied across (a WARM continuation at the iterate where each one stopped) —
-  // whose symbolic phase runs on its first instance's matrix AT THAT ITERATE, so its leader's next factorisation passes
-  // the reference's threshold test by construction and every round advances at least the leader by one Newton iteration;
-  // instances the new order suits run on to convergence, the others stop again and go into the next round. Plan-table
-  // kernels only (a specialised kernel would cost an NVRTC run per pivot order). Iteration counts accumulate across
-  // rounds against the reference's cap of 100 per solve.
+  // Per-instance re-pivoting (first half): continue, IN PLACE, the instances a kernel stopped with
+  // ST_REPIVOT_CODE (or with an exactly zero frozen pivot). Round by round: the first open instance's load sweep AT ITS
+  // CURRENT ITERATE is probed on the GPU, the reference's Markowitz search gives a pivot order for that matrix (so its next
+  // factorisation passes the reference's threshold test by construction and every round advances at least that instance by
+  // one Newton iteration), and a plan-table kernel is relaunched in resume mode (SolveCtl::resume): only the stopped
+  // instances run — warm, with what is left of their own 100 iterations —, every other column of the batch is untouched.
+  // Instances the new order suits run on to convergence, the others stop again and go into the next round. No sub-batches,
+  // no column copies, no allocation per round: a round costs a probe, a small symbolic phase, one table upload and one
+  // launch (the first implementation gathered the open instances into a batch of their own per round: C1-circuit supply
+  // sweep 295 ms, C4 429 ms end to end, against 33 / 212 ms without the repair).
   void resolve_repivot(const std::vector<size_t>& flagged, double* hx, int32_t* hs, int32_t* hi, int32_t* hl) {
     const int N = flat_.n_vars();
     std::vector<size_t> open = flagged;
-    for (int round = 0; round < 128 && !open.empty(); round++) {
-      std::unique_ptr<Batch> sub(new Batch(spec_, flat_, device_, open.size()));
-      sub->repair_depth_ = repair_depth_ + 1;
-      sub->no_resolve_ = true;  // its stopped instances come back to this loop
-      sub->allow_jit_ = false;
-      sub->set_stream(stream_);
-      std::vector<double> vals(open.size());
-      for (const Override& o : overrides_) {
-        for (size_t k = 0; k < open.size(); k++) vals[k] = o.values[open[k]];
-        sub->add_override(o.kind + ":" + o.name + ":" + o.param, vals.data());
+    bool rewrite = false;
+    for (size_t i : open) if (hs[i] != ST_REPIVOT_CODE) { hs[i] = ST_REPIVOT_CODE; rewrite = true; }  // zero frozen pivot: continue it as well
+    hstatus_.alloc(Bs_); hiters_.alloc(Bs_); hloads_.alloc(Bs_);
+    if (rewrite) {
+      std::memcpy(hstatus_.p, hs, B_ * sizeof(int32_t));
+      S21_CUDA(cudaMemcpyAsync(status_.p, hstatus_.p, B_ * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
+    }
+    const size_t budget = std::max<size_t>(10000000, (size_t)4000 * (size_t)N);
+    for (int round = 0; round < 256 && !open.empty(); round++) {
+      repair_plan_.valid = false;
+      ensure_plan(repair_plan_, AN_OP, 0.0, open[0], budget);
+      if (repair_plan_.host.status != ST_OK) {  // the reference's own factorisation fails on this matrix (or the attempt ran over budget)
+        const int32_t st = repair_plan_.host.status;
+        hs[open[0]] = st;
+        S21_CUDA(cudaMemcpyAsync(status_.p + open[0], hs + open[0], sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
+        S21_CUDA(cudaStreamSynchronize(stream_));
+        open.erase(open.begin());
+        continue;
       }
-      sub->gmin_eff_ = gmin_eff_;
-      sub->reset_pending_ = false;
-      int used = 100;
-      for (size_t k = 0; k < open.size(); k++) {
-        sub->copy_instance_from(*this, open[k], k);
-        used = std::min(used, (int)hi[open[k]]);
-      }
-      sub->max_iter_ = std::max(1, max_iter_ - used);
-      sub->dcop_device();
-      const double* sx = nullptr;
-      const int32_t *ss = nullptr, *si = nullptr;
-      sub->read_view(true, &sx, &ss, &si);
-      const int32_t* sl = si + open.size();
-      std::vector<size_t> next;
-      for (size_t k = 0; k < open.size(); k++) {
-        const size_t i = open[k];
-        hi[i] += si[k];
-        hl[i] += sl[k];
-        int32_t st = ss[k];
-        if (st == ST_CONV && hi[i] < max_iter_) st = ST_REPIVOT_CODE;  // ran out of THIS launch's budget, not of the solve's
-        copy_instance_from(*sub, k, i);
-        if (st == ST_REPIVOT_CODE && hi[i] < max_iter_) { next.push_back(i); continue; }
-        hs[i] = st == ST_REPIVOT_CODE ? ST_CONV : st;  // the cap of 100 iterations was reached while re-pivoting
-        std::memcpy(hx + i * (size_t)N, sx + k * (size_t)N, (size_t)N * sizeof(double));
-        S21_CUDA(cudaMemcpyAsync(status_.p + i, hs + i, sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
-        S21_CUDA(cudaMemcpyAsync(iters_.p + i, hi + i, sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
-        S21_CUDA(cudaMemcpyAsync(loads_.p + i, hl + i, sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
-        repaired_++;
-      }
+      launch_plan_dcop(repair_plan_, true);
+      S21_CUDA(cudaMemcpyAsync(hstatus_.p, status_.p, B_ * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
       S21_CUDA(cudaStreamSynchronize(stream_));
       repivot_rounds_++;
+      std::vector<size_t> next;
+      for (size_t i : open) {
+        hs[i] = hstatus_.p[i];
+        if (hs[i] == ST_REPIVOT_CODE) next.push_back(i);
+        else repaired_++;
+      }
       open.swap(next);
     }
-    for (size_t i : open) hs[i] = ST_PIVOT;  // 128 rounds without settling
-    rows_fresh_ = false; host_rows_fresh_ = false;
+    for (size_t i : open) {  // 256 rounds without settling
+      hs[i] = ST_PIVOT;
+      S21_CUDA(cudaMemcpyAsync(status_.p + i, hs + i, sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
+    }
+    // the continued instances' rows, counters and codes: pack everything again (one kernel, one copy)
+    d_rows_.alloc(rows_words());
+    int rc = launch_pack_out(x_.p, status_.p, iters_.p, loads_.p, d_rows_.p, N, Bs_, (int)B_, stream_);
+    launches_++;
+    if (rc) throw S21Error(ST_CUDA, std::string("k_pack_out launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+    PinnedBuf<double>& stage = repack_;
+    stage.alloc(rows_words());
+    S21_CUDA(cudaMemcpyAsync(stage.p, d_rows_.p, rows_words() * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    S21_CUDA(cudaStreamSynchronize(stream_));
+    const int32_t* ts = reinterpret_cast<const int32_t*>(stage.p + (size_t)N * B_);
+    for (size_t i : flagged) {
+      std::memcpy(hx + i * (size_t)N, stage.p + i * (size_t)N, (size_t)N * sizeof(double));
+      hs[i] = ts[i]; hi[i] = ts[B_ + i]; hl[i] = ts[2 * B_ + i];
+    }
+    rows_fresh_ = true; host_rows_fresh_ = false;
   }
   long long weak_seen() const { return weak_seen_; }
   long long repaired() const { return repaired_; }
@@ -985,6 +996,10 @@ class Batch {
   bool params_dirty_ = true, rebuild_ = true, codes_dirty_ = true, rows_fresh_ = false;
   bool host_rows_fresh_ = false, want_host_rows_ = false;  // result rows of the last solve already in hx_ (written by the kernel) host_rows_fresh_ = false;
   PlanDevice op_plan_, tran_plan_, ac_plan_;
+  PlanDevice repair_plan_;          // resolve_repivot: the order taken at a stopped instance's iterate
+  DBuf<int32_t> iters_base_;        // iters_ at the start of the current solve (only kept for warm starts)
+  bool iters_base_valid_ = false;
+  PinnedBuf<double> repack_;        // resolve_repivot: staging of the re-packed result rows
   const PlanDevice* last_plan_ = nullptr;
   size_t lu_rows_ = 0;
   int launches_ = 0;
@@ -1202,7 +1217,7 @@ class Batch {
     o.status = status_.p; o.iters = iters_.p; o.loads = loads_.p;
     return o;
   }
-  SolveCtl make_ctl(int mode, double dt) const {
+  SolveCtl make_ctl(int mode, double dt, const PlanDevice* plan = nullptr) const {
     SolveCtl c;
     c.B = (int)B_; c.mode = mode; c.gmin = gmin_eff_ >= 0.0 ? gmin_eff_ : flat_.opts.gmin; c.dt = dt;
     c.reltol = flat_.opts.reltol; c.iabstol = flat_.opts.iabstol; c.omega = nullptr; c.par_inst_stride = 1;
@@ -1210,12 +1225,48 @@ class Batch {
     for (const FlatDev& d : flat_.devs) if (d.type == DT_BSIM4) { c.has_bsim4 = 1; break; }
     c.max_iter = max_iter_;
     c.stop_on_weak = (mode == AN_OP || mode == AN_AC) && pivot_stop_enabled() ? 1 : 0;
-    c.relaxed = (mode == AN_OP ? op_plan_ : mode == AN_TRAN ? tran_plan_ : ac_plan_).host.relaxed ? 1 : 0;
+    c.relaxed = (plan ? *plan : mode == AN_OP ? op_plan_ : mode == AN_TRAN ? tran_plan_ : ac_plan_).host.relaxed ? 1 : 0;
+    c.weak_mult = pivot_weak_mult();
     if (c.relaxed) {
       c.weak_mult = INFINITY;  // |pivot| * inf < |entry| is never true (and NaN for a zero pivot, which the singular test catches)
       if (const char* e = std::getenv("S21_GRID_WEAK_MULT")) { const double v = std::atof(e); if (v >= 1.0) c.weak_mult = v; }
     }
     return c;
+  }
+  // One dcop launch on a plan-table kernel (hybrid / grid-wide / cooperative / direct, by circuit shape) against plan `pd`.
+  // resume: SolveCtl::resume — continue the stopped instances in place with this plan's pivot order.
+  int launch_plan_dcop(PlanDevice& pd, bool resume) {
+    SolveCtl ctl = make_ctl(AN_OP, 0.0, &pd);
+    ctl.resume = resume ? 1 : 0;
+    NewtonOut o = out();
+    o.iters_base = iters_base_valid_ ? iters_base_.p : nullptr;
+    CoopCfg hcfg;
+    int rc;
+    if (use_coop_ && use_hybrid(pd, 1, &hcfg)) {
+      hcfg.cold = !resume && reset_pending_;
+      if (!resume) reset_pending_ = false;
+      if (!resume) last_kernel_ = "hybrid";
+      rc = launch_hybrid_dcop(coop_dev(pd), pd.coop_plan(), pd.coop(), work(), o, ctl, hcfg, stream_);
+    } else if (use_coop_ && use_grid()) {
+      materialize_reset();
+      CoopCfg cfg = coop_cfg(pd, B_, 1);
+      cfg.smem_bytes = 0; cfg.mixed = false;
+      d_gctl_.alloc(1);
+      if (!resume) last_kernel_ = "grid";
+      rc = launch_grid_dcop(coop_dev(pd), pd.coop_plan(), pd.coop(), work(), stage_for(cfg, pd.host), o, ctl, d_gctl_.p, stream_);
+    } else if (use_coop_) {
+      materialize_reset();
+      CoopCfg cfg = coop_cfg(pd, B_, 1);
+      if (!resume) last_kernel_ = "coop";
+      rc = launch_coop_dcop(coop_dev(pd), pd.coop_plan(), pd.coop(), work(), stage_for(cfg, pd.host), o, ctl, cfg, stream_);
+    } else {
+      materialize_reset();
+      if (!resume) last_kernel_ = "direct";
+      rc = launch_dcop(dev_tables(pd.itab.p), pd.tables(), work(), o, ctl, stream_);
+    }
+    launches_++;
+    if (rc) throw S21Error(ST_CUDA, std::string("dcop kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+    return rc;
   }
   void run_op() {
     if (op_plan_.host.status != ST_OK) {  // the reference fails in its first factorisation: every instance reports it
@@ -1225,10 +1276,15 @@ class Batch {
       S21_CUDA(cudaStreamSynchronize(stream_));
       return;
     }
-    DevTables dt = dev_tables(op_plan_.itab.p);
     int rc;
-    CoopCfg hcfg;
     rows_fresh_ = false; host_rows_fresh_ = false;
+    // iteration counts accumulate over warm solves: a continued solve (resolve_repivot) needs to know where THIS one started
+    iters_base_valid_ = false;
+    if (!reset_pending_) {
+      iters_base_.alloc(Bs_);
+      S21_CUDA(cudaMemcpyAsync(iters_base_.p, iters_.p, Bs_ * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream_));
+      iters_base_valid_ = true;
+    }
     if (const jit::Kernel* jk = jit_kernel(op_plan_, false)) {
       const bool cold = reset_pending_;
       reset_pending_ = false;
@@ -1246,35 +1302,17 @@ class Batch {
       rc = launch_jit(*jk, AN_OP, 0.0, cold, 2, nullptr, 0, nullptr, rows);
       rows_fresh_ = rc == 0 && rows != nullptr && !to_host;
       host_rows_fresh_ = rc == 0 && to_host;
-    } else if (use_coop_ && use_hybrid(op_plan_, 1, &hcfg)) {
-      hcfg.cold = reset_pending_;
-      reset_pending_ = false;
-      last_kernel_ = "hybrid";
-      rc = launch_hybrid_dcop(coop_dev(op_plan_), op_plan_.coop_plan(), op_plan_.coop(), work(), out(), make_ctl(AN_OP, 0.0), hcfg, stream_);
-    } else if (use_coop_ && use_grid()) {
-      materialize_reset();
-      CoopCfg cfg = coop_cfg(op_plan_, B_, 1);
-      cfg.smem_bytes = 0; cfg.mixed = false;
-      d_gctl_.alloc(1);
-      last_kernel_ = "grid";
-      rc = launch_grid_dcop(coop_dev(op_plan_), op_plan_.coop_plan(), op_plan_.coop(), work(), stage_for(cfg, op_plan_.host), out(),
-                            make_ctl(AN_OP, 0.0), d_gctl_.p, stream_);
-    } else if (use_coop_) {
-      materialize_reset();
-      CoopCfg cfg = coop_cfg(op_plan_, B_, 1);
-      last_kernel_ = "coop";
-      rc = launch_coop_dcop(coop_dev(op_plan_), op_plan_.coop_plan(), op_plan_.coop(), work(), stage_for(cfg, op_plan_.host), out(),
-                            make_ctl(AN_OP, 0.0), cfg, stream_);
     } else {
-      materialize_reset();
-      last_kernel_ = "direct";
-      rc = launch_dcop(dt, op_plan_.tables(), work(), out(), make_ctl(AN_OP, 0.0), stream_);
+      rc = launch_plan_dcop(op_plan_, false);
+      launches_--;  // counted below
     }
     launches_++;
     if (rc) throw S21Error(ST_CUDA, std::string("dcop kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
   }
-  // Symbolic phase for one analysis mode: probe instance 0's first load sweep on the GPU, pivot on the host.
-  void ensure_plan(PlanDevice& pd, int mode, double dt) {
+  // Symbolic phase for one analysis mode: probe one instance's load sweep at its current iterate on the GPU (instance 0 at the
+  // start of a solve; the first stopped instance when a solve is continued with a new order), pivot on the host.
+  // update_budget > 0: the attempt is abandoned beyond that many Schur updates (host/symbolic.hpp build_plan).
+  void ensure_plan(PlanDevice& pd, int mode, double dt, size_t inst = 0, size_t update_budget = 0) {
     if (pd.valid) return;
     materialize_reset();
     const int N = flat_.n_vars();
@@ -1288,13 +1326,13 @@ class Batch {
     const size_t ns_rows = (size_t)flat_.n_state;
     if (ns_rows) {
       keep.alloc(ns_rows);
-      S21_CUDA(cudaMemcpy2DAsync(keep.p, sizeof(double), st_guess_.p, Bs_ * sizeof(double), sizeof(double), ns_rows, cudaMemcpyDeviceToDevice, stream_));
+      S21_CUDA(cudaMemcpy2DAsync(keep.p, sizeof(double), st_guess_.p + inst, Bs_ * sizeof(double), sizeof(double), ns_rows, cudaMemcpyDeviceToDevice, stream_));
     }
-    int rc = launch_probe_real(dtab, work(), make_ctl(mode, dt), flat_.n_elems(), N, 0, probe.p, stream_);
+    int rc = launch_probe_real(dtab, work(), make_ctl(mode, dt), flat_.n_elems(), N, (int)inst, probe.p, stream_);
     launches_++;
     if (rc) throw S21Error(ST_CUDA, std::string("k_probe launch failed: ") + cudaGetErrorString((cudaError_t)rc));
     if (ns_rows)
-      S21_CUDA(cudaMemcpy2DAsync(st_guess_.p, Bs_ * sizeof(double), keep.p, sizeof(double), sizeof(double), ns_rows, cudaMemcpyDeviceToDevice, stream_));
+      S21_CUDA(cudaMemcpy2DAsync(st_guess_.p + inst, Bs_ * sizeof(double), keep.p, sizeof(double), sizeof(double), ns_rows, cudaMemcpyDeviceToDevice, stream_));
     std::vector<double> vals((size_t)flat_.n_elems());
     S21_CUDA(cudaMemcpyAsync(vals.data(), probe.p, vals.size() * sizeof(double), cudaMemcpyDeviceToHost, stream_));
     S21_CUDA(cudaStreamSynchronize(stream_));
@@ -1310,9 +1348,7 @@ class Batch {
     // S21_PLAN_EXACT=1 asks for the bit-identical chains.
     const char* exact = std::getenv("S21_PLAN_EXACT");
     const bool relaxed = use_coop_ && use_grid() && !(exact && std::atoi(exact) != 0);
-    // a re-pivot attempt (a sub-batch of resolve_repivot) works under an update budget; the primary plans never do
-    const size_t budget = repair_depth_ > 0 ? std::max<size_t>(10000000, (size_t)4000 * (size_t)N) : 0;
-    pd.host = build_plan<double>(N, flat_.elem_row, flat_.elem_col, vals.data(), relaxed, budget);
+    pd.host = build_plan<double>(N, flat_.elem_row, flat_.elem_col, vals.data(), relaxed, update_budget);
     const auto t_sym1 = std::chrono::steady_clock::now();
     upload_plan(pd, mode);
     symbolic_s_ += std::chrono::duration<double>(t_sym1 - t_sym0).count();

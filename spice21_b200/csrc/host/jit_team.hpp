@@ -19,6 +19,8 @@
 // in ascending pivot order, the back-substitution row sum runs over ascending columns — results are bit-identical to
 // the other kernels (tests/test_gpu.py::test_kernel_variants_bit_identical).
 #pragma once
+#include <cstring>
+
 #include "jit.hpp"
 #include "staging.hpp"
 
@@ -537,7 +539,12 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
   }
   // pivot health: a multiplier of this factorisation >= 1000 on any lane of the instance -> stop before the update, the host
   // re-pivots at this iterate (kernels/newton.cu, host/batch.hpp resolve_repivot)
-  o << "          const bool wk = (__ballot_sync(FULLM, r_wk > 0x408f4000) & imask) != 0;\n          r_wk = 0;\n";
+  {  // a multiplier above SolveCtl::weak_mult (high words compare like the magnitudes; the bound's own high word is the literal)
+    const double wm = pivot_weak_mult();
+    long long bits; std::memcpy(&bits, &wm, sizeof bits);
+    char lit[24]; std::snprintf(lit, sizeof lit, "0x%08x", (unsigned)((unsigned long long)bits >> 32));
+    o << "          const bool wk = (__ballot_sync(FULLM, r_wk > " << lit << ") & imask) != 0;\n          r_wk = 0;\n";
+  }
   o << "          bool baddx = false;\n          const double rm = s_rcp(m);\n          if (r_act && !sing && !wk) {\n";
   for (int q = 0; q < Q; q++)
     o << "            if (v" << q << ") { double dxk = c" << q << "; if (m > 1.0) dxk = s_div_r(s_mul(dxk, 1.0), m, rm); xp" << q << " = s_add(xp" << q

@@ -58,7 +58,8 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
   int* nld = nsol + gi;
   int* convnow = nld + gi;
   int* weak = convnow + gi;  // pivot health: a frozen pivot the reference's threshold test would have refused (mod.rs:735-783)
-  uint64_t* mbar = (uint64_t*)(((size_t)(weak + gi) + 7) & ~(size_t)7);  // 9 int arrays: 8-byte alignment is not automatic
+  int* left = weak + gi;     // resume: iterations this instance's solve has left; < 0 = not a stopped instance, leave it alone
+  uint64_t* mbar = (uint64_t*)(((size_t)(left + gi) + 7) & ~(size_t)7);  // 10 int arrays: 8-byte alignment is not automatic
   size_t off = ((size_t)((unsigned char*)(mbar + 1) - smem_raw) + 15) / 16 * 16;
   if (a.arena_bytes > 0) {
     int* sa = (int*)(smem_raw + off);
@@ -109,6 +110,18 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
   // ---- prologue
   if (tid < gi) {
     stat[tid] = (tid < ni && KIND == K_TRAN) ? o.status[i0 + tid] : 0;
+    left[tid] = 1 << 30;
+    if (KIND == K_DCOP && ctl.resume) {  // continue the stopped instances only (SolveCtl::resume)
+      const int s0 = tid < ni ? o.status[i0 + tid] : 0;
+      if (tid < ni && s0 == CST_REPIVOT) {
+        const int l = ctl.max_iter - (o.iters[i0 + tid] - (o.iters_base ? o.iters_base[i0 + tid] : 0));
+        stat[tid] = l > 0 ? CST_OK : CST_CONV;
+        left[tid] = l > 0 ? l : -1;
+      } else {
+        stat[tid] = s0;
+        left[tid] = -1;
+      }
+    }
     weak[tid] = 0;
     nsol[tid] = 0; nld[tid] = 0; convnow[tid] = 0; dxok[tid] = 1; act[tid] = 0;
   }
@@ -135,7 +148,7 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
   if constexpr (KIND == K_AC) omega = valid ? ctl.omega[i0 + li] : 0.0;
 
   for (int tp = 1; tp < n_points; tp++) {
-    if (tid < gi) { act[tid] = (tid < ni && stat[tid] == CST_OK) ? 1 : 0; dxok[tid] = 1; }
+    if (tid < gi) { act[tid] = (tid < ni && stat[tid] == CST_OK && left[tid] > 0) ? 1 : 0; dxok[tid] = 1; }
     __syncthreads();
     const int max_it = real_kind ? min(TolC<T>::max_iter, ctl.max_iter) : TolC<T>::max_iter;
     for (int iter = 0; iter < max_it; iter++) {
@@ -215,7 +228,7 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
             T* t = lu + (I)ct.lu_t[op] * ws + col;
             const T u = lu[(I)ct.lu_u[op] * ws + col];
             if (l < 0) {
-              if (l == -1 && ctl.stop_on_weak && s_abs(u) * 1.000001e3 < s_abs(*t)) weak[li] = 1;  // -2: a pivot the reference chose without threshold
+              if (l == -1 && ctl.stop_on_weak && s_abs(u) * ctl.weak_mult < s_abs(*t)) weak[li] = 1;  // -2: a pivot the reference chose without threshold
               *t = s_div(*t, u);
             } else {
               *t = s_sub(*t, s_mul(u, lu[(I)l * ws + col]));
@@ -280,6 +293,7 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
         else {
           nsol[tid] += 1;
           if (KIND == K_AC && ctl.ac_direct) act[tid] = 0;  // linear system: x = A^-1 b is the answer (engine.hpp SolveCtl::ac_direct)
+          if (nsol[tid] >= left[tid]) { act[tid] = 0; stat[tid] = CST_CONV; }  // resume: its own 100 iterations are used up
         }
       }
       __syncthreads();
@@ -311,13 +325,13 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
     }
   }
   if (tid < ni) {
-    o.status[i0 + tid] = stat[tid];
+    o.status[i0 + tid] = stat[tid];  // resume: an instance that was left alone has its old code in stat[] and zeros in the counters
     o.iters[i0 + tid] += nsol[tid];
     o.loads[i0 + tid] += nld[tid];
   }
 }
 
-size_t ctrl_bytes(int gi) { return ((8 + 9 * 4) * (size_t)gi + 8 + 8 + 15) / 16 * 16; }
+size_t ctrl_bytes(int gi) { return ((8 + 10 * 4) * (size_t)gi + 8 + 8 + 15) / 16 * 16; }
 
 template <class T, int KIND, bool B4>
 int launch_b4(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<T>& w, T* stage, const NewtonOut& o,

@@ -3,6 +3,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
 
 #include "../scalar.h"
 
@@ -58,6 +59,9 @@ enum { ST_REPIVOT_CODE = 9 };
 
 struct NewtonOut {
   int32_t* status;    // [B] S21_* code
+  // resume launches (SolveCtl::resume) only: [B] value of iters[] when the solve being continued started (nullptr = zeros),
+  // so that an instance's budget is what is left of ITS 100 iterations
+  const int32_t* iters_base = nullptr;
   int32_t* iters;     // [B] iterations that reached the linear solve (accumulated)
   int32_t* loads;     // [B] device-load sweeps (accumulated)
 };
@@ -79,17 +83,29 @@ struct SolveCtl {
   int stop_on_weak = 0;
   int max_iter = 100;      // real solves: iteration budget of this launch (analysis.rs:173 caps a solve at 100; a solve continued
                            // after a re-pivot gets what is left)
-  // A frozen pivot is "weak" when |pivot| * weak_mult < |an entry below it|. 1e3 (+ a margin that keeps a pivot AT the host's
-  // threshold unflagged) is the reference's own acceptance test (sparse21/mod.rs:735-783): iteration counts then follow the
-  // reference's. Tolerance-mode plans (one large circuit on the grid-wide kernel, where a re-pivot costs a whole host symbolic
-  // phase — and the reference's value-driven order taken at an intermediate iterate can fill the matrix, host/symbolic.hpp
-  // build_plan) do not stop for weak pivots at all (weak_mult = inf): an inexact factorisation is an inexact Newton step, and
-  // the convergence test is on the true residual; an exactly zero pivot still goes to the host. Read by kernels/grid.cu; the
-  // batched kernels keep the reference's figure.
+  // A frozen pivot is "weak" when |pivot| * weak_mult < |an entry below it|, i.e. when a multiplier of the elimination exceeds
+  // weak_mult. 1e3 (+ a margin that keeps a pivot AT the host's threshold unflagged) is the reference's own acceptance test
+  // (sparse21/mod.rs:735-783): every factorisation the reference — which searches its pivots anew each time — would have
+  // ordered differently is re-ordered here too, so iteration counts and the outcome of the 100-iteration cap follow the
+  // reference's. S21_PIVOT_MULT=<bound> loosens it (experiments): measured with 1e10 the answers of converging instances
+  // stay within tolerance (the convergence test is on the true residual) but iteration counts drift by up to 15 %, instances
+  // converge that the reference caps, and a long Mos1 chain returns NaNs as "converged" (the reference's tolerance test lets
+  // NaN through, analysis.rs:331-345) — profiles/r02q_*; the bound therefore stays at the reference's figure.
   double weak_mult = 1.000001e3;
+  // 1 (dcop kernels with plan tables only): continue a solve in place. Only instances whose status is ST_REPIVOT_CODE run — warm,
+  // from the iterate where they stopped, against the pivot order of THIS launch's plan, with the iterations their solve has left
+  // (max_iter - (iters - iters_base)); every other instance keeps its x, device state, status and counters untouched.
+  int resume = 0;
   int relaxed = 0;         // the plan's level schedules are in tolerance mode (host/symbolic.hpp build_levels): apply updates atomically
   int has_bsim4 = 0;       // selects the kernel build that links the Bsim4 evaluation (kept out of the others: register pressure)
 };
+
+// Host-side: the multiplier bound of SolveCtl::weak_mult; read at every solve setup / kernel generation (the generated text
+// carries the figure, so the cubin cache keys on it).
+inline double pivot_weak_mult() {
+  if (const char* e = std::getenv("S21_PIVOT_MULT")) { const double v = std::atof(e); if (v >= 1.0) return v; }
+  return 1.000001e3;
+}
 
 // Extra shared tables of the cooperative kernel (kernels/coop.cu): staged assembly + level schedules (host/symbolic.hpp).
 struct CoopTables {

@@ -34,8 +34,10 @@ __global__ void __launch_bounds__(256, B4 ? 1 : 2) k_grid(DevTables d, PlanTable
   double* sop = g.st_op; double* sguess = g.st_guess;
   const double vtol = ctl.reltol, itol = ctl.iabstol;
 
+  // resume (SolveCtl::resume; the host only launches it for an instance it found stopped): what is left of the solve's budget
+  const int used = (KIND == K_DCOP && ctl.resume) ? o.iters[0] - (o.iters_base ? o.iters_base[0] : 0) : 0;  // written at the very end only
   if (tid == 0) {
-    gc->stat = KIND == K_TRAN ? o.status[0] : 0;
+    gc->stat = KIND == K_TRAN ? o.status[0] : (used >= ctl.max_iter ? CST_CONV : 0);
     gc->nsol = 0; gc->nld = 0; gc->dxok = 1; gc->act = 0; gc->resok = 1; gc->sing = 0; gc->weak = 0; gc->maxabs = 0ull;
   }
   if constexpr (KIND == K_TRAN) {
@@ -46,7 +48,7 @@ __global__ void __launch_bounds__(256, B4 ? 1 : 2) k_grid(DevTables d, PlanTable
   for (int tp = 1; tp < n_points; tp++) {
     if (tid == 0) { gc->act = gc->stat == CST_OK ? 1 : 0; gc->dxok = 1; }
     grid.sync();
-    const int max_it = min(TolC<double>::max_iter, ctl.max_iter);
+    const int max_it = min(TolC<double>::max_iter, ctl.max_iter) - used;
     for (int iter = 0; iter < max_it; iter++) {
       if (!gc->act) break;  // uniform: written before the last barrier
       // ---- P1: device evaluation, devices in parallel

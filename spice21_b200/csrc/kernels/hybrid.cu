@@ -97,6 +97,17 @@ __global__ void __launch_bounds__(256, 2) k_hyb(DevTables d, PlanTables p, CoopT
   // per-instance control state lives in registers, replicated over the 8 lanes of the instance
   const bool rvalid = ri < ni;
   int r_stat = (rvalid && KIND == K_TRAN) ? o.status[i0 + ri] : 0;
+  int r_left = 1 << 30;      // resume: iterations this instance's solve has left
+  bool r_skip = false;       // resume: not a stopped instance — nothing of it is touched
+  if (KIND == K_DCOP && ctl.resume) {
+    const int s0 = rvalid ? o.status[i0 + ri] : 0;
+    r_skip = !rvalid || s0 != CST_REPIVOT;
+    r_stat = r_skip ? s0 : CST_OK;
+    if (!r_skip) {
+      r_left = ctl.max_iter - (o.iters[i0 + ri] - (o.iters_base ? o.iters_base[i0 + ri] : 0));
+      if (r_left <= 0) { r_stat = CST_CONV; r_skip = true; }
+    }
+  }
   bool r_weak = false;  // pivot health (see newton.cu): set by the division steps of the current factorisation
   int r_nsol = 0, r_nld = 0;
   mbar_wait(mbar, 0);
@@ -112,7 +123,7 @@ __global__ void __launch_bounds__(256, 2) k_hyb(DevTables d, PlanTables p, CoopT
   if constexpr (KIND == K_AC) omega = evalid ? ctl.omega[i0 + ei] : 0.0;
 
   for (int tp = 1; tp < n_points; tp++) {
-    bool r_act = rvalid && r_stat == CST_OK;
+    bool r_act = rvalid && r_stat == CST_OK && !r_skip;
     bool r_dxok = true;
     if (q == 0) act_s[ri] = r_act ? 1 : 0;
     __syncthreads();
@@ -186,7 +197,7 @@ __global__ void __launch_bounds__(256, 2) k_hyb(DevTables d, PlanTables p, CoopT
             const int l = ct.lu_l[op];
             T* t = lu + (I)ct.lu_t[op] * HY_P + ri;
             const T u = lu[(I)ct.lu_u[op] * HY_P + ri];
-            if (l < 0) { r_weak = r_weak || (l == -1 && ctl.stop_on_weak && s_abs(u) * 1.000001e3 < s_abs(*t)); *t = s_div(*t, u); }
+            if (l < 0) { r_weak = r_weak || (l == -1 && ctl.stop_on_weak && s_abs(u) * ctl.weak_mult < s_abs(*t)); *t = s_div(*t, u); }
             else *t = s_sub(*t, s_mul(u, lu[(I)l * HY_P + ri]));
           }
         }
@@ -257,6 +268,7 @@ __global__ void __launch_bounds__(256, 2) k_hyb(DevTables d, PlanTables p, CoopT
         else {
           r_nsol += 1;
           if (KIND == K_AC && ctl.ac_direct) r_act = false;  // linear system: one solve is the answer
+          if (r_nsol >= r_left) { r_act = false; r_stat = CST_CONV; }  // resume: this instance's own 100 iterations are used up
         }
       }
       if (q == 0) act_s[ri] = r_act ? 1 : 0;

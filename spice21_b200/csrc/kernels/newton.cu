@@ -172,7 +172,7 @@ __device__ int newton_solve(const DevTables& d, const PlanTables& p, const WorkT
       const T piv = lu[(size_t)__ldg(p.diag_slot + k) * S];
       if (s_is_zero(piv)) return ST_SINGULAR_;
       const int lb = __ldg(p.l_off + k), le = __ldg(p.l_off + k + 1);
-      const double pth = __ldg(p.piv_chk + k) ? s_abs(piv) * 1.000001e3 : INFINITY;  // pivots the fallback searches chose carry no threshold
+      const double pth = __ldg(p.piv_chk + k) ? s_abs(piv) * ctl.weak_mult : INFINITY;  // pivots the fallback searches chose carry no threshold
       for (int j = lb; j < le; j++) {
         T* a = lu + (size_t)__ldg(p.l_slot + j) * S;
         // pivot health: the reference, which searches its pivots anew in every factorisation, would not have taken this
@@ -235,6 +235,12 @@ __global__ void __launch_bounds__(128) k_dcop(DevTables d, PlanTables p, WorkTab
   const size_t inst = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (inst >= (size_t)ctl.B) return;
   int ns = 0, nl = 0;
+  if (ctl.resume) {  // continue the stopped instances only, each with what is left of its own iteration budget
+    if (o.status[inst] != ST_REPIVOT_) return;
+    const int left = ctl.max_iter - (o.iters[inst] - (o.iters_base ? o.iters_base[inst] : 0));
+    if (left <= 0) { o.status[inst] = ST_CONV_; return; }
+    ctl.max_iter = left;
+  }
   const int st = newton_solve<double, B4>(d, p, w, ctl, inst, 0.0, ctl.reltol, ctl.iabstol, true, &ns, &nl);
   o.status[inst] = st;
   o.iters[inst] += ns;
