@@ -66,6 +66,13 @@ int32_t s21_ckt_add_r(s21_ckt* c, const char* module, const char* name, const ch
 int32_t s21_ckt_add_c(s21_ckt* c, const char* module, const char* name, const char* p, const char* n, double cap);
 int32_t s21_ckt_add_i(s21_ckt* c, const char* module, const char* name, const char* p, const char* n, double dc);
 int32_t s21_ckt_add_v(s21_ckt* c, const char* module, const char* name, const char* p, const char* n, double dc, double acm);
+/* EXTENSION (the reference's Vsrc is DC / acm only, spice21.proto:29-35, comps/mod.rs:95-150): a voltage
+ * source whose transient value follows SPICE's PULSE (kind 1: v1 v2 td tr tf pw per; per = 0: a single pulse) or SIN (kind 2:
+ * vo va freq td theta). The operating point uses `dc` (give it the wave's value at t = 0). On the wire: Vsrc fields 6 (kind)
+ * and 7 (repeated double), ignored by the reference's decoder. Evaluated on the device at every time point (fixed-step and
+ * adaptive transients). */
+int32_t s21_ckt_add_v_wave(s21_ckt* c, const char* module, const char* name, const char* p, const char* n, double dc, double acm,
+                           int32_t kind, size_t n_params, const double* params);
 int32_t s21_ckt_add_d(s21_ckt* c, const char* module, const char* name, const char* p, const char* n, const char* model,
                       const char* params);
 int32_t s21_ckt_add_mos(s21_ckt* c, const char* module, const char* name, const char* model, const char* params, const char* d,

@@ -28,7 +28,7 @@ S21_OK, S21_CONVERGENCE_FAILED, S21_SINGULAR_MATRIX, S21_PIVOT_SEARCH_FAIL, S21_
 ABI_SYMBOLS = [
     "s21_last_error", "s21_free", "s21_cuda_device_count", "s21_op_bytes", "s21_tran_bytes", "s21_ac_bytes", "s21_ckt_from_proto",
     "s21_ckt_new", "s21_ckt_destroy", "s21_ckt_signal", "s21_ckt_add_r", "s21_ckt_add_c", "s21_ckt_add_i", "s21_ckt_add_v",
-    "s21_ckt_add_d", "s21_ckt_add_mos", "s21_ckt_add_x", "s21_ckt_def_module", "s21_ckt_define", "s21_ckt_elaborate",
+    "s21_ckt_add_d", "s21_ckt_add_v_wave", "s21_ckt_add_mos", "s21_ckt_add_x", "s21_ckt_def_module", "s21_ckt_define", "s21_ckt_elaborate",
     "s21_ckt_num_vars", "s21_ckt_var_name", "s21_ckt_var_kind", "s21_ckt_num_devices", "s21_ckt_stamp_map", "s21_batch_create",
     "s21_batch_destroy", "s21_batch_set_stream", "s21_batch_override", "s21_batch_sync_params", "s21_batch_reset", "s21_batch_dcop",
     "s21_batch_dcop_device", "s21_batch_read", "s21_tran_num_points", "s21_batch_tran", "s21_ac_freqs", "s21_batch_ac",
@@ -76,6 +76,7 @@ def lib():
             getattr(L, f).argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_double]
         L.s21_ckt_add_v.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_double, C.c_double]
         L.s21_ckt_add_d.argtypes = [C.c_void_p] + [C.c_char_p] * 6
+        L.s21_ckt_add_v_wave.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_double, C.c_double, C.c_int32, C.c_size_t, C.c_void_p]
         L.s21_ckt_add_mos.argtypes = [C.c_void_p] + [C.c_char_p] * 8
         L.s21_ckt_add_x.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p]
         L.s21_ckt_def_module.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p]
@@ -261,6 +262,14 @@ class Circuit:
 
     def i(self, name, p, n, dc, module=None):
         _check(lib().s21_ckt_add_i(self.h, _b(module) if module else None, _b(name), _b(p), _b(n), dc))
+
+    def v_wave(self, name, p, n, dc, kind, params, acm=0.0, module=None):
+        """Time-varying voltage source (extension, s21_ckt_add_v_wave): kind "pulse" (v1 v2 td tr tf pw per) or "sin"
+        (vo va freq td theta); `dc` is the operating-point value."""
+        w = np.ascontiguousarray(params, dtype=np.float64)
+        _check(lib().s21_ckt_add_v_wave(self.h, _b(module) if module else None, _b(name), _b(p), _b(n), dc, acm, {"pulse": 1, "sin": 2}[kind], len(w),
+                                        w.ctypes.data_as(C.c_void_p)))
+        return self
 
     def v(self, name, p, n, dc, acm=0.0, module=None):
         _check(lib().s21_ckt_add_v(self.h, _b(module) if module else None, _b(name), _b(p), _b(n), dc, acm))

@@ -198,6 +198,19 @@ int32_t s21_ckt_add_r(s21_ckt* c, const char* m, const char* name, const char* p
 int32_t s21_ckt_add_c(s21_ckt* c, const char* m, const char* name, const char* p, const char* n, double cap) { return add_two_term(c, m, CK_C, name, p, n, cap, 0.0); }
 int32_t s21_ckt_add_i(s21_ckt* c, const char* m, const char* name, const char* p, const char* n, double dc) { return add_two_term(c, m, CK_I, name, p, n, dc, 0.0); }
 int32_t s21_ckt_add_v(s21_ckt* c, const char* m, const char* name, const char* p, const char* n, double dc, double acm) { return add_two_term(c, m, CK_V, name, p, n, dc, acm); }
+int32_t s21_ckt_add_v_wave(s21_ckt* c, const char* module, const char* name, const char* p, const char* n, double dc, double acm, int32_t kind,
+                           size_t n_params, const double* params) {
+  S21_TRY
+  if (kind != SRC_PULSE && kind != SRC_SIN) throw S21Error(ST_INVALID, "source wave kind must be 1 (PULSE) or 2 (SIN)");
+  if (n_params > 7 || (n_params && !params)) throw S21Error(ST_INVALID, "a source wave takes at most 7 parameters");
+  CompSpec s;
+  s.kind = CK_V; s.name = nz(name); s.p = nz(p); s.n = nz(n); s.val = dc; s.acm = acm; s.wave_kind = kind;
+  for (size_t k = 0; k < n_params; k++) s.wave[k] = params[k];
+  if (kind == SRC_PULSE && (!(s.wave[3] > 0.0) || !(s.wave[4] > 0.0))) throw S21Error(ST_INVALID, "PULSE needs rise and fall times > 0");
+  comp_list(c, module).push_back(s);
+  return S21_OK;
+  S21_CATCH
+}
 int32_t s21_ckt_add_d(s21_ckt* c, const char* module, const char* name, const char* p, const char* n, const char* model, const char* params) {
   S21_TRY
   CompSpec s;

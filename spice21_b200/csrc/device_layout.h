@@ -26,7 +26,11 @@ enum { I_P = 0, I_N, I_NI };
 enum { IP_I = 0, IP_N };
 // ---- Vsrc (comps/mod.rs:95-150): itab [p, n, i, e_pi, e_ip, e_ni, e_in]; params v (OP), v (TRAN), acm.
 enum { V_P = 0, V_N, V_I, V_EPI, V_EIP, V_ENI, V_EIN, V_NI };
-enum { VP_V_OP = 0, VP_V_TRAN, VP_ACM, VP_N };
+// VP_WKIND / VP_W0..6: time-varying source (an extension — the reference's Vsrc is DC / acm only,
+// spice21.proto:29-35). kind 0 = none (the transient value is VP_V_TRAN, as in the reference), 1 = PULSE(v1 v2 td tr tf pw per),
+// 2 = SIN(vo va freq td theta); SPICE's definitions. The OP always uses VP_V_OP (the `dc` field).
+enum { VP_V_OP = 0, VP_V_TRAN, VP_ACM, VP_WKIND, VP_W0, VP_W1, VP_W2, VP_W3, VP_W4, VP_W5, VP_W6, VP_N };
+enum { SRC_NONE = 0, SRC_PULSE = 1, SRC_SIN = 2 };
 // ---- Diode (comps/diode.rs:217-355): itab [p, n, r, e_pp, e_pr, e_rp, e_rr, e_nr, e_rn, e_nn].
 enum { D_P = 0, D_N, D_R, D_EPP, D_EPR, D_ERP, D_ERR, D_ENR, D_ERN, D_ENN, D_NI };
 enum { DP_VTE = 0, DP_VCRIT, DP_ISAT, DP_GSPR, DP_CZ, DP_CZ2, DP_DEPTH, DP_F1, DP_F3, DP_BV, DP_HASBV, DP_TT, DP_VJ, DP_M, DP_N };

@@ -37,6 +37,8 @@ struct CompSpec {
   std::string name;
   std::string p, n;            // two-terminal devices ("" = ground)
   double val = 0.0, acm = 0.0; // g | c | dc ; acm for V
+  int wave_kind = 0;           // V only (extension, device_layout.h SRC_*): 0 none, 1 PULSE, 2 SIN
+  double wave[7] = {0, 0, 0, 0, 0, 0, 0};
   std::string model, params;   // D, MOS
   std::string d, g, s, b;      // MOS ports
   std::string module;          // X
@@ -73,12 +75,18 @@ namespace pb {
 
 inline void two_term(PbReader r, CompSpec* c, bool has_acm) {  // Resistor/Capacitor/Isrc/Vsrc (spice21.proto:8-36)
   uint32_t f, w;
+  int nwave = 0;
   while (r.next(&f, &w)) {
     if (f == 1 && w == 2) c->name = r.str();
     else if (f == 2 && w == 2) c->p = r.str();
     else if (f == 3 && w == 2) c->n = r.str();
     else if (f == 4 && w == 1) c->val = r.fixed64_double();
     else if (f == 5 && w == 1 && has_acm) c->acm = r.fixed64_double();
+    // extension fields of Vsrc (not in the reference's spice21.proto:29-35, which is DC / acm only): 6 = wave kind (varint),
+    // 7 = wave parameters (repeated double, packed or not)
+    else if (f == 6 && w == 0 && has_acm) c->wave_kind = (int)r.varint();
+    else if (f == 7 && w == 1 && has_acm) { const double v = r.fixed64_double(); if (nwave < 7) c->wave[nwave++] = v; }
+    else if (f == 7 && w == 2 && has_acm) { PbReader pr = r.sub(); while (!pr.done()) { const double v = pr.fixed64_double(); if (nwave < 7) c->wave[nwave++] = v; } }
     else r.skip(w);
   }
 }

@@ -140,13 +140,16 @@ class Flattener {
     pp(d)[RP_G_OP] = g_op; pp(d)[RP_G_TRAN] = g_tran;
     d.is_ic = is_ic;
   }
-  void add_vsrc(const std::string& path, int p, int n, int ivar, double v_op, double v_tran, double acm, bool is_ic) {
+  void add_vsrc(const std::string& path, int p, int n, int ivar, double v_op, double v_tran, double acm, bool is_ic, int wave_kind = 0,
+                const double* wave = nullptr) {
     FlatDev& d = begin_dev(DT_V, path, V_NI, VP_N, 0, 5);
     int* t = it(d);
     t[V_P] = p; t[V_N] = n; t[V_I] = ivar;
     t[V_EPI] = element(p, ivar); t[V_EIP] = element(ivar, p); t[V_ENI] = element(n, ivar); t[V_EIN] = element(ivar, n);  // comps/mod.rs:127-132
     d.created = {t[V_EPI], t[V_EIP], t[V_ENI], t[V_EIN]};
     pp(d)[VP_V_OP] = v_op; pp(d)[VP_V_TRAN] = v_tran; pp(d)[VP_ACM] = acm;
+    pp(d)[VP_WKIND] = (double)wave_kind;
+    for (int k = 0; k < 7; k++) pp(d)[VP_W0 + k] = (wave_kind && wave) ? wave[k] : 0.0;
     d.is_ic = is_ic;
   }
 
@@ -175,7 +178,7 @@ class Flattener {
         bool top = path_.empty();
         int p = node(c.p, top, ns), n = node(c.n, top, ns);
         int ivar = new_var(joined(c.name), 1);
-        add_vsrc(joined(c.name), p, n, ivar, c.val, c.val, c.acm, false);
+        add_vsrc(joined(c.name), p, n, ivar, c.val, c.val, c.acm, false, c.wave_kind, c.wave);
         break;
       }
       case CK_D: diode(c, ns); break;

@@ -216,7 +216,7 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
   for (int k = 0; k < Q * TM_LPI + 8; k++) o << (k ? "," : "") << (k < N ? P.col_i2e[(size_t)k] * PSV : 0);
   o << "};\n";
   o << "struct JBase {\n  const double* pval; size_t pinst; double* sop; double* sguess; const double* X; double* S;\n"
-       "  int mode" << (XP ? ", j" : "") << "; double dt, gmin, omega;\n"
+       "  int mode" << (XP ? ", j" : "") << "; double dt, gmin, omega, time;\n"
        "  __device__ __forceinline__ double volt(int var) const { return var < 0 ? 0.0 : X[var * PS]; }\n};\n";
   // the Env base of the branch-free evaluation (kernels/devices.cuh math hooks): fast paths only, exceptions deferred
   o << "struct JFast : JBase {\n  bool dbad;\n"
@@ -337,10 +337,10 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
   const char* ebi = WP ? "ri" : "ei";  // the instance a lane evaluates devices for
   o << "  JBase eb; eb.pval = pval; eb.pinst = (size_t)i0 + (size_t)" << ebi << "; eb.sop = sop + " << ebi << "; eb.sguess = sguess + " << ebi
     << "; eb.X = X + " << ebi << "; eb.S = S + " << ebi << ";" << (XP ? " eb.j = j;" : "") << "\n"
-       "  eb.mode = " << (tran ? "AN_TRAN" : "AN_OP") << "; eb.dt = dt; eb.gmin = gmin; eb.omega = 0.0;\n";  // literal: the other mode's code is dropped
+       "  eb.mode = " << (tran ? "AN_TRAN" : "AN_OP") << "; eb.dt = dt; eb.gmin = gmin; eb.omega = 0.0; eb.time = " << (tran ? "dt" : "0.0") << ";\n";  // literal: the other mode's code is dropped
   if (prof) o << "  __shared__ long long prof_s[32];\n  if (tid < 32) prof_s[tid] = 0;\n  __syncthreads();\n  long long t_last = clock64();\n";
   o << "  const int n_points = " << (tran ? "T_points" : "2") << ";\n"
-       "  for (int tp = 1; tp < n_points; tp++) {\n"
+       "  for (int tp = 1; tp < n_points; tp++" << (tran ? ", eb.time += dt" : "") << ") {\n"
        "    bool r_act = rvalid && r_stat == 0;\n    bool r_dxok = true;\n"
        << (WP ? "    __syncwarp();\n" : "    if (j == 0 && rin) act_s[ri] = r_act ? 1 : 0;\n    __syncthreads();\n");
   for (int q = 0; q < Q; q++) o << "    double xp" << q << " = (v" << q << " && rin) ? X[xo" << q << " + ri] : 0.0;\n";

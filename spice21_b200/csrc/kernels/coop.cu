@@ -147,7 +147,8 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
   double omega = 0.0;
   if constexpr (KIND == K_AC) omega = valid ? ctl.omega[i0 + li] : 0.0;
 
-  for (int tp = 1; tp < n_points; tp++) {
+  double tnow = KIND == K_TRAN ? ctl.dt : 0.0;  // analysis.rs:552-569: t starts at tstep and accumulates tstep
+  for (int tp = 1; tp < n_points; tp++, tnow += ctl.dt) {
     if (tid < gi) { act[tid] = (tid < ni && stat[tid] == CST_OK && left[tid] > 0) ? 1 : 0; dxok[tid] = 1; }
     __syncthreads();
     const int max_it = real_kind ? min(TolC<T>::max_iter, ctl.max_iter) : TolC<T>::max_iter;
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
           e.sop = sop + so; e.sguess = sguess + so; e.sstride = ss;
           e.x = x + col; e.xstride = ws;
           e.S = S + (IS)ct.stage_off[dev] * wS + colS; e.Sstride = wS;
-          e.mode = ctl.mode; e.dt = ctl.dt; e.gmin = ctl.gmin; e.omega = omega;
+          e.mode = ctl.mode; e.dt = ctl.dt; e.gmin = ctl.gmin; e.omega = omega; e.time = tnow;
           load_one<T, B4>(d.type[dev], e, (d.par_direct && d.par_direct[dev]) ? d.pval + d.par_off[dev] : nullptr);
         }
       }

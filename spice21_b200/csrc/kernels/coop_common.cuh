@@ -53,6 +53,7 @@ struct EnvS {  // staged Env (see devices.cuh): stamps go to this device's priva
   IS Sstride;       // the staging area may live elsewhere than x (cooperative kernel, mixed workspace: x on chip, staging in HBM)
   int mode;
   double dt, gmin, omega;
+  double time;      // transient: the time point being solved (time-varying sources)
   __device__ __forceinline__ int node(int k) const { return it[k]; }
   __device__ __forceinline__ double par(int k) const {
     const int c = pc[k];

@@ -82,12 +82,34 @@ template <class Env> __device__ __forceinline__ void load_isrc(Env& e) {
   e.add_b_at(I_N, -i);
 }
 // ---------------------------------------------------------------- Vsrc (comps/mod.rs:133-138)
+// Time-varying source value at time t (extension, device_layout.h VP_WKIND): SPICE's PULSE and SIN.
+template <class Env> __device__ __noinline__ double source_wave(Env& e, int kind, double t) {
+  const double w0 = e.par(VP_W0), w1 = e.par(VP_W1), w2 = e.par(VP_W2), w3 = e.par(VP_W3), w4 = e.par(VP_W4), w5 = e.par(VP_W5), w6 = e.par(VP_W6);
+  if (kind == SRC_PULSE) {  // v1 v2 td tr tf pw per
+    double tt = t - w2;
+    if (tt < 0.0) return w0;
+    if (w6 > 0.0) tt -= w6 * floor(tt / w6);
+    if (tt < w3) return w0 + (w1 - w0) * (tt / w3);
+    if (tt < w3 + w5) return w1;
+    if (tt < w3 + w5 + w4) return w1 + (w0 - w1) * ((tt - w3 - w5) / w4);
+    return w0;
+  }
+  // SIN: vo va freq td theta
+  const double tt = t - w3;
+  if (tt < 0.0) return w0;
+  return w0 + w1 * exp(-tt * w4) * sin(6.283185307179586476925286766559 * w2 * tt);
+}
 template <class Env> __device__ __forceinline__ void load_vsrc(Env& e) {
   e.add_g_at(V_EPI, 1.0);
   e.add_g_at(V_EIP, 1.0);
   e.add_g_at(V_ENI, -1.0);
   e.add_g_at(V_EIN, -1.0);
-  e.add_b_at(V_I, e.par(e.mode == AN_OP ? VP_V_OP : VP_V_TRAN));
+  double v = e.par(e.mode == AN_OP ? VP_V_OP : VP_V_TRAN);
+  if (e.mode == AN_TRAN) {
+    const int kind = (int)e.par(VP_WKIND);
+    if (kind != SRC_NONE) v = source_wave(e, kind, e.time);
+  }
+  e.add_b_at(V_I, v);
 }
 // ---------------------------------------------------------------- Diode (comps/diode.rs:228-245, 279-355)
 template <class Env> __device__ __forceinline__ double diode_limit(Env& e, double vd, double vold) {

@@ -70,6 +70,7 @@ struct SolveCtl {
   int B;             // instances (threads)
   int mode;          // AnMode
   double gmin, dt;
+  double time = 0.0;       // direct kernels: the time point being solved (they carry it here; the others keep it in their time loop)
   double reltol, iabstol;  // real solve: |dx| <= reltol (absolute!) and |res| <= iabstol (analysis.rs:331-345)
   const double* omega;     // [B] AC only
   size_t par_inst_stride;  // 1: parameter/state instance == workspace instance; 0: all columns use instance 0 (AC sweep)

@@ -45,7 +45,8 @@ __global__ void __launch_bounds__(256, B4 ? 1 : 2) k_grid(DevTables d, PlanTable
   }
   grid.sync();
   const int n_points = KIND == K_TRAN ? T_points : 2;
-  for (int tp = 1; tp < n_points; tp++) {
+  double tnow = KIND == K_TRAN ? ctl.dt : 0.0;  // analysis.rs:552-569: t starts at tstep and accumulates tstep
+  for (int tp = 1; tp < n_points; tp++, tnow += ctl.dt) {
     if (tid == 0) { gc->act = gc->stat == CST_OK ? 1 : 0; gc->dxok = 1; }
     grid.sync();
     const int max_it = min(TolC<double>::max_iter, ctl.max_iter) - used;
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(256, B4 ? 1 : 2) k_grid(DevTables d, PlanTable
         e.sop = sop + so; e.sguess = sguess + so; e.sstride = 1;
         e.x = x; e.xstride = 1; e.Sstride = 1;
         e.S = S + (size_t)ct.stage_off[dev];
-        e.mode = ctl.mode; e.dt = ctl.dt; e.gmin = ctl.gmin; e.omega = 0.0;
+        e.mode = ctl.mode; e.dt = ctl.dt; e.gmin = ctl.gmin; e.omega = 0.0; e.time = tnow;
         load_one<double, B4>(d.type[dev], e, (d.par_direct && d.par_direct[dev]) ? d.pval + d.par_off[dev] : nullptr);
       }
       if (tid == 0) { gc->resok = 1; gc->sing = 0; gc->weak = 0; gc->maxabs = 0ull; }

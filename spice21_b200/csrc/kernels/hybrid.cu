@@ -122,7 +122,8 @@ __global__ void __launch_bounds__(256, 2) k_hyb(DevTables d, PlanTables p, CoopT
   double omega = 0.0;
   if constexpr (KIND == K_AC) omega = evalid ? ctl.omega[i0 + ei] : 0.0;
 
-  for (int tp = 1; tp < n_points; tp++) {
+  double tnow = KIND == K_TRAN ? ctl.dt : 0.0;  // analysis.rs:552-569: t starts at tstep and accumulates tstep
+  for (int tp = 1; tp < n_points; tp++, tnow += ctl.dt) {
     bool r_act = rvalid && r_stat == CST_OK && !r_skip;
     bool r_dxok = true;
     if (q == 0) act_s[ri] = r_act ? 1 : 0;
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(256, 2) k_hyb(DevTables d, PlanTables p, CoopT
           e.sop = sop + so; e.sguess = sguess + so; e.sstride = HY_P;
           e.x = x + ei; e.xstride = HY_P; e.Sstride = HY_P;
           e.S = S + (I)ct.stage_off[dev] * HY_P + ei;
-          e.mode = ctl.mode; e.dt = ctl.dt; e.gmin = ctl.gmin; e.omega = omega;
+          e.mode = ctl.mode; e.dt = ctl.dt; e.gmin = ctl.gmin; e.omega = omega; e.time = tnow;
           load_one<T, B4>(d.type[dev], e, (d.par_direct && d.par_direct[dev]) ? d.pval + d.par_off[dev] : nullptr);
         }
       }

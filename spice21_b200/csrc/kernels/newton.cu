@@ -43,6 +43,7 @@ struct Env {
   size_t stride, w;
   int mode;
   double dt, gmin, omega;
+  double time;  // transient: the time point being solved (time-varying sources)
 
   __device__ __forceinline__ int node(int k) const { return __ldg(it + k); }
   __device__ __forceinline__ double par(int k) const {
@@ -139,7 +140,7 @@ __device__ int newton_solve(const DevTables& d, const PlanTables& p, const WorkT
   e.pval = d.pval;
   e.sstride = wk.st_stride; e.sinst = pinst; e.pinst = pinst;
   e.x = wk.x; e.lu = wk.lu; e.rhs = wk.rhs; e.stride = S; e.w = inst;
-  e.mode = ctl.mode; e.dt = ctl.dt; e.gmin = ctl.gmin; e.omega = omega;
+  e.mode = ctl.mode; e.dt = ctl.dt; e.gmin = ctl.gmin; e.omega = omega; e.time = ctl.time;
   const int N = p.N;
   bool dx_ok = true;  // dx = 0 before the first iteration
   const int max_it = std::is_same<T, double>::value ? min(Tol<T>::max_iter, ctl.max_iter) : Tol<T>::max_iter;
@@ -256,7 +257,8 @@ __global__ void __launch_bounds__(128) k_tran(DevTables d, PlanTables p, WorkTab
   int st = o.status[inst];  // status of the OP solve
   for (int s = 0; s < n_save; s++) wave[(size_t)s * B + inst] = w.x[(size_t)__ldg(save_vars + s) * w.stride + inst];
   int ns = 0, nl = 0;
-  for (int tp = 1; tp < T; tp++) {
+  ctl.time = ctl.dt;  // analysis.rs:552-569: t starts at tstep and accumulates tstep (the host's time axis is built the same way)
+  for (int tp = 1; tp < T; tp++, ctl.time += ctl.dt) {
     if (st == ST_OK_) st = newton_solve<double, B4>(d, p, w, ctl, inst, 0.0, ctl.reltol, ctl.iabstol, true, &ns, &nl);
     for (int s = 0; s < n_save; s++) {
       const double v = st == ST_OK_ ? w.x[(size_t)__ldg(save_vars + s) * w.stride + inst] : __longlong_as_double(0x7ff8000000000000LL);
@@ -307,6 +309,7 @@ __global__ void __launch_bounds__(128) k_tran_adaptive(DevTables d, PlanTables p
     for (int k = 0; k < d.n_state; k++) a.st_save[(size_t)k * SS + inst] = w.st_op[(size_t)k * SS + inst];
     SolveCtl c = ctl;
     c.dt = h;
+    c.time = t + h;
     int rc = newton_solve<double, B4>(d, p, w, c, inst, 0.0, ctl.reltol, ctl.iabstol, true, &ns, &nl);  // a weak frozen pivot counts as a failed attempt
     double ratio = 0.0;
     if (rc == ST_OK_ && nacc >= 1) {
@@ -379,6 +382,7 @@ __global__ void k_probe(DevTables d, WorkTables<T> w, SolveCtl ctl, int n_elems,
   e.sstride = w.st_stride; e.sinst = pinst; e.pinst = pinst;
   e.x = w.x; e.lu = w.lu; e.rhs = w.rhs; e.stride = w.stride; e.w = inst;
   e.mode = ctl.mode; e.dt = ctl.dt; e.gmin = ctl.gmin; e.omega = ctl.omega ? ctl.omega[inst] : 0.0;
+  e.time = ctl.mode == AN_TRAN ? ctl.dt : 0.0;  // the transient plan is taken at the first time point
   for (int k = 0; k < n_elems; k++) w.lu[(size_t)k * w.stride + inst] = Scalar<T>::zero();
   for (int k = 0; k < N; k++) w.rhs[(size_t)k * w.stride + inst] = Scalar<T>::zero();
   load_sweep<true>(d, e, w.st_op, w.st_guess);

