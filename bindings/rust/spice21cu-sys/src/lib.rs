@@ -42,6 +42,7 @@ extern "C" {
     pub fn s21_ckt_add_c(c: *mut s21_ckt, module: *const c_char, name: *const c_char, p: *const c_char, n: *const c_char, cap: f64) -> i32;
     pub fn s21_ckt_add_i(c: *mut s21_ckt, module: *const c_char, name: *const c_char, p: *const c_char, n: *const c_char, dc: f64) -> i32;
     pub fn s21_ckt_add_v(c: *mut s21_ckt, module: *const c_char, name: *const c_char, p: *const c_char, n: *const c_char, dc: f64, acm: f64) -> i32;
+    pub fn s21_ckt_add_v_wave(c: *mut s21_ckt, module: *const c_char, name: *const c_char, p: *const c_char, n: *const c_char, dc: f64, acm: f64, kind: i32, n_params: usize, params: *const f64) -> i32;
     pub fn s21_ckt_add_d(c: *mut s21_ckt, module: *const c_char, name: *const c_char, p: *const c_char, n: *const c_char, model: *const c_char, params: *const c_char) -> i32;
     pub fn s21_ckt_add_mos(c: *mut s21_ckt, module: *const c_char, name: *const c_char, model: *const c_char, params: *const c_char, d: *const c_char, g: *const c_char, s: *const c_char, b: *const c_char) -> i32;
     pub fn s21_ckt_add_x(c: *mut s21_ckt, module: *const c_char, name: *const c_char, module_name: *const c_char, n_ports: usize, port_names: *const *const c_char, port_nodes: *const *const c_char) -> i32;

@@ -245,10 +245,29 @@ inline void def(PbReader r, CktSpec* cs) {
       case 1: { ModuleSpec m = module_def(s); cs->modules[m.name] = m; break; }
       case 2: { ParamBag b; std::string n = wrapped_params(s, 1, diode_model_fields(), &b); cs->diode_models[n] = b; break; }
       case 3: { ParamBag b; std::string n = wrapped_params(s, 1, diode_inst_fields(), &b); cs->diode_insts[n] = b; break; }
-      case 4: {  // Bsim4Model: only mos_type (=1) and name (=900) exist on the wire (bsim4.proto:45-50, 930)
+      case 4: {  // Bsim4Model: only mos_type (=1) and name (=900) exist on the reference's wire (bsim4.proto:45-50, 930)
+        // EXTENSION: field 901, repeated { string name = 1; double value = 2 } — the model card's parameters by
+        // their `Bsim4ModelSpecs` field names (the 876 commented-out fields of bsim4.proto, carried as a list instead of one
+        // numbered field each). The reference's decoder skips it; here it fills the same bag s21_ckt_define("bsim4model") does.
         MosModelSpec m;
-        ParamBag dummy;
-        std::string n = wrapped_params(s, 900, {}, &dummy, &m, 1, 0);
+        std::string n;
+        uint32_t ff, ww;
+        while (s.next(&ff, &ww)) {
+          if (ff == 900 && ww == 2) n = s.str();
+          else if (ff == 1 && ww == 0) m.mos_type = (int)s.varint();
+          else if (ff == 901 && ww == 2) {
+            PbReader q = s.sub();
+            std::string key;
+            double val = 0.0;
+            uint32_t f3, w3;
+            while (q.next(&f3, &w3)) {
+              if (f3 == 1 && w3 == 2) key = q.str();
+              else if (f3 == 2 && w3 == 1) val = q.fixed64_double();
+              else q.skip(w3);
+            }
+            if (!key.empty()) m.p.kv[key] = val;
+          } else s.skip(ww);
+        }
         cs->bsim4_models[n] = m;
         break;
       }

@@ -101,15 +101,24 @@ def _build():
     _wrapped(m, [("rbdb", 19), ("rbsb", 20), ("rbpb", 21), ("rbps", 22), ("rbpd", 23), ("delvto", 24), ("xgw", 25), ("ngcon", 26)])
     _wrapped(m, [("trnqsmod", 27), ("acnqsmod", 28), ("rbodymod", 29), ("rgatemod", 30), ("geomod", 31)], _UV)
     _field(m, "name", 40, _F.TYPE_STRING)
+    m = _msg(fd, "Bsim4ModelParam")  # extension: one model-card parameter by its Bsim4ModelSpecs field name
+    _field(m, "name", 1, _F.TYPE_STRING)
+    _field(m, "value", 2, _F.TYPE_DOUBLE)
     m = _msg(fd, "Bsim4Model")
     _field(m, "mos_type", 1, _F.TYPE_ENUM, ".spice21.MosType")
     _field(m, "name", 900, _F.TYPE_STRING)
+    # extension field (the reference's message stops at `name`; its 876 model fields are commented out, bsim4.proto:51-929)
+    _field(m, "params", 901, _F.TYPE_MESSAGE, ".spice21.Bsim4ModelParam", repeated=True)
 
     # ---- spice21.proto
     _two_term(fd, "Resistor", "g")
     _two_term(fd, "Capacitor", "c")
     _two_term(fd, "Isrc", "dc")
-    _two_term(fd, "Vsrc", "dc", extra=(("acm", 5),))
+    m = _two_term(fd, "Vsrc", "dc", extra=(("acm", 5),))
+    # extension fields (not in the reference's spice21.proto:29-35; its decoder skips unknown fields): a time-varying source,
+    # wave_kind 1 = PULSE(v1 v2 td tr tf pw per), 2 = SIN(vo va freq td theta) — include/spice21cu.h s21_ckt_add_v_wave
+    _field(m, "wave_kind", 6, _F.TYPE_INT32)
+    _field(m, "wave", 7, _F.TYPE_DOUBLE, repeated=True)
     m = _msg(fd, "TwoTerms")
     _field(m, "p", 2, _F.TYPE_STRING)
     _field(m, "n", 3, _F.TYPE_STRING)
@@ -196,7 +205,7 @@ _pool = descriptor_pool.Default()
 _file = _pool.Add(_build()) if hasattr(_pool, "Add") else None
 if _file is None:
     _pool.AddSerializedFile(_build().SerializeToString())
-_NAMES = ["MosPorts", "Mos", "Mos1InstParams", "Mos1Model", "Bsim4InstParams", "Bsim4Model", "Resistor", "Capacitor", "Isrc", "Vsrc",
+_NAMES = ["MosPorts", "Mos", "Mos1InstParams", "Mos1Model", "Bsim4InstParams", "Bsim4ModelParam", "Bsim4Model", "Resistor", "Capacitor", "Isrc", "Vsrc",
           "TwoTerms", "DiodeModel", "DiodeInstParams", "Diode", "Instance", "Module", "ModuleInstance", "Def", "Defs", "Circuit",
           "SimOptions", "Op", "OpResult", "TranOptions", "Tran", "DoubleArray", "TranResult", "ComplexNum", "ComplexArray", "AcOptions",
           "Ac", "AcResult"]

@@ -36,8 +36,10 @@ class _Scope:
         self.comps.append(("I", name, str(p), str(n), float(dc)))
         return self
 
-    def V(self, name, p, n, dc, acm=0.0):
-        self.comps.append(("V", name, str(p), str(n), float(dc), float(acm)))
+    def V(self, name, p, n, dc, acm=0.0, wave=None):
+        """wave = ("pulse", [v1, v2, td, tr, tf, pw, per]) | ("sin", [vo, va, freq, td, theta]): time-varying source (an
+        extension of the product; the reference and the oracle have DC / acm sources only)."""
+        self.comps.append(("V", name, str(p), str(n), float(dc), float(acm)) + ((wave[0], [float(v) for v in wave[1]]) if wave else ()))
         return self
 
     def D(self, name, p, n, model, params):
@@ -122,6 +124,8 @@ class Ckt(_Scope):
         if k == "I":
             return P.Instance(i=P.Isrc(name=c[1], p=c[2], n=c[3], dc=c[4]))
         if k == "V":
+            if len(c) > 6:
+                return P.Instance(v=P.Vsrc(name=c[1], p=c[2], n=c[3], dc=c[4], acm=c[5], wave_kind={"pulse": 1, "sin": 2}[c[6]], wave=c[7]))
             return P.Instance(v=P.Vsrc(name=c[1], p=c[2], n=c[3], dc=c[4], acm=c[5]))
         if k == "D":
             return P.Instance(d=P.Diode(name=c[1], p=c[2], n=c[3], model=c[4], params=c[5]))
@@ -143,8 +147,11 @@ class Ckt(_Scope):
             msg = cls(name=name)
             if kind in ("mos1model", "bsim4model"):
                 msg.mos_type = t
-            if kind == "bsim4model" and p:
-                raise ValueError("Bsim4Model carries only mos_type on the wire (bsim4.proto:45-50)")
+            if kind == "bsim4model":  # the reference's message carries only mos_type (bsim4.proto:45-50): card values ride in the
+                for k, v in p.items():   # product's extension field 901 (repeated name / value), which the reference would skip
+                    msg.params.append(P.Bsim4ModelParam(name=k, value=float(v)))
+                ck.defs.append(P.Def(**{kind: msg}))
+                continue
             for k, v in p.items():
                 fld = msg.DESCRIPTOR.fields_by_name[k]
                 sub = getattr(msg, k)
@@ -171,6 +178,8 @@ class Ckt(_Scope):
             ck.c(c[1], c[2], c[3], c[4], module=module)
         elif k == "I":
             ck.i(c[1], c[2], c[3], c[4], module=module)
+        elif k == "V" and len(c) > 6:
+            ck.v_wave(c[1], c[2], c[3], c[4], c[6], c[7], acm=c[5], module=module)
         elif k == "V":
             ck.v(c[1], c[2], c[3], c[4], c[5], module=module)
         elif k == "D":

@@ -278,3 +278,24 @@ def test_specialised_kernel_sources_compile(s21, oracle, shape):
         o = oracle.Circuit(ck.to_text()).structure()
         with pytest.raises(s21.Spice21Error):
             ck.to_s21().elaborate().jit_source(o["a0"], mode=0, shape=1)
+
+
+def test_wire_extensions_decode_like_the_builder(s21):
+    """The two wire-format extensions of SURVEY §8 f2 — Vsrc fields 6 / 7 (time-varying source) and Bsim4Model field 901 (model
+    card parameters by name) — decode into the same elaborated circuit as the C-ABI builder calls: same variables, same stamp
+    map (the card's rgatemod = 1 adds the internal gate node), and a message without them still decodes as before."""
+    def build(wave, card):
+        c = Ckt().define("bsim4model", "n", 0, **card).define("bsim4inst", "i", l=1e-6, w=4e-6)
+        c.M("mn", "n", "i", d="d", g="g", s=GND, b=GND).V("vd", "d", GND, 1.0).V("vg", "g", GND, 0.8, wave=wave)
+        return c
+
+    full = build(("pulse", [0.0, 1.0, 1e-9, 1e-10, 1e-10, 1e-9, 4e-9]), {"mobmod": 1, "rgatemod": 1, "toxe": 2e-9, "toxp": 2e-9})
+    a, b = full.to_s21().elaborate(), full.to_s21(via_proto=True).elaborate()
+    assert a.names == b.names and a.n_vars == 5
+    ma, mb = a.stamp_map(), b.stamp_map()
+    assert all(np.array_equal(x, y) for x, y in zip(ma, mb))
+    plain = build(None, {})
+    p1, p2 = plain.to_s21().elaborate(), plain.to_s21(via_proto=True).elaborate()
+    assert p1.names == p2.names and p1.n_vars == 4
+    raw = full.to_proto().SerializeToString()
+    assert b"rgatemod" in raw and len(raw) > len(plain.to_proto().SerializeToString())
