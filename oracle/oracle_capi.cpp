@@ -428,6 +428,15 @@ int orc_st_a0(void* s, double* out, int cap) {
 }
 void orc_st_free(void* s) { delete (Structure*)s; }
 
+#if defined(ORC_WITH_BSIM4) && defined(S21_B4_COUNT)
+// instrumented build only (make liboracle_count.so; scripts/b4_opcount.py): executed operations of the Bsim4 evaluation
+void orc_b4_counts(unsigned long long* out6, int reset) {
+  auto& c = s21::b4e::b4_counts();
+  out6[0] = c.evals; out6[1] = c.div; out6[2] = c.div_special; out6[3] = c.exp; out6[4] = c.log; out6[5] = c.sqrt;
+  if (reset) c = {0, 0, 0, 0, 0, 0};
+}
+#endif
+
 // Factorise an arbitrary matrix with the restated sparse21 and report the pivot order and the L+U pattern
 // (internal coordinates, creation order). width 1 = real vals[nnz], 2 = complex vals[nnz][2].
 // Returns the status of lu_factorize (0 OK / 2 singular / 3 pivot fail); outputs sized by the caller:

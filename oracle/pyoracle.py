@@ -26,7 +26,7 @@ def build(force=False):
 def lib():
     global _LIB
     if _LIB is None:
-        so = os.path.join(_HERE, "liboracle.so")
+        so = os.environ.get("ORC_LIB") or os.path.join(_HERE, "liboracle.so")  # ORC_LIB: an instrumented build (oracle/Makefile)
         if not os.path.exists(so):
             build()
         L = C.CDLL(so)

@@ -43,6 +43,22 @@ static __device__ __noinline__ double b4_ddiv_ool(double a, double b) { return _
 #endif
 #if defined(__CUDA_ARCH__) && defined(S21_B4_NIDIV)
 #define B4_DIV(a, b) ::s21::b4e::b4_ddiv_ool((double)(a), (double)(b))
+#elif !defined(__CUDACC__) && defined(S21_B4_COUNT)
+// host-only instrumentation (scripts/b4_opcount.py): executed divisions / exp / log / sqrt per evaluation, and how many
+// divisions leave the range in which the division fast path is exact (zero, subnormal, huge or non-finite operands / results)
+struct B4Counts { unsigned long long evals, div, div_special, exp, log, sqrt; };
+inline B4Counts& b4_counts() { static B4Counts c = {0, 0, 0, 0, 0, 0}; return c; }
+inline double b4_count_div(double a, double b) {
+  B4Counts& c = b4_counts();
+  c.div++;
+  const double q = a / b, ab = fabs(b), aq = fabs(q), aa = fabs(a);
+  if (!(ab >= 1e-290 && ab <= 1e290) || !(aa <= 1e290) || (aa != 0.0 && aa < 1e-290) || !(aq <= 1e290) || (aq != 0.0 && aq < 1e-290)) c.div_special++;
+  return q;
+}
+inline double exp(double x) { b4_counts().exp++; return ::exp(x); }
+inline double log(double x) { b4_counts().log++; return ::log(x); }
+inline double sqrt(double x) { b4_counts().sqrt++; return ::sqrt(x); }
+#define B4_DIV(a, b) ::s21::b4e::b4_count_div((double)(a), (double)(b))
 #else
 #define B4_DIV(a, b) ((a) / (b))
 #endif
