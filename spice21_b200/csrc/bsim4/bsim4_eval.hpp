@@ -41,8 +41,25 @@ namespace b4e {
 #if defined(__CUDACC__) && defined(S21_B4_NIDIV)
 static __device__ __noinline__ double b4_ddiv_ool(double a, double b) { return __ddiv_rn(a, b); }  // IEEE quotient
 #endif
+//   * -DS21_B4_RCPDIV: a / b as a * rcp(b), rcp = the hardware seed (MUFU.RCP64H) plus one cubic Newton step (3 DFMA):
+//     6 instructions and no control flow against the 16 + an out-of-line slow path of the IEEE quotient, and — because the
+//     reciprocal is a pure function of b — the compiler shares it between all divisions by one denominator. The quotient
+//     is then within ~1.5 ulp of a / b instead of correctly rounded (far inside the 1e-9 / reltol parity bounds; the host
+//     build and the oracle keep the IEEE quotient). Counted on the host (scripts/b4_opcount.py): 235 divisions are executed
+//     per evaluation and none has an operand or result outside the range in which the seed + Newton step is valid.
+#if defined(__CUDACC__) && defined(S21_B4_RCPDIV)
+__device__ __forceinline__ double b4_rcp(double b) {
+  double r0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(b));  // not volatile: identical reciprocals are merged
+  double e = __fma_rn(-b, r0, 1.0);
+  e = __fma_rn(e, e, e);
+  return __fma_rn(r0, e, r0);
+}
+#endif
 #if defined(__CUDA_ARCH__) && defined(S21_B4_NIDIV)
 #define B4_DIV(a, b) ::s21::b4e::b4_ddiv_ool((double)(a), (double)(b))
+#elif defined(__CUDA_ARCH__) && defined(S21_B4_RCPDIV)
+#define B4_DIV(a, b) ((double)(a) * ::s21::b4e::b4_rcp((double)(b)))
 #elif !defined(__CUDACC__) && defined(S21_B4_COUNT)
 // host-only instrumentation (scripts/b4_opcount.py): executed divisions / exp / log / sqrt per evaluation, and how many
 // divisions leave the range in which the division fast path is exact (zero, subnormal, huge or non-finite operands / results)

@@ -720,6 +720,7 @@ class Batch {
     if (rc) throw S21Error(ST_CUDA, std::string("tran kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
     S21_CUDA(cudaEventRecord(ev1_, stream_)); ev_pair_ = true;
     phase("time loop kernel");
+    if (info && last_kernel_ == "grid") grid_phase_report();
     last_plan_ = &tran_plan_;
     if (wave) {
       hwave_.alloc((size_t)T * n_save * Bs_);
@@ -972,6 +973,16 @@ class Batch {
   DBuf<int> d_type_, d_ioff_, d_poff_, d_soff_, d_itab_raw_, d_pcode_, d_pdirect_, d_save_;
   DBuf<double> d_pval_, x_, rhs_, c_, lu_, st_op_, st_guess_, d_wave_, d_omega_, d_rows_;
   DBuf<GridCtl> d_gctl_;
+  void grid_phase_report() {  // S21_PLAN_INFO: where the grid-wide kernel's launch went (GridCtl::phase_ns)
+    GridCtl h;
+    if (cudaMemcpy(&h, d_gctl_.p, sizeof(GridCtl), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+    static const char* names[GridCtl::kPhases] = {"evaluation", "assembly", "residual+decision", "LU", "forward", "backward", "limit+update"};
+    double tot = 0.0;
+    for (int k = 0; k < GridCtl::kPhases; k++) tot += (double)h.phase_ns[k];
+    std::fprintf(stderr, "[s21 grid] phases of the launch (ms):");
+    for (int k = 0; k < GridCtl::kPhases; k++) std::fprintf(stderr, " %s %.3f", names[k], (double)h.phase_ns[k] * 1e-6);
+    std::fprintf(stderr, " | total %.3f, %d loads, huge gather lists %d\n", tot * 1e-6, h.nld, h.n_huge);
+  }
   DBuf<double> ad_x1_, ad_xs_, ad_st_;   // adaptive transient scratch
   DBuf<int32_t> ad_acc_, ad_rej_;
   double symbolic_s_ = 0.0;  // host time spent in build_plan (diagnostics)

@@ -166,8 +166,15 @@ int launch_hybrid_ac(const DevTables& d, const PlanTables& p, const CoopTables& 
 // Grid-wide variant (kernels/grid.cu) for ONE large circuit (B = 1, instance stride 1, workspace and staging in HBM/L2):
 // a cooperative launch with grid barriers between phases / dependency levels. `gc` is a device-resident control block.
 struct GridCtl {
+  static constexpr int kHugeCap = 64;
   int stat, nsol, nld, dxok, act, resok, sing, convnow, weak;
+  int n_huge;             // tolerance mode: gather lists too long for one warp, summed in chunks by the whole grid (grid.cu)
   unsigned long long maxabs;
+  int huge[kHugeCap];
+  // wall clock per phase of the launch in ns (thread 0, %globaltimer): 0 evaluation, 1 assembly, 2 residual + decision, 3 LU,
+  // 4 forward, 5 backward substitution, 6 step limit + update
+  static constexpr int kPhases = 7;
+  unsigned long long phase_ns[kPhases];
 };
 int launch_grid_dcop(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<double>& w, double* stage, const NewtonOut& o,
                      const SolveCtl& c, GridCtl* gc, void* stream);
