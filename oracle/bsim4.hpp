@@ -17,6 +17,9 @@
 #include <map>
 #include <memory>
 
+#ifdef S21_B4_COUNT
+#include "bsim4_count.hpp"  // instrumented build: defines B4_DIV and the counting exp / log / sqrt before the evaluation headers
+#endif
 #include "../spice21_b200/csrc/bsim4/bsim4_eval.hpp"
 #include "../spice21_b200/csrc/bsim4/bsim4_pack.hpp"
 #include "circuit.hpp"
@@ -96,6 +99,9 @@ struct Bsim4 : Component {
   Stamps<double> load(const Variables<double>& vars, const AnalysisInfo& an, const Options& opts) override {  // bsim4solver.rs:134-144
     Stamps<double> st;
     Env e{this, &vars, &st, an.kind == AnalysisInfo::TRAN ? (int)s21::AN_TRAN : (int)s21::AN_OP, an.tran ? an.tran->dt : 0.0, opts.gmin, 0.0};
+#ifdef S21_B4_COUNT
+    s21::b4e::b4_counts().evals++;
+#endif
     s21::b4e::load_bsim4(e);
     return st;
   }

@@ -41,42 +41,32 @@ namespace b4e {
 #if defined(__CUDACC__) && defined(S21_B4_NIDIV)
 static __device__ __noinline__ double b4_ddiv_ool(double a, double b) { return __ddiv_rn(a, b); }  // IEEE quotient
 #endif
-//   * -DS21_B4_RCPDIV: a / b as a * rcp(b), rcp = the hardware seed (MUFU.RCP64H) plus one cubic Newton step (3 DFMA):
-//     6 instructions and no control flow against the 16 + an out-of-line slow path of the IEEE quotient, and — because the
-//     reciprocal is a pure function of b — the compiler shares it between all divisions by one denominator. The quotient
-//     is then within ~1.5 ulp of a / b instead of correctly rounded (far inside the 1e-9 / reltol parity bounds; the host
-//     build and the oracle keep the IEEE quotient). Counted on the host (scripts/b4_opcount.py): 235 divisions are executed
-//     per evaluation and none has an operand or result outside the range in which the seed + Newton step is valid.
+//   * -DS21_B4_RCPDIV (kernels/coop_fast.cu, opt-in at run time with S21_B4_FAST=1): a / b as a * rcp(b), rcp = the hardware
+//     seed (MUFU.RCP64H) plus one cubic Newton step (3 DFMA) — 8 instructions and no control flow against the 16 + an
+//     out-of-line slow path of the IEEE quotient — and, because the reciprocal is a pure function of b, the compiler shares
+//     it between all divisions by one denominator (806 MUFU in the kernel text against 1258). The quotient is within
+//     ~1.5 ulp of a / b instead of correctly rounded: inside the 1e-9 (dcop) / reltol (tran) parity bounds, but no longer
+//     the reference's bits, so it is not the default; the host build and the oracle keep the IEEE quotient. Counted on
+//     the host (scripts/b4_opcount.py): 235 divisions are executed per evaluation, none with an operand or result outside
+//     the normal range on the exact trajectory — a Newton iterate that overshoots can still produce an infinite or zero
+//     denominator (exp overflow), where the Newton step gives NaN: then the seed itself (0 for +-inf, +-inf for +-0) is
+//     the IEEE answer and is selected without a branch.
 #if defined(__CUDACC__) && defined(S21_B4_RCPDIV)
 __device__ __forceinline__ double b4_rcp(double b) {
   double r0;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(b));  // not volatile: identical reciprocals are merged
   double e = __fma_rn(-b, r0, 1.0);
+  const bool fin = e == e;  // NaN <=> b is +-0 / subnormal (seed +-inf), +-inf (seed 0) or NaN
   e = __fma_rn(e, e, e);
-  return __fma_rn(r0, e, r0);
+  const double r = __fma_rn(r0, e, r0);
+  return fin ? r : r0;
 }
 #endif
 #if defined(__CUDA_ARCH__) && defined(S21_B4_NIDIV)
 #define B4_DIV(a, b) ::s21::b4e::b4_ddiv_ool((double)(a), (double)(b))
 #elif defined(__CUDA_ARCH__) && defined(S21_B4_RCPDIV)
 #define B4_DIV(a, b) ((double)(a) * ::s21::b4e::b4_rcp((double)(b)))
-#elif !defined(__CUDACC__) && defined(S21_B4_COUNT)
-// host-only instrumentation (scripts/b4_opcount.py): executed divisions / exp / log / sqrt per evaluation, and how many
-// divisions leave the range in which the division fast path is exact (zero, subnormal, huge or non-finite operands / results)
-struct B4Counts { unsigned long long evals, div, div_special, exp, log, sqrt; };
-inline B4Counts& b4_counts() { static B4Counts c = {0, 0, 0, 0, 0, 0}; return c; }
-inline double b4_count_div(double a, double b) {
-  B4Counts& c = b4_counts();
-  c.div++;
-  const double q = a / b, ab = fabs(b), aq = fabs(q), aa = fabs(a);
-  if (!(ab >= 1e-290 && ab <= 1e290) || !(aa <= 1e290) || (aa != 0.0 && aa < 1e-290) || !(aq <= 1e290) || (aq != 0.0 && aq < 1e-290)) c.div_special++;
-  return q;
-}
-inline double exp(double x) { b4_counts().exp++; return ::exp(x); }
-inline double log(double x) { b4_counts().log++; return ::log(x); }
-inline double sqrt(double x) { b4_counts().sqrt++; return ::sqrt(x); }
-#define B4_DIV(a, b) ::s21::b4e::b4_count_div((double)(a), (double)(b))
-#else
+#elif !defined(B4_DIV)  // a host build may bring its own (an instrumented test build counts the executed divisions)
 #define B4_DIV(a, b) ((a) / (b))
 #endif
 #if defined(__CUDACC__) && defined(S21_B4_NIMATH)

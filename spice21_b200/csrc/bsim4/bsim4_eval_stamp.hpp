@@ -484,9 +484,6 @@ template <class E> B4_HD void load_bsim4(E& e) {
   B4Chan c;
   B4Tunnel t;
   B4Dyn y;
-#if !defined(__CUDACC__) && defined(S21_B4_COUNT)
-  b4_counts().evals++;
-#endif
   b4_limit_bias(e, v);
   b4_junction_dc(e, v, o);
   b4_channel_dc(e, v, o, c);

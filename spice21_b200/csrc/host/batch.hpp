@@ -127,6 +127,7 @@ struct PlanDevice {
   // cooperative kernel: every shared index table packed into one allocation ("arena") so that a CTA can bring all of
   // them into shared memory with a single TMA bulk copy. Offsets are in ints, each table 16-byte aligned.
   DBuf<int> arena;
+  DBuf<int> res_off, res_slot, res_x;  // CoopTables::res_off / res_slot (tolerance-mode plans; outside the arena: the grid-wide kernel never copies it)
   size_t arena_bytes = 0, arena_core_bytes = 0;  // core = all tables but the parameter codes (packed last)
   struct ArenaOffsets {
     size_t type, itab_off, par_off, state_off, itab, pcode, par_direct, row_i2e, col_i2e, col_e2i, rowptr, colidx, diag_slot, stage_off, eval_order,
@@ -155,6 +156,7 @@ struct PlanDevice {
     c.lu_lvl_off = arena.p + ao.lu_lvl_off; c.lu_t = arena.p + ao.lu_t; c.lu_u = arena.p + ao.lu_u; c.lu_l = arena.p + ao.lu_l;
     c.fw_lvl_off = arena.p + ao.fw_lvl_off; c.fw_k = arena.p + ao.fw_k; c.fw_row = arena.p + ao.fw_row; c.fw_slot = arena.p + ao.fw_slot;
     c.bw_lvl_off = arena.p + ao.bw_lvl_off; c.bw_row = arena.p + ao.bw_row;
+    if (host.relaxed) { c.res_off = res_off.p; c.res_slot = res_slot.p; c.res_x = res_x.p; }
     return c;
   }
   PlanTables tables() const {
@@ -209,6 +211,7 @@ class Batch {
       jit_team_forced_ = v == "jitteam";
       ac_kernel_forced_ = true;
     }
+    if (const char* f = std::getenv("S21_B4_FAST")) b4_fast_ = std::atoi(f) != 0;  // kernels/coop_fast.cu
     max_smem_ = (size_t)coop_max_smem_optin(device_);
     if (cudaDeviceGetAttribute(&n_sm_, cudaDevAttrMultiProcessorCount, device_) != cudaSuccess || n_sm_ <= 0) n_sm_ = 148;
     // workspace
@@ -709,9 +712,11 @@ class Batch {
                             d_gctl_.p, T, d_save_.p, (int)n_save, d_wave_.p, stream_);
     } else if (use_coop_) {
       CoopCfg cfg = coop_cfg(tran_plan_, B_, 1);
-      last_kernel_ = "coop";
-      rc = launch_coop_tran(coop_dev(tran_plan_), tran_plan_.coop_plan(), tran_plan_.coop(), work(), stage_for(cfg, tran_plan_.host),
-                            out(), ctl, cfg, T, d_save_.p, (int)n_save, d_wave_.p, stream_);
+      const bool fast = b4_fast_ && ctl.has_bsim4;
+      last_kernel_ = fast ? "coop-rcp" : "coop";
+      rc = (fast ? launch_coop_tran_fast : launch_coop_tran)(coop_dev(tran_plan_), tran_plan_.coop_plan(), tran_plan_.coop(), work(),
+                                                             stage_for(cfg, tran_plan_.host), out(), ctl, cfg, T, d_save_.p, (int)n_save,
+                                                             d_wave_.p, stream_);
     } else {
       last_kernel_ = "direct";
       rc = launch_tran(dt, tran_plan_.tables(), work(), out(), ctl, T, d_save_.p, (int)n_save, d_wave_.p, stream_);
@@ -1022,6 +1027,7 @@ class Batch {
   DBuf<int> d_stage_off_, d_eval_order_;
   DBuf<double> d_stage_;
   DBuf<cplx> zstage_;
+  bool b4_fast_ = false;  // S21_B4_FAST=1: Bsim4 batches on the cooperative kernel run kernels/coop_fast.cu
   bool use_coop_ = true, allow_hybrid_ = true, allow_jit_ = true, jit_forced_ = false, jit_team_forced_ = false, ac_kernel_forced_ = false;
   std::string jit_error_;  // why the specialised kernel is not in use (empty when it is, or was never wanted)
   bool reset_pending_ = false;
@@ -1268,8 +1274,10 @@ class Batch {
     } else if (use_coop_) {
       materialize_reset();
       CoopCfg cfg = coop_cfg(pd, B_, 1);
-      if (!resume) last_kernel_ = "coop";
-      rc = launch_coop_dcop(coop_dev(pd), pd.coop_plan(), pd.coop(), work(), stage_for(cfg, pd.host), o, ctl, cfg, stream_);
+      const bool fast = b4_fast_ && ctl.has_bsim4;
+      if (!resume) last_kernel_ = fast ? "coop-rcp" : "coop";
+      rc = (fast ? launch_coop_dcop_fast : launch_coop_dcop)(coop_dev(pd), pd.coop_plan(), pd.coop(), work(), stage_for(cfg, pd.host), o, ctl, cfg,
+                                                             stream_);
     } else {
       materialize_reset();
       if (!resume) last_kernel_ = "direct";
@@ -1408,6 +1416,16 @@ class Batch {
       o.pcode = put(pcode_h_);
       pd.arena_bytes = A.size() * sizeof(int);
       pd.arena.upload(A, stream_);
+      if (P.relaxed) {  // rows of A proper in pivoted order (slots with a non-empty gather list), for the grid-wide kernel's residual
+        std::vector<int> ro((size_t)P.N + 1, 0), rs, rx;
+        for (int r = 0; r < P.N; r++) {
+          for (int sl = P.rowptr[(size_t)r]; sl < P.rowptr[(size_t)r + 1]; sl++)
+            if (P.asm_off[(size_t)sl + 1] > P.asm_off[(size_t)sl]) { rs.push_back(sl); rx.push_back(P.col_i2e[(size_t)P.colidx[(size_t)sl]]); }
+          ro[(size_t)r + 1] = (int)rs.size();
+        }
+        if (rs.empty()) { rs.push_back(0); rx.push_back(0); }
+        pd.res_off.upload(ro, stream_); pd.res_slot.upload(rs, stream_); pd.res_x.upload(rx, stream_);
+      }
     }
     S21_CUDA(cudaStreamSynchronize(stream_));  // host vectors above are temporaries
     pd.valid = true;

@@ -370,11 +370,27 @@ int launch(const DevTables& d, const PlanTables& p, const CoopTables& ct, const 
   if constexpr (KIND != K_AC) {
     if (c.has_bsim4) return launch_b4<T, KIND, true>(d, p, ct, w, stage, o, c, cfg, T_points, save_vars, n_save, wave, stream);
   }
+#ifdef S21_COOP_FAST
+  return (int)cudaErrorInvalidValue;  // coop_fast.cu holds the Bsim4 kernels only
+#else
   return launch_b4<T, KIND, false>(d, p, ct, w, stage, o, c, cfg, T_points, save_vars, n_save, wave, stream);
+#endif
 }
 
 }  // namespace
 
+#ifdef S21_COOP_FAST
+// kernels/coop_fast.cu: the same Bsim4 kernels with the evaluation's divisions as a * rcp(b) (bsim4/bsim4_eval.hpp)
+int launch_coop_dcop_fast(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<double>& w, double* stage,
+                          const NewtonOut& o, const SolveCtl& c, const CoopCfg& cfg, void* stream) {
+  return launch<double, K_DCOP>(d, p, ct, w, stage, o, c, cfg, 2, nullptr, 0, nullptr, stream);
+}
+int launch_coop_tran_fast(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<double>& w, double* stage,
+                          const NewtonOut& o, const SolveCtl& c, const CoopCfg& cfg, int T, const int* save_vars, int n_save, double* wave,
+                          void* stream) {
+  return launch<double, K_TRAN>(d, p, ct, w, stage, o, c, cfg, T, save_vars, n_save, wave, stream);
+}
+#else
 size_t coop_ctrl_bytes(int gi) { return ctrl_bytes(gi); }
 size_t coop_mixed_bytes(int N, int nnz, int gi, int scalar_width) { return 8 * (size_t)scalar_width * (size_t)gi * (3 * (size_t)N + (size_t)nnz); }
 size_t coop_work_bytes(int N, int nnz, int n_stage, int n_state, int gi, int scalar_width) {
@@ -400,5 +416,6 @@ int launch_coop_ac(const DevTables& d, const PlanTables& p, const CoopTables& ct
                    const NewtonOut& o, const SolveCtl& c, const CoopCfg& cfg, void* stream) {
   return launch<cplx, K_AC>(d, p, ct, w, stage, o, c, cfg, 2, nullptr, 0, nullptr, stream);
 }
+#endif  // S21_COOP_FAST
 
 }  // namespace s21

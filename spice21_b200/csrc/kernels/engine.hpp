@@ -118,6 +118,10 @@ struct CoopTables {
   const int *lu_lvl_off, *lu_t, *lu_u, *lu_l;
   const int *fw_lvl_off, *fw_k, *fw_row, *fw_slot;
   const int *bw_lvl_off, *bw_row;
+  // tolerance-mode plans only (grid-wide kernel; nullptr otherwise): per pivoted row, those of its L+U slots that receive
+  // stamps — the entries of A proper. The residual then skips the fill-in slots (exact zeros before the factorisation:
+  // 4.0 M of the 4.07 M slots of config C3)
+  const int *res_off = nullptr, *res_slot = nullptr, *res_x = nullptr;  // res_x: the variable each of those entries multiplies
 };
 
 // Launch geometry of the cooperative kernel: a CTA of `threads` threads (a multiple of `gi`) owns `gi` consecutive
@@ -153,6 +157,13 @@ int launch_coop_tran(const DevTables& d, const PlanTables& p, const CoopTables& 
                      void* stream);
 int launch_coop_ac(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<cplx>& w, cplx* stage,
                    const NewtonOut& o, const SolveCtl& c, const CoopCfg& cfg, void* stream);
+// kernels/coop_fast.cu (Bsim4 circuits only, S21_B4_FAST=1): divisions of the Bsim4 evaluation as a * rcp(b); same contracts,
+// results within round-off of the default kernels instead of bit-identical
+int launch_coop_dcop_fast(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<double>& w, double* stage,
+                          const NewtonOut& o, const SolveCtl& c, const CoopCfg& cfg, void* stream);
+int launch_coop_tran_fast(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<double>& w, double* stage,
+                          const NewtonOut& o, const SolveCtl& c, const CoopCfg& cfg, int T, const int* save_vars, int n_save, double* wave,
+                          void* stream);
 // Hybrid variants (kernels/hybrid.cu) for small circuits: 32 instances per 256-thread CTA, workspace + arena always in
 // shared memory (cfg.gi / cfg.threads are ignored; cfg.smem_bytes = hybrid_work_bytes(...)). Bit-identical results.
 size_t hybrid_smem_bytes(int N, int nnz, int n_stage, int n_state, size_t arena_bytes, int scalar_width);

@@ -55,7 +55,7 @@ template <class F>
 __device__ __forceinline__ double warp_sum(int b0, int b1, int lane, F f) {
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
   int q = b0 + lane;
-  for (; q + 96 < b1; q += 128) {
+  for (; q + 96 < b1; q += 128) {  // four chains of dependent loads in flight per lane (eight measured slower: backward 11.7 -> 18.2 ms on C3)
     const double v0 = f(q), v1 = f(q + 32), v2 = f(q + 64), v3 = f(q + 96);
     a0 += v0; a1 += v1; a2 += v2; a3 += v3;
   }
@@ -64,7 +64,7 @@ __device__ __forceinline__ double warp_sum(int b0, int b1, int lane, F f) {
 }
 
 template <int KIND, bool B4>
-__global__ void __launch_bounds__(256, B4 ? 1 : 2) k_grid(DevTables d, PlanTables p, CoopTables ct, WorkTables<double> g, double* S, NewtonOut o,
+__global__ void __launch_bounds__(B4 ? 256 : 512, 1) k_grid(DevTables d, PlanTables p, CoopTables ct, WorkTables<double> g, double* S, NewtonOut o,
                                                             SolveCtl ctl, GridCtl* gc_, int T_points, int n_save, const int* save_vars, double* wave) {
   volatile GridCtl* gc = gc_;  // control words change between grid barriers: never keep them in registers
   cg::grid_group grid = cg::this_grid();
@@ -182,16 +182,16 @@ __global__ void __launch_bounds__(256, B4 ? 1 : 2) k_grid(DevTables d, PlanTable
         }
         if (!ok) gc->resok = 0;
       } else {
-        // fill-in slots (empty gather list) hold exact zeros at this point: long rows skip them without touching x
+        // fill-in slots (empty gather list) hold exact zeros at this point: the rows of A proper (CoopTables::res_off) skip them
         bool ok = true;
         for (size_t base = gw * 32; base < (size_t)N; base += nw * 32) {
           const size_t r = base + lane;
           int s0 = 0, se = 0;
-          if (r < (size_t)N) { s0 = p.rowptr[r]; se = p.rowptr[r + 1]; }
+          if (r < (size_t)N) { s0 = ct.res_off[r]; se = ct.res_off[r + 1]; }
           const bool lng = (se - s0) > kLongList;
           if (!lng && r < (size_t)N) {
             double acc = 0.0;
-            for (int s = s0; s < se; s++) acc = s_add(acc, s_mul(lu[s], x[p.col_i2e[p.colidx[s]]]));
+            for (int q = s0; q < se; q++) acc = s_add(acc, s_mul(lu[ct.res_slot[q]], x[ct.res_x[q]]));
             const double rv = s_sub(rhs[p.row_i2e[r]], acc);
             c[r] = rv;
             if (!TolC<double>::ok(s_abs(rv), itol)) ok = false;
@@ -201,9 +201,7 @@ __global__ void __launch_bounds__(256, B4 ? 1 : 2) k_grid(DevTables d, PlanTable
             const int src = __ffs(m) - 1;
             m &= m - 1;
             const int b0 = __shfl_sync(0xffffffffu, s0, src), b1 = __shfl_sync(0xffffffffu, se, src);
-            const double acc = warp_sum(b0, b1, lane, [&](int s) {
-              return ct.asm_off[s + 1] > ct.asm_off[s] ? s_mul(lu[s], x[p.col_i2e[p.colidx[s]]]) : 0.0;
-            });
+            const double acc = warp_sum(b0, b1, lane, [&](int q) { return s_mul(lu[ct.res_slot[q]], x[ct.res_x[q]]); });
             if (lane == src) {
               const double rv = s_sub(rhs[p.row_i2e[r]], acc);
               c[r] = rv;
@@ -403,14 +401,18 @@ int launch_k(const DevTables& d, const PlanTables& p, const CoopTables& ct, cons
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return (int)e;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0);
+  // One CTA per SM: a grid barrier costs with the number of CTAs, not of threads. Measured on C3 with two 256-thread CTAs per
+  // SM (profiles/r02v_c3_phases.txt): the latency-bound phases (assembly, LU, forward) gain from the second set of warps,
+  // the barrier-bound ones lose as much — hence ONE CTA of 512 threads for circuits without Bsim4 devices (256 with: the
+  // evaluation needs the registers). S21_GRID_THREADS / S21_GRID_CTAS override both for measurements.
+  int threads = B4 ? 256 : 512;
+  if (const char* v = std::getenv("S21_GRID_THREADS")) threads = std::max(64, std::min(B4 ? 256 : 512, std::atoi(v) / 32 * 32));
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0);
   if (e != cudaSuccess) return (int)e;
   if (per_sm < 1) return (int)cudaErrorLaunchOutOfResources;
-  // barriers cost more with more CTAs and the widest phases (4 M gathers) are still short: one CTA per SM is enough
-  // (S21_GRID_CTAS=2 for measurements)
   int per = 1;
   if (const char* v = std::getenv("S21_GRID_CTAS")) per = std::max(1, std::min(per_sm, std::atoi(v)));
-  dim3 grid((unsigned)(sms * per)), block(256);
+  dim3 grid((unsigned)(sms * per)), block((unsigned)threads);
   DevTables d_ = d; PlanTables p_ = p; CoopTables ct_ = ct; WorkTables<double> w_ = w; NewtonOut o_ = o; SolveCtl c_ = c;
   void* args[] = {&d_, &p_, &ct_, &w_, &stage, &o_, &c_, &gc, &T, &n_save, &save_vars, &wave};
   e = cudaLaunchCooperativeKernel((const void*)kern, grid, block, args, 0, (cudaStream_t)stream);

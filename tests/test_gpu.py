@@ -1104,6 +1104,64 @@ def test_c4_bsim4_ring_sweep_matches_oracle(s21, oracle):
     assert np.allclose(wave[:, -1, vdd], ovr["V:vsup:dc"], rtol=0, atol=1e-12)  # every instance really ran at its own supply
 
 
+def test_bsim4_fast_division_within_tolerance(s21, oracle, monkeypatch):
+    """S21_B4_FAST=1 (kernels/coop_fast.cu): the cooperative kernel with the Bsim4 evaluation's divisions as a * rcp(b) —
+    quotients within ~1.5 ulp instead of correctly rounded. Not bit-identical to the default kernels (which is why it is
+    opt-in); it must stay inside BASELINE.json's bounds — dcop 1e-9 relative, transient SPICE reltol 1e-3 / vntol 1e-6 —
+    against the oracle, on config C4's sweep (24 instances x 60 points), on a dcop of the Bsim4 amplifier and on the
+    reference's own Bsim4 ring-oscillator golden waveform (reference tolerance 1e-6, tests.rs:948-964)."""
+    monkeypatch.setenv("S21_B4_FAST", "1")
+    monkeypatch.setenv("S21_KERNEL", "coop")
+    # dcop
+    ck = _bsim4_amp()
+    b = s21.Batch(ck.to_s21().elaborate(), 4)
+    x, status, _ = b.dcop()
+    assert b.kernel_name() == "coop-rcp" and np.all(status == 0)
+    od = oracle.Circuit(ck.to_text()).dcop()
+    assert close(x[0], od.data[0], rtol=1e-9)
+    # the reference's golden transient
+    g = golden("test_bsim4_cmos_ro_tran")
+    rb = cc.cmos_ro3(cc.add_bsim4_defaults)
+    cb = rb.to_s21().elaborate(ic={"1": 0.0})
+    bb = s21.Batch(cb, 1)
+    tb, wb, stb, _ = bb.tran(1e-10, 3e-7)
+    assert bb.kernel_name() == "coop-rcp" and stb[0] == 0 and len(tb) == len(g["time"])
+    for k, name in enumerate(cb.names):
+        assert np.max(np.abs(wb[0, :, k] - g[name])) <= 1e-6, name
+    monkeypatch.delenv("S21_KERNEL")
+    # C4 sweep
+    B, npts, tstep = 24, 60, 1e-10
+    ck, ic = cc.bsim4_ring(21)
+    ovr = {k: v[::85][:B] for k, v in cc.c4_sweep(2048).items()}
+    bf = s21.Batch(ck.to_s21().elaborate(ic=ic), B)
+    for k, v in ovr.items():
+        bf.override(k, v)
+    t, wave, status, iters = bf.tran(tstep, npts * tstep)
+    assert bf.kernel_name() == "coop-rcp"
+    monkeypatch.delenv("S21_B4_FAST")
+    bd = s21.Batch(ck.to_s21().elaborate(ic=ic), B)
+    for k, v in ovr.items():
+        bd.override(k, v)
+    td, wd, sd, itd = bd.tran(tstep, npts * tstep)
+    assert bd.kernel_name() == "coop"
+    o = oracle.Circuit(ck.to_text()).batch(1, B, overrides=ovr, tstep=tstep, tstop=npts * tstep, ic=ic, nthreads=8)
+    okp = status == 0
+    print(f"fast division: status {status.tolist()}, max |fast - default| = {float(np.max(np.abs(wave[okp] - wd[okp]))):.3e}, "
+          f"max |fast - oracle| = {float(np.max(np.abs(wave[okp] - o['x'][okp]))):.3e}, Newton iterations "
+          f"{int(iters[okp].sum())} vs {int(itd[okp].sum())}")
+    # A device-resident time loop runs on the pivot order frozen at its first iteration (nobody can re-pivot inside it,
+    # DESIGN.md §4): an instance whose iterate drives a frozen pivot to exactly zero stops with S21_SINGULAR_MATRIX — with
+    # the default kernel on other circuits (test_c4x_...), and here, with last bits that differ, on one supply voltage of
+    # the 24 (measured: instance 17; the same supply converges inside the 2048-instance bench batch, whose OP repair takes
+    # its order from another instance). It is reported, never returned as a result; every other instance must agree.
+    ok = status == 0
+    assert np.all(o["status"] == 0) and np.all(sd == 0)
+    assert int(np.sum(ok)) >= B - 2 and np.all(np.isin(status[~ok], [s21.S21_SINGULAR_MATRIX]))
+    tol = 1e-6 + 1e-3 * np.abs(o["x"][ok])
+    assert np.all(np.abs(wave[ok] - o["x"][ok]) <= tol)
+    assert np.max(np.abs(wave[ok] - o["x"][ok])) <= 1e-6  # in fact far inside vntol on this circuit
+
+
 def test_c4_ptm65_statuses_match_oracle(s21, oracle):
     """SURVEY's literal C4 cards (PTM 65 nm): under the reference's Newton loop some supply voltages do not converge.
     The GPU path must report the same per-instance outcome as the oracle, and the same waveforms where it converges."""
