@@ -987,6 +987,28 @@ class Batch {
     std::fprintf(stderr, "[s21 grid] phases of the launch (ms):");
     for (int k = 0; k < GridCtl::kPhases; k++) std::fprintf(stderr, " %s %.3f", names[k], (double)h.phase_ns[k] * 1e-6);
     std::fprintf(stderr, " | total %.3f, %d loads, huge gather lists %d\n", tot * 1e-6, h.nld, h.n_huge);
+    const Plan& P = tran_plan_.host;
+    const std::vector<int>* offs[3] = {&P.lu_lvl_off, &P.fw_lvl_off, &P.bw_lvl_off};
+    static const char* what[3] = {"LU", "forward", "backward"};
+    for (int w = 0; w < 3; w++) {
+      std::fprintf(stderr, "[s21 grid] %s levels (items: ms):", what[w]);
+      for (size_t q = 0; q + 1 < offs[w]->size() && q < (size_t)GridCtl::kLevels; q++)
+        std::fprintf(stderr, " %d: %.3f", (*offs[w])[q + 1] - (*offs[w])[q], (double)h.level_ns[w][q] * 1e-6);
+      std::fprintf(stderr, "\n");
+    }
+    {  // backward: entries per level (the rows' U parts)
+      std::fprintf(stderr, "[s21 grid] backward entries per level:");
+      for (size_t q = 0; q + 1 < P.bw_lvl_off.size(); q++) {
+        long long n = 0; int mx = 0;
+        for (int r = P.bw_lvl_off[q]; r < P.bw_lvl_off[q + 1]; r++) {
+          const int k = P.bw_row[(size_t)r];
+          const int len = P.rowptr[(size_t)k + 1] - P.diag_slot[(size_t)k] - 1;
+          n += len; mx = std::max(mx, len);
+        }
+        std::fprintf(stderr, " %lld (max row %d)", n, mx);
+      }
+      std::fprintf(stderr, "\n");
+    }
   }
   DBuf<double> ad_x1_, ad_xs_, ad_st_;   // adaptive transient scratch
   DBuf<int32_t> ad_acc_, ad_rej_;

@@ -102,6 +102,10 @@ inline void build_levels(Plan& P, bool relaxed = false) {
     }
     std::vector<int> order;
     P.lu_lvl_off = level_sort(lev, &order);
+    if (relaxed)  // updates of one level that share a target sit next to each other: the kernel sums each run inside a warp
+      for (size_t q = 0; q + 1 < P.lu_lvl_off.size(); q++)  // and issues ONE atomic per run (grid.cu) instead of a chain on one address
+        std::stable_sort(order.begin() + P.lu_lvl_off[q], order.begin() + P.lu_lvl_off[q + 1],
+                         [&](int a, int b) { return t[(size_t)a] < t[(size_t)b]; });
     for (int j : order) { P.lu_t.push_back(t[(size_t)j]); P.lu_u.push_back(u[(size_t)j]); P.lu_l.push_back(l[(size_t)j]); }
   }
   // ---- forward substitution

@@ -186,6 +186,9 @@ struct GridCtl {
   // 4 forward, 5 backward substitution, 6 step limit + update
   static constexpr int kPhases = 7;
   unsigned long long phase_ns[kPhases];
+  // the same per dependency level (the first kLevels of each schedule): LU, forward, backward
+  static constexpr int kLevels = 24;
+  unsigned long long level_ns[3][kLevels];
 };
 int launch_grid_dcop(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<double>& w, double* stage, const NewtonOut& o,
                      const SolveCtl& c, GridCtl* gc, void* stream);

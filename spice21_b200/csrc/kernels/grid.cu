@@ -43,6 +43,7 @@ __device__ __forceinline__ unsigned long long now_ns() {
 }
 // per-phase wall clock of the launch, kept by thread 0 (it leaves every grid barrier with everybody else): GridCtl::phase_ns,
 // printed by the host under S21_PLAN_INFO
+#define GRID_LEVEL(w, q) do { if (tid == 0 && (q) < GridCtl::kLevels) { const unsigned long long t_ = now_ns(); gc_->level_ns[w][q] += t_ - t_lv; t_lv = t_; } } while (0)
 #define GRID_PHASE(k) do { if (tid == 0) { const unsigned long long t_ = now_ns(); gc_->phase_ns[k] += t_ - t_ph; t_ph = t_; } } while (0)
 
 __device__ __forceinline__ double warp_total(double a) {
@@ -84,8 +85,9 @@ __global__ void __launch_bounds__(B4 ? 256 : 512, 1) k_grid(DevTables d, PlanTab
     gc->stat = KIND == K_TRAN ? o.status[0] : (used >= ctl.max_iter ? CST_CONV : 0);
     gc->nsol = 0; gc->nld = 0; gc->dxok = 1; gc->act = 0; gc->resok = 1; gc->sing = 0; gc->weak = 0; gc->maxabs = 0ull;
     for (int k = 0; k < GridCtl::kPhases; k++) gc_->phase_ns[k] = 0ull;
+    for (int w = 0; w < 3; w++) for (int k = 0; k < GridCtl::kLevels; k++) gc_->level_ns[w][k] = 0ull;
   }
-  unsigned long long t_ph = now_ns();
+  unsigned long long t_ph = now_ns(), t_lv = t_ph;
   if constexpr (KIND == K_TRAN) {
     for (size_t s = tid; s < (size_t)n_save; s += nt) wave[s] = x[save_vars[s]];
   }
@@ -227,6 +229,7 @@ __global__ void __launch_bounds__(B4 ? 256 : 512, 1) k_grid(DevTables d, PlanTab
       }
       GRID_PHASE(2);
       // ---- numeric LU, one barrier per dependency level
+      if (tid == 0) t_lv = now_ns();
       for (int q = 0; q < ct.n_lu_lvl; q++) {
         const size_t b = (size_t)ct.lu_lvl_off[q], e_ = (size_t)ct.lu_lvl_off[q + 1];
         if (!relaxed) {
@@ -242,7 +245,8 @@ __global__ void __launch_bounds__(B4 ? 256 : 512, 1) k_grid(DevTables d, PlanTab
         } else {
           // the operations of one level are independent apart from shared targets (atomic): four of them in flight per thread
           // — index loads, then operand loads, then the updates — instead of one dependent chain of L2 latencies per operation
-          for (size_t op = b + tid; op < e_; op += 4 * nt) {
+          for (size_t op0 = b + (tid - lane); op0 < e_; op0 += 4 * nt) {  // warp-uniform trip count: the body shuffles
+            const size_t op = op0 + lane;
             int li[4], ti[4], ui[4];
             double uv[4], lv[4];
 #pragma unroll
@@ -260,8 +264,25 @@ __global__ void __launch_bounds__(B4 ? 256 : 512, 1) k_grid(DevTables d, PlanTab
             }
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-              if (li[j] >= 0) atomicAdd(lu + ti[j], -s_mul(uv[j], lv[j]));  // several updates of one level may share the target
-              else if (li[j] > -3) {
+              // Several updates of one level may share the target (atomic). The host sorted the level by target, so a shared
+              // target is a run of consecutive lanes: the run is summed inside the warp (segmented shuffle reduction) and only
+              // its first lane issues the atomic — the 2000 diagonal entries of C3's dense block receive ~1000 updates each
+              // in one level, which as single atomics queued on one L2 address each (5.4 of the LU phase's 10.5 ms).
+              const bool upd = li[j] >= 0;
+              const int key = upd ? ti[j] : -1 - lane;  // never equal between lanes unless both are updates of one target
+              double v = upd ? -s_mul(uv[j], lv[j]) : 0.0;
+              const int knext = __shfl_down_sync(0xffffffffu, key, 1);
+              if (__any_sync(0xffffffffu, lane < 31 && knext == key)) {
+#pragma unroll
+                for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                  const double ov = __shfl_down_sync(0xffffffffu, v, dlt);
+                  const int ok_ = __shfl_down_sync(0xffffffffu, key, dlt);
+                  if (lane + dlt < 32 && ok_ == key) v += ov;
+                }
+                const int kprev = __shfl_up_sync(0xffffffffu, key, 1);
+                if (upd && (lane == 0 || kprev != key)) atomicAdd(lu + ti[j], v);
+              } else if (upd) atomicAdd(lu + ti[j], v);
+              if (!upd && li[j] > -3) {
                 if (li[j] == -1 && ctl.stop_on_weak && s_abs(uv[j]) * ctl.weak_mult < s_abs(lv[j])) gc->weak = 1;
                 lu[ti[j]] = s_div(lv[j], uv[j]);
               }
@@ -269,6 +290,7 @@ __global__ void __launch_bounds__(B4 ? 256 : 512, 1) k_grid(DevTables d, PlanTab
           }
         }
         grid.sync();
+        GRID_LEVEL(0, q);
       }
       GRID_PHASE(3);
       // ---- forward substitution
@@ -304,6 +326,7 @@ __global__ void __launch_bounds__(B4 ? 256 : 512, 1) k_grid(DevTables d, PlanTab
           }
         }
         grid.sync();
+        GRID_LEVEL(1, q);
       }
       GRID_PHASE(4);
       // ---- backward substitution
@@ -318,27 +341,27 @@ __global__ void __launch_bounds__(B4 ? 256 : 512, 1) k_grid(DevTables d, PlanTab
             c[k] = s_div(ck, lu[ds]);
           }
         } else {
-          for (size_t base = b + gw * 32; base < e_; base += nw * 32) {
-            const size_t r = base + lane;
-            int k = 0, ds = 0, s0 = 0, se = 0;
-            if (r < e_) { k = ct.bw_row[r]; ds = p.diag_slot[k]; s0 = ds + 1; se = p.rowptr[k + 1]; }
-            const bool lng = (se - s0) > kLongList;
-            if (!lng && r < e_) {
-              double ck = c[k];
-              for (int s = s0; s < se; s++) ck = s_sub(ck, s_mul(c[p.colidx[s]], lu[s]));
-              c[k] = s_div(ck, lu[ds]);
-            }
-            unsigned m = __ballot_sync(0xffffffffu, lng);
-            while (m) {
-              const int src = __ffs(m) - 1;
-              m &= m - 1;
-              const int b0 = __shfl_sync(0xffffffffu, s0, src), b1 = __shfl_sync(0xffffffffu, se, src);
-              const double acc = warp_sum(b0, b1, lane, [&](int s) { return s_mul(c[p.colidx[s]], lu[s]); });
-              if (lane == src) c[k] = s_div(s_sub(c[k], acc), lu[ds]);
-            }
+          // Long rows come in blocks here (C3: one level holds the 2000 rows of a dense triangle, 2 M entries), so a warp
+          // owning 32 consecutive rows would walk 32 long rows while 2300 warps idle (measured: 13.5 of 14.8 ms). Two passes
+          // over the level instead, on disjoint rows: a thread per short row, then a warp per long row, warp-strided.
+          for (size_t r = b + tid; r < e_; r += nt) {
+            const int k = ct.bw_row[r];
+            const int ds = p.diag_slot[k], se = p.rowptr[k + 1];
+            if (se - (ds + 1) > kLongList) continue;
+            double ck = c[k];
+            for (int s = ds + 1; s < se; s++) ck = s_sub(ck, s_mul(c[p.colidx[s]], lu[s]));
+            c[k] = s_div(ck, lu[ds]);
+          }
+          for (size_t r = b + gw; r < e_; r += nw) {  // warp-uniform row
+            const int k = ct.bw_row[r];
+            const int ds = p.diag_slot[k], se = p.rowptr[k + 1];
+            if (se - (ds + 1) <= kLongList) continue;
+            const double acc = warp_sum(ds + 1, se, lane, [&](int s) { return s_mul(c[p.colidx[s]], lu[s]); });
+            if (lane == 0) c[k] = s_div(s_sub(c[k], acc), lu[ds]);
           }
         }
         grid.sync();
+        GRID_LEVEL(2, q);
       }
       GRID_PHASE(5);
       // ---- zero-pivot check and max |dx|
