@@ -729,6 +729,14 @@ def run_ours(args):
         m = measure_dcop(args, D, s21, cc, torch, C2(), scaling, stream, flush)
         if D.world > 1 and scaling == "strong":
             w = guarded("weak", lambda: measure_dcop(args, D, s21, cc, torch, C2(), "weak", stream, flush))
+    # The sampler polls nvidia-smi at 10 Hz: it covers the headline's timed regions (the contract) and stops before the
+    # secondary configurations — C4's 0.2 s cooperative launches measured 184 ms in some runs and 216-232 ms in others with
+    # the poll running through them, 177-186 ms in eight stand-alone processes without it (profiles/r02C_c4_modes.txt).
+    # S21_BENCH_SAMPLE_EXTRAS=1 keeps it running (the earlier behaviour); each configuration records one query after its loop.
+    keep_sampling = os.environ.get("S21_BENCH_SAMPLE_EXTRAS", "1" if args.config != "c2" else "0") == "1"
+    if not keep_sampling:
+        sampler.stop_flag.set()
+        sampler.join(timeout=2)
     if args.extras or args.config != "c2":
         want = ["c1", "c4", "c5", "c3"] if args.extras else [args.config]
         if "c1" in want:

@@ -23,7 +23,18 @@ save = [c.names.index("s1"), c.names.index(f"s{n_stages // 2}"), c.names.index("
 b = s21.Batch(c, B)
 for k, v in ovr.items():
     b.override(k, v)
-for rep in range(2):
+# experiments (profiles/r02E_c4_modes.txt): what bench.py does around the same batch
+if os.environ.get("RUNC4_TORCH"):
+    import torch
+    torch.cuda.set_device(0)
+    _stream = torch.cuda.Stream()
+    torch.cuda.set_stream(_stream)
+    if os.environ.get("RUNC4_TORCH") == "2":
+        _flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+    b.set_stream(_stream.cuda_stream)
+for rep in range(int(os.environ.get("RUNC4_REPS", "2"))):
+    if os.environ.get("RUNC4_FORCE"):
+        b.sync_params(force_upload=True)
     b.reset()
     t0 = time.time()
     t, wave, status, iters = b.tran(tstep, n_points * tstep, save=save)

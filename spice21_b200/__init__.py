@@ -451,7 +451,7 @@ class Batch:
         T = lib().s21_tran_num_points(tstep, tstop)
         save = np.arange(self.N, dtype=np.int32) if save is None else np.ascontiguousarray(save, dtype=np.int32)
         time = np.zeros(T)
-        wave = np.zeros((self.B, T, len(save))) if want_wave else None
+        wave = np.empty((self.B, T, len(save))) if want_wave else None  # every entry is written by the library
         status = np.zeros(self.B, dtype=np.int32)
         iters = np.zeros(self.B, dtype=np.int64)
         _check(lib().s21_batch_tran(self.h, tstep, tstop, save.ctypes.data_as(C.c_void_p), len(save), time.ctypes.data_as(C.c_void_p),
@@ -474,7 +474,7 @@ class Batch:
 
     def ac(self, freqs):
         f = np.ascontiguousarray(freqs, dtype=np.float64)
-        x = np.zeros((len(f), self.N, 2))
+        x = np.empty((len(f), self.N, 2))  # every entry is written by the library
         status = np.zeros(len(f), dtype=np.int32)
         iters = np.zeros(len(f), dtype=np.int32)
         _check(lib().s21_batch_ac(self.h, f.ctypes.data_as(C.c_void_p), len(f), x.ctypes.data_as(C.c_void_p),

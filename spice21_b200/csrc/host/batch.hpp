@@ -193,6 +193,8 @@ class Batch {
     // Instance stride of every per-instance table. Rounded to a warp for batches; a single large circuit (C3) keeps its
     // tables dense instead — with stride 32 its 4 M L+U values would be spread over 1 GB and miss L2 on every access.
     Bs_ = (B_ == 1 && N > 96) ? 1 : (B_ + 31) / 32 * 32;
+    // (a stride padded to an odd multiple of 32 instances, against power-of-two strides between table entries, was measured on
+    // C4: default kernel 180 -> 199 ms, reciprocal-division kernel unchanged — not done; profiles/r02C_c4_modes.txt)
     // shared device tables
     std::vector<int> type, ioff, poff, soff;
     for (const FlatDev& d : flat_.devs) { type.push_back(d.type); ioff.push_back(d.itab_off); poff.push_back(d.par_off); soff.push_back(d.state_off); }
@@ -727,17 +729,36 @@ class Batch {
     phase("time loop kernel");
     if (info && last_kernel_ == "grid") grid_phase_report();
     last_plan_ = &tran_plan_;
-    if (wave) {
-      hwave_.alloc((size_t)T * n_save * Bs_);
-      S21_CUDA(cudaMemcpyAsync(hwave_.p, d_wave_.p, (size_t)T * n_save * Bs_ * sizeof(double), cudaMemcpyDeviceToHost, stream_));
-    }
+    const bool packed = wave && wave_fetch_begin(T, n_save);
     std::vector<int32_t> it32(B_);
     read(nullptr, status, it32.data());
     if (iters) for (size_t i = 0; i < B_; i++) iters[i] = it32[i];
-    if (wave)
-      for (size_t i = 0; i < B_; i++)
-        for (int t = 0; t < T; t++)
-          for (size_t s = 0; s < n_save; s++) wave[(i * (size_t)T + (size_t)t) * n_save + s] = hwave_.p[((size_t)t * n_save + s) * Bs_ + i];
+    if (wave) wave_fetch_end(packed, T, n_save, wave);
+  }
+  // Waveforms to the caller's [instance][time point][saved variable] layout: transposed on the device (k_pack_wave), one
+  // contiguous D2H into pinned memory, one memcpy. Falls back to the strided host pass when the launch is refused.
+  bool wave_fetch_begin(int T, size_t n_save) {
+    const size_t M = (size_t)T * n_save;
+    bool packed = false;
+    if (!std::getenv("S21_WAVE_HOST_TRANSPOSE")) {
+      d_wave_rows_.alloc(B_ * M);
+      packed = launch_pack_wave(d_wave_.p, d_wave_rows_.p, M, Bs_, (int)B_, stream_) == 0;
+      if (packed) launches_++;
+    }
+    if (packed) {
+      hwave_.alloc(B_ * M);
+      S21_CUDA(cudaMemcpyAsync(hwave_.p, d_wave_rows_.p, B_ * M * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    } else {
+      hwave_.alloc(M * Bs_);
+      S21_CUDA(cudaMemcpyAsync(hwave_.p, d_wave_.p, M * Bs_ * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    }
+    return packed;
+  }
+  void wave_fetch_end(bool packed, int T, size_t n_save, double* wave) {  // after a stream synchronise (read())
+    const size_t M = (size_t)T * n_save;
+    if (packed) { std::memcpy(wave, hwave_.p, B_ * M * sizeof(double)); return; }
+    for (size_t i = 0; i < B_; i++)
+      for (size_t m = 0; m < M; m++) wave[i * M + m] = hwave_.p[m * Bs_ + i];
   }
 
   // ---- adaptive transient (opt-in) -------------------------------------------------------------------
@@ -780,10 +801,7 @@ class Batch {
     if (rc) throw S21Error(ST_CUDA, std::string("adaptive tran kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
     S21_CUDA(cudaEventRecord(ev1_, stream_)); ev_pair_ = true;
     last_plan_ = &tran_plan_;
-    if (wave) {
-      hwave_.alloc((size_t)T * n_save * Bs_);
-      S21_CUDA(cudaMemcpyAsync(hwave_.p, d_wave_.p, (size_t)T * n_save * Bs_ * sizeof(double), cudaMemcpyDeviceToHost, stream_));
-    }
+    const bool packed = wave && wave_fetch_begin(T, n_save);
     std::vector<int32_t> acc(Bs_), rej(Bs_), it32(B_);
     S21_CUDA(cudaMemcpyAsync(acc.data(), ad_acc_.p, Bs_ * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
     S21_CUDA(cudaMemcpyAsync(rej.data(), ad_rej_.p, Bs_ * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
@@ -793,10 +811,7 @@ class Batch {
       if (accepted) accepted[i] = acc[i];
       if (rejected) rejected[i] = rej[i];
     }
-    if (wave)
-      for (size_t i = 0; i < B_; i++)
-        for (int t = 0; t < T; t++)
-          for (size_t s2 = 0; s2 < n_save; s2++) wave[(i * (size_t)T + (size_t)t) * n_save + s2] = hwave_.p[((size_t)t * n_save + s2) * Bs_ + i];
+    if (wave) wave_fetch_end(packed, T, n_save, wave);
   }
 
   // ---- ac: frequency points are the batch axis of circuit instance 0 ------------------------------------------
@@ -881,9 +896,24 @@ class Batch {
     if (rc) throw S21Error(ST_CUDA, std::string("ac kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
     S21_CUDA(cudaEventRecord(ev1_, stream_)); ev_pair_ = true;
     last_plan_ = &ac_plan_;
-    std::vector<cplx> hx((size_t)N * Fs);
+    // x leaves the kernels as [variable][frequency point]; the caller's layout is [frequency point][variable]: transposed on
+    // the device and copied straight into the caller's buffer (100 000 points x 73 variables = 117 MB: the strided host
+    // pass over a pageable staging vector was ~60 of the sweep's 79 ms end to end)
+    bool x_packed = false;
+    std::vector<cplx> hx;
+    if (x_out) {
+      if (!std::getenv("S21_WAVE_HOST_TRANSPOSE")) {
+        zrows_.alloc(F * (size_t)N);
+        x_packed = launch_pack_ac(zx_.p, zrows_.p, (size_t)N, Fs, (int)F, stream_) == 0;
+        if (x_packed) launches_++;
+      }
+      if (x_packed) S21_CUDA(cudaMemcpyAsync(x_out, zrows_.p, F * (size_t)N * sizeof(cplx), cudaMemcpyDeviceToHost, stream_));
+      else {
+        hx.resize((size_t)N * Fs);
+        S21_CUDA(cudaMemcpyAsync(hx.data(), zx_.p, hx.size() * sizeof(cplx), cudaMemcpyDeviceToHost, stream_));
+      }
+    }
     std::vector<int32_t> hs(Fs), hi(Fs), hl(Fs);
-    S21_CUDA(cudaMemcpyAsync(hx.data(), zx_.p, hx.size() * sizeof(cplx), cudaMemcpyDeviceToHost, stream_));
     S21_CUDA(cudaMemcpyAsync(hs.data(), ac_status_.p, Fs * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
     S21_CUDA(cudaMemcpyAsync(hi.data(), ac_iters_.p, Fs * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
     S21_CUDA(cudaMemcpyAsync(hl.data(), ac_loads_.p, Fs * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
@@ -893,7 +923,7 @@ class Batch {
       if (status) status[f] = hs[f];
       if (iters) iters[f] = hi[f];
       sum_iters_ += hi[f]; sum_loads_ += hl[f];
-      if (x_out)
+      if (x_out && !x_packed)
         for (int k = 0; k < N; k++) {
           x_out[(f * (size_t)N + (size_t)k) * 2 + 0] = hx[(size_t)k * Fs + f].re;
           x_out[(f * (size_t)N + (size_t)k) * 2 + 1] = hx[(size_t)k * Fs + f].im;
@@ -1016,6 +1046,7 @@ class Batch {
   DBuf<cplx> zx_, zrhs_, zc_, zlu_;
   DBuf<int32_t> status_, iters_, loads_, ac_status_, ac_iters_, ac_loads_;
   PinnedBuf<double> pval_h_, hx_, hwave_;
+  DBuf<double> d_wave_rows_;  // waveforms in the caller's layout (k_pack_wave)
   double* ext_x_ = nullptr;       // set_result_target
   size_t wave_T_ = 0, wave_ns_ = 0;
   int repair_depth_ = 0;
@@ -1049,6 +1080,7 @@ class Batch {
   DBuf<int> d_stage_off_, d_eval_order_;
   DBuf<double> d_stage_;
   DBuf<cplx> zstage_;
+  DBuf<cplx> zrows_;  // AC results in the caller's layout (launch_pack_ac)
   bool b4_fast_ = false;  // S21_B4_FAST=1: Bsim4 batches on the cooperative kernel run kernels/coop_fast.cu
   bool use_coop_ = true, allow_hybrid_ = true, allow_jit_ = true, jit_forced_ = false, jit_team_forced_ = false, ac_kernel_forced_ = false;
   std::string jit_error_;  // why the specialised kernel is not in use (empty when it is, or was never wanted)

@@ -20,6 +20,8 @@
 //
 // Replaces the same reference functions as newton.cu (analysis.rs:153-210, 253-303, 331-345, 553-570;
 // sparse21/mod.rs:272-327, 865-991).
+#include <cstdlib>
+
 #include "coop_common.cuh"
 
 namespace s21 {
@@ -349,6 +351,8 @@ int launch_b4(const DevTables& d, const PlanTables& p, const CoopTables& ct, con
     auto kern = k_coop<T, KIND, 2, B4>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
+    if (const char* cv = std::getenv("S21_COOP_CARVEOUT"))  // measurement: shared-memory share of the L1 / shared array, in percent
+      cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(cv));
     kern<<<grid, cfg.threads, smem, (cudaStream_t)stream>>>(d, p, ct, w, stage, o, c, a);
   } else if (cfg.smem_bytes > 0) {
     auto kern = k_coop<T, KIND, 1, B4>;

@@ -212,6 +212,9 @@ int launch_ac(const DevTables& d, const PlanTables& p, const WorkTables<cplx>& w
 // Result packing on the device: out = [x as [instance][variable], B*N f64][status B i32][iters B i32][loads B i32].
 int launch_pack_out(const double* x, const int32_t* status, const int32_t* iters, const int32_t* loads, double* out, int N, size_t stride, int B,
                     void* stream);
+// Waveform packing on the device: wave [M = T * n_save][stride] (instance fastest) -> out [B][M], the caller's layout.
+int launch_pack_wave(const double* wave, double* out, size_t M, size_t stride, int B, void* stream);
+int launch_pack_ac(const cplx* x, cplx* out, size_t N, size_t stride, int F, void* stream);  // x [N][stride] -> out [F][N]
 // First load sweep of instance `inst` in `mode`, assembled by raw element id into out[n_elems] (device memory).
 int launch_probe_real(const DevTables& d, const WorkTables<double>& w, const SolveCtl& c, int n_elems, int N, int inst, double* out, void* stream);
 int launch_probe_cplx(const DevTables& d, const WorkTables<cplx>& w, const SolveCtl& c, int n_elems, int N, int inst, cplx* out, void* stream);

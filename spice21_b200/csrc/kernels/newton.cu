@@ -432,6 +432,36 @@ int launch_pack_out(const double* x, const int32_t* status, const int32_t* iters
   k_pack_out<<<grid_for(B, 128), 128, 0, (cudaStream_t)stream>>>(x, status, iters, loads, out, N, stride, B);
   return (int)cudaGetLastError();
 }
+// Waveforms leave the time loops as [time point][saved variable][instance] (instance fastest: coalesced stores from every
+// kernel family); the caller's layout is [instance][time point][saved variable]. A tiled transpose of the [M][stride]
+// matrix, M = T * n_save, so that the host needs one contiguous copy instead of a strided pass over 40 MB (C1 sweep:
+// 8192 instances x 201 points x 3 signals took ~20 ms on the host).
+template <class T>
+__global__ void k_pack_wave(const T* __restrict__ w, T* __restrict__ out, size_t M, size_t stride, int B) {
+  __shared__ T tile[32][33];
+  const size_t m0 = (size_t)blockIdx.y * 32, i0 = (size_t)blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const size_t m = m0 + r, i = i0 + threadIdx.x;
+    tile[r][threadIdx.x] = (m < M && i < (size_t)B) ? w[m * stride + i] : Scalar<T>::zero();
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const size_t i = i0 + r, m = m0 + threadIdx.x;
+    if (i < (size_t)B && m < M) out[i * M + m] = tile[threadIdx.x][r];
+  }
+}
+template <class T>
+static int pack_rows(const T* w, T* out, size_t M, size_t stride, int B, void* stream) {
+  if (M == 0 || B <= 0) return 0;
+  const size_t gy = (M + 31) / 32;
+  if (gy > 65535) return (int)cudaErrorInvalidConfiguration;  // the caller falls back to the host transpose
+  dim3 grid((unsigned)((B + 31) / 32), (unsigned)gy), block(32, 8);
+  k_pack_wave<T><<<grid, block, 0, (cudaStream_t)stream>>>(w, out, M, stride, B);
+  return (int)cudaGetLastError();
+}
+int launch_pack_wave(const double* wave, double* out, size_t M, size_t stride, int B, void* stream) { return pack_rows<double>(wave, out, M, stride, B, stream); }
+// the same for an AC sweep: x [variable][frequency point] (complex) -> out [frequency point][variable]
+int launch_pack_ac(const cplx* x, cplx* out, size_t N, size_t stride, int F, void* stream) { return pack_rows<cplx>(x, out, N, stride, F, stream); }
 int launch_probe_real(const DevTables& d, const WorkTables<double>& w, const SolveCtl& c, int n_elems, int N, int inst, double* out, void* stream) {
   k_probe<double><<<1, 32, 0, (cudaStream_t)stream>>>(d, w, c, n_elems, N, inst, out);
   return (int)cudaGetLastError();
