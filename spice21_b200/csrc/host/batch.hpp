@@ -555,6 +555,66 @@ class Batch {
     }
     rows_fresh_ = false; host_rows_fresh_ = false;
   }
+  static bool tran_stop_enabled() { const char* e = std::getenv("S21_TRAN_REPIVOT"); return !e || std::atoi(e) != 0; }
+  // Re-pivoting INSIDE a transient (cooperative kernel). The time loop runs on the pivot order frozen at its first iteration;
+  // the reference takes a new order in every factorisation (sparse21/mod.rs:930-932). An instance whose frozen order meets an
+  // exactly zero pivot — or a vanishing one: a non-finite step — at some time point goes back to its last accepted point and
+  // comes back with ST_REPIVOT_CODE and that time point (SolveCtl::tran_stop). Round by round, as for a dcop: the first such
+  // instance's load sweep at that point is probed, the reference's Markowitz search orders that matrix, and the kernel is
+  // relaunched in resume mode — only those instances run, each from its own time point to the end, against the new order;
+  // whichever stops again goes into the next round. S21_TRAN_REPIVOT=0 restores the earlier behaviour (Singular Matrix).
+  void resolve_tran_stops(double tstep, int T, size_t n_save) {
+    hstatus_.alloc(Bs_);
+    S21_CUDA(cudaMemcpyAsync(hstatus_.p, status_.p, B_ * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+    S21_CUDA(cudaStreamSynchronize(stream_));
+    std::vector<size_t> open;
+    for (size_t i = 0; i < B_; i++) if (hstatus_.p[i] == ST_REPIVOT_CODE) open.push_back(i);
+    if (open.empty()) return;
+    weak_seen_ += (long long)open.size();
+    const int N = flat_.n_vars();
+    const size_t budget = std::max<size_t>(10000000, (size_t)4000 * (size_t)N);
+    auto give_up = [&](size_t i, int32_t st) {
+      S21_CUDA(cudaMemcpyAsync(status_.p + i, &st, sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
+      S21_CUDA(cudaStreamSynchronize(stream_));
+    };
+    const bool info = std::getenv("S21_PLAN_INFO") != nullptr;
+    for (int round = 0; round < 64 && !open.empty(); round++) {
+      repair_plan_.valid = false;
+      ensure_plan(repair_plan_, AN_TRAN, tstep, open[0], budget);
+      if (info) {
+        int tp0 = -1;
+        cudaMemcpy(&tp0, tp_stop_.p + open[0], sizeof(int), cudaMemcpyDeviceToHost);
+        std::fprintf(stderr, "[s21 tran] re-pivot round %d: %zu instances handed back, first = %zu at time point %d, plan status %d\n", round,
+                     open.size(), open[0], tp0, repair_plan_.host.status);
+      }
+      if (repair_plan_.host.status != ST_OK) {  // the reference's own factorisation fails on this matrix
+        give_up(open[0], repair_plan_.host.status);
+        open.erase(open.begin());
+        continue;
+      }
+      SolveCtl ctl = make_ctl(AN_TRAN, tstep, &repair_plan_);
+      ctl.tran_stop = 1; ctl.resume = 1;
+      CoopCfg cfg = coop_cfg(repair_plan_, B_, 1);
+      cfg.tp_stop = tp_stop_.p; cfg.x_acc = x_acc_.p;
+      const bool fast = b4_fast_ && ctl.has_bsim4;
+      int rc = (fast ? launch_coop_tran_fast : launch_coop_tran)(coop_dev(repair_plan_), repair_plan_.coop_plan(), repair_plan_.coop(), work(),
+                                                                 stage_for(cfg, repair_plan_.host), out(), ctl, cfg, T, d_save_.p, (int)n_save,
+                                                                 d_wave_.p, stream_);
+      launches_++;
+      if (rc) throw S21Error(ST_CUDA, std::string("tran resume launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+      S21_CUDA(cudaMemcpyAsync(hstatus_.p, status_.p, B_ * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+      S21_CUDA(cudaStreamSynchronize(stream_));
+      repivot_rounds_++;
+      std::vector<size_t> next;
+      for (size_t i : open) {
+        if (hstatus_.p[i] == ST_REPIVOT_CODE) next.push_back(i);
+        else repaired_++;
+      }
+      open.swap(next);
+    }
+    for (size_t i : open) give_up(i, ST_SINGULAR);  // 64 rounds without settling
+    rows_fresh_ = false; host_rows_fresh_ = false;
+  }
   static bool pivot_stop_enabled() { const char* e = std::getenv("S21_PIVOT_HEALTH"); return !e || std::atoi(e) != 0; }
   static bool pivot_repair_enabled() { const char* e = std::getenv("S21_PIVOT_REPAIR"); return !e || std::atoi(e) != 0; }
   // Per-instance re-pivoting (first half): continue, IN PLACE, the instances a kernel stopped with
@@ -578,6 +638,7 @@ class Batch {
       S21_CUDA(cudaMemcpyAsync(status_.p, hstatus_.p, B_ * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
     }
     const size_t budget = std::max<size_t>(10000000, (size_t)4000 * (size_t)N);
+    std::vector<int> sing_retries_(B_, 0);
     for (int round = 0; round < 256 && !open.empty(); round++) {
       repair_plan_.valid = false;
       ensure_plan(repair_plan_, AN_OP, 0.0, open[0], budget);
@@ -593,12 +654,20 @@ class Batch {
       S21_CUDA(cudaMemcpyAsync(hstatus_.p, status_.p, B_ * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
       S21_CUDA(cudaStreamSynchronize(stream_));
       repivot_rounds_++;
+      // An order taken at open[0]'s matrix can hold an exactly zero pivot for ANOTHER instance (its devices sit in other
+      // regions): the kernel reports Singular Matrix with x untouched. That instance is not singular under an order of its
+      // own — it stays open (measured on the plain 41-stage Bsim4 ring: 7 of 16 supplies ended their OP with Singular Matrix
+      // after 2 iterations inside the batch, every one of them converges alone). Truly singular matrices end when they head
+      // the list: the host's own factorisation then says so. A few retries per instance bound the loop.
       std::vector<size_t> next;
+      bool rewrite_st = false;
       for (size_t i : open) {
         hs[i] = hstatus_.p[i];
+        if (hs[i] == ST_SINGULAR && sing_retries_[i] < 8) { sing_retries_[i]++; hs[i] = ST_REPIVOT_CODE; hstatus_.p[i] = ST_REPIVOT_CODE; rewrite_st = true; }
         if (hs[i] == ST_REPIVOT_CODE) next.push_back(i);
         else repaired_++;
       }
+      if (rewrite_st) S21_CUDA(cudaMemcpyAsync(status_.p, hstatus_.p, B_ * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
       open.swap(next);
     }
     for (size_t i : open) {  // 256 rounds without settling
@@ -696,6 +765,7 @@ class Batch {
     DevTables dt = dev_tables(tran_plan_.itab.p);
     SolveCtl ctl = make_ctl(AN_TRAN, tstep);
     int rc = 0;
+    bool coop_tran_stop = false;
     if (tran_plan_.host.status != ST_OK) {
       throw S21Error(tran_plan_.host.status, status_text(tran_plan_.host.status));
     } else if (const jit::Kernel* jk = jit_kernel(tran_plan_, true)) {
@@ -716,6 +786,13 @@ class Batch {
       CoopCfg cfg = coop_cfg(tran_plan_, B_, 1);
       const bool fast = b4_fast_ && ctl.has_bsim4;
       last_kernel_ = fast ? "coop-rcp" : "coop";
+      coop_tran_stop = tran_stop_enabled();
+      if (coop_tran_stop) {  // instances whose frozen order fails inside the time loop come back for a pivot order of their own
+        ctl.tran_stop = 1;
+        if (const char* inj = std::getenv("S21_TRAN_INJECT")) ctl.tran_inject_tp = std::atoi(inj);
+        tp_stop_.alloc(Bs_); x_acc_.alloc((size_t)flat_.n_vars() * Bs_);
+        cfg.tp_stop = tp_stop_.p; cfg.x_acc = x_acc_.p;
+      }
       rc = (fast ? launch_coop_tran_fast : launch_coop_tran)(coop_dev(tran_plan_), tran_plan_.coop_plan(), tran_plan_.coop(), work(),
                                                              stage_for(cfg, tran_plan_.host), out(), ctl, cfg, T, d_save_.p, (int)n_save,
                                                              d_wave_.p, stream_);
@@ -729,6 +806,10 @@ class Batch {
     phase("time loop kernel");
     if (info && last_kernel_ == "grid") grid_phase_report();
     last_plan_ = &tran_plan_;
+    if (coop_tran_stop) {
+      resolve_tran_stops(tstep, T, n_save);
+      phase("time loop: re-pivot + resume");
+    }
     const bool packed = wave && wave_fetch_begin(T, n_save);
     std::vector<int32_t> it32(B_);
     read(nullptr, status, it32.data());
@@ -1047,6 +1128,8 @@ class Batch {
   DBuf<int32_t> status_, iters_, loads_, ac_status_, ac_iters_, ac_loads_;
   PinnedBuf<double> pval_h_, hx_, hwave_;
   DBuf<double> d_wave_rows_;  // waveforms in the caller's layout (k_pack_wave)
+  DBuf<int> tp_stop_;         // cooperative transient kernel: time point at which an instance was handed back (resolve_tran_stops)
+  DBuf<double> x_acc_;        // ... and every instance's x at its last accepted time point
   double* ext_x_ = nullptr;       // set_result_target
   size_t wave_T_ = 0, wave_ns_ = 0;
   int repair_depth_ = 0;

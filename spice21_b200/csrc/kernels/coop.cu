@@ -61,7 +61,9 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
   int* convnow = nld + gi;
   int* weak = convnow + gi;  // pivot health: a frozen pivot the reference's threshold test would have refused (mod.rs:735-783)
   int* left = weak + gi;     // resume: iterations this instance's solve has left; < 0 = not a stopped instance, leave it alone
-  uint64_t* mbar = (uint64_t*)(((size_t)(left + gi) + 7) & ~(size_t)7);  // 10 int arrays: 8-byte alignment is not automatic
+  int* start = left + gi;    // transient: first time point this instance takes part in (1; a resumed instance: where it stopped)
+  int* stopat = start + gi;  // transient: time point at which this launch stopped the instance for the host to re-pivot (0 = not)
+  uint64_t* mbar = (uint64_t*)(((size_t)(stopat + gi) + 7) & ~(size_t)7);  // 12 int arrays: 8-byte alignment is not automatic
   size_t off = ((size_t)((unsigned char*)(mbar + 1) - smem_raw) + 15) / 16 * 16;
   if (a.arena_bytes > 0) {
     int* sa = (int*)(smem_raw + off);
@@ -124,6 +126,12 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
         left[tid] = -1;
       }
     }
+    start[tid] = 1; stopat[tid] = 0;
+    if (KIND == K_TRAN && ctl.resume) {  // continue, from the time point where they stopped, the instances a transient launch handed back
+      const int s0 = tid < ni ? o.status[i0 + tid] : 0;
+      if (tid < ni && s0 == CST_REPIVOT) { stat[tid] = CST_OK; start[tid] = a.tp_stop[i0 + tid]; }
+      else { stat[tid] = s0; left[tid] = -1; }
+    }
     weak[tid] = 0;
     nsol[tid] = 0; nld[tid] = 0; convnow[tid] = 0; dxok[tid] = 1; act[tid] = 0;
   }
@@ -140,8 +148,9 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
   if (a.arena_bytes > 0) mbar_wait(mbar, 0);
   __syncthreads();
   if constexpr (KIND == K_TRAN) {
-    for (int s = item0; s < a.n_save; s += istep)
-      if (valid) a.wave[(size_t)s * g.stride + i0 + li] = x[(I)a.save_vars[s] * ws + col];
+    if (!ctl.resume)
+      for (int s = item0; s < a.n_save; s += istep)
+        if (valid) a.wave[(size_t)s * g.stride + i0 + li] = x[(I)a.save_vars[s] * ws + col];
   }
   const double vtol = real_kind ? ctl.reltol : 1e-3, itol = real_kind ? ctl.iabstol : 1e-9;  // analysis.rs:271-272, 331-345
   const int n_points = KIND == K_TRAN ? a.T_points : 2;
@@ -151,8 +160,14 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
 
   double tnow = KIND == K_TRAN ? ctl.dt : 0.0;  // analysis.rs:552-569: t starts at tstep and accumulates tstep
   for (int tp = 1; tp < n_points; tp++, tnow += ctl.dt) {
-    if (tid < gi) { act[tid] = (tid < ni && stat[tid] == CST_OK && left[tid] > 0) ? 1 : 0; dxok[tid] = 1; }
+    if (tid < gi) { act[tid] = (tid < ni && stat[tid] == CST_OK && left[tid] > 0 && tp >= start[tid]) ? 1 : 0; dxok[tid] = 1; }
     __syncthreads();
+    if constexpr (KIND == K_TRAN && real_kind) {
+      if (ctl.resume && !__syncthreads_or(tid < gi && act[tid])) continue;  // nothing of this CTA has reached its time point yet
+      // the last accepted point: what a stopped instance goes back to (SolveCtl::tran_stop)
+      if (ctl.tran_stop && act[li] != 0)
+        for (int k = item0; k < N; k += istep) a.x_acc[(size_t)k * g.stride + i0 + li] = x[(I)k * ws + col];
+    }
     const int max_it = real_kind ? min(TolC<T>::max_iter, ctl.max_iter) : TolC<T>::max_iter;
     for (int iter = 0; iter < max_it; iter++) {
       const bool on = act[li] != 0;  // stable until the decision phase (which is fenced by barriers on both sides)
@@ -274,7 +289,10 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
           if (k + 1 < N && s_is_zero(lu[(I)p.diag_slot[k] * ws + col])) sing[li] = 1;
           const double v = s_abs(c[(I)p.col_e2i[k] * ws + col]);
           if (v > m) m = v;
+          // a vanishing (not exactly zero) frozen pivot shows as a non-finite step: where the host can re-pivot, hand it back too
+          if (KIND == K_TRAN && ctl.tran_stop && !(v <= 1.7976931348623157e308)) weak[li] = 1;
         }
+        if (KIND == K_TRAN && ctl.tran_stop && !ctl.resume && ctl.tran_inject_tp == tp && iter == 1) weak[li] = 1;  // test hook
         if (m > 0.0) atomicMax((unsigned long long*)&maxabs[li], (unsigned long long)__double_as_longlong(m));
       }
       __syncthreads();
@@ -291,7 +309,11 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
       }
       __syncthreads();
       if (tid < gi && act[tid]) {
-        if (sing[tid]) { act[tid] = 0; stat[tid] = CST_SINGULAR; }
+        if (KIND == K_TRAN && ctl.tran_stop && (sing[tid] || weak[tid])) {
+          // inside the time loop: back to the last accepted point (below), the host takes a pivot order there and resumes
+          act[tid] = 0; stat[tid] = CST_REPIVOT; stopat[tid] = tp; a.tp_stop[i0 + tid] = tp;
+        }
+        else if (sing[tid]) { act[tid] = 0; stat[tid] = CST_SINGULAR; }
         else if (weak[tid]) { act[tid] = 0; stat[tid] = CST_REPIVOT; }  // x untouched: the host re-pivots at this iterate and continues
         else {
           nsol[tid] += 1;
@@ -304,7 +326,11 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
     if (tid < gi && act[tid]) { stat[tid] = CST_CONV; act[tid] = 0; }  // "Convergence Failed" (analysis.rs:209, 302)
     __syncthreads();
     if constexpr (KIND == K_TRAN) {
-      if (valid) {
+      if (real_kind && ctl.tran_stop && stopat[li] == tp && tp > 0) {  // stopped at this point: x and the in-flight state as the point began
+        for (int k = item0; k < N; k += istep) x[(I)k * ws + col] = a.x_acc[(size_t)k * g.stride + i0 + li];
+        for (int k = item0; k < d.n_state; k += istep) sguess[(IS)k * ss + scol] = sop[(IS)k * ss + scol];
+      }
+      if (valid && left[li] > 0 && tp >= start[li]) {  // an instance this launch leaves alone keeps its waveform
         const bool good = stat[li] == CST_OK;
         for (int s = item0; s < a.n_save; s += istep)
           a.wave[((size_t)tp * a.n_save + s) * g.stride + i0 + li] =
@@ -334,13 +360,14 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
   }
 }
 
-size_t ctrl_bytes(int gi) { return ((8 + 10 * 4) * (size_t)gi + 8 + 8 + 15) / 16 * 16; }
+size_t ctrl_bytes(int gi) { return ((8 + 12 * 4) * (size_t)gi + 8 + 8 + 15) / 16 * 16; }
 
 template <class T, int KIND, bool B4>
 int launch_b4(const DevTables& d, const PlanTables& p, const CoopTables& ct, const WorkTables<T>& w, T* stage, const NewtonOut& o,
            const SolveCtl& c, const CoopCfg& cfg, int T_points, const int* save_vars, int n_save, double* wave, void* stream) {
   CoopArgs a;
   a.lg_gi = 0; a.gi = cfg.gi; a.cold = 0; a.T_points = T_points; a.n_save = n_save; a.save_vars = save_vars; a.wave = wave;
+  a.tp_stop = cfg.tp_stop; a.x_acc = cfg.x_acc;
   a.arena = cfg.arena;
   a.pcode_global = cfg.arena_in_smem && cfg.arena_core_bytes > 0 ? 1 : 0;
   a.arena_bytes = cfg.arena_in_smem ? (int)(a.pcode_global ? cfg.arena_core_bytes : cfg.arena_bytes) : 0;

@@ -133,6 +133,10 @@ struct CoopArgs {
   const int* arena;      // packed index tables in HBM (all table pointers point into it)
   int arena_bytes;       // > 0: copy the arena into shared memory with TMA and rebase the pointers
   int pcode_global;      // cooperative kernel: the copy stops short of the parameter-code table (last in the arena), which stays in HBM
+  // cooperative transient kernel with SolveCtl::tran_stop / resume: [B] time point at which an instance was handed back (and
+  // resumes), [N][stride] x of every instance at its last accepted time point
+  int* tp_stop = nullptr;
+  double* x_acc = nullptr;
 };
 
 

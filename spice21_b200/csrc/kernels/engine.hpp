@@ -97,6 +97,12 @@ struct SolveCtl {
   // from the iterate where they stopped, against the pivot order of THIS launch's plan, with the iterations their solve has left
   // (max_iter - (iters - iters_base)); every other instance keeps its x, device state, status and counters untouched.
   int resume = 0;
+  // Cooperative transient kernel only. 1: an instance whose frozen pivot order fails INSIDE the time loop (an exactly zero pivot,
+  // or a non-finite step from a vanishing one) is not ended with Singular Matrix: it goes back to its last accepted time
+  // point and stops with ST_REPIVOT_CODE and the time point recorded, and the host continues it — pivot order taken at that
+  // iterate, a resume launch (resume = 1) that runs only those instances from their own time point on.
+  int tran_stop = 0;
+  int tran_inject_tp = 0;  // test hook (S21_TRAN_INJECT): every instance is handed back once, in the second iteration of this time point
   int relaxed = 0;         // the plan's level schedules are in tolerance mode (host/symbolic.hpp build_levels): apply updates atomically
   int has_bsim4 = 0;       // selects the kernel build that links the Bsim4 evaluation (kept out of the others: register pressure)
 };
@@ -141,6 +147,9 @@ struct CoopCfg {
   // cooperative kernel: smem_bytes covers x, rhs, residual and the L+U values only (coop_mixed_bytes); the stamp staging area
   // (`stage` must be given) and the device state stay in HBM/L2
   bool mixed = false;
+  // cooperative transient kernel with SolveCtl::tran_stop / resume (CoopArgs::tp_stop / x_acc)
+  int* tp_stop = nullptr;
+  double* x_acc = nullptr;
 };
 // Shared-memory budget of one CTA: control words + (optional) arena copy + workspace.
 size_t coop_ctrl_bytes(int gi);

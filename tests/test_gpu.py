@@ -1149,14 +1149,10 @@ def test_bsim4_fast_division_within_tolerance(s21, oracle, monkeypatch):
     print(f"fast division: status {status.tolist()}, max |fast - default| = {float(np.max(np.abs(wave[okp] - wd[okp]))):.3e}, "
           f"max |fast - oracle| = {float(np.max(np.abs(wave[okp] - o['x'][okp]))):.3e}, Newton iterations "
           f"{int(iters[okp].sum())} vs {int(itd[okp].sum())}")
-    # A device-resident time loop runs on the pivot order frozen at its first iteration (nobody can re-pivot inside it,
-    # DESIGN.md §4): an instance whose iterate drives a frozen pivot to exactly zero stops with S21_SINGULAR_MATRIX — with
-    # the default kernel on other circuits (test_c4x_...), and here, with last bits that differ, on one supply voltage of
-    # the 24 (measured: instance 17; the same supply converges inside the 2048-instance bench batch, whose OP repair takes
-    # its order from another instance). It is reported, never returned as a result; every other instance must agree.
+    # (before the OP repair kept instances that are singular under ANOTHER instance's pivot order open, instance 17 of this
+    # sweep ended its operating point with Singular Matrix under this kernel's last bits — resolve_repivot, host/batch.hpp)
     ok = status == 0
-    assert np.all(o["status"] == 0) and np.all(sd == 0)
-    assert int(np.sum(ok)) >= B - 2 and np.all(np.isin(status[~ok], [s21.S21_SINGULAR_MATRIX]))
+    assert np.all(o["status"] == 0) and np.all(sd == 0) and np.all(ok)
     tol = 1e-6 + 1e-3 * np.abs(o["x"][ok])
     assert np.all(np.abs(wave[ok] - o["x"][ok]) <= tol)
     assert np.max(np.abs(wave[ok] - o["x"][ok])) <= 1e-6  # in fact far inside vntol on this circuit
@@ -1190,7 +1186,8 @@ def test_c4x_41_stage_ring_with_internal_nodes_matches_oracle(s21, oracle):
     reference's loop (a Newton iteration that cycles until the 100-iteration cap): where both sides converge the waveforms
     and iteration counts must agree; a cycling iteration is sensitive to the last bits (the frozen pivot order rounds
     differently from the reference's per-iteration order), so single instances may fall on the other side of the cap —
-    the outcome must agree for at least 13 of the 16, and no instance may return a wrong waveform as converged."""
+    the outcome must agree for at least 14 of the 16 (measured: all 16), and no instance may return a wrong waveform as converged.
+    The plain-card 41-stage ring (N = 47) converges at every supply in the reference, and here."""
     ck, ic = cc.bsim4_ring(41, ic_every=20, rbodymod=1, rgatemod=1)
     c = ck.to_s21().elaborate(ic=ic)
     assert c.n_vars == 375 and sorted(ic) == ["s0", "s20"]   # 373 circuit unknowns + the second IC's source branch pair
@@ -1209,7 +1206,7 @@ def test_c4x_41_stage_ring_with_internal_nodes_matches_oracle(s21, oracle):
     # how a caller tells. It is counted as failed here.
     gpu_failed = (status != 0) | np.any(~np.isfinite(wave), axis=(1, 2))
     same = gpu_failed == (o["status"] != 0)
-    assert int(np.sum(same)) >= 13, (status, gpu_failed, o["status"])
+    assert int(np.sum(same)) >= 14, (status, gpu_failed, o["status"])
     ok = ~gpu_failed & (o["status"] == 0)
     assert 4 <= int(np.sum(ok)) < B
     assert np.max(np.abs(wave[ok] - o["x"][ok][:, :, save])) <= 1e-7
@@ -1219,19 +1216,45 @@ def test_c4x_41_stage_ring_with_internal_nodes_matches_oracle(s21, oracle):
     assert np.all(np.abs(iters[ok] - o["iters"][ok]) <= 0.15 * o["iters"][ok]), (iters[ok], o["iters"][ok])
     only_gpu = ~gpu_failed & (o["status"] != 0)   # converged here, capped in the oracle: the result must still be a solution
     assert np.all(np.abs(wave[only_gpu][:, :, -1] - ovr["V:vsup:dc"][only_gpu, None]) < 1e-9)
-    # The plain-card 41-stage ring (N = 47) converges at every supply in the reference. Here the operating points all converge
-    # (re-pivoted in place where needed), but inside the device-resident time loop nobody re-pivots: at some supplies the
-    # order frozen at the first transient iteration meets an exactly zero pivot later on and the instance ends with Singular
-    # Matrix (a known limitation, DESIGN.md "C4"). Where the transient runs through it agrees with the oracle.
+    # The plain-card 41-stage ring (N = 47) converges at every supply in the reference, and here. (Until the OP repair kept
+    # instances that are singular under ANOTHER instance's pivot order open — resolve_repivot, host/batch.hpp — 7 of these 16
+    # supplies ended their operating point with Singular Matrix after 2 iterations inside the batch, although every one of
+    # them converges alone; the earlier reading "the frozen order fails inside the time loop" was wrong.)
     ck2, ic2 = cc.bsim4_ring(41, ic_every=20)
     c2 = ck2.to_s21().elaborate(ic=ic2)
     b2 = s21.Batch(c2, B)
     b2.override("V:vsup:dc", ovr["V:vsup:dc"])
     t2, w2, st2, it2 = b2.tran(tstep, npts * tstep)
     o2 = oracle.Circuit(ck2.to_text()).batch(1, B, overrides=ovr, tstep=tstep, tstop=npts * tstep, ic=ic2, nthreads=8)
-    ok2 = st2 == 0
-    assert np.all(o2["status"] == 0) and int(np.sum(ok2)) >= B // 2 and np.all(np.isin(st2[~ok2], [s21.S21_SINGULAR_MATRIX]))
-    assert np.max(np.abs(w2[ok2] - o2["x"][ok2])) <= 1e-7
+    assert np.all(o2["status"] == 0) and np.all(st2 == 0), (st2, o2["status"])
+    assert np.max(np.abs(w2 - o2["x"])) <= 1e-8
+    assert np.all(np.abs(it2 - o2["iters"]) <= 0.1 * o2["iters"]), (it2, o2["iters"])
+
+
+def test_transient_hand_back_and_resume(s21, monkeypatch):
+    """Re-pivoting inside a transient (cooperative kernel; SolveCtl::tran_stop, Batch::resolve_tran_stops): an instance whose
+    frozen pivot order meets an exactly zero pivot — or a non-finite step — inside the time loop goes back to its last
+    accepted time point, comes back to the host with the time point recorded, gets a pivot order taken at that iterate and
+    is continued by a resume launch from its own time point on. No circuit of the suite drives a pivot to zero inside its
+    time loop, so the path is exercised by injection (S21_TRAN_INJECT=7: every instance is handed back once, in the second
+    Newton iteration of time point 7 — x and the in-flight device state already moved): the continued waveforms must equal
+    the uninterrupted run's (same matrix, same first-iteration order: bit for bit), and the hand-backs must show in the counters."""
+    ck, ic = cc.bsim4_ring(21)
+    ovr = {k: v[::85][:24] for k, v in cc.c4_sweep(2048).items()}
+
+    def run():
+        b = s21.Batch(ck.to_s21().elaborate(ic=ic), 24)
+        for k, v in ovr.items():
+            b.override(k, v)
+        t, w, st, it = b.tran(1e-10, 40e-10)
+        return w, st, it, b.setup_stats(), b.kernel_name()
+    w0, st0, it0, ss0, kn = run()
+    monkeypatch.setenv("S21_TRAN_INJECT", "7")
+    w1, st1, it1, ss1, _ = run()
+    assert kn == "coop" and np.all(st0 == 0) and np.all(st1 == 0)
+    assert ss1["repaired_instances"] == ss0["repaired_instances"] + 24
+    assert np.array_equal(w0, w1)
+    assert np.all(it1 >= it0) and np.all(it1 - it0 <= 3)  # the abandoned attempt's iterations are counted
 
 
 def test_grid_kernel_single_large_circuit(s21, oracle, monkeypatch):
@@ -1263,7 +1286,11 @@ def test_grid_kernel_single_large_circuit(s21, oracle, monkeypatch):
     # array takes FEWER iterations than the exact mode's re-ordered ones: 42 against 59)
     assert diff <= 1e-7 and abs(int(it[0]) - int(itx[0])) <= 0.4 * int(itx[0])
     o = oracle.Circuit(ck.to_text()).tran(1e-11, 1e-10, ic=ic)
-    assert np.max(np.abs(w[0] - o.data)) <= 1e-8
+    # the tolerance mode is not bit-reproducible (atomic sums): every run stops its Newton iterations on the reference's
+    # criterion (|dx| < 1e-3, |res| < 1e-12 A) along a slightly different path — measured 3e-10 ... 2.5e-8 against the oracle
+    # over this round's runs; the bound sits 10x inside SPICE's vntol (1e-6), the exact mode is held to 1e-9
+    assert np.max(np.abs(w[0] - o.data)) <= 1e-7
+    assert np.max(np.abs(wx[0] - o.data)) <= 1e-9
     x, sd, _ = s21.Batch(cc.inverter_array(20, 5)[0].to_s21().elaborate(), 1).dcop()
     assert sd[0] in (0, 1)  # without the IC the 100-iteration cap may hit, as in the reference; the launch must not hang
 
