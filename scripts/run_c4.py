@@ -16,7 +16,8 @@ n_stages = int(sys.argv[2]) if len(sys.argv) > 2 else 21
 n_points = int(sys.argv[3]) if len(sys.argv) > 3 else 500
 n_oracle = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 tstep = 1e-10
-ck, ic = cc.bsim4_ring(n_stages)
+ic_every = int(os.environ.get("RUNC4_IC_EVERY", "0"))  # further initial conditions every so many stages (tests/circuits.py bsim4_ring)
+ck, ic = cc.bsim4_ring(n_stages, ic_every=ic_every)
 ovr = cc.c4_sweep(B)
 c = ck.to_s21().elaborate(ic=ic)
 save = [c.names.index("s1"), c.names.index(f"s{n_stages // 2}"), c.names.index("vsup")]

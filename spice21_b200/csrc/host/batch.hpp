@@ -658,12 +658,13 @@ class Batch {
       // regions): the kernel reports Singular Matrix with x untouched. That instance is not singular under an order of its
       // own — it stays open (measured on the plain 41-stage Bsim4 ring: 7 of 16 supplies ended their OP with Singular Matrix
       // after 2 iterations inside the batch, every one of them converges alone). Truly singular matrices end when they head
-      // the list: the host's own factorisation then says so. A few retries per instance bound the loop.
+      // the list: the host's own factorisation then says so; the 256 rounds bound the loop. (A cap of 8 such retries per
+      // instance was too low for a 2048-instance batch with ~60 rounds: 160 instances of the 41-stage ring sweep were dropped.)
       std::vector<size_t> next;
       bool rewrite_st = false;
       for (size_t i : open) {
         hs[i] = hstatus_.p[i];
-        if (hs[i] == ST_SINGULAR && sing_retries_[i] < 8) { sing_retries_[i]++; hs[i] = ST_REPIVOT_CODE; hstatus_.p[i] = ST_REPIVOT_CODE; rewrite_st = true; }
+        if (hs[i] == ST_SINGULAR && sing_retries_[i] < 200) { sing_retries_[i]++; hs[i] = ST_REPIVOT_CODE; hstatus_.p[i] = ST_REPIVOT_CODE; rewrite_st = true; }
         if (hs[i] == ST_REPIVOT_CODE) next.push_back(i);
         else repaired_++;
       }
