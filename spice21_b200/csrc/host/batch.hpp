@@ -957,6 +957,9 @@ class Batch {
     DevTables dt = dev_tables(ac_plan_.itab.p);
     int rc;
     CoopCfg hcfg;
+    // time the sweep kernel itself, as tran() does for its time loop: the operating point, the probe and the host symbolic phase
+    // above were inside this pair until ncu showed the kernel at 1.07 ms of the 1.8 ms reported for C5 (profiles/r02M_c5_full.txt)
+    S21_CUDA(cudaEventRecord(ev0_, stream_)); ev_pair_ = false;
     // A long sweep is a huge batch of independent points: one thread per point (kernels/newton.cu::k_ac, HBM-resident
     // workspace, instance-fastest layout = coalesced) fills the GPU by itself and skips every barrier of the co-operative
     // kernels. Measured on C5 (N = 73, nnzLU = 365, 100 000 points): 3.8 ms against 29.8 ms (profiles/r01p_c5.txt).
@@ -971,6 +974,10 @@ class Batch {
       last_kernel_ = "coop";
       rc = launch_coop_ac(coop_dev(ac_plan_), ac_plan_.coop_plan(), ac_plan_.coop(), w, stage, o, ctl, cfg, stream_);
     } else {
+      // (a level-scheduled variant of the thread-per-point kernel — staged assembly, four independent operations of a
+      // dependency level in flight — was built on the reading that this kernel is a chain of dependent round trips; it is
+      // not: bit-identical, and SLOWER, 2.19-2.28 ms against 1.73-1.77 ms on C5, by about what its extra staging traffic costs
+      // at ~5 TB/s. The kernel is bandwidth-bound in the bytes it really moves; removed. profiles/r02L_c5.txt)
       last_kernel_ = "direct";
       rc = launch_ac(dt, ac_plan_.tables(), w, o, ctl, stream_);
     }

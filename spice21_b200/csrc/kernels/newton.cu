@@ -155,7 +155,15 @@ __device__ int newton_solve(const DevTables& d, const PlanTables& p, const WorkT
     for (int r = 0; r < N; r++) {
       T acc = Scalar<T>::zero();
       const int b = __ldg(p.rowptr + r), en = __ldg(p.rowptr + r + 1);
-      for (int s = b; s < en; s++) {
+      int s = b;
+      for (; s + 4 <= en; s += 4) {  // operands of four entries in flight, the sum in list order (see the LU loop below)
+        const int c0 = __ldg(p.col_i2e + __ldg(p.colidx + s)), c1 = __ldg(p.col_i2e + __ldg(p.colidx + s + 1));
+        const int c2 = __ldg(p.col_i2e + __ldg(p.colidx + s + 2)), c3 = __ldg(p.col_i2e + __ldg(p.colidx + s + 3));
+        const T a0 = lu[(size_t)s * S], a1 = lu[(size_t)(s + 1) * S], a2 = lu[(size_t)(s + 2) * S], a3 = lu[(size_t)(s + 3) * S];
+        const T x0 = x[(size_t)c0 * S], x1 = x[(size_t)c1 * S], x2 = x[(size_t)c2 * S], x3 = x[(size_t)c3 * S];
+        acc = s_add(s_add(s_add(s_add(acc, s_mul(a0, x0)), s_mul(a1, x1)), s_mul(a2, x2)), s_mul(a3, x3));
+      }
+      for (; s < en; s++) {
         const int col = __ldg(p.colidx + s);
         acc = s_add(acc, s_mul(lu[(size_t)s * S], x[(size_t)__ldg(p.col_i2e + col) * S]));
       }
@@ -174,7 +182,21 @@ __device__ int newton_solve(const DevTables& d, const PlanTables& p, const WorkT
       if (s_is_zero(piv)) return ST_SINGULAR_;
       const int lb = __ldg(p.l_off + k), le = __ldg(p.l_off + k + 1);
       const double pth = __ldg(p.piv_chk + k) ? s_abs(piv) * ctl.weak_mult : INFINITY;  // pivots the fallback searches chose carry no threshold
-      for (int j = lb; j < le; j++) {
+      // One thread walks its instance's whole factorisation against an HBM / L2-resident workspace: every operation is a
+      // chain index -> operand -> store, and the compiler cannot overlap two of them (a store to lu[] may alias the next
+      // load). Within one pivot step the operations are independent — the entries of the L column, and the update targets
+      // (i, j), are all distinct, the operands (pivot row, divided column) are not written — so four are issued together:
+      // indices, then operands, then the arithmetic and the stores. Same values, same bits; four times the loads in flight
+      // (config C5, 100 000 AC points on this kernel: the one workload whose bytes really move).
+      int j = lb;
+      for (; j + 4 <= le; j += 4) {
+        T* a0 = lu + (size_t)__ldg(p.l_slot + j) * S; T* a1 = lu + (size_t)__ldg(p.l_slot + j + 1) * S;
+        T* a2 = lu + (size_t)__ldg(p.l_slot + j + 2) * S; T* a3 = lu + (size_t)__ldg(p.l_slot + j + 3) * S;
+        const T v0 = *a0, v1 = *a1, v2 = *a2, v3 = *a3;
+        if (pth < s_abs(v0) || pth < s_abs(v1) || pth < s_abs(v2) || pth < s_abs(v3)) weak = true;
+        *a0 = s_div(v0, piv); *a1 = s_div(v1, piv); *a2 = s_div(v2, piv); *a3 = s_div(v3, piv);
+      }
+      for (; j < le; j++) {
         T* a = lu + (size_t)__ldg(p.l_slot + j) * S;
         // pivot health: the reference, which searches its pivots anew in every factorisation, would not have taken this
         // diagonal (|d| < 1e-3 * column max, mod.rs:735-783)
@@ -182,7 +204,18 @@ __device__ int newton_solve(const DevTables& d, const PlanTables& p, const WorkT
         *a = s_div(*a, piv);
       }
       const int ub = __ldg(p.upd_off + k), ue = __ldg(p.upd_off + k + 1);
-      for (int j = ub; j < ue; j++) {
+      j = ub;
+      for (; j + 4 <= ue; j += 4) {
+        T* t0 = lu + (size_t)__ldg(p.upd_t + j) * S; T* t1 = lu + (size_t)__ldg(p.upd_t + j + 1) * S;
+        T* t2 = lu + (size_t)__ldg(p.upd_t + j + 2) * S; T* t3 = lu + (size_t)__ldg(p.upd_t + j + 3) * S;
+        const T u0 = lu[(size_t)__ldg(p.upd_u + j) * S], u1 = lu[(size_t)__ldg(p.upd_u + j + 1) * S];
+        const T u2 = lu[(size_t)__ldg(p.upd_u + j + 2) * S], u3 = lu[(size_t)__ldg(p.upd_u + j + 3) * S];
+        const T l0 = lu[(size_t)__ldg(p.upd_l + j) * S], l1 = lu[(size_t)__ldg(p.upd_l + j + 1) * S];
+        const T l2 = lu[(size_t)__ldg(p.upd_l + j + 2) * S], l3 = lu[(size_t)__ldg(p.upd_l + j + 3) * S];
+        const T w0 = *t0, w1 = *t1, w2 = *t2, w3 = *t3;
+        *t0 = s_sub(w0, s_mul(u0, l0)); *t1 = s_sub(w1, s_mul(u1, l1)); *t2 = s_sub(w2, s_mul(u2, l2)); *t3 = s_sub(w3, s_mul(u3, l3));
+      }
+      for (; j < ue; j++) {
         T* t = lu + (size_t)__ldg(p.upd_t + j) * S;
         const T v = s_mul(lu[(size_t)__ldg(p.upd_u + j) * S], lu[(size_t)__ldg(p.upd_l + j) * S]);
         *t = s_sub(*t, v);
@@ -196,7 +229,16 @@ __device__ int newton_solve(const DevTables& d, const PlanTables& p, const WorkT
       const T ck = c[(size_t)k * S];
       if (s_is_zero(ck)) continue;
       const int lb = __ldg(p.l_off + k), le = __ldg(p.l_off + k + 1);
-      for (int j = lb; j < le; j++) {
+      int j = lb;
+      for (; j + 4 <= le; j += 4) {  // the rows of one L column are distinct
+        T* t0 = c + (size_t)__ldg(p.l_row + j) * S; T* t1 = c + (size_t)__ldg(p.l_row + j + 1) * S;
+        T* t2 = c + (size_t)__ldg(p.l_row + j + 2) * S; T* t3 = c + (size_t)__ldg(p.l_row + j + 3) * S;
+        const T l0 = lu[(size_t)__ldg(p.l_slot + j) * S], l1 = lu[(size_t)__ldg(p.l_slot + j + 1) * S];
+        const T l2 = lu[(size_t)__ldg(p.l_slot + j + 2) * S], l3 = lu[(size_t)__ldg(p.l_slot + j + 3) * S];
+        const T w0 = *t0, w1 = *t1, w2 = *t2, w3 = *t3;
+        *t0 = s_sub(w0, s_mul(ck, l0)); *t1 = s_sub(w1, s_mul(ck, l1)); *t2 = s_sub(w2, s_mul(ck, l2)); *t3 = s_sub(w3, s_mul(ck, l3));
+      }
+      for (; j < le; j++) {
         T* t = c + (size_t)__ldg(p.l_row + j) * S;
         *t = s_sub(*t, s_mul(ck, lu[(size_t)__ldg(p.l_slot + j) * S]));
       }
@@ -206,7 +248,14 @@ __device__ int newton_solve(const DevTables& d, const PlanTables& p, const WorkT
       const int ds = __ldg(p.diag_slot + k);
       const int en = __ldg(p.rowptr + k + 1);
       T ck = c[(size_t)k * S];
-      for (int s = ds + 1; s < en; s++) ck = s_sub(ck, s_mul(c[(size_t)__ldg(p.colidx + s) * S], lu[(size_t)s * S]));
+      int s = ds + 1;
+      for (; s + 4 <= en; s += 4) {  // operands of four entries in flight, the subtractions in list order
+        const T c0 = c[(size_t)__ldg(p.colidx + s) * S], c1 = c[(size_t)__ldg(p.colidx + s + 1) * S];
+        const T c2 = c[(size_t)__ldg(p.colidx + s + 2) * S], c3 = c[(size_t)__ldg(p.colidx + s + 3) * S];
+        const T a0 = lu[(size_t)s * S], a1 = lu[(size_t)(s + 1) * S], a2 = lu[(size_t)(s + 2) * S], a3 = lu[(size_t)(s + 3) * S];
+        ck = s_sub(s_sub(s_sub(s_sub(ck, s_mul(c0, a0)), s_mul(c1, a1)), s_mul(c2, a2)), s_mul(c3, a3));
+      }
+      for (; s < en; s++) ck = s_sub(ck, s_mul(c[(size_t)__ldg(p.colidx + s) * S], lu[(size_t)s * S]));
       c[(size_t)k * S] = s_div(ck, lu[(size_t)ds * S]);  // no zero check here in the reference either (mod.rs:978)
     }
     *n_solves += 1;
