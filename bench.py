@@ -102,7 +102,32 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.rows = index, threading.Event(), []
 
+    def _nvml_loop(self):
+        """In-process NVML (nvidia_ml_py): a query costs microseconds, so the short headline loops (20 steps of 0.1 ms) get many
+        samples; nvidia-smi as a subprocess (the recipe's line) manages one per ~50 ms and is the fallback."""
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8), "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag.is_set():
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            r = int(get_reasons(h))
+            try:
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+            except Exception:
+                pw = 0.0
+            self.rows.append([str(sm), str(mx), str(pw)] + ["Active" if r & int(b) else "Not Active" for b in bits.values()])
+            self.stop_flag.wait(0.002)
+
     def run(self):
+        try:
+            self._nvml_loop()
+            return
+        except Exception:
+            pass
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],

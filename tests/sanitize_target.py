@@ -1,7 +1,8 @@
 """Workload that tests/test_gpu.py::test_compute_sanitizer_clean runs UNDER compute-sanitizer (memcheck / racecheck):
 one small pass through every kernel family — the run-time specialised team kernel (dcop + transient, ragged batch so
 that padding lanes exist), the thread-per-instance specialised kernel, hybrid, cooperative (shared-memory and HBM
-workspace, the latter with Bsim4), direct (dcop, tran, adaptive tran, AC), grid-wide, the probe and pack kernels.
+workspace, the latter with Bsim4 — default and reciprocal-division builds, plus a hand-back / resume inside the time loop),
+direct (dcop, tran, adaptive tran, AC), grid-wide, the probe and pack kernels (results, waveforms, AC rows).
 Sizes are tiny: the sanitizer slows kernels by one to two orders of magnitude. Prints SANITIZE_TARGET_OK at the end."""
 import os
 import sys
@@ -61,6 +62,15 @@ if which in ("all", "bsim4"):
     b.override("V:v1:dc", np.array([0.9, 1.0, 1.1]))
     t, w, st, it = b.tran(1e-10, 4e-10)
     assert np.all(st == 0), st
+    # the opt-in reciprocal-division build of the same kernel, with every instance handed back once inside the time loop
+    # and continued by a resume launch (SolveCtl::tran_stop; S21_TRAN_INJECT is the test hook)
+    os.environ["S21_B4_FAST"] = "1"
+    os.environ["S21_TRAN_INJECT"] = "2"
+    b = s21.Batch(rb.to_s21().elaborate(ic={"1": 0.0}), 3)
+    b.override("V:v1:dc", np.array([0.9, 1.0, 1.1]))
+    t, w2, st, it = b.tran(1e-10, 4e-10)
+    os.environ.pop("S21_B4_FAST"); os.environ.pop("S21_TRAN_INJECT")
+    assert np.all(st == 0) and b.kernel_name() == "coop-rcp" and np.max(np.abs(w2 - w)) < 1e-6, st
 
 if which in ("all", "ac"):
     c = cc.Ckt().V("vin", "inp", cc.GND, 1.0, acm=1.0).R("r1", "inp", "out", 1e-3).C("c1", "out", cc.GND, 1e-9)
