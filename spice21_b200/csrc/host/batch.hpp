@@ -970,7 +970,7 @@ class Batch {
     } else if (use_coop_ && !ac_direct) {
       CoopCfg cfg = coop_cfg(ac_plan_, F, 2);
       cplx* stage = nullptr;
-      if (cfg.smem_bytes == 0 || cfg.mixed) { zstage_.alloc((size_t)ac_plan_.host.n_stage * Fs); stage = zstage_.p; }
+      if (cfg.smem_bytes == 0 || cfg.mixed) { zstage_.alloc((size_t)ac_plan_.host.n_stage * (Fs + 32)); stage = zstage_.p; }
       last_kernel_ = "coop";
       rc = launch_coop_ac(coop_dev(ac_plan_), ac_plan_.coop_plan(), ac_plan_.coop(), w, stage, o, ctl, cfg, stream_);
     } else {
@@ -1351,7 +1351,7 @@ class Batch {
   }
   double* stage_for(const CoopCfg& cfg, const Plan& P) {
     if (cfg.smem_bytes && !cfg.mixed) return nullptr;
-    d_stage_.alloc((size_t)P.n_stage * Bs_);
+    d_stage_.alloc((size_t)P.n_stage * (Bs_ + 32));  // + 32: the cooperative kernel's CTA-blocked layout rounds the batch up to grid x gi
     return d_stage_.p;
   }
 

@@ -105,9 +105,13 @@ __global__ void __launch_bounds__(B4 ? 320 : 256, B4 ? 1 : 2) k_coop(DevTables d
     sguess = (double*)(smem_raw + off);
     wS = (IS)gi; colS = (IS)li; ss = (IS)gi; scol = (IS)li;
   } else {
-    S = gstage;
+    // The staging area is scratch of this launch: each CTA gets ONE contiguous block ([slot][instance of the CTA], 20 KB x gi on
+    // config C4) instead of columns of the batch-wide [slot][stride] table, whose entries of one instance lie a whole batch
+    // stride (16 KB at 2048 instances) apart. S21_COOP_STAGE_BLOCKED=0 (CoopArgs::stage_blocked) keeps the strided layout.
+    if (a.stage_blocked) { S = gstage + (size_t)blockIdx.x * (size_t)ct.n_stage * (size_t)gi; wS = (IS)gi; colS = (IS)li; }
+    else { S = gstage; wS = (IS)g.stride; colS = (IS)i0 + (IS)li; }
     sop = g.st_op; sguess = g.st_guess;
-    wS = (IS)g.stride; colS = (IS)i0 + (IS)li; ss = (IS)g.st_stride; scol = ((IS)i0 + (IS)li) * (IS)ctl.par_inst_stride;
+    ss = (IS)g.st_stride; scol = ((IS)i0 + (IS)li) * (IS)ctl.par_inst_stride;
   }
   const bool valid = li < ni;
 
@@ -368,6 +372,10 @@ int launch_b4(const DevTables& d, const PlanTables& p, const CoopTables& ct, con
   CoopArgs a;
   a.lg_gi = 0; a.gi = cfg.gi; a.cold = 0; a.T_points = T_points; a.n_save = n_save; a.save_vars = save_vars; a.wave = wave;
   a.tp_stop = cfg.tp_stop; a.x_acc = cfg.x_acc;
+  {
+    const char* sb = std::getenv("S21_COOP_STAGE_BLOCKED");
+    a.stage_blocked = (sb && std::atoi(sb) == 0) ? 0 : 1;
+  }
   a.arena = cfg.arena;
   a.pcode_global = cfg.arena_in_smem && cfg.arena_core_bytes > 0 ? 1 : 0;
   a.arena_bytes = cfg.arena_in_smem ? (int)(a.pcode_global ? cfg.arena_core_bytes : cfg.arena_bytes) : 0;

@@ -137,6 +137,7 @@ struct CoopArgs {
   // resumes), [N][stride] x of every instance at its last accepted time point
   int* tp_stop = nullptr;
   double* x_acc = nullptr;
+  int stage_blocked = 0;  // cooperative kernel, staging in HBM: one contiguous [slot][gi] block per CTA (needs n_stage x (grid x gi) entries)
 };
 
 
