@@ -446,12 +446,19 @@ class Batch:
                                     iters.ctypes.data_as(C.c_void_p)))
         return x, status, iters
 
-    def tran(self, tstep, tstop, save=None, want_wave=True):
-        """want_wave=False leaves the waveforms in HBM (wave_device) and returns None for them."""
+    def tran(self, tstep, tstop, save=None, want_wave=True, out=None):
+        """want_wave=False leaves the waveforms in HBM (wave_device) and returns None for them. out: a C-contiguous float64
+        array of shape [B][T][n_save] to receive the waveforms (a caller that repeats a sweep reuses its buffer: a fresh
+        40 MB array costs more in first-touch page faults than the copy that fills it)."""
         T = lib().s21_tran_num_points(tstep, tstop)
         save = np.arange(self.N, dtype=np.int32) if save is None else np.ascontiguousarray(save, dtype=np.int32)
         time = np.zeros(T)
-        wave = np.empty((self.B, T, len(save))) if want_wave else None  # every entry is written by the library
+        if want_wave and out is not None:
+            if out.shape != (self.B, T, len(save)) or out.dtype != np.float64 or not out.flags["C_CONTIGUOUS"]:
+                raise ValueError(f"out must be a C-contiguous float64 array of shape {(self.B, T, len(save))}")
+            wave = out
+        else:
+            wave = np.empty((self.B, T, len(save))) if want_wave else None  # every entry is written by the library
         status = np.zeros(self.B, dtype=np.int32)
         iters = np.zeros(self.B, dtype=np.int64)
         _check(lib().s21_batch_tran(self.h, tstep, tstop, save.ctypes.data_as(C.c_void_p), len(save), time.ctypes.data_as(C.c_void_p),
@@ -472,9 +479,15 @@ class Batch:
         _check(lib().s21_batch_tran_adaptive(self.h, tstep, tstop, p(ctl), p(save), len(save), p(time), p(wave), p(status), p(iters), p(acc), p(rej)))
         return time, wave, status, iters, acc, rej
 
-    def ac(self, freqs):
+    def ac(self, freqs, out=None):
+        """out: a C-contiguous complex128 array of shape [F][N] to receive the results (see tran)."""
         f = np.ascontiguousarray(freqs, dtype=np.float64)
-        x = np.empty((len(f), self.N, 2))  # every entry is written by the library
+        if out is not None:
+            if out.shape != (len(f), self.N) or out.dtype != np.complex128 or not out.flags["C_CONTIGUOUS"]:
+                raise ValueError(f"out must be a C-contiguous complex128 array of shape {(len(f), self.N)}")
+            x = out.view(np.float64).reshape(len(f), self.N, 2)
+        else:
+            x = np.empty((len(f), self.N, 2))  # every entry is written by the library
         status = np.zeros(len(f), dtype=np.int32)
         iters = np.zeros(len(f), dtype=np.int32)
         _check(lib().s21_batch_ac(self.h, f.ctypes.data_as(C.c_void_p), len(f), x.ctypes.data_as(C.c_void_p),

@@ -114,10 +114,6 @@ inline std::string debug_jit_source(const FlatCkt& flat, int mode, int shape, co
 struct PlanDevice {
   Plan host;
   bool valid = false;
-  // S21_PLAN_CACHE=1 (experimental, unmeasured): the probe values this plan was derived from. A transient re-derives its
-  // plan on every call; when the probe of an unchanged batch returns the same bits, the derivation would return the same
-  // plan, so it is skipped (C3: the whole host symbolic phase of a repeated run). Cleared with the parameter pool.
-  std::vector<double> probe_vals;
   std::vector<int> host_itab;         // itab with element handles translated to L+U slots
   jit::Kernel jit_dcop, jit_tran;     // circuit-specialised kernels (host/jit.hpp), compiled on first use
   bool jit_tried_dcop = false, jit_tried_tran = false;
@@ -1500,13 +1496,9 @@ class Batch {
     std::vector<double> vals((size_t)flat_.n_elems());
     S21_CUDA(cudaMemcpyAsync(vals.data(), probe.p, vals.size() * sizeof(double), cudaMemcpyDeviceToHost, stream_));
     S21_CUDA(cudaStreamSynchronize(stream_));
-    static const bool plan_cache = [] { const char* e = std::getenv("S21_PLAN_CACHE"); return e && std::atoi(e) != 0; }();
-    if (plan_cache && !pd.probe_vals.empty() && pd.probe_vals.size() == vals.size() &&
-        std::memcmp(pd.probe_vals.data(), vals.data(), vals.size() * sizeof(double)) == 0) {
-      pd.valid = true;  // same first-iteration matrix, bit for bit: same pivot order, same tables (already on the device)
-      return;
-    }
-    if (plan_cache) pd.probe_vals = vals;
+    // (A plan cache keyed on these probe values — skip the derivation when an unchanged batch probes the same bits — was
+    // measured and removed: 0.07 ms of a 19 ms call on the C1 sweep, and it cannot hit on C3, whose tolerance-mode operating
+    // point is not bit-reproducible. profiles/r02Q_c1_e2e.txt)
     const auto t_sym0 = std::chrono::steady_clock::now();
     // One large circuit on the grid-wide kernel: tolerance-mode level schedules (host/symbolic.hpp build_levels) unless
     // S21_PLAN_EXACT=1 asks for the bit-identical chains.
@@ -1714,7 +1706,6 @@ class Batch {
     }
     // a parameter change invalidates the frozen pivot orders (and the tables packed with them)
     op_plan_.valid = false; tran_plan_.valid = false; ac_plan_.valid = false;
-    op_plan_.probe_vals.clear(); tran_plan_.probe_vals.clear(); ac_plan_.probe_vals.clear();  // the kernels embed the pool's layout
   }
 };
 
