@@ -108,7 +108,9 @@ inline std::string debug_jit_source(const FlatCkt& flat, int mode, int shape, co
   }
   if (!jit::team_eligible(flat, P, (size_t)227 * 1024)) throw S21Error(ST_UNSUPPORTED, "circuit not eligible for the team kernel");
   const int lpi = jit::team_lpi(P.N, jit::team_heavy_devices(flat));
-  return jit::team_source(flat, P, si, itab, pcode, mode == AN_TRAN, lpi, smem_out, 148, jit::team_gi(0, 0, lpi));
+  size_t Bdbg = 0;  // S21_JIT_SOURCE_B: the batch size the generator's shape decisions are taken for (host-only debugging)
+  if (const char* e = std::getenv("S21_JIT_SOURCE_B")) Bdbg = (size_t)std::atoll(e);
+  return jit::team_source(flat, P, si, itab, pcode, mode == AN_TRAN, lpi, smem_out, 148, jit::team_gi(Bdbg, 148, lpi, mode == AN_TRAN), nullptr, Bdbg);
 }
 
 struct PlanDevice {

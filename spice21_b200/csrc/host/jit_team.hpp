@@ -114,11 +114,18 @@ inline bool team_eligible(const FlatCkt& flat, const Plan& P, size_t max_smem) {
 inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageInfo& si, const std::vector<int>& itab,
                                const std::vector<int>& pcode, bool tran, int TM_LPI, size_t* smem_out, int n_sm = 148, int GI = TM_GI, int* tpb_out = nullptr,
                                size_t B = 0) {
-  (void)n_sm;
   std::ostringstream o;
   const bool XP = team_wp(tran, B);
   const int PSV = XP ? GI + 4 : TM_P;  // padded instance stride of the shared-memory columns (36 for a full CTA, as kernels/hybrid.cu)
   const int N = P.N, NST = P.n_stage, NSTATE = std::max(flat.n_state, 1), Q = (N + TM_LPI - 1) / TM_LPI;
+  // Committed device state in HBM / L2 instead of shared memory (transients only). The state of a time loop lives on chip
+  // for the whole launch; on the C1-circuit sweep that is 139 KB per 32-instance CTA — ONE CTA per SM, so 8192 instances =
+  // 256 CTAs ran as two waves on 148 SMs (ncu: profiles/r02T_c1_full.txt; 2048 instances take half the time of 8192).
+  // The committed copy (`op`) is read a few times per device evaluation and written once per accepted time point; leaving
+  // it in its HBM column (read through L2: __ldcg, coherent with the warp's own stores) takes the CTA under half an SM's
+  // shared memory — two CTAs per SM, one wave. Taken only when that is what it buys: a transient, a batch of more CTAs
+  // than SMs, and a footprint that crosses the half-SM line with it. S21_TEAM_SOPG=0 / 1 forces it off / on.
+  bool SOPG = false;  // decided below, once the size of the gather table (part of the footprint) is known
   const int IPW = 32 / TM_LPI;        // instances per warp in the linear-algebra phase
   const int NW_LA = GI / IPW;      // warps of the linear-algebra phase
   // S21_TEAM_NW adds warps that only take part in the evaluation phase and sit out the linear algebra (ri >= GI).
@@ -192,6 +199,14 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
     emit_gather("b" + std::to_string(q), lists);
   }
 
+  {
+    const size_t half_sm = (233472 - 2 * 1024) / 2;  // sm_100a: 228 KB per SM, 1 KB reserved per CTA
+    const size_t slots_full = (size_t)N + (size_t)NST + 1 + 2 * (size_t)NSTATE, slots_red = slots_full - (size_t)NSTATE;
+    const size_t ctrl = (((size_t)GI + G.table.size() + (size_t)TM_LPI) * 4 + 15) / 16 * 16;  // as ctrl_bytes below (the table gets one more row)
+    const bool two_waves = B > 0 && (B + (size_t)GI - 1) / (size_t)GI > (size_t)std::max(n_sm, 1);
+    SOPG = tran && two_waves && ctrl + 8 * (size_t)PSV * slots_full > half_sm && ctrl + 8 * (size_t)PSV * slots_red <= half_sm;
+    if (const char* e = std::getenv("S21_TEAM_SOPG")) SOPG = tran && std::atoi(e) != 0;
+  }
   // ---- source
   const bool prof = team_profile();
   const bool fast_la = team_fast();
@@ -215,7 +230,7 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
   o << "__device__ const int XO_G[" << Q * TM_LPI + 8 << "] = {";
   for (int k = 0; k < Q * TM_LPI + 8; k++) o << (k ? "," : "") << (k < N ? P.col_i2e[(size_t)k] * PSV : 0);
   o << "};\n";
-  o << "struct JBase {\n  const double* pval; size_t pinst; double* sop; double* sguess; const double* X; double* S;\n"
+  o << "struct JBase {\n  const double* pval; size_t pinst; double* sop; double* sguess; const double* X; double* S;" << (SOPG ? " size_t sops;" : "") << "\n"
        "  int mode" << (XP ? ", j" : "") << "; double dt, gmin, omega, time;\n"
        "  __device__ __forceinline__ double volt(int var) const { return var < 0 ? 0.0 : X[var * PS]; }\n};\n";
   // the Env base of the branch-free evaluation (kernels/devices.cuh math hooks): fast paths only, exceptions deferred
@@ -236,7 +251,8 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
       o << " case " << j << ": return __ldg(pval + " << (c >> 1) << ((c & 1) ? " + pinst" : "") << ");";
     }
     o << " default: return 0.0; } }\n";
-    o << "  __device__ __forceinline__ double op(int k) const { return sop[(" << d.state_off << " + k) * PS]; }\n";
+    if (SOPG) o << "  using Base::sops;\n  __device__ __forceinline__ double op(int k) const { return __ldcg(sop + (size_t)(" << d.state_off << " + k) * sops); }\n";
+    else o << "  __device__ __forceinline__ double op(int k) const { return sop[(" << d.state_off << " + k) * PS]; }\n";
     o << "  __device__ __forceinline__ double guess(int k) const { return sguess[(" << d.state_off << " + k) * PS]; }\n";
     o << "  __device__ __forceinline__ void set_guess(int k, double v) { sguess[(" << d.state_off << " + k) * PS] = v; }\n";
     o << "  __device__ __forceinline__ void add_g_at(int pos, double v) { S[(" << sto << " + pos) * PS] = v; }\n";
@@ -289,7 +305,8 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
       o << " default: return 0.0; } }\n";
       const std::string so = selj(vals([&](const FlatDev& d, int) { return d.state_off; }));
       const std::string st = selj(vals([&](const FlatDev&, int d) { return si.stage_off[(size_t)d]; }));
-      o << "  __device__ __forceinline__ double op(int k) const { return sop[(" << so << " + k) * PS]; }\n";
+      if (SOPG) o << "  using Base::sops;\n  __device__ __forceinline__ double op(int k) const { return __ldcg(sop + (size_t)(" << so << " + k) * sops); }\n";
+      else o << "  __device__ __forceinline__ double op(int k) const { return sop[(" << so << " + k) * PS]; }\n";
       o << "  __device__ __forceinline__ double guess(int k) const { return sguess[(" << so << " + k) * PS]; }\n";
       o << "  __device__ __forceinline__ void set_guess(int k, double v) { sguess[(" << so << " + k) * PS] = v; }\n";
       o << "  __device__ __forceinline__ void add_g_at(int pos, double v) { S[(" << st << " + pos) * PS] = v; }\n";
@@ -300,7 +317,7 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
   const size_t n_gt = G.table.size();
   const size_t ctrl_ints = (size_t)GI + n_gt;
   const size_t ctrl_bytes = (ctrl_ints * 4 + 15) / 16 * 16;
-  *smem_out = ctrl_bytes + 8 * (size_t)PSV * ((size_t)N + (size_t)NST + 1 + 2 * (size_t)NSTATE);
+  *smem_out = ctrl_bytes + 8 * (size_t)PSV * ((size_t)N + (size_t)NST + 1 + (SOPG ? 1 : 2) * (size_t)NSTATE);
 
   o << "extern \"C\" __global__ void __launch_bounds__(" << NW * 32 << ", " << 2 << ") k_jit(const double* __restrict__ pval, double* gx, double* st_op, double* st_guess,\n"
        "    int* status, int* iters, int* loads, size_t stride, size_t st_stride, int B, int n_state_arg, int mode, double gmin, double dt,\n"
@@ -314,15 +331,17 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
        "  int* act_s = (int*)smem_raw;\n  int* gt = act_s + " << GI << ";\n"
        "  double* X = (double*)(smem_raw + " << ctrl_bytes << ");\n"
        "  double* S = X + " << N * PSV << ";\n"
-       "  double* sop = S + " << (NST + 1) * PSV << ";\n"
-       "  double* sguess = sop + " << NSTATE * PSV << ";\n"
+       << (SOPG ? "  double* sop = st_op + i0;  // committed state stays in its HBM column: entry k of instance e at sop[k * st_stride + e]\n"
+                : "  double* sop = S + " + std::to_string((NST + 1) * PSV) + ";\n")
+       << "  double* sguess = " << (SOPG ? "S + " + std::to_string((NST + 1) * PSV) : "sop + " + std::to_string(NSTATE * PSV)) << ";\n"
        "  for (int k = tid; k < " << n_gt << "; k += " << NW * 32 << ") gt[k] = GT_G[k];\n"
        "  if (tid < PS) S[" << zero_off << " + tid] = 0.0;\n"
        "  const bool evalid = ei < ni, rvalid = ri < ni" << (POW2 ? "" : " && j < " + std::to_string(TM_LPI)) << ", rin = ri < " << GI << ";\n"
        "  " << (XP ? "if (ei < PS) " : "") << "for (int k = warp; k < " << N << "; k += " << NW << ") X[k * PS + ei] = (evalid && !cold) ? gx[(size_t)k * stride + i0 + ei] : 0.0;\n"
        "  " << (XP ? "if (ei < PS) " : "") << "for (int k = warp; k < " << flat.n_state << "; k += " << NW << ") {\n"
        "    const size_t src = (size_t)k * st_stride + (size_t)i0 + (size_t)(evalid ? ei : 0);\n"
-       "    sop[k * PS + ei] = cold ? 0.0 : st_op[src];\n    sguess[k * PS + ei] = cold ? 0.0 : st_guess[src];\n  }\n"
+       << (SOPG ? "    if (cold && evalid) st_op[src] = 0.0;\n" : "    sop[k * PS + ei] = cold ? 0.0 : st_op[src];\n")
+       << "    sguess[k * PS + ei] = cold ? 0.0 : st_guess[src];\n  }\n"
        "  int r_stat = " << (tran ? "rvalid ? status[i0 + ri] : 0" : "0") << ";\n"
        "  int r_wk = 0;\n"
        "  int r_nsol = 0, r_nld = 0;\n"
@@ -336,7 +355,7 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
   }
   const char* ebi = WP ? "ri" : "ei";  // the instance a lane evaluates devices for
   o << "  JBase eb; eb.pval = pval; eb.pinst = (size_t)i0 + (size_t)" << ebi << "; eb.sop = sop + " << ebi << "; eb.sguess = sguess + " << ebi
-    << "; eb.X = X + " << ebi << "; eb.S = S + " << ebi << ";" << (XP ? " eb.j = j;" : "") << "\n"
+    << "; eb.X = X + " << ebi << "; eb.S = S + " << ebi << ";" << (XP ? " eb.j = j;" : "") << (SOPG ? " eb.sops = st_stride;" : "") << "\n"
        "  eb.mode = " << (tran ? "AN_TRAN" : "AN_OP") << "; eb.dt = dt; eb.gmin = gmin; eb.omega = 0.0; eb.time = " << (tran ? "dt" : "0.0") << ";\n";  // literal: the other mode's code is dropped
   if (prof) o << "  __shared__ long long prof_s[32];\n  if (tid < 32) prof_s[tid] = 0;\n  __syncthreads();\n  long long t_last = clock64();\n";
   o << "  const int n_points = " << (tran ? "T_points" : "2") << ";\n"
@@ -509,7 +528,7 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
   for (int q = 0; q < Q; q++) o << "        bad = bad || (v" << q << " && s_abs(c" << q << ") > iabstol);\n";
   o << "        const bool resok = (__ballot_sync(FULLM, bad) & imask) == 0;\n"
        "        if (r_act) {\n          r_nld += 1;\n          if (r_dxok && resok) {\n"
-       "            for (int k = j; k < " << flat.n_state << "; k += " << TM_LPI << ") sop[k * PS + ri] = sguess[k * PS + ri];\n"
+       "            for (int k = j; k < " << flat.n_state << "; k += " << TM_LPI << ") sop[" << (SOPG ? "(size_t)k * st_stride" : "k * PS") << " + ri] = sguess[k * PS + ri];\n"
        "            r_act = false;\n          }\n        }\n";
   o << "        PH(4)\n        if (__any_sync(FULLM, r_act)) {\n          bool sing = false;\n";
   if (fast_la) {
@@ -567,7 +586,7 @@ inline std::string team_source(const FlatCkt& flat, const Plan& P, const StageIn
        "    for (int k = warp; k < " << N << "; k += " << NW << ") gx[(size_t)k * stride + i0 + ei] = X[k * PS + ei];\n"
        "    for (int k = warp; k < " << flat.n_state << "; k += " << NW << ") {\n"
        "      const size_t dst = (size_t)k * st_stride + i0 + ei;\n"
-       "      st_op[dst] = sop[k * PS + ei];\n      st_guess[dst] = sguess[k * PS + ei];\n    }\n  }\n"
+       << (SOPG ? "" : "      st_op[dst] = sop[k * PS + ei];\n") << "      st_guess[dst] = sguess[k * PS + ei];\n    }\n  }\n"
        "  if (rvalid && j == 0) {\n"
        "    status[i0 + ri] = r_stat;\n"
        "    iters[i0 + ri] = (cold ? 0 : iters[i0 + ri]) + r_nsol;\n"

@@ -54,6 +54,9 @@ if which in ("all", "team"):
     wref = tran_ro(5, "direct")
     for kern in (None, "hybrid", "coop"):
         assert np.array_equal(tran_ro(5, kern), wref), kern
+    os.environ["S21_TEAM_SOPG"] = "1"  # team kernel with the committed device state left in its HBM column (host/jit_team.hpp)
+    assert np.array_equal(tran_ro(5, "jitteam"), wref)
+    os.environ.pop("S21_TEAM_SOPG")
     os.environ.pop("S21_KERNEL", None)
 
 if which in ("all", "bsim4"):

@@ -1231,6 +1231,30 @@ def test_c4x_41_stage_ring_with_internal_nodes_matches_oracle(s21, oracle):
     assert np.all(np.abs(it2 - o2["iters"]) <= 0.1 * o2["iters"]), (it2, o2["iters"])
 
 
+def test_team_kernel_committed_state_in_hbm(s21, monkeypatch):
+    """Team kernel, transients of batches with more CTAs than SMs (host/jit_team.hpp SOPG): the committed device state stays in
+    its HBM column (read through L2) instead of shared memory, which takes a CTA of the C1-circuit sweep from 139 KB to
+    114 KB — two CTAs per SM, one wave for 8192 instances instead of two. Same arithmetic: forced on a small ragged batch
+    (S21_TEAM_SOPG=1), waveforms, iteration counts and the committed state a second transient starts from must equal the
+    shared-memory version's bit for bit."""
+    ck = cc.cmos_ro3(cc.add_mos1_defaults)
+    sup = np.linspace(0.9, 1.1, 70)
+
+    def run():
+        b = s21.Batch(ck.to_s21().elaborate(ic={"1": 0.0}), 70)
+        b.override("V:v1:dc", sup)
+        t, w, st, it = b.tran(1e-11, 60e-11)
+        x2, st2, it2 = b.dcop()  # warm dcop from the transient's end state: reads x and the device state the kernel left in HBM
+        return w, st, it, x2, b.kernel_name()
+    monkeypatch.setenv("S21_KERNEL", "jitteam")
+    monkeypatch.setenv("S21_TEAM_SOPG", "0")
+    w0, st0, it0, x0, kn = run()
+    monkeypatch.setenv("S21_TEAM_SOPG", "1")
+    w1, st1, it1, x1, _ = run()
+    assert kn == "jit-team" and np.all(st0 == 0) and np.all(st1 == 0)
+    assert np.array_equal(w0, w1) and np.array_equal(it0, it1) and np.array_equal(x0, x1)
+
+
 def test_transient_hand_back_and_resume(s21, monkeypatch):
     """Re-pivoting inside a transient (cooperative kernel; SolveCtl::tran_stop, Batch::resolve_tran_stops): an instance whose
     frozen pivot order meets an exactly zero pivot — or a non-finite step — inside the time loop goes back to its last
