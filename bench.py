@@ -571,12 +571,16 @@ def measure_c1(args, D, s21, cc, torch, scaling, stream, B=C1_B, reps=3):
             "instances_per_gpu": n_loc, "_ms": ms, "_bi": bi, "_iters_local": out[1]}
 
 
-def c1_roofline(r, P):
+def c1_roofline(r, P, facts=None):
     ach = r["_bi"]["total"] * r["_iters_local"] / (r["_ms"] * 1e-3) / 1e9
+    peak = 148 * 4 * 1.965
+    wi = ((facts or {}).get("jit-team-tran") or {}).get("warp_insts_per_newton_iter")
+    issue = wi * r["_iters_local"] / (r["_ms"] * 1e-3) / 1e9 if wi else None
     return {"bound": "issue", "hbm_algorithmic": {"achieved": ach, "peak": P["hbm_gbs"], "unit": "GB/s", "frac": ach / P["hbm_gbs"],
                                                    "algorithmic_bytes_per_iteration": r["_bi"]},
-            "achieved": None, "peak": 148 * 4 * 1.965, "unit": "Gwarp-inst/s", "frac": None, "traffic": None,
-            "note": "same kernel family as C2 (state in shared memory and registers for the whole time loop): latency-bound, DRAM idle"}
+            "achieved": issue, "peak": peak, "unit": "Gwarp-inst/s", "frac": issue / peak if issue else None, "traffic": None,
+            "warp_insts_per_newton_iter": wi, "warp_insts_source": ((facts or {}).get("jit-team-tran") or {}).get("source"),
+            "note": "same kernel family as C2 (in-flight state in shared memory and registers for the whole time loop): latency-bound, DRAM idle"}
 
 
 # ---- C3: one large circuit (2000 five-stage Mos1 rings on one supply = 20 000 transistors)
@@ -799,7 +803,7 @@ def run_ours(args):
     sampler.join(timeout=2)
 
     if D.rank == 0:
-        rl = {"c1": lambda r: c1_roofline(r, P), "c4": lambda r: c4_roofline(r, P, facts), "c5": lambda r: c5_roofline(r, P, facts),
+        rl = {"c1": lambda r: c1_roofline(r, P, facts), "c4": lambda r: c4_roofline(r, P, facts), "c5": lambda r: c5_roofline(r, P, facts),
               "c3": lambda r: c3_roofline(r, P)}
         cfgs = {}
         for k, r in extras.items():
