@@ -612,7 +612,8 @@ def c3_roofline(r, P):
     return {"bound": "hbm", "achieved": ach, "peak": P["hbm_gbs"], "unit": "GB/s", "frac": ach / P["hbm_gbs"], "peak_source": P["hbm_source"],
             "traffic": None, "algorithmic_bytes_per_iteration": bi,
             "note": "grid-wide kernel, tolerance-mode level schedule (one grid barrier per dependency level, long sums spread over a warp or "
-                    "the grid): the L+U values (32 MB at full size) sit in L2, DRAM is idle; bounded by L2 latency per dependent operation and the barriers"}
+                    "the grid): the L+U values (32 MB at full size) and most of the plan tables sit in L2 (hit rate 51 %, DRAM 0.65 TB/s: profiles/r02AA_c3_full.txt); "
+                    "bounded by L2 / HBM latency per dependent operation and the ~40 grid barriers per Newton iteration"}
 
 
 # ----------------------------------------------------------------------------------------------------- CPU baselines
