@@ -155,7 +155,13 @@ int32_t s21_batch_packed_device(s21_batch* b, const double** dev_ptr, size_t* n_
 int32_t s21_batch_wave_device(const s21_batch* b, const double** dev_ptr, size_t* T, size_t* n_save, size_t* stride);
 /* Tran::solve (analysis.rs:526-573): OP at t=0, IC release, then fixed-step Backward Euler while t < tstop.
  * n_points_out = number of time points incl. t=0 (decided by the reference's floating-point `t += tstep`).
- * wave[B][T][n_save] and time[T] are host buffers sized by s21_tran_num_points; iters[B] counts all solves. */
+ * wave[B][T][n_save] and time[T] are host buffers sized by s21_tran_num_points; iters[B] counts all solves.
+ * The whole time loop runs on the device against the pivot order taken at its first iteration (the reference takes one per
+ * factorisation, sparse21/mod.rs:930-932). On the cooperative kernel (Bsim4 circuits, larger circuits) an instance whose
+ * frozen order fails inside the loop — an exactly zero pivot, a non-finite step — is not ended with Singular Matrix: it is
+ * handed back at its last accepted time point and continued with an order taken there (S21_TRAN_REPIVOT=0 turns that off);
+ * the other kernel families report Singular Matrix for such an instance. An instance that fails has NaN from that time
+ * point on in wave[] and its code in status[]. */
 int64_t s21_tran_num_points(double tstep, double tstop);
 int32_t s21_batch_tran(s21_batch* b, double tstep, double tstop, const int32_t* save_vars, size_t n_save, double* time,
                        double* wave, int32_t* status, int64_t* iters);
