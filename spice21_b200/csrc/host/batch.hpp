@@ -961,7 +961,9 @@ class Batch {
     // A long sweep is a huge batch of independent points: one thread per point (kernels/newton.cu::k_ac, HBM-resident
     // workspace, instance-fastest layout = coalesced) fills the GPU by itself and skips every barrier of the co-operative
     // kernels. Measured on C5 (N = 73, nnzLU = 365, 100 000 points): 3.8 ms against 29.8 ms (profiles/r01p_c5.txt).
-    const bool ac_direct = !ac_kernel_forced_ && F >= (size_t)16384;
+    // Where the switch sits (profiles/r02AD_c5_small.txt, C5 circuit): 2049 points 0.37 ms co-operative against 0.44 ms thread
+    // per point, 6251 points 1.01 against 0.43 ms, 12 500 points (an 8-GPU shard of the 100 000) 2.00 against 0.56 ms.
+    const bool ac_direct = !ac_kernel_forced_ && F >= (size_t)4096;
     if (use_coop_ && !ac_direct && use_hybrid(ac_plan_, 2, &hcfg)) {
       last_kernel_ = "hybrid";
       rc = launch_hybrid_ac(coop_dev(ac_plan_), ac_plan_.coop_plan(), ac_plan_.coop(), w, o, ctl, hcfg, stream_);

@@ -729,9 +729,10 @@ def test_ac_rc_opamp_full_sweep_properties(s21, oracle):
     assert oa.data.shape == (10000, c.n_vars)
     assert np.max(np.abs(x[::10] - oa.data) / np.maximum(1.0, np.abs(oa.data))) <= 1e-9
     # frequency points are independent: a shuffled batch gives the shuffled answer bit for bit
-    perm = np.random.default_rng(5).permutation(4096)
-    x2, st2, _ = b.ac(f[:4096][perm])
-    assert np.array_equal(x2, x[:4096][perm])
+    # (2048 points: below the switch to the thread-per-point kernel, so this also compares two kernel families)
+    perm = np.random.default_rng(5).permutation(2048)
+    x2, st2, _ = b.ac(f[:2048][perm])
+    assert b.kernel_name() != "direct" and np.array_equal(x2, x[:2048][perm])
 
 
 @pytest.mark.parametrize("B", [1, 31, 33, 257])
